@@ -1,0 +1,551 @@
+// oracle_pybind.cc -- Python face of the CPU oracle (TEST INFRASTRUCTURE ONLY).
+// Builds oracle/_monte_oracle*.so ; imported only by tests/, smoke() and
+// bench.py's cpu_baseline / --impl reference legs.
+#include <pybind11/functional.h>
+#include <pybind11/numpy.h>
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include <sstream>
+
+#include "monte_oracle.hh"
+
+namespace py = pybind11;
+using namespace monte_oracle;
+
+namespace {
+
+typedef py::array_t<int32_t, py::array::c_style | py::array::forcecast> i32arr;
+typedef py::array_t<double, py::array::c_style | py::array::forcecast> f64arr;
+
+std::vector<int> to_vec(i32arr const &a) {
+  auto r = a.unchecked<1>();
+  std::vector<int> v(r.shape(0));
+  for (py::ssize_t i = 0; i < r.shape(0); ++i) v[i] = r(i);
+  return v;
+}
+std::vector<double> to_dvec(f64arr const &a) {
+  auto r = a.unchecked<1>();
+  std::vector<double> v(r.shape(0));
+  for (py::ssize_t i = 0; i < r.shape(0); ++i) v[i] = r(i);
+  return v;
+}
+i32arr from_vec(std::vector<int> const &v) {
+  i32arr a(v.size());
+  auto w = a.mutable_unchecked<1>();
+  for (size_t i = 0; i < v.size(); ++i) w(i) = v[i];
+  return a;
+}
+f64arr from_dvec(std::vector<double> const &v) {
+  f64arr a(v.size());
+  auto w = a.mutable_unchecked<1>();
+  for (size_t i = 0; i < v.size(); ++i) w(i) = v[i];
+  return a;
+}
+
+IsingState make_state(std::vector<int> const &shape, std::vector<int> const &occ,
+                      double T, double mu) {
+  IsingConfiguration config(shape, 1, /*allow_3d=*/true);
+  config.set_occupation(occ);
+  ValueMap cond;
+  cond.scalar_values["temperature"] = T;
+  cond.vector_values["exchange_potential"] = std::vector<double>{mu};
+  return IsingState(config, cond);
+}
+
+struct Engine {
+  std::shared_ptr<std::mt19937_64> e = std::make_shared<std::mt19937_64>();
+};
+
+py::dict cc_results_to_dict(CompletionCheckResults const &r) {
+  py::dict d;
+  d["count"] = r.count.has_value() ? py::cast(r.count.value()) : py::none();
+  d["n_samples"] = r.n_samples;
+  d["has_all_minimums_met"] = r.has_all_minimums_met;
+  d["has_any_maximum_met"] = r.has_any_maximum_met;
+  d["n_samples_at_convergence_check"] =
+      r.n_samples_at_convergence_check.has_value()
+          ? py::cast(r.n_samples_at_convergence_check.value())
+          : py::none();
+  d["is_complete"] = r.is_complete;
+  py::dict eq;
+  eq["all_equilibrated"] = r.equilibration_check_results.all_equilibrated;
+  eq["N_samples_for_all_to_equilibrate"] =
+      r.equilibration_check_results.N_samples_for_all_to_equilibrate;
+  py::list eql;
+  for (auto const &kv : r.equilibration_check_results.individual_results) {
+    py::dict e;
+    e["sampler_name"] = kv.first.sampler_name;
+    e["component_index"] = kv.first.component_index;
+    e["is_equilibrated"] = kv.second.is_equilibrated;
+    e["N_samples_for_equilibration"] = kv.second.N_samples_for_equilibration;
+    eql.append(e);
+  }
+  eq["individual_results"] = eql;
+  d["equilibration_check_results"] = eq;
+  py::dict cv;
+  cv["all_converged"] = r.convergence_check_results.all_converged;
+  cv["N_samples_for_statistics"] =
+      r.convergence_check_results.N_samples_for_statistics;
+  py::list cvl;
+  for (auto const &kv : r.convergence_check_results.individual_results) {
+    py::dict e;
+    e["sampler_name"] = kv.first.sampler_name;
+    e["component_index"] = kv.first.component_index;
+    e["is_converged"] = kv.second.is_converged;
+    e["mean"] = kv.second.stats.mean;
+    e["calculated_precision"] = kv.second.stats.calculated_precision;
+    cvl.append(e);
+  }
+  cv["individual_results"] = cvl;
+  d["convergence_check_results"] = cv;
+  return d;
+}
+
+// Build CompletionCheckParams from a python dict with the reference's field
+// names (include/casm/monte/checks/CompletionCheck.hh:20-61).
+CompletionCheckParams params_from_dict(py::dict const &d) {
+  CompletionCheckParams p;
+  auto opt_count = [&](const char *k, std::optional<CountType> &dst) {
+    if (d.contains(k) && !d[k].is_none()) dst = d[k].cast<CountType>();
+  };
+  auto opt_time = [&](const char *k, std::optional<TimeType> &dst) {
+    if (d.contains(k) && !d[k].is_none()) dst = d[k].cast<double>();
+  };
+  opt_count("min_count", p.cutoff_params.min_count);
+  opt_count("max_count", p.cutoff_params.max_count);
+  opt_count("min_sample", p.cutoff_params.min_sample);
+  opt_count("max_sample", p.cutoff_params.max_sample);
+  opt_time("min_time", p.cutoff_params.min_time);
+  opt_time("max_time", p.cutoff_params.max_time);
+  opt_time("min_clocktime", p.cutoff_params.min_clocktime);
+  opt_time("max_clocktime", p.cutoff_params.max_clocktime);
+  if (d.contains("log_spacing")) p.log_spacing = d["log_spacing"].cast<bool>();
+  if (d.contains("check_begin")) p.check_begin = d["check_begin"].cast<long>();
+  if (d.contains("check_period")) p.check_period = d["check_period"].cast<long>();
+  if (d.contains("check_base")) p.check_base = d["check_base"].cast<double>();
+  if (d.contains("check_shift")) p.check_shift = d["check_shift"].cast<double>();
+  if (d.contains("check_period_max"))
+    p.check_period_max = d["check_period_max"].cast<long>();
+  if (d.contains("confidence"))
+    p.calc_statistics_f =
+        BasicStatisticsCalculator(d["confidence"].cast<double>());
+  if (d.contains("requested_precision")) {
+    // list of (sampler_name, component_index, abs or None, rel or None)
+    for (auto item : d["requested_precision"].cast<py::list>()) {
+      auto t = item.cast<py::tuple>();
+      SamplerComponent key(t[0].cast<std::string>(), t[1].cast<long>(),
+                           std::to_string(t[1].cast<long>()));
+      RequestedPrecision rp;
+      if (!t[2].is_none()) {
+        rp.abs_convergence_is_required = true;
+        rp.abs_precision = t[2].cast<double>();
+      }
+      if (t.size() > 3 && !t[3].is_none()) {
+        rp.rel_convergence_is_required = true;
+        rp.rel_precision = t[3].cast<double>();
+      }
+      p.requested_precision.emplace(key, rp);
+    }
+  }
+  return p;
+}
+
+py::dict data_to_dict(BasicOccupationMetropolisData const &data,
+                      IsingState const &state) {
+  py::dict out;
+  out["occupation"] = from_vec(state.configuration.occupation());
+  out["n_pass"] = data.n_pass;
+  out["n_accept"] = data.n_accept;
+  out["n_reject"] = data.n_reject;
+  py::dict s;
+  for (auto const &kv : data.samplers) s[kv.first.c_str()] =
+      from_dvec(kv.second->component(0));
+  out["samplers"] = s;
+  out["completion_check_results"] =
+      cc_results_to_dict(data.completion_check.results());
+  out["n_checks"] = data.completion_check.n_checks();
+  return out;
+}
+
+// Full reference-order SGC run (serial Metropolis, mt19937_64).
+py::dict sgc_run(std::vector<int> shape, i32arr occ_in, double J, double T,
+                 double mu, bool use_nlist, Engine &engine, py::dict cc_params,
+                 int sample_period) {
+  IsingState state = make_state(shape, to_vec(occ_in), T, mu);
+  auto system = std::make_shared<IsingSystem>(
+      IsingFormationEnergy(J, 1, use_nlist), IsingParamComposition());
+  auto mc = std::make_shared<SemiGrandCanonicalCalculator>(system);
+  StateSamplingFunctionMap fns;
+  for (auto const &f : {make_parametric_composition_f(mc),
+                        make_formation_energy_f(mc), make_potential_energy_f(mc)})
+    fns.emplace(f.name, f);
+  CompletionCheckParams p = params_from_dict(cc_params);
+  SemiGrandCanonicalCalculator::event_generator_type gen;
+  std::optional<MethodLog> log = MethodLog();
+  auto no_status = [](BasicOccupationMetropolisData const &, MethodLog &) {};
+  {
+    py::gil_scoped_release release;
+    mc->run(state, fns, p, gen, sample_period, log, engine.e, no_status);
+  }
+  return data_to_dict(*mc->data, state);
+}
+
+py::dict checkerboard_run(std::vector<int> shape, i32arr occ_in, double J,
+                          double T, double mu, uint64_t seed, uint32_t chain,
+                          uint64_t pass0, long n_passes, long sample_period) {
+  std::vector<int> occ = to_vec(occ_in);
+  const int dim = static_cast<int>(shape.size());
+  for (int s : shape)
+    if (s % 2) throw std::runtime_error("checkerboard needs even extents");
+  AcceptTable tab = make_accept_table(dim, J, T, mu);
+  CheckerboardResult res;
+  std::vector<long long> Ss, Bs;
+  long long N = 1;
+  for (int s : shape) N *= s;
+  {
+    py::gil_scoped_release release;
+    for (long t = 0; t < n_passes; ++t) {
+      checkerboard_pass(occ, shape, tab, seed, chain, pass0 + t, res);
+      if (sample_period > 0 && ((t + 1) % sample_period) == 0) {
+        long long S, B;
+        integer_observables(occ, shape, S, B);
+        Ss.push_back(S);
+        Bs.push_back(B);
+      }
+    }
+  }
+  py::dict out;
+  out["occupation"] = from_vec(occ);
+  out["n_accept"] = res.n_accept;
+  out["n_reject"] = n_passes * N - res.n_accept;
+  py::array_t<long long> aS(Ss.size()), aB(Bs.size());
+  f64arr x(Ss.size()), ef(Ss.size()), ep(Ss.size());
+  for (size_t i = 0; i < Ss.size(); ++i) {
+    aS.mutable_at(i) = Ss[i];
+    aB.mutable_at(i) = Bs[i];
+    IntensiveObservables o = observables_from_sums(Ss[i], Bs[i], N, J, mu);
+    x.mutable_at(i) = o.param_composition;
+    ef.mutable_at(i) = o.formation_energy;
+    ep.mutable_at(i) = o.potential_energy;
+  }
+  out["S"] = aS;
+  out["B"] = aB;
+  out["param_composition"] = x;
+  out["formation_energy"] = ef;
+  out["potential_energy"] = ep;
+  return out;
+}
+
+}  // namespace
+
+PYBIND11_MODULE(_monte_oracle, m) {
+  m.doc() = "CPU oracle for the Ising SGC Metropolis path (test infrastructure)";
+  m.attr("KB") = KB;
+
+  py::class_<Engine>(m, "RandomNumberEngine")
+      .def(py::init<>())
+      .def("seed", [](Engine &e, uint64_t s) { e.e->seed(s); })
+      .def("dump",
+           [](Engine const &e) {
+             std::stringstream ss;
+             ss << *e.e;
+             return ss.str();
+           })
+      .def("load", [](Engine &e, std::string const &s) {
+        std::stringstream ss(s);
+        ss >> *e.e;
+      });
+
+  m.def("random_int", [](Engine &e, uint64_t maximum_value) {
+    RandomNumberGenerator<> g(e.e);
+    return g.random_int<uint64_t>(maximum_value);
+  });
+  m.def("random_int_long", [](Engine &e, long maximum_value) {
+    RandomNumberGenerator<> g(e.e);
+    return g.random_int<long>(maximum_value);
+  });
+  m.def("random_real", [](Engine &e, double maximum_value) {
+    RandomNumberGenerator<> g(e.e);
+    return g.random_real<double>(maximum_value);
+  });
+
+  m.def("within", [](std::vector<int> shape, long index, int dim) {
+    IsingConfiguration c(shape, 1, true);
+    return c.within(index, dim);
+  });
+  m.def("from_linear_site_index", [](std::vector<int> shape, long l) {
+    IsingConfiguration c(shape, 1, true);
+    return c.from_linear_site_index(l);
+  });
+  m.def("to_linear_site_index", [](std::vector<int> shape, std::vector<int> mi) {
+    IsingConfiguration c(shape, 1, true);
+    return c.to_linear_site_index(mi);
+  });
+  m.def("ising_configuration_2d_only", [](std::vector<int> shape) {
+    IsingConfiguration c(shape, 1, false);  // throws unless 2-d
+    return c.n_sites;
+  });
+
+  m.def("formation_energy",
+        [](std::vector<int> shape, i32arr occ, double J, bool use_nlist) {
+          IsingState st = make_state(shape, to_vec(occ), 1.0, 0.0);
+          IsingFormationEnergy f(J, 1, use_nlist);
+          f.set_state(&st);
+          return py::make_tuple(f.per_supercell(), f.per_unitcell());
+        });
+  m.def("formation_energy_delta",
+        [](std::vector<int> shape, i32arr occ, double J, bool use_nlist,
+           std::vector<long> l, std::vector<int> new_occ) {
+          IsingState st = make_state(shape, to_vec(occ), 1.0, 0.0);
+          IsingFormationEnergy f(J, 1, use_nlist);
+          f.set_state(&st);
+          return f.occ_delta_per_supercell(l, new_occ);
+        });
+  m.def("param_composition", [](std::vector<int> shape, i32arr occ) {
+    IsingState st = make_state(shape, to_vec(occ), 1.0, 0.0);
+    IsingParamComposition c;
+    c.set_state(&st);
+    return py::make_tuple(c.per_supercell()[0], c.per_unitcell()[0]);
+  });
+  m.def("param_composition_delta",
+        [](std::vector<int> shape, i32arr occ, std::vector<long> l,
+           std::vector<int> new_occ) {
+          IsingState st = make_state(shape, to_vec(occ), 1.0, 0.0);
+          IsingParamComposition c;
+          c.set_state(&st);
+          return c.occ_delta_per_supercell(l, new_occ)[0];
+        });
+  m.def("potential", [](std::vector<int> shape, i32arr occ, double J, double T,
+                        double mu, bool use_nlist) {
+    IsingState st = make_state(shape, to_vec(occ), T, mu);
+    auto sys = std::make_shared<IsingSystem>(
+        IsingFormationEnergy(J, 1, use_nlist), IsingParamComposition());
+    SemiGrandCanonicalPotential pot(sys);
+    pot.set_state(&st, std::make_shared<SemiGrandCanonicalConditions>(
+                           SemiGrandCanonicalConditions::from_values(
+                               st.conditions)));
+    return py::make_tuple(pot.per_supercell(), pot.per_unitcell());
+  });
+  m.def("potential_delta",
+        [](std::vector<int> shape, i32arr occ, double J, double T, double mu,
+           bool use_nlist, std::vector<long> l, std::vector<int> new_occ) {
+          IsingState st = make_state(shape, to_vec(occ), T, mu);
+          auto sys = std::make_shared<IsingSystem>(
+              IsingFormationEnergy(J, 1, use_nlist), IsingParamComposition());
+          SemiGrandCanonicalPotential pot(sys);
+          pot.set_state(&st, std::make_shared<SemiGrandCanonicalConditions>(
+                                 SemiGrandCanonicalConditions::from_values(
+                                     st.conditions)));
+          return pot.occ_delta_per_supercell(l, new_occ);
+        });
+  // dE of the single-site flip at every site, through the reference call chain
+  m.def("potential_delta_all_sites",
+        [](std::vector<int> shape, i32arr occ, double J, double T, double mu,
+           bool use_nlist) {
+          IsingState st = make_state(shape, to_vec(occ), T, mu);
+          auto sys = std::make_shared<IsingSystem>(
+              IsingFormationEnergy(J, 1, use_nlist), IsingParamComposition());
+          SemiGrandCanonicalPotential pot(sys);
+          pot.set_state(&st, std::make_shared<SemiGrandCanonicalConditions>(
+                                 SemiGrandCanonicalConditions::from_values(
+                                     st.conditions)));
+          long N = st.configuration.n_sites;
+          f64arr out(N);
+          auto w = out.mutable_unchecked<1>();
+          std::vector<long> l(1);
+          std::vector<int> no(1);
+          for (long i = 0; i < N; ++i) {
+            l[0] = i;
+            no[0] = -st.configuration.occ(i);
+            w(i) = pot.occ_delta_per_supercell(l, no);
+          }
+          return out;
+        });
+  // acceptance decision at every site given one uniform per site
+  // (include/casm/monte/methods/metropolis.hh:26-35 with the draw supplied)
+  m.def("accept_all_sites", [](f64arr dE, f64arr u, double T) {
+    auto d = dE.unchecked<1>();
+    auto uu = u.unchecked<1>();
+    double beta = 1.0 / (KB * T);
+    py::array_t<uint8_t> out(d.shape(0));
+    auto w = out.mutable_unchecked<1>();
+    for (py::ssize_t i = 0; i < d.shape(0); ++i) {
+      bool acc = d(i) < 0.0;
+      if (!acc) acc = uu(i) < std::exp(-d(i) * beta);
+      w(i) = acc ? 1 : 0;
+    }
+    return out;
+  });
+
+  m.def("accept_table", [](int dim, double J, double T, double mu) {
+    AcceptTable t = make_accept_table(dim, J, T, mu);
+    const int z = 2 * dim;
+    f64arr dE({2, z + 1}), prob({2, z + 1});
+    py::array_t<uint32_t> thr({2, z + 1});
+    for (int s = 0; s < 2; ++s)
+      for (int n = 0; n <= z; ++n) {
+        dE.mutable_at(s, n) = t.dE[s][n];
+        prob.mutable_at(s, n) = t.prob[s][n];
+        thr.mutable_at(s, n) = t.thr_m1[s][n];
+      }
+    py::dict d;
+    d["dE"] = dE;
+    d["prob"] = prob;
+    d["thr_m1"] = thr;
+    d["beta"] = t.beta;
+    return d;
+  });
+
+  m.def("integer_observables", [](std::vector<int> shape, i32arr occ) {
+    long long S, B;
+    integer_observables(to_vec(occ), shape, S, B);
+    return py::make_tuple(S, B);
+  });
+  m.def("observables_from_sums",
+        [](long long S, long long B, long long N, double J, double mu) {
+          IntensiveObservables o = observables_from_sums(S, B, N, J, mu);
+          return py::make_tuple(o.param_composition, o.formation_energy,
+                                o.potential_energy);
+        });
+  m.def("heat_capacity", [](f64arr e, long long N, double T) {
+    return heat_capacity(to_dvec(e), N, T);
+  });
+  m.def("susceptibility", [](f64arr x, long long N, double T) {
+    return susceptibility(to_dvec(x), N, T);
+  });
+
+  m.def("sgc_run", &sgc_run, py::arg("shape"), py::arg("occupation"),
+        py::arg("J"), py::arg("temperature"), py::arg("mu"),
+        py::arg("use_nlist"), py::arg("engine"),
+        py::arg("completion_check_params"), py::arg("sample_period") = 1);
+  m.def("checkerboard_run", &checkerboard_run, py::arg("shape"),
+        py::arg("occupation"), py::arg("J"), py::arg("temperature"),
+        py::arg("mu"), py::arg("seed"), py::arg("chain") = 0,
+        py::arg("pass0") = 0, py::arg("n_passes") = 1,
+        py::arg("sample_period") = 1);
+
+  m.def("philox4x32_10", [](std::array<uint32_t, 4> c, std::array<uint32_t, 2> k) {
+    return Philox4x32::generate(c, k, 10);
+  });
+
+  // statistics
+  m.def("variance", [](f64arr x, double mean) {
+    auto v = to_dvec(x);
+    return variance(v.data(), v.size(), mean);
+  });
+  m.def("covariance_lag", [](f64arr x, long k, double mean) {
+    auto v = to_dvec(x);
+    long n = static_cast<long>(v.size()) - k;
+    return covariance(v.data(), v.data() + k, n, mean);
+  });
+  m.def("approx_erf_inv", &approx_erf_inv);
+  m.def("autocorrelation_factor", [](f64arr x, double increment) {
+    auto v = to_dvec(x);
+    Index k = 0;
+    double f = autocorrelation_factor(v.data(), v.size(), increment, &k);
+    return py::make_tuple(f, k);
+  }, py::arg("observations"), py::arg("increment") = 1.0);
+  m.def("basic_statistics",
+        [](f64arr x, f64arr w, double confidence, long method, long n_resamples) {
+          BasicStatisticsCalculator c(confidence, method, n_resamples);
+          BasicStatistics s = c(to_dvec(x), to_dvec(w));
+          return py::make_tuple(s.mean, s.calculated_precision);
+        },
+        py::arg("observations"), py::arg("sample_weight") = f64arr(0),
+        py::arg("confidence") = 0.95, py::arg("method") = 1,
+        py::arg("n_resamples") = 10000);
+  m.def("default_equilibration_check",
+        [](f64arr x, f64arr w, py::object abs, py::object rel) {
+          RequestedPrecision rp;
+          if (!abs.is_none()) {
+            rp.abs_convergence_is_required = true;
+            rp.abs_precision = abs.cast<double>();
+          }
+          if (!rel.is_none()) {
+            rp.rel_convergence_is_required = true;
+            rp.rel_precision = rel.cast<double>();
+          }
+          auto r = default_equilibration_check(to_dvec(x), to_dvec(w), rp);
+          return py::make_tuple(r.is_equilibrated,
+                                r.N_samples_for_equilibration);
+        },
+        py::arg("observations"), py::arg("sample_weight") = f64arr(0),
+        py::arg("abs") = py::none(), py::arg("rel") = py::none());
+
+  // Sampler + CompletionCheck objects, for tests that mirror
+  // python/tests/sampling/test_Sampler.py and test_CompletionCheck.py
+  py::class_<Sampler, std::shared_ptr<Sampler>>(m, "Sampler")
+      .def(py::init([](std::vector<Index> shape,
+                       std::optional<std::vector<std::string>> names,
+                       CountType inc) {
+             if (names.has_value())
+               return std::make_shared<Sampler>(shape, names.value(), inc);
+             return std::make_shared<Sampler>(shape, inc);
+           }),
+           py::arg("shape"), py::arg("component_names") = py::none(),
+           py::arg("capacity_increment") = 1000)
+      .def("append",
+           [](Sampler &s, std::vector<double> v) { s.push_back(v); })
+      .def("clear", &Sampler::clear)
+      .def("set_sample_capacity", &Sampler::set_sample_capacity)
+      .def("set_capacity_increment", &Sampler::set_capacity_increment)
+      .def("component_names", &Sampler::component_names)
+      .def("shape", &Sampler::shape)
+      .def("n_components", &Sampler::n_components)
+      .def("n_samples", &Sampler::n_samples)
+      .def("sample_capacity", &Sampler::sample_capacity)
+      .def("component",
+           [](Sampler const &s, Index c) { return from_dvec(s.component(c)); })
+      .def("sample",
+           [](Sampler const &s, CountType r) { return from_dvec(s.sample(r)); })
+      .def("values", [](Sampler const &s) {
+        f64arr a({static_cast<py::ssize_t>(s.n_samples()),
+                  static_cast<py::ssize_t>(s.n_components())});
+        for (Index c = 0; c < s.n_components(); ++c)
+          for (CountType r = 0; r < s.n_samples(); ++r)
+            a.mutable_at(r, c) = s.component_data(c)[r];
+        return a;
+      });
+  m.def("default_component_names", &default_component_names);
+  m.def("colmajor_component_names", &colmajor_component_names);
+
+  struct CC {
+    CompletionCheck cc;
+    Clock clock;
+    explicit CC(py::dict d) : cc(params_from_dict(d)) {}
+  };
+  py::class_<CC>(m, "CompletionCheck")
+      .def(py::init<py::dict>())
+      .def("reset", [](CC &c) { c.cc.reset(); })
+      .def("count_check",
+           [](CC &c, std::map<std::string, std::shared_ptr<Sampler>> samplers,
+              std::shared_ptr<Sampler> weight, CountType count) {
+             return c.cc.is_complete(samplers, *weight, count, c.clock);
+           },
+           py::arg("samplers"), py::arg("sample_weight"), py::arg("count"))
+      .def("check",
+           [](CC &c, std::map<std::string, std::shared_ptr<Sampler>> samplers,
+              std::shared_ptr<Sampler> weight) {
+             return c.cc.is_complete(samplers, *weight, c.clock);
+           })
+      .def("n_checks", [](CC const &c) { return c.cc.n_checks(); })
+      .def("results", [](CC const &c) { return cc_results_to_dict(c.cc.results()); });
+
+  // Conversions (diagonal transformation matrix)
+  m.def("conv_l_size", [](std::array<long, 3> n, long nb) {
+    DiagonalConversions c{{n[0], n[1], n[2]}, nb};
+    return c.l_size();
+  });
+  m.def("conv_l_to_bijk", [](std::array<long, 3> n, long nb, long l) {
+    DiagonalConversions c{{n[0], n[1], n[2]}, nb};
+    long ijk[3];
+    c.l_to_ijk(l, ijk);
+    return py::make_tuple(c.l_to_b(l), ijk[0], ijk[1], ijk[2]);
+  });
+  m.def("conv_bijk_to_l",
+        [](std::array<long, 3> n, long nb, long b, long i, long j, long k) {
+          DiagonalConversions c{{n[0], n[1], n[2]}, nb};
+          return c.bijk_to_l(b, i, j, k);
+        });
+}
