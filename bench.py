@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py -- Metropolis flip attempts/s of the Ising SGC hot path on B200.
+
+Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W`
+prints ONE JSON line.  A "step" is PASSES_PER_STEP checkerboard passes (one
+pass = one attempted flip per site, on-device sampling of energy and
+composition every pass) over one synthetic lattice.
+
+Workload (BASELINE.json configs[1]): 2-d square 4096x4096 SGC Ising, J = 0.1 eV,
+mu = 0, headline at T = 2633 K (T_c).  With N > 1 GPUs the temperature sweep
+of that config is sharded: rank r runs its own 4096x4096 lattice at T_sweep[r]
+with no communication (weak scaling).
+
+`--impl reference` times the CPU restatement of the reference loop
+(oracle/oracle_bench, one independent chain per host core) on a bounded sample
+of the same workload; it is the reference arm, not the product.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N0 = N1 = 4096
+J = 0.1
+MU = 0.0
+T_HEADLINE = 2633.0
+T_SWEEP = [2633.0, 1800.0, 2200.0, 2500.0, 2600.0, 2660.0, 2800.0, 3200.0]
+PASSES_PER_STEP = 200
+ALGO_BYTES_PER_ATTEMPT = 3.0  # int8, two colour planes: read own + read other + write own
+METRIC = "metropolis_flip_attempts_per_s"
+UNIT = "attempts/s"
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(
+                    ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                    capture_output=True, text=True, timeout=5,
+                ).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except Exception:
+                continue
+            for nm, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {
+            "sm_mhz": statistics.median(sm) if sm else None,
+            "sm_max_mhz": max(mx) if mx else None,
+            "reasons": sorted(reasons),
+            "samples": len(sm),
+        }
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_cpu_reference(n0, n1, T, mu, n_passes, sample_period, use_nlist, threads, seed=12345):
+    exe = os.path.join(ROOT, "oracle", "oracle_bench")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-j2"], stdout=subprocess.DEVNULL)
+    out = subprocess.run(
+        [exe, str(n0), str(n1), str(T), str(mu), str(n_passes), str(sample_period), str(int(use_nlist)), str(threads), str(seed)],
+        capture_output=True, text=True, check=True,
+    ).stdout
+    return json.loads(out.strip().splitlines()[-1])
+
+
+def reference_arm(args):
+    """CPU implementation of the path on the host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = host_cores()
+    total_steps = args.steps + args.warmup
+    if total_steps <= 12:
+        n0, n1, passes = N0, N1, 1
+        sample = f"{cores} independent chains (one per core) x 1 pass of the full {N0}x{N1} lattice per step, use_nlist=false, sampling every pass"
+    else:
+        n0, n1, passes = 1024, 1024, 2
+        sample = f"{cores} independent chains x 2 passes of a 1024x1024 proxy lattice per step (full size would exceed the time budget), use_nlist=false, sampling every pass"
+    for _ in range(args.warmup):
+        run_cpu_reference(n0, n1, T_HEADLINE, MU, passes, 1, False, cores)
+    t_total, attempts = 0.0, 0.0
+    for i in range(args.steps):
+        r = run_cpu_reference(n0, n1, T_HEADLINE, MU, passes, 1, False, cores, seed=1000 + i)
+        t_total += r["wall_s"]
+        attempts += float(n0) * n1 * passes * cores
+    value = attempts / t_total
+    line = {
+        "impl": "reference",
+        "metric": METRIC,
+        "value": value,
+        "unit": UNIT,
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": 1e3 * t_total / max(args.steps, 1),
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "int32 occupation / f64 energies (CPU)",
+        "data": "synthetic",
+        "config": workload_config(1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus):
+    return {
+        "workload": f"2D square Ising SGC checkerboard sweeps, {N0}x{N1} supercell per GPU, J=0.1 eV, mu=0, "
+        + (f"T=2633 K (T_c)" if n_gpus == 1 else f"temperature sweep through T_c sharded over {n_gpus} GPUs (rank r at T_sweep[r]), no communication"),
+        "lattice": [N0, N1],
+        "passes_per_step": PASSES_PER_STEP,
+        "sample_period": 1,
+        "initial_state": "i.i.d. +1/-1 (Philox, seed 12345)",
+        "philox_seed": "0xC0FFEE + rank",
+        "l2": "L2 flushed (256 MiB write) between timed steps; the 16 MiB int8 lattice is L2-resident within a step by design",
+        "timing": "CUDA events on the launching stream per step, summed; max over ranks",
+    }
+
+
+def ours(args):
+    import numpy as np
+    import torch
+
+    from casmcode_monte_b200 import MODE_CHECKERBOARD, IsingLatticeGPU
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    T = T_HEADLINE if world == 1 else T_SWEEP[rank % len(T_SWEEP)]
+    stream = torch.cuda.Stream()
+    lat = IsingLatticeGPU([N0, N1], device=local_rank, J=J)
+    lat.set_stream(stream.cuda_stream)
+    lat.set_conditions(T, MU)
+    lat.seed_philox(0xC0FFEE + rank)
+    lat.randomize(12345 + rank, 0.5)
+    lat.sync()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    n_sites = N0 * N1
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step(timed):
+        with torch.cuda.stream(stream):
+            flush.fill_(1)  # L2 flush, outside the events
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            lat.run_passes(PASSES_PER_STEP, MODE_CHECKERBOARD, 1)
+            e1.record(stream)
+        return (e0, e1)
+
+    for _ in range(args.warmup):
+        one_step(False)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = lat.launch_count
+    lat.clear_samples()
+    barrier()
+    t_wall0 = time.perf_counter()
+    evs = [one_step(True) for _ in range(args.steps)]
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    launches = lat.launch_count - launches0
+    ms_steps = [a.elapsed_time(b) for a, b in evs]
+    total_ms = sum(ms_steps)
+    if dist is not None:
+        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+        lt = torch.tensor([launches], device="cuda", dtype=torch.int64)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt.item())
+    attempts = float(n_sites) * PASSES_PER_STEP * args.steps * world
+    value = attempts / (total_ms * 1e-3)
+    # sanity: the run really sampled and moved
+    S, B = lat.samples_sb()
+    assert len(S) == PASSES_PER_STEP * args.steps
+    x_mean = float((n_sites + S.astype(np.float64)).mean() / 2.0 / n_sites)
+
+    # ---- end to end through the C ABI with HOST buffers (H2D + D2H in the timed region)
+    host_occ = torch.empty(n_sites, dtype=torch.int32).pin_memory()
+    host_occ.numpy()[:] = lat.download()
+    host_out = torch.empty(n_sites, dtype=torch.int32).pin_memory()
+    e2e_steps = max(1, min(args.steps, 5))
+
+    def e2e_step():
+        lat.upload(host_occ.numpy())  # H2D of the int32 occupation + colour-plane split
+        lat.clear_samples()
+        lat.run_passes(PASSES_PER_STEP, MODE_CHECKERBOARD, 1)
+        lat.download(out=host_out.numpy())  # D2H of the final occupation
+        s, b = lat.samples_sb()  # D2H of the sampled (S, B) series
+        return s, b
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = float(n_sites) * PASSES_PER_STEP * e2e_steps * world / e2e_s
+
+    peak, peak_src = measured_peak()
+    n_half_sweeps = 2 * PASSES_PER_STEP * args.steps
+    avg_launch_s = (sum(ms_steps) * 1e-3) / n_half_sweeps
+    bytes_per_launch = ALGO_BYTES_PER_ATTEMPT * n_sites / 2
+    achieved = bytes_per_launch / avg_launch_s / 1e9
+
+    line = {
+        "metric": METRIC,
+        "value": value,
+        "unit": UNIT,
+        "n_gpus": world,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "u8 occupation, u32 Philox/threshold compare, f64 tables",
+        "data": "synthetic",
+        "config": workload_config(world),
+        "clocks": clocks,
+        "e2e": {
+            "value": e2e_value,
+            "unit": UNIT,
+            "h2d_bytes_per_step": 4 * n_sites,
+            "d2h_bytes_per_step": 4 * n_sites + 16 * PASSES_PER_STEP,
+            "steps": e2e_steps,
+        },
+        "gpu_launches": launches,
+        "roofline": {
+            "bound": "hbm",
+            "achieved": achieved,
+            "peak": peak,
+            "peak_source": peak_src,
+            "unit": "GB/s",
+            "frac": achieved / peak,
+            "traffic": None,
+            "kernel": "k_halfsweep_" + lat.kernel_variant,
+            "algorithmic_bytes_per_launch": bytes_per_launch,
+            "avg_launch_us": avg_launch_s * 1e6,
+            "note": "3 B per attempted flip (int8, two colour planes); lattice is L2-resident so DRAM traffic << algorithmic bytes; kernel is issue-bound (Philox)",
+        },
+        "wall_s_timed_region": t_wall,
+        "check": {"mean_param_composition": x_mean, "acceptance_rate": lat.counters()[1] / max(1, lat.counters()[1] + lat.counters()[2])},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = host_cores()
+        r = run_cpu_reference(N0, N1, T_HEADLINE, MU, 2, 1, False, cores)
+        line["cpu_baseline"] = {
+            "value": r["attempts_per_s"],
+            "unit": UNIT,
+            "cores": cores,
+            "kind": "port",
+            "sample": f"{cores} independent chains (one per core) x 2 passes of the {N0}x{N1} lattice, use_nlist=false, sampling every pass ({r['wall_s']:.1f} s wall)",
+        }
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        ours(args)
+
+
+if __name__ == "__main__":
+    main()

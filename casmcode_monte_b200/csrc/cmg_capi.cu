@@ -1,0 +1,1484 @@
+// cmg_capi.cu -- host side of the C ABI declared in include/casm_monte_gpu.h.
+// Owns device memory, builds the per-chain dE / acceptance tables with the
+// reference's expression order, and launches the sm_100a kernels of
+// cmg_device.cuh.  No CPU fallback: every entry point needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/casm_monte_gpu.h"
+#include "cmg_device.cuh"
+
+using namespace cmg;
+
+// ---------------------------------------------------------------------------
+struct GraphKey {
+  int variant;
+  long long passes;
+  long long sample_period;
+  bool operator<(GraphKey const &o) const {
+    if (variant != o.variant) return variant < o.variant;
+    if (passes != o.passes) return passes < o.passes;
+    return sample_period < o.sample_period;
+  }
+};
+
+struct RunState {
+  unsigned long long pass;
+  long long n_samples;
+};
+
+enum Variant { V_AUTO = 0, V_GENERIC = 1, V_BULK2D = 2, V_BULK3D = 3, V_SMEM = 4 };
+
+struct cmg_context {
+  int device = 0;
+  cudaStream_t stream = 0;
+  int dim = 2;
+  long long shape[3] = {1, 1, 1};
+  long long n_sites = 0;
+  int n_chains = 1;
+  bool planar = false;  // all extents even -> colour planes
+  // slab decomposition
+  bool slab = false;
+  long long col_begin = 0;
+  long long global_shape[3] = {1, 1, 1};
+  uint8_t *d_halo[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [colour][side]
+  uint8_t *push[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};    // [colour][side]
+  std::vector<void *> ipc_opened;
+
+  uint8_t *d_planes = nullptr;
+  long long plane_stride = 0, chain_stride = 0;
+  uint8_t *d_nat = nullptr;  // [n_chains][n_sites]
+  bool nat_is_current = false;     // natural copy mirrors the planes
+  int32_t *d_stage = nullptr;      // [n_sites] int32 staging
+  int *d_flag = nullptr;
+
+  ChainTables *d_tabs = nullptr;
+  std::vector<ChainTables> h_tabs;
+  double J = 1.0;
+  int lattice_type = 1;
+  bool model_set = false;
+
+  unsigned long long philox_seed = 0;
+  unsigned long long h_pass = 0;  // global pass index (Philox counter)
+  RunState *d_run = nullptr;
+  long long n_pass = 0;  // passes since reset_counters
+  unsigned long long *d_n_accept = nullptr;
+
+  MT64State *d_engines = nullptr;
+  std::vector<char> engine_seeded;
+  long long *d_cur_sb = nullptr;  // [n_chains][2]
+  long long *d_scratch_sb = nullptr;  // [2]
+
+  // sample series, sample-major: slot s at d_series + s*n_chains*2
+  long long *d_series = nullptr;
+  long long capacity = 0;
+  long long n_samples = 0;
+  double *d_dbl = nullptr;  // [n_chains][3][dbl_capacity]
+  long long dbl_capacity = 0;
+  long long dbl_valid = 0;
+
+  int forced_variant = V_AUTO;
+  int js = 0;  // 0 = auto
+  long long launches = 0;
+  std::string last_error;
+  std::string variant_name = "auto";
+};
+
+static thread_local std::string g_last_error;
+
+static int fail(cmg_context *ctx, int code, const std::string &msg) {
+  if (ctx) ctx->last_error = msg;
+  g_last_error = msg;
+  return code;
+}
+
+#define CU(ctx, call)                                                          \
+  do {                                                                         \
+    cudaError_t e__ = (call);                                                  \
+    if (e__ != cudaSuccess) {                                                  \
+      char buf__[512];                                                         \
+      snprintf(buf__, sizeof buf__, "%s failed: %s (%s:%d)", #call,            \
+               cudaGetErrorString(e__), __FILE__, __LINE__);                   \
+      return fail(ctx, (e__ == cudaErrorMemoryAllocation) ? CMG_ENOMEM : CMG_ECUDA, \
+                  buf__);                                                      \
+    }                                                                          \
+  } while (0)
+
+#define NEED(ctx)                                                 \
+  do {                                                            \
+    if (!(ctx)) return fail(nullptr, CMG_EINVAL, "null context"); \
+    cudaSetDevice((ctx)->device);                                 \
+  } while (0)
+
+static inline unsigned int nblocks(long long n, int bs) {
+  return (unsigned int)((n + bs - 1) / bs);
+}
+
+// ---------------------------------------------------------------------------
+// Tables.  Expression order follows the reference exactly:
+//   dE_f = (-J * (new_occ - s)) * sum_nbr      model.hh:312-314 (left to right)
+//   Ndx  = 0.0 + (new_occ - s) / 2.0           model.hh:430-433
+//   dE   = dE_f - mu * Ndx                     basic_semigrand_canonical.hh:185-191
+//   prob = exp(-dE * beta), beta = 1/(KB*T)    metropolis.hh:33,
+//                                              basic_occupation_metropolis.hh:361
+// This translation unit is compiled with -fmad=false for device code and the
+// host compiler's default (no contraction across statements on x86-64 without
+// -march flags), and the statements are kept separate.
+// ---------------------------------------------------------------------------
+static void build_tables(ChainTables &t, int dim, double J, double T, double mu) {
+  memset(&t, 0, sizeof t);
+  t.J = J;
+  t.mu = mu;
+  t.temperature = T;
+  volatile double kt = CMG_KB * T;
+  t.beta = 1.0 / kt;
+  const int z = 2 * dim;
+  for (int b = 0; b < 2; ++b) {
+    const int s = b ? 1 : -1;
+    const int new_occ = -s;
+    for (int nu = 0; nu <= z; ++nu) {
+      const int nb_sum = 2 * nu - z;
+      volatile double a = -J * (new_occ - s);
+      volatile double dE_f = a * nb_sum;
+      volatile double Ndx = 0.0;
+      Ndx = Ndx + (new_occ - s) / 2.0;
+      volatile double m = mu * Ndx;
+      const double dE = dE_f - m;
+      volatile double arg = -dE * t.beta;
+      const double p = std::exp(arg);
+      const int idx = 2 * nu + b;
+      t.dE[idx] = dE;
+      t.prob[idx] = p;
+      uint32_t thr;
+      if (dE < 0.0 || p >= 1.0) {
+        thr = 0xFFFFFFFFu;
+      } else {
+        double scaled = std::ceil(p * 4294967296.0);
+        if (scaled < 1.0) scaled = 1.0;
+        if (scaled > 4294967296.0) scaled = 4294967296.0;
+        thr = (uint32_t)((unsigned long long)scaled - 1ull);
+      }
+      t.thr_m1[idx] = thr;
+    }
+  }
+  t.valid = 1;
+}
+
+// Winitzki's erf^-1 approximation as used for the confidence factor
+// (include/casm/monte/misc/math.hh:62-72; BasicStatistics.cc:127)
+static double z_confidence(double confidence) {
+  const double a = 0.147, PI = 3.141592653589793238463;
+  const double sgn = (confidence < 0.0) ? -1.0 : 1.0;
+  const double b = std::log((1.0 - confidence) * (1.0 + confidence));
+  const double c = 2.0 / (PI * a) + b * 0.5;
+  const double d = b / a;
+  return std::sqrt(2.0) * (sgn * std::sqrt(std::sqrt(c * c - d) - c));
+}
+
+static NaturalShape nat_shape(const cmg_context *c) {
+  NaturalShape s;
+  s.n0 = (int)c->shape[0];
+  s.n1 = (int)c->shape[1];
+  s.n2 = (int)c->shape[2];
+  s.dim = c->dim;
+  s.n_sites = c->n_sites;
+  return s;
+}
+
+static LatticeView view(const cmg_context *c) {
+  LatticeView L;
+  memset(&L, 0, sizeof L);
+  L.planes = c->d_planes;
+  L.plane_stride = c->plane_stride;
+  L.chain_stride = c->chain_stride;
+  L.h = (int)(c->shape[0] / 2);
+  L.n1 = (int)c->shape[1];
+  L.n2 = (int)c->shape[2];
+  L.dim = c->dim;
+  L.col_offset = c->col_begin;
+  if (c->slab) {
+    for (int col = 0; col < 2; ++col) {
+      L.halo_lo[col] = c->d_halo[col][0];
+      L.halo_hi[col] = c->d_halo[col][1];
+      L.push_lo[col] = c->push[col][0];
+      L.push_hi[col] = c->push[col][1];
+    }
+  }
+  return L;
+}
+
+// ---------------------------------------------------------------------------
+extern "C" {
+
+int cmg_abi_version(void) { return CMG_ABI_VERSION; }
+const char *cmg_last_global_error(void) { return g_last_error.c_str(); }
+const char *cmg_last_error(const cmg_context *ctx) {
+  return ctx ? ctx->last_error.c_str() : g_last_error.c_str();
+}
+
+int cmg_device_count(int *count) {
+  if (!count) return fail(nullptr, CMG_EINVAL, "count == null");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    *count = 0;
+    cudaGetLastError();
+    return fail(nullptr, CMG_ENODEVICE,
+                std::string("no CUDA device: ") + cudaGetErrorString(e));
+  }
+  *count = n;
+  return CMG_OK;
+}
+
+static int create_common(int dim, const int64_t *shape, int n_chains, int device,
+                         bool slab, long long col_begin, const int64_t *gshape,
+                         cmg_context **out) {
+  if (!out) return fail(nullptr, CMG_EINVAL, "out == null");
+  *out = nullptr;
+  if (dim != 2 && dim != 3)
+    return fail(nullptr, CMG_EINVAL, "IsingConfiguration only supports 2d (3d is the extension)");
+  if (!shape) return fail(nullptr, CMG_EINVAL, "shape == null");
+  if (n_chains < 1 || n_chains >= (1 << 24))
+    return fail(nullptr, CMG_EINVAL, "n_chains must be in [1, 2^24)");
+  for (int d = 0; d < dim; ++d)
+    if (shape[d] < 2 || shape[d] > 0x7fffffffLL)
+      return fail(nullptr, CMG_EINVAL, "extent out of range (need 2 <= n < 2^31)");
+  int ndev = 0;
+  int rc = cmg_device_count(&ndev);
+  if (rc != CMG_OK) return rc;
+  if (ndev == 0) return fail(nullptr, CMG_ENODEVICE, "no CUDA device");
+  if (device < 0 || device >= ndev) return fail(nullptr, CMG_EINVAL, "bad device index");
+
+  cmg_context *c = new cmg_context();
+  c->device = device;
+  c->dim = dim;
+  c->n_chains = n_chains;
+  c->n_sites = 1;
+  for (int d = 0; d < 3; ++d) {
+    c->shape[d] = d < dim ? shape[d] : 1;
+    c->global_shape[d] = gshape ? (d < dim ? gshape[d] : 1) : c->shape[d];
+    c->n_sites *= c->shape[d];
+  }
+  c->slab = slab;
+  c->col_begin = col_begin;
+  // colour planes need even extents; a slab needs only n0 (and the GLOBAL n1) even
+  c->planar = (c->shape[0] % 2 == 0) && (slab || c->shape[1] % 2 == 0) &&
+              (dim == 2 || c->shape[2] % 2 == 0);
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) {
+    delete c;
+    return fail(nullptr, CMG_ECUDA, cudaGetErrorString(e));
+  }
+#define CUC(call)                                                        \
+  do {                                                                   \
+    cudaError_t e__ = (call);                                            \
+    if (e__ != cudaSuccess) {                                            \
+      std::string m__ = std::string(#call) + ": " + cudaGetErrorString(e__); \
+      cmg_destroy(c);                                                    \
+      return fail(nullptr, e__ == cudaErrorMemoryAllocation ? CMG_ENOMEM : CMG_ECUDA, m__); \
+    }                                                                    \
+  } while (0)
+  if (c->planar) {
+    long long plane_bytes = c->n_sites / 2;
+    c->plane_stride = (plane_bytes + 255) / 256 * 256;
+    c->chain_stride = 2 * c->plane_stride;
+    CUC(cudaMalloc(&c->d_planes, (size_t)c->chain_stride * n_chains));
+    CUC(cudaMemset(c->d_planes, 1, (size_t)c->chain_stride * n_chains));
+  } else {
+    CUC(cudaMalloc(&c->d_nat, (size_t)c->n_sites * n_chains));
+    CUC(cudaMemset(c->d_nat, 1, (size_t)c->n_sites * n_chains));
+    c->nat_is_current = true;
+  }
+  CUC(cudaMalloc(&c->d_tabs, sizeof(ChainTables) * n_chains));
+  CUC(cudaMemset(c->d_tabs, 0, sizeof(ChainTables) * n_chains));
+  c->h_tabs.resize(n_chains);
+  for (auto &t : c->h_tabs) memset(&t, 0, sizeof t);
+  CUC(cudaMalloc(&c->d_n_accept, sizeof(unsigned long long) * n_chains));
+  CUC(cudaMemset(c->d_n_accept, 0, sizeof(unsigned long long) * n_chains));
+  CUC(cudaMalloc(&c->d_run, sizeof(RunState)));
+  CUC(cudaMemset(c->d_run, 0, sizeof(RunState)));
+  CUC(cudaMalloc(&c->d_flag, sizeof(int)));
+  CUC(cudaMemset(c->d_flag, 0, sizeof(int)));
+  CUC(cudaMalloc(&c->d_cur_sb, sizeof(long long) * 2 * n_chains));
+  CUC(cudaMalloc(&c->d_scratch_sb, sizeof(long long) * 2));
+  c->engine_seeded.assign(n_chains, 0);
+  if (slab) {
+    const long long hb = c->shape[0] / 2;
+    for (int col = 0; col < 2; ++col)
+      for (int side = 0; side < 2; ++side) {
+        CUC(cudaMalloc(&c->d_halo[col][side], (size_t)hb));
+        CUC(cudaMemset(c->d_halo[col][side], 1, (size_t)hb));
+      }
+  }
+#undef CUC
+  *out = c;
+  return CMG_OK;
+}
+
+int cmg_create(int dim, const int64_t *shape, int n_chains, int device,
+               cmg_context **out) {
+  return create_common(dim, shape, n_chains, device, false, 0, nullptr, out);
+}
+
+int cmg_create_slab(int dim, const int64_t *global_shape, int64_t col_begin,
+                    int64_t n_cols_local, int device, cmg_context **out) {
+  if (dim != 2) return fail(nullptr, CMG_EUNSUPPORTED, "slab decomposition is 2-d only");
+  if (!global_shape) return fail(nullptr, CMG_EINVAL, "global_shape == null");
+  if (global_shape[0] % 32 != 0)
+    return fail(nullptr, CMG_EINVAL, "slab decomposition needs n0 % 32 == 0");
+  if (global_shape[1] % 2 != 0)
+    return fail(nullptr, CMG_EINVAL, "checkerboard needs even extents");
+  if (col_begin < 0 || n_cols_local < 1 || col_begin + n_cols_local > global_shape[1])
+    return fail(nullptr, CMG_EINVAL, "slab column range outside the lattice");
+  if (col_begin % 2 != 0)
+    return fail(nullptr, CMG_EINVAL, "slab col_begin must be even (local colour == global colour)");
+  int64_t local[2] = {global_shape[0], n_cols_local};
+  return create_common(2, local, 1, device, true, col_begin, global_shape, out);
+}
+
+int cmg_destroy(cmg_context *c) {
+  if (!c) return CMG_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (void *p : c->ipc_opened) cudaIpcCloseMemHandle(p);
+  cudaFree(c->d_planes);
+  cudaFree(c->d_nat);
+  cudaFree(c->d_stage);
+  cudaFree(c->d_flag);
+  cudaFree(c->d_tabs);
+  cudaFree(c->d_run);
+  cudaFree(c->d_n_accept);
+  cudaFree(c->d_engines);
+  cudaFree(c->d_cur_sb);
+  cudaFree(c->d_scratch_sb);
+  cudaFree(c->d_series);
+  cudaFree(c->d_dbl);
+  for (int col = 0; col < 2; ++col)
+    for (int side = 0; side < 2; ++side) cudaFree(c->d_halo[col][side]);
+  delete c;
+  return CMG_OK;
+}
+
+int cmg_set_stream(cmg_context *c, void *cuda_stream) {
+  NEED(c);
+  CU(c, cudaStreamSynchronize(c->stream));
+  c->stream = (cudaStream_t)cuda_stream;
+  return CMG_OK;
+}
+
+int cmg_sync(cmg_context *c) {
+  NEED(c);
+  CU(c, cudaStreamSynchronize(c->stream));
+  return CMG_OK;
+}
+
+int cmg_n_sites(const cmg_context *c, int64_t *n) {
+  if (!c || !n) return fail(nullptr, CMG_EINVAL, "null argument");
+  *n = c->n_sites;
+  return CMG_OK;
+}
+
+// ---- model / conditions ------------------------------------------------------
+int cmg_set_model(cmg_context *c, double J, int lattice_type) {
+  NEED(c);
+  if (lattice_type != 1) return fail(c, CMG_EINVAL, "Unsupported lattice_type");
+  c->J = J;
+  c->lattice_type = lattice_type;
+  c->model_set = true;
+  // conditions already set keep their (T, mu) but need new tables
+  for (int ch = 0; ch < c->n_chains; ++ch)
+    if (c->h_tabs[ch].valid)
+      build_tables(c->h_tabs[ch], c->dim, J, c->h_tabs[ch].temperature, c->h_tabs[ch].mu);
+  CU(c, cudaMemcpyAsync(c->d_tabs, c->h_tabs.data(), sizeof(ChainTables) * c->n_chains,
+                        cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return CMG_OK;
+}
+
+int cmg_set_conditions(cmg_context *c, int chain, double temperature, double mu) {
+  NEED(c);
+  if (chain < -1 || chain >= c->n_chains) return fail(c, CMG_EINVAL, "bad chain index");
+  if (!(temperature > 0.0)) return fail(c, CMG_EINVAL, "temperature must be > 0");
+  const int lo = chain < 0 ? 0 : chain, hi = chain < 0 ? c->n_chains : chain + 1;
+  for (int ch = lo; ch < hi; ++ch) build_tables(c->h_tabs[ch], c->dim, c->J, temperature, mu);
+  CU(c, cudaMemcpyAsync(c->d_tabs + lo, c->h_tabs.data() + lo, sizeof(ChainTables) * (hi - lo),
+                        cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return CMG_OK;
+}
+
+int cmg_get_tables(cmg_context *c, int chain, double *dE, double *prob, uint32_t *thr) {
+  NEED(c);
+  if (chain < 0 || chain >= c->n_chains) return fail(c, CMG_EINVAL, "bad chain index");
+  if (!c->h_tabs[chain].valid) return fail(c, CMG_ESTATE, "conditions not set");
+  const int n = 2 * (2 * c->dim + 1);
+  for (int i = 0; i < n; ++i) {
+    if (dE) dE[i] = c->h_tabs[chain].dE[i];
+    if (prob) prob[i] = c->h_tabs[chain].prob[i];
+    if (thr) thr[i] = c->h_tabs[chain].thr_m1[i];
+  }
+  return CMG_OK;
+}
+
+// ---- occupation ----------------------------------------------------------------
+static int ensure_stage(cmg_context *c) {
+  if (!c->d_stage) CU(c, cudaMalloc(&c->d_stage, sizeof(int32_t) * (size_t)c->n_sites));
+  return CMG_OK;
+}
+static int ensure_nat(cmg_context *c) {
+  if (!c->d_nat) {
+    CU(c, cudaMalloc(&c->d_nat, (size_t)c->n_sites * c->n_chains));
+    c->nat_is_current = false;
+  }
+  return CMG_OK;
+}
+static NaturalShape slab_aware_shape(const cmg_context *c) { return nat_shape(c); }
+
+// planes -> natural for all chains (no-op when the lattice is natural-only)
+static int sync_nat_from_planes(cmg_context *c) {
+  if (!c->planar) return CMG_OK;
+  int rc = ensure_nat(c);
+  if (rc) return rc;
+  if (c->nat_is_current) return CMG_OK;
+  NaturalShape s = slab_aware_shape(c);
+  for (int ch = 0; ch < c->n_chains; ++ch) {
+    k_planes_to_natural<<<nblocks(c->n_sites, 256), 256, 0, c->stream>>>(
+        c->d_planes + ch * c->chain_stride, c->plane_stride,
+        c->d_nat + ch * c->n_sites, s);
+    ++c->launches;
+  }
+  CU(c, cudaGetLastError());
+  c->nat_is_current = true;
+  return CMG_OK;
+}
+static int sync_planes_from_nat(cmg_context *c) {
+  if (!c->planar) return CMG_OK;
+  NaturalShape s = slab_aware_shape(c);
+  for (int ch = 0; ch < c->n_chains; ++ch) {
+    k_natural_to_planes<<<nblocks(c->n_sites, 256), 256, 0, c->stream>>>(
+        c->d_nat + ch * c->n_sites, c->d_planes + ch * c->chain_stride, c->plane_stride, s);
+    ++c->launches;
+  }
+  CU(c, cudaGetLastError());
+  return CMG_OK;
+}
+
+static int upload_from_stage(cmg_context *c, int chain, const int32_t *src_dev) {
+  CU(c, cudaMemsetAsync(c->d_flag, 0, sizeof(int), c->stream));
+  NaturalShape s = nat_shape(c);
+  if (c->planar) {
+    k_i32_to_planes<<<nblocks(c->n_sites, 256), 256, 0, c->stream>>>(
+        src_dev, c->d_planes + chain * c->chain_stride, c->plane_stride, s, c->d_flag);
+    c->nat_is_current = false;
+  } else {
+    k_i32_to_natural<<<nblocks(c->n_sites, 256), 256, 0, c->stream>>>(
+        src_dev, c->d_nat + chain * c->n_sites, c->n_sites, c->d_flag);
+  }
+  ++c->launches;
+  CU(c, cudaGetLastError());
+  int bad = 0;
+  CU(c, cudaMemcpyAsync(&bad, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  if (bad) return fail(c, CMG_EINVAL, "occupation values must be +1 or -1");
+  return CMG_OK;
+}
+
+int cmg_upload_occupation_i32(cmg_context *c, int chain, const int32_t *occ, int64_t n) {
+  NEED(c);
+  if (chain < 0 || chain >= c->n_chains) return fail(c, CMG_EINVAL, "bad chain index");
+  if (!occ || n != c->n_sites)
+    return fail(c, CMG_EINVAL, "Error in set_occupation: size mismatch");
+  if (c->slab && (c->col_begin & 1))
+    return fail(c, CMG_EUNSUPPORTED, "slab col_begin must be even");
+  int rc = ensure_stage(c);
+  if (rc) return rc;
+  CU(c, cudaMemcpyAsync(c->d_stage, occ, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice,
+                        c->stream));
+  return upload_from_stage(c, chain, c->d_stage);
+}
+
+int cmg_upload_occupation_i32_dev(cmg_context *c, int chain, const int32_t *occ_dev,
+                                  int64_t n) {
+  NEED(c);
+  if (chain < 0 || chain >= c->n_chains) return fail(c, CMG_EINVAL, "bad chain index");
+  if (!occ_dev || n != c->n_sites)
+    return fail(c, CMG_EINVAL, "Error in set_occupation: size mismatch");
+  return upload_from_stage(c, chain, occ_dev);
+}
+
+static int download_to(cmg_context *c, int chain, int32_t *dst_dev) {
+  NaturalShape s = nat_shape(c);
+  if (c->planar) {
+    k_planes_to_i32<<<nblocks(c->n_sites, 256), 256, 0, c->stream>>>(
+        c->d_planes + chain * c->chain_stride, c->plane_stride, dst_dev, s);
+  } else {
+    k_natural_to_i32<<<nblocks(c->n_sites, 256), 256, 0, c->stream>>>(
+        c->d_nat + chain * c->n_sites, dst_dev, c->n_sites);
+  }
+  ++c->launches;
+  CU(c, cudaGetLastError());
+  return CMG_OK;
+}
+
+int cmg_download_occupation_i32(cmg_context *c, int chain, int32_t *occ, int64_t n) {
+  NEED(c);
+  if (chain < 0 || chain >= c->n_chains) return fail(c, CMG_EINVAL, "bad chain index");
+  if (!occ || n != c->n_sites) return fail(c, CMG_EINVAL, "size mismatch");
+  int rc = ensure_stage(c);
+  if (rc) return rc;
+  rc = download_to(c, chain, c->d_stage);
+  if (rc) return rc;
+  CU(c, cudaMemcpyAsync(occ, c->d_stage, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost,
+                        c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return CMG_OK;
+}
+
+int cmg_download_occupation_i32_dev(cmg_context *c, int chain, int32_t *occ_dev, int64_t n) {
+  NEED(c);
+  if (chain < 0 || chain >= c->n_chains) return fail(c, CMG_EINVAL, "bad chain index");
+  if (!occ_dev || n != c->n_sites) return fail(c, CMG_EINVAL, "size mismatch");
+  return download_to(c, chain, occ_dev);
+}
+
+int cmg_fill_occupation(cmg_context *c, int chain, int value) {
+  NEED(c);
+  if (chain < -1 || chain >= c->n_chains) return fail(c, CMG_EINVAL, "bad chain index");
+  if (value != 1 && value != -1) return fail(c, CMG_EINVAL, "fill value must be +1 or -1");
+  const int lo = chain < 0 ? 0 : chain, hi = chain < 0 ? c->n_chains : chain + 1;
+  const int b = value > 0 ? 1 : 0;
+  if (c->planar) {
+    CU(c, cudaMemsetAsync(c->d_planes + lo * c->chain_stride, b,
+                          (size_t)c->chain_stride * (hi - lo), c->stream));
+    c->nat_is_current = false;
+  } else {
+    CU(c, cudaMemsetAsync(c->d_nat + lo * c->n_sites, b, (size_t)c->n_sites * (hi - lo),
+                          c->stream));
+  }
+  return CMG_OK;
+}
+
+int cmg_randomize_occupation(cmg_context *c, int chain, uint64_t seed, double p_up) {
+  NEED(c);
+  if (chain < -1 || chain >= c->n_chains) return fail(c, CMG_EINVAL, "bad chain index");
+  if (!(p_up >= 0.0 && p_up <= 1.0)) return fail(c, CMG_EINVAL, "p_up outside [0,1]");
+  int rc = ensure_nat(c);
+  if (rc) return rc;
+  const int lo = chain < 0 ? 0 : chain, hi = chain < 0 ? c->n_chains : chain + 1;
+  double scaled = std::ceil(p_up * 4294967296.0);
+  const int always = scaled >= 4294967296.0;
+  const uint32_t thr = scaled < 1.0 ? 0u : (uint32_t)((unsigned long long)scaled - 1ull);
+  if (c->planar && !(lo == 0 && hi == c->n_chains)) {
+    rc = sync_nat_from_planes(c);
+    if (rc) return rc;
+  }
+  for (int ch = lo; ch < hi; ++ch) {
+    if (scaled < 1.0) {
+      CU(c, cudaMemsetAsync(c->d_nat + ch * c->n_sites, 0, (size_t)c->n_sites, c->stream));
+    } else {
+      k_randomize_natural<<<nblocks((c->n_sites + 3) / 4, 256), 256, 0, c->stream>>>(
+          c->d_nat + ch * c->n_sites, c->n_sites, seed + 0x9E3779B97F4A7C15ull * (uint64_t)ch,
+          thr, always);
+      ++c->launches;
+    }
+  }
+  CU(c, cudaGetLastError());
+  if (c->planar) {
+    rc = sync_planes_from_nat(c);
+    if (rc) return rc;
+    c->nat_is_current = true;
+  }
+  return CMG_OK;
+}
+
+// ---- RNG -------------------------------------------------------------------------
+int cmg_seed_philox(cmg_context *c, uint64_t seed) {
+  NEED(c);
+  c->philox_seed = seed;
+  return CMG_OK;
+}
+
+static int push_run_state(cmg_context *c) {
+  RunState rs;
+  rs.pass = c->h_pass;
+  rs.n_samples = c->n_samples;
+  CU(c, cudaMemcpyAsync(c->d_run, &rs, sizeof rs, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return CMG_OK;
+}
+
+int cmg_set_pass_counter(cmg_context *c, uint64_t pass_index) {
+  NEED(c);
+  c->h_pass = pass_index;
+  return push_run_state(c);
+}
+
+static int ensure_engines(cmg_context *c) {
+  if (!c->d_engines) {
+    CU(c, cudaMalloc(&c->d_engines, sizeof(MT64State) * c->n_chains));
+    CU(c, cudaMemset(c->d_engines, 0, sizeof(MT64State) * c->n_chains));
+  }
+  return CMG_OK;
+}
+
+// std::mt19937_64::seed(value): x[0] = value, x[i] = f*(x[i-1]^(x[i-1]>>62)) + i,
+// position = 312 so the first draw regenerates (C++11 [rand.eng.mers])
+int cmg_seed_mt19937_64(cmg_context *c, int chain, uint64_t seed) {
+  NEED(c);
+  if (chain < 0 || chain >= c->n_chains) return fail(c, CMG_EINVAL, "bad chain index");
+  int rc = ensure_engines(c);
+  if (rc) return rc;
+  MT64State st;
+  memset(&st, 0, sizeof st);
+  st.x[0] = seed;
+  for (int i = 1; i < 312; ++i)
+    st.x[i] = 6364136223846793005ull * (st.x[i - 1] ^ (st.x[i - 1] >> 62)) + (unsigned long long)i;
+  st.pos = 312;
+  CU(c, cudaMemcpyAsync(c->d_engines + chain, &st, sizeof st, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  c->engine_seeded[chain] = 1;
+  return CMG_OK;
+}
+
+int cmg_set_mt19937_64_state(cmg_context *c, int chain, const uint64_t *state312, int position) {
+  NEED(c);
+  if (chain < 0 || chain >= c->n_chains) return fail(c, CMG_EINVAL, "bad chain index");
+  if (!state312 || position < 0 || position > 312)
+    return fail(c, CMG_EINVAL, "bad engine state");
+  int rc = ensure_engines(c);
+  if (rc) return rc;
+  MT64State st;
+  memset(&st, 0, sizeof st);
+  for (int i = 0; i < 312; ++i) st.x[i] = state312[i];
+  st.pos = position;
+  CU(c, cudaMemcpyAsync(c->d_engines + chain, &st, sizeof st, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  c->engine_seeded[chain] = 1;
+  return CMG_OK;
+}
+
+int cmg_get_mt19937_64_state(cmg_context *c, int chain, uint64_t *state312, int *position) {
+  NEED(c);
+  if (chain < 0 || chain >= c->n_chains) return fail(c, CMG_EINVAL, "bad chain index");
+  if (!state312 || !position) return fail(c, CMG_EINVAL, "null argument");
+  if (!c->d_engines || !c->engine_seeded[chain]) return fail(c, CMG_ESTATE, "engine not seeded");
+  MT64State st;
+  CU(c, cudaMemcpyAsync(&st, c->d_engines + chain, sizeof st, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < 312; ++i) state312[i] = st.x[i];
+  *position = st.pos;
+  return CMG_OK;
+}
+
+int cmg_rng_draw(cmg_context *c, int chain, int n, const int64_t *int_max, const double *real_max,
+                 const uint8_t *is_real, int64_t *int_out, double *real_out) {
+  NEED(c);
+  if (chain < 0 || chain >= c->n_chains) return fail(c, CMG_EINVAL, "bad chain index");
+  if (n < 0 || !int_max || !real_max || !is_real || !int_out || !real_out)
+    return fail(c, CMG_EINVAL, "null argument");
+  if (!c->d_engines || !c->engine_seeded[chain]) return fail(c, CMG_ESTATE, "engine not seeded");
+  if (n == 0) return CMG_OK;
+  long long *d_imax = nullptr, *d_iout = nullptr;
+  double *d_rmax = nullptr, *d_rout = nullptr;
+  uint8_t *d_isr = nullptr;
+  CU(c, cudaMalloc(&d_imax, 8 * n));
+  CU(c, cudaMalloc(&d_iout, 8 * n));
+  CU(c, cudaMalloc(&d_rmax, 8 * n));
+  CU(c, cudaMalloc(&d_rout, 8 * n));
+  CU(c, cudaMalloc(&d_isr, n));
+  CU(c, cudaMemcpyAsync(d_imax, int_max, 8 * n, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemcpyAsync(d_rmax, real_max, 8 * n, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemcpyAsync(d_isr, is_real, n, cudaMemcpyHostToDevice, c->stream));
+  k_rng_draw<<<1, 1, 0, c->stream>>>(c->d_engines + chain, n, d_imax, d_rmax, d_isr, d_iout, d_rout);
+  ++c->launches;
+  CU(c, cudaGetLastError());
+  CU(c, cudaMemcpyAsync(int_out, d_iout, 8 * n, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaMemcpyAsync(real_out, d_rout, 8 * n, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  cudaFree(d_imax);
+  cudaFree(d_iout);
+  cudaFree(d_rmax);
+  cudaFree(d_rout);
+  cudaFree(d_isr);
+  return CMG_OK;
+}
+
+// ---- sample series storage -------------------------------------------------------
+static int ensure_series(cmg_context *c, long long need) {
+  if (need <= c->capacity) return CMG_OK;
+  long long cap = c->capacity ? c->capacity : 1024;
+  while (cap < need) cap *= 2;
+  long long *nb = nullptr;
+  const size_t slot_bytes = sizeof(long long) * 2 * (size_t)c->n_chains;
+  CU(c, cudaMalloc(&nb, slot_bytes * (size_t)cap));
+  CU(c, cudaMemsetAsync(nb, 0, slot_bytes * (size_t)cap, c->stream));
+  if (c->d_series && c->n_samples > 0)
+    CU(c, cudaMemcpyAsync(nb, c->d_series, slot_bytes * (size_t)c->n_samples,
+                          cudaMemcpyDeviceToDevice, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  cudaFree(c->d_series);
+  c->d_series = nb;
+  c->capacity = cap;
+  return CMG_OK;
+}
+
+// ---- the hot loop ------------------------------------------------------------------
+static int pick_variant(cmg_context *c) {
+  if (c->forced_variant != V_AUTO) return c->forced_variant;
+  if (c->dim == 2 && c->shape[0] % 32 == 0) return V_BULK2D;
+  if (c->dim == 3 && c->shape[0] % 32 == 0) return V_BULK3D;
+  return V_GENERIC;
+}
+
+static int pick_js(const cmg_context *c, int variant) {
+  if (c->js > 0) return c->js;
+  // strips long enough to amortise the two extra column loads, short enough to
+  // give every SM several CTAs (148 SMs x 16 CTAs of 128 threads)
+  const long long V = c->shape[0] / 32;
+  const long long layers = variant == V_BULK3D ? c->shape[2] : 1;
+  const long long target_threads = 148LL * 512;
+  int js = 32;
+  while (js > 2 && V * ((c->shape[1] + js - 1) / js) * layers * c->n_chains < target_threads) js >>= 1;
+  return js;
+}
+
+static int launch_half_sweep(cmg_context *c, int variant, int colour, unsigned long long pass,
+                             bool sample, long long slot) {
+  SweepArgs A;
+  memset(&A, 0, sizeof A);
+  A.L = view(c);
+  A.tabs = c->d_tabs;
+  A.n_accept = c->d_n_accept;
+  A.sb = sample ? c->d_series + slot * 2 * c->n_chains : nullptr;
+  A.sb_chain_stride = 2;
+  A.pass = pass;
+  for (int r = 0; r < 10; ++r) {
+    A.rk[2 * r] = (uint32_t)c->philox_seed + (uint32_t)r * kPhiloxW0;
+    A.rk[2 * r + 1] = (uint32_t)(c->philox_seed >> 32) + (uint32_t)r * kPhiloxW1;
+  }
+  A.colour = colour;
+  A.js = pick_js(c, variant);
+  const long long plane_size = c->n_sites / 2;
+  dim3 block(128);
+  if (variant == V_GENERIC) {
+    dim3 grid(nblocks((plane_size + 3) / 4, 128), c->n_chains);
+    if (sample)
+      k_halfsweep_generic<true><<<grid, block, 0, c->stream>>>(A);
+    else
+      k_halfsweep_generic<false><<<grid, block, 0, c->stream>>>(A);
+  } else if (variant == V_BULK2D) {
+    const long long V = c->shape[0] / 32;
+    const long long strips = (c->shape[1] + A.js - 1) / A.js;
+    dim3 grid(nblocks(V * strips, 128), c->n_chains);
+    if (sample)
+      k_halfsweep_bulk2d<true><<<grid, block, 0, c->stream>>>(A);
+    else
+      k_halfsweep_bulk2d<false><<<grid, block, 0, c->stream>>>(A);
+  } else if (variant == V_BULK3D) {
+    const long long V = c->shape[0] / 32;
+    const long long strips = (c->shape[1] + A.js - 1) / A.js;
+    dim3 grid(nblocks(V * strips * c->shape[2], 128), c->n_chains);
+    if (sample)
+      k_halfsweep_bulk3d<true><<<grid, block, 0, c->stream>>>(A);
+    else
+      k_halfsweep_bulk3d<false><<<grid, block, 0, c->stream>>>(A);
+  } else {
+    return fail(c, CMG_EUNSUPPORTED, "kernel variant not available");
+  }
+  ++c->launches;
+  return CMG_OK;
+}
+
+static const char *variant_str(int v) {
+  switch (v) {
+    case V_GENERIC: return "generic";
+    case V_BULK2D: return "bulk2d";
+    case V_BULK3D: return "bulk3d";
+    case V_SMEM: return "smem";
+    default: return "auto";
+  }
+}
+
+static int check_ready(cmg_context *c) {
+  for (int ch = 0; ch < c->n_chains; ++ch)
+    if (!c->h_tabs[ch].valid) return fail(c, CMG_ESTATE, "conditions not set for every chain");
+  return CMG_OK;
+}
+
+static int observables_now(cmg_context *c, int chain, long long *dst_dev /* {ones,B} */) {
+  CU(c, cudaMemsetAsync(dst_dev, 0, 2 * sizeof(long long), c->stream));
+  if (c->planar) {
+    LatticeView L = view(c);
+    k_observables_planes<<<(unsigned)std::min<long long>(nblocks(c->n_sites / 2, 256), 148 * 8),
+                           256, 0, c->stream>>>(L, chain, dst_dev);
+  } else {
+    k_observables_natural<<<(unsigned)std::min<long long>(nblocks(c->n_sites, 256), 148 * 8), 256,
+                            0, c->stream>>>(c->d_nat + chain * c->n_sites, nat_shape(c), dst_dev);
+  }
+  ++c->launches;
+  CU(c, cudaGetLastError());
+  return CMG_OK;
+}
+
+static int run_serial(cmg_context *c, long long n_passes, long long sample_period) {
+  if (c->slab) return fail(c, CMG_EUNSUPPORTED, "serial reference mode is single-GPU only");
+  for (int ch = 0; ch < c->n_chains; ++ch)
+    if (!c->d_engines || !c->engine_seeded[ch])
+      return fail(c, CMG_ESTATE, "mt19937_64 engine not seeded for every chain");
+  int rc = sync_nat_from_planes(c);
+  if (rc) return rc;
+  for (int ch = 0; ch < c->n_chains; ++ch) {
+    CU(c, cudaMemsetAsync(c->d_cur_sb + 2 * ch, 0, 2 * sizeof(long long), c->stream));
+    k_observables_natural<<<(unsigned)std::min<long long>(nblocks(c->n_sites, 256), 148 * 8), 256,
+                            0, c->stream>>>(c->d_nat + ch * c->n_sites, nat_shape(c),
+                                            c->d_cur_sb + 2 * ch);
+    ++c->launches;
+  }
+  long long n_new = 0;
+  if (sample_period > 0)
+    n_new = (c->n_pass + n_passes) / sample_period - c->n_pass / sample_period;
+  rc = ensure_series(c, c->n_samples + n_new);
+  if (rc) return rc;
+  SerialArgs A;
+  memset(&A, 0, sizeof A);
+  A.nat = c->d_nat;
+  A.shape = nat_shape(c);
+  A.tabs = c->d_tabs;
+  A.engines = c->d_engines;
+  A.n_accept = c->d_n_accept;
+  A.cur_sb = c->d_cur_sb;
+  A.series = c->d_series + c->n_samples * 2 * c->n_chains;
+  A.series_chain_stride = 2;
+  A.n_passes = n_passes;
+  A.sample_period = sample_period;
+  A.pass_base = c->n_pass;
+  // slots of consecutive samples are n_chains*2 apart: the kernel indexes
+  // series + chain*2 + 2*slot, so give it a per-chain contiguous view only when
+  // n_chains == 1; otherwise stage through a temporary
+  long long *tmp = nullptr;
+  if (c->n_chains > 1 && n_new > 0) {
+    CU(c, cudaMalloc(&tmp, sizeof(long long) * 2 * (size_t)n_new * c->n_chains));
+    A.series = tmp;
+    A.series_chain_stride = 2 * n_new;
+  }
+  size_t smem = 312 * sizeof(unsigned long long);
+  A.use_smem = 0;
+  if ((size_t)c->n_sites + smem <= 200 * 1024) {
+    A.use_smem = 1;
+    smem += (size_t)c->n_sites;
+  }
+  CU(c, cudaFuncSetAttribute(k_serial_reference, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(204 * 1024)));
+  k_serial_reference<<<c->n_chains, 128, smem, c->stream>>>(A);
+  ++c->launches;
+  CU(c, cudaGetLastError());
+  if (tmp) {
+    // tmp[chain][slot][2] -> series[slot][chain][2]
+    for (int ch = 0; ch < c->n_chains; ++ch)
+      CU(c, cudaMemcpy2DAsync(c->d_series + c->n_samples * 2 * c->n_chains + 2 * ch,
+                              sizeof(long long) * 2 * c->n_chains, tmp + 2 * n_new * ch,
+                              sizeof(long long) * 2, sizeof(long long) * 2, (size_t)n_new,
+                              cudaMemcpyDeviceToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    cudaFree(tmp);
+  }
+  c->n_samples += n_new;
+  c->n_pass += n_passes;
+  rc = sync_planes_from_nat(c);
+  if (rc) return rc;
+  c->nat_is_current = true;
+  c->variant_name = "serial_reference";
+  return CMG_OK;
+}
+
+int cmg_run_passes(cmg_context *c, int64_t n_passes, int mode, int64_t sample_period) {
+  NEED(c);
+  if (n_passes < 0 || sample_period < 0) return fail(c, CMG_EINVAL, "negative count");
+  int rc = check_ready(c);
+  if (rc) return rc;
+  if (n_passes == 0) return CMG_OK;
+  if (mode == CMG_MODE_SERIAL_REFERENCE) return run_serial(c, n_passes, sample_period);
+  if (mode != CMG_MODE_CHECKERBOARD) return fail(c, CMG_EINVAL, "unknown mode");
+  if (!c->planar)
+    return fail(c, CMG_EINVAL,
+                "checkerboard mode needs even extents; use CMG_MODE_SERIAL_REFERENCE");
+  if (c->slab)
+    return fail(c, CMG_ESTATE, "slab contexts are stepped with cmg_slab_half_sweep");
+  const int variant = pick_variant(c);
+  if (variant == V_BULK2D && !(c->dim == 2 && c->shape[0] % 32 == 0))
+    return fail(c, CMG_EINVAL, "bulk2d needs dim == 2 and n0 % 32 == 0");
+  if (variant == V_BULK3D && !(c->dim == 3 && c->shape[0] % 32 == 0))
+    return fail(c, CMG_EINVAL, "bulk3d needs dim == 3 and n0 % 32 == 0");
+  c->variant_name = variant_str(variant);
+  long long n_new = 0;
+  if (sample_period > 0)
+    n_new = (c->n_pass + n_passes) / sample_period - c->n_pass / sample_period;
+  rc = ensure_series(c, c->n_samples + n_new);
+  if (rc) return rc;
+  c->nat_is_current = false;
+  for (long long t = 0; t < n_passes; ++t) {
+    const bool sample = sample_period > 0 && ((c->n_pass + 1) % sample_period) == 0;
+    rc = launch_half_sweep(c, variant, 0, c->h_pass, false, 0);
+    if (rc) return rc;
+    rc = launch_half_sweep(c, variant, 1, c->h_pass, sample, c->n_samples);
+    if (rc) return rc;
+    ++c->h_pass;
+    ++c->n_pass;
+    if (sample) ++c->n_samples;
+  }
+  CU(c, cudaGetLastError());
+  return CMG_OK;
+}
+
+int cmg_slab_half_sweep(cmg_context *c, int colour, uint64_t pass_index, int sample) {
+  NEED(c);
+  if (!c->slab) return fail(c, CMG_ESTATE, "not a slab context");
+  if (colour != 0 && colour != 1) return fail(c, CMG_EINVAL, "colour must be 0 or 1");
+  int rc = check_ready(c);
+  if (rc) return rc;
+  const bool do_sample = sample && colour == 1;
+  if (do_sample) {
+    rc = ensure_series(c, c->n_samples + 1);
+    if (rc) return rc;
+  }
+  c->nat_is_current = false;
+  c->variant_name = "bulk2d";
+  rc = launch_half_sweep(c, V_BULK2D, colour, pass_index, do_sample, c->n_samples);
+  if (rc) return rc;
+  if (colour == 1) {
+    ++c->n_pass;
+    c->h_pass = pass_index + 1;
+    if (do_sample) ++c->n_samples;
+  }
+  CU(c, cudaGetLastError());
+  return CMG_OK;
+}
+
+int cmg_slab_boundary_ptr(cmg_context *c, int colour, int side, void **dev_ptr, int64_t *n_bytes) {
+  NEED(c);
+  if (!c->slab) return fail(c, CMG_ESTATE, "not a slab context");
+  if ((colour | side) & ~1) return fail(c, CMG_EINVAL, "colour/side must be 0 or 1");
+  if (!dev_ptr || !n_bytes) return fail(c, CMG_EINVAL, "null argument");
+  const long long hb = c->shape[0] / 2;
+  *dev_ptr = c->d_planes + colour * c->plane_stride + (side ? hb * (c->shape[1] - 1) : 0);
+  *n_bytes = hb;
+  return CMG_OK;
+}
+
+int cmg_slab_halo_ptr(cmg_context *c, int colour, int side, void **dev_ptr, int64_t *n_bytes) {
+  NEED(c);
+  if (!c->slab) return fail(c, CMG_ESTATE, "not a slab context");
+  if ((colour | side) & ~1) return fail(c, CMG_EINVAL, "colour/side must be 0 or 1");
+  if (!dev_ptr || !n_bytes) return fail(c, CMG_EINVAL, "null argument");
+  *dev_ptr = c->d_halo[colour][side];
+  *n_bytes = c->shape[0] / 2;
+  return CMG_OK;
+}
+
+struct SlabIpcBlob {
+  cudaIpcMemHandle_t h[2][2];
+};
+
+int cmg_slab_ipc_export(cmg_context *c, void *handle_out, int64_t handle_bytes) {
+  NEED(c);
+  if (!c->slab) return fail(c, CMG_ESTATE, "not a slab context");
+  if (!handle_out || handle_bytes < (int64_t)sizeof(SlabIpcBlob))
+    return fail(c, CMG_EINVAL, "handle buffer too small (need 256 bytes)");
+  SlabIpcBlob blob;
+  for (int col = 0; col < 2; ++col)
+    for (int side = 0; side < 2; ++side)
+      CU(c, cudaIpcGetMemHandle(&blob.h[col][side], c->d_halo[col][side]));
+  memcpy(handle_out, &blob, sizeof blob);
+  return CMG_OK;
+}
+
+// side = which of OUR boundaries the peer sits on (0: peer is the low neighbour,
+// so our column 0 is pushed into the peer's halo_hi; 1: high neighbour).
+int cmg_slab_ipc_attach(cmg_context *c, int side, const void *handle, int64_t handle_bytes,
+                        int same_process, cmg_context *peer) {
+  NEED(c);
+  if (!c->slab) return fail(c, CMG_ESTATE, "not a slab context");
+  if (side & ~1) return fail(c, CMG_EINVAL, "side must be 0 or 1");
+  if (same_process) {
+    if (!peer || !peer->slab) return fail(c, CMG_EINVAL, "peer context missing");
+    if (peer->device != c->device) {
+      int can = 0;
+      CU(c, cudaDeviceCanAccessPeer(&can, c->device, peer->device));
+      if (!can) return fail(c, CMG_EUNSUPPORTED, "no peer access between the two devices");
+      cudaError_t e = cudaDeviceEnablePeerAccess(peer->device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+        return fail(c, CMG_ECUDA, cudaGetErrorString(e));
+      cudaGetLastError();
+    }
+    for (int col = 0; col < 2; ++col) c->push[col][side] = peer->d_halo[col][1 - side];
+    return CMG_OK;
+  }
+  if (!handle || handle_bytes < (int64_t)sizeof(SlabIpcBlob))
+    return fail(c, CMG_EINVAL, "bad ipc handle");
+  SlabIpcBlob blob;
+  memcpy(&blob, handle, sizeof blob);
+  for (int col = 0; col < 2; ++col) {
+    void *p = nullptr;
+    CU(c, cudaIpcOpenMemHandle(&p, blob.h[col][1 - side], cudaIpcMemLazyEnablePeerAccess));
+    c->ipc_opened.push_back(p);
+    c->push[col][side] = (uint8_t *)p;
+  }
+  return CMG_OK;
+}
+
+int cmg_counters(cmg_context *c, int chain, int64_t *n_pass, int64_t *n_accept, int64_t *n_reject) {
+  NEED(c);
+  if (chain < 0 || chain >= c->n_chains) return fail(c, CMG_EINVAL, "bad chain index");
+  unsigned long long acc = 0;
+  CU(c, cudaMemcpyAsync(&acc, c->d_n_accept + chain, sizeof acc, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  if (n_pass) *n_pass = c->n_pass;
+  if (n_accept) *n_accept = (int64_t)acc;
+  if (n_reject) *n_reject = c->n_pass * c->n_sites - (int64_t)acc;
+  return CMG_OK;
+}
+
+int cmg_reset_counters(cmg_context *c) {
+  NEED(c);
+  CU(c, cudaMemsetAsync(c->d_n_accept, 0, sizeof(unsigned long long) * c->n_chains, c->stream));
+  c->n_pass = 0;
+  return CMG_OK;
+}
+
+// ---- sampling ---------------------------------------------------------------------
+int cmg_sample_now(cmg_context *c, int chain, int64_t *S, int64_t *B) {
+  NEED(c);
+  if (chain < 0 || chain >= c->n_chains) return fail(c, CMG_EINVAL, "bad chain index");
+  int rc = observables_now(c, chain, c->d_scratch_sb);
+  if (rc) return rc;
+  long long sb[2];
+  CU(c, cudaMemcpyAsync(sb, c->d_scratch_sb, sizeof sb, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  if (S) *S = 2 * sb[0] - c->n_sites;
+  if (B) *B = sb[1];
+  return CMG_OK;
+}
+
+int cmg_line_dots(cmg_context *c, int chain, int64_t *row_dots, int64_t *col_dots) {
+  NEED(c);
+  if (chain < 0 || chain >= c->n_chains) return fail(c, CMG_EINVAL, "bad chain index");
+  if (c->dim != 2) return fail(c, CMG_EUNSUPPORTED, "line dots are 2-d only");
+  if (!row_dots || !col_dots) return fail(c, CMG_EINVAL, "null argument");
+  int rc = sync_nat_from_planes(c);
+  if (rc) return rc;
+  long long *d = nullptr;
+  const size_t n = (size_t)(c->shape[0] + c->shape[1]);
+  CU(c, cudaMalloc(&d, sizeof(long long) * n));
+  CU(c, cudaMemsetAsync(d, 0, sizeof(long long) * n, c->stream));
+  k_line_dots<<<nblocks(c->n_sites, 256), 256, 0, c->stream>>>(c->d_nat + chain * c->n_sites,
+                                                               nat_shape(c), d, d + c->shape[0]);
+  ++c->launches;
+  CU(c, cudaGetLastError());
+  CU(c, cudaMemcpyAsync(row_dots, d, sizeof(long long) * c->shape[0], cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaMemcpyAsync(col_dots, d + c->shape[0], sizeof(long long) * c->shape[1],
+                        cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  cudaFree(d);
+  return CMG_OK;
+}
+
+int cmg_n_samples(cmg_context *c, int64_t *n) {
+  if (!c || !n) return fail(c, CMG_EINVAL, "null argument");
+  *n = c->n_samples;
+  return CMG_OK;
+}
+
+int cmg_clear_samples(cmg_context *c) {
+  NEED(c);
+  if (c->d_series)
+    CU(c, cudaMemsetAsync(c->d_series, 0, sizeof(long long) * 2 * (size_t)c->n_chains * c->capacity,
+                          c->stream));
+  c->n_samples = 0;
+  c->dbl_valid = 0;
+  return CMG_OK;
+}
+
+int cmg_read_samples_sb(cmg_context *c, int chain, int64_t first, int64_t count, int64_t *S,
+                        int64_t *B) {
+  NEED(c);
+  if (chain < 0 || chain >= c->n_chains) return fail(c, CMG_EINVAL, "bad chain index");
+  if (first < 0 || count < 0 || first + count > c->n_samples)
+    return fail(c, CMG_EINVAL, "sample range outside the series");
+  if (count == 0) return CMG_OK;
+  std::vector<long long> tmp(2 * (size_t)count);
+  CU(c, cudaMemcpy2DAsync(tmp.data(), sizeof(long long) * 2,
+                          c->d_series + first * 2 * c->n_chains + 2 * chain,
+                          sizeof(long long) * 2 * c->n_chains, sizeof(long long) * 2, (size_t)count,
+                          cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  for (long long i = 0; i < count; ++i) {
+    if (S) S[i] = 2 * tmp[2 * i] - c->n_sites;
+    if (B) B[i] = tmp[2 * i + 1];
+  }
+  return CMG_OK;
+}
+
+// convert new (ones,B) samples of every chain to the three double columns
+static int ensure_doubles(cmg_context *c) {
+  if (c->n_samples == 0) return CMG_OK;
+  if (c->dbl_capacity < c->n_samples) {
+    long long cap = c->dbl_capacity ? c->dbl_capacity : 1024;
+    while (cap < c->n_samples) cap *= 2;
+    cudaFree(c->d_dbl);
+    c->d_dbl = nullptr;
+    CU(c, cudaMalloc(&c->d_dbl, sizeof(double) * 3 * (size_t)cap * c->n_chains));
+    c->dbl_capacity = cap;
+    c->dbl_valid = 0;
+  }
+  if (c->dbl_valid >= c->n_samples) return CMG_OK;
+  const long long first = c->dbl_valid, count = c->n_samples - first;
+  // per chain: gather the strided (ones,B) pairs into a contiguous temp, convert
+  long long *tmp = nullptr;
+  CU(c, cudaMalloc(&tmp, sizeof(long long) * 2 * (size_t)c->n_samples));
+  for (int ch = 0; ch < c->n_chains; ++ch) {
+    CU(c, cudaMemcpy2DAsync(tmp + 2 * first, sizeof(long long) * 2,
+                            c->d_series + first * 2 * c->n_chains + 2 * ch,
+                            sizeof(long long) * 2 * c->n_chains, sizeof(long long) * 2,
+                            (size_t)count, cudaMemcpyDeviceToDevice, c->stream));
+    double *base = c->d_dbl + (size_t)3 * c->dbl_capacity * ch;
+    k_series_to_doubles<<<nblocks(count, 256), 256, 0, c->stream>>>(
+        tmp, first, count, c->n_sites, c->d_tabs + ch, base, base + c->dbl_capacity,
+        base + 2 * c->dbl_capacity);
+    ++c->launches;
+  }
+  CU(c, cudaGetLastError());
+  CU(c, cudaStreamSynchronize(c->stream));
+  cudaFree(tmp);
+  c->dbl_valid = c->n_samples;
+  return CMG_OK;
+}
+
+int cmg_read_samples(cmg_context *c, int chain, int quantity, int64_t first, int64_t count,
+                     double *out) {
+  NEED(c);
+  if (chain < 0 || chain >= c->n_chains) return fail(c, CMG_EINVAL, "bad chain index");
+  if (quantity < 0 || quantity > 2) return fail(c, CMG_EINVAL, "bad quantity");
+  if (first < 0 || count < 0 || first + count > c->n_samples)
+    return fail(c, CMG_EINVAL, "sample range outside the series");
+  if (count == 0) return CMG_OK;
+  if (!out) return fail(c, CMG_EINVAL, "null argument");
+  int rc = ensure_doubles(c);
+  if (rc) return rc;
+  const double *src = c->d_dbl + (size_t)3 * c->dbl_capacity * chain +
+                      (size_t)quantity * c->dbl_capacity + first;
+  CU(c, cudaMemcpyAsync(out, src, sizeof(double) * (size_t)count, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return CMG_OK;
+}
+
+// ---- probes -----------------------------------------------------------------------
+int cmg_delta_e_probe(cmg_context *c, int chain, double *dE_per_site) {
+  NEED(c);
+  if (chain < 0 || chain >= c->n_chains) return fail(c, CMG_EINVAL, "bad chain index");
+  if (!dE_per_site) return fail(c, CMG_EINVAL, "null argument");
+  if (!c->h_tabs[chain].valid) return fail(c, CMG_ESTATE, "conditions not set");
+  if (c->slab) return fail(c, CMG_EUNSUPPORTED, "probe is single-GPU only");
+  int rc = sync_nat_from_planes(c);
+  if (rc) return rc;
+  double *d = nullptr;
+  CU(c, cudaMalloc(&d, sizeof(double) * (size_t)c->n_sites));
+  k_delta_e_probe<<<nblocks(c->n_sites, 256), 256, 0, c->stream>>>(
+      c->d_nat + chain * c->n_sites, nat_shape(c), c->d_tabs + chain, d);
+  ++c->launches;
+  CU(c, cudaGetLastError());
+  CU(c, cudaMemcpyAsync(dE_per_site, d, sizeof(double) * (size_t)c->n_sites, cudaMemcpyDeviceToHost,
+                        c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  cudaFree(d);
+  return CMG_OK;
+}
+
+int cmg_accept_probe(cmg_context *c, int chain, const double *uniforms, uint8_t *accept) {
+  NEED(c);
+  if (chain < 0 || chain >= c->n_chains) return fail(c, CMG_EINVAL, "bad chain index");
+  if (!uniforms || !accept) return fail(c, CMG_EINVAL, "null argument");
+  if (!c->h_tabs[chain].valid) return fail(c, CMG_ESTATE, "conditions not set");
+  if (c->slab) return fail(c, CMG_EUNSUPPORTED, "probe is single-GPU only");
+  int rc = sync_nat_from_planes(c);
+  if (rc) return rc;
+  double *du = nullptr;
+  uint8_t *da = nullptr;
+  CU(c, cudaMalloc(&du, sizeof(double) * (size_t)c->n_sites));
+  CU(c, cudaMalloc(&da, (size_t)c->n_sites));
+  CU(c, cudaMemcpyAsync(du, uniforms, sizeof(double) * (size_t)c->n_sites, cudaMemcpyHostToDevice,
+                        c->stream));
+  k_accept_probe<<<nblocks(c->n_sites, 256), 256, 0, c->stream>>>(
+      c->d_nat + chain * c->n_sites, nat_shape(c), c->d_tabs + chain, du, da);
+  ++c->launches;
+  CU(c, cudaGetLastError());
+  CU(c, cudaMemcpyAsync(accept, da, (size_t)c->n_sites, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  cudaFree(du);
+  cudaFree(da);
+  return CMG_OK;
+}
+
+// ---- series statistics ---------------------------------------------------------------
+static int run_stats_jobs(cmg_context *c, cudaStream_t stream, const std::vector<SeriesJob> &jobs,
+                          double confidence, double *mean, double *prec, double *var,
+                          int64_t *k_star) {
+  const int n = (int)jobs.size();
+  if (n == 0) return CMG_OK;
+  SeriesJob *dj = nullptr;
+  double *dout = nullptr;
+  long long *dk = nullptr;
+  CU(c, cudaMalloc(&dj, sizeof(SeriesJob) * n));
+  CU(c, cudaMalloc(&dout, sizeof(double) * 4 * n));
+  CU(c, cudaMalloc(&dk, sizeof(long long) * n));
+  CU(c, cudaMemcpyAsync(dj, jobs.data(), sizeof(SeriesJob) * n, cudaMemcpyHostToDevice, stream));
+  k_series_stats<<<n, 256, 0, stream>>>(dj, z_confidence(confidence), dout, dk);
+  if (c) ++c->launches;
+  CU(c, cudaGetLastError());
+  std::vector<double> h(4 * (size_t)n);
+  std::vector<long long> hk(n);
+  CU(c, cudaMemcpyAsync(h.data(), dout, sizeof(double) * 4 * n, cudaMemcpyDeviceToHost, stream));
+  CU(c, cudaMemcpyAsync(hk.data(), dk, sizeof(long long) * n, cudaMemcpyDeviceToHost, stream));
+  CU(c, cudaStreamSynchronize(stream));
+  for (int i = 0; i < n; ++i) {
+    if (mean) mean[i] = h[4 * i];
+    if (var) var[i] = h[4 * i + 1];
+    if (prec) prec[i] = h[4 * i + 3];
+    if (k_star) k_star[i] = hk[i];
+  }
+  cudaFree(dj);
+  cudaFree(dout);
+  cudaFree(dk);
+  return CMG_OK;
+}
+
+static int run_equil_jobs(cmg_context *c, cudaStream_t stream, const std::vector<SeriesJob> &jobs,
+                          double prec, int *is_eq, int64_t *n_eq) {
+  const int n = (int)jobs.size();
+  if (n == 0) return CMG_OK;
+  SeriesJob *dj = nullptr;
+  int *de = nullptr;
+  long long *dn = nullptr;
+  CU(c, cudaMalloc(&dj, sizeof(SeriesJob) * n));
+  CU(c, cudaMalloc(&de, sizeof(int) * n));
+  CU(c, cudaMalloc(&dn, sizeof(long long) * n));
+  CU(c, cudaMemcpyAsync(dj, jobs.data(), sizeof(SeriesJob) * n, cudaMemcpyHostToDevice, stream));
+  k_series_equilibration<<<nblocks(n, 32), 32, 0, stream>>>(dj, n, prec, de, dn);
+  if (c) ++c->launches;
+  CU(c, cudaGetLastError());
+  std::vector<int> he(n);
+  std::vector<long long> hn(n);
+  CU(c, cudaMemcpyAsync(he.data(), de, sizeof(int) * n, cudaMemcpyDeviceToHost, stream));
+  CU(c, cudaMemcpyAsync(hn.data(), dn, sizeof(long long) * n, cudaMemcpyDeviceToHost, stream));
+  CU(c, cudaStreamSynchronize(stream));
+  for (int i = 0; i < n; ++i) {
+    if (is_eq) is_eq[i] = he[i];
+    if (n_eq) n_eq[i] = hn[i];
+  }
+  cudaFree(dj);
+  cudaFree(de);
+  cudaFree(dn);
+  return CMG_OK;
+}
+
+static const double *series_ptr(const cmg_context *c, int chain, int quantity) {
+  return c->d_dbl + (size_t)3 * c->dbl_capacity * chain + (size_t)quantity * c->dbl_capacity;
+}
+
+int cmg_series_stats(cmg_context *c, int chain, int quantity, int64_t first, int64_t count,
+                     double confidence, double *mean, double *calculated_precision,
+                     double *variance, int64_t *k_star) {
+  NEED(c);
+  if (chain < 0 || chain >= c->n_chains) return fail(c, CMG_EINVAL, "bad chain index");
+  if (quantity < 0 || quantity > 2) return fail(c, CMG_EINVAL, "bad quantity");
+  if (count <= 0)
+    return fail(c, CMG_EINVAL, "Error in BasicStatisticsCalculator: observations.size()==0");
+  if (first < 0 || first + count > c->n_samples)
+    return fail(c, CMG_EINVAL, "sample range outside the series");
+  int rc = ensure_doubles(c);
+  if (rc) return rc;
+  std::vector<SeriesJob> jobs(1);
+  jobs[0].x = series_ptr(c, chain, quantity) + first;
+  jobs[0].n = count;
+  return run_stats_jobs(c, c->stream, jobs, confidence, mean, calculated_precision, variance, k_star);
+}
+
+int cmg_series_stats_all(cmg_context *c, int quantity, const int64_t *first, int64_t count_total,
+                         double confidence, double *mean, double *calculated_precision,
+                         double *variance, int64_t *k_star) {
+  NEED(c);
+  if (quantity < 0 || quantity > 2) return fail(c, CMG_EINVAL, "bad quantity");
+  if (count_total <= 0 || count_total > c->n_samples)
+    return fail(c, CMG_EINVAL, "sample range outside the series");
+  int rc = ensure_doubles(c);
+  if (rc) return rc;
+  std::vector<SeriesJob> jobs(c->n_chains);
+  for (int ch = 0; ch < c->n_chains; ++ch) {
+    const long long f = first ? first[ch] : 0;
+    if (f < 0 || f > count_total) return fail(c, CMG_EINVAL, "bad first index");
+    jobs[ch].x = series_ptr(c, ch, quantity) + f;
+    jobs[ch].n = count_total - f;
+  }
+  return run_stats_jobs(c, c->stream, jobs, confidence, mean, calculated_precision, variance, k_star);
+}
+
+int cmg_series_equilibration(cmg_context *c, int chain, int quantity, int64_t count,
+                             double abs_precision, int *is_equilibrated, int64_t *n_equil) {
+  NEED(c);
+  if (chain < 0 || chain >= c->n_chains) return fail(c, CMG_EINVAL, "bad chain index");
+  if (quantity < 0 || quantity > 2) return fail(c, CMG_EINVAL, "bad quantity");
+  if (count <= 0) return fail(c, CMG_EINVAL, "Error in equilibration_check: observations.size()==0");
+  if (count > c->n_samples) return fail(c, CMG_EINVAL, "sample range outside the series");
+  int rc = ensure_doubles(c);
+  if (rc) return rc;
+  std::vector<SeriesJob> jobs(1);
+  jobs[0].x = series_ptr(c, chain, quantity);
+  jobs[0].n = count;
+  return run_equil_jobs(c, c->stream, jobs, abs_precision, is_equilibrated, n_equil);
+}
+
+int cmg_series_equilibration_all(cmg_context *c, int quantity, int64_t count, double abs_precision,
+                                 int *is_equilibrated, int64_t *n_equil) {
+  NEED(c);
+  if (quantity < 0 || quantity > 2) return fail(c, CMG_EINVAL, "bad quantity");
+  if (count <= 0 || count > c->n_samples)
+    return fail(c, CMG_EINVAL, "sample range outside the series");
+  int rc = ensure_doubles(c);
+  if (rc) return rc;
+  std::vector<SeriesJob> jobs(c->n_chains);
+  for (int ch = 0; ch < c->n_chains; ++ch) {
+    jobs[ch].x = series_ptr(c, ch, quantity);
+    jobs[ch].n = count;
+  }
+  return run_equil_jobs(c, c->stream, jobs, abs_precision, is_equilibrated, n_equil);
+}
+
+static int device_ok(int device) {
+  int ndev = 0;
+  int rc = cmg_device_count(&ndev);
+  if (rc) return rc;
+  if (ndev == 0) return fail(nullptr, CMG_ENODEVICE, "no CUDA device");
+  if (device < 0 || device >= ndev) return fail(nullptr, CMG_EINVAL, "bad device index");
+  cudaSetDevice(device);
+  return CMG_OK;
+}
+
+int cmg_host_series_stats(int device, const double *x, int64_t n, double confidence, double *mean,
+                          double *calculated_precision, double *variance, int64_t *k_star) {
+  int rc = device_ok(device);
+  if (rc) return rc;
+  if (!x || n <= 0)
+    return fail(nullptr, CMG_EINVAL, "Error in BasicStatisticsCalculator: observations.size()==0");
+  double *d = nullptr;
+  cmg_context *c = nullptr;
+  CU(c, cudaMalloc(&d, sizeof(double) * (size_t)n));
+  CU(c, cudaMemcpy(d, x, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
+  std::vector<SeriesJob> jobs(1);
+  jobs[0].x = d;
+  jobs[0].n = n;
+  rc = run_stats_jobs(nullptr, 0, jobs, confidence, mean, calculated_precision, variance, k_star);
+  cudaFree(d);
+  return rc;
+}
+
+int cmg_host_series_equilibration(int device, const double *x, int64_t n, double abs_precision,
+                                  int *is_equilibrated, int64_t *n_equil) {
+  int rc = device_ok(device);
+  if (rc) return rc;
+  if (!x || n <= 0)
+    return fail(nullptr, CMG_EINVAL, "Error in equilibration_check: observations.size()==0");
+  double *d = nullptr;
+  cmg_context *c = nullptr;
+  CU(c, cudaMalloc(&d, sizeof(double) * (size_t)n));
+  CU(c, cudaMemcpy(d, x, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
+  std::vector<SeriesJob> jobs(1);
+  jobs[0].x = d;
+  jobs[0].n = n;
+  rc = run_equil_jobs(nullptr, 0, jobs, abs_precision, is_equilibrated, n_equil);
+  cudaFree(d);
+  return rc;
+}
+
+// ---- conversions ----------------------------------------------------------------------
+int cmg_conv_l_to_bijk(int device, const int64_t *n3, int64_t n_basis, const int64_t *l,
+                       int64_t count, int64_t *bijk_out) {
+  int rc = device_ok(device);
+  if (rc) return rc;
+  if (!n3 || !l || !bijk_out || count < 0 || n_basis < 1)
+    return fail(nullptr, CMG_EINVAL, "bad argument");
+  if (count == 0) return CMG_OK;
+  const long long total = n3[0] * n3[1] * n3[2] * n_basis;
+  for (int64_t i = 0; i < count; ++i)
+    if (l[i] < 0 || l[i] >= total) return fail(nullptr, CMG_EINVAL, "linear index out of range");
+  cmg_context *c = nullptr;
+  long long *dl = nullptr, *db = nullptr;
+  CU(c, cudaMalloc(&dl, 8 * (size_t)count));
+  CU(c, cudaMalloc(&db, 32 * (size_t)count));
+  CU(c, cudaMemcpy(dl, l, 8 * (size_t)count, cudaMemcpyHostToDevice));
+  k_conv_l_to_bijk<<<nblocks(count, 256), 256>>>(n3[0], n3[1], n3[2], dl, count, db);
+  CU(c, cudaGetLastError());
+  CU(c, cudaMemcpy(bijk_out, db, 32 * (size_t)count, cudaMemcpyDeviceToHost));
+  cudaFree(dl);
+  cudaFree(db);
+  return CMG_OK;
+}
+
+int cmg_conv_bijk_to_l(int device, const int64_t *n3, int64_t n_basis, const int64_t *bijk,
+                       int64_t count, int64_t *l_out) {
+  int rc = device_ok(device);
+  if (rc) return rc;
+  if (!n3 || !bijk || !l_out || count < 0 || n_basis < 1)
+    return fail(nullptr, CMG_EINVAL, "bad argument");
+  if (count == 0) return CMG_OK;
+  for (int64_t i = 0; i < count; ++i)
+    if (bijk[4 * i] < 0 || bijk[4 * i] >= n_basis)
+      return fail(nullptr, CMG_EINVAL, "sublattice index out of range");
+  cmg_context *c = nullptr;
+  long long *dl = nullptr, *db = nullptr;
+  CU(c, cudaMalloc(&dl, 8 * (size_t)count));
+  CU(c, cudaMalloc(&db, 32 * (size_t)count));
+  CU(c, cudaMemcpy(db, bijk, 32 * (size_t)count, cudaMemcpyHostToDevice));
+  k_conv_bijk_to_l<<<nblocks(count, 256), 256>>>(n3[0], n3[1], n3[2], db, count, dl);
+  CU(c, cudaGetLastError());
+  CU(c, cudaMemcpy(l_out, dl, 8 * (size_t)count, cudaMemcpyDeviceToHost));
+  cudaFree(dl);
+  cudaFree(db);
+  return CMG_OK;
+}
+
+// ---- introspection ----------------------------------------------------------------------
+int cmg_launch_count(const cmg_context *c, int64_t *n) {
+  if (!c || !n) return fail(nullptr, CMG_EINVAL, "null argument");
+  *n = c->launches;
+  return CMG_OK;
+}
+
+const char *cmg_kernel_variant(const cmg_context *c) { return c ? c->variant_name.c_str() : ""; }
+
+int cmg_set_kernel_variant(cmg_context *c, const char *name) {
+  NEED(c);
+  if (!name) return fail(c, CMG_EINVAL, "null name");
+  std::string s(name);
+  // "bulk2d:js=8" style suffix sets the strip length
+  c->js = 0;
+  size_t p = s.find(":js=");
+  if (p != std::string::npos) {
+    c->js = atoi(s.c_str() + p + 4);
+    if (c->js < 1) return fail(c, CMG_EINVAL, "bad js");
+    s = s.substr(0, p);
+  }
+  if (s == "auto") c->forced_variant = V_AUTO;
+  else if (s == "generic") c->forced_variant = V_GENERIC;
+  else if (s == "bulk2d") c->forced_variant = V_BULK2D;
+  else if (s == "bulk3d") c->forced_variant = V_BULK3D;
+  else if (s == "smem") c->forced_variant = V_SMEM;
+  else return fail(c, CMG_EINVAL, "unknown kernel variant");
+  return CMG_OK;
+}
+
+}  // extern "C"

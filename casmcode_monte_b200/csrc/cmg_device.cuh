@@ -1,0 +1,1077 @@
+// cmg_device.cuh -- sm_100a kernels of the Ising SGC Metropolis path.
+//
+// Data layout in HBM: every lattice ("chain") is held as
+// two int8 checkerboard colour planes.  A site (i,j,k) has colour
+// c = (i+j+k)&1 and lives in plane c at plane index
+//     q = (i>>1) + h*(j + n1*k),  h = n0/2
+// so i = 2*(q%h) + ((j+k+c)&1).  A plane byte is the occupation index
+// b = (1+s)/2 in {0,1} of the reference's +1/-1 occupation
+// (include/casm/monte/ising_cpp/model.hh:48).  With this layout the 2*dim
+// neighbours of a colour-c site all sit in plane 1-c, at the SAME p for the
+// j/k neighbours and at p and p+-1 for the two i neighbours.
+//
+// The physics is table-driven: for each chain the host builds dE and
+// exp(-dE*beta) for the 2*(2*dim+1) possible (b, n_up) cases with the
+// reference's exact double-precision expression order; kernels index the table
+// with idx = 2*n_up + b.  No floating point is evaluated in the hot kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cmg {
+
+constexpr int kMaxIdx = 14;  // 2*(2*3+1)
+
+struct ChainTables {
+  double dE[16];
+  double prob[16];
+  uint32_t thr_m1[16];  // checkerboard: accept iff philox_u32 <= thr_m1[idx]
+  double J, mu, temperature, beta;
+  int valid;
+  int pad[3];
+};
+
+struct LatticeView {
+  uint8_t *planes;       // chain 0, colour 0
+  long long plane_stride;  // bytes between the two colour planes of a chain
+  long long chain_stride;  // bytes between chains
+  int h, n1, n2, dim;      // h = n0/2 (planes layout)
+  // slab decomposition (2-d): global column index of local column 0 and the
+  // halo columns standing in for local columns -1 and n1.  halo_lo/hi[c] point
+  // at h bytes of plane-c data; null => periodic wrap inside this lattice.
+  long long col_offset;
+  const uint8_t *halo_lo[2];
+  const uint8_t *halo_hi[2];
+  // fused halo push: where to store this slab's freshly updated boundary
+  // columns (the neighbour's halo buffers, possibly peer memory); null => none
+  uint8_t *push_lo[2];  // our column 0      -> low neighbour's halo_hi
+  uint8_t *push_hi[2];  // our column n1-1   -> high neighbour's halo_lo
+};
+
+struct SweepArgs {
+  LatticeView L;
+  const ChainTables *tabs;
+  unsigned long long *n_accept;  // [chain]
+  long long *sb;                 // sample slot of chain 0: {S,B}; null if !SAMPLE
+  long long sb_chain_stride;     // in long long units
+  unsigned long long pass;
+  // Philox round keys k_r = seed + r*(W0,W1), r = 0..9: launch-uniform, so they
+  // are read straight from the kernel-parameter constant bank
+  uint32_t rk[20];
+  int colour;
+  int js;  // columns per thread strip (bulk kernels)
+};
+
+// ---------------------------------------------------------------------------
+// Philox4x32-10 (Salmon, Moraes, Dror, Shaw, SC'11).  Counter-based: the
+// stream is a pure function of (site group, pass, colour, seed, chain), so the
+// trajectory does not depend on launch geometry or on the number of GPUs.
+// ---------------------------------------------------------------------------
+constexpr uint32_t kPhiloxM0 = 0xD2511F53u, kPhiloxM1 = 0xCD9E8D57u;
+constexpr uint32_t kPhiloxW0 = 0x9E3779B9u, kPhiloxW1 = 0xBB67AE85u;
+
+// rk = the ten round-key pairs (key + r*(W0,W1))
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, const uint32_t *rk) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    unsigned long long p0 = (unsigned long long)kPhiloxM0 * c.x;
+    unsigned long long p1 = (unsigned long long)kPhiloxM1 * c.z;
+    uint4 n;
+    n.x = (uint32_t)(p1 >> 32) ^ c.y ^ rk[2 * r];
+    n.y = (uint32_t)p1;
+    n.z = (uint32_t)(p0 >> 32) ^ c.w ^ rk[2 * r + 1];
+    n.w = (uint32_t)p0;
+    c = n;
+  }
+  return c;
+}
+
+// The uniforms of site group `group` (4 consecutive plane indices) of `chain`
+// in half-sweep (pass, colour): counter = {lo32(group), (hi32(group)&0xff) |
+// chain<<8, lo32(pass), hi32(pass)<<1 | colour}, key = seed.
+__device__ __forceinline__ uint4 site_group_random(unsigned long long group,
+                                                   uint32_t chain_word,
+                                                   unsigned long long pass,
+                                                   int colour, const uint32_t *rk) {
+  uint4 c;
+  c.x = (uint32_t)group;
+  c.y = ((uint32_t)(group >> 32) & 0xffu) | chain_word;
+  c.z = (uint32_t)pass;
+  c.w = ((uint32_t)(pass >> 32) << 1) | (uint32_t)colour;
+  return philox4x32_10(c, rk);
+}
+
+// accept mask for 4 sites packed in a word: idx4 holds the table index of each
+// site in its byte, r the four 32-bit uniforms.  Returns 0x01 in the byte of
+// every accepted site (accept iff r <= thr).  The four compares run through the
+// carry flag: thr - r borrows iff the site is rejected, and addc shifts the
+// borrow into a 4-bit mask (2 instructions per site, no predicates/selects).
+__device__ __forceinline__ uint32_t accept_mask4(uint32_t idx4, uint4 r,
+                                                 const uint32_t *thr) {
+  const uint32_t t0 = thr[idx4 & 0xffu];
+  const uint32_t t1 = thr[(idx4 >> 8) & 0xffu];
+  const uint32_t t2 = thr[(idx4 >> 16) & 0xffu];
+  const uint32_t t3 = thr[idx4 >> 24];
+  uint32_t rej;
+  asm("{\n\t"
+      ".reg .u32 d;\n\t"
+      "sub.cc.u32 d, %1, %5;\n\t"
+      "addc.u32 %0, 0, 0;\n\t"
+      "sub.cc.u32 d, %2, %6;\n\t"
+      "addc.u32 %0, %0, %0;\n\t"
+      "sub.cc.u32 d, %3, %7;\n\t"
+      "addc.u32 %0, %0, %0;\n\t"
+      "sub.cc.u32 d, %4, %8;\n\t"
+      "addc.u32 %0, %0, %0;\n\t"
+      "}"
+      : "=r"(rej)
+      : "r"(t3), "r"(t2), "r"(t1), "r"(t0), "r"(r.w), "r"(r.z), "r"(r.y), "r"(r.x));
+  // bit k of rej = site k rejected; spread the 4 bits to the low bit of 4 bytes
+  const uint32_t rej_bytes = (rej * 0x00204081u) & 0x01010101u;
+  return rej_bytes ^ 0x01010101u;
+}
+
+// sum of the four bytes of a word
+__device__ __forceinline__ int bytesum(uint32_t w) {
+  return (int)__dp4a(w, 0x01010101u, 0u);
+}
+
+// block-wide sums -> one atomic per CTA and quantity
+template <int NT>
+__device__ __forceinline__ void block_accumulate(unsigned int acc, long long s_ones,
+                                                 long long bsum, bool sample,
+                                                 unsigned long long *n_accept,
+                                                 long long *sb) {
+  __shared__ unsigned int sh_acc[NT / 32];
+  __shared__ long long sh_s[NT / 32];
+  __shared__ long long sh_b[NT / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  acc = __reduce_add_sync(0xffffffffu, acc);
+  if (sample) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s_ones += __shfl_xor_sync(0xffffffffu, s_ones, o);
+      bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
+    }
+  }
+  if (lane == 0) {
+    sh_acc[warp] = acc;
+    sh_s[warp] = s_ones;
+    sh_b[warp] = bsum;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long a = 0;
+    long long s = 0, b = 0;
+#pragma unroll
+    for (int w = 0; w < NT / 32; ++w) {
+      a += sh_acc[w];
+      s += sh_s[w];
+      b += sh_b[w];
+    }
+    if (a) atomicAdd(n_accept, a);
+    if (sample) {
+      atomicAdd((unsigned long long *)&sb[0], (unsigned long long)s);
+      atomicAdd((unsigned long long *)&sb[1], (unsigned long long)b);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// k_halfsweep_generic: any even extents, 2-d or 3-d.  One thread per group of
+// four consecutive plane indices (one Philox call).  Byte accesses; this is the
+// correctness baseline the tuned kernels are cross-checked against.
+//
+// SAMPLE: the launch is the colour-1 half-sweep that completes a sampled pass;
+// it accumulates ones(plane0)+ones(plane1) and B = sum over colour-1 sites of
+// s*(sum of neighbour s) (every bond joins the two colours exactly once).
+// The host turns ones into S = 2*ones - N.
+// ---------------------------------------------------------------------------
+template <bool SAMPLE>
+__global__ void __launch_bounds__(128) k_halfsweep_generic(SweepArgs A) {
+  const LatticeView &L = A.L;
+  const int chain = blockIdx.y;
+  __shared__ uint32_t s_thr[16];
+  if (threadIdx.x < 16) s_thr[threadIdx.x] = A.tabs[chain].thr_m1[threadIdx.x];
+  __syncthreads();
+
+  uint8_t *C = L.planes + (long long)chain * L.chain_stride +
+               (long long)A.colour * L.plane_stride;
+  const uint8_t *O = L.planes + (long long)chain * L.chain_stride +
+                     (long long)(1 - A.colour) * L.plane_stride;
+  const long long plane_size = (long long)L.h * L.n1 * L.n2;
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int z = 2 * L.dim;
+
+  unsigned int acc = 0;
+  long long ones = 0, bsum = 0;
+  if (4 * g < plane_size) {
+    uint4 r4 = site_group_random((unsigned long long)g, (uint32_t)chain << 8, A.pass,
+                                 A.colour, A.rk);
+    const uint32_t rr[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const long long q = 4 * g + w;
+      if (q >= plane_size) break;
+      const int p = (int)(q % L.h);
+      const long long jk = q / L.h;
+      const int j = (int)(jk % L.n1);
+      const int k = (int)(jk / L.n1);
+      const int par = (j + k + A.colour) & 1;  // i = 2p + par
+      const int jm = (j == 0) ? L.n1 - 1 : j - 1, jp = (j == L.n1 - 1) ? 0 : j + 1;
+      const long long rowk = (long long)L.n1 * k;
+      int n_up = O[p + (long long)L.h * (jm + rowk)] + O[p + (long long)L.h * (jp + rowk)] +
+                 O[p + (long long)L.h * (j + rowk)];
+      // the other i-neighbour: p-1 if i even, p+1 if i odd (periodic in p)
+      const int ps = par ? ((p == L.h - 1) ? 0 : p + 1) : ((p == 0) ? L.h - 1 : p - 1);
+      n_up += O[ps + (long long)L.h * (j + rowk)];
+      if (L.dim == 3) {
+        const int km = (k == 0) ? L.n2 - 1 : k - 1, kp = (k == L.n2 - 1) ? 0 : k + 1;
+        n_up += O[p + (long long)L.h * (j + (long long)L.n1 * km)] +
+                O[p + (long long)L.h * (j + (long long)L.n1 * kp)];
+      }
+      int b = C[q];
+      if (rr[w] <= s_thr[2 * n_up + b]) {
+        b ^= 1;
+        C[q] = (uint8_t)b;
+        ++acc;
+      }
+      if (SAMPLE) {
+        ones += b + O[q];
+        bsum += (2 * b - 1) * (2 * n_up - z);
+      }
+    }
+  }
+  block_accumulate<128>(acc, ones, bsum, SAMPLE, A.n_accept + chain,
+                        SAMPLE ? A.sb + (long long)chain * A.sb_chain_stride : nullptr);
+}
+
+// ---------------------------------------------------------------------------
+// k_halfsweep_bulk2d: the production 2-d kernel.  Requires n0 % 32 == 0 (so a
+// plane column is a whole number of 16-byte vectors) and n1 even.
+//
+// A thread owns one 16-byte vector (16 same-colour sites, consecutive p) and
+// walks a strip of `js` columns.  The three opposite-colour columns j-1, j,
+// j+1 needed by column j are kept in registers as a rolling window, so moving
+// to the next column costs one 16-byte load of the opposite plane, one of the
+// own plane, one byte for the p+-1 neighbour across the vector edge, and one
+// 16-byte store: 3 B of traffic per attempted flip.  Neighbour counts are
+// formed four sites at a time with plain 32-bit adds (bytes are 0/1, sums <= 4
+// never carry).  Four Philox calls give the 16 uniforms.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ld16(const uint8_t *p) {
+  return *reinterpret_cast<const uint4 *>(p);
+}
+__device__ __forceinline__ uint4 ld16_nc(const uint8_t *p) {
+  return __ldg(reinterpret_cast<const uint4 *>(p));
+}
+
+// out byte k = in byte k-1, byte 0 <- lo (a single byte value)
+__device__ __forceinline__ uint4 shift_up_1(uint4 v, uint32_t lo) {
+  uint4 o;
+  o.x = (v.x << 8) | lo;
+  o.y = __funnelshift_l(v.x, v.y, 8);
+  o.z = __funnelshift_l(v.y, v.z, 8);
+  o.w = __funnelshift_l(v.z, v.w, 8);
+  return o;
+}
+// out byte k = in byte k+1, byte 15 <- hi
+__device__ __forceinline__ uint4 shift_down_1(uint4 v, uint32_t hi) {
+  uint4 o;
+  o.x = __funnelshift_r(v.x, v.y, 8);
+  o.y = __funnelshift_r(v.y, v.z, 8);
+  o.z = __funnelshift_r(v.z, v.w, 8);
+  o.w = (v.w >> 8) | (hi << 24);
+  return o;
+}
+
+struct Accum {
+  unsigned int acc;
+  int ones;
+  int bsum;
+};
+
+// update 16 sites; returns new centre vector
+template <bool SAMPLE>
+__device__ __forceinline__ uint4 update16(uint4 ce, uint4 om, uint4 oc, uint4 op,
+                                          uint4 side, unsigned long long group0,
+                                          unsigned long long pass, int colour,
+                                          uint32_t chain_word, const uint32_t *rk,
+                                          const uint32_t *s_thr, int z,
+                                          Accum &a) {
+  uint32_t cw[4] = {ce.x, ce.y, ce.z, ce.w};
+  const uint32_t nw[4] = {om.x + oc.x + op.x + side.x, om.y + oc.y + op.y + side.y,
+                          om.z + oc.z + op.z + side.z, om.w + oc.w + op.w + side.w};
+  const uint32_t ow[4] = {oc.x, oc.y, oc.z, oc.w};
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    const uint4 r = site_group_random(group0 + w, chain_word, pass, colour, rk);
+    const uint32_t idx4 = nw[w] + nw[w] + cw[w];
+    const uint32_t m = accept_mask4(idx4, r, s_thr);
+    cw[w] ^= m;
+    a.acc += __popc(m);
+    if (SAMPLE) {
+      // ones of both planes; B = sum (2b-1)(2n-z) = 4*sum_{b=1} n - 2*sum n - z*(2*ones_c - 4)
+      const uint32_t sel = nw[w] & (cw[w] * 0xffu);
+      const int c1 = bytesum(cw[w]);
+      a.ones += c1 + bytesum(ow[w]);
+      a.bsum += 4 * bytesum(sel) - 2 * bytesum(nw[w]) - z * (2 * c1 - 4);
+    }
+  }
+  return make_uint4(cw[0], cw[1], cw[2], cw[3]);
+}
+
+template <bool SAMPLE>
+__global__ void __launch_bounds__(128) k_halfsweep_bulk2d(SweepArgs A) {
+  const LatticeView &L = A.L;
+  const int chain = blockIdx.y;
+  __shared__ uint32_t s_thr[16];
+  if (threadIdx.x < 16) s_thr[threadIdx.x] = A.tabs[chain].thr_m1[threadIdx.x];
+  __syncthreads();
+
+  const int h = L.h, n1 = L.n1;
+  const int V = h >> 4;  // 16-byte vectors per column
+  const int n_strips = (n1 + A.js - 1) / A.js;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  Accum acc = {0u, 0, 0};
+
+  if (t < (long long)V * n_strips) {
+    const int v = (int)(t % V);
+    const int strip = (int)(t / V);
+    const int p0 = v << 4;
+    const int jbeg = strip * A.js;
+    const int jend = min(jbeg + A.js, n1);
+    uint8_t *C = L.planes + (long long)chain * L.chain_stride +
+                 (long long)A.colour * L.plane_stride;
+    const uint8_t *O = L.planes + (long long)chain * L.chain_stride +
+                       (long long)(1 - A.colour) * L.plane_stride;
+    const uint8_t *halo_lo = L.halo_lo[1 - A.colour];
+    const uint8_t *halo_hi = L.halo_hi[1 - A.colour];
+    uint8_t *push_lo = L.push_lo[A.colour];
+    uint8_t *push_hi = L.push_hi[A.colour];
+    const uint32_t chain_word = (uint32_t)chain << 8;
+
+    // column pointer of the opposite plane with periodic wrap / halo
+    auto ocol = [&](int j) -> const uint8_t * {
+      if (j < 0) return halo_lo ? halo_lo : O + (long long)h * (n1 - 1);
+      if (j >= n1) return halo_hi ? halo_hi : O;
+      return O + (long long)h * j;
+    };
+
+    uint4 om = ld16_nc(ocol(jbeg - 1) + p0);
+    uint4 oc = ld16_nc(ocol(jbeg) + p0);
+    const int p_below = (p0 == 0) ? h - 1 : p0 - 1;
+    const int p_above = (p0 + 16 == h) ? 0 : p0 + 16;
+
+    for (int j = jbeg; j < jend; ++j) {
+      const uint4 op = ld16_nc(ocol(j + 1) + p0);
+      const uint4 ce = ld16(C + (long long)h * j + p0);
+      const long long jg = (long long)j + L.col_offset;
+      const int par = (int)((jg + A.colour) & 1);  // i = 2p + par
+      const uint8_t *ocj = O + (long long)h * j;
+      uint4 side;
+      if (par == 0) {
+        side = shift_up_1(oc, __ldg(ocj + p_below));  // neighbour i-1 -> p-1
+      } else {
+        side = shift_down_1(oc, __ldg(ocj + p_above));  // neighbour i+1 -> p+1
+      }
+      const unsigned long long group0 =
+          (unsigned long long)(((long long)h * jg + p0) >> 2);
+      const uint4 cn = update16<SAMPLE>(ce, om, oc, op, side, group0, A.pass,
+                                        A.colour, chain_word, A.rk, s_thr, 4, acc);
+      *reinterpret_cast<uint4 *>(C + (long long)h * j + p0) = cn;
+      if (push_lo && j == 0) *reinterpret_cast<uint4 *>(push_lo + p0) = cn;
+      if (push_hi && j == n1 - 1) *reinterpret_cast<uint4 *>(push_hi + p0) = cn;
+      om = oc;
+      oc = op;
+    }
+  }
+  block_accumulate<128>(acc.acc, (long long)acc.ones, (long long)acc.bsum, SAMPLE,
+                        A.n_accept + chain,
+                        SAMPLE ? A.sb + (long long)chain * A.sb_chain_stride : nullptr);
+}
+
+// ---------------------------------------------------------------------------
+// k_halfsweep_bulk3d: 3-d simple cubic, n0 % 32 == 0, n1 and n2 even.
+// Same scheme; the strip runs along j inside one k-layer, the k+-1 neighbours
+// are two extra 16-byte loads per column (served by L2: a k-layer of 512^3 is
+// 128 KiB per colour).
+// ---------------------------------------------------------------------------
+template <bool SAMPLE>
+__global__ void __launch_bounds__(128) k_halfsweep_bulk3d(SweepArgs A) {
+  const LatticeView &L = A.L;
+  const int chain = blockIdx.y;
+  __shared__ uint32_t s_thr[16];
+  if (threadIdx.x < 16) s_thr[threadIdx.x] = A.tabs[chain].thr_m1[threadIdx.x];
+  __syncthreads();
+
+  const int h = L.h, n1 = L.n1, n2 = L.n2;
+  const int V = h >> 4;
+  const int n_strips = (n1 + A.js - 1) / A.js;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  Accum acc = {0u, 0, 0};
+
+  if (t < (long long)V * n_strips * n2) {
+    const int v = (int)(t % V);
+    const long long t2 = t / V;
+    const int strip = (int)(t2 % n_strips);
+    const int k = (int)(t2 / n_strips);
+    const int p0 = v << 4;
+    const int jbeg = strip * A.js;
+    const int jend = min(jbeg + A.js, n1);
+    const long long layer = (long long)h * n1;
+    uint8_t *C = L.planes + (long long)chain * L.chain_stride +
+                 (long long)A.colour * L.plane_stride + layer * k;
+    const uint8_t *Oall = L.planes + (long long)chain * L.chain_stride +
+                          (long long)(1 - A.colour) * L.plane_stride;
+    const uint8_t *O = Oall + layer * k;
+    const uint8_t *Okm = Oall + layer * ((k == 0) ? n2 - 1 : k - 1);
+    const uint8_t *Okp = Oall + layer * ((k == n2 - 1) ? 0 : k + 1);
+    const uint32_t chain_word = (uint32_t)chain << 8;
+
+    auto wrapj = [&](int j) { return (j < 0) ? n1 - 1 : (j >= n1 ? 0 : j); };
+    uint4 om = ld16_nc(O + (long long)h * wrapj(jbeg - 1) + p0);
+    uint4 oc = ld16_nc(O + (long long)h * jbeg + p0);
+    const int p_below = (p0 == 0) ? h - 1 : p0 - 1;
+    const int p_above = (p0 + 16 == h) ? 0 : p0 + 16;
+
+    for (int j = jbeg; j < jend; ++j) {
+      const long long off = (long long)h * j + p0;
+      const uint4 op = ld16_nc(O + (long long)h * wrapj(j + 1) + p0);
+      const uint4 ka = ld16_nc(Okm + off);
+      const uint4 kb = ld16_nc(Okp + off);
+      const uint4 ce = ld16(C + off);
+      const int par = (j + k + A.colour) & 1;
+      const uint8_t *ocj = O + (long long)h * j;
+      uint4 side;
+      if (par == 0) {
+        side = shift_up_1(oc, __ldg(ocj + p_below));
+      } else {
+        side = shift_down_1(oc, __ldg(ocj + p_above));
+      }
+      // fold the two k-neighbours into the "side" word: sums stay <= 6
+      side.x += ka.x + kb.x;
+      side.y += ka.y + kb.y;
+      side.z += ka.z + kb.z;
+      side.w += ka.w + kb.w;
+      const unsigned long long group0 =
+          (unsigned long long)((layer * k + off) >> 2);
+      const uint4 cn = update16<SAMPLE>(ce, om, oc, op, side, group0, A.pass,
+                                        A.colour, chain_word, A.rk, s_thr, 6, acc);
+      *reinterpret_cast<uint4 *>(C + off) = cn;
+      om = oc;
+      oc = op;
+    }
+  }
+  block_accumulate<128>(acc.acc, (long long)acc.ones, (long long)acc.bsum, SAMPLE,
+                        A.n_accept + chain,
+                        SAMPLE ? A.sb + (long long)chain * A.sb_chain_stride : nullptr);
+}
+
+// ---------------------------------------------------------------------------
+// Natural-order helpers.  "Natural" = one int8 b per site in the reference's
+// linear order l = i + n0*(j + n1*k) (model.hh:82-99); used at the API edge,
+// by the probes and by the serial reference mode, and as the only layout for
+// lattices with an odd extent (which cannot be two-coloured periodically).
+// ---------------------------------------------------------------------------
+struct NaturalShape {
+  int n0, n1, n2, dim;
+  long long n_sites;
+};
+
+__device__ __forceinline__ long long plane_addr(const NaturalShape &s, long long l,
+                                                long long plane_stride) {
+  const int i = (int)(l % s.n0);
+  const long long r = l / s.n0;
+  const int j = (int)(r % s.n1);
+  const int k = (int)(r / s.n1);
+  const int c = (i + j + k) & 1;
+  return (long long)c * plane_stride + (i >> 1) +
+         (long long)(s.n0 >> 1) * (j + (long long)s.n1 * k);
+}
+
+// int32 (+1/-1, natural) -> planes ; flags any value that is not +-1
+__global__ void k_i32_to_planes(const int32_t *__restrict__ src, uint8_t *planes,
+                                long long plane_stride, NaturalShape s, int *bad) {
+  const long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= s.n_sites) return;
+  const int v = src[l];
+  if (v != 1 && v != -1) atomicExch(bad, 1);
+  planes[plane_addr(s, l, plane_stride)] = (uint8_t)(v > 0);
+}
+__global__ void k_planes_to_i32(const uint8_t *__restrict__ planes,
+                                long long plane_stride, int32_t *dst, NaturalShape s) {
+  const long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= s.n_sites) return;
+  dst[l] = planes[plane_addr(s, l, plane_stride)] ? 1 : -1;
+}
+__global__ void k_i32_to_natural(const int32_t *__restrict__ src, uint8_t *nat,
+                                 long long n, int *bad) {
+  const long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= n) return;
+  const int v = src[l];
+  if (v != 1 && v != -1) atomicExch(bad, 1);
+  nat[l] = (uint8_t)(v > 0);
+}
+__global__ void k_natural_to_i32(const uint8_t *__restrict__ nat, int32_t *dst,
+                                 long long n) {
+  const long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= n) return;
+  dst[l] = nat[l] ? 1 : -1;
+}
+__global__ void k_planes_to_natural(const uint8_t *__restrict__ planes,
+                                    long long plane_stride, uint8_t *nat,
+                                    NaturalShape s) {
+  const long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= s.n_sites) return;
+  nat[l] = planes[plane_addr(s, l, plane_stride)];
+}
+__global__ void k_natural_to_planes(const uint8_t *__restrict__ nat, uint8_t *planes,
+                                    long long plane_stride, NaturalShape s) {
+  const long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= s.n_sites) return;
+  planes[plane_addr(s, l, plane_stride)] = nat[l];
+}
+__global__ void k_fill_bytes(uint8_t *dst, long long n, uint8_t v) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = v;
+}
+// synthetic input: i.i.d. b with P(b=1) = p_up, keyed on the natural index
+__global__ void k_randomize_natural(uint8_t *nat, long long n, unsigned long long seed,
+                                    uint32_t thr_m1, int always) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (4 * g >= n) return;
+  uint32_t rk[20];
+  for (int i = 0; i < 10; ++i) {
+    rk[2 * i] = (uint32_t)seed + i * kPhiloxW0;
+    rk[2 * i + 1] = (uint32_t)(seed >> 32) + i * kPhiloxW1;
+  }
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)g, (uint32_t)(g >> 32), 0x5EEDu, 0u), rk);
+  const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+  for (int w = 0; w < 4; ++w)
+    if (4 * g + w < n) nat[4 * g + w] = (uint8_t)(always || rr[w] <= thr_m1);
+}
+
+// neighbour count and own occupation of site l, natural layout
+__device__ __forceinline__ int natural_n_up(const uint8_t *nat, const NaturalShape &s,
+                                            long long l) {
+  const int i = (int)(l % s.n0);
+  const long long r = l / s.n0;
+  const int j = (int)(r % s.n1);
+  const int k = (int)(r / s.n1);
+  const long long base = (long long)s.n0 * (j + (long long)s.n1 * k);
+  const int ip = (i + 1 == s.n0) ? 0 : i + 1, im = (i == 0) ? s.n0 - 1 : i - 1;
+  const int jp = (j + 1 == s.n1) ? 0 : j + 1, jm = (j == 0) ? s.n1 - 1 : j - 1;
+  const long long kk = (long long)s.n1 * k;
+  int n = nat[base + ip] + nat[base + im] + nat[i + (long long)s.n0 * (jp + kk)] +
+          nat[i + (long long)s.n0 * (jm + kk)];
+  if (s.dim == 3) {
+    const int kp = (k + 1 == s.n2) ? 0 : k + 1, km = (k == 0) ? s.n2 - 1 : k - 1;
+    n += nat[i + (long long)s.n0 * (j + (long long)s.n1 * kp)] +
+         nat[i + (long long)s.n0 * (j + (long long)s.n1 * km)];
+  }
+  return n;
+}
+
+// Integer observables from the natural layout:
+// ones = #(+1), B = sum_l s_l*(s_{+i} + s_{+j} [+ s_{+k}])   (model.hh:266-270)
+__global__ void __launch_bounds__(256) k_observables_natural(const uint8_t *__restrict__ nat,
+                                                             NaturalShape s,
+                                                             long long *out /* {ones,B} */) {
+  long long ones = 0, bsum = 0;
+  for (long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x; l < s.n_sites;
+       l += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(l % s.n0);
+    const long long r = l / s.n0;
+    const int j = (int)(r % s.n1);
+    const int k = (int)(r / s.n1);
+    const int b = nat[l];
+    const int ip = (i + 1 == s.n0) ? 0 : i + 1;
+    const int jp = (j + 1 == s.n1) ? 0 : j + 1;
+    int nb = (2 * nat[ip + (long long)s.n0 * (j + (long long)s.n1 * k)] - 1) +
+             (2 * nat[i + (long long)s.n0 * (jp + (long long)s.n1 * k)] - 1);
+    if (s.dim == 3) {
+      const int kp = (k + 1 == s.n2) ? 0 : k + 1;
+      nb += 2 * nat[i + (long long)s.n0 * (j + (long long)s.n1 * kp)] - 1;
+    }
+    ones += b;
+    bsum += (2 * b - 1) * nb;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ones += __shfl_xor_sync(0xffffffffu, ones, o);
+    bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
+  }
+  __shared__ long long sh[2][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) {
+    sh[0][warp] = ones;
+    sh[1][warp] = bsum;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long a = 0, b = 0;
+    for (int w = 0; w < 8; ++w) {
+      a += sh[0][w];
+      b += sh[1][w];
+    }
+    atomicAdd((unsigned long long *)&out[0], (unsigned long long)a);
+    atomicAdd((unsigned long long *)&out[1], (unsigned long long)b);
+  }
+}
+
+// Integer observables straight from the colour planes (even extents): one
+// thread per 4 plane indices of colour 1.
+__global__ void __launch_bounds__(256) k_observables_planes(LatticeView L, int chain,
+                                                            long long *out) {
+  const uint8_t *C = L.planes + (long long)chain * L.chain_stride + L.plane_stride;
+  const uint8_t *O = L.planes + (long long)chain * L.chain_stride;
+  const long long plane_size = (long long)L.h * L.n1 * L.n2;
+  const int z = 2 * L.dim;
+  long long ones = 0, bsum = 0;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < plane_size;
+       q += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(q % L.h);
+    const long long jk = q / L.h;
+    const int j = (int)(jk % L.n1);
+    const int k = (int)(jk / L.n1);
+    const int par = (j + k + 1) & 1;
+    const int jm = (j == 0) ? L.n1 - 1 : j - 1, jp = (j == L.n1 - 1) ? 0 : j + 1;
+    const long long rowk = (long long)L.n1 * k;
+    const uint8_t *lo = (L.halo_lo[0] && j == 0) ? L.halo_lo[0] + p : O + p + (long long)L.h * (jm + rowk);
+    const uint8_t *hi = (L.halo_hi[0] && j == L.n1 - 1) ? L.halo_hi[0] + p : O + p + (long long)L.h * (jp + rowk);
+    int n_up = *lo + *hi + O[p + (long long)L.h * (j + rowk)];
+    const int ps = par ? ((p == L.h - 1) ? 0 : p + 1) : ((p == 0) ? L.h - 1 : p - 1);
+    n_up += O[ps + (long long)L.h * (j + rowk)];
+    if (L.dim == 3) {
+      const int km = (k == 0) ? L.n2 - 1 : k - 1, kp = (k == L.n2 - 1) ? 0 : k + 1;
+      n_up += O[p + (long long)L.h * (j + (long long)L.n1 * km)] +
+              O[p + (long long)L.h * (j + (long long)L.n1 * kp)];
+    }
+    const int b = C[q];
+    ones += b + O[q];
+    bsum += (2 * b - 1) * (2 * n_up - z);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ones += __shfl_xor_sync(0xffffffffu, ones, o);
+    bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
+  }
+  __shared__ long long sh[2][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) {
+    sh[0][warp] = ones;
+    sh[1][warp] = bsum;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long a = 0, b = 0;
+    for (int w = 0; w < 8; ++w) {
+      a += sh[0][w];
+      b += sh[1][w];
+    }
+    atomicAdd((unsigned long long *)&out[0], (unsigned long long)a);
+    atomicAdd((unsigned long long *)&out[1], (unsigned long long)b);
+  }
+}
+
+// use_nlist=false energy form (model.hh:273-285): integer dot products of each
+// "row" i with row i+1 and of each "column" j with column j+1 (2-d, natural).
+__global__ void k_line_dots(const uint8_t *__restrict__ nat, NaturalShape s,
+                            long long *row_dots, long long *col_dots) {
+  const long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= s.n_sites) return;
+  const int i = (int)(l % s.n0);
+  const int j = (int)(l / s.n0);
+  const int sv = 2 * nat[l] - 1;
+  const int ip = (i + 1 == s.n0) ? 0 : i + 1;
+  const int jp = (j + 1 == s.n1) ? 0 : j + 1;
+  const int right = 2 * nat[ip + (long long)s.n0 * j] - 1;
+  const int down = 2 * nat[i + (long long)s.n0 * jp] - 1;
+  atomicAdd((unsigned long long *)&row_dots[i], (unsigned long long)(long long)(sv * right));
+  atomicAdd((unsigned long long *)&col_dots[j], (unsigned long long)(long long)(sv * down));
+}
+
+// ---------------------------------------------------------------------------
+// Parity probes (natural layout).  dE_per_site[l] = table dE of flipping l;
+// accept[l] = (dE < 0) || (u[l] < exp(-dE*beta))   (methods/metropolis.hh:28-34)
+// ---------------------------------------------------------------------------
+__global__ void k_delta_e_probe(const uint8_t *__restrict__ nat, NaturalShape s,
+                                const ChainTables *tab, double *dE) {
+  const long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= s.n_sites) return;
+  dE[l] = tab->dE[2 * natural_n_up(nat, s, l) + nat[l]];
+}
+__global__ void k_accept_probe(const uint8_t *__restrict__ nat, NaturalShape s,
+                               const ChainTables *tab, const double *__restrict__ u,
+                               uint8_t *accept) {
+  const long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= s.n_sites) return;
+  const int idx = 2 * natural_n_up(nat, s, l) + nat[l];
+  const double d = tab->dE[idx];
+  bool a = d < 0.0;
+  if (!a) a = u[l] < tab->prob[idx];
+  accept[l] = a ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------
+// Serial reference mode.  One thread per chain walks the reference's loop
+// (methods/basic_occupation_metropolis.hh:381-404) on the reference's random
+// stream: std::mt19937_64, libstdc++-13 uniform_int_distribution<long>(0,N-1)
+// (Lemire's nearly-divisionless method on 64-bit words) for the site, and
+// generate_canonical<double,53> for the acceptance draw, drawn only when
+// dE >= 0.  S and B are tracked incrementally (exact integers) and written to
+// the sample series at the sampled pass boundaries.
+// ---------------------------------------------------------------------------
+struct MT64State {
+  unsigned long long x[312];
+  int pos;
+  int pad;
+};
+
+__device__ __forceinline__ void mt64_twist(unsigned long long *x) {
+  constexpr unsigned long long UPPER = 0xFFFFFFFF80000000ull, LOWER = 0x7FFFFFFFull;
+  constexpr unsigned long long A = 0xB5026F5AA96619E9ull;
+  for (int k = 0; k < 312 - 156; ++k) {
+    unsigned long long y = (x[k] & UPPER) | (x[k + 1] & LOWER);
+    x[k] = x[k + 156] ^ (y >> 1) ^ ((y & 1ull) ? A : 0ull);
+  }
+  for (int k = 312 - 156; k < 311; ++k) {
+    unsigned long long y = (x[k] & UPPER) | (x[k + 1] & LOWER);
+    x[k] = x[k + (156 - 312)] ^ (y >> 1) ^ ((y & 1ull) ? A : 0ull);
+  }
+  unsigned long long y = (x[311] & UPPER) | (x[0] & LOWER);
+  x[311] = x[155] ^ (y >> 1) ^ ((y & 1ull) ? A : 0ull);
+}
+__device__ __forceinline__ unsigned long long mt64_next(unsigned long long *x, int &pos) {
+  if (pos >= 312) {
+    mt64_twist(x);
+    pos = 0;
+  }
+  unsigned long long z = x[pos++];
+  z ^= (z >> 29) & 0x5555555555555555ull;
+  z ^= (z << 17) & 0x71D67FFFEDA60000ull;
+  z ^= (z << 37) & 0xFFF7EEE000000000ull;
+  z ^= (z >> 43);
+  return z;
+}
+// libstdc++ 13 bits/uniform_int_dist.h:252-281 (_S_nd with 128-bit products),
+// range = maximum_value + 1 (must be < 2^64)
+__device__ __forceinline__ unsigned long long mt64_uniform_int(unsigned long long *x,
+                                                               int &pos,
+                                                               unsigned long long range) {
+  unsigned long long u = mt64_next(x, pos);
+  unsigned long long low = u * range;
+  unsigned long long high = __umul64hi(u, range);
+  if (low < range) {
+    const unsigned long long threshold = (0ull - range) % range;
+    while (low < threshold) {
+      u = mt64_next(x, pos);
+      low = u * range;
+      high = __umul64hi(u, range);
+    }
+  }
+  return high;
+}
+// libstdc++ 13 bits/random.tcc:3349-3381 (one 64-bit draw for 53 bits), then
+// uniform_real_distribution: r*(b-a)+a  (bits/random.h:1904-1910)
+__device__ __forceinline__ double mt64_uniform_real(unsigned long long *x, int &pos,
+                                                    double maximum_value) {
+  const unsigned long long u = mt64_next(x, pos);
+  double r = __ddiv_rn(__ull2double_rn(u), 18446744073709551616.0);
+  if (r >= 1.0) r = 0.99999999999999988897769753748434595763683319091796875;
+  return __dadd_rn(__dmul_rn(r, __dsub_rn(maximum_value, 0.0)), 0.0);
+}
+
+struct SerialArgs {
+  uint8_t *nat;             // [chain][n_sites]
+  NaturalShape shape;
+  const ChainTables *tabs;
+  MT64State *engines;       // [chain]
+  unsigned long long *n_accept;  // [chain]
+  long long *cur_sb;        // [chain][2] current {ones, B}, updated in place
+  long long *series;        // chain 0 sample slot base {ones,B}; may be null
+  long long series_chain_stride;
+  long long n_passes;
+  long long sample_period;  // 0 = never
+  long long pass_base;      // passes already done (for the sample schedule)
+  int use_smem;             // lattice staged in shared memory
+};
+
+__global__ void __launch_bounds__(128) k_serial_reference(SerialArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int chain = blockIdx.x;
+  unsigned long long *mt = reinterpret_cast<unsigned long long *>(smem_raw);
+  uint8_t *lat_s = smem_raw + 312 * sizeof(unsigned long long);
+  const NaturalShape s = A.shape;
+  uint8_t *nat_g = A.nat + (long long)chain * s.n_sites;
+  MT64State *eng = A.engines + chain;
+
+  for (int i = threadIdx.x; i < 312; i += blockDim.x) mt[i] = eng->x[i];
+  if (A.use_smem)
+    for (long long i = threadIdx.x; i < s.n_sites; i += blockDim.x) lat_s[i] = nat_g[i];
+  __syncthreads();
+
+  if (threadIdx.x == 0) {
+    uint8_t *nat = A.use_smem ? lat_s : nat_g;
+    const ChainTables *tab = A.tabs + chain;
+    int pos = eng->pos;
+    long long ones = A.cur_sb[2 * chain], B = A.cur_sb[2 * chain + 1];
+    unsigned long long n_acc = 0;
+    const int z = 2 * s.dim;
+    long long slot = 0;
+    for (long long pass = 0; pass < A.n_passes; ++pass) {
+      for (long long step = 0; step < s.n_sites; ++step) {
+        const long long l =
+            (long long)mt64_uniform_int(mt, pos, (unsigned long long)s.n_sites);
+        const int n_up = natural_n_up(nat, s, l);
+        const int b = nat[l];
+        const int idx = 2 * n_up + b;
+        const double dE = tab->dE[idx];
+        bool accept = dE < 0.0;
+        if (!accept) {
+          const double u = mt64_uniform_real(mt, pos, 1.0);
+          accept = u < tab->prob[idx];
+        }
+        if (accept) {
+          nat[l] = (uint8_t)(b ^ 1);
+          ++n_acc;
+          const int ds = -2 * (2 * b - 1);  // new - old
+          ones += b ? -1 : 1;
+          B += (long long)ds * (2 * n_up - z);
+        }
+      }
+      if (A.sample_period > 0 && A.series &&
+          ((A.pass_base + pass + 1) % A.sample_period) == 0) {
+        long long *dst = A.series + (long long)chain * A.series_chain_stride + 2 * slot;
+        dst[0] = ones;
+        dst[1] = B;
+        ++slot;
+      }
+    }
+    eng->pos = pos;
+    A.cur_sb[2 * chain] = ones;
+    A.cur_sb[2 * chain + 1] = B;
+    A.n_accept[chain] += n_acc;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 312; i += blockDim.x) eng->x[i] = mt[i];
+  if (A.use_smem)
+    for (long long i = threadIdx.x; i < s.n_sites; i += blockDim.x) nat_g[i] = lat_s[i];
+}
+
+// draws through the device engine, for the RNG parity probe
+__global__ void k_rng_draw(MT64State *eng, int n, const long long *int_max,
+                           const double *real_max, const uint8_t *is_real,
+                           long long *int_out, double *real_out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int pos = eng->pos;
+  for (int i = 0; i < n; ++i) {
+    if (is_real[i]) {
+      real_out[i] = mt64_uniform_real(eng->x, pos, real_max[i]);
+      int_out[i] = 0;
+    } else {
+      const unsigned long long mx = (unsigned long long)int_max[i];
+      // range == 2^64 is the identity mapping (uniform_int_dist.h:283-286)
+      int_out[i] = (mx == ~0ull) ? (long long)mt64_next(eng->x, pos)
+                                 : (long long)mt64_uniform_int(eng->x, pos, mx + 1ull);
+      real_out[i] = 0.0;
+    }
+  }
+  eng->pos = pos;
+}
+
+// ---------------------------------------------------------------------------
+// Sample series -> intensive doubles, with the reference's expression order
+// (model.hh:266-270, :412-422, :293-295; basic_semigrand_canonical.hh:165-174).
+// Explicit round-to-nearest intrinsics keep the compiler from contracting
+// mul+sub into an FMA, which would change the last bit.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void intensive_from_sums(long long ones, long long B,
+                                                    long long N, double J, double mu,
+                                                    double &x, double &ef, double &ep) {
+  const long long S = 2 * ones - N;
+  const double e_formation = __dmul_rn((double)B, -J);
+  const double Nx = __ddiv_rn((double)(N + S), 2.0);
+  x = __ddiv_rn(Nx, (double)N);
+  ef = __ddiv_rn(e_formation, (double)N);
+  ep = __ddiv_rn(__dsub_rn(e_formation, __dmul_rn(mu, Nx)), (double)N);
+}
+
+// series (ones,B) int64 pairs -> three double columns, for samples [first, first+count)
+__global__ void k_series_to_doubles(const long long *__restrict__ sb, long long first,
+                                    long long count, long long N, const ChainTables *tab,
+                                    double *x, double *ef, double *ep) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  double a, b, c;
+  intensive_from_sums(sb[2 * (first + i)], sb[2 * (first + i) + 1], N, tab->J, tab->mu, a, b, c);
+  x[first + i] = a;
+  ef[first + i] = b;
+  ep[first + i] = c;
+}
+
+// ---------------------------------------------------------------------------
+// Series statistics (src/casm/monte/BasicStatistics.cc:24-48, :114-131;
+// include/casm/monte/misc/math.hh:21-39).  One CTA per series.  mean and
+// variance by block reduction; the lag search evaluates lag-k autocovariances
+// in order until |cov_k / cov_0| <= 0.5.
+// out: {mean, variance, f_autocorr, precision}, k_star
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum_256(double v, double *sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  double t = 0.0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) t += sh[w];
+  return t;
+}
+
+struct SeriesJob {
+  const double *x;  // series start (already offset to `first`)
+  long long n;
+};
+
+__global__ void __launch_bounds__(256) k_series_stats(const SeriesJob *jobs, double z_conf,
+                                                      double *out4, long long *k_star) {
+  __shared__ double sh[8];
+  const SeriesJob job = jobs[blockIdx.x];
+  const double *x = job.x;
+  const long long N = job.n;
+  double *out = out4 + 4 * blockIdx.x;
+  if (N <= 0) {
+    if (threadIdx.x == 0) {
+      out[0] = out[1] = out[2] = out[3] = 0.0;
+      k_star[blockIdx.x] = -2;
+    }
+    return;
+  }
+  double s = 0.0;
+  for (long long i = threadIdx.x; i < N; i += blockDim.x) s += x[i];
+  const double mean = block_sum_256(s, sh) / (double)N;
+  s = 0.0;
+  for (long long i = threadIdx.x; i < N; i += blockDim.x) {
+    const double d = x[i] - mean;
+    s += d * d;
+  }
+  const double var = block_sum_256(s, sh) / (double)N;
+
+  double f = 1.0;
+  long long ks = 0;
+  if (!(fabs(var / mean) < 1e-8 || var == 0.0)) {
+    f = 1.7976931348623157e308;
+    ks = -1;
+    for (long long k = 1; k < N; ++k) {
+      const long long m = N - k;
+      double c = 0.0;
+      for (long long i = threadIdx.x; i < m; i += blockDim.x)
+        c += (x[i] - mean) * (x[i + k] - mean);
+      const double cov = block_sum_256(c, sh) / (double)m;
+      if (fabs(cov / var) <= 0.5) {
+        const double rho = pow(2.0, -1.0 / (double)k);
+        f = (1.0 + rho) / (1.0 - rho);
+        ks = k;
+        break;
+      }
+    }
+  }
+  if (threadIdx.x == 0) {
+    out[0] = mean;
+    out[1] = var;
+    out[2] = f;
+    out[3] = z_conf * sqrt(f * var / (double)N);
+    k_star[blockIdx.x] = ks;
+  }
+}
+
+// Equilibration check, sequential semantics kept exactly
+// (src/casm/monte/checks/EquilibrationCheck.cc:50-117): one thread per series.
+__global__ void k_series_equilibration(const SeriesJob *jobs, int n_jobs, double prec,
+                                       int *is_eq, long long *n_eq) {
+  const int jb = blockIdx.x * blockDim.x + threadIdx.x;
+  if (jb >= n_jobs) return;
+  const double *x = jobs[jb].x;
+  const long long N = jobs[jb].n;
+  if (N <= 0) {
+    is_eq[jb] = 0;
+    n_eq[jb] = 0;
+    return;
+  }
+  const double eps = (x[0] == 0.0) ? 1e-8 : fabs(x[0]) * 1e-8;
+  bool is_even = ((N % 2) == 0);
+  bool all_same = true;
+  for (long long i = 0; i < N; ++i)
+    if (fabs(x[i] - x[0]) > eps) {
+      all_same = false;
+      break;
+    }
+  if (all_same) {
+    is_eq[jb] = 1;
+    n_eq[jb] = 0;
+    return;
+  }
+  long long start1 = 0, start2 = is_even ? N / 2 : (N / 2) + 1;
+  double sum1 = 0.0, sum2 = 0.0;
+  for (long long i = 0; i < start2; ++i) sum1 = __dadd_rn(sum1, x[i]);
+  for (long long i = start2; i < N; ++i) sum2 = __dadd_rn(sum2, x[i]);
+  while (fabs(__dsub_rn(__ddiv_rn(sum1, (double)(start2 - start1)),
+                        __ddiv_rn(sum2, (double)(N - start2)))) > prec &&
+         start1 < N - 2) {
+    if (is_even) {
+      sum1 = __dsub_rn(sum1, x[start1]);
+      sum1 = __dadd_rn(sum1, x[start2]);
+      sum2 = __dsub_rn(sum2, x[start2]);
+      start2++;
+    } else {
+      sum1 = __dsub_rn(sum1, x[start1]);
+    }
+    start1++;
+    is_even = !is_even;
+  }
+  const double mean_tot = __ddiv_rn(__dadd_rn(sum1, sum2), (double)(N - start1));
+  if (x[start1] < mean_tot) {
+    while (x[start1] < mean_tot && start1 < N - 1) start1++;
+  } else {
+    while (x[start1] > mean_tot && start1 < N - 1) start1++;
+  }
+  is_eq[jb] = (start1 < N - 1) ? 1 : 0;
+  n_eq[jb] = start1;
+}
+
+// ---------------------------------------------------------------------------
+// Supercell index conversions, diagonal transformation matrix
+// (src/casm/monte/Conversions.cc:181-229 forwarding to
+// xtal::UnitCellCoordIndexConverter): l = b*n_unitcells + i + n0*(j + n1*k)
+// ---------------------------------------------------------------------------
+__global__ void k_conv_l_to_bijk(long long n0, long long n1, long long n2,
+                                 const long long *__restrict__ l, long long count,
+                                 long long *bijk) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  const long long vol = n0 * n1 * n2;
+  const long long v = l[t];
+  const long long u = v % vol;
+  bijk[4 * t + 0] = v / vol;
+  bijk[4 * t + 1] = u % n0;
+  bijk[4 * t + 2] = (u / n0) % n1;
+  bijk[4 * t + 3] = u / (n0 * n1);
+}
+__device__ __forceinline__ long long floor_mod(long long a, long long m) {
+  long long r = a % m;
+  return r < 0 ? r + m : r;
+}
+__global__ void k_conv_bijk_to_l(long long n0, long long n1, long long n2,
+                                 const long long *__restrict__ bijk, long long count,
+                                 long long *l) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  const long long vol = n0 * n1 * n2;
+  l[t] = bijk[4 * t] * vol + floor_mod(bijk[4 * t + 1], n0) +
+         n0 * (floor_mod(bijk[4 * t + 2], n1) + n1 * floor_mod(bijk[4 * t + 3], n2));
+}
+
+}  // namespace cmg

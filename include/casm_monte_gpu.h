@@ -1,0 +1,255 @@
+/* casm_monte_gpu.h -- C ABI of the B200-native Ising SGC Metropolis path.
+ *
+ * This is the drop-in boundary for ONE hot path of libcasm-monte 2.2.0: the
+ * semi-grand-canonical Ising Metropolis loop and the sampling / statistics it
+ * feeds.  The reference has no FFI of its own for this path (it is a set of
+ * header templates bound with pybind11), so each entry point cites the
+ * reference interface it stands behind (paths relative to the reference root).
+ * INTEGRATION.md shows the binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - every function returns CMG_OK (0) or a negative CMG_E* code, never throws;
+ *     cmg_last_error() gives the message for the last failure on that context,
+ *     cmg_last_global_error() for failures without a context (create).
+ *   - one host thread per context.  Work is enqueued on the context's CUDA
+ *     stream (cmg_set_stream); functions that return host data synchronise that
+ *     stream, the others are asynchronous unless stated.
+ *   - occupation crosses the boundary in the reference's representation:
+ *     int32, values +1/-1, column-major  l = i + n0*(j + n1*k)
+ *     (include/casm/monte/ising_cpp/model.hh:48, :82-99).  On the device it is
+ *     held as two int8 checkerboard colour planes.
+ *   - there is NO CPU fallback: without a CUDA device every call fails with
+ *     CMG_ENODEVICE.
+ */
+#ifndef CASM_MONTE_GPU_H
+#define CASM_MONTE_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CMG_ABI_VERSION 1
+
+/* status codes */
+#define CMG_OK 0
+#define CMG_EINVAL -1     /* bad argument (also: odd extent in checkerboard mode) */
+#define CMG_ENODEVICE -2  /* no CUDA device / driver */
+#define CMG_ECUDA -3      /* a CUDA runtime call failed */
+#define CMG_ENOMEM -4
+#define CMG_ESTATE -5     /* call sequence error (e.g. conditions not set) */
+#define CMG_EUNSUPPORTED -6
+
+/* update modes for cmg_run_passes */
+#define CMG_MODE_CHECKERBOARD 0     /* production: two coloured half-sweeps per pass, Philox4x32-10 */
+#define CMG_MODE_SERIAL_REFERENCE 1 /* validation: the reference's serial random-site loop on the
+                                       reference's std::mt19937_64 stream, trajectory-exact */
+
+/* sampled quantities (the reference's default sampling functions,
+ * include/casm/monte/ising_cpp/basic_semigrand_canonical.hh:486-590) */
+#define CMG_Q_PARAM_COMPOSITION 0
+#define CMG_Q_FORMATION_ENERGY 1
+#define CMG_Q_POTENTIAL_ENERGY 2
+
+/* Boltzmann constant used for beta = 1/(KB*T)
+ * (include/casm/monte/methods/basic_occupation_metropolis.hh:361; the value
+ * lives in CASMcode_global's casm/global/definitions.hh). */
+#define CMG_KB 8.6173303E-05
+
+typedef struct cmg_context cmg_context;
+
+/* ---- library ------------------------------------------------------------ */
+int cmg_abi_version(void);
+const char *cmg_last_global_error(void);
+const char *cmg_last_error(const cmg_context *ctx);
+int cmg_device_count(int *count);
+
+/* ---- lifecycle ------------------------------------------------------------
+ * A context holds n_chains independent lattices of the same shape (one Markov
+ * chain each, e.g. the points of a (T, mu) grid) on one device.
+ * Replaces: IsingConfiguration(shape) + IsingState
+ * (include/casm/monte/ising_cpp/model.hh:19-34, :141-157); dim is 2 (the
+ * reference) or 3 (simple cubic, extension).  All lattices start filled +1.
+ * Extents must be >= 2; checkerboard mode additionally needs even extents. */
+int cmg_create(int dim, const int64_t *shape, int n_chains, int device,
+               cmg_context **out);
+int cmg_destroy(cmg_context *ctx);
+/* cuda_stream is a cudaStream_t (e.g. torch.cuda.Stream.cuda_stream); 0 = legacy default */
+int cmg_set_stream(cmg_context *ctx, void *cuda_stream);
+int cmg_sync(cmg_context *ctx);
+int cmg_n_sites(const cmg_context *ctx, int64_t *n_sites);
+
+/* ---- slab decomposition (one context per GPU, column slabs along the slowest
+ * axis).  Call instead of cmg_create: the context owns columns
+ * [col_begin, col_begin + n_cols_local) of a global lattice and two halo
+ * columns per colour plane.  Philox counters are keyed on GLOBAL site indices,
+ * so the decomposed trajectory is bit-identical to the single-GPU one. */
+int cmg_create_slab(int dim, const int64_t *global_shape, int64_t col_begin,
+                    int64_t n_cols_local, int device, cmg_context **out);
+/* Halo plumbing.  The halo columns live in device memory owned by the context;
+ * side 0 = low neighbour, 1 = high neighbour.  get_boundary/ set_halo give the
+ * host/driver (NCCL send/recv through torch.distributed, or a gloo test) a
+ * device pointer + byte count for the freshly updated boundary column of
+ * `colour` and for the halo it must fill on the neighbour. */
+int cmg_slab_boundary_ptr(cmg_context *ctx, int colour, int side, void **dev_ptr,
+                          int64_t *n_bytes);
+int cmg_slab_halo_ptr(cmg_context *ctx, int colour, int side, void **dev_ptr,
+                      int64_t *n_bytes);
+/* CUDA-IPC export/import of the halo buffers for the fused peer-store path:
+ * once peers are attached, the half-sweep kernel itself writes its boundary
+ * results into the neighbour's halo over NVLink and raises a flag there. */
+int cmg_slab_ipc_export(cmg_context *ctx, void *handle_out, int64_t handle_bytes);
+int cmg_slab_ipc_attach(cmg_context *ctx, int side, const void *handle,
+                        int64_t handle_bytes, int same_process,
+                        cmg_context *peer_if_same_process);
+/* one half-sweep of one pass (checkerboard), for drivers that interleave their
+ * own halo exchange.  pass_index is the global pass number (Philox counter). */
+int cmg_slab_half_sweep(cmg_context *ctx, int colour, uint64_t pass_index,
+                        int sample);
+
+/* ---- model and conditions --------------------------------------------------
+ * Replaces IsingFormationEnergy(J, lattice_type) (model.hh:168-181) and
+ * SemiGrandCanonicalConditions{temperature, exchange_potential[0]}
+ * (basic_semigrand_canonical.hh:36-80).  The host builds, with the reference's
+ * exact expression order, the table of dE for every (spin, neighbour-sum) case
+ * (model.hh:312-314, :430-433; basic_semigrand_canonical.hh:185-191) and of
+ * exp(-dE*beta) (methods/metropolis.hh:33); kernels only look them up.
+ * chain = -1 applies to all chains. */
+int cmg_set_model(cmg_context *ctx, double J, int lattice_type);
+int cmg_set_conditions(cmg_context *ctx, int chain, double temperature, double mu);
+/* tables as built: index = 2*n_up + b, n_up = number of +1 neighbours
+ * (0..2*dim), b = 1 if the site holds +1.  Arrays of 2*(2*dim+1) entries. */
+int cmg_get_tables(cmg_context *ctx, int chain, double *dE, double *prob,
+                   uint32_t *thr_m1);
+
+/* ---- occupation ------------------------------------------------------------
+ * Replaces IsingConfiguration::set_occupation / occupation()
+ * (model.hh:52-60).  n must equal n_sites.  Values must be +1 / -1. */
+int cmg_upload_occupation_i32(cmg_context *ctx, int chain, const int32_t *occ,
+                              int64_t n);
+int cmg_download_occupation_i32(cmg_context *ctx, int chain, int32_t *occ,
+                                int64_t n);
+/* same, with DEVICE pointers (no host copy; for callers that already hold the
+ * lattice in HBM, e.g. torch tensors) */
+int cmg_upload_occupation_i32_dev(cmg_context *ctx, int chain,
+                                  const int32_t *occ_dev, int64_t n);
+int cmg_download_occupation_i32_dev(cmg_context *ctx, int chain, int32_t *occ_dev,
+                                    int64_t n);
+int cmg_fill_occupation(cmg_context *ctx, int chain, int value);
+/* i.i.d. +1/-1 from Philox (synthetic benchmark input), probability of +1 = p_up */
+int cmg_randomize_occupation(cmg_context *ctx, int chain, uint64_t seed, double p_up);
+
+/* ---- random numbers --------------------------------------------------------
+ * Checkerboard mode: counter-based Philox4x32-10; key = (seed, chain), counter
+ * = (site group, pass index, colour).  Serial mode: the reference's
+ * RandomNumberGenerator<std::mt19937_64> (include/casm/monte/
+ * RandomNumberGenerator.hh:15-42, definitions.hh:17) restated on the device:
+ * libstdc++-13 uniform_int_distribution (Lemire) and generate_canonical. */
+int cmg_seed_philox(cmg_context *ctx, uint64_t seed);
+int cmg_set_pass_counter(cmg_context *ctx, uint64_t pass_index);
+int cmg_seed_mt19937_64(cmg_context *ctx, int chain, uint64_t seed);
+/* raw engine state: 312 words + position, i.e. what operator<< of the engine
+ * prints (python/src/monte.cpp:495-513 dump()/load()) */
+int cmg_set_mt19937_64_state(cmg_context *ctx, int chain, const uint64_t *state312,
+                             int position);
+int cmg_get_mt19937_64_state(cmg_context *ctx, int chain, uint64_t *state312,
+                             int *position);
+/* draw through the device engine exactly as RandomNumberGenerator does
+ * (random_int(max) in [0,max], random_real(max) in [0,max)) -- parity probe */
+int cmg_rng_draw(cmg_context *ctx, int chain, int n, const int64_t *int_max,
+                 const double *real_max, const uint8_t *is_real,
+                 int64_t *int_out, double *real_out);
+
+/* ---- the hot loop ----------------------------------------------------------
+ * Replaces the body of methods::basic_occupation_metropolis
+ * (include/casm/monte/methods/basic_occupation_metropolis.hh:381-422):
+ * propose (basic_semigrand_canonical.hh:308-315), dE (:178-192), acceptance
+ * (methods/metropolis.hh:26-35), apply (:318-320), pass counting (:399-403) and
+ * sampling of the three default observables when n_pass hits the sample
+ * schedule (:406-411).  Runs n_passes passes (n_sites attempts each) on every
+ * chain; if sample_period > 0 a sample is appended to the on-device series
+ * whenever the pass count is a multiple of sample_period.  Asynchronous. */
+int cmg_run_passes(cmg_context *ctx, int64_t n_passes, int mode,
+                   int64_t sample_period);
+int cmg_counters(cmg_context *ctx, int chain, int64_t *n_pass, int64_t *n_accept,
+                 int64_t *n_reject);
+int cmg_reset_counters(cmg_context *ctx);
+
+/* ---- sampling --------------------------------------------------------------
+ * Integer sums of the current state: S = sum_l s_l and
+ * B = sum_l s_l*(s_right + s_down [+ s_back]); the host (or cmg_read_samples)
+ * applies the reference formulae (model.hh:266-270, :412-422;
+ * basic_semigrand_canonical.hh:165-174) to get bit-identical doubles. */
+int cmg_sample_now(cmg_context *ctx, int chain, int64_t *S, int64_t *B);
+/* use_nlist=false form of the energy (model.hh:273-285): per-line integer dot
+ * products, n0 "row" values then n1 "column" values (2-d only) */
+int cmg_line_dots(cmg_context *ctx, int chain, int64_t *row_dots, int64_t *col_dots);
+int cmg_n_samples(cmg_context *ctx, int64_t *n_samples);
+int cmg_clear_samples(cmg_context *ctx);
+int cmg_read_samples_sb(cmg_context *ctx, int chain, int64_t first, int64_t count,
+                        int64_t *S, int64_t *B);
+int cmg_read_samples(cmg_context *ctx, int chain, int quantity, int64_t first,
+                     int64_t count, double *out);
+
+/* ---- parity probes ---------------------------------------------------------
+ * dE of flipping each site, in site order l (SemiGrandCanonicalPotential::
+ * occ_delta_per_supercell for every single-site event); and the acceptance
+ * decision of metropolis_acceptance for each site given one uniform per site.
+ * Bit-exact against the reference expressions. */
+int cmg_delta_e_probe(cmg_context *ctx, int chain, double *dE_per_site);
+int cmg_accept_probe(cmg_context *ctx, int chain, const double *uniforms,
+                     uint8_t *accept);
+
+/* ---- statistics on the device-resident sample series -----------------------
+ * Replaces BasicStatisticsCalculator::operator() (src/casm/monte/
+ * BasicStatistics.cc:114-131: mean, variance, lag-k autocovariance search,
+ * precision of the mean) and default_equilibration_check (src/casm/monte/
+ * checks/EquilibrationCheck.cc:50-162) over samples [first, first+count).
+ * k_star: lag found (0 = no-variation early-out, -1 = none found). */
+int cmg_series_stats(cmg_context *ctx, int chain, int quantity, int64_t first,
+                     int64_t count, double confidence, double *mean,
+                     double *calculated_precision, double *variance,
+                     int64_t *k_star);
+int cmg_series_equilibration(cmg_context *ctx, int chain, int quantity,
+                             int64_t count, double abs_precision,
+                             int *is_equilibrated, int64_t *n_equil);
+/* the same two, for every chain at once (results arrays of n_chains) */
+int cmg_series_stats_all(cmg_context *ctx, int quantity, const int64_t *first,
+                         int64_t count_total, double confidence, double *mean,
+                         double *calculated_precision, double *variance,
+                         int64_t *k_star);
+int cmg_series_equilibration_all(cmg_context *ctx, int quantity, int64_t count,
+                                 double abs_precision, int *is_equilibrated,
+                                 int64_t *n_equil);
+/* statistics of an arbitrary host series (Sampler columns that did not come
+ * from the device path): uploads, computes on the device, returns */
+int cmg_host_series_stats(int device, const double *x, int64_t n, double confidence,
+                          double *mean, double *calculated_precision,
+                          double *variance, int64_t *k_star);
+int cmg_host_series_equilibration(int device, const double *x, int64_t n,
+                                  double abs_precision, int *is_equilibrated,
+                                  int64_t *n_equil);
+
+/* ---- supercell index conversions --------------------------------------------
+ * Replaces Conversions::l_to_b / l_to_ijk / bijk_to_l (include/casm/monte/
+ * Conversions.hh:43-135, src/casm/monte/Conversions.cc:181-229) for a diagonal
+ * transformation matrix diag(n0,n1,n2) and n_basis sublattices, batched on the
+ * device: l = b*n_unitcells + i + n0*(j + n1*k), ijk wrapped periodically. */
+int cmg_conv_l_to_bijk(int device, const int64_t *n3, int64_t n_basis,
+                       const int64_t *l, int64_t count, int64_t *bijk_out);
+int cmg_conv_bijk_to_l(int device, const int64_t *n3, int64_t n_basis,
+                       const int64_t *bijk, int64_t count, int64_t *l_out);
+
+/* ---- introspection for bench / tests ---------------------------------------- */
+/* number of kernels this context has launched since creation */
+int cmg_launch_count(const cmg_context *ctx, int64_t *n_launches);
+/* name of the half-sweep kernel variant the context selected ("bulk2d", ...) */
+const char *cmg_kernel_variant(const cmg_context *ctx);
+/* force a variant ("auto", "generic", "bulk2d", "bulk3d", "smem"); for tests */
+int cmg_set_kernel_variant(cmg_context *ctx, const char *name);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CASM_MONTE_GPU_H */

@@ -1722,8 +1722,9 @@ inline AcceptTable make_accept_table(int dim, double J, double T, double mu) {
 // Colour c = (i + j [+ k]) & 1.  Sites of one colour are numbered by the
 // "plane index" q = (i >> 1) + (n0/2) * (j + n1 * k); the 32-bit uniform of
 // site q in pass t, colour c, chain ch is word (q & 3) of
-//   Philox4x32-10(counter = {lo32(q>>2), hi32(q>>2), lo32(t), (hi32(t)<<1)|c},
-//                 key     = {lo32(seed), hi32(seed) ^ ch}).
+//   Philox4x32-10(counter = {lo32(q>>2), (hi32(q>>2)&0xff) | ch<<8, lo32(t),
+//                            (hi32(t)<<1)|c},
+//                 key     = {lo32(seed), hi32(seed)}).
 // Requires even extents.  One pass = colour 0 half-sweep then colour 1.
 struct CheckerboardResult {
   long long n_accept = 0;
@@ -1736,7 +1737,7 @@ inline void checkerboard_pass(std::vector<int> &occ, std::vector<int> const &sha
   const long n0 = shape[0], n1 = shape[1], n2 = (dim == 3) ? shape[2] : 1;
   const long h = n0 / 2;
   std::array<uint32_t, 2> key = {static_cast<uint32_t>(seed),
-                                 static_cast<uint32_t>(seed >> 32) ^ chain};
+                                 static_cast<uint32_t>(seed >> 32)};
   for (int colour = 0; colour < 2; ++colour) {
     for (long k = 0; k < n2; ++k)
       for (long j = 0; j < n1; ++j)
@@ -1749,7 +1750,8 @@ inline void checkerboard_pass(std::vector<int> &occ, std::vector<int> const &sha
                             static_cast<uint64_t>(n1) * static_cast<uint64_t>(k));
           uint64_t g = q >> 2;
           std::array<uint32_t, 4> ctr = {
-              static_cast<uint32_t>(g), static_cast<uint32_t>(g >> 32),
+              static_cast<uint32_t>(g),
+              (static_cast<uint32_t>(g >> 32) & 0xffu) | (chain << 8),
               static_cast<uint32_t>(pass_index),
               (static_cast<uint32_t>(pass_index >> 32) << 1) |
                   static_cast<uint32_t>(colour)};

@@ -1,0 +1,53 @@
+"""GPU micro-sweep: throughput of the half-sweep kernel variants / strip lengths.
+Usage (on the GPU box): python tools/sweep_variants.py > gpurun_out/sweep.json"""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from casmcode_monte_b200 import MODE_CHECKERBOARD, IsingLatticeGPU
+
+
+def time_passes(lat, stream, n_passes, sample_period):
+    lat.run_passes(10, MODE_CHECKERBOARD, sample_period)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    lat.run_passes(n_passes, MODE_CHECKERBOARD, sample_period)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e-3
+
+
+def main():
+    stream = torch.cuda.Stream()
+    out = []
+    cases = [
+        ("2d", [4096, 4096], 1, ["generic"] + [f"bulk2d:js={j}" for j in (1, 2, 4, 8, 16, 32)], 100),
+        ("2d_grid", [256, 256], 128, [f"bulk2d:js={j}" for j in (2, 4, 8, 16)], 100),
+        ("2d_big", [16384, 16384], 1, [f"bulk2d:js={j}" for j in (4, 16, 32)], 20),
+        ("3d", [512, 512, 512], 1, [f"bulk3d:js={j}" for j in (2, 4, 8, 16)], 10),
+    ]
+    for name, shape, chains, variants, n_passes in cases:
+        lat = IsingLatticeGPU(shape, n_chains=chains, J=0.1)
+        lat.set_stream(stream.cuda_stream)
+        lat.set_conditions(2633.0 if len(shape) == 2 else 5235.0, 0.0)
+        lat.seed_philox(1)
+        lat.randomize(5, 0.5)
+        n = chains
+        for s in shape:
+            n *= s
+        for v in variants:
+            lat.set_kernel_variant(v)
+            for sp in (0, 1):
+                t = time_passes(lat, stream, n_passes, sp)
+                rec = {"case": name, "variant": v, "sample_period": sp, "attempts_per_s": n * n_passes / t, "us_per_halfsweep": t / (2 * n_passes) * 1e6}
+                out.append(rec)
+                print(json.dumps(rec), flush=True)
+        lat.close()
+
+
+if __name__ == "__main__":
+    main()
