@@ -33,7 +33,7 @@ struct RunState {
   long long n_samples;
 };
 
-enum Variant { V_AUTO = 0, V_GENERIC = 1, V_BULK2D = 2, V_BULK3D = 3, V_SMEM = 4 };
+enum Variant { V_AUTO = 0, V_GENERIC = 1, V_BULK2D = 2, V_BULK3D = 3, V_TILE2D = 4 };
 
 struct cmg_context {
   int device = 0;
@@ -85,6 +85,10 @@ struct cmg_context {
 
   int forced_variant = V_AUTO;
   int js = 0;  // 0 = auto
+  int tile_passes = 2;   // passes per launch of the tiled kernel (halo = 2*P columns)
+  int tile_threads = 512;
+  int sm_count = 148;
+  size_t smem_optin = 0;
   long long launches = 0;
   std::string last_error;
   std::string variant_name = "auto";
@@ -274,6 +278,13 @@ static int create_common(int dim, const int64_t *shape, int n_chains, int device
   if (e != cudaSuccess) {
     delete c;
     return fail(nullptr, CMG_ECUDA, cudaGetErrorString(e));
+  }
+  {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0)
+      c->sm_count = v;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) == cudaSuccess)
+      c->smem_optin = (size_t)v;
   }
 #define CUC(call)                                                        \
   do {                                                                   \
@@ -729,8 +740,56 @@ static int ensure_series(cmg_context *c, long long need) {
 }
 
 // ---- the hot loop ------------------------------------------------------------------
+// Geometry of the tiled kernel for this lattice: number of column tiles,
+// passes per launch and dynamic shared memory.  ok = false if the lattice does
+// not suit it (columns too tall for a useful tile, or n0 % 64 != 0).
+struct TilePlan {
+  bool ok = false;
+  int n_tiles = 1, passes = 1, halo = 0, w_max = 0;
+  size_t smem = 0;
+};
+static TilePlan plan_tiles(const cmg_context *c, long long passes_wanted) {
+  TilePlan t;
+  if (c->dim != 2 || c->slab || c->shape[0] % 64 != 0 || c->smem_optin < 64 * 1024) return t;
+  const long long h = c->shape[0] / 2, n1 = c->shape[1];
+  const long long budget = (long long)c->smem_optin - 2048;  // static smem + slack
+  if (2 * n1 * h <= budget) {  // whole lattice in one tile: periodic, no halo
+    t.ok = true;
+    t.n_tiles = 1;
+    t.passes = (int)std::min<long long>(passes_wanted, 64);
+    t.halo = 0;
+    t.w_max = (int)n1;
+    t.smem = (size_t)(2 * n1 * h);
+    return t;
+  }
+  const int P = (int)std::min<long long>(passes_wanted, c->tile_passes);
+  const long long H = 2 * P;
+  const long long w_fit = budget / (2 * h);
+  long long tw = w_fit - 2 * H;
+  if (tw < 4 * H) return t;  // redundant halo work would exceed ~20 %
+  long long n_tiles = (n1 + tw - 1) / tw;
+  // use every SM: round the tile count up to a multiple of the SM count
+  n_tiles = (n_tiles + c->sm_count - 1) / c->sm_count * c->sm_count;
+  if (n_tiles > n1) n_tiles = n1;
+  const long long tw_max = (n1 + n_tiles - 1) / n_tiles;
+  if (tw_max < 4 * H && n_tiles > c->sm_count) {
+    // too thin after rounding: fall back to the plain fit
+    n_tiles = (n1 + tw - 1) / tw;
+  }
+  const long long tw_max2 = (n1 + n_tiles - 1) / n_tiles;
+  if (tw_max2 + 2 * H > n1) return t;
+  t.ok = true;
+  t.n_tiles = (int)n_tiles;
+  t.passes = P;
+  t.halo = (int)H;
+  t.w_max = (int)(tw_max2 + 2 * H);
+  t.smem = (size_t)(2 * t.w_max * h);
+  return t;
+}
+
 static int pick_variant(cmg_context *c) {
   if (c->forced_variant != V_AUTO) return c->forced_variant;
+  if (plan_tiles(c, c->tile_passes).ok) return V_TILE2D;
   if (c->dim == 2 && c->shape[0] % 32 == 0) return V_BULK2D;
   if (c->dim == 3 && c->shape[0] % 32 == 0) return V_BULK3D;
   return V_GENERIC;
@@ -767,7 +826,7 @@ static int launch_half_sweep(cmg_context *c, int variant, int colour, unsigned l
   const long long plane_size = c->n_sites / 2;
   dim3 block(128);
   if (variant == V_GENERIC) {
-    dim3 grid(nblocks((plane_size + 3) / 4, 128), c->n_chains);
+    dim3 grid(nblocks((plane_size + 7) / 8, 128), c->n_chains);
     if (sample)
       k_halfsweep_generic<true><<<grid, block, 0, c->stream>>>(A);
     else
@@ -795,12 +854,54 @@ static int launch_half_sweep(cmg_context *c, int variant, int colour, unsigned l
   return CMG_OK;
 }
 
+static int launch_tile_passes_sp(cmg_context *c, const TilePlan &tp, int n_passes,
+                                 long long sample_period) {
+  TileArgs A;
+  memset(&A, 0, sizeof A);
+  A.L = view(c);
+  A.tabs = c->d_tabs;
+  A.n_accept = c->d_n_accept;
+  A.sb = c->d_series ? c->d_series + c->n_samples * 2 * c->n_chains : nullptr;
+  A.sb_chain_stride = 2;
+  A.sb_slot_stride = 2 * c->n_chains;
+  A.pass0 = c->h_pass;
+  A.pass_phase = c->n_pass;
+  A.sample_period = sample_period;
+  for (int r = 0; r < 10; ++r) {
+    A.rk[2 * r] = (uint32_t)c->philox_seed + (uint32_t)r * kPhiloxW0;
+    A.rk[2 * r + 1] = (uint32_t)(c->philox_seed >> 32) + (uint32_t)r * kPhiloxW1;
+  }
+  A.n_passes = n_passes;
+  A.n_tiles = tp.n_tiles;
+  A.halo = tp.n_tiles == 1 ? 0 : 2 * n_passes;
+  A.w_max = tp.w_max;
+  const unsigned long long V = (unsigned long long)(c->shape[0] / 32);
+  A.v_magic = (uint32_t)((0x100000000ull + V - 1) / V);
+  dim3 grid(tp.n_tiles, c->n_chains);
+  cudaError_t e;
+#define LAUNCH_TILE(NT)                                                                       \
+  e = cudaFuncSetAttribute(k_tile2d<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+                           (int)tp.smem);                                                     \
+  if (e != cudaSuccess) return fail(c, CMG_ECUDA, cudaGetErrorString(e));                     \
+  k_tile2d<NT><<<grid, NT, tp.smem, c->stream>>>(A);
+  if (c->tile_threads == 1024) {
+    LAUNCH_TILE(1024)
+  } else if (c->tile_threads == 256) {
+    LAUNCH_TILE(256)
+  } else {
+    LAUNCH_TILE(512)
+  }
+#undef LAUNCH_TILE
+  ++c->launches;
+  return CMG_OK;
+}
+
 static const char *variant_str(int v) {
   switch (v) {
     case V_GENERIC: return "generic";
     case V_BULK2D: return "bulk2d";
     case V_BULK3D: return "bulk3d";
-    case V_SMEM: return "smem";
+    case V_TILE2D: return "tile2d";
     default: return "auto";
   }
 }
@@ -915,6 +1016,8 @@ int cmg_run_passes(cmg_context *c, int64_t n_passes, int mode, int64_t sample_pe
     return fail(c, CMG_EINVAL, "bulk2d needs dim == 2 and n0 % 32 == 0");
   if (variant == V_BULK3D && !(c->dim == 3 && c->shape[0] % 32 == 0))
     return fail(c, CMG_EINVAL, "bulk3d needs dim == 3 and n0 % 32 == 0");
+  if (variant == V_TILE2D && !plan_tiles(c, 1).ok)
+    return fail(c, CMG_EINVAL, "tile2d does not fit this lattice (need dim 2, n0 % 64 == 0, short columns)");
   c->variant_name = variant_str(variant);
   long long n_new = 0;
   if (sample_period > 0)
@@ -922,6 +1025,24 @@ int cmg_run_passes(cmg_context *c, int64_t n_passes, int mode, int64_t sample_pe
   rc = ensure_series(c, c->n_samples + n_new);
   if (rc) return rc;
   c->nat_is_current = false;
+  if (variant == V_TILE2D) {
+    long long left = n_passes;
+    while (left > 0) {
+      TilePlan tp = plan_tiles(c, left);
+      if (!tp.ok) return fail(c, CMG_EINVAL, "tile2d does not fit this lattice (need dim 2, n0 % 64 == 0, short columns)");
+      rc = launch_tile_passes_sp(c, tp, tp.passes, sample_period);
+      if (rc) return rc;
+      long long n_new_here = 0;
+      if (sample_period > 0)
+        n_new_here = (c->n_pass + tp.passes) / sample_period - c->n_pass / sample_period;
+      c->h_pass += tp.passes;
+      c->n_pass += tp.passes;
+      c->n_samples += n_new_here;
+      left -= tp.passes;
+    }
+    CU(c, cudaGetLastError());
+    return CMG_OK;
+  }
   for (long long t = 0; t < n_passes; ++t) {
     const bool sample = sample_period > 0 && ((c->n_pass + 1) % sample_period) == 0;
     rc = launch_half_sweep(c, variant, 0, c->h_pass, false, 0);
@@ -1464,19 +1585,31 @@ int cmg_set_kernel_variant(cmg_context *c, const char *name) {
   NEED(c);
   if (!name) return fail(c, CMG_EINVAL, "null name");
   std::string s(name);
-  // "bulk2d:js=8" style suffix sets the strip length
+  // "bulk2d:js=8" sets the strip length; "tile2d:p=2:nt=512" passes per launch / CTA size
   c->js = 0;
   size_t p = s.find(":js=");
   if (p != std::string::npos) {
     c->js = atoi(s.c_str() + p + 4);
     if (c->js < 1) return fail(c, CMG_EINVAL, "bad js");
-    s = s.substr(0, p);
   }
+  p = s.find(":p=");
+  if (p != std::string::npos) {
+    c->tile_passes = atoi(s.c_str() + p + 3);
+    if (c->tile_passes < 1 || c->tile_passes > 16) return fail(c, CMG_EINVAL, "bad p");
+  }
+  p = s.find(":nt=");
+  if (p != std::string::npos) {
+    c->tile_threads = atoi(s.c_str() + p + 4);
+    if (c->tile_threads != 256 && c->tile_threads != 512 && c->tile_threads != 1024)
+      return fail(c, CMG_EINVAL, "nt must be 256, 512 or 1024");
+  }
+  p = s.find(':');
+  if (p != std::string::npos) s = s.substr(0, p);
   if (s == "auto") c->forced_variant = V_AUTO;
   else if (s == "generic") c->forced_variant = V_GENERIC;
   else if (s == "bulk2d") c->forced_variant = V_BULK2D;
   else if (s == "bulk3d") c->forced_variant = V_BULK3D;
-  else if (s == "smem") c->forced_variant = V_SMEM;
+  else if (s == "tile2d") c->forced_variant = V_TILE2D;
   else return fail(c, CMG_EINVAL, "unknown kernel variant");
   return CMG_OK;
 }

@@ -86,49 +86,78 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, const uint32_t *rk) {
   return c;
 }
 
-// The uniforms of site group `group` (4 consecutive plane indices) of `chain`
-// in half-sweep (pass, colour): counter = {lo32(group), (hi32(group)&0xff) |
-// chain<<8, lo32(pass), hi32(pass)<<1 | colour}, key = seed.
+// Random words of site group `group` (8 consecutive plane indices, one 16-bit
+// lane each) of `chain` in half-sweep (pass, colour): counter = {lo32(group),
+// (hi32(group)&0xff) | chain<<8, lo32(pass), hi32(pass)<<2 | refine<<1 | colour},
+// key = seed.  refine = 0: the leading 16 bits r16 of each site's uniform;
+// refine = 1: the trailing 16 bits r16' (only evaluated on a tie, see below).
 __device__ __forceinline__ uint4 site_group_random(unsigned long long group,
                                                    uint32_t chain_word,
                                                    unsigned long long pass,
-                                                   int colour, const uint32_t *rk) {
+                                                   int colour, int refine,
+                                                   const uint32_t *rk) {
   uint4 c;
   c.x = (uint32_t)group;
   c.y = ((uint32_t)(group >> 32) & 0xffu) | chain_word;
   c.z = (uint32_t)pass;
-  c.w = ((uint32_t)(pass >> 32) << 1) | (uint32_t)colour;
+  c.w = ((uint32_t)(pass >> 32) << 2) | ((uint32_t)refine << 1) | (uint32_t)colour;
   return philox4x32_10(c, rk);
 }
 
-// accept mask for 4 sites packed in a word: idx4 holds the table index of each
-// site in its byte, r the four 32-bit uniforms.  Returns 0x01 in the byte of
-// every accepted site (accept iff r <= thr).  The four compares run through the
-// carry flag: thr - r borrows iff the site is rejected, and addc shifts the
-// borrow into a 4-bit mask (2 instructions per site, no predicates/selects).
-__device__ __forceinline__ uint32_t accept_mask4(uint32_t idx4, uint4 r,
-                                                 const uint32_t *thr) {
-  const uint32_t t0 = thr[idx4 & 0xffu];
-  const uint32_t t1 = thr[(idx4 >> 8) & 0xffu];
-  const uint32_t t2 = thr[(idx4 >> 16) & 0xffu];
-  const uint32_t t3 = thr[idx4 >> 24];
-  uint32_t rej;
+// Acceptance of 4 sites packed in a word.  Each site's uniform is the 32-bit
+// integer R = r16<<16 | r16' and the site is flipped iff R <= thr (thr =
+// thr_m1 of its table entry).  Only r16 is generated up front: with Y = r16<<16,
+//   Y >  thr              -> rejected whatever r16' is,
+//   Y <= thr - 65536      -> accepted whatever r16' is,
+//   otherwise (r16 equals the top half of thr, probability 2^-16) a tie that
+//   needs r16'.
+// idx4: table index of each site in its byte; r01 / r23: the Philox words
+// holding the r16 of sites (0,1) / (2,3) in their (low, high) halves; nthr:
+// table of ~thr.  D = Y + ~thr carries out iff Y > thr (2 instructions per site
+// through the carry flag, no predicates), and D >= 0xFFFF0000 iff tie, tracked
+// with one max per site.  Returns 0x01 in the byte of every (provisionally)
+// accepted site; ties count as accepted here and are resolved by the caller
+// when dmax >= 0xFFFF0000.
+__device__ __forceinline__ uint32_t accept_mask4_fast(uint32_t idx4, uint32_t r01,
+                                                      uint32_t r23, const uint32_t *nthr,
+                                                      uint32_t &dmax) {
+  const uint32_t t0 = nthr[idx4 & 0xffu];
+  const uint32_t t1 = nthr[__byte_perm(idx4, 0u, 0x4441u)];
+  const uint32_t t2 = nthr[__byte_perm(idx4, 0u, 0x4442u)];
+  const uint32_t t3 = nthr[idx4 >> 24];
+  const uint32_t y0 = r01 << 16, y1 = r01 & 0xffff0000u;
+  const uint32_t y2 = r23 << 16, y3 = r23 & 0xffff0000u;
+  uint32_t rej, mx = dmax;
   asm("{\n\t"
       ".reg .u32 d;\n\t"
-      "sub.cc.u32 d, %1, %5;\n\t"
+      "add.cc.u32 d, %2, %6;\n\t"
       "addc.u32 %0, 0, 0;\n\t"
-      "sub.cc.u32 d, %2, %6;\n\t"
+      "max.u32 %1, %1, d;\n\t"
+      "add.cc.u32 d, %3, %7;\n\t"
       "addc.u32 %0, %0, %0;\n\t"
-      "sub.cc.u32 d, %3, %7;\n\t"
+      "max.u32 %1, %1, d;\n\t"
+      "add.cc.u32 d, %4, %8;\n\t"
       "addc.u32 %0, %0, %0;\n\t"
-      "sub.cc.u32 d, %4, %8;\n\t"
+      "max.u32 %1, %1, d;\n\t"
+      "add.cc.u32 d, %5, %9;\n\t"
       "addc.u32 %0, %0, %0;\n\t"
+      "max.u32 %1, %1, d;\n\t"
       "}"
-      : "=r"(rej)
-      : "r"(t3), "r"(t2), "r"(t1), "r"(t0), "r"(r.w), "r"(r.z), "r"(r.y), "r"(r.x));
+      : "=r"(rej), "+r"(mx)
+      : "r"(t3), "r"(t2), "r"(t1), "r"(t0), "r"(y3), "r"(y2), "r"(y1), "r"(y0));
+  dmax = mx;
   // bit k of rej = site k rejected; spread the 4 bits to the low bit of 4 bytes
   const uint32_t rej_bytes = (rej * 0x00204081u) & 0x01010101u;
   return rej_bytes ^ 0x01010101u;
+}
+
+// Exact form with both halves (tie path and the generic kernel).
+__device__ __forceinline__ bool accept_exact(uint32_t r16, uint32_t r16b, uint32_t thr) {
+  return ((r16 << 16) | r16b) <= thr;
+}
+__device__ __forceinline__ uint32_t lane16(uint4 v, int lane) {
+  const uint32_t w = (lane >> 1) == 0 ? v.x : (lane >> 1) == 1 ? v.y : (lane >> 1) == 2 ? v.z : v.w;
+  return (lane & 1) ? (w >> 16) : (w & 0xffffu);
 }
 
 // sum of the four bytes of a word
@@ -205,13 +234,14 @@ __global__ void __launch_bounds__(128) k_halfsweep_generic(SweepArgs A) {
 
   unsigned int acc = 0;
   long long ones = 0, bsum = 0;
-  if (4 * g < plane_size) {
-    uint4 r4 = site_group_random((unsigned long long)g, (uint32_t)chain << 8, A.pass,
-                                 A.colour, A.rk);
-    const uint32_t rr[4] = {r4.x, r4.y, r4.z, r4.w};
+  if (8 * g < plane_size) {
+    const uint4 ra = site_group_random((unsigned long long)g, (uint32_t)chain << 8, A.pass,
+                                       A.colour, 0, A.rk);
+    const uint4 rb = site_group_random((unsigned long long)g, (uint32_t)chain << 8, A.pass,
+                                       A.colour, 1, A.rk);
 #pragma unroll
-    for (int w = 0; w < 4; ++w) {
-      const long long q = 4 * g + w;
+    for (int w = 0; w < 8; ++w) {
+      const long long q = 8 * g + w;
       if (q >= plane_size) break;
       const int p = (int)(q % L.h);
       const long long jk = q / L.h;
@@ -231,7 +261,7 @@ __global__ void __launch_bounds__(128) k_halfsweep_generic(SweepArgs A) {
                 O[p + (long long)L.h * (j + (long long)L.n1 * kp)];
       }
       int b = C[q];
-      if (rr[w] <= s_thr[2 * n_up + b]) {
+      if (accept_exact(lane16(ra, w), lane16(rb, w), s_thr[2 * n_up + b])) {
         b ^= 1;
         C[q] = (uint8_t)b;
         ++acc;
@@ -291,25 +321,69 @@ struct Accum {
   int bsum;
 };
 
-// update 16 sites; returns new centre vector
+// Rare path: some site of a 16-site vector tied on its leading 16 bits.  Redo
+// all 16 decisions exactly with both halves (regenerating the leading words so
+// the hot path does not have to keep them alive).
+__device__ __noinline__ uint4 resolve_ties16(uint4 idx, unsigned long long group0,
+                                             unsigned long long pass, int colour,
+                                             uint32_t chain_word, const uint32_t *rk,
+                                             const uint32_t *s_nthr) {
+  const uint32_t iw[4] = {idx.x, idx.y, idx.z, idx.w};
+  uint32_t m[4];
+  for (int half = 0; half < 2; ++half) {
+    const uint4 r = site_group_random(group0 + half, chain_word, pass, colour, 0, rk);
+    const uint4 q = site_group_random(group0 + half, chain_word, pass, colour, 1, rk);
+#pragma unroll
+    for (int ww = 0; ww < 2; ++ww) {
+      const int w = 2 * half + ww;
+      uint32_t mm = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int lane = 4 * ww + k;
+        const uint32_t thr = ~s_nthr[(iw[w] >> (8 * k)) & 0xffu];
+        mm |= accept_exact(lane16(r, lane), lane16(q, lane), thr) ? (1u << (8 * k)) : 0u;
+      }
+      m[w] = mm;
+    }
+  }
+  return make_uint4(m[0], m[1], m[2], m[3]);
+}
+
+// Update 16 sites (one 16-byte vector of a colour plane); returns the new
+// centre vector.  group0 = plane index of the first site >> 3.
 template <bool SAMPLE>
 __device__ __forceinline__ uint4 update16(uint4 ce, uint4 om, uint4 oc, uint4 op,
                                           uint4 side, unsigned long long group0,
                                           unsigned long long pass, int colour,
                                           uint32_t chain_word, const uint32_t *rk,
-                                          const uint32_t *s_thr, int z,
+                                          const uint32_t *s_nthr, int z,
                                           Accum &a) {
   uint32_t cw[4] = {ce.x, ce.y, ce.z, ce.w};
   const uint32_t nw[4] = {om.x + oc.x + op.x + side.x, om.y + oc.y + op.y + side.y,
                           om.z + oc.z + op.z + side.z, om.w + oc.w + op.w + side.w};
   const uint32_t ow[4] = {oc.x, oc.y, oc.z, oc.w};
+  const uint4 ra = site_group_random(group0, chain_word, pass, colour, 0, rk);
+  const uint4 rb = site_group_random(group0 + 1, chain_word, pass, colour, 0, rk);
+  const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+  uint32_t idx[4], m[4], dmax = 0;
 #pragma unroll
   for (int w = 0; w < 4; ++w) {
-    const uint4 r = site_group_random(group0 + w, chain_word, pass, colour, rk);
-    const uint32_t idx4 = nw[w] + nw[w] + cw[w];
-    const uint32_t m = accept_mask4(idx4, r, s_thr);
-    cw[w] ^= m;
-    a.acc += __popc(m);
+    idx[w] = nw[w] + nw[w] + cw[w];
+    m[w] = accept_mask4_fast(idx[w], rw[2 * w], rw[2 * w + 1], s_nthr, dmax);
+  }
+  if (dmax >= 0xffff0000u)  // a tie somewhere in these 16 sites (probability 16 * 2^-16)
+  {
+    const uint4 mm = resolve_ties16(make_uint4(idx[0], idx[1], idx[2], idx[3]), group0, pass,
+                                    colour, chain_word, rk, s_nthr);
+    m[0] = mm.x;
+    m[1] = mm.y;
+    m[2] = mm.z;
+    m[3] = mm.w;
+  }
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    cw[w] ^= m[w];
+    a.acc += __popc(m[w]);
     if (SAMPLE) {
       // ones of both planes; B = sum (2b-1)(2n-z) = 4*sum_{b=1} n - 2*sum n - z*(2*ones_c - 4)
       const uint32_t sel = nw[w] & (cw[w] * 0xffu);
@@ -325,8 +399,8 @@ template <bool SAMPLE>
 __global__ void __launch_bounds__(128) k_halfsweep_bulk2d(SweepArgs A) {
   const LatticeView &L = A.L;
   const int chain = blockIdx.y;
-  __shared__ uint32_t s_thr[16];
-  if (threadIdx.x < 16) s_thr[threadIdx.x] = A.tabs[chain].thr_m1[threadIdx.x];
+  __shared__ uint32_t s_thr[16];  // holds ~thr_m1 (see accept_mask4)
+  if (threadIdx.x < 16) s_thr[threadIdx.x] = ~A.tabs[chain].thr_m1[threadIdx.x];
   __syncthreads();
 
   const int h = L.h, n1 = L.n1;
@@ -376,7 +450,7 @@ __global__ void __launch_bounds__(128) k_halfsweep_bulk2d(SweepArgs A) {
         side = shift_down_1(oc, __ldg(ocj + p_above));  // neighbour i+1 -> p+1
       }
       const unsigned long long group0 =
-          (unsigned long long)(((long long)h * jg + p0) >> 2);
+          (unsigned long long)(((long long)h * jg + p0) >> 3);
       const uint4 cn = update16<SAMPLE>(ce, om, oc, op, side, group0, A.pass,
                                         A.colour, chain_word, A.rk, s_thr, 4, acc);
       *reinterpret_cast<uint4 *>(C + (long long)h * j + p0) = cn;
@@ -392,6 +466,183 @@ __global__ void __launch_bounds__(128) k_halfsweep_bulk2d(SweepArgs A) {
 }
 
 // ---------------------------------------------------------------------------
+// k_tile2d: shared-memory resident 2-d kernel with temporal blocking.
+//
+// A CTA owns a tile of whole columns (all n0/2 bytes of a plane column, so the
+// periodic wrap along i stays inside the tile) of one chain, stages both colour
+// planes of the tile plus H = 2*P halo columns on each side in shared memory,
+// and advances P passes (2*P half-sweeps) before writing the owned columns
+// back.  Half-sweep s can only update local columns [s+1, W-1-s): one more halo
+// column goes stale per half-sweep.  The halo work is redundant -- the
+// neighbouring tile computes the same sites -- but because the random numbers
+// are counter-based (a pure function of site, pass, colour) both CTAs get the
+// same answer, so no communication is needed inside the launch.
+// With n_tiles == 1 the tile is the whole lattice: no halo, periodic columns,
+// any number of passes per launch (the 256x256 chains of the (T, mu) grid).
+// Launches per pass drop from 2 to 1/P and the per-site loads become LDS.
+// ---------------------------------------------------------------------------
+struct TileArgs {
+  LatticeView L;
+  const ChainTables *tabs;
+  unsigned long long *n_accept;  // [chain]
+  long long *sb;                 // slot of the first sample taken by this launch (chain 0)
+  long long sb_chain_stride;     // long long units
+  long long sb_slot_stride;      // long long units
+  unsigned long long pass0;      // Philox pass index of the first pass
+  long long pass_phase;          // passes done before this launch (sample schedule)
+  long long sample_period;       // 0 = never
+  uint32_t rk[20];
+  int n_passes;                  // P
+  int n_tiles;
+  int halo;                      // 2*P, or 0 when n_tiles == 1
+  int w_max;                     // widest tile incl. halos (smem plane = w_max*h bytes)
+  uint32_t v_magic;              // ceil(2^32 / V), V = h/16
+};
+
+template <int NT>
+__device__ __forceinline__ void block_add2(long long a, long long b, long long *dst,
+                                           long long *sh /* [2*NT/32] */) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) {
+    sh[warp] = a;
+    sh[NT / 32 + warp] = b;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long ta = 0, tb = 0;
+    for (int w = 0; w < NT / 32; ++w) {
+      ta += sh[w];
+      tb += sh[NT / 32 + w];
+    }
+    atomicAdd((unsigned long long *)&dst[0], (unsigned long long)ta);
+    atomicAdd((unsigned long long *)&dst[1], (unsigned long long)tb);
+  }
+  __syncthreads();
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT, 1) k_tile2d(TileArgs A) {
+  extern __shared__ __align__(16) unsigned char tile_smem[];
+  __shared__ uint32_t s_nthr[16];
+  __shared__ long long s_red[2 * NT / 32];
+  const LatticeView &L = A.L;
+  const int chain = blockIdx.y;
+  const int tile = blockIdx.x;
+  if (threadIdx.x < 16) s_nthr[threadIdx.x] = ~A.tabs[chain].thr_m1[threadIdx.x];
+
+  const int h = L.h, n1 = L.n1;
+  const int V = h >> 4;
+  const bool periodic = (A.n_tiles == 1);
+  const int H = periodic ? 0 : A.halo;
+  const int c0 = (int)(((long long)tile * n1) / A.n_tiles);
+  const int c1 = (int)(((long long)(tile + 1) * n1) / A.n_tiles);
+  const int TW = c1 - c0;
+  const int W = TW + 2 * H;
+  unsigned char *S[2] = {tile_smem, tile_smem + (size_t)A.w_max * h};
+  uint8_t *G[2] = {L.planes + (long long)chain * L.chain_stride,
+                   L.planes + (long long)chain * L.chain_stride + L.plane_stride};
+  const uint32_t chain_word = (uint32_t)chain << 8;
+
+  // ---- stage the tile: local column cl <-> global column (c0 - H + cl) mod n1
+  for (int it = threadIdx.x; it < 2 * W * V; it += NT) {
+    const int plane = it >= W * V;
+    const int r = it - plane * W * V;
+    const int cl = (int)__umulhi((uint32_t)r, A.v_magic);
+    const int v = r - cl * V;
+    int gc = c0 - H + cl;
+    gc += (gc < 0) ? n1 : 0;
+    gc -= (gc >= n1) ? n1 : 0;
+    *reinterpret_cast<uint4 *>(S[plane] + (size_t)cl * h + (v << 4)) =
+        *reinterpret_cast<const uint4 *>(G[plane] + (long long)gc * h + (v << 4));
+  }
+  __syncthreads();
+
+  unsigned int n_acc = 0;
+  int slot = 0;
+  for (int s = 0; s < 2 * A.n_passes; ++s) {
+    const int colour = s & 1;
+    const int pl = s >> 1;
+    const unsigned long long pass = A.pass0 + (unsigned long long)pl;
+    const int lo = periodic ? 0 : s + 1;
+    const int hi = periodic ? W : W - 1 - s;
+    const bool sample = colour == 1 && A.sample_period > 0 &&
+                        ((A.pass_phase + pl + 1) % A.sample_period) == 0;
+    unsigned char *C = S[colour];
+    const unsigned char *O = S[1 - colour];
+    Accum acc = {0u, 0, 0};
+    const int items = (hi - lo) * V;
+    for (int it = threadIdx.x; it < items; it += NT) {
+      const int dc = (int)__umulhi((uint32_t)it, A.v_magic);
+      const int v = it - dc * V;
+      const int cl = lo + dc;
+      int cm = cl - 1, cp = cl + 1;
+      if (periodic) {
+        cm = (cm < 0) ? W - 1 : cm;
+        cp = (cp >= W) ? 0 : cp;
+      }
+      int gc = c0 - H + cl;
+      gc += (gc < 0) ? n1 : 0;
+      gc -= (gc >= n1) ? n1 : 0;
+      const int p0 = v << 4;
+      const int par = (gc + colour) & 1;  // i = 2p + par
+      const unsigned char *ocol = O + (size_t)cl * h;
+      const uint4 ce = *reinterpret_cast<const uint4 *>(C + (size_t)cl * h + p0);
+      const uint4 oc = *reinterpret_cast<const uint4 *>(ocol + p0);
+      const uint4 om = *reinterpret_cast<const uint4 *>(O + (size_t)cm * h + p0);
+      const uint4 op = *reinterpret_cast<const uint4 *>(O + (size_t)cp * h + p0);
+      uint4 side;
+      if (par == 0) {
+        side = shift_up_1(oc, ocol[(p0 == 0) ? h - 1 : p0 - 1]);
+      } else {
+        side = shift_down_1(oc, ocol[(p0 + 16 == h) ? 0 : p0 + 16]);
+      }
+      const unsigned long long group0 =
+          (unsigned long long)(((long long)h * gc + p0) >> 3);
+      Accum a = {0u, 0, 0};
+      uint4 cn;
+      if (sample)
+        cn = update16<true>(ce, om, oc, op, side, group0, pass, colour, chain_word, A.rk,
+                            s_nthr, 4, a);
+      else
+        cn = update16<false>(ce, om, oc, op, side, group0, pass, colour, chain_word, A.rk,
+                             s_nthr, 4, a);
+      *reinterpret_cast<uint4 *>(C + (size_t)cl * h + p0) = cn;
+      if (periodic || (cl >= H && cl < H + TW)) {  // count owned columns only
+        acc.acc += a.acc;
+        acc.ones += a.ones;
+        acc.bsum += a.bsum;
+      }
+    }
+    n_acc += acc.acc;
+    __syncthreads();
+    if (sample) {
+      block_add2<NT>((long long)acc.ones, (long long)acc.bsum,
+                     A.sb + (long long)slot * A.sb_slot_stride +
+                         (long long)chain * A.sb_chain_stride,
+                     s_red);
+      ++slot;
+    }
+  }
+
+  // ---- write the owned columns back
+  for (int it = threadIdx.x; it < 2 * TW * V; it += NT) {
+    const int plane = it >= TW * V;
+    const int r = it - plane * TW * V;
+    const int dc = (int)__umulhi((uint32_t)r, A.v_magic);
+    const int v = r - dc * V;
+    *reinterpret_cast<uint4 *>(G[plane] + (long long)(c0 + dc) * h + (v << 4)) =
+        *reinterpret_cast<const uint4 *>(S[plane] + (size_t)(H + dc) * h + (v << 4));
+  }
+  n_acc = __reduce_add_sync(0xffffffffu, n_acc);
+  if ((threadIdx.x & 31) == 0 && n_acc) atomicAdd(A.n_accept + chain, (unsigned long long)n_acc);
+}
+
+// ---------------------------------------------------------------------------
 // k_halfsweep_bulk3d: 3-d simple cubic, n0 % 32 == 0, n1 and n2 even.
 // Same scheme; the strip runs along j inside one k-layer, the k+-1 neighbours
 // are two extra 16-byte loads per column (served by L2: a k-layer of 512^3 is
@@ -401,8 +652,8 @@ template <bool SAMPLE>
 __global__ void __launch_bounds__(128) k_halfsweep_bulk3d(SweepArgs A) {
   const LatticeView &L = A.L;
   const int chain = blockIdx.y;
-  __shared__ uint32_t s_thr[16];
-  if (threadIdx.x < 16) s_thr[threadIdx.x] = A.tabs[chain].thr_m1[threadIdx.x];
+  __shared__ uint32_t s_thr[16];  // holds ~thr_m1 (see accept_mask4)
+  if (threadIdx.x < 16) s_thr[threadIdx.x] = ~A.tabs[chain].thr_m1[threadIdx.x];
   __syncthreads();
 
   const int h = L.h, n1 = L.n1, n2 = L.n2;
@@ -455,7 +706,7 @@ __global__ void __launch_bounds__(128) k_halfsweep_bulk3d(SweepArgs A) {
       side.z += ka.z + kb.z;
       side.w += ka.w + kb.w;
       const unsigned long long group0 =
-          (unsigned long long)((layer * k + off) >> 2);
+          (unsigned long long)((layer * k + off) >> 3);
       const uint4 cn = update16<SAMPLE>(ce, om, oc, op, side, group0, A.pass,
                                         A.colour, chain_word, A.rk, s_thr, 6, acc);
       *reinterpret_cast<uint4 *>(C + off) = cn;

@@ -35,7 +35,7 @@ class IsingLatticeGPU:
         self.n_chains = int(n_chains)
         self.device = int(device)
         self._ctx = C.c_void_p()
-        sh = (C.c_int64 * 3)(*(list(self.shape) + [1] * (3 - self.dim)))
+        sh = (C.c_int64 * max(3, self.dim))(*(list(self.shape) + [1] * (3 - self.dim)))
         if slab is None:
             check(self._lib.cmg_create(self.dim, sh, self.n_chains, self.device, C.byref(self._ctx)))
             self.local_shape = self.shape
@@ -142,7 +142,7 @@ class IsingLatticeGPU:
     def rng_draw(self, requests, chain=0):
         """requests: list of ('int', max) / ('real', max); returns list of draws."""
         n = len(requests)
-        imax = np.array([int(m) if k == "int" else 0 for k, m in requests], dtype=np.uint64).view(np.int64)
+        imax = np.fromiter((int(m) if k == "int" else 0 for k, m in requests), dtype=np.uint64, count=n).view(np.int64)
         rmax = np.array([float(m) if k == "real" else 0.0 for k, m in requests], dtype=np.float64)
         isr = np.array([1 if k == "real" else 0 for k, _ in requests], dtype=np.uint8)
         iout = np.zeros(n, dtype=np.int64)

@@ -1720,15 +1720,36 @@ inline AcceptTable make_accept_table(int dim, double J, double T, double mu) {
 
 // Checkerboard lattice update, scalar restatement of the production kernels.
 // Colour c = (i + j [+ k]) & 1.  Sites of one colour are numbered by the
-// "plane index" q = (i >> 1) + (n0/2) * (j + n1 * k); the 32-bit uniform of
-// site q in pass t, colour c, chain ch is word (q & 3) of
-//   Philox4x32-10(counter = {lo32(q>>2), (hi32(q>>2)&0xff) | ch<<8, lo32(t),
-//                            (hi32(t)<<1)|c},
-//                 key     = {lo32(seed), hi32(seed)}).
+// "plane index" q = (i >> 1) + (n0/2) * (j + n1 * k).  The acceptance uniform
+// of site q in pass t, colour c, chain ch is the 32-bit integer
+//     R = (r16 << 16) | r16'
+// where r16 is 16-bit lane (q & 7) of
+//   Philox4x32-10(counter = {lo32(q>>3), (hi32(q>>3)&0xff) | ch<<8, lo32(t),
+//                            (hi32(t)<<2) | c},          key = {lo32(seed), hi32(seed)})
+// (lane l = bits [16*(l&1), 16*(l&1)+16) of output word l>>1) and r16' is the
+// same lane of the call with counter word 3 | 2 ("refinement" stream; the
+// kernels only evaluate it when r16 ties with the top half of the threshold).
+// The site is flipped iff R <= thr_m1[b][n_up].
 // Requires even extents.  One pass = colour 0 half-sweep then colour 1.
 struct CheckerboardResult {
   long long n_accept = 0;
 };
+inline uint32_t checkerboard_uniform(uint64_t q, uint32_t chain, uint64_t pass_index,
+                                     int colour, std::array<uint32_t, 2> key) {
+  const uint64_t g = q >> 3;
+  const int lane = static_cast<int>(q & 7);
+  std::array<uint32_t, 4> ctr = {
+      static_cast<uint32_t>(g),
+      (static_cast<uint32_t>(g >> 32) & 0xffu) | (chain << 8),
+      static_cast<uint32_t>(pass_index),
+      (static_cast<uint32_t>(pass_index >> 32) << 2) | static_cast<uint32_t>(colour)};
+  const uint32_t w0 = Philox4x32::generate(ctr, key)[lane >> 1];
+  ctr[3] |= 2u;
+  const uint32_t w1 = Philox4x32::generate(ctr, key)[lane >> 1];
+  const uint32_t r16 = (w0 >> (16 * (lane & 1))) & 0xffffu;
+  const uint32_t r16b = (w1 >> (16 * (lane & 1))) & 0xffffu;
+  return (r16 << 16) | r16b;
+}
 inline void checkerboard_pass(std::vector<int> &occ, std::vector<int> const &shape,
                               AcceptTable const &tab, uint64_t seed,
                               uint32_t chain, uint64_t pass_index,
@@ -1748,14 +1769,7 @@ inline void checkerboard_pass(std::vector<int> &occ, std::vector<int> const &sha
                        static_cast<uint64_t>(h) *
                            (static_cast<uint64_t>(j) +
                             static_cast<uint64_t>(n1) * static_cast<uint64_t>(k));
-          uint64_t g = q >> 2;
-          std::array<uint32_t, 4> ctr = {
-              static_cast<uint32_t>(g),
-              (static_cast<uint32_t>(g >> 32) & 0xffu) | (chain << 8),
-              static_cast<uint32_t>(pass_index),
-              (static_cast<uint32_t>(pass_index >> 32) << 1) |
-                  static_cast<uint32_t>(colour)};
-          uint32_t r = Philox4x32::generate(ctr, key)[q & 3];
+          uint32_t r = checkerboard_uniform(q, chain, pass_index, colour, key);
           long ip = (i + 1) % n0, im = (i + n0 - 1) % n0;
           long jp = (j + 1) % n1, jm = (j + n1 - 1) % n1;
           int n_up = (occ[ip + n0 * (j + n1 * k)] > 0) +

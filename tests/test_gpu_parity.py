@@ -189,6 +189,52 @@ def test_bulk2d_matches_oracle(cm, oracle, shape, js):
     assert lat.counters()[1] == ref["n_accept"]
 
 
+@pytest.mark.parametrize(
+    "shape,variant",
+    [
+        ([64, 48], "tile2d"),  # whole lattice in one tile: periodic columns, many passes per launch
+        ([256, 256], "tile2d"),
+        ([64, 6], "tile2d:nt=256"),
+        ([4096, 64], "tile2d"),  # 64 one-column tiles with 4-column halos (2 passes per launch)
+        ([4096, 64], "tile2d:p=1"),
+        ([4096, 64], "tile2d:p=3:nt=1024"),
+        ([1024, 512], "tile2d:p=2"),
+        ([1024, 514], "tile2d:p=4:nt=256"),  # uneven tile widths
+    ],
+)
+def test_tile2d_matches_oracle(cm, oracle, shape, variant):
+    n = nsites(shape)
+    occ = rand_occ(n, 24)
+    T, mu = 2633.0, 0.02
+    lat = run_cb(cm, shape, occ, T, mu, 424242, 5, variant, sample_period=2)
+    assert lat.kernel_variant == "tile2d"
+    ref = oracle.checkerboard_run(shape, occ, J, T, mu, 424242, 0, 0, 5, 2)
+    assert np.array_equal(lat.download(), ref["occupation"])
+    S, B = lat.samples_sb()
+    assert np.array_equal(S, ref["S"]) and np.array_equal(B, ref["B"])
+    assert lat.counters()[1] == ref["n_accept"]
+    # continue with sampling every pass: the schedule phase carries over launches
+    lat.run_passes(3, cm.MODE_CHECKERBOARD, 1)
+    ref2 = oracle.checkerboard_run(shape, ref["occupation"], J, T, mu, 424242, 0, 5, 3, 1)
+    assert np.array_equal(lat.download(), ref2["occupation"])
+    S2, B2 = lat.samples_sb(first=len(S))
+    assert np.array_equal(S2, ref2["S"]) and np.array_equal(B2, ref2["B"])
+
+
+def test_threshold_ties_take_the_exact_path(cm, oracle):
+    # mu chosen so that a threshold's top half is hit often is impossible to arrange
+    # (probability 2^-16 per site); instead run enough sites that ties occur:
+    # 1024x1024 x 8 passes = 8.4M attempts -> ~128 expected ties; every one must
+    # resolve exactly as the oracle's 32-bit compare does.
+    shape = [1024, 1024]
+    occ = rand_occ(nsites(shape), 25)
+    for variant in ("tile2d", "bulk2d"):
+        lat = run_cb(cm, shape, occ, 2633.0, 0.013, 31337, 8, variant, sample_period=8)
+        ref = oracle.checkerboard_run(shape, occ, J, 2633.0, 0.013, 31337, 0, 0, 8, 8)
+        assert np.array_equal(lat.download(), ref["occupation"])
+        assert lat.counters()[1] == ref["n_accept"]
+
+
 @pytest.mark.parametrize("shape", [[32, 4, 2], [64, 6, 4], [32, 10, 8]])
 def test_bulk3d_matches_oracle(cm, oracle, shape):
     n = nsites(shape)
@@ -209,7 +255,7 @@ def test_multichain_grid_matches_oracle(cm, oracle):
     n = nsites(shape)
     conds = [(t, m) for t in (1500.0, 4000.0) for m in (-0.2, 0.0, 0.2)]
     occs = [rand_occ(n, 100 + i) for i in range(len(conds))]
-    for variant in ("generic", "bulk2d"):
+    for variant in ("generic", "bulk2d", "tile2d"):
         lat = run_cb(cm, shape, occs, None, None, 777, 5, variant, n_chains=len(conds), chain_conditions=conds)
         for ch, (t, m) in enumerate(conds):
             ref = oracle.checkerboard_run(shape, occs[ch], J, t, m, 777, ch, 0, 5, 1)
@@ -225,7 +271,7 @@ def test_pass_counter_continuation(cm, oracle):
     shape = [64, 16]
     occ = rand_occ(nsites(shape), 31)
     a = run_cb(cm, shape, occ, 2500.0, 0.0, 5, 6, "bulk2d")
-    b = run_cb(cm, shape, occ, 2500.0, 0.0, 5, 2, "bulk2d")
+    b = run_cb(cm, shape, occ, 2500.0, 0.0, 5, 2, "tile2d")
     b.run_passes(4, cm.MODE_CHECKERBOARD, 1)
     assert np.array_equal(a.download(), b.download())
     assert np.array_equal(a.samples_sb()[1], b.samples_sb()[1])
@@ -411,14 +457,17 @@ def test_full_size_4096_properties(cm):
     assert int(g.sum()) == S[-1]
     assert int((g * (np.roll(g, -1, 0) + np.roll(g, -1, 1))).sum()) == B[-1]
     assert lat.counters(0)[1] + lat.counters(0)[2] == 3 * n
-    # bulk2d and the generic kernel agree at full size
-    lat3 = cm.IsingLatticeGPU(shape, J=J)
-    lat3.set_conditions(2633.0, 0.0)
-    lat3.seed_philox(0xC0FFEE)
-    lat3.set_kernel_variant("generic")
-    lat3.upload(a0)
-    lat3.run_passes(3, cm.MODE_CHECKERBOARD, 1)
-    assert np.array_equal(lat3.download(0), a3)
+    # the tiled kernel (auto), bulk2d and the generic kernel agree at full size
+    assert lat.kernel_variant == "tile2d"
+    for variant in ("generic", "bulk2d"):
+        lat3 = cm.IsingLatticeGPU(shape, J=J)
+        lat3.set_conditions(2633.0, 0.0)
+        lat3.seed_philox(0xC0FFEE)
+        lat3.set_kernel_variant(variant)
+        lat3.upload(a0)
+        lat3.run_passes(3, cm.MODE_CHECKERBOARD, 1)
+        assert np.array_equal(lat3.download(0), a3)
+        assert np.array_equal(lat3.samples_sb(0)[1], B)
     # frozen limit: T -> 0+ from all-up never flips (dE = 8J > 0, exp(-dE*beta) underflows)
     lat4 = cm.IsingLatticeGPU(shape, J=J)
     lat4.set_conditions(1.0, 0.0)
