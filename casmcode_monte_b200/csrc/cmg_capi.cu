@@ -759,7 +759,7 @@ static TilePlan plan_tiles(const cmg_context *c, long long passes_wanted) {
     t.passes = (int)std::min<long long>(passes_wanted, 64);
     t.halo = 0;
     t.w_max = (int)n1;
-    t.smem = (size_t)(2 * n1 * h);
+    t.smem = (size_t)(2 * n1 * h) + kSmemTile;
     return t;
   }
   const int P = (int)std::min<long long>(passes_wanted, c->tile_passes);
@@ -783,7 +783,7 @@ static TilePlan plan_tiles(const cmg_context *c, long long passes_wanted) {
   t.passes = P;
   t.halo = (int)H;
   t.w_max = (int)(tw_max2 + 2 * H);
-  t.smem = (size_t)(2 * t.w_max * h);
+  t.smem = (size_t)(2 * t.w_max * h) + kSmemTile;
   return t;
 }
 
@@ -828,25 +828,25 @@ static int launch_half_sweep(cmg_context *c, int variant, int colour, unsigned l
   if (variant == V_GENERIC) {
     dim3 grid(nblocks((plane_size + 7) / 8, 128), c->n_chains);
     if (sample)
-      k_halfsweep_generic<true><<<grid, block, 0, c->stream>>>(A);
+      k_halfsweep_generic<true><<<grid, block, kSmemTile, c->stream>>>(A);
     else
-      k_halfsweep_generic<false><<<grid, block, 0, c->stream>>>(A);
+      k_halfsweep_generic<false><<<grid, block, kSmemTile, c->stream>>>(A);
   } else if (variant == V_BULK2D) {
     const long long V = c->shape[0] / 32;
     const long long strips = (c->shape[1] + A.js - 1) / A.js;
     dim3 grid(nblocks(V * strips, 128), c->n_chains);
     if (sample)
-      k_halfsweep_bulk2d<true><<<grid, block, 0, c->stream>>>(A);
+      k_halfsweep_bulk2d<true><<<grid, block, kSmemTile, c->stream>>>(A);
     else
-      k_halfsweep_bulk2d<false><<<grid, block, 0, c->stream>>>(A);
+      k_halfsweep_bulk2d<false><<<grid, block, kSmemTile, c->stream>>>(A);
   } else if (variant == V_BULK3D) {
     const long long V = c->shape[0] / 32;
     const long long strips = (c->shape[1] + A.js - 1) / A.js;
     dim3 grid(nblocks(V * strips * c->shape[2], 128), c->n_chains);
     if (sample)
-      k_halfsweep_bulk3d<true><<<grid, block, 0, c->stream>>>(A);
+      k_halfsweep_bulk3d<true><<<grid, block, kSmemTile, c->stream>>>(A);
     else
-      k_halfsweep_bulk3d<false><<<grid, block, 0, c->stream>>>(A);
+      k_halfsweep_bulk3d<false><<<grid, block, kSmemTile, c->stream>>>(A);
   } else {
     return fail(c, CMG_EUNSUPPORTED, "kernel variant not available");
   }

@@ -104,6 +104,22 @@ __device__ __forceinline__ uint4 site_group_random(unsigned long long group,
   return philox4x32_10(c, rk);
 }
 
+// All sweep kernels use one dynamic shared-memory buffer.  Its first 64 bytes
+// hold the chain's acceptance table as ~thr_m1 (16 x u32); tile data follows at
+// kSmemTile.  Declaring it at namespace scope keeps every access a plain LDS
+// with a constant offset (no generic-address conversion).
+extern __shared__ __align__(16) unsigned char cmg_smem[];
+constexpr int kSmemTile = 128;
+
+__device__ __forceinline__ void load_accept_table(const ChainTables *tab) {
+  if (threadIdx.x < 16)
+    reinterpret_cast<uint32_t *>(cmg_smem)[threadIdx.x] = ~tab->thr_m1[threadIdx.x];
+}
+// byte_off = 4 * table index
+__device__ __forceinline__ uint32_t nthr_at(uint32_t byte_off) {
+  return *reinterpret_cast<const uint32_t *>(cmg_smem + byte_off);
+}
+
 // Acceptance of 4 sites packed in a word.  Each site's uniform is the 32-bit
 // integer R = r16<<16 | r16' and the site is flipped iff R <= thr (thr =
 // thr_m1 of its table entry).  Only r16 is generated up front: with Y = r16<<16,
@@ -111,20 +127,19 @@ __device__ __forceinline__ uint4 site_group_random(unsigned long long group,
 //   Y <= thr - 65536      -> accepted whatever r16' is,
 //   otherwise (r16 equals the top half of thr, probability 2^-16) a tie that
 //   needs r16'.
-// idx4: table index of each site in its byte; r01 / r23: the Philox words
-// holding the r16 of sites (0,1) / (2,3) in their (low, high) halves; nthr:
-// table of ~thr.  D = Y + ~thr carries out iff Y > thr (2 instructions per site
-// through the carry flag, no predicates), and D >= 0xFFFF0000 iff tie, tracked
-// with one max per site.  Returns 0x01 in the byte of every (provisionally)
-// accepted site; ties count as accepted here and are resolved by the caller
-// when dmax >= 0xFFFF0000.
-__device__ __forceinline__ uint32_t accept_mask4_fast(uint32_t idx4, uint32_t r01,
-                                                      uint32_t r23, const uint32_t *nthr,
-                                                      uint32_t &dmax) {
-  const uint32_t t0 = nthr[idx4 & 0xffu];
-  const uint32_t t1 = nthr[__byte_perm(idx4, 0u, 0x4441u)];
-  const uint32_t t2 = nthr[__byte_perm(idx4, 0u, 0x4442u)];
-  const uint32_t t3 = nthr[idx4 >> 24];
+// idx4s: 4 * table index of each site in its byte; r01 / r23: the Philox words
+// holding the r16 of sites (0,1) / (2,3) in their (low, high) halves.
+// D = Y + ~thr carries out iff Y > thr (2 instructions per site through the
+// carry flag, no predicates), and D >= 0xFFFF0000 iff tie, tracked with one max
+// per site.  Returns 0x01 in the byte of every (provisionally) accepted site;
+// ties count as accepted here and are resolved by the caller when
+// dmax >= 0xFFFF0000.
+__device__ __forceinline__ uint32_t accept_mask4_fast(uint32_t idx4s, uint32_t r01,
+                                                      uint32_t r23, uint32_t &dmax) {
+  const uint32_t t0 = nthr_at(idx4s & 0xffu);
+  const uint32_t t1 = nthr_at(__byte_perm(idx4s, 0u, 0x4441u));
+  const uint32_t t2 = nthr_at(__byte_perm(idx4s, 0u, 0x4442u));
+  const uint32_t t3 = nthr_at(idx4s >> 24);
   const uint32_t y0 = r01 << 16, y1 = r01 & 0xffff0000u;
   const uint32_t y2 = r23 << 16, y3 = r23 & 0xffff0000u;
   uint32_t rej, mx = dmax;
@@ -220,8 +235,7 @@ template <bool SAMPLE>
 __global__ void __launch_bounds__(128) k_halfsweep_generic(SweepArgs A) {
   const LatticeView &L = A.L;
   const int chain = blockIdx.y;
-  __shared__ uint32_t s_thr[16];
-  if (threadIdx.x < 16) s_thr[threadIdx.x] = A.tabs[chain].thr_m1[threadIdx.x];
+  load_accept_table(A.tabs + chain);
   __syncthreads();
 
   uint8_t *C = L.planes + (long long)chain * L.chain_stride +
@@ -261,7 +275,7 @@ __global__ void __launch_bounds__(128) k_halfsweep_generic(SweepArgs A) {
                 O[p + (long long)L.h * (j + (long long)L.n1 * kp)];
       }
       int b = C[q];
-      if (accept_exact(lane16(ra, w), lane16(rb, w), s_thr[2 * n_up + b])) {
+      if (accept_exact(lane16(ra, w), lane16(rb, w), ~nthr_at(4u * (2 * n_up + b)))) {
         b ^= 1;
         C[q] = (uint8_t)b;
         ++acc;
@@ -315,20 +329,13 @@ __device__ __forceinline__ uint4 shift_down_1(uint4 v, uint32_t hi) {
   return o;
 }
 
-struct Accum {
-  unsigned int acc;
-  int ones;
-  int bsum;
-};
-
 // Rare path: some site of a 16-site vector tied on its leading 16 bits.  Redo
 // all 16 decisions exactly with both halves (regenerating the leading words so
 // the hot path does not have to keep them alive).
-__device__ __noinline__ uint4 resolve_ties16(uint4 idx, unsigned long long group0,
+__device__ __noinline__ uint4 resolve_ties16(uint4 idx4s, unsigned long long group0,
                                              unsigned long long pass, int colour,
-                                             uint32_t chain_word, const uint32_t *rk,
-                                             const uint32_t *s_nthr) {
-  const uint32_t iw[4] = {idx.x, idx.y, idx.z, idx.w};
+                                             uint32_t chain_word, const uint32_t *rk) {
+  const uint32_t iw[4] = {idx4s.x, idx4s.y, idx4s.z, idx4s.w};
   uint32_t m[4];
   for (int half = 0; half < 2; ++half) {
     const uint4 r = site_group_random(group0 + half, chain_word, pass, colour, 0, rk);
@@ -340,13 +347,29 @@ __device__ __noinline__ uint4 resolve_ties16(uint4 idx, unsigned long long group
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int lane = 4 * ww + k;
-        const uint32_t thr = ~s_nthr[(iw[w] >> (8 * k)) & 0xffu];
+        const uint32_t thr = ~nthr_at((iw[w] >> (8 * k)) & 0xffu);
         mm |= accept_exact(lane16(r, lane), lane16(q, lane), thr) ? (1u << (8 * k)) : 0u;
       }
       m[w] = mm;
     }
   }
   return make_uint4(m[0], m[1], m[2], m[3]);
+}
+
+// Per-thread accumulators.  Sampling terms are kept as raw byte sums and turned
+// into (ones, B) once, at the end of the thread's work:
+//   c1   = #(b = 1) among the updated sites,   opp = #(b = 1) of the facing sites
+//   u7   = sum over updated sites of (b ? n : 7 - n),   n = # of +1 neighbours
+//   B    = sum (2b-1)(2n-z) = 2*u7 - 2*(7-z)*(sites - c1) - z*sites
+struct Accum {
+  unsigned int acc;
+  unsigned int c1, opp, u7, sites;
+};
+__device__ __forceinline__ void accum_finish(const Accum &a, int z, long long &ones,
+                                             long long &bsum) {
+  ones = (long long)a.c1 + (long long)a.opp;
+  bsum = 2ll * a.u7 - 2ll * (7 - z) * ((long long)a.sites - (long long)a.c1) -
+         (long long)z * a.sites;
 }
 
 // Update 16 sites (one 16-byte vector of a colour plane); returns the new
@@ -356,7 +379,6 @@ __device__ __forceinline__ uint4 update16(uint4 ce, uint4 om, uint4 oc, uint4 op
                                           uint4 side, unsigned long long group0,
                                           unsigned long long pass, int colour,
                                           uint32_t chain_word, const uint32_t *rk,
-                                          const uint32_t *s_nthr, int z,
                                           Accum &a) {
   uint32_t cw[4] = {ce.x, ce.y, ce.z, ce.w};
   const uint32_t nw[4] = {om.x + oc.x + op.x + side.x, om.y + oc.y + op.y + side.y,
@@ -368,13 +390,12 @@ __device__ __forceinline__ uint4 update16(uint4 ce, uint4 om, uint4 oc, uint4 op
   uint32_t idx[4], m[4], dmax = 0;
 #pragma unroll
   for (int w = 0; w < 4; ++w) {
-    idx[w] = nw[w] + nw[w] + cw[w];
-    m[w] = accept_mask4_fast(idx[w], rw[2 * w], rw[2 * w + 1], s_nthr, dmax);
+    idx[w] = (nw[w] + nw[w] + cw[w]) << 2;  // 4 * (2*n_up + b) per byte, <= 52
+    m[w] = accept_mask4_fast(idx[w], rw[2 * w], rw[2 * w + 1], dmax);
   }
-  if (dmax >= 0xffff0000u)  // a tie somewhere in these 16 sites (probability 16 * 2^-16)
-  {
+  if (dmax >= 0xffff0000u) {  // a tie somewhere in these 16 sites (probability 16 * 2^-16)
     const uint4 mm = resolve_ties16(make_uint4(idx[0], idx[1], idx[2], idx[3]), group0, pass,
-                                    colour, chain_word, rk, s_nthr);
+                                    colour, chain_word, rk);
     m[0] = mm.x;
     m[1] = mm.y;
     m[2] = mm.z;
@@ -383,15 +404,15 @@ __device__ __forceinline__ uint4 update16(uint4 ce, uint4 om, uint4 oc, uint4 op
 #pragma unroll
   for (int w = 0; w < 4; ++w) {
     cw[w] ^= m[w];
-    a.acc += __popc(m[w]);
+    a.acc = __dp4a(m[w], 0x01010101u, a.acc);
     if (SAMPLE) {
-      // ones of both planes; B = sum (2b-1)(2n-z) = 4*sum_{b=1} n - 2*sum n - z*(2*ones_c - 4)
-      const uint32_t sel = nw[w] & (cw[w] * 0xffu);
-      const int c1 = bytesum(cw[w]);
-      a.ones += c1 + bytesum(ow[w]);
-      a.bsum += 4 * bytesum(sel) - 2 * bytesum(nw[w]) - z * (2 * c1 - 4);
+      const uint32_t flip7 = ~(cw[w] * 0xffu) & 0x07070707u;  // 7 where b = 0
+      a.u7 = __dp4a(nw[w] ^ flip7, 0x01010101u, a.u7);
+      a.c1 = __dp4a(cw[w], 0x01010101u, a.c1);
+      a.opp = __dp4a(ow[w], 0x01010101u, a.opp);
     }
   }
+  if (SAMPLE) a.sites += 16;
   return make_uint4(cw[0], cw[1], cw[2], cw[3]);
 }
 
@@ -399,15 +420,14 @@ template <bool SAMPLE>
 __global__ void __launch_bounds__(128) k_halfsweep_bulk2d(SweepArgs A) {
   const LatticeView &L = A.L;
   const int chain = blockIdx.y;
-  __shared__ uint32_t s_thr[16];  // holds ~thr_m1 (see accept_mask4)
-  if (threadIdx.x < 16) s_thr[threadIdx.x] = ~A.tabs[chain].thr_m1[threadIdx.x];
+  load_accept_table(A.tabs + chain);
   __syncthreads();
 
   const int h = L.h, n1 = L.n1;
   const int V = h >> 4;  // 16-byte vectors per column
   const int n_strips = (n1 + A.js - 1) / A.js;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  Accum acc = {0u, 0, 0};
+  Accum acc = {0u, 0u, 0u, 0u, 0u};
 
   if (t < (long long)V * n_strips) {
     const int v = (int)(t % V);
@@ -452,7 +472,7 @@ __global__ void __launch_bounds__(128) k_halfsweep_bulk2d(SweepArgs A) {
       const unsigned long long group0 =
           (unsigned long long)(((long long)h * jg + p0) >> 3);
       const uint4 cn = update16<SAMPLE>(ce, om, oc, op, side, group0, A.pass,
-                                        A.colour, chain_word, A.rk, s_thr, 4, acc);
+                                        A.colour, chain_word, A.rk, acc);
       *reinterpret_cast<uint4 *>(C + (long long)h * j + p0) = cn;
       if (push_lo && j == 0) *reinterpret_cast<uint4 *>(push_lo + p0) = cn;
       if (push_hi && j == n1 - 1) *reinterpret_cast<uint4 *>(push_hi + p0) = cn;
@@ -460,8 +480,9 @@ __global__ void __launch_bounds__(128) k_halfsweep_bulk2d(SweepArgs A) {
       oc = op;
     }
   }
-  block_accumulate<128>(acc.acc, (long long)acc.ones, (long long)acc.bsum, SAMPLE,
-                        A.n_accept + chain,
+  long long ones = 0, bsum = 0;
+  if (SAMPLE) accum_finish(acc, 4, ones, bsum);
+  block_accumulate<128>(acc.acc, ones, bsum, SAMPLE, A.n_accept + chain,
                         SAMPLE ? A.sb + (long long)chain * A.sb_chain_stride : nullptr);
 }
 
@@ -525,15 +546,21 @@ __device__ __forceinline__ void block_add2(long long a, long long b, long long *
   __syncthreads();
 }
 
+// 16-byte shared-memory accesses by byte offset into cmg_smem
+__device__ __forceinline__ uint4 lds16(uint32_t off) {
+  return *reinterpret_cast<const uint4 *>(cmg_smem + off);
+}
+__device__ __forceinline__ void sts16(uint32_t off, uint4 v) {
+  *reinterpret_cast<uint4 *>(cmg_smem + off) = v;
+}
+
 template <int NT>
 __global__ void __launch_bounds__(NT, 1) k_tile2d(TileArgs A) {
-  extern __shared__ __align__(16) unsigned char tile_smem[];
-  __shared__ uint32_t s_nthr[16];
   __shared__ long long s_red[2 * NT / 32];
   const LatticeView &L = A.L;
   const int chain = blockIdx.y;
   const int tile = blockIdx.x;
-  if (threadIdx.x < 16) s_nthr[threadIdx.x] = ~A.tabs[chain].thr_m1[threadIdx.x];
+  load_accept_table(A.tabs + chain);
 
   const int h = L.h, n1 = L.n1;
   const int V = h >> 4;
@@ -543,7 +570,8 @@ __global__ void __launch_bounds__(NT, 1) k_tile2d(TileArgs A) {
   const int c1 = (int)(((long long)(tile + 1) * n1) / A.n_tiles);
   const int TW = c1 - c0;
   const int W = TW + 2 * H;
-  unsigned char *S[2] = {tile_smem, tile_smem + (size_t)A.w_max * h};
+  // byte offsets of the two colour planes of the tile inside cmg_smem
+  const uint32_t soff[2] = {(uint32_t)kSmemTile, (uint32_t)kSmemTile + (uint32_t)A.w_max * (uint32_t)h};
   uint8_t *G[2] = {L.planes + (long long)chain * L.chain_stride,
                    L.planes + (long long)chain * L.chain_stride + L.plane_stride};
   const uint32_t chain_word = (uint32_t)chain << 8;
@@ -557,8 +585,8 @@ __global__ void __launch_bounds__(NT, 1) k_tile2d(TileArgs A) {
     int gc = c0 - H + cl;
     gc += (gc < 0) ? n1 : 0;
     gc -= (gc >= n1) ? n1 : 0;
-    *reinterpret_cast<uint4 *>(S[plane] + (size_t)cl * h + (v << 4)) =
-        *reinterpret_cast<const uint4 *>(G[plane] + (long long)gc * h + (v << 4));
+    sts16(soff[plane] + (uint32_t)(cl * h + (v << 4)),
+          __ldg(reinterpret_cast<const uint4 *>(G[plane] + (long long)gc * h + (v << 4))));
   }
   __syncthreads();
 
@@ -572,56 +600,55 @@ __global__ void __launch_bounds__(NT, 1) k_tile2d(TileArgs A) {
     const int hi = periodic ? W : W - 1 - s;
     const bool sample = colour == 1 && A.sample_period > 0 &&
                         ((A.pass_phase + pl + 1) % A.sample_period) == 0;
-    unsigned char *C = S[colour];
-    const unsigned char *O = S[1 - colour];
-    Accum acc = {0u, 0, 0};
+    const uint32_t cbase = colour ? soff[1] : soff[0];
+    const uint32_t obase = colour ? soff[0] : soff[1];
+    // global column of local column lo, its parity and Philox group base
+    int gc_lo = c0 - H + lo;
+    gc_lo += (gc_lo < 0) ? n1 : 0;
+    Accum acc = {0u, 0u, 0u, 0u, 0u};
     const int items = (hi - lo) * V;
     for (int it = threadIdx.x; it < items; it += NT) {
       const int dc = (int)__umulhi((uint32_t)it, A.v_magic);
-      const int v = it - dc * V;
+      const int p0 = (it - dc * V) << 4;
       const int cl = lo + dc;
       int cm = cl - 1, cp = cl + 1;
       if (periodic) {
         cm = (cm < 0) ? W - 1 : cm;
         cp = (cp >= W) ? 0 : cp;
       }
-      int gc = c0 - H + cl;
-      gc += (gc < 0) ? n1 : 0;
+      int gc = gc_lo + dc;
       gc -= (gc >= n1) ? n1 : 0;
-      const int p0 = v << 4;
-      const int par = (gc + colour) & 1;  // i = 2p + par
-      const unsigned char *ocol = O + (size_t)cl * h;
-      const uint4 ce = *reinterpret_cast<const uint4 *>(C + (size_t)cl * h + p0);
-      const uint4 oc = *reinterpret_cast<const uint4 *>(ocol + p0);
-      const uint4 om = *reinterpret_cast<const uint4 *>(O + (size_t)cm * h + p0);
-      const uint4 op = *reinterpret_cast<const uint4 *>(O + (size_t)cp * h + p0);
+      const uint32_t col_off = (uint32_t)(cl * h);
+      const uint4 ce = lds16(cbase + col_off + p0);
+      const uint4 oc = lds16(obase + col_off + p0);
+      const uint4 om = lds16(obase + (uint32_t)(cm * h) + p0);
+      const uint4 op = lds16(obase + (uint32_t)(cp * h) + p0);
       uint4 side;
-      if (par == 0) {
-        side = shift_up_1(oc, ocol[(p0 == 0) ? h - 1 : p0 - 1]);
-      } else {
-        side = shift_down_1(oc, ocol[(p0 + 16 == h) ? 0 : p0 + 16]);
+      if (((gc + colour) & 1) == 0) {  // i = 2p: the other i-neighbour is p-1
+        side = shift_up_1(oc, cmg_smem[obase + col_off + ((p0 == 0) ? h - 1 : p0 - 1)]);
+      } else {  // i = 2p+1: p+1
+        side = shift_down_1(oc, cmg_smem[obase + col_off + ((p0 + 16 == h) ? 0 : p0 + 16)]);
       }
       const unsigned long long group0 =
           (unsigned long long)(((long long)h * gc + p0) >> 3);
-      Accum a = {0u, 0, 0};
+      const bool owned = periodic || (cl >= H && cl < H + TW);
       uint4 cn;
-      if (sample)
-        cn = update16<true>(ce, om, oc, op, side, group0, pass, colour, chain_word, A.rk,
-                            s_nthr, 4, a);
-      else
+      if (sample && owned) {
+        cn = update16<true>(ce, om, oc, op, side, group0, pass, colour, chain_word, A.rk, acc);
+      } else {
+        Accum scratch = {0u, 0u, 0u, 0u, 0u};
         cn = update16<false>(ce, om, oc, op, side, group0, pass, colour, chain_word, A.rk,
-                             s_nthr, 4, a);
-      *reinterpret_cast<uint4 *>(C + (size_t)cl * h + p0) = cn;
-      if (periodic || (cl >= H && cl < H + TW)) {  // count owned columns only
-        acc.acc += a.acc;
-        acc.ones += a.ones;
-        acc.bsum += a.bsum;
+                             scratch);
+        if (owned) acc.acc += scratch.acc;
       }
+      sts16(cbase + col_off + p0, cn);
     }
     n_acc += acc.acc;
     __syncthreads();
     if (sample) {
-      block_add2<NT>((long long)acc.ones, (long long)acc.bsum,
+      long long ones, bsum;
+      accum_finish(acc, 4, ones, bsum);
+      block_add2<NT>(ones, bsum,
                      A.sb + (long long)slot * A.sb_slot_stride +
                          (long long)chain * A.sb_chain_stride,
                      s_red);
@@ -636,7 +663,7 @@ __global__ void __launch_bounds__(NT, 1) k_tile2d(TileArgs A) {
     const int dc = (int)__umulhi((uint32_t)r, A.v_magic);
     const int v = r - dc * V;
     *reinterpret_cast<uint4 *>(G[plane] + (long long)(c0 + dc) * h + (v << 4)) =
-        *reinterpret_cast<const uint4 *>(S[plane] + (size_t)(H + dc) * h + (v << 4));
+        lds16(soff[plane] + (uint32_t)((H + dc) * h + (v << 4)));
   }
   n_acc = __reduce_add_sync(0xffffffffu, n_acc);
   if ((threadIdx.x & 31) == 0 && n_acc) atomicAdd(A.n_accept + chain, (unsigned long long)n_acc);
@@ -652,15 +679,14 @@ template <bool SAMPLE>
 __global__ void __launch_bounds__(128) k_halfsweep_bulk3d(SweepArgs A) {
   const LatticeView &L = A.L;
   const int chain = blockIdx.y;
-  __shared__ uint32_t s_thr[16];  // holds ~thr_m1 (see accept_mask4)
-  if (threadIdx.x < 16) s_thr[threadIdx.x] = ~A.tabs[chain].thr_m1[threadIdx.x];
+  load_accept_table(A.tabs + chain);
   __syncthreads();
 
   const int h = L.h, n1 = L.n1, n2 = L.n2;
   const int V = h >> 4;
   const int n_strips = (n1 + A.js - 1) / A.js;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  Accum acc = {0u, 0, 0};
+  Accum acc = {0u, 0u, 0u, 0u, 0u};
 
   if (t < (long long)V * n_strips * n2) {
     const int v = (int)(t % V);
@@ -708,14 +734,15 @@ __global__ void __launch_bounds__(128) k_halfsweep_bulk3d(SweepArgs A) {
       const unsigned long long group0 =
           (unsigned long long)((layer * k + off) >> 3);
       const uint4 cn = update16<SAMPLE>(ce, om, oc, op, side, group0, A.pass,
-                                        A.colour, chain_word, A.rk, s_thr, 6, acc);
+                                        A.colour, chain_word, A.rk, acc);
       *reinterpret_cast<uint4 *>(C + off) = cn;
       om = oc;
       oc = op;
     }
   }
-  block_accumulate<128>(acc.acc, (long long)acc.ones, (long long)acc.bsum, SAMPLE,
-                        A.n_accept + chain,
+  long long ones = 0, bsum = 0;
+  if (SAMPLE) accum_finish(acc, 6, ones, bsum);
+  block_accumulate<128>(acc.acc, ones, bsum, SAMPLE, A.n_accept + chain,
                         SAMPLE ? A.sb + (long long)chain * A.sb_chain_stride : nullptr);
 }
 

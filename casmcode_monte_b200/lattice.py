@@ -142,7 +142,7 @@ class IsingLatticeGPU:
     def rng_draw(self, requests, chain=0):
         """requests: list of ('int', max) / ('real', max); returns list of draws."""
         n = len(requests)
-        imax = np.fromiter((int(m) if k == "int" else 0 for k, m in requests), dtype=np.uint64, count=n).view(np.int64)
+        imax = np.frombuffer((C.c_uint64 * n)(*[int(m) if k == "int" else 0 for k, m in requests]), dtype=np.uint64).view(np.int64).copy()
         rmax = np.array([float(m) if k == "real" else 0.0 for k, m in requests], dtype=np.float64)
         isr = np.array([1 if k == "real" else 0 for k, _ in requests], dtype=np.uint8)
         iout = np.zeros(n, dtype=np.int64)
