@@ -6,10 +6,14 @@ prints ONE JSON line.  A "step" is PASSES_PER_STEP checkerboard passes (one
 pass = one attempted flip per site, on-device sampling of energy and
 composition every pass) over one synthetic lattice.
 
-Workload (BASELINE.json configs[1]): 2-d square 4096x4096 SGC Ising, J = 0.1 eV,
-mu = 0, headline at T = 2633 K (T_c).  With N > 1 GPUs the temperature sweep
-of that config is sharded: rank r runs its own 4096x4096 lattice at T_sweep[r]
-with no communication (weak scaling).
+Workload (BASELINE.json configs[1]): the 2-d square 4096x4096 SGC Ising
+temperature sweep through T_c, J = 0.1 eV: the eight temperatures of the sweep
+(1800 ... 3200 K, T_c = 2633 K among them) run as eight independent lattices
+("chains") of one context on one GPU, mu = 0.  With N > 1 GPUs every rank runs
+the same eight-temperature sweep at its own exchange potential mu_r (a
+(T, mu) phase-diagram grid sharded over GPUs, no communication: weak scaling).
+The throughput of a single 4096x4096 lattice at T_c alone is reported next to
+it as `single_lattice`.
 
 `--impl reference` times the CPU restatement of the reference loop
 (oracle/oracle_bench, one independent chain per host core) on a bounded sample
@@ -31,8 +35,9 @@ N0 = N1 = 4096
 J = 0.1
 MU = 0.0
 T_HEADLINE = 2633.0
-T_SWEEP = [2633.0, 1800.0, 2200.0, 2500.0, 2600.0, 2660.0, 2800.0, 3200.0]
-PASSES_PER_STEP = 200
+T_SWEEP = [1800.0, 2200.0, 2500.0, 2600.0, 2633.0, 2660.0, 2800.0, 3200.0]
+MU_GRID = [0.0, 0.02, -0.02, 0.04, -0.04, 0.06, -0.06, 0.08]
+PASSES_PER_STEP = 500
 ALGO_BYTES_PER_ATTEMPT = 3.0  # int8, two colour planes: read own + read other + write own
 METRIC = "metropolis_flip_attempts_per_s"
 UNIT = "attempts/s"
@@ -157,14 +162,16 @@ def reference_arm(args):
 
 def workload_config(n_gpus):
     return {
-        "workload": f"2D square Ising SGC checkerboard sweeps, {N0}x{N1} supercell per GPU, J=0.1 eV, mu=0, "
-        + (f"T=2633 K (T_c)" if n_gpus == 1 else f"temperature sweep through T_c sharded over {n_gpus} GPUs (rank r at T_sweep[r]), no communication"),
+        "workload": f"2D square Ising SGC temperature sweep through T_c, {N0}x{N1} supercell, checkerboard sweeps: "
+        f"{len(T_SWEEP)} temperatures {T_SWEEP} K as {len(T_SWEEP)} concurrent lattices per GPU, J=0.1 eV, "
+        + ("mu=0" if n_gpus == 1 else f"rank r at mu_r={MU_GRID[:n_gpus]} eV ((T, mu) grid sharded over {n_gpus} GPUs, no communication)"),
         "lattice": [N0, N1],
+        "lattices_per_gpu": len(T_SWEEP),
         "passes_per_step": PASSES_PER_STEP,
         "sample_period": 1,
         "initial_state": "i.i.d. +1/-1 (Philox, seed 12345)",
         "philox_seed": "0xC0FFEE + rank",
-        "l2": "L2 flushed (256 MiB write) between timed steps; the 16 MiB int8 lattice is L2-resident within a step by design",
+        "l2": "L2 flushed (256 MiB write) between timed steps; the 8 x 16 MiB int8 planes (128 MiB) slightly exceed the 126 MB L2",
         "timing": "CUDA events on the launching stream per step, summed; max over ranks",
     }
 
@@ -187,16 +194,18 @@ def ours(args):
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    T = T_HEADLINE if world == 1 else T_SWEEP[rank % len(T_SWEEP)]
+    mu = MU if world == 1 else MU_GRID[rank % len(MU_GRID)]
+    n_lat = len(T_SWEEP)
     stream = torch.cuda.Stream()
-    lat = IsingLatticeGPU([N0, N1], device=local_rank, J=J)
+    lat = IsingLatticeGPU([N0, N1], n_chains=n_lat, device=local_rank, J=J)
     lat.set_stream(stream.cuda_stream)
-    lat.set_conditions(T, MU)
+    for ch, T in enumerate(T_SWEEP):
+        lat.set_conditions(T, mu, chain=ch)
     lat.seed_philox(0xC0FFEE + rank)
     lat.randomize(12345 + rank, 0.5)
     lat.sync()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    n_sites = N0 * N1
+    n_sites = N0 * N1 * n_lat  # sites per pass over all lattices of this GPU
 
     def barrier():
         torch.cuda.synchronize()
@@ -228,6 +237,7 @@ def ours(args):
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop()
     launches = lat.launch_count - launches0
+    launches_per_rank = launches
     ms_steps = [a.elapsed_time(b) for a, b in evs]
     total_ms = sum(ms_steps)
     if dist is not None:
@@ -240,23 +250,30 @@ def ours(args):
     attempts = float(n_sites) * PASSES_PER_STEP * args.steps * world
     value = attempts / (total_ms * 1e-3)
     # sanity: the run really sampled and moved
-    S, B = lat.samples_sb()
+    i_tc = T_SWEEP.index(T_HEADLINE)
+    S, B = lat.samples_sb(i_tc)
     assert len(S) == PASSES_PER_STEP * args.steps
-    x_mean = float((n_sites + S.astype(np.float64)).mean() / 2.0 / n_sites)
+    x_mean = float((N0 * N1 + S.astype(np.float64)).mean() / 2.0 / (N0 * N1))
+    acc_tc = lat.counters(i_tc)
 
     # ---- end to end through the C ABI with HOST buffers (H2D + D2H in the timed region)
-    host_occ = torch.empty(n_sites, dtype=torch.int32).pin_memory()
-    host_occ.numpy()[:] = lat.download()
-    host_out = torch.empty(n_sites, dtype=torch.int32).pin_memory()
-    e2e_steps = max(1, min(args.steps, 5))
+    per_lat = N0 * N1
+    host_occ = torch.empty((n_lat, per_lat), dtype=torch.int32).pin_memory()
+    for ch in range(n_lat):
+        lat.download(ch, out=host_occ.numpy()[ch])
+    host_out = torch.empty((n_lat, per_lat), dtype=torch.int32).pin_memory()
+    e2e_steps = max(1, min(args.steps, 3))
 
     def e2e_step():
-        lat.upload(host_occ.numpy())  # H2D of the int32 occupation + colour-plane split
+        for ch in range(n_lat):
+            lat.upload(host_occ.numpy()[ch], ch)  # H2D of the int32 occupation + colour-plane split
         lat.clear_samples()
         lat.run_passes(PASSES_PER_STEP, MODE_CHECKERBOARD, 1)
-        lat.download(out=host_out.numpy())  # D2H of the final occupation
-        s, b = lat.samples_sb()  # D2H of the sampled (S, B) series
-        return s, b
+        out = []
+        for ch in range(n_lat):
+            lat.download(ch, out=host_out.numpy()[ch])  # D2H of the final occupation
+            out.append(lat.samples_sb(ch))  # D2H of the sampled (S, B) series
+        return out
 
     e2e_step()
     barrier()
@@ -271,10 +288,27 @@ def ours(args):
         e2e_s = float(t.item())
     e2e_value = float(n_sites) * PASSES_PER_STEP * e2e_steps * world / e2e_s
 
+    # ---- the single 4096x4096 lattice at T_c on its own (tiled shared-memory kernel)
+    single = IsingLatticeGPU([N0, N1], device=local_rank, J=J)
+    single.set_stream(stream.cuda_stream)
+    single.set_conditions(T_HEADLINE, mu)
+    single.seed_philox(0xC0FFEE + rank)
+    single.randomize(12345 + rank, 0.5)
+    with torch.cuda.stream(stream):
+        single.run_passes(60, MODE_CHECKERBOARD, 1)
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(stream)
+        single.run_passes(PASSES_PER_STEP, MODE_CHECKERBOARD, 1)
+        s1.record(stream)
+    torch.cuda.synchronize()
+    single_value = float(per_lat) * PASSES_PER_STEP / (s0.elapsed_time(s1) * 1e-3)
+    single_variant = single.kernel_variant
+    single.close()
+
     peak, peak_src = measured_peak()
-    n_half_sweeps = 2 * PASSES_PER_STEP * args.steps
-    avg_launch_s = (sum(ms_steps) * 1e-3) / n_half_sweeps
-    bytes_per_launch = ALGO_BYTES_PER_ATTEMPT * n_sites / 2
+    n_launches_step = launches_per_rank / max(1, args.steps)
+    avg_launch_s = (sum(ms_steps) * 1e-3) / max(1, launches_per_rank)
+    bytes_per_launch = ALGO_BYTES_PER_ATTEMPT * float(n_sites) * PASSES_PER_STEP * args.steps / max(1, launches_per_rank)
     achieved = bytes_per_launch / avg_launch_s / 1e9
 
     line = {
@@ -296,7 +330,7 @@ def ours(args):
             "value": e2e_value,
             "unit": UNIT,
             "h2d_bytes_per_step": 4 * n_sites,
-            "d2h_bytes_per_step": 4 * n_sites + 16 * PASSES_PER_STEP,
+            "d2h_bytes_per_step": 4 * n_sites + 16 * PASSES_PER_STEP * n_lat,
             "steps": e2e_steps,
         },
         "gpu_launches": launches,
@@ -308,13 +342,15 @@ def ours(args):
             "unit": "GB/s",
             "frac": achieved / peak,
             "traffic": None,
-            "kernel": "k_halfsweep_" + lat.kernel_variant,
+            "kernel": ("k_halfsweep_" if lat.kernel_variant.startswith("bulk") else "k_") + lat.kernel_variant,
             "algorithmic_bytes_per_launch": bytes_per_launch,
             "avg_launch_us": avg_launch_s * 1e6,
-            "note": "3 B per attempted flip (int8, two colour planes); lattice is L2-resident so DRAM traffic << algorithmic bytes; kernel is issue-bound (Philox)",
+            "launches_per_step": n_launches_step,
+            "note": "3 B per attempted flip (int8, two colour planes); kernel is ALU-issue-bound (Philox4x32-10 + table compare), not HBM-bound: see DESIGN.md / profiles/",
         },
+        "single_lattice": {"value": single_value, "unit": UNIT, "kernel": "k_" + single_variant, "workload": f"one {N0}x{N1} lattice at T=2633 K, sampling every pass", "frac_of_roofline": single_value * ALGO_BYTES_PER_ATTEMPT / 1e9 / peak},
         "wall_s_timed_region": t_wall,
-        "check": {"mean_param_composition": x_mean, "acceptance_rate": lat.counters()[1] / max(1, lat.counters()[1] + lat.counters()[2])},
+        "check": {"T": T_HEADLINE, "mean_param_composition": x_mean, "acceptance_rate": acc_tc[1] / max(1, acc_tc[1] + acc_tc[2])},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = host_cores()

@@ -85,7 +85,7 @@ struct cmg_context {
 
   int forced_variant = V_AUTO;
   int js = 0;  // 0 = auto
-  int tile_passes = 2;   // passes per launch of the tiled kernel (halo = 2*P columns)
+  int tile_passes = 3;   // passes per launch of the tiled kernel (halo = 2*P columns)
   int tile_threads = 512;
   int sm_count = 148;
   size_t smem_optin = 0;
@@ -789,7 +789,10 @@ static TilePlan plan_tiles(const cmg_context *c, long long passes_wanted) {
 
 static int pick_variant(cmg_context *c) {
   if (c->forced_variant != V_AUTO) return c->forced_variant;
-  if (plan_tiles(c, c->tile_passes).ok) return V_TILE2D;
+  // the tiled kernel wins while a half-sweep is short enough for launch ramp
+  // and L2 latency to matter; very large batches stream better through bulk2d
+  if (plan_tiles(c, c->tile_passes).ok && c->n_sites * c->n_chains <= (1ll << 25))
+    return V_TILE2D;
   if (c->dim == 2 && c->shape[0] % 32 == 0) return V_BULK2D;
   if (c->dim == 3 && c->shape[0] % 32 == 0) return V_BULK3D;
   return V_GENERIC;
@@ -802,7 +805,7 @@ static int pick_js(const cmg_context *c, int variant) {
   const long long V = c->shape[0] / 32;
   const long long layers = variant == V_BULK3D ? c->shape[2] : 1;
   const long long target_threads = 148LL * 512;
-  int js = 32;
+  int js = 16;
   while (js > 2 && V * ((c->shape[1] + js - 1) / js) * layers * c->n_chains < target_threads) js >>= 1;
   return js;
 }

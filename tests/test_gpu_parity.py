@@ -293,11 +293,13 @@ def test_device_rng_matches_libstdcxx(cm, oracle):
     e.seed(5489)
     reqs = []
     rng = np.random.default_rng(0)
+    int_choices = [9, 624, 9999, 2**31, 2**64 - 1, 16777215]
+    real_choices = [1.0, 9.0, 0.1]
     for i in range(700):  # crosses two state regenerations
         if i % 3 == 2:
-            reqs.append(("real", float(rng.choice([1.0, 9.0, 0.1]))))
+            reqs.append(("real", real_choices[int(rng.integers(len(real_choices)))]))
         else:
-            reqs.append(("int", int(rng.choice([9, 624, 9999, 2**31, 2**64 - 1, 16777215]))))
+            reqs.append(("int", int_choices[int(rng.integers(len(int_choices)))]))
     got = lat.rng_draw(reqs)
     for (kind, mx), g in zip(reqs, got):
         want = oracle.random_real(e, mx) if kind == "real" else oracle.random_int(e, mx)
