@@ -52,6 +52,9 @@ SIGNATURES = {
     "cmg_upload_occupation_i32_dev": (C.c_int, [_ctx, C.c_int, C.c_void_p, C.c_int64]),
     "cmg_download_occupation_i32_dev": (C.c_int, [_ctx, C.c_int, C.c_void_p, C.c_int64]),
     "cmg_fill_occupation": (C.c_int, [_ctx, C.c_int, C.c_int]),
+    "cmg_get_occ": (C.c_int, [_ctx, C.c_int, C.c_int64, _i32p]),
+    "cmg_set_occ": (C.c_int, [_ctx, C.c_int, C.c_int64, C.c_int32]),
+    "cmg_event_delta": (C.c_int, [_ctx, C.c_int, C.c_int, _i64p, _i32p, _f64p, _f64p]),
     "cmg_randomize_occupation": (C.c_int, [_ctx, C.c_int, C.c_uint64, C.c_double]),
     "cmg_seed_philox": (C.c_int, [_ctx, C.c_uint64]),
     "cmg_set_pass_counter": (C.c_int, [_ctx, C.c_uint64]),

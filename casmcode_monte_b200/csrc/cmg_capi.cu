@@ -57,6 +57,7 @@ struct cmg_context {
   bool nat_is_current = false;     // natural copy mirrors the planes
   int32_t *d_stage = nullptr;      // [n_sites] int32 staging
   int *d_flag = nullptr;
+  unsigned char *d_event = nullptr;  // event staging for cmg_event_delta
 
   ChainTables *d_tabs = nullptr;
   std::vector<ChainTables> h_tabs;
@@ -362,6 +363,7 @@ int cmg_destroy(cmg_context *c) {
   cudaFree(c->d_nat);
   cudaFree(c->d_stage);
   cudaFree(c->d_flag);
+  cudaFree(c->d_event);
   cudaFree(c->d_tabs);
   cudaFree(c->d_run);
   cudaFree(c->d_n_accept);
@@ -572,6 +574,79 @@ int cmg_fill_occupation(cmg_context *c, int chain, int value) {
     CU(c, cudaMemsetAsync(c->d_nat + lo * c->n_sites, b, (size_t)c->n_sites * (hi - lo),
                           c->stream));
   }
+  return CMG_OK;
+}
+
+// base pointer of a chain for single-site kernels: planes when two-coloured
+static uint8_t *chain_base(cmg_context *c, int chain) {
+  return c->planar ? c->d_planes + chain * c->chain_stride : c->d_nat + chain * c->n_sites;
+}
+
+int cmg_get_occ(cmg_context *c, int chain, int64_t l, int32_t *value) {
+  NEED(c);
+  if (chain < 0 || chain >= c->n_chains) return fail(c, CMG_EINVAL, "bad chain index");
+  if (l < 0 || l >= c->n_sites || !value) return fail(c, CMG_EINVAL, "site index out of range");
+  k_get_occ<<<1, 1, 0, c->stream>>>(chain_base(c, chain), nat_shape(c), c->planar ? 1 : 0,
+                                    c->plane_stride, l, c->d_flag);
+  ++c->launches;
+  CU(c, cudaGetLastError());
+  int v = 0;
+  CU(c, cudaMemcpyAsync(&v, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  *value = v;
+  return CMG_OK;
+}
+
+int cmg_set_occ(cmg_context *c, int chain, int64_t l, int32_t value) {
+  NEED(c);
+  if (chain < 0 || chain >= c->n_chains) return fail(c, CMG_EINVAL, "bad chain index");
+  if (l < 0 || l >= c->n_sites) return fail(c, CMG_EINVAL, "site index out of range");
+  if (value != 1 && value != -1) return fail(c, CMG_EINVAL, "occupation values must be +1 or -1");
+  k_set_occ<<<1, 1, 0, c->stream>>>(chain_base(c, chain), nat_shape(c), c->planar ? 1 : 0,
+                                    c->plane_stride, l, value);
+  ++c->launches;
+  if (c->planar) c->nat_is_current = false;
+  CU(c, cudaGetLastError());
+  return CMG_OK;
+}
+
+int cmg_event_delta(cmg_context *c, int chain, int n_event, const int64_t *ls,
+                    const int32_t *new_occ, double *dE_formation, double *dNx) {
+  NEED(c);
+  if (chain < 0 || chain >= c->n_chains) return fail(c, CMG_EINVAL, "bad chain index");
+  if (n_event < 0 || n_event > kMaxEventSites || (n_event > 0 && (!ls || !new_occ)))
+    return fail(c, CMG_EINVAL, "event size must be in [0, 64]");
+  if (!c->model_set) return fail(c, CMG_ESTATE, "model not set");
+  for (int e = 0; e < n_event; ++e)
+    if (ls[e] < 0 || ls[e] >= c->n_sites) return fail(c, CMG_EINVAL, "site index out of range");
+  if (n_event == 0) {
+    if (dE_formation) *dE_formation = 0.0;
+    if (dNx) *dNx = 0.0;
+    return CMG_OK;
+  }
+  struct {
+    long long l[kMaxEventSites];
+    int v[kMaxEventSites];
+  } h;
+  for (int e = 0; e < n_event; ++e) {
+    h.l[e] = ls[e];
+    h.v[e] = new_occ[e];
+  }
+  if (!c->d_event) CU(c, cudaMalloc(&c->d_event, sizeof h + 2 * sizeof(double)));
+  CU(c, cudaMemcpyAsync(c->d_event, &h, sizeof h, cudaMemcpyHostToDevice, c->stream));
+  double *d_out = reinterpret_cast<double *>(c->d_event + sizeof h);
+  k_event_delta<<<1, 1, 0, c->stream>>>(chain_base(c, chain), nat_shape(c), c->planar ? 1 : 0,
+                                        c->plane_stride, c->J, n_event,
+                                        reinterpret_cast<const long long *>(c->d_event),
+                                        reinterpret_cast<const int *>(c->d_event + sizeof h.l),
+                                        d_out);
+  ++c->launches;
+  CU(c, cudaGetLastError());
+  double out[2];
+  CU(c, cudaMemcpyAsync(out, d_out, sizeof out, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  if (dE_formation) *dE_formation = out[0];
+  if (dNx) *dNx = out[1];
   return CMG_OK;
 }
 

@@ -993,6 +993,65 @@ __global__ void k_accept_probe(const uint8_t *__restrict__ nat, NaturalShape s,
 }
 
 // ---------------------------------------------------------------------------
+// Single-site access and event deltas (the calculator interface used one event
+// at a time, e.g. by a host-driven loop).  `base` is either the natural array
+// or the planes of the chain; planar != 0 selects plane addressing.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ long long site_addr(const NaturalShape &s, long long l, int planar,
+                                               long long plane_stride) {
+  return planar ? plane_addr(s, l, plane_stride) : l;
+}
+__device__ __forceinline__ long long wrap_site(const NaturalShape &s, int i, int j, int k) {
+  return i + (long long)s.n0 * (j + (long long)s.n1 * k);
+}
+__global__ void k_get_occ(const uint8_t *base, NaturalShape s, int planar, long long plane_stride,
+                          long long l, int *out) {
+  *out = base[site_addr(s, l, planar, plane_stride)] ? 1 : -1;
+}
+__global__ void k_set_occ(uint8_t *base, NaturalShape s, int planar, long long plane_stride,
+                          long long l, int value) {
+  base[site_addr(s, l, planar, plane_stride)] = (uint8_t)(value > 0);
+}
+// model.hh:354-379 and :425-435, one thread.  n_event <= kMaxEventSites.
+constexpr int kMaxEventSites = 64;
+__global__ void k_event_delta(uint8_t *base, NaturalShape s, int planar, long long plane_stride,
+                              double J, int n_event, const long long *ls, const int *new_occ,
+                              double *out /* {dE_f, dNx} */) {
+  double dE = 0.0, dNx = 0.0;
+  uint8_t orig[kMaxEventSites];
+  for (int e = 0; e < n_event; ++e) {
+    const long long l = ls[e];
+    const int i = (int)(l % s.n0);
+    const long long r = l / s.n0;
+    const int j = (int)(r % s.n1);
+    const int k = (int)(r / s.n1);
+    const int ip = (i + 1 == s.n0) ? 0 : i + 1, im = (i == 0) ? s.n0 - 1 : i - 1;
+    const int jp = (j + 1 == s.n1) ? 0 : j + 1, jm = (j == 0) ? s.n1 - 1 : j - 1;
+    int nb = 0;
+    nb += base[site_addr(s, wrap_site(s, ip, j, k), planar, plane_stride)] ? 1 : -1;
+    nb += base[site_addr(s, wrap_site(s, im, j, k), planar, plane_stride)] ? 1 : -1;
+    nb += base[site_addr(s, wrap_site(s, i, jp, k), planar, plane_stride)] ? 1 : -1;
+    nb += base[site_addr(s, wrap_site(s, i, jm, k), planar, plane_stride)] ? 1 : -1;
+    if (s.dim == 3) {
+      const int kp = (k + 1 == s.n2) ? 0 : k + 1, km = (k == 0) ? s.n2 - 1 : k - 1;
+      nb += base[site_addr(s, wrap_site(s, i, j, kp), planar, plane_stride)] ? 1 : -1;
+      nb += base[site_addr(s, wrap_site(s, i, j, km), planar, plane_stride)] ? 1 : -1;
+    }
+    const long long a = site_addr(s, l, planar, plane_stride);
+    orig[e] = base[a];
+    const int ds = new_occ[e] - (orig[e] ? 1 : -1);
+    dE = __dadd_rn(dE, __dmul_rn(__dmul_rn(-J, (double)ds), (double)nb));
+    dNx = __dadd_rn(dNx, __ddiv_rn((double)ds, 2.0));
+    if (n_event > 1) base[a] = (uint8_t)(new_occ[e] > 0);  // applied while summing (:361-371)
+  }
+  if (n_event > 1)  // un-applied in forward order, as the reference does (:374-376)
+    for (int e = 0; e < n_event; ++e)
+      base[site_addr(s, ls[e], planar, plane_stride)] = orig[e];
+  out[0] = dE;
+  out[1] = dNx;
+}
+
+// ---------------------------------------------------------------------------
 // Serial reference mode.  One thread per chain walks the reference's loop
 // (methods/basic_occupation_metropolis.hh:381-404) on the reference's random
 // stream: std::mt19937_64, libstdc++-13 uniform_int_distribution<long>(0,N-1)

@@ -102,6 +102,22 @@ class IsingLatticeGPU:
     def download_dev(self, dev_ptr, n, chain=0):
         self._ck(self._lib.cmg_download_occupation_i32_dev(self._ctx, chain, C.c_void_p(int(dev_ptr)), int(n)))
 
+    def get_occ(self, l, chain=0):
+        v = C.c_int32()
+        self._ck(self._lib.cmg_get_occ(self._ctx, chain, int(l), C.byref(v)))
+        return v.value
+
+    def set_occ(self, l, value, chain=0):
+        self._ck(self._lib.cmg_set_occ(self._ctx, chain, int(l), int(value)))
+
+    def event_delta(self, linear_site_index, new_occ, chain=0):
+        """(dE_formation, dNx) of an event, model.hh:354-379 / :425-435."""
+        ls = np.ascontiguousarray(linear_site_index, dtype=np.int64)
+        no = np.ascontiguousarray(new_occ, dtype=np.int32)
+        dE, dN = C.c_double(), C.c_double()
+        self._ck(self._lib.cmg_event_delta(self._ctx, chain, ls.size, _p(ls, C.c_int64), _p(no, C.c_int32), C.byref(dE), C.byref(dN)))
+        return dE.value, dN.value
+
     def fill(self, value, chain=-1):
         self._ck(self._lib.cmg_fill_occupation(self._ctx, chain, int(value)))
 

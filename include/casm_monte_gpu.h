@@ -137,6 +137,18 @@ int cmg_upload_occupation_i32_dev(cmg_context *ctx, int chain,
 int cmg_download_occupation_i32_dev(cmg_context *ctx, int chain, int32_t *occ_dev,
                                     int64_t n);
 int cmg_fill_occupation(cmg_context *ctx, int chain, int value);
+/* single-site access: IsingConfiguration::occ / set_occ (model.hh:62-70) */
+int cmg_get_occ(cmg_context *ctx, int chain, int64_t linear_site_index, int32_t *value);
+int cmg_set_occ(cmg_context *ctx, int chain, int64_t linear_site_index, int32_t value);
+/* Change of formation energy and of N*x for an event on n_event sites, with the
+ * reference's semantics for multi-site events (each flip evaluated after the
+ * previous ones are applied, then all un-applied; model.hh:354-379, :425-435):
+ *   dE_f = sum_i ((-J) * (new_i - old_i)) * (sum of the 2*dim neighbours)
+ *   dNx  = sum_i (new_i - old_i) / 2.0
+ * Evaluated on the device; the lattice is left unchanged. */
+int cmg_event_delta(cmg_context *ctx, int chain, int n_event,
+                    const int64_t *linear_site_index, const int32_t *new_occ,
+                    double *dE_formation, double *dNx);
 /* i.i.d. +1/-1 from Philox (synthetic benchmark input), probability of +1 = p_up */
 int cmg_randomize_occupation(cmg_context *ctx, int chain, uint64_t seed, double p_up);
 
