@@ -616,7 +616,6 @@ int cmg_event_delta(cmg_context *c, int chain, int n_event, const int64_t *ls,
   if (chain < 0 || chain >= c->n_chains) return fail(c, CMG_EINVAL, "bad chain index");
   if (n_event < 0 || n_event > kMaxEventSites || (n_event > 0 && (!ls || !new_occ)))
     return fail(c, CMG_EINVAL, "event size must be in [0, 64]");
-  if (!c->model_set) return fail(c, CMG_ESTATE, "model not set");
   for (int e = 0; e < n_event; ++e)
     if (ls[e] < 0 || ls[e] >= c->n_sites) return fail(c, CMG_EINVAL, "site index out of range");
   if (n_event == 0) {

@@ -1,0 +1,918 @@
+// monte_module.cpp -- pybind11 face of include/casm_monte_b200/monte.hh.
+//
+// Mirrors the part of the libcasm.monte Python API that the Ising SGC path
+// uses: same class names, constructor arguments, attribute
+// and method names as python/src/monte*.cpp of the reference, so the
+// reference's own Python tests for this path run with only the import root
+// changed.  One extension module; casmcode_monte_b200/monte/** re-exports it in
+// the reference's package layout.  numpy arrays are used where the reference
+// uses Eigen (pybind11/eigen.h needs Eigen, which is not required here).
+#include <pybind11/functional.h>
+#include <pybind11/numpy.h>
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+#include <pybind11/stl_bind.h>
+
+#include "casm_monte_b200/monte.hh"
+
+namespace py = pybind11;
+using namespace casm_monte_b200;
+
+typedef SemiGrandCanonicalCalculator calculator_type;
+typedef SemiGrandCanonicalEventGenerator<default_engine_type> event_generator_type;
+typedef std::map<std::string, std::vector<double>> VectorValueMap;
+typedef std::map<std::string, double> ScalarValueMap;
+typedef std::map<std::string, bool> BooleanValueMap;
+
+// JSON-valued sampling (include/casm/monte/sampling/StateSamplingFunction.hh:79-95,
+// Sampler.hh:114-117): JSON values are Python objects here.
+struct jsonStateSamplingFunction {
+  std::string name, description;
+  py::object function;
+};
+struct jsonSampler {
+  py::list values;
+};
+typedef std::map<std::string, jsonStateSamplingFunction> jsonStateSamplingFunctionMap;
+typedef std::map<std::string, jsonSampler> jsonSamplerMap;
+
+// per-run extras that live next to SemiGrandCanonicalData in the binding
+struct RunExtras {
+  jsonStateSamplingFunctionMap json_sampling_functions;
+  jsonSamplerMap json_samplers;
+};
+static std::map<SemiGrandCanonicalData const *, std::shared_ptr<RunExtras>> &extras_registry() {
+  static std::map<SemiGrandCanonicalData const *, std::shared_ptr<RunExtras>> r;
+  return r;
+}
+
+PYBIND11_MAKE_OPAQUE(SamplerMap);
+PYBIND11_MAKE_OPAQUE(StateSamplingFunctionMap);
+PYBIND11_MAKE_OPAQUE(jsonStateSamplingFunctionMap);
+PYBIND11_MAKE_OPAQUE(jsonSamplerMap);
+PYBIND11_MAKE_OPAQUE(RequestedPrecisionMap);
+PYBIND11_MAKE_OPAQUE(ScalarValueMap);
+PYBIND11_MAKE_OPAQUE(VectorValueMap);
+PYBIND11_MAKE_OPAQUE(BooleanValueMap);
+PYBIND11_MAKE_OPAQUE(std::vector<long>);
+PYBIND11_MAKE_OPAQUE(std::vector<int>);
+
+namespace {
+
+py::array_t<double> as_array(std::vector<double> const &v) {
+  py::array_t<double> a(v.size());
+  std::copy(v.begin(), v.end(), a.mutable_data());
+  return a;
+}
+std::vector<double> to_dvec(py::handle h) {
+  py::array_t<double, py::array::c_style | py::array::forcecast> a =
+      py::array_t<double, py::array::c_style | py::array::forcecast>::ensure(h);
+  if (!a) throw std::runtime_error("expected a float array");
+  std::vector<double> v(a.size());
+  std::copy(a.data(), a.data() + a.size(), v.begin());
+  return v;
+}
+std::vector<int> to_ivec(py::handle h) {
+  py::array_t<long, py::array::c_style | py::array::forcecast> a =
+      py::array_t<long, py::array::c_style | py::array::forcecast>::ensure(h);
+  if (!a) throw std::runtime_error("expected an integer array");
+  std::vector<int> v(a.size());
+  for (py::ssize_t i = 0; i < a.size(); ++i) v[i] = static_cast<int>(a.data()[i]);
+  return v;
+}
+
+// ---- ValueMap <-> dict (src/casm/monte/io/json/ValueMap_json_io.cc:9-55) ----
+ValueMap valuemap_from_dict(py::dict d) {
+  ValueMap v;
+  for (auto item : d) {
+    std::string key = py::str(item.first);
+    py::handle val = item.second;
+    if (py::isinstance<py::bool_>(val)) {
+      v.boolean_values[key] = val.cast<bool>();
+    } else if (py::isinstance<py::int_>(val) || py::isinstance<py::float_>(val)) {
+      v.scalar_values[key] = val.cast<double>();
+    } else {
+      py::array_t<double, py::array::c_style | py::array::forcecast> a =
+          py::array_t<double, py::array::c_style | py::array::forcecast>::ensure(val);
+      if (!a) throw std::runtime_error("Error in ValueMap.from_dict: unsupported value for '" + key + "'");
+      if (a.ndim() == 1) {
+        v.vector_values[key] = std::vector<double>(a.data(), a.data() + a.size());
+      } else if (a.ndim() == 2) {
+        MatrixValue m;
+        m.rows = a.shape(0);
+        m.cols = a.shape(1);
+        m.data.resize(a.size());
+        for (Index c = 0; c < m.cols; ++c)
+          for (Index r = 0; r < m.rows; ++r) m.data[r + m.rows * c] = a.at(r, c);
+        v.matrix_values[key] = m;
+      } else {
+        throw std::runtime_error("Error in ValueMap.from_dict: unsupported array rank");
+      }
+    }
+  }
+  return v;
+}
+py::dict valuemap_to_dict(ValueMap const &v) {
+  py::dict d;
+  for (auto const &p : v.boolean_values) d[py::str(p.first)] = p.second;
+  for (auto const &p : v.scalar_values) d[py::str(p.first)] = p.second;
+  for (auto const &p : v.vector_values) d[py::str(p.first)] = py::cast(p.second);
+  for (auto const &p : v.matrix_values) {
+    py::list rows;
+    for (Index r = 0; r < p.second.rows; ++r) {
+      py::list row;
+      for (Index c = 0; c < p.second.cols; ++c) row.append(p.second.data[r + p.second.rows * c]);
+      rows.append(row);
+    }
+    d[py::str(p.first)] = rows;
+  }
+  return d;
+}
+
+py::dict req_prec_to_dict(RequestedPrecision const &r) {
+  py::dict d;
+  if (r.abs_convergence_is_required) d["abs_precision"] = r.abs_precision;
+  if (r.rel_convergence_is_required) d["rel_precision"] = r.rel_precision;
+  return d;
+}
+py::dict stats_to_dict(BasicStatistics const &s) {
+  py::dict d;
+  d["mean"] = s.mean;
+  d["calculated_precision"] = s.calculated_precision;
+  return d;
+}
+py::dict eq_results_to_dict(EquilibrationCheckResults const &v) {
+  py::dict d;
+  d["all_equilibrated"] = v.all_equilibrated;
+  if (v.all_equilibrated)
+    d["N_samples_for_all_to_equilibrate"] = v.N_samples_for_all_to_equilibrate;
+  else
+    d["N_samples_for_equilibration"] = "did_not_equilibrate";
+  py::list l;
+  for (auto const &p : v.individual_results) {
+    py::dict t;
+    t["is_equilibrated"] = p.second.is_equilibrated;
+    if (p.second.is_equilibrated)
+      t["N_samples_for_equilibration"] = p.second.N_samples_for_equilibration;
+    else
+      t["N_samples_for_equilibration"] = "did_not_equilibrate";
+    t["sampler_name"] = p.first.sampler_name;
+    t["component_name"] = p.first.component_name;
+    t["component_index"] = p.first.component_index;
+    l.append(t);
+  }
+  d["individual_results"] = l;
+  return d;
+}
+py::dict conv_results_to_dict(ConvergenceCheckResults const &v) {
+  py::dict d;
+  d["all_converged"] = v.all_converged;
+  d["N_samples_for_statistics"] = v.N_samples_for_statistics;
+  py::list l;
+  for (auto const &p : v.individual_results) {
+    py::dict t;
+    t["is_converged"] = p.second.is_converged;
+    t["requested_precision"] = req_prec_to_dict(p.second.requested_precision);
+    t["stats"] = stats_to_dict(p.second.stats);
+    t["sampler_name"] = p.first.sampler_name;
+    t["component_name"] = p.first.component_name;
+    t["component_index"] = p.first.component_index;
+    l.append(t);
+  }
+  d["individual_results"] = l;
+  return d;
+}
+// include/casm/monte/checks/io/json/CompletionCheck_json_io.hh:421-438
+py::dict cc_results_to_dict(CompletionCheckResults const &v) {
+  py::dict d;
+  d["has_all_minimums_met"] = v.has_all_minimums_met;
+  d["has_any_maximum_met"] = v.has_any_maximum_met;
+  d["count"] = v.count.has_value() ? py::cast(*v.count) : py::none();
+  d["time"] = v.time.has_value() ? py::cast(*v.time) : py::none();
+  d["clocktime"] = v.clocktime;
+  d["n_samples"] = v.n_samples;
+  d["is_complete"] = v.is_complete;
+  if (v.n_samples_at_convergence_check.has_value()) {
+    d["n_samples_at_convergence_check"] = *v.n_samples_at_convergence_check;
+    d["equilibration_check_results"] = eq_results_to_dict(v.equilibration_check_results);
+    d["convergence_check_results"] = conv_results_to_dict(v.convergence_check_results);
+  }
+  return d;
+}
+
+template <typename T>
+py::list to_pylist(std::vector<T> const &v) {
+  py::list l;
+  for (auto const &x : v) l.append(x);
+  return l;
+}
+template <typename T>
+py::array_t<long> to_long_array(std::vector<T> const &v) {
+  py::array_t<long> a(v.size());
+  for (size_t i = 0; i < v.size(); ++i) a.mutable_data()[i] = static_cast<long>(v[i]);
+  return a;
+}
+py::dict config_to_dict(IsingConfiguration const &c) {
+  py::dict d;
+  d["shape"] = to_pylist(c.shape);
+  d["occupation"] = to_pylist(c.occupation());
+  return d;
+}
+IsingConfiguration config_from_dict(py::dict d) {
+  if (!d.contains("shape"))
+    throw std::runtime_error("Error reading IsingConfiguration from JSON: no 'shape'");
+  if (!d.contains("occupation"))
+    throw std::runtime_error("Error reading IsingConfiguration from JSON: no 'occupation'");
+  IsingConfiguration c(to_ivec(d["shape"]));
+  c.set_occupation(to_ivec(d["occupation"]));
+  return c;
+}
+
+struct PyEngine {
+  std::shared_ptr<default_engine_type> e;
+};
+
+}  // namespace
+
+PYBIND11_MODULE(_monte_b200, m) {
+  m.doc() = "B200-native Ising SGC Metropolis path behind the libcasm.monte API subset";
+  m.attr("KB") = KB;
+
+  // ------------------------------------------------------------------ monte
+  py::bind_map<ScalarValueMap>(m, "ScalarValueMap");
+  py::bind_map<BooleanValueMap>(m, "BooleanValueMap");
+  // vector values: numpy views so that values.vector_values["x"][0] = 2.0 sticks
+  py::class_<VectorValueMap>(m, "VectorValueMap")
+      .def(py::init<>())
+      .def("__len__", [](VectorValueMap const &v) { return v.size(); })
+      .def("__contains__", [](VectorValueMap const &v, std::string const &k) { return v.count(k) > 0; })
+      .def("__iter__", [](VectorValueMap const &v) { return py::make_key_iterator(v.begin(), v.end()); },
+           py::keep_alive<0, 1>())
+      .def("keys", [](VectorValueMap const &v) {
+        py::list l;
+        for (auto const &p : v) l.append(p.first);
+        return l;
+      })
+      .def("items", [](py::object self) {
+        auto &v = self.cast<VectorValueMap &>();
+        py::list l;
+        for (auto &p : v)
+          l.append(py::make_tuple(p.first, py::array_t<double>({p.second.size()}, {sizeof(double)},
+                                                               p.second.data(), self)));
+        return l;
+      })
+      .def("__getitem__", [](py::object self, std::string const &k) {
+        auto &v = self.cast<VectorValueMap &>();
+        auto it = v.find(k);
+        if (it == v.end()) throw py::key_error(k);
+        return py::array_t<double>({it->second.size()}, {sizeof(double)}, it->second.data(), self);
+      })
+      .def("__setitem__", [](VectorValueMap &v, std::string const &k, py::object val) { v[k] = to_dvec(val); })
+      .def("__delitem__", [](VectorValueMap &v, std::string const &k) {
+        if (!v.erase(k)) throw py::key_error(k);
+      });
+
+  py::class_<ValueMap>(m, "ValueMap")
+      .def(py::init([](std::optional<py::dict> data) {
+             return data.has_value() ? valuemap_from_dict(*data) : ValueMap();
+           }),
+           py::arg("data") = py::none())
+      .def_readwrite("boolean_values", &ValueMap::boolean_values)
+      .def_readwrite("scalar_values", &ValueMap::scalar_values)
+      .def_readwrite("vector_values", &ValueMap::vector_values)
+      .def("is_mismatched", [](ValueMap const &a, ValueMap const &b) { return is_mismatched(a, b); })
+      .def("make_incremented_values",
+           [](ValueMap const &a, ValueMap const &inc, double n) { return make_incremented_values(a, inc, n); },
+           py::arg("increment"), py::arg("n_increment"))
+      .def_static("from_dict", &valuemap_from_dict, py::arg("data"))
+      .def("to_dict", &valuemap_to_dict)
+      .def("__copy__", [](ValueMap const &v) { return ValueMap(v); })
+      .def("__deepcopy__", [](ValueMap const &v, py::dict) { return ValueMap(v); });
+
+  py::class_<MethodLog>(m, "MethodLog")
+      .def(py::init([](std::optional<std::string> logfile_path, std::optional<double> log_frequency) {
+             MethodLog l;
+             if (logfile_path.has_value()) {
+               l.logfile_path = *logfile_path;
+               l.reset();
+             }
+             l.log_frequency = log_frequency;
+             return l;
+           }),
+           py::arg("logfile_path") = py::none(), py::arg("log_frequency") = py::none())
+      .def("logfile_path", [](MethodLog const &l) { return l.logfile_path; })
+      .def("log_frequency", [](MethodLog const &l) { return l.log_frequency; })
+      .def("reset", &MethodLog::reset)
+      .def("reset_to_stdout", &MethodLog::reset_to_stdout)
+      .def("restart_clock", [](MethodLog &l) { l.log.restart_clock(); })
+      .def("time_s", [](MethodLog const &l) { return l.log.time_s(); })
+      .def("begin_lap", [](MethodLog &l) { l.log.begin_lap(); })
+      .def("lap_time", [](MethodLog const &l) { return l.log.lap_time(); })
+      .def("print", [](MethodLog &l, std::string const &what) { (*l.log.out) << what; l.log.out->flush(); })
+      .def("section", [](MethodLog &l, std::string const &what, bool show_clock) {
+        (*l.log.out) << "-- " << what << " -- ";
+        if (show_clock) (*l.log.out) << "Time: " << l.log.time_s() << " (s)";
+        (*l.log.out) << std::endl;
+      }, py::arg("what"), py::arg("show_clock") = false);
+
+  // python/src/monte.cpp:469-550
+  py::class_<PyEngine>(m, "RandomNumberEngine")
+      .def(py::init([]() {
+        PyEngine e;
+        e.e = std::make_shared<default_engine_type>();
+        std::random_device device;
+        e.e->seed(device());
+        return e;
+      }))
+      .def("seed", [](PyEngine &e, uint64_t value) { e.e->seed(value); }, py::arg("value"))
+      .def("seed_seq", [](PyEngine &e, std::vector<uint32_t> values) {
+        std::seed_seq ss(values.begin(), values.end());
+        e.e->seed(ss);
+      }, py::arg("values"))
+      .def("dump", [](PyEngine const &e) {
+        std::stringstream ss;
+        ss << *e.e;
+        return ss.str();
+      })
+      .def("load", [](PyEngine &e, std::string state) {
+        std::stringstream ss(state);
+        ss >> *e.e;
+      }, py::arg("state"));
+
+  py::class_<RandomNumberGenerator<>>(m, "RandomNumberGenerator")
+      .def(py::init([](std::optional<PyEngine> engine) {
+             return RandomNumberGenerator<>(engine.has_value() ? engine->e : nullptr);
+           }),
+           py::arg("engine") = py::none())
+      .def("random_int", [](RandomNumberGenerator<> &g, uint64_t maximum_value) {
+        return g.random_int<uint64_t>(maximum_value);
+      }, py::arg("maximum_value"))
+      .def("random_real", [](RandomNumberGenerator<> &g, double maximum_value) {
+        return g.random_real<double>(maximum_value);
+      }, py::arg("maximum_value"))
+      .def("engine", [](RandomNumberGenerator<> &g) {
+        PyEngine e;
+        e.e = g.engine;
+        return e;
+      });
+
+  // ----------------------------------------------------------------- events
+  py::bind_vector<std::vector<long>>(m, "LongVector");
+  py::bind_vector<std::vector<int>>(m, "IntVector");
+  // python lists / tuples / arrays are accepted wherever these vectors are expected
+  py::implicitly_convertible<py::list, std::vector<long>>();
+  py::implicitly_convertible<py::tuple, std::vector<long>>();
+  py::implicitly_convertible<py::array, std::vector<long>>();
+  py::implicitly_convertible<py::list, std::vector<int>>();
+  py::implicitly_convertible<py::tuple, std::vector<int>>();
+  py::implicitly_convertible<py::array, std::vector<int>>();
+  py::class_<OccEvent>(m, "OccEvent")
+      .def(py::init<>())
+      .def_readwrite("linear_site_index", &OccEvent::linear_site_index)
+      .def_readwrite("new_occ", &OccEvent::new_occ);
+
+  py::class_<Conversions>(m, "Conversions")
+      .def(py::init<std::vector<long>, long, int>(), py::arg("supercell_extents"),
+           py::arg("n_basis") = 1, py::arg("device") = 0)
+      .def("l_size", &Conversions::l_size)
+      .def("l_to_b", &Conversions::l_to_b)
+      .def("l_to_ijk", &Conversions::l_to_ijk)
+      .def("l_to_bijk", [](Conversions const &c, long l) { return c.l_to_bijk(l); })
+      .def("bijk_to_l", [](Conversions const &c, std::vector<long> bijk) {
+        if (bijk.size() != 4) throw std::runtime_error("bijk must have 4 entries");
+        return c.bijk_to_l(bijk[0], bijk[1], bijk[2], bijk[3]);
+      })
+      .def("l_to_bijk_batch", [](Conversions const &c, std::vector<int64_t> l) {
+        auto out = c.l_to_bijk(l);
+        py::array_t<int64_t> a({static_cast<py::ssize_t>(l.size()), static_cast<py::ssize_t>(4)});
+        std::copy(out.begin(), out.end(), a.mutable_data());
+        return a;
+      })
+      .def("bijk_to_l_batch", [](Conversions const &c,
+                                 py::array_t<int64_t, py::array::c_style | py::array::forcecast> bijk) {
+        std::vector<int64_t> in(bijk.data(), bijk.data() + bijk.size());
+        return c.bijk_to_l(in);
+      });
+
+  // --------------------------------------------------------------- ising_cpp
+  py::class_<IsingConfiguration>(m, "IsingConfiguration")
+      .def(py::init([](py::object shape, int fill_value) {
+             return IsingConfiguration(to_ivec(shape), fill_value);
+           }),
+           py::arg("shape") = std::vector<int>{0, 0}, py::arg("fill_value") = 1)
+      .def_property("shape", [](IsingConfiguration const &c) { return to_long_array(c.shape); },
+                    [](IsingConfiguration &c, py::object s) { c.shape = to_ivec(s); })
+      .def_readonly("n_sites", &IsingConfiguration::n_sites)
+      .def_readonly("n_variable_sites", &IsingConfiguration::n_variable_sites)
+      .def_readonly("n_unitcells", &IsingConfiguration::n_unitcells)
+      .def("occupation", [](IsingConfiguration const &c) {
+        auto const &o = c.occupation();
+        py::array_t<int32_t> a(o.size());
+        std::copy(o.begin(), o.end(), a.mutable_data());
+        return a;
+      })
+      .def("set_occupation", [](IsingConfiguration &c, py::object occ) { c.set_occupation(to_ivec(occ)); },
+           py::arg("occupation"))
+      .def("occ", &IsingConfiguration::occ, py::arg("linear_site_index"))
+      .def("set_occ", &IsingConfiguration::set_occ, py::arg("linear_site_index"), py::arg("new_occ"))
+      .def("within", &IsingConfiguration::within, py::arg("index"), py::arg("dim"))
+      .def("from_linear_site_index", [](IsingConfiguration const &c, Index l) {
+        return to_long_array(c.from_linear_site_index(l));
+      }, py::arg("linear_site_index"))
+      .def("to_linear_site_index", [](IsingConfiguration const &c, py::object mi) {
+        return c.to_linear_site_index(to_ivec(mi));
+      }, py::arg("multi_index"))
+      .def("to_dict", &config_to_dict)
+      .def_static("from_dict", &config_from_dict, py::arg("data"))
+      .def("__copy__", [](IsingConfiguration const &c) { return IsingConfiguration(c); })
+      .def("__deepcopy__", [](IsingConfiguration const &c, py::dict) { return IsingConfiguration(c); });
+
+  py::class_<IsingState>(m, "IsingState")
+      .def(py::init([](IsingConfiguration const &configuration, ValueMap const &conditions,
+                       std::optional<ValueMap> properties) {
+             return IsingState(configuration, conditions, properties.value_or(ValueMap()));
+           }),
+           py::arg("configuration"), py::arg("conditions"), py::arg("properties") = py::none())
+      .def_readwrite("configuration", &IsingState::configuration)
+      .def_readwrite("conditions", &IsingState::conditions)
+      .def_readwrite("properties", &IsingState::properties)
+      .def("to_dict", [](IsingState const &s) {
+        py::dict d;
+        d["configuration"] = config_to_dict(s.configuration);
+        d["conditions"] = valuemap_to_dict(s.conditions);
+        d["properties"] = valuemap_to_dict(s.properties);
+        return d;
+      })
+      .def_static("from_dict", [](py::dict d) {
+        return IsingState(config_from_dict(d["configuration"].cast<py::dict>()),
+                          valuemap_from_dict(d["conditions"].cast<py::dict>()),
+                          d.contains("properties") ? valuemap_from_dict(d["properties"].cast<py::dict>())
+                                                   : ValueMap());
+      }, py::arg("data"));
+
+  py::class_<IsingFormationEnergy>(m, "IsingFormationEnergy")
+      .def(py::init([](double J, int lattice_type, bool use_nlist, IsingState const *state) {
+             IsingFormationEnergy f(J, lattice_type, use_nlist);
+             return f;
+           }),
+           py::arg("J") = 1.0, py::arg("lattice_type") = 1, py::arg("use_nlist") = true,
+           py::arg("state") = nullptr)
+      .def_readwrite("J", &IsingFormationEnergy::J)
+      .def_readwrite("lattice_type", &IsingFormationEnergy::lattice_type)
+      .def("set_state", &IsingFormationEnergy::set_state, py::arg("state"), py::keep_alive<1, 2>())
+      .def("per_supercell", &IsingFormationEnergy::per_supercell)
+      .def("per_unitcell", &IsingFormationEnergy::per_unitcell)
+      .def("occ_delta_per_supercell", [](IsingFormationEnergy const &f, std::vector<long> l, std::vector<int> o) {
+        return f.occ_delta_per_supercell(l, o);
+      }, py::arg("linear_site_index"), py::arg("new_occ"));
+
+  py::class_<IsingParamComposition>(m, "IsingParamComposition")
+      .def(py::init([](IsingState const *state) { return IsingParamComposition(); }), py::arg("state") = nullptr)
+      .def("set_state", &IsingParamComposition::set_state, py::arg("state"), py::keep_alive<1, 2>())
+      .def("n_independent_compositions", &IsingParamComposition::n_independent_compositions)
+      .def("per_supercell", [](IsingParamComposition const &c) { return as_array(c.per_supercell()); })
+      .def("per_unitcell", [](IsingParamComposition const &c) { return as_array(c.per_unitcell()); })
+      .def("occ_delta_per_supercell", [](IsingParamComposition const &c, std::vector<long> l, std::vector<int> o) {
+        return as_array(c.occ_delta_per_supercell(l, o));
+      }, py::arg("linear_site_index"), py::arg("new_occ"));
+
+  py::class_<IsingSystem, std::shared_ptr<IsingSystem>>(m, "IsingSystem")
+      .def(py::init<IsingFormationEnergy, IsingParamComposition>(), py::arg("formation_energy_calculator"),
+           py::arg("param_composition_calculator"))
+      .def_readwrite("formation_energy_calculator", &IsingSystem::formation_energy_calculator)
+      .def_readwrite("param_composition_calculator", &IsingSystem::param_composition_calculator);
+
+  // ----------------------------------------------------------------- sampling
+  py::class_<Sampler, std::shared_ptr<Sampler>>(m, "Sampler")
+      .def(py::init([](std::vector<Index> shape, std::optional<std::vector<std::string>> component_names,
+                       CountType capacity_increment) {
+             if (component_names.has_value())
+               return std::make_shared<Sampler>(shape, *component_names, capacity_increment);
+             return std::make_shared<Sampler>(shape, capacity_increment);
+           }),
+           py::arg("shape"), py::arg("component_names") = py::none(), py::arg("capacity_increment") = 1000)
+      .def("append", [](Sampler &s, py::object v) { s.push_back(to_dvec(v)); }, py::arg("vector"))
+      .def("set_values", [](Sampler &s, py::array_t<double, py::array::c_style | py::array::forcecast> a) {
+        if (a.ndim() != 2) throw std::runtime_error("set_values expects a 2d array");
+        std::vector<std::vector<double>> rows(a.shape(0), std::vector<double>(a.shape(1)));
+        for (py::ssize_t r = 0; r < a.shape(0); ++r)
+          for (py::ssize_t c = 0; c < a.shape(1); ++c) rows[r][c] = a.at(r, c);
+        s.set_values(rows);
+      })
+      .def("clear", &Sampler::clear)
+      .def("set_sample_capacity", &Sampler::set_sample_capacity)
+      .def("set_capacity_increment", &Sampler::set_capacity_increment)
+      .def("component_names", &Sampler::component_names)
+      .def("shape", &Sampler::shape)
+      .def("n_components", &Sampler::n_components)
+      .def("n_samples", &Sampler::n_samples)
+      .def("sample_capacity", &Sampler::sample_capacity)
+      .def("values", [](Sampler const &s) {
+        py::array_t<double> a({static_cast<py::ssize_t>(s.n_samples()), static_cast<py::ssize_t>(s.n_components())});
+        auto w = a.mutable_unchecked<2>();
+        for (Index c = 0; c < s.n_components(); ++c)
+          for (CountType r = 0; r < s.n_samples(); ++r) w(r, c) = s.component_data(c)[r];
+        return a;
+      })
+      .def("component", [](Sampler const &s, Index i) { return as_array(s.component(i)); })
+      .def("sample", [](Sampler const &s, CountType i) { return as_array(s.sample(i)); });
+  py::bind_map<SamplerMap>(m, "SamplerMap");
+  m.def("get_n_samples", &get_n_samples, py::arg("samplers"));
+  m.def("scalar_as_vector", [](double v) { return as_array(std::vector<double>{v}); });
+  m.def("vector_as_vector", [](py::object v) { return as_array(to_dvec(v)); });
+  m.def("matrix_as_vector", [](py::array_t<double, py::array::f_style | py::array::forcecast> a) {
+    return as_array(std::vector<double>(a.data(), a.data() + a.size()));  // column-major unrolling
+  });
+  m.def("default_component_names", &default_component_names, py::arg("shape"));
+  m.def("colmajor_component_names", &colmajor_component_names, py::arg("n_rows"), py::arg("n_cols"));
+
+  py::class_<SamplerComponent>(m, "SamplerComponent")
+      .def(py::init<std::string, Index, std::string>(), py::arg("sampler_name"), py::arg("component_index"),
+           py::arg("component_name"))
+      .def_readwrite("sampler_name", &SamplerComponent::sampler_name)
+      .def_readwrite("component_index", &SamplerComponent::component_index)
+      .def_readwrite("component_name", &SamplerComponent::component_name)
+      .def("__lt__", [](SamplerComponent const &a, SamplerComponent const &b) { return a < b; })
+      .def("__eq__", [](SamplerComponent const &a, SamplerComponent const &b) { return !(a < b) && !(b < a); })
+      .def("__hash__", [](SamplerComponent const &a) {
+        return py::hash(py::make_tuple(a.sampler_name, a.component_index));
+      });
+
+  py::class_<StateSamplingFunction>(m, "StateSamplingFunction")
+      .def(py::init([](std::string name, std::string description, std::vector<Index> shape, py::object function,
+                       std::optional<std::vector<std::string>> component_names) {
+             auto f = [function]() -> std::vector<double> {
+               py::gil_scoped_acquire gil;
+               return to_dvec(function());
+             };
+             return StateSamplingFunction(name, description, shape, f, component_names);
+           }),
+           py::arg("name"), py::arg("description"), py::arg("shape"), py::arg("function"),
+           py::arg("component_names") = py::none())
+      .def_readwrite("name", &StateSamplingFunction::name)
+      .def_readwrite("description", &StateSamplingFunction::description)
+      .def_readwrite("shape", &StateSamplingFunction::shape)
+      .def_readwrite("component_names", &StateSamplingFunction::component_names)
+      .def("__call__", [](StateSamplingFunction const &f) { return as_array(f()); });
+  py::bind_map<StateSamplingFunctionMap>(m, "StateSamplingFunctionMap");
+
+  py::class_<jsonStateSamplingFunction>(m, "jsonStateSamplingFunction")
+      .def(py::init([](std::string name, std::string description, py::object function) {
+             return jsonStateSamplingFunction{name, description, function};
+           }),
+           py::arg("name"), py::arg("description"), py::arg("function"))
+      .def_readwrite("name", &jsonStateSamplingFunction::name)
+      .def_readwrite("description", &jsonStateSamplingFunction::description)
+      .def_readwrite("function", &jsonStateSamplingFunction::function)
+      .def("__call__", [](jsonStateSamplingFunction const &f) { return f.function(); });
+  py::bind_map<jsonStateSamplingFunctionMap>(m, "jsonStateSamplingFunctionMap");
+  py::class_<jsonSampler>(m, "jsonSampler")
+      .def(py::init<>())
+      .def_readwrite("values", &jsonSampler::values)
+      .def("to_list", [](jsonSampler const &s) { return py::list(s.values); });
+  py::bind_map<jsonSamplerMap>(m, "jsonSamplerMap");
+
+  py::class_<RequestedPrecision>(m, "RequestedPrecision")
+      .def(py::init([](std::optional<double> abs, std::optional<double> rel) {
+             RequestedPrecision r;
+             if (abs.has_value()) {
+               r.abs_convergence_is_required = true;
+               r.abs_precision = *abs;
+             }
+             if (rel.has_value()) {
+               r.rel_convergence_is_required = true;
+               r.rel_precision = *rel;
+             }
+             return r;
+           }),
+           py::arg("abs") = py::none(), py::arg("rel") = py::none())
+      .def_readwrite("abs_convergence_is_required", &RequestedPrecision::abs_convergence_is_required)
+      .def_readwrite("abs_precision", &RequestedPrecision::abs_precision)
+      .def_readwrite("rel_convergence_is_required", &RequestedPrecision::rel_convergence_is_required)
+      .def_readwrite("rel_precision", &RequestedPrecision::rel_precision)
+      .def("to_dict", &req_prec_to_dict)
+      .def_static("from_dict", [](py::dict d) {
+        RequestedPrecision r;
+        for (const char *k : {"abs_precision", "precision"})
+          if (d.contains(k)) {
+            r.abs_convergence_is_required = true;
+            r.abs_precision = d[k].cast<double>();
+          }
+        if (d.contains("rel_precision")) {
+          r.rel_convergence_is_required = true;
+          r.rel_precision = d["rel_precision"].cast<double>();
+        }
+        return r;
+      });
+  py::bind_map<RequestedPrecisionMap>(m, "RequestedPrecisionMap");
+
+  py::class_<BasicStatistics>(m, "BasicStatistics")
+      .def(py::init<>())
+      .def_readwrite("mean", &BasicStatistics::mean)
+      .def_readwrite("calculated_precision", &BasicStatistics::calculated_precision)
+      .def("relative_precision", [](BasicStatistics const &s) { return get_calculated_relative_precision(s); })
+      .def("to_dict", &stats_to_dict);
+  py::class_<BasicStatisticsCalculator>(m, "BasicStatisticsCalculator")
+      .def(py::init<double, Index, Index>(), py::arg("confidence") = 0.95,
+           py::arg("weighted_observations_method") = 1, py::arg("n_resamples") = 10000)
+      .def_readwrite("confidence", &BasicStatisticsCalculator::confidence)
+      .def_readwrite("weighted_observations_method", &BasicStatisticsCalculator::method)
+      .def_readwrite("n_resamples", &BasicStatisticsCalculator::n_resamples)
+      .def("__call__", [](BasicStatisticsCalculator const &c, py::object obs, py::object w) {
+        return c(to_dvec(obs), w.is_none() ? std::vector<double>() : to_dvec(w));
+      }, py::arg("observations"), py::arg("sample_weight") = py::none())
+      .def("calculate", [](BasicStatisticsCalculator const &c, py::object obs, py::object w) {
+        return c(to_dvec(obs), w.is_none() ? std::vector<double>() : to_dvec(w));
+      }, py::arg("observations"), py::arg("sample_weight") = py::none())
+      .def("to_dict", [](BasicStatisticsCalculator const &c) {
+        py::dict d;
+        d["confidence"] = c.confidence;
+        d["weighted_observations_method"] = c.method;
+        d["n_resamples"] = c.n_resamples;
+        return d;
+      });
+
+  py::class_<IndividualEquilibrationCheckResult>(m, "IndividualEquilibrationResult")
+      .def(py::init<>())
+      .def_readwrite("is_equilibrated", &IndividualEquilibrationCheckResult::is_equilibrated)
+      .def_readwrite("N_samples_for_equilibration", &IndividualEquilibrationCheckResult::N_samples_for_equilibration);
+  py::class_<EquilibrationCheckResults>(m, "EquilibrationCheckResults")
+      .def(py::init<>())
+      .def_readwrite("all_equilibrated", &EquilibrationCheckResults::all_equilibrated)
+      .def_readwrite("N_samples_for_all_to_equilibrate", &EquilibrationCheckResults::N_samples_for_all_to_equilibrate)
+      .def_readwrite("individual_results", &EquilibrationCheckResults::individual_results)
+      .def("to_dict", &eq_results_to_dict);
+  m.def("default_equilibration_check", [](py::object obs, py::object w, RequestedPrecision rp) {
+    return default_equilibration_check(to_dvec(obs), w.is_none() ? std::vector<double>() : to_dvec(w), rp);
+  }, py::arg("observations"), py::arg("sample_weight"), py::arg("requested_precision"));
+
+  py::class_<IndividualConvergenceCheckResult>(m, "IndividualConvergenceResult")
+      .def(py::init<>())
+      .def_readwrite("is_converged", &IndividualConvergenceCheckResult::is_converged)
+      .def_readwrite("requested_precision", &IndividualConvergenceCheckResult::requested_precision)
+      .def_readwrite("stats", &IndividualConvergenceCheckResult::stats);
+  py::class_<ConvergenceCheckResults>(m, "ConvergenceCheckResults")
+      .def(py::init<>())
+      .def_readwrite("all_converged", &ConvergenceCheckResults::all_converged)
+      .def_readwrite("N_samples_for_statistics", &ConvergenceCheckResults::N_samples_for_statistics)
+      .def_readwrite("individual_results", &ConvergenceCheckResults::individual_results)
+      .def("to_dict", &conv_results_to_dict);
+
+  py::class_<CutoffCheckParams>(m, "CutoffCheckParams")
+      .def(py::init<>())
+      .def_readwrite("min_count", &CutoffCheckParams::min_count)
+      .def_readwrite("min_time", &CutoffCheckParams::min_time)
+      .def_readwrite("min_sample", &CutoffCheckParams::min_sample)
+      .def_readwrite("min_clocktime", &CutoffCheckParams::min_clocktime)
+      .def_readwrite("max_count", &CutoffCheckParams::max_count)
+      .def_readwrite("max_time", &CutoffCheckParams::max_time)
+      .def_readwrite("max_sample", &CutoffCheckParams::max_sample)
+      .def_readwrite("max_clocktime", &CutoffCheckParams::max_clocktime);
+  m.def("all_minimums_met", &all_minimums_met);
+  m.def("any_maximum_met", &any_maximum_met);
+
+  py::class_<CompletionCheckParams>(m, "CompletionCheckParams")
+      .def(py::init<>())
+      .def_readwrite("cutoff_params", &CompletionCheckParams::cutoff_params)
+      .def_readwrite("requested_precision", &CompletionCheckParams::requested_precision)
+      .def_readwrite("log_spacing", &CompletionCheckParams::log_spacing)
+      .def_readwrite("check_begin", &CompletionCheckParams::check_begin)
+      .def_readwrite("check_period", &CompletionCheckParams::check_period)
+      .def_readwrite("check_base", &CompletionCheckParams::check_base)
+      .def_readwrite("check_shift", &CompletionCheckParams::check_shift)
+      .def_readwrite("check_period_max", &CompletionCheckParams::check_period_max)
+      .def_property("calc_statistics_f", [](CompletionCheckParams const &) { return py::none(); },
+                    [](CompletionCheckParams &p, py::object f) {
+                      if (py::isinstance<BasicStatisticsCalculator>(f)) {
+                        p.calc_statistics_f = f.cast<BasicStatisticsCalculator>();
+                      } else {
+                        p.calc_statistics_f = [f](std::vector<double> const &o, std::vector<double> const &w) {
+                          py::gil_scoped_acquire gil;
+                          return f(as_array(o), as_array(w)).cast<BasicStatistics>();
+                        };
+                      }
+                    })
+      .def_property("equilibration_check_f", [](CompletionCheckParams const &) { return py::none(); },
+                    [](CompletionCheckParams &p, py::object f) {
+                      p.equilibration_check_f = [f](std::vector<double> const &o, std::vector<double> const &w,
+                                                    RequestedPrecision rp) {
+                        py::gil_scoped_acquire gil;
+                        return f(as_array(o), as_array(w), rp).cast<IndividualEquilibrationCheckResult>();
+                      };
+                    });
+
+  py::class_<CompletionCheckResults>(m, "CompletionCheckResults")
+      .def(py::init<>())
+      .def_readwrite("params", &CompletionCheckResults::params)
+      .def_readwrite("count", &CompletionCheckResults::count)
+      .def_readwrite("time", &CompletionCheckResults::time)
+      .def_readwrite("clocktime", &CompletionCheckResults::clocktime)
+      .def_readwrite("n_samples", &CompletionCheckResults::n_samples)
+      .def_readwrite("has_all_minimums_met", &CompletionCheckResults::has_all_minimums_met)
+      .def_readwrite("has_any_maximum_met", &CompletionCheckResults::has_any_maximum_met)
+      .def_readwrite("n_samples_at_convergence_check", &CompletionCheckResults::n_samples_at_convergence_check)
+      .def_readwrite("equilibration_check_results", &CompletionCheckResults::equilibration_check_results)
+      .def_readwrite("convergence_check_results", &CompletionCheckResults::convergence_check_results)
+      .def_readwrite("is_complete", &CompletionCheckResults::is_complete)
+      .def("partial_reset", [](CompletionCheckResults &r) { r.partial_reset(); })
+      .def("full_reset", [](CompletionCheckResults &r) { r.full_reset(); })
+      .def("to_dict", &cc_results_to_dict);
+
+  py::class_<CompletionCheck>(m, "CompletionCheck")
+      .def(py::init<CompletionCheckParams>(), py::arg("params"))
+      .def("reset", &CompletionCheck::reset)
+      .def("params", &CompletionCheck::params, py::return_value_policy::reference_internal)
+      .def("results", &CompletionCheck::results, py::return_value_policy::reference_internal)
+      .def("n_checks", &CompletionCheck::n_checks)
+      .def("count_check", [](CompletionCheck &c, SamplerMap const &samplers, Sampler const &w, CountType count,
+                             MethodLog &log) { return c.is_complete(samplers, w, count, log.log); },
+           py::arg("samplers"), py::arg("sample_weight"), py::arg("count"), py::arg("method_log"))
+      .def("check", [](CompletionCheck &c, SamplerMap const &samplers, Sampler const &w, MethodLog &log) {
+        return c.is_complete(samplers, w, log.log);
+      }, py::arg("samplers"), py::arg("sample_weight"), py::arg("method_log"))
+      .def("time_check", [](CompletionCheck &c, SamplerMap const &samplers, Sampler const &w, double time,
+                            MethodLog &log) { return c.is_complete_time(samplers, w, time, log.log); },
+           py::arg("samplers"), py::arg("sample_weight"), py::arg("time"), py::arg("method_log"))
+      .def("count_and_time_check", [](CompletionCheck &c, SamplerMap const &samplers, Sampler const &w,
+                                      CountType count, double time, MethodLog &log) {
+        return c.is_complete(samplers, w, count, time, log.log);
+      }, py::arg("samplers"), py::arg("sample_weight"), py::arg("count"), py::arg("time"), py::arg("method_log"))
+      .def("__call__", [](CompletionCheck &c, SamplerMap const &samplers, Sampler const &w,
+                          std::optional<CountType> count, std::optional<double> time, MethodLog &log) {
+        if (count && time) return c.is_complete(samplers, w, *count, *time, log.log);
+        if (count) return c.is_complete(samplers, w, *count, log.log);
+        if (time) return c.is_complete_time(samplers, w, *time, log.log);
+        return c.is_complete(samplers, w, log.log);
+      }, py::arg("samplers"), py::arg("sample_weight"), py::arg("count") = py::none(),
+           py::arg("time") = py::none(), py::arg("method_log"));
+
+  // ------------------------------------------------------------------ methods
+  m.def("metropolis_acceptance", [](double dE, double beta, RandomNumberGenerator<> &rng) {
+    return metropolis_acceptance(dE, beta, rng);
+  }, py::arg("delta_potential_energy"), py::arg("beta"), py::arg("random_number_generator"));
+
+  // ------------------------------------------------- ising_cpp.semigrand_canonical
+  py::class_<SemiGrandCanonicalConditions, std::shared_ptr<SemiGrandCanonicalConditions>>(
+      m, "SemiGrandCanonicalConditions")
+      .def(py::init([](double temperature, py::object exchange_potential) {
+             return SemiGrandCanonicalConditions(temperature, to_dvec(exchange_potential));
+           }),
+           py::arg("temperature"), py::arg("exchange_potential"))
+      .def_readwrite("temperature", &SemiGrandCanonicalConditions::temperature)
+      .def_property("exchange_potential",
+                    [](SemiGrandCanonicalConditions const &c) { return as_array(c.exchange_potential); },
+                    [](SemiGrandCanonicalConditions &c, py::object v) { c.exchange_potential = to_dvec(v); })
+      .def("to_values", &SemiGrandCanonicalConditions::to_values)
+      .def_static("from_values", &SemiGrandCanonicalConditions::from_values, py::arg("values"))
+      .def("to_dict", [](SemiGrandCanonicalConditions const &c) { return valuemap_to_dict(c.to_values()); })
+      .def_static("from_dict", [](py::dict d) {
+        return SemiGrandCanonicalConditions::from_values(valuemap_from_dict(d));
+      }, py::arg("data"));
+
+  py::class_<SemiGrandCanonicalPotential>(m, "SemiGrandCanonicalPotential")
+      .def(py::init<std::shared_ptr<IsingSystem>>(), py::arg("system"))
+      .def("set_state", &SemiGrandCanonicalPotential::set_state, py::arg("state"), py::arg("conditions"),
+           py::keep_alive<1, 2>())
+      .def("per_supercell", &SemiGrandCanonicalPotential::per_supercell)
+      .def("per_unitcell", &SemiGrandCanonicalPotential::per_unitcell)
+      .def("occ_delta_per_supercell", [](SemiGrandCanonicalPotential const &p, std::vector<long> l, std::vector<int> o) {
+        return p.occ_delta_per_supercell(l, o);
+      }, py::arg("linear_site_index"), py::arg("new_occ"))
+      .def("occ_event_delta_per_supercell", [](SemiGrandCanonicalPotential const &p, OccEvent const &e) {
+        return p.occ_delta_per_supercell(e);
+      }, py::arg("occ_event"));
+
+  py::class_<SemiGrandCanonicalData, std::shared_ptr<SemiGrandCanonicalData>>(m, "SemiGrandCanonicalData")
+      .def(py::init([](StateSamplingFunctionMap const &sf, jsonStateSamplingFunctionMap const &jsf,
+                       CountType n_steps_per_pass, CompletionCheckParams const &p) {
+             auto d = std::make_shared<SemiGrandCanonicalData>(sf, n_steps_per_pass, p);
+             auto ex = std::make_shared<RunExtras>();
+             ex->json_sampling_functions = jsf;
+             for (auto const &kv : jsf) ex->json_samplers.emplace(kv.first, jsonSampler());
+             extras_registry()[d.get()] = ex;
+             return d;
+           }),
+           py::arg("sampling_functions"), py::arg("json_sampling_functions"), py::arg("n_steps_per_pass"),
+           py::arg("completion_check_params"))
+      .def_readwrite("sampling_functions", &SemiGrandCanonicalData::sampling_functions)
+      .def_readwrite("samplers", &SemiGrandCanonicalData::samplers)
+      .def_property_readonly("json_sampling_functions", [](SemiGrandCanonicalData const &d) {
+        return extras_registry().at(&d)->json_sampling_functions;
+      })
+      .def_property_readonly("json_samplers", [](SemiGrandCanonicalData const &d) -> jsonSamplerMap & {
+        return extras_registry().at(&d)->json_samplers;
+      }, py::return_value_policy::reference)
+      .def_readwrite("sample_weight", &SemiGrandCanonicalData::sample_weight)
+      .def_readwrite("n_pass", &SemiGrandCanonicalData::n_pass)
+      .def_readwrite("n_steps_per_pass", &SemiGrandCanonicalData::n_steps_per_pass)
+      .def_readwrite("n_accept", &SemiGrandCanonicalData::n_accept)
+      .def_readwrite("n_reject", &SemiGrandCanonicalData::n_reject)
+      .def_readonly("completion_check", &SemiGrandCanonicalData::completion_check)
+      .def("acceptance_rate", &SemiGrandCanonicalData::acceptance_rate)
+      .def("rejection_rate", &SemiGrandCanonicalData::rejection_rate)
+      .def("reset", &SemiGrandCanonicalData::reset)
+      .def("to_dict", [](SemiGrandCanonicalData const &d) {
+        // basic_occupation_metropolis.hh:168-180
+        py::dict out;
+        out["completion_check_results"] = cc_results_to_dict(d.completion_check.results());
+        out["n_pass"] = d.n_pass;
+        out["n_steps_per_pass"] = d.n_steps_per_pass;
+        out["n_accept"] = static_cast<long>(d.n_accept);
+        out["n_reject"] = static_cast<long>(d.n_reject);
+        out["acceptance_rate"] = d.acceptance_rate();
+        out["rejection_rate"] = d.rejection_rate();
+        return out;
+      });
+
+  py::class_<event_generator_type>(m, "SemiGrandCanonicalEventGenerator")
+      .def(py::init<>())
+      .def("set_state", &event_generator_type::set_state, py::arg("state"), py::keep_alive<1, 2>())
+      .def("propose", &event_generator_type::propose, py::arg("random_number_generator"),
+           py::return_value_policy::reference_internal)
+      .def("apply", &event_generator_type::apply, py::arg("occ_event"));
+
+  py::class_<calculator_type, std::shared_ptr<calculator_type>>(m, "SemiGrandCanonicalCalculator")
+      .def(py::init<std::shared_ptr<IsingSystem>>(), py::arg("system"))
+      .def_readonly("system", &calculator_type::system)
+      .def_property_readonly("state", [](calculator_type const &c) { return c.state; },
+                             py::return_value_policy::reference_internal)
+      .def_readonly("conditions", &calculator_type::conditions)
+      .def_readonly("potential", &calculator_type::potential)
+      .def_property_readonly("formation_energy_calculator",
+                             [](calculator_type const &c) { return c.formation_energy_calculator; },
+                             py::return_value_policy::reference_internal)
+      .def_property_readonly("param_composition_calculator",
+                             [](calculator_type const &c) { return c.param_composition_calculator; },
+                             py::return_value_policy::reference_internal)
+      .def_readonly("data", &calculator_type::data)
+      .def_readwrite("update_mode", &calculator_type::update_mode)
+      .def_readonly("last_kernel", &calculator_type::last_kernel)
+      .def("default_sampling_functions", [](std::shared_ptr<calculator_type> mc) {
+        StateSamplingFunctionMap fns;
+        for (auto const &f : {make_parametric_composition_f(mc), make_formation_energy_f(mc),
+                              make_potential_energy_f(mc)})
+          fns.emplace(f.name, f);
+        return fns;
+      })
+      .def("default_json_sampling_functions", [](py::object self) {
+        jsonStateSamplingFunctionMap fns;
+        py::object weak = py::module_::import("weakref").attr("ref")(self);
+        py::object f = py::cpp_function([weak]() -> py::object {
+          py::object mc = weak();
+          if (mc.is_none()) throw std::runtime_error("Error in configuration sampling function: mc_calculator == nullptr");
+          auto &c = mc.cast<calculator_type &>();
+          if (c.state == nullptr)
+            throw std::runtime_error("Error in configuration sampling function: mc_calculator->state == nullptr");
+          return config_to_dict(c.state->configuration);
+        });
+        fns.emplace("configuration", jsonStateSamplingFunction{"configuration", "Configuration values", f});
+        return fns;
+      })
+      .def("run", [](std::shared_ptr<calculator_type> mc, IsingState &state,
+                     StateSamplingFunctionMap const &sampling_functions,
+                     jsonStateSamplingFunctionMap const &json_sampling_functions,
+                     CompletionCheckParams const &completion_check_params,
+                     event_generator_type const &event_generator, int sample_period,
+                     std::optional<MethodLog> method_log, std::optional<PyEngine> random_engine,
+                     py::object write_status_f, std::optional<std::string> update_mode) {
+        if (update_mode.has_value()) mc->update_mode = *update_mode;
+        auto extras = std::make_shared<RunExtras>();
+        extras->json_sampling_functions = json_sampling_functions;
+        for (auto const &kv : json_sampling_functions) extras->json_samplers.emplace(kv.first, jsonSampler());
+        calculator_type::write_status_type wsf;
+        if (write_status_f.is_none()) {
+          wsf = default_write_status;
+        } else {
+          wsf = [write_status_f, mc](calculator_type const &, MethodLog &log) {
+            write_status_f(mc, py::cast(&log, py::return_value_policy::reference));
+          };
+        }
+        std::function<void()> json_hook;
+        if (!json_sampling_functions.empty()) {
+          json_hook = [extras]() {
+            for (auto &kv : extras->json_sampling_functions)
+              extras->json_samplers.at(kv.first).values.append(kv.second.function());
+          };
+        }
+        // `data` is created inside run; register the extras as soon as it exists
+        // by wrapping the status writer and the hook
+        auto reg = [mc, extras]() {
+          if (mc->data) extras_registry()[mc->data.get()] = extras;
+        };
+        calculator_type::write_status_type wsf2 = [wsf, reg](calculator_type const &c, MethodLog &log) {
+          reg();
+          wsf(c, log);
+        };
+        std::function<void()> hook2;
+        if (json_hook) hook2 = [json_hook, reg]() { reg(); json_hook(); };
+        mc->run(state, sampling_functions, completion_check_params, event_generator, sample_period, method_log,
+                random_engine.has_value() ? random_engine->e : nullptr, wsf2, hook2);
+        reg();
+      },
+           py::arg("state"), py::arg("sampling_functions"), py::arg("json_sampling_functions"),
+           py::arg("completion_check_params"), py::arg("event_generator"), py::arg("sample_period") = 1,
+           py::arg("method_log") = py::none(), py::arg("random_engine") = py::none(),
+           py::arg("write_status_f") = py::none(), py::arg("update_mode") = py::none());
+
+  m.def("default_write_status", &default_write_status, py::arg("mc_calculator"), py::arg("method_log"));
+}

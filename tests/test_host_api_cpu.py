@@ -1,0 +1,179 @@
+"""Host-side logic of the drop-in Python API that needs no GPU: mirrors the
+reference's own tests python/tests/test_ValueMap.py, test_RandomNumberGeneratory.py,
+sampling/test_Sampler.py and sampling/test_CompletionCheck.py:5-37, with only
+the import root changed."""
+import math
+
+import numpy as np
+import pytest
+
+import casmcode_monte_b200.monte as monte
+import casmcode_monte_b200.monte.ising_cpp as ising
+import casmcode_monte_b200.monte.ising_cpp.semigrand_canonical as sgc
+import casmcode_monte_b200.monte.sampling as sampling
+
+
+def test_value_map_round_trip():
+    values = monte.ValueMap()
+    values.scalar_values["check"] = 1.0
+    assert math.isclose(values.scalar_values["check"], 1.0)
+    v = np.array([1.0, 1.0])
+    values.vector_values["check"] = v
+    assert np.allclose(values.vector_values["check"], v)
+    values.vector_values["check"][0] = 2.0  # in-place, as with the reference's Eigen views
+    assert np.allclose(values.vector_values["check"], np.array([2.0, 1.0]))
+    values = monte.ValueMap()
+    values.scalar_values["is_scalar"] = 1.0
+    values.vector_values["is_vector"] = [2.0, 1.0]
+    values.boolean_values["flag"] = True
+    data = values.to_dict()
+    values_2 = monte.ValueMap.from_dict(data)
+    assert len(values_2.scalar_values) == 1 and "is_scalar" in values_2.scalar_values
+    assert len(values_2.vector_values) == 1 and np.allclose(values_2.vector_values["is_vector"], [2.0, 1.0])
+    assert values_2.boolean_values["flag"] is True
+    # from_dict typing rule: bool -> boolean, number -> scalar, array -> vector
+    d = monte.ValueMap.from_dict({"temperature": 2000.0, "exchange_potential": [0.0], "m": [[1, 2], [3, 4]]})
+    assert "temperature" in d.scalar_values and "exchange_potential" in d.vector_values
+    assert d.to_dict()["m"] == [[1.0, 2.0], [3.0, 4.0]]
+    inc = monte.ValueMap.from_dict({"temperature": 10.0, "exchange_potential": [0.5]})
+    out = d.make_incremented_values(inc, 3)
+    assert out.scalar_values["temperature"] == 2030.0 and np.allclose(out.vector_values["exchange_potential"], [1.5])
+    assert not d.is_mismatched(inc) and inc.is_mismatched(d)
+
+
+def test_rng_range_and_reproducibility():
+    rng = monte.RandomNumberGenerator()
+    for _ in range(10000):
+        assert 0 <= rng.random_int(9) <= 9
+    e = monte.RandomNumberEngine()
+    state = e.dump()
+    rng = monte.RandomNumberGenerator(e)
+    x = [rng.random_int(9) for _ in range(10)]
+    e.load(state)
+    assert x == [rng.random_int(9) for _ in range(10)]
+    e.load(state)
+    r = [rng.random_real(9) for _ in range(10)]
+    e.load(state)
+    assert r == [rng.random_real(9) for _ in range(10)]
+
+
+def test_rng_matches_oracle_stream(oracle):
+    e = monte.RandomNumberEngine()
+    e.seed(4242)
+    g = monte.RandomNumberGenerator(e)
+    o = oracle.RandomNumberEngine()
+    o.seed(4242)
+    for _ in range(50):
+        assert g.random_int(624) == oracle.random_int(o, 624)
+        assert g.random_real(1.0) == oracle.random_real(o, 1.0)
+    assert e.dump() == o.dump()
+
+
+def test_sampler_scalar_vector_matrix():
+    sampler = sampling.Sampler(shape=[], component_names=["x"], capacity_increment=10000)
+    assert sampler.n_components() == 1 and sampler.n_samples() == 0
+    assert sampler.component_names() == ["x"]
+    for _ in range(100):
+        sampler.append([0.3])
+    assert sampler.n_samples() == 100
+    sampler.clear()
+    for _ in range(100):
+        sampler.append(sampling.scalar_as_vector(0.3))
+    assert sampler.values().shape == (100, 1)
+    sampler.clear()
+    assert sampler.sample_capacity() == 10000
+    n = 100000
+    for _ in range(n):
+        sampler.append([0.3])
+    assert sampler.n_samples() == n and sampler.values().shape == (n, 1)
+    assert sampler.sample_capacity() == n
+    s2 = sampling.Sampler(shape=[2], component_names=["x1", "x2"])
+    s2.append([0.3, 0.5])
+    s2.append(sampling.vector_as_vector([0.3, 0.5]))
+    assert s2.values().shape == (2, 2) and np.allclose(s2.component(1), [0.5, 0.5])
+    s3 = sampling.Sampler(shape=[2, 2])
+    assert s3.component_names() == ["0,0", "1,0", "0,1", "1,1"]
+    s3.append(sampling.matrix_as_vector(np.array([[0.1, 0.2], [0.3, 0.4]])))
+    assert np.allclose(s3.sample(0), [0.1, 0.3, 0.2, 0.4])  # column-major unrolling
+    assert sampling.default_component_names([]) == ["0"]
+    assert sampling.default_component_names([3]) == ["0", "1", "2"]
+    with pytest.raises(RuntimeError):
+        sampling.default_component_names([2, 2, 2])
+    with pytest.raises(RuntimeError):
+        s3.append([1.0])
+
+
+def test_completion_check_max_count(tmp_path):
+    params = sampling.CompletionCheckParams()
+    params.cutoff_params.max_count = 12
+    cc = sampling.CompletionCheck(params)
+    samplers = sampling.SamplerMap()
+    samplers["e"] = sampling.Sampler(shape=[])
+    samplers["x"] = sampling.Sampler(shape=[3])
+    weight = sampling.Sampler(shape=[])
+    log = monte.MethodLog(str(tmp_path / "log.txt"))
+    n_steps = 0
+    while not cc.count_check(samplers=samplers, sample_weight=weight, count=n_steps, method_log=log):
+        n_steps += 1
+        if n_steps % 10 == 0:
+            samplers["e"].append([0])
+            samplers["x"].append([0, 0, 0])
+    assert n_steps == 12
+    r = cc.results().to_dict()
+    assert r["is_complete"] and r["has_any_maximum_met"] and r["count"] == 12 and r["n_samples"] == 1
+
+
+def test_requested_precision_and_converge_helper():
+    rp = sampling.RequestedPrecision(abs=0.001)
+    assert rp.abs_convergence_is_required and not rp.rel_convergence_is_required
+    assert rp.to_dict() == {"abs_precision": 0.001}
+    assert sampling.RequestedPrecision.from_dict({"precision": 0.5, "rel_precision": 0.1}).abs_precision == 0.5
+    mc = sgc.SemiGrandCanonicalCalculator(
+        system=ising.IsingSystem(
+            formation_energy_calculator=ising.IsingFormationEnergy(J=0.1, lattice_type=1),
+            param_composition_calculator=ising.IsingParamComposition(),
+        )
+    )
+    fns = mc.default_sampling_functions()
+    assert sorted(fns.keys()) == ["formation_energy", "param_composition", "potential_energy"]
+    params = sampling.CompletionCheckParams()
+    sampling.converge(fns, params).set_precision("potential_energy", abs=0.001).set_precision("param_composition", rel=0.01)
+    keys = sorted((k.sampler_name, k.component_index, k.component_name) for k, _ in params.requested_precision.items())
+    assert keys == [("param_composition", 0, "0"), ("potential_energy", 0, "0")]
+    with pytest.raises(Exception):
+        sampling.converge(fns, params).set_precision("nope", abs=1.0)
+    with pytest.raises(Exception):
+        sampling.converge(fns, params).set_precision("potential_energy")
+
+
+def test_configuration_host_side():
+    c = ising.IsingConfiguration(shape=(25, 25))
+    assert c.n_sites == 625 and c.n_variable_sites == 625 and c.n_unitcells == 625
+    assert list(c.shape) == [25, 25]
+    assert c.occ(7) == 1
+    c.set_occ(7, -1)
+    assert c.occ(7) == -1 and c.occupation()[7] == -1
+    assert c.within(-1, 0) == 24 and c.within(25, 1) == 0
+    assert list(c.from_linear_site_index(27)) == [2, 1]
+    assert c.to_linear_site_index([2, 1]) == 27
+    d = c.to_dict()
+    assert d["shape"] == [25, 25] and len(d["occupation"]) == 625
+    c2 = ising.IsingConfiguration.from_dict(d)
+    assert np.array_equal(c2.occupation(), c.occupation())
+    with pytest.raises(RuntimeError):
+        ising.IsingConfiguration(shape=[4])  # model.hh:25-27
+    with pytest.raises(RuntimeError):
+        c.set_occupation(np.ones(3, dtype=int))  # model.hh:56-58
+    with pytest.raises(RuntimeError):
+        ising.IsingFormationEnergy(J=0.1, lattice_type=2)  # model.hh:175-177
+    import copy
+
+    c3 = copy.deepcopy(c)
+    c3.set_occ(0, -1)
+    assert c.occ(0) == 1
+    cond = sgc.SemiGrandCanonicalConditions(temperature=2000.0, exchange_potential=[0.5])
+    v = cond.to_values()
+    assert v.scalar_values["temperature"] == 2000.0
+    assert sgc.SemiGrandCanonicalConditions.from_values(v).exchange_potential[0] == 0.5
+    with pytest.raises(RuntimeError):
+        sgc.SemiGrandCanonicalConditions.from_values(monte.ValueMap.from_dict({"temperature": 1.0}))
