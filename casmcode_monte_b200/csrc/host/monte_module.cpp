@@ -41,9 +41,17 @@ struct RunExtras {
   jsonStateSamplingFunctionMap json_sampling_functions;
   jsonSamplerMap json_samplers;
 };
-static std::map<SemiGrandCanonicalData const *, std::shared_ptr<RunExtras>> &extras_registry() {
-  static std::map<SemiGrandCanonicalData const *, std::shared_ptr<RunExtras>> r;
-  return r;
+// Keyed by the data object's address.  Deliberately leaked: it holds Python
+// objects, which must not be released after the interpreter has shut down.
+typedef std::map<SemiGrandCanonicalData const *, std::shared_ptr<RunExtras>> ExtrasRegistry;
+static ExtrasRegistry &extras_registry() {
+  static ExtrasRegistry *r = new ExtrasRegistry();
+  return *r;
+}
+static void register_extras(SemiGrandCanonicalData const *d, std::shared_ptr<RunExtras> ex) {
+  ExtrasRegistry &r = extras_registry();
+  if (r.size() > 4096) r.clear();  // bound the bookkeeping of long sessions
+  r[d] = std::move(ex);
 }
 
 PYBIND11_MAKE_OPAQUE(SamplerMap);
@@ -789,7 +797,7 @@ PYBIND11_MODULE(_monte_b200, m) {
              auto ex = std::make_shared<RunExtras>();
              ex->json_sampling_functions = jsf;
              for (auto const &kv : jsf) ex->json_samplers.emplace(kv.first, jsonSampler());
-             extras_registry()[d.get()] = ex;
+             register_extras(d.get(), ex);
              return d;
            }),
            py::arg("sampling_functions"), py::arg("json_sampling_functions"), py::arg("n_steps_per_pass"),
@@ -897,7 +905,7 @@ PYBIND11_MODULE(_monte_b200, m) {
         // `data` is created inside run; register the extras as soon as it exists
         // by wrapping the status writer and the hook
         auto reg = [mc, extras]() {
-          if (mc->data) extras_registry()[mc->data.get()] = extras;
+          if (mc->data) register_extras(mc->data.get(), extras);
         };
         calculator_type::write_status_type wsf2 = [wsf, reg](calculator_type const &c, MethodLog &log) {
           reg();
