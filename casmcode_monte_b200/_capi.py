@@ -58,6 +58,7 @@ SIGNATURES = {
     "cmg_randomize_occupation": (C.c_int, [_ctx, C.c_int, C.c_uint64, C.c_double]),
     "cmg_seed_philox": (C.c_int, [_ctx, C.c_uint64]),
     "cmg_set_pass_counter": (C.c_int, [_ctx, C.c_uint64]),
+    "cmg_set_chain_offset": (C.c_int, [_ctx, C.c_int64]),
     "cmg_seed_mt19937_64": (C.c_int, [_ctx, C.c_int, C.c_uint64]),
     "cmg_set_mt19937_64_state": (C.c_int, [_ctx, C.c_int, _u64p, C.c_int]),
     "cmg_get_mt19937_64_state": (C.c_int, [_ctx, C.c_int, _u64p, _intp]),

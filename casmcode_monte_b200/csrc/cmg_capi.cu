@@ -49,6 +49,11 @@ struct cmg_context {
   long long global_shape[3] = {1, 1, 1};
   uint8_t *d_halo[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [colour][side]
   uint8_t *push[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};    // [colour][side]
+  unsigned long long *d_flags = nullptr;       // [2] wait flags, raised by the neighbours
+  unsigned long long *peer_flag[2] = {nullptr, nullptr};  // the neighbours' wait flags
+  unsigned int *d_done = nullptr;
+  unsigned long long slab_epoch_base = 0;  // half-sweep index of the first fused half-sweep
+  bool slab_epoch_set = false;
   std::vector<void *> ipc_opened;
 
   uint8_t *d_planes = nullptr;
@@ -66,6 +71,7 @@ struct cmg_context {
   bool model_set = false;
 
   unsigned long long philox_seed = 0;
+  int chain_offset = 0;
   unsigned long long h_pass = 0;  // global pass index (Philox counter)
   RunState *d_run = nullptr;
   long long n_pass = 0;  // passes since reset_counters
@@ -214,6 +220,12 @@ static LatticeView view(const cmg_context *c) {
       L.push_lo[col] = c->push[col][0];
       L.push_hi[col] = c->push[col][1];
     }
+    for (int side = 0; side < 2; ++side) {
+      // only meaningful once a peer is attached on that side
+      L.wait_flag[side] = c->peer_flag[side] ? c->d_flags + side : nullptr;
+      L.signal_flag[side] = c->peer_flag[side];
+    }
+    L.done_counter = (c->peer_flag[0] || c->peer_flag[1]) ? c->d_done : nullptr;
   }
   return L;
 }
@@ -327,6 +339,10 @@ static int create_common(int dim, const int64_t *shape, int n_chains, int device
         CUC(cudaMalloc(&c->d_halo[col][side], (size_t)hb));
         CUC(cudaMemset(c->d_halo[col][side], 1, (size_t)hb));
       }
+    CUC(cudaMalloc(&c->d_flags, 2 * sizeof(unsigned long long)));
+    CUC(cudaMemset(c->d_flags, 0, 2 * sizeof(unsigned long long)));
+    CUC(cudaMalloc(&c->d_done, sizeof(unsigned int)));
+    CUC(cudaMemset(c->d_done, 0, sizeof(unsigned int)));
   }
 #undef CUC
   *out = c;
@@ -374,6 +390,8 @@ int cmg_destroy(cmg_context *c) {
   cudaFree(c->d_dbl);
   for (int col = 0; col < 2; ++col)
     for (int side = 0; side < 2; ++side) cudaFree(c->d_halo[col][side]);
+  cudaFree(c->d_flags);
+  cudaFree(c->d_done);
   delete c;
   return CMG_OK;
 }
@@ -698,6 +716,14 @@ static int push_run_state(cmg_context *c) {
   return CMG_OK;
 }
 
+int cmg_set_chain_offset(cmg_context *c, int64_t global_index_of_chain_0) {
+  NEED(c);
+  if (global_index_of_chain_0 < 0 || global_index_of_chain_0 + c->n_chains > (1 << 24))
+    return fail(c, CMG_EINVAL, "chain offset out of range");
+  c->chain_offset = (int)global_index_of_chain_0;
+  return CMG_OK;
+}
+
 int cmg_set_pass_counter(cmg_context *c, uint64_t pass_index) {
   NEED(c);
   c->h_pass = pass_index;
@@ -899,6 +925,8 @@ static int launch_half_sweep(cmg_context *c, int variant, int colour, unsigned l
     A.rk[2 * r + 1] = (uint32_t)(c->philox_seed >> 32) + (uint32_t)r * kPhiloxW1;
   }
   A.colour = colour;
+  A.chain_offset = c->chain_offset;
+  A.L.epoch = 2ull * pass + (unsigned long long)colour - c->slab_epoch_base;
   A.js = pick_js(c, variant);
   const long long plane_size = c->n_sites / 2;
   dim3 block(128);
@@ -949,6 +977,7 @@ static int launch_tile_passes_sp(cmg_context *c, const TilePlan &tp, int n_passe
     A.rk[2 * r + 1] = (uint32_t)(c->philox_seed >> 32) + (uint32_t)r * kPhiloxW1;
   }
   A.n_passes = n_passes;
+  A.chain_offset = c->chain_offset;
   A.n_tiles = tp.n_tiles;
   A.halo = tp.n_tiles == 1 ? 0 : 2 * n_passes;
   A.w_max = tp.w_max;
@@ -1147,6 +1176,10 @@ int cmg_slab_half_sweep(cmg_context *c, int colour, uint64_t pass_index, int sam
   }
   c->nat_is_current = false;
   c->variant_name = "bulk2d";
+  if (!c->slab_epoch_set) {  // flags count half-sweeps from the first one stepped
+    c->slab_epoch_base = 2ull * pass_index + (unsigned long long)colour;
+    c->slab_epoch_set = true;
+  }
   rc = launch_half_sweep(c, V_BULK2D, colour, pass_index, do_sample, c->n_samples);
   if (rc) return rc;
   if (colour == 1) {
@@ -1181,17 +1214,19 @@ int cmg_slab_halo_ptr(cmg_context *c, int colour, int side, void **dev_ptr, int6
 
 struct SlabIpcBlob {
   cudaIpcMemHandle_t h[2][2];
+  cudaIpcMemHandle_t flags;
 };
 
 int cmg_slab_ipc_export(cmg_context *c, void *handle_out, int64_t handle_bytes) {
   NEED(c);
   if (!c->slab) return fail(c, CMG_ESTATE, "not a slab context");
   if (!handle_out || handle_bytes < (int64_t)sizeof(SlabIpcBlob))
-    return fail(c, CMG_EINVAL, "handle buffer too small (need 256 bytes)");
+    return fail(c, CMG_EINVAL, "handle buffer too small (need 320 bytes)");
   SlabIpcBlob blob;
   for (int col = 0; col < 2; ++col)
     for (int side = 0; side < 2; ++side)
       CU(c, cudaIpcGetMemHandle(&blob.h[col][side], c->d_halo[col][side]));
+  CU(c, cudaIpcGetMemHandle(&blob.flags, c->d_flags));
   memcpy(handle_out, &blob, sizeof blob);
   return CMG_OK;
 }
@@ -1215,6 +1250,7 @@ int cmg_slab_ipc_attach(cmg_context *c, int side, const void *handle, int64_t ha
       cudaGetLastError();
     }
     for (int col = 0; col < 2; ++col) c->push[col][side] = peer->d_halo[col][1 - side];
+    c->peer_flag[side] = peer->d_flags + (1 - side);
     return CMG_OK;
   }
   if (!handle || handle_bytes < (int64_t)sizeof(SlabIpcBlob))
@@ -1226,6 +1262,12 @@ int cmg_slab_ipc_attach(cmg_context *c, int side, const void *handle, int64_t ha
     CU(c, cudaIpcOpenMemHandle(&p, blob.h[col][1 - side], cudaIpcMemLazyEnablePeerAccess));
     c->ipc_opened.push_back(p);
     c->push[col][side] = (uint8_t *)p;
+  }
+  {
+    void *p = nullptr;
+    CU(c, cudaIpcOpenMemHandle(&p, blob.flags, cudaIpcMemLazyEnablePeerAccess));
+    c->ipc_opened.push_back(p);
+    c->peer_flag[side] = (unsigned long long *)p + (1 - side);
   }
   return CMG_OK;
 }

@@ -46,6 +46,14 @@ struct LatticeView {
   // columns (the neighbour's halo buffers, possibly peer memory); null => none
   uint8_t *push_lo[2];  // our column 0      -> low neighbour's halo_hi
   uint8_t *push_hi[2];  // our column n1-1   -> high neighbour's halo_lo
+  // cross-GPU ordering of the fused push (all null when not used):
+  // wait_flag[side] lives in OUR memory and is raised by the neighbour on that
+  // side when its half-sweep has finished pushing; signal_flag[side] is the
+  // neighbour's wait flag (peer memory).  Values count finished half-sweeps.
+  const unsigned long long *wait_flag[2];
+  unsigned long long *signal_flag[2];
+  unsigned int *done_counter;   // CTAs of this launch that have finished
+  unsigned long long epoch;     // index of this half-sweep (2*pass + colour)
 };
 
 struct SweepArgs {
@@ -60,6 +68,7 @@ struct SweepArgs {
   uint32_t rk[20];
   int colour;
   int js;  // columns per thread strip (bulk kernels)
+  int chain_offset;  // global index of chain 0 (chains sharded over several contexts)
 };
 
 // ---------------------------------------------------------------------------
@@ -249,9 +258,9 @@ __global__ void __launch_bounds__(128) k_halfsweep_generic(SweepArgs A) {
   unsigned int acc = 0;
   long long ones = 0, bsum = 0;
   if (8 * g < plane_size) {
-    const uint4 ra = site_group_random((unsigned long long)g, (uint32_t)chain << 8, A.pass,
+    const uint4 ra = site_group_random((unsigned long long)g, (uint32_t)(chain + A.chain_offset) << 8, A.pass,
                                        A.colour, 0, A.rk);
-    const uint4 rb = site_group_random((unsigned long long)g, (uint32_t)chain << 8, A.pass,
+    const uint4 rb = site_group_random((unsigned long long)g, (uint32_t)(chain + A.chain_offset) << 8, A.pass,
                                        A.colour, 1, A.rk);
 #pragma unroll
     for (int w = 0; w < 8; ++w) {
@@ -416,12 +425,49 @@ __device__ __forceinline__ uint4 update16(uint4 ce, uint4 om, uint4 oc, uint4 op
   return make_uint4(cw[0], cw[1], cw[2], cw[3]);
 }
 
+// ---- cross-GPU ordering for slab decomposition ------------------------------
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// before reading halos: both neighbours must have finished half-sweep epoch-1
+__device__ __forceinline__ void slab_wait_neighbours(const LatticeView &L) {
+  if (L.epoch == 0) return;
+  if (threadIdx.x == 0) {
+    for (int side = 0; side < 2; ++side)
+      if (L.wait_flag[side])
+        while (ld_acquire_sys(L.wait_flag[side]) < L.epoch) __nanosleep(64);
+  }
+  __syncthreads();
+}
+// after the last store: the last CTA of the launch raises the neighbours' flags
+__device__ __forceinline__ void slab_signal_neighbours(const LatticeView &L) {
+  if (!L.done_counter) return;
+  __threadfence_system();  // this thread's peer stores are visible system-wide
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
+    const unsigned int prev = atomicAdd(L.done_counter, 1u);
+    if (prev == total - 1) {
+      *L.done_counter = 0;
+      __threadfence_system();
+      for (int side = 0; side < 2; ++side)
+        if (L.signal_flag[side]) st_release_sys(L.signal_flag[side], L.epoch + 1);
+    }
+  }
+}
+
 template <bool SAMPLE>
 __global__ void __launch_bounds__(128) k_halfsweep_bulk2d(SweepArgs A) {
   const LatticeView &L = A.L;
   const int chain = blockIdx.y;
   load_accept_table(A.tabs + chain);
   __syncthreads();
+  slab_wait_neighbours(L);
 
   const int h = L.h, n1 = L.n1;
   const int V = h >> 4;  // 16-byte vectors per column
@@ -443,7 +489,7 @@ __global__ void __launch_bounds__(128) k_halfsweep_bulk2d(SweepArgs A) {
     const uint8_t *halo_hi = L.halo_hi[1 - A.colour];
     uint8_t *push_lo = L.push_lo[A.colour];
     uint8_t *push_hi = L.push_hi[A.colour];
-    const uint32_t chain_word = (uint32_t)chain << 8;
+    const uint32_t chain_word = (uint32_t)(chain + A.chain_offset) << 8;
 
     // column pointer of the opposite plane with periodic wrap / halo
     auto ocol = [&](int j) -> const uint8_t * {
@@ -484,6 +530,7 @@ __global__ void __launch_bounds__(128) k_halfsweep_bulk2d(SweepArgs A) {
   if (SAMPLE) accum_finish(acc, 4, ones, bsum);
   block_accumulate<128>(acc.acc, ones, bsum, SAMPLE, A.n_accept + chain,
                         SAMPLE ? A.sb + (long long)chain * A.sb_chain_stride : nullptr);
+  slab_signal_neighbours(L);
 }
 
 // ---------------------------------------------------------------------------
@@ -518,6 +565,7 @@ struct TileArgs {
   int halo;                      // 2*P, or 0 when n_tiles == 1
   int w_max;                     // widest tile incl. halos (smem plane = w_max*h bytes)
   uint32_t v_magic;              // ceil(2^32 / V), V = h/16
+  int chain_offset;              // global index of chain 0
 };
 
 template <int NT>
@@ -574,7 +622,7 @@ __global__ void __launch_bounds__(NT, 1) k_tile2d(TileArgs A) {
   const uint32_t soff[2] = {(uint32_t)kSmemTile, (uint32_t)kSmemTile + (uint32_t)A.w_max * (uint32_t)h};
   uint8_t *G[2] = {L.planes + (long long)chain * L.chain_stride,
                    L.planes + (long long)chain * L.chain_stride + L.plane_stride};
-  const uint32_t chain_word = (uint32_t)chain << 8;
+  const uint32_t chain_word = (uint32_t)(chain + A.chain_offset) << 8;
 
   // ---- stage the tile: local column cl <-> global column (c0 - H + cl) mod n1
   for (int it = threadIdx.x; it < 2 * W * V; it += NT) {
@@ -704,7 +752,7 @@ __global__ void __launch_bounds__(128) k_halfsweep_bulk3d(SweepArgs A) {
     const uint8_t *O = Oall + layer * k;
     const uint8_t *Okm = Oall + layer * ((k == 0) ? n2 - 1 : k - 1);
     const uint8_t *Okp = Oall + layer * ((k == n2 - 1) ? 0 : k + 1);
-    const uint32_t chain_word = (uint32_t)chain << 8;
+    const uint32_t chain_word = (uint32_t)(chain + A.chain_offset) << 8;
 
     auto wrapj = [&](int j) { return (j < 0) ? n1 - 1 : (j >= n1 ? 0 : j); };
     uint4 om = ld16_nc(O + (long long)h * wrapj(jbeg - 1) + p0);

@@ -131,6 +131,9 @@ class IsingLatticeGPU:
     def set_pass_counter(self, t):
         self._ck(self._lib.cmg_set_pass_counter(self._ctx, int(t)))
 
+    def set_chain_offset(self, global_index_of_chain_0):
+        self._ck(self._lib.cmg_set_chain_offset(self._ctx, int(global_index_of_chain_0)))
+
     def seed_mt19937_64(self, seed, chain=0):
         self._ck(self._lib.cmg_seed_mt19937_64(self._ctx, chain, int(seed)))
 
@@ -283,16 +286,16 @@ class IsingLatticeGPU:
         return p.value, n.value
 
     def slab_ipc_export(self):
-        buf = C.create_string_buffer(256)
-        self._ck(self._lib.cmg_slab_ipc_export(self._ctx, buf, 256))
+        buf = C.create_string_buffer(320)
+        self._ck(self._lib.cmg_slab_ipc_export(self._ctx, buf, 320))
         return buf.raw
 
     def slab_ipc_attach(self, side, handle=None, peer=None):
         if peer is not None:
             self._ck(self._lib.cmg_slab_ipc_attach(self._ctx, side, None, 0, 1, peer._ctx))
         else:
-            buf = C.create_string_buffer(handle, 256)
-            self._ck(self._lib.cmg_slab_ipc_attach(self._ctx, side, buf, 256, 0, None))
+            buf = C.create_string_buffer(handle, 320)
+            self._ck(self._lib.cmg_slab_ipc_attach(self._ctx, side, buf, 320, 0, None))
 
     # -- introspection --
     @property

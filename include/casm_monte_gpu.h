@@ -160,6 +160,9 @@ int cmg_randomize_occupation(cmg_context *ctx, int chain, uint64_t seed, double 
  * libstdc++-13 uniform_int_distribution (Lemire) and generate_canonical. */
 int cmg_seed_philox(cmg_context *ctx, uint64_t seed);
 int cmg_set_pass_counter(cmg_context *ctx, uint64_t pass_index);
+/* chains sharded over several contexts / GPUs keep the Philox stream of their
+ * GLOBAL chain index: global index = this offset + local chain */
+int cmg_set_chain_offset(cmg_context *ctx, int64_t global_index_of_chain_0);
 int cmg_seed_mt19937_64(cmg_context *ctx, int chain, uint64_t seed);
 /* raw engine state: 312 words + position, i.e. what operator<< of the engine
  * prints (python/src/monte.cpp:495-513 dump()/load()) */

@@ -1790,6 +1790,40 @@ inline void checkerboard_pass(std::vector<int> &occ, std::vector<int> const &sha
   }
 }
 
+// One coloured half-sweep of a column slab (2-d): the slab holds global columns
+// [col_begin, col_begin + n_cols) in `occ` (n0 x n_cols, column-major) and the
+// two neighbouring columns in halo_lo / halo_hi (n0 entries each).  Same
+// uniforms as checkerboard_pass (keyed on GLOBAL plane indices), so stitching
+// the slabs back together reproduces the undecomposed trajectory bit for bit.
+inline long long checkerboard_half_sweep_slab(std::vector<int> &occ, std::vector<int> const &halo_lo,
+                                              std::vector<int> const &halo_hi, long n0,
+                                              long col_begin, long n_cols,
+                                              AcceptTable const &tab, uint64_t seed, uint32_t chain,
+                                              uint64_t pass_index, int colour) {
+  const long h = n0 / 2;
+  std::array<uint32_t, 2> key = {static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)};
+  long long n_accept = 0;
+  for (long jl = 0; jl < n_cols; ++jl) {
+    const long j = col_begin + jl;
+    for (long p = 0; p < h; ++p) {
+      const long i = 2 * p + ((j + colour) & 1);
+      const uint64_t q = static_cast<uint64_t>(p) + static_cast<uint64_t>(h) * static_cast<uint64_t>(j);
+      const uint32_t r = checkerboard_uniform(q, chain, pass_index, colour, key);
+      const long ip = (i + 1) % n0, im = (i + n0 - 1) % n0;
+      const int left = (jl == 0) ? halo_lo[i] : occ[i + n0 * (jl - 1)];
+      const int right = (jl == n_cols - 1) ? halo_hi[i] : occ[i + n0 * (jl + 1)];
+      const int n_up = (occ[ip + n0 * jl] > 0) + (occ[im + n0 * jl] > 0) + (left > 0) + (right > 0);
+      const long l = i + n0 * jl;
+      const int sp = occ[l] > 0 ? 1 : 0;
+      if (r <= tab.thr_m1[sp][n_up]) {
+        occ[l] = -occ[l];
+        ++n_accept;
+      }
+    }
+  }
+  return n_accept;
+}
+
 // Integer observables: S = sum_l s_l ; B = sum_l s_l*(s_{+i} + s_{+j} [+ s_{+k}])
 inline void integer_observables(std::vector<int> const &occ,
                                 std::vector<int> const &shape, long long &S,

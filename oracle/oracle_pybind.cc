@@ -425,6 +425,15 @@ PYBIND11_MODULE(_monte_oracle, m) {
         py::arg("pass0") = 0, py::arg("n_passes") = 1,
         py::arg("sample_period") = 1);
 
+  m.def("checkerboard_half_sweep_slab",
+        [](i32arr occ, i32arr halo_lo, i32arr halo_hi, long n0, long col_begin, long n_cols, double J,
+           double T, double mu, uint64_t seed, uint32_t chain, uint64_t pass_index, int colour) {
+          std::vector<int> o = to_vec(occ);
+          AcceptTable tab = make_accept_table(2, J, T, mu);
+          long long acc = checkerboard_half_sweep_slab(o, to_vec(halo_lo), to_vec(halo_hi), n0, col_begin,
+                                                       n_cols, tab, seed, chain, pass_index, colour);
+          return py::make_tuple(from_vec(o), acc);
+        });
   m.def("philox4x32_10", [](std::array<uint32_t, 4> c, std::array<uint32_t, 2> k) {
     return Philox4x32::generate(c, k, 10);
   });
