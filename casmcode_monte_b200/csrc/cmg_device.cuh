@@ -444,10 +444,12 @@ __device__ __forceinline__ void slab_wait_neighbours(const LatticeView &L) {
   }
   __syncthreads();
 }
-// after the last store: the last CTA of the launch raises the neighbours' flags
-__device__ __forceinline__ void slab_signal_neighbours(const LatticeView &L) {
+// after the last store: the last CTA of the launch raises the neighbours' flags.
+// `pushed`: this thread stored into a neighbour's halo (only those threads pay
+// for a system-scope fence; the CTA barrier + the counter chain order the rest).
+__device__ __forceinline__ void slab_signal_neighbours(const LatticeView &L, bool pushed) {
   if (!L.done_counter) return;
-  __threadfence_system();  // this thread's peer stores are visible system-wide
+  if (pushed) __threadfence_system();  // this thread's peer stores are visible system-wide
   __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
@@ -474,6 +476,7 @@ __global__ void __launch_bounds__(128) k_halfsweep_bulk2d(SweepArgs A) {
   const int n_strips = (n1 + A.js - 1) / A.js;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   Accum acc = {0u, 0u, 0u, 0u, 0u};
+  bool pushed = false;
 
   if (t < (long long)V * n_strips) {
     const int v = (int)(t % V);
@@ -520,8 +523,14 @@ __global__ void __launch_bounds__(128) k_halfsweep_bulk2d(SweepArgs A) {
       const uint4 cn = update16<SAMPLE>(ce, om, oc, op, side, group0, A.pass,
                                         A.colour, chain_word, A.rk, acc);
       *reinterpret_cast<uint4 *>(C + (long long)h * j + p0) = cn;
-      if (push_lo && j == 0) *reinterpret_cast<uint4 *>(push_lo + p0) = cn;
-      if (push_hi && j == n1 - 1) *reinterpret_cast<uint4 *>(push_hi + p0) = cn;
+      if (push_lo && j == 0) {
+        *reinterpret_cast<uint4 *>(push_lo + p0) = cn;
+        pushed = true;
+      }
+      if (push_hi && j == n1 - 1) {
+        *reinterpret_cast<uint4 *>(push_hi + p0) = cn;
+        pushed = true;
+      }
       om = oc;
       oc = op;
     }
@@ -530,7 +539,7 @@ __global__ void __launch_bounds__(128) k_halfsweep_bulk2d(SweepArgs A) {
   if (SAMPLE) accum_finish(acc, 4, ones, bsum);
   block_accumulate<128>(acc.acc, ones, bsum, SAMPLE, A.n_accept + chain,
                         SAMPLE ? A.sb + (long long)chain * A.sb_chain_stride : nullptr);
-  slab_signal_neighbours(L);
+  slab_signal_neighbours(L, pushed);
 }
 
 // ---------------------------------------------------------------------------
