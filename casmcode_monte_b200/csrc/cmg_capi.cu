@@ -852,7 +852,7 @@ static TilePlan plan_tiles(const cmg_context *c, long long passes_wanted) {
   TilePlan t;
   if (c->dim != 2 || c->slab || c->shape[0] % 64 != 0 || c->smem_optin < 64 * 1024) return t;
   const long long h = c->shape[0] / 2, n1 = c->shape[1];
-  const long long budget = (long long)c->smem_optin - 2048;  // static smem + slack
+  const long long budget = (long long)c->smem_optin - kSmemTile - 1024;  // tables + static smem
   if (2 * n1 * h <= budget) {  // whole lattice in one tile: periodic, no halo
     t.ok = true;
     t.n_tiles = 1;

@@ -113,20 +113,35 @@ __device__ __forceinline__ uint4 site_group_random(unsigned long long group,
   return philox4x32_10(c, rk);
 }
 
-// All sweep kernels use one dynamic shared-memory buffer.  Its first 64 bytes
-// hold the chain's acceptance table as ~thr_m1 (16 x u32); tile data follows at
-// kSmemTile.  Declaring it at namespace scope keeps every access a plain LDS
-// with a constant offset (no generic-address conversion).
+// All sweep kernels use one dynamic shared-memory buffer, declared at
+// namespace scope so that every access is a plain LDS (no generic-address
+// conversion):
+//   [0, 64)                 the chain's acceptance table as ~thr_m1, 16 x u32
+//   [kSmemPair, +14*2048)   pair table: entry (A, B) = {~thr[A], ~thr[B]} at byte
+//                           offset 8*A + 2048*B, so the 16-bit value formed by two
+//                           neighbouring index bytes (each holding 8*index) IS the
+//                           byte offset of the pair: one LDS.64 per two sites
+//   [kSmemTile, ...)        tile data (k_tile2d)
 extern __shared__ __align__(16) unsigned char cmg_smem[];
-constexpr int kSmemTile = 128;
+constexpr int kSmemPair = 2048;
+constexpr int kSmemTile = kSmemPair + 14 * 2048;
 
 __device__ __forceinline__ void load_accept_table(const ChainTables *tab) {
   if (threadIdx.x < 16)
     reinterpret_cast<uint32_t *>(cmg_smem)[threadIdx.x] = ~tab->thr_m1[threadIdx.x];
+  for (int e = threadIdx.x; e < 14 * 14; e += blockDim.x) {
+    const int A = e % 14, B = e / 14;
+    *reinterpret_cast<uint2 *>(cmg_smem + kSmemPair + 8 * A + 2048 * B) =
+        make_uint2(~tab->thr_m1[A], ~tab->thr_m1[B]);
+  }
 }
 // byte_off = 4 * table index
 __device__ __forceinline__ uint32_t nthr_at(uint32_t byte_off) {
   return *reinterpret_cast<const uint32_t *>(cmg_smem + byte_off);
+}
+// pair_off = 8*indexA + 2048*indexB
+__device__ __forceinline__ uint2 nthr_pair_at(uint32_t pair_off) {
+  return *reinterpret_cast<const uint2 *>(cmg_smem + kSmemPair + pair_off);
 }
 
 // Acceptance of 4 sites packed in a word.  Each site's uniform is the 32-bit
@@ -136,19 +151,18 @@ __device__ __forceinline__ uint32_t nthr_at(uint32_t byte_off) {
 //   Y <= thr - 65536      -> accepted whatever r16' is,
 //   otherwise (r16 equals the top half of thr, probability 2^-16) a tie that
 //   needs r16'.
-// idx4s: 4 * table index of each site in its byte; r01 / r23: the Philox words
+// idx4e: 8 * table index of each site in its byte; r01 / r23: the Philox words
 // holding the r16 of sites (0,1) / (2,3) in their (low, high) halves.
 // D = Y + ~thr carries out iff Y > thr (2 instructions per site through the
 // carry flag, no predicates), and D >= 0xFFFF0000 iff tie, tracked with one max
 // per site.  Returns 0x01 in the byte of every (provisionally) accepted site;
 // ties count as accepted here and are resolved by the caller when
 // dmax >= 0xFFFF0000.
-__device__ __forceinline__ uint32_t accept_mask4_fast(uint32_t idx4s, uint32_t r01,
+__device__ __forceinline__ uint32_t accept_mask4_fast(uint32_t idx4e, uint32_t r01,
                                                       uint32_t r23, uint32_t &dmax) {
-  const uint32_t t0 = nthr_at(idx4s & 0xffu);
-  const uint32_t t1 = nthr_at(__byte_perm(idx4s, 0u, 0x4441u));
-  const uint32_t t2 = nthr_at(__byte_perm(idx4s, 0u, 0x4442u));
-  const uint32_t t3 = nthr_at(idx4s >> 24);
+  const uint2 p01 = nthr_pair_at(idx4e & 0xffffu);
+  const uint2 p23 = nthr_pair_at(idx4e >> 16);
+  const uint32_t t0 = p01.x, t1 = p01.y, t2 = p23.x, t3 = p23.y;
   const uint32_t y0 = r01 << 16, y1 = r01 & 0xffff0000u;
   const uint32_t y2 = r23 << 16, y3 = r23 & 0xffff0000u;
   uint32_t rej, mx = dmax;
@@ -341,10 +355,10 @@ __device__ __forceinline__ uint4 shift_down_1(uint4 v, uint32_t hi) {
 // Rare path: some site of a 16-site vector tied on its leading 16 bits.  Redo
 // all 16 decisions exactly with both halves (regenerating the leading words so
 // the hot path does not have to keep them alive).
-__device__ __noinline__ uint4 resolve_ties16(uint4 idx4s, unsigned long long group0,
+__device__ __noinline__ uint4 resolve_ties16(uint4 idx4e, unsigned long long group0,
                                              unsigned long long pass, int colour,
                                              uint32_t chain_word, const uint32_t *rk) {
-  const uint32_t iw[4] = {idx4s.x, idx4s.y, idx4s.z, idx4s.w};
+  const uint32_t iw[4] = {idx4e.x, idx4e.y, idx4e.z, idx4e.w};
   uint32_t m[4];
   for (int half = 0; half < 2; ++half) {
     const uint4 r = site_group_random(group0 + half, chain_word, pass, colour, 0, rk);
@@ -356,7 +370,7 @@ __device__ __noinline__ uint4 resolve_ties16(uint4 idx4s, unsigned long long gro
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int lane = 4 * ww + k;
-        const uint32_t thr = ~nthr_at((iw[w] >> (8 * k)) & 0xffu);
+        const uint32_t thr = ~nthr_at(((iw[w] >> (8 * k)) & 0xffu) >> 1);
         mm |= accept_exact(lane16(r, lane), lane16(q, lane), thr) ? (1u << (8 * k)) : 0u;
       }
       m[w] = mm;
@@ -399,7 +413,7 @@ __device__ __forceinline__ uint4 update16(uint4 ce, uint4 om, uint4 oc, uint4 op
   uint32_t idx[4], m[4], dmax = 0;
 #pragma unroll
   for (int w = 0; w < 4; ++w) {
-    idx[w] = (nw[w] + nw[w] + cw[w]) << 2;  // 4 * (2*n_up + b) per byte, <= 52
+    idx[w] = (nw[w] + nw[w] + cw[w]) << 3;  // 8 * (2*n_up + b) per byte, <= 104
     m[w] = accept_mask4_fast(idx[w], rw[2 * w], rw[2 * w + 1], dmax);
   }
   if (dmax >= 0xffff0000u) {  // a tie somewhere in these 16 sites (probability 16 * 2^-16)
@@ -663,11 +677,8 @@ __global__ void __launch_bounds__(NT, 1) k_tile2d(TileArgs A) {
     int gc_lo = c0 - H + lo;
     gc_lo += (gc_lo < 0) ? n1 : 0;
     Accum acc = {0u, 0u, 0u, 0u, 0u};
-    const int items = (hi - lo) * V;
-    for (int it = threadIdx.x; it < items; it += NT) {
-      const int dc = (int)__umulhi((uint32_t)it, A.v_magic);
-      const int p0 = (it - dc * V) << 4;
-      const int cl = lo + dc;
+    // one 16-site vector of column cl (local), vector offset p0 (bytes)
+    auto process = [&](int cl, int dc, int p0) {
       int cm = cl - 1, cp = cl + 1;
       if (periodic) {
         cm = (cm < 0) ? W - 1 : cm;
@@ -699,6 +710,18 @@ __global__ void __launch_bounds__(NT, 1) k_tile2d(TileArgs A) {
         if (owned) acc.acc += scratch.acc;
       }
       sts16(cbase + col_off + p0, cn);
+    };
+    if (NT % V == 0) {
+      // each thread keeps its vector offset and strides over columns
+      const int p0 = (threadIdx.x % V) << 4;
+      const int cstep = NT / V;
+      for (int dc = threadIdx.x / V; dc < hi - lo; dc += cstep) process(lo + dc, dc, p0);
+    } else {
+      const int items = (hi - lo) * V;
+      for (int it = threadIdx.x; it < items; it += NT) {
+        const int dc = (int)__umulhi((uint32_t)it, A.v_magic);
+        process(lo + dc, dc, (it - dc * V) << 4);
+      }
     }
     n_acc += acc.acc;
     __syncthreads();
