@@ -933,25 +933,25 @@ static int launch_half_sweep(cmg_context *c, int variant, int colour, unsigned l
   if (variant == V_GENERIC) {
     dim3 grid(nblocks((plane_size + 7) / 8, 128), c->n_chains);
     if (sample)
-      k_halfsweep_generic<true><<<grid, block, kSmemTile, c->stream>>>(A);
+      k_halfsweep_generic<true><<<grid, block, kSmemSmall, c->stream>>>(A);
     else
-      k_halfsweep_generic<false><<<grid, block, kSmemTile, c->stream>>>(A);
+      k_halfsweep_generic<false><<<grid, block, kSmemSmall, c->stream>>>(A);
   } else if (variant == V_BULK2D) {
     const long long V = c->shape[0] / 32;
     const long long strips = (c->shape[1] + A.js - 1) / A.js;
     dim3 grid(nblocks(V * strips, 128), c->n_chains);
     if (sample)
-      k_halfsweep_bulk2d<true><<<grid, block, kSmemTile, c->stream>>>(A);
+      k_halfsweep_bulk2d<true><<<grid, block, kSmemSmall, c->stream>>>(A);
     else
-      k_halfsweep_bulk2d<false><<<grid, block, kSmemTile, c->stream>>>(A);
+      k_halfsweep_bulk2d<false><<<grid, block, kSmemSmall, c->stream>>>(A);
   } else if (variant == V_BULK3D) {
     const long long V = c->shape[0] / 32;
     const long long strips = (c->shape[1] + A.js - 1) / A.js;
     dim3 grid(nblocks(V * strips * c->shape[2], 128), c->n_chains);
     if (sample)
-      k_halfsweep_bulk3d<true><<<grid, block, kSmemTile, c->stream>>>(A);
+      k_halfsweep_bulk3d<true><<<grid, block, kSmemSmall, c->stream>>>(A);
     else
-      k_halfsweep_bulk3d<false><<<grid, block, kSmemTile, c->stream>>>(A);
+      k_halfsweep_bulk3d<false><<<grid, block, kSmemSmall, c->stream>>>(A);
   } else {
     return fail(c, CMG_EUNSUPPORTED, "kernel variant not available");
   }
@@ -994,6 +994,10 @@ static int launch_tile_passes_sp(cmg_context *c, const TilePlan &tp, int n_passe
     LAUNCH_TILE(1024)
   } else if (c->tile_threads == 256) {
     LAUNCH_TILE(256)
+  } else if (c->tile_threads == 640) {
+    LAUNCH_TILE(640)
+  } else if (c->tile_threads == 768) {
+    LAUNCH_TILE(768)
   } else {
     LAUNCH_TILE(512)
   }
@@ -1719,8 +1723,9 @@ int cmg_set_kernel_variant(cmg_context *c, const char *name) {
   p = s.find(":nt=");
   if (p != std::string::npos) {
     c->tile_threads = atoi(s.c_str() + p + 4);
-    if (c->tile_threads != 256 && c->tile_threads != 512 && c->tile_threads != 1024)
-      return fail(c, CMG_EINVAL, "nt must be 256, 512 or 1024");
+    if (c->tile_threads != 256 && c->tile_threads != 512 && c->tile_threads != 640 &&
+        c->tile_threads != 768 && c->tile_threads != 1024)
+      return fail(c, CMG_EINVAL, "nt must be 256, 512, 640, 768 or 1024");
   }
   p = s.find(':');
   if (p != std::string::npos) s = s.substr(0, p);

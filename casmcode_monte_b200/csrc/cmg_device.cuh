@@ -126,9 +126,12 @@ extern __shared__ __align__(16) unsigned char cmg_smem[];
 constexpr int kSmemPair = 2048;
 constexpr int kSmemTile = kSmemPair + 14 * 2048;
 
-__device__ __forceinline__ void load_accept_table(const ChainTables *tab) {
+constexpr int kSmemSmall = 128;  // kernels that only use the 16-entry table
+
+__device__ __forceinline__ void load_accept_table(const ChainTables *tab, bool with_pairs) {
   if (threadIdx.x < 16)
     reinterpret_cast<uint32_t *>(cmg_smem)[threadIdx.x] = ~tab->thr_m1[threadIdx.x];
+  if (!with_pairs) return;
   for (int e = threadIdx.x; e < 14 * 14; e += blockDim.x) {
     const int A = e % 14, B = e / 14;
     *reinterpret_cast<uint2 *>(cmg_smem + kSmemPair + 8 * A + 2048 * B) =
@@ -158,11 +161,22 @@ __device__ __forceinline__ uint2 nthr_pair_at(uint32_t pair_off) {
 // per site.  Returns 0x01 in the byte of every (provisionally) accepted site;
 // ties count as accepted here and are resolved by the caller when
 // dmax >= 0xFFFF0000.
+// PAIR: index bytes hold 8*index and thresholds come two at a time from the pair
+// table; otherwise they hold 4*index and come from the 16-entry table.
+template <bool PAIR>
 __device__ __forceinline__ uint32_t accept_mask4_fast(uint32_t idx4e, uint32_t r01,
                                                       uint32_t r23, uint32_t &dmax) {
-  const uint2 p01 = nthr_pair_at(idx4e & 0xffffu);
-  const uint2 p23 = nthr_pair_at(idx4e >> 16);
-  const uint32_t t0 = p01.x, t1 = p01.y, t2 = p23.x, t3 = p23.y;
+  uint32_t t0, t1, t2, t3;
+  if (PAIR) {
+    const uint2 p01 = nthr_pair_at(idx4e & 0xffffu);
+    const uint2 p23 = nthr_pair_at(idx4e >> 16);
+    t0 = p01.x, t1 = p01.y, t2 = p23.x, t3 = p23.y;
+  } else {
+    t0 = nthr_at(idx4e & 0xffu);
+    t1 = nthr_at(__byte_perm(idx4e, 0u, 0x4441u));
+    t2 = nthr_at(__byte_perm(idx4e, 0u, 0x4442u));
+    t3 = nthr_at(idx4e >> 24);
+  }
   const uint32_t y0 = r01 << 16, y1 = r01 & 0xffff0000u;
   const uint32_t y2 = r23 << 16, y3 = r23 & 0xffff0000u;
   uint32_t rej, mx = dmax;
@@ -258,7 +272,7 @@ template <bool SAMPLE>
 __global__ void __launch_bounds__(128) k_halfsweep_generic(SweepArgs A) {
   const LatticeView &L = A.L;
   const int chain = blockIdx.y;
-  load_accept_table(A.tabs + chain);
+  load_accept_table(A.tabs + chain, false);
   __syncthreads();
 
   uint8_t *C = L.planes + (long long)chain * L.chain_stride +
@@ -355,7 +369,7 @@ __device__ __forceinline__ uint4 shift_down_1(uint4 v, uint32_t hi) {
 // Rare path: some site of a 16-site vector tied on its leading 16 bits.  Redo
 // all 16 decisions exactly with both halves (regenerating the leading words so
 // the hot path does not have to keep them alive).
-__device__ __noinline__ uint4 resolve_ties16(uint4 idx4e, unsigned long long group0,
+__device__ __noinline__ uint4 resolve_ties16(uint4 idx4e, int idx_shift, unsigned long long group0,
                                              unsigned long long pass, int colour,
                                              uint32_t chain_word, const uint32_t *rk) {
   const uint32_t iw[4] = {idx4e.x, idx4e.y, idx4e.z, idx4e.w};
@@ -370,7 +384,7 @@ __device__ __noinline__ uint4 resolve_ties16(uint4 idx4e, unsigned long long gro
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int lane = 4 * ww + k;
-        const uint32_t thr = ~nthr_at(((iw[w] >> (8 * k)) & 0xffu) >> 1);
+        const uint32_t thr = ~nthr_at(((iw[w] >> (8 * k)) & 0xffu) >> idx_shift);
         mm |= accept_exact(lane16(r, lane), lane16(q, lane), thr) ? (1u << (8 * k)) : 0u;
       }
       m[w] = mm;
@@ -397,7 +411,7 @@ __device__ __forceinline__ void accum_finish(const Accum &a, int z, long long &o
 
 // Update 16 sites (one 16-byte vector of a colour plane); returns the new
 // centre vector.  group0 = plane index of the first site >> 3.
-template <bool SAMPLE>
+template <bool SAMPLE, bool PAIR = false>
 __device__ __forceinline__ uint4 update16(uint4 ce, uint4 om, uint4 oc, uint4 op,
                                           uint4 side, unsigned long long group0,
                                           unsigned long long pass, int colour,
@@ -413,12 +427,12 @@ __device__ __forceinline__ uint4 update16(uint4 ce, uint4 om, uint4 oc, uint4 op
   uint32_t idx[4], m[4], dmax = 0;
 #pragma unroll
   for (int w = 0; w < 4; ++w) {
-    idx[w] = (nw[w] + nw[w] + cw[w]) << 3;  // 8 * (2*n_up + b) per byte, <= 104
-    m[w] = accept_mask4_fast(idx[w], rw[2 * w], rw[2 * w + 1], dmax);
+    idx[w] = (nw[w] + nw[w] + cw[w]) << (PAIR ? 3 : 2);  // 8 (or 4) * (2*n_up + b) per byte
+    m[w] = accept_mask4_fast<PAIR>(idx[w], rw[2 * w], rw[2 * w + 1], dmax);
   }
   if (dmax >= 0xffff0000u) {  // a tie somewhere in these 16 sites (probability 16 * 2^-16)
-    const uint4 mm = resolve_ties16(make_uint4(idx[0], idx[1], idx[2], idx[3]), group0, pass,
-                                    colour, chain_word, rk);
+    const uint4 mm = resolve_ties16(make_uint4(idx[0], idx[1], idx[2], idx[3]), PAIR ? 1 : 0,
+                                    group0, pass, colour, chain_word, rk);
     m[0] = mm.x;
     m[1] = mm.y;
     m[2] = mm.z;
@@ -481,7 +495,7 @@ template <bool SAMPLE>
 __global__ void __launch_bounds__(128) k_halfsweep_bulk2d(SweepArgs A) {
   const LatticeView &L = A.L;
   const int chain = blockIdx.y;
-  load_accept_table(A.tabs + chain);
+  load_accept_table(A.tabs + chain, false);
   __syncthreads();
   slab_wait_neighbours(L);
 
@@ -625,13 +639,16 @@ __device__ __forceinline__ void sts16(uint32_t off, uint4 v) {
   *reinterpret_cast<uint4 *>(cmg_smem + off) = v;
 }
 
+constexpr int kTileMaxPasses = 64;
+
 template <int NT>
 __global__ void __launch_bounds__(NT, 1) k_tile2d(TileArgs A) {
-  __shared__ long long s_red[2 * NT / 32];
+  __shared__ long long s_acc[2 * kTileMaxPasses];  // per-pass {ones, B} of this CTA
+  for (int i = threadIdx.x; i < 2 * kTileMaxPasses; i += NT) s_acc[i] = 0;
   const LatticeView &L = A.L;
   const int chain = blockIdx.y;
   const int tile = blockIdx.x;
-  load_accept_table(A.tabs + chain);
+  load_accept_table(A.tabs + chain, true);
 
   const int h = L.h, n1 = L.n1;
   const int V = h >> 4;
@@ -702,11 +719,11 @@ __global__ void __launch_bounds__(NT, 1) k_tile2d(TileArgs A) {
       const bool owned = periodic || (cl >= H && cl < H + TW);
       uint4 cn;
       if (sample && owned) {
-        cn = update16<true>(ce, om, oc, op, side, group0, pass, colour, chain_word, A.rk, acc);
+        cn = update16<true, true>(ce, om, oc, op, side, group0, pass, colour, chain_word, A.rk, acc);
       } else {
         Accum scratch = {0u, 0u, 0u, 0u, 0u};
-        cn = update16<false>(ce, om, oc, op, side, group0, pass, colour, chain_word, A.rk,
-                             scratch);
+        cn = update16<false, true>(ce, om, oc, op, side, group0, pass, colour, chain_word, A.rk,
+                                   scratch);
         if (owned) acc.acc += scratch.acc;
       }
       sts16(cbase + col_off + p0, cn);
@@ -724,16 +741,29 @@ __global__ void __launch_bounds__(NT, 1) k_tile2d(TileArgs A) {
       }
     }
     n_acc += acc.acc;
-    __syncthreads();
     if (sample) {
+      // warp partial sums -> per-pass shared accumulators (flushed once at the end)
       long long ones, bsum;
       accum_finish(acc, 4, ones, bsum);
-      block_add2<NT>(ones, bsum,
-                     A.sb + (long long)slot * A.sb_slot_stride +
-                         (long long)chain * A.sb_chain_stride,
-                     s_red);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        ones += __shfl_xor_sync(0xffffffffu, ones, o);
+        bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
+      }
+      if ((threadIdx.x & 31) == 0) {
+        atomicAdd(reinterpret_cast<unsigned long long *>(&s_acc[2 * slot]), (unsigned long long)ones);
+        atomicAdd(reinterpret_cast<unsigned long long *>(&s_acc[2 * slot + 1]), (unsigned long long)bsum);
+      }
       ++slot;
     }
+    __syncthreads();
+  }
+
+  // ---- flush the sampled sums of this launch (one global atomic per slot and quantity)
+  for (int i = threadIdx.x; i < 2 * slot; i += NT) {
+    long long *dst = A.sb + (long long)(i >> 1) * A.sb_slot_stride +
+                     (long long)chain * A.sb_chain_stride + (i & 1);
+    atomicAdd(reinterpret_cast<unsigned long long *>(dst), (unsigned long long)s_acc[i]);
   }
 
   // ---- write the owned columns back
@@ -759,7 +789,7 @@ template <bool SAMPLE>
 __global__ void __launch_bounds__(128) k_halfsweep_bulk3d(SweepArgs A) {
   const LatticeView &L = A.L;
   const int chain = blockIdx.y;
-  load_accept_table(A.tabs + chain);
+  load_accept_table(A.tabs + chain, false);
   __syncthreads();
 
   const int h = L.h, n1 = L.n1, n2 = L.n2;

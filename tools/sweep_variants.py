@@ -25,12 +25,11 @@ def main():
     stream = torch.cuda.Stream()
     out = []
     cases = [
-        ("2d", [4096, 4096], 1, [f"bulk2d:js={j}" for j in (2, 4, 8)] + [f"tile2d:p={p}:nt={nt}" for p in (1, 2, 3, 4) for nt in (512, 1024)] + ["tile2d:p=2:nt=256"], 120),
-        ("2d_sweep8", [4096, 4096], 8, ["bulk2d:js=8", "bulk2d:js=16", "tile2d:p=2:nt=512", "tile2d:p=3:nt=512"], 48),
-        ("2d_grid", [256, 256], 128, ["bulk2d:js=2", "tile2d:nt=256", "tile2d:nt=512", "tile2d:nt=1024"], 128),
-        ("2d_8k", [8192, 8192], 1, ["bulk2d:js=8", "bulk2d:js=16", "tile2d:p=1:nt=512", "tile2d:p=2:nt=512"], 48),
-        ("2d_big", [16384, 16384], 1, [f"bulk2d:js={j}" for j in (8, 16)], 20),
-        ("3d", [512, 512, 512], 1, [f"bulk3d:js={j}" for j in (4, 8)], 10),
+        ("2d", [4096, 4096], 1, ["bulk2d:js=8"] + [f"tile2d:p={p}:nt={nt}" for p in (3, 4) for nt in (512, 640, 768)], 120),
+        ("2d_sweep8", [4096, 4096], 8, ["bulk2d:js=16", "tile2d:p=3:nt=512", "tile2d:p=3:nt=640"], 48),
+        ("2d_grid", [256, 256], 128, ["tile2d:nt=256", "tile2d:nt=512", "tile2d:nt=640", "tile2d:nt=768"], 128),
+        ("2d_big", [16384, 16384], 1, ["bulk2d:js=16"], 20),
+        ("3d", [512, 512, 512], 1, ["bulk3d:js=8"], 10),
     ]
     for name, shape, chains, variants, n_passes in cases:
         lat = IsingLatticeGPU(shape, n_chains=chains, J=0.1)
