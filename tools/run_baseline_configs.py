@@ -1,0 +1,165 @@
+"""Runs the single-GPU BASELINE.json configs through the C ABI and writes one
+JSON record per config (throughput + physics checks) to stdout.
+
+  python tools/run_baseline_configs.py config2   # 4096^2 temperature sweep vs Onsager
+  python tools/run_baseline_configs.py config3   # 512^3 run to precision, on-device statistics
+  python tools/run_baseline_configs.py config4   # 128 of the 1024 (T, mu) chains of 256^2 (one GPU's share)
+
+(config 1 is the CPU reference case: oracle/oracle_bench; config 5 needs several
+GPUs: tools/slab_multi_gpu.py under torchrun.)
+"""
+import json
+import math
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+import casmcode_monte_b200 as cm
+
+J = 0.1
+KB = cm.KB
+Z95 = 1.959964
+
+
+def onsager_energy_per_site(T):
+    """Exact internal energy per site of the infinite square lattice, E = -J sum_<ij> s_i s_j."""
+    from scipy.special import ellipk
+
+    K = J / (KB * T)
+    kappa = 2.0 * math.sinh(2 * K) / math.cosh(2 * K) ** 2
+    return -J / math.tanh(2 * K) * (1.0 + (2.0 / math.pi) * (2.0 * math.tanh(2 * K) ** 2 - 1.0) * ellipk(kappa**2))
+
+
+def onsager_x(T):
+    K = J / (KB * T)
+    s = math.sinh(2 * K)
+    if s <= 1.0:
+        return 0.5
+    return 0.5 * (1.0 + (1.0 - s**-4) ** 0.125)
+
+
+def timed(fn):
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    fn()
+    torch.cuda.synchronize()
+    return time.perf_counter() - t0
+
+
+def config2():
+    temps = [1800.0, 2200.0, 2500.0, 2600.0, 2633.0, 2660.0, 2800.0, 3200.0]
+    n0 = n1 = 4096
+    n_eq, n_meas = 1000, 4000
+    lat = cm.IsingLatticeGPU([n0, n1], n_chains=len(temps), J=J)
+    tc = 2 * J / (KB * math.log(1 + math.sqrt(2)))
+    for ch, T in enumerate(temps):
+        lat.set_conditions(T, 0.0, chain=ch)
+        if T < tc:
+            lat.fill(1, chain=ch)  # ordered phase: start inside one magnetisation sector
+        else:
+            lat.randomize(12345 + ch, 0.5, chain=ch)
+    lat.seed_philox(0xC0FFEE)
+    lat.run_passes(n_eq, cm.MODE_CHECKERBOARD, 0)
+    lat.sync()
+    dt = timed(lambda: (lat.run_passes(n_meas, cm.MODE_CHECKERBOARD, 1), lat.sync()))
+    rows = []
+    for ch, T in enumerate(temps):
+        st_e = lat.series_stats(cm.Q_FORMATION_ENERGY, ch)
+        st_x = lat.series_stats(cm.Q_PARAM_COMPOSITION, ch)
+        e = lat.samples(cm.Q_POTENTIAL_ENERGY, ch)
+        x = lat.samples(cm.Q_PARAM_COMPOSITION, ch)
+        n = n0 * n1
+        row = {
+            "T": T,
+            "e_formation": st_e["mean"], "e_precision": st_e["calculated_precision"], "e_onsager": onsager_energy_per_site(T),
+            "x": st_x["mean"], "x_precision": st_x["calculated_precision"], "x_onsager": onsager_x(T),
+            "heat_capacity_per_site_kB": n * float(np.var(e)) / (KB * T * T) / KB,
+            "susceptibility_per_site": n * float(np.var(x)) / (KB * T),
+            "acceptance": lat.counters(ch)[1] / (lat.counters(ch)[1] + lat.counters(ch)[2]),
+        }
+        # 3-sigma check against the exact infinite-lattice values away from T_c
+        # (|T - T_c| > 150 K: finite-size and critical-slowing effects are negligible there)
+        if abs(T - tc) > 150:
+            row["e_within_3sigma"] = bool(abs(row["e_formation"] - row["e_onsager"]) < 3 * row["e_precision"] / Z95 + 2e-7)
+            row["x_within_3sigma"] = bool(abs(row["x"] - row["x_onsager"]) < 3 * row["x_precision"] / Z95 + 2e-6)
+        rows.append(row)
+    return {
+        "config": "2: 2D 4096x4096 SGC temperature sweep through T_c, 8 temperatures as 8 concurrent lattices, 1000 + 4000 passes, sample every pass",
+        "kernel": lat.kernel_variant,
+        "attempts_per_s": len(temps) * n0 * n1 * n_meas / dt,
+        "seconds_measured": dt,
+        "T_c": tc,
+        "rows": rows,
+    }
+
+
+def config3():
+    shape = [512, 512, 512]
+    n = 512**3
+    out = []
+    for T, mu in [(4000.0, 0.0), (6500.0, 0.05)]:
+        lat = cm.IsingLatticeGPU(shape, J=J)
+        lat.set_conditions(T, mu)
+        lat.seed_philox(0xC0FFEE)
+        lat.fill(1)
+        target = 1e-4
+        check_begin, check_period, max_count = 100, 100, 20000
+        t0 = time.perf_counter()
+        n_pass = 0
+        done = False
+        res = None
+        while not done and n_pass < max_count:
+            lat.run_passes(check_begin if n_pass == 0 else check_period, cm.MODE_CHECKERBOARD, 1)
+            n_pass = lat.counters()[0]
+            # on-device equilibration + convergence statistics (no series leaves the GPU)
+            eq = [lat.series_equilibration(q, target) for q in (cm.Q_POTENTIAL_ENERGY, cm.Q_PARAM_COMPOSITION)]
+            if all(e[0] for e in eq):
+                n_eq = max(e[1] for e in eq)
+                st = [lat.series_stats(q, first=n_eq) for q in (cm.Q_POTENTIAL_ENERGY, cm.Q_PARAM_COMPOSITION)]
+                res = {"n_equil": n_eq, "potential_energy": st[0], "param_composition": st[1]}
+                done = all(s["calculated_precision"] < target for s in st)
+        lat.sync()
+        dt = time.perf_counter() - t0
+        out.append({"T": T, "mu": mu, "n_pass": n_pass, "converged": bool(done), "seconds": dt, "attempts_per_s": n * n_pass / dt, "kernel": lat.kernel_variant, "results": res})
+        lat.close()
+    return {"config": "3: 3D simple-cubic 512^3 SGC run to abs precision 1e-4 on potential_energy and param_composition with on-device sampling, equilibration and convergence statistics", "runs": out}
+
+
+def config4():
+    from casmcode_monte_b200.parallel import shard_chains
+
+    temps = np.linspace(1500.0, 4000.0, 32)
+    mus = np.linspace(-0.2, 0.2, 32)
+    conds = [(float(T), float(mu)) for T in temps for mu in mus]
+    mine = shard_chains(len(conds), 8, 0)  # rank 0 of 8: 128 chains
+    shape = [256, 256]
+    lat = cm.IsingLatticeGPU(shape, n_chains=len(mine), J=J)
+    for local, g in enumerate(mine):
+        lat.set_conditions(*conds[g], chain=local)
+    lat.seed_philox(0xC0FFEE)
+    lat.set_chain_offset(mine[0])
+    n_eq, n_meas = 2000, 8000
+    lat.run_passes(n_eq, cm.MODE_CHECKERBOARD, 0)
+    lat.sync()
+    dt = timed(lambda: (lat.run_passes(n_meas, cm.MODE_CHECKERBOARD, 1), lat.sync()))
+    t_stats = timed(lambda: lat.series_stats_all(cm.Q_POTENTIAL_ENERGY))
+    m, p, v, k = lat.series_stats_all(cm.Q_POTENTIAL_ENERGY)
+    mx, px, vx, kx = lat.series_stats_all(cm.Q_PARAM_COMPOSITION)
+    return {
+        "config": "4: 1024-point (T, mu) grid of independent 256x256 SGC chains; this is one GPU's share (128 chains), 2000 + 8000 passes, sample every pass, per-chain statistics on the device",
+        "kernel": lat.kernel_variant,
+        "n_chains": len(mine),
+        "attempts_per_s": len(mine) * 256 * 256 * n_meas / dt,
+        "seconds_measured": dt,
+        "seconds_device_statistics_all_chains": t_stats,
+        "sample": [{"T": conds[g][0], "mu": conds[g][1], "e_pot": float(m[i]), "e_pot_precision": float(p[i]), "x": float(mx[i]), "k_star": int(k[i])} for i, g in list(enumerate(mine))[:: max(1, len(mine) // 8)]],
+    }
+
+
+if __name__ == "__main__":
+    which = sys.argv[1] if len(sys.argv) > 1 else "config2"
+    print(json.dumps({"config2": config2, "config3": config3, "config4": config4}[which]()), flush=True)
