@@ -342,7 +342,11 @@ def ours(args):
             "peak_source": peak_src,
             "unit": "GB/s",
             "frac": achieved / peak,
-            "traffic": None,
+            # dram__bytes_read.sum + dram__bytes_write.sum of one k_halfsweep_bulk2d launch of this
+            # workload from the ncu --set full capture in profiles/ncu_bulk2d_sweep8_r1c.txt
+            # (134.59 MB + 68.72 MB); the 128 MiB of planes do not fit the L2, so every
+            # half-sweep streams from HBM and traffic ~= algorithmic bytes (201.3 MB)
+            "traffic": 203.3e6 if lat.kernel_variant == "bulk2d" else None,
             "kernel": ("k_halfsweep_" if lat.kernel_variant.startswith("bulk") else "k_") + lat.kernel_variant,
             "algorithmic_bytes_per_launch": bytes_per_launch,
             "avg_launch_us": avg_launch_s * 1e6,

@@ -529,23 +529,33 @@ __global__ void __launch_bounds__(128) k_halfsweep_bulk2d(SweepArgs A) {
       return O + (long long)h * j;
     };
 
-    uint4 om = ld16_nc(ocol(jbeg - 1) + p0);
-    uint4 oc = ld16_nc(ocol(jbeg) + p0);
     const int p_below = (p0 == 0) ? h - 1 : p0 - 1;
     const int p_above = (p0 + 16 == h) ? 0 : p0 + 16;
+    // the byte across the vector edge for column j: p-1 if i = 2p (parity 0), else p+1
+    auto edge_byte = [&](int j) -> uint32_t {
+      const int par = (int)(((long long)j + L.col_offset + A.colour) & 1);
+      return __ldg(O + (long long)h * j + (par ? p_above : p_below));
+    };
+
+    // software pipeline: the loads of column j+1 are in flight while column j is
+    // computed (the ~300 instructions per column hide an L2/HBM round trip)
+    uint4 om = ld16_nc(ocol(jbeg - 1) + p0);
+    uint4 oc = ld16_nc(ocol(jbeg) + p0);
+    uint4 op = ld16_nc(ocol(jbeg + 1) + p0);
+    uint4 ce = ld16(C + (long long)h * jbeg + p0);
+    uint32_t eb = edge_byte(jbeg);
 
     for (int j = jbeg; j < jend; ++j) {
-      const uint4 op = ld16_nc(ocol(j + 1) + p0);
-      const uint4 ce = ld16(C + (long long)h * j + p0);
+      uint4 op_n = op, ce_n = ce;
+      uint32_t eb_n = eb;
+      if (j + 1 < jend) {
+        op_n = ld16_nc(ocol(j + 2) + p0);
+        ce_n = ld16(C + (long long)h * (j + 1) + p0);
+        eb_n = edge_byte(j + 1);
+      }
       const long long jg = (long long)j + L.col_offset;
       const int par = (int)((jg + A.colour) & 1);  // i = 2p + par
-      const uint8_t *ocj = O + (long long)h * j;
-      uint4 side;
-      if (par == 0) {
-        side = shift_up_1(oc, __ldg(ocj + p_below));  // neighbour i-1 -> p-1
-      } else {
-        side = shift_down_1(oc, __ldg(ocj + p_above));  // neighbour i+1 -> p+1
-      }
+      const uint4 side = (par == 0) ? shift_up_1(oc, eb) : shift_down_1(oc, eb);
       const unsigned long long group0 =
           (unsigned long long)(((long long)h * jg + p0) >> 3);
       const uint4 cn = update16<SAMPLE>(ce, om, oc, op, side, group0, A.pass,
@@ -561,6 +571,9 @@ __global__ void __launch_bounds__(128) k_halfsweep_bulk2d(SweepArgs A) {
       }
       om = oc;
       oc = op;
+      op = op_n;
+      ce = ce_n;
+      eb = eb_n;
     }
   }
   long long ones = 0, bsum = 0;

@@ -25,10 +25,10 @@ def main():
     stream = torch.cuda.Stream()
     out = []
     cases = [
-        ("2d", [4096, 4096], 1, ["bulk2d:js=8"] + [f"tile2d:p={p}:nt={nt}" for p in (3, 4) for nt in (512, 640, 768)], 120),
-        ("2d_sweep8", [4096, 4096], 8, ["bulk2d:js=16", "tile2d:p=3:nt=512", "tile2d:p=3:nt=640"], 48),
-        ("2d_grid", [256, 256], 128, ["tile2d:nt=256", "tile2d:nt=512", "tile2d:nt=640", "tile2d:nt=768"], 128),
-        ("2d_big", [16384, 16384], 1, ["bulk2d:js=16"], 20),
+        ("2d", [4096, 4096], 1, ["bulk2d:js=8", "bulk2d:js=16", "tile2d:p=3:nt=512"], 120),
+        ("2d_sweep8", [4096, 4096], 8, ["bulk2d:js=8", "bulk2d:js=16", "bulk2d:js=32", "tile2d:p=3:nt=512"], 48),
+        ("2d_grid", [256, 256], 128, ["tile2d:nt=512"], 128),
+        ("2d_big", [16384, 16384], 1, ["bulk2d:js=16", "bulk2d:js=32"], 20),
         ("3d", [512, 512, 512], 1, ["bulk3d:js=8"], 10),
     ]
     for name, shape, chains, variants, n_passes in cases:
