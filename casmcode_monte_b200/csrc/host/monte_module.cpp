@@ -759,6 +759,44 @@ PYBIND11_MODULE(_monte_b200, m) {
     return metropolis_acceptance(dE, beta, rng);
   }, py::arg("delta_potential_energy"), py::arg("beta"), py::arg("random_number_generator"));
 
+  // python/src/monte_methods.cpp:196-263: the generic loop with Python callbacks
+  m.def("basic_occupation_metropolis",
+        [](std::shared_ptr<SemiGrandCanonicalData> data, double temperature, py::object dpotential_f,
+           py::object propose_event_f, py::object apply_event_f, int sample_period,
+           std::optional<MethodLog> method_log, std::optional<PyEngine> random_engine,
+           py::object write_status_f) {
+          auto holder = std::make_shared<OccEvent>();
+          std::function<double(OccEvent const &)> dpot = [dpotential_f](OccEvent const &e) {
+            return dpotential_f(py::cast(&e, py::return_value_policy::reference)).cast<double>();
+          };
+          std::function<OccEvent const &(RandomNumberGenerator<> &)> propose =
+              [propose_event_f, holder](RandomNumberGenerator<> &rng) -> OccEvent const & {
+            *holder = propose_event_f(py::cast(&rng, py::return_value_policy::reference)).cast<OccEvent>();
+            return *holder;
+          };
+          std::function<void(OccEvent const &)> apply = [apply_event_f](OccEvent const &e) {
+            apply_event_f(py::cast(&e, py::return_value_policy::reference));
+          };
+          std::function<void(BasicOccupationMetropolisData const &, MethodLog &)> wsf;
+          if (write_status_f.is_none()) {
+            wsf = [](BasicOccupationMetropolisData const &d, MethodLog &log) {
+              default_write_run_status(d, log, std::cout);
+              default_finish_write_status(d, log);
+            };
+          } else {
+            wsf = [write_status_f, data](BasicOccupationMetropolisData const &, MethodLog &log) {
+              write_status_f(data, py::cast(&log, py::return_value_policy::reference));
+            };
+          }
+          basic_occupation_metropolis<default_engine_type>(
+              *data, temperature, dpot, propose, apply, sample_period, method_log,
+              random_engine.has_value() ? random_engine->e : nullptr, wsf);
+        },
+        py::arg("data"), py::arg("temperature"), py::arg("potential_occ_delta_per_supercell_f"),
+        py::arg("propose_event_f"), py::arg("apply_event_f"), py::arg("sample_period") = 1,
+        py::arg("method_log") = py::none(), py::arg("random_engine") = py::none(),
+        py::arg("write_status_f") = py::none());
+
   // ------------------------------------------------- ising_cpp.semigrand_canonical
   py::class_<SemiGrandCanonicalConditions, std::shared_ptr<SemiGrandCanonicalConditions>>(
       m, "SemiGrandCanonicalConditions")

@@ -1075,6 +1075,111 @@ struct BasicOccupationMetropolisData {
   }
 };
 
+// ---------------------------------------------------------------------------
+// JSON text of the results, same keys as
+// include/casm/monte/checks/io/json/CompletionCheck_json_io.hh:421-438,
+// src/casm/monte/checks/io/json/EquilibrationCheck_json_io.cc:15-47 and
+// include/casm/monte/checks/io/json/ConvergenceCheck_json_io.hh:35-62
+// (what default_finish_write_status writes to status.json)
+// ---------------------------------------------------------------------------
+inline std::string json_number(double v) {
+  if (!std::isfinite(v)) return "null";
+  std::ostringstream ss;
+  ss.precision(17);
+  ss << v;
+  return ss.str();
+}
+inline std::string json_string(std::string const &s) {
+  std::string out = "\"";
+  for (char c : s) {
+    if (c == '"' || c == '\\') out += '\\';
+    out += c;
+  }
+  return out + "\"";
+}
+inline std::string to_json_text(RequestedPrecision const &r) {
+  std::string s = "{";
+  bool first = true;
+  if (r.abs_convergence_is_required) {
+    s += "\"abs_precision\": " + json_number(r.abs_precision);
+    first = false;
+  }
+  if (r.rel_convergence_is_required) s += std::string(first ? "" : ", ") + "\"rel_precision\": " + json_number(r.rel_precision);
+  return s + "}";
+}
+inline std::string to_json_text(EquilibrationCheckResults const &v) {
+  std::ostringstream s;
+  s << "{\"all_equilibrated\": " << (v.all_equilibrated ? "true" : "false") << ", ";
+  if (v.all_equilibrated)
+    s << "\"N_samples_for_all_to_equilibrate\": " << v.N_samples_for_all_to_equilibrate;
+  else
+    s << "\"N_samples_for_equilibration\": \"did_not_equilibrate\"";
+  s << ", \"individual_results\": [";
+  bool first = true;
+  for (auto const &p : v.individual_results) {
+    s << (first ? "" : ", ") << "{\"is_equilibrated\": " << (p.second.is_equilibrated ? "true" : "false")
+      << ", \"N_samples_for_equilibration\": ";
+    if (p.second.is_equilibrated) s << p.second.N_samples_for_equilibration;
+    else s << "\"did_not_equilibrate\"";
+    s << ", \"sampler_name\": " << json_string(p.first.sampler_name) << ", \"component_name\": "
+      << json_string(p.first.component_name) << ", \"component_index\": " << p.first.component_index << "}";
+    first = false;
+  }
+  s << "]}";
+  return s.str();
+}
+inline std::string to_json_text(ConvergenceCheckResults const &v) {
+  std::ostringstream s;
+  s << "{\"all_converged\": " << (v.all_converged ? "true" : "false")
+    << ", \"N_samples_for_statistics\": " << v.N_samples_for_statistics << ", \"individual_results\": [";
+  bool first = true;
+  for (auto const &p : v.individual_results) {
+    s << (first ? "" : ", ") << "{\"is_converged\": " << (p.second.is_converged ? "true" : "false")
+      << ", \"requested_precision\": " << to_json_text(p.second.requested_precision)
+      << ", \"stats\": {\"mean\": " << json_number(p.second.stats.mean) << ", \"calculated_precision\": "
+      << json_number(p.second.stats.calculated_precision) << "}, \"sampler_name\": "
+      << json_string(p.first.sampler_name) << ", \"component_name\": " << json_string(p.first.component_name)
+      << ", \"component_index\": " << p.first.component_index << "}";
+    first = false;
+  }
+  s << "]}";
+  return s.str();
+}
+inline std::string to_json_text(CompletionCheckResults const &v) {
+  std::ostringstream s;
+  s << "{\"has_all_minimums_met\": " << (v.has_all_minimums_met ? "true" : "false")
+    << ", \"has_any_maximum_met\": " << (v.has_any_maximum_met ? "true" : "false") << ", \"count\": ";
+  if (v.count.has_value()) s << *v.count; else s << "null";
+  s << ", \"time\": " << (v.time.has_value() ? json_number(*v.time) : std::string("null"))
+    << ", \"clocktime\": " << json_number(v.clocktime) << ", \"n_samples\": " << v.n_samples
+    << ", \"is_complete\": " << (v.is_complete ? "true" : "false");
+  if (v.n_samples_at_convergence_check.has_value())
+    s << ", \"n_samples_at_convergence_check\": " << *v.n_samples_at_convergence_check
+      << ", \"equilibration_check_results\": " << to_json_text(v.equilibration_check_results)
+      << ", \"convergence_check_results\": " << to_json_text(v.convergence_check_results);
+  s << "}";
+  return s.str();
+}
+/// basic_occupation_metropolis.hh:168-180
+inline std::string to_json_text(BasicOccupationMetropolisData const &d) {
+  std::ostringstream s;
+  s << "{\"completion_check_results\": " << to_json_text(d.completion_check.results())
+    << ", \"n_pass\": " << d.n_pass << ", \"n_steps_per_pass\": " << d.n_steps_per_pass
+    << ", \"n_accept\": " << static_cast<long>(d.n_accept) << ", \"n_reject\": " << static_cast<long>(d.n_reject)
+    << ", \"acceptance_rate\": " << json_number(d.acceptance_rate()) << ", \"rejection_rate\": "
+    << json_number(d.rejection_rate()) << "}";
+  return s.str();
+}
+/// basic_occupation_metropolis.hh:248-260: results JSON to the log file, lap restarted
+inline void default_finish_write_status(BasicOccupationMetropolisData const &data, MethodLog &method_log) {
+  method_log.reset();
+  if (method_log.fout) {
+    (*method_log.fout) << to_json_text(data.completion_check.results()) << std::endl;
+    method_log.fout->flush();
+  }
+  method_log.log.begin_lap();
+}
+
 /// basic_occupation_metropolis.hh:224-241
 inline void default_write_run_status(BasicOccupationMetropolisData const &data,
                                      MethodLog &method_log, std::ostream &sout) {
@@ -1408,8 +1513,62 @@ inline void default_write_status(SemiGrandCanonicalCalculator const &mc_calculat
   sout << "  AllEquilibrated=" << results.equilibration_check_results.all_equilibrated << std::endl;
   if (results.equilibration_check_results.all_equilibrated)
     sout << "  AllConverged=" << results.convergence_check_results.all_converged << std::endl;
-  method_log.reset();
-  method_log.log.begin_lap();
+  default_finish_write_status(*mc_calculator.data, method_log);
+}
+
+/// The generic driver with caller-supplied callbacks
+/// (methods/basic_occupation_metropolis.hh:354-425; Python form
+/// python/src/monte_methods.cpp:196-263).  It only sequences the callbacks --
+/// the arithmetic is in whatever they call (e.g. the device-backed calculators
+/// above).  SemiGrandCanonicalCalculator::run does NOT go through this; it
+/// drives the device loop directly.
+template <typename EngineType = default_engine_type>
+void basic_occupation_metropolis(
+    BasicOccupationMetropolisData &data, double temperature,
+    std::function<double(OccEvent const &)> potential_occ_delta_per_supercell_f,
+    std::function<OccEvent const &(RandomNumberGenerator<EngineType> &)> propose_event_f,
+    std::function<void(OccEvent const &)> apply_event_f, int sample_period = 1,
+    std::optional<MethodLog> method_log = std::nullopt,
+    std::shared_ptr<EngineType> random_engine = nullptr,
+    std::function<void(BasicOccupationMetropolisData const &, MethodLog &)> write_status_f = nullptr) {
+  double beta = 1.0 / (KB * temperature);
+  RandomNumberGenerator<EngineType> random_number_generator(random_engine);
+  if (!method_log.has_value()) {
+    method_log = MethodLog();
+    method_log->logfile_path = "status.json";
+    method_log->log_frequency = 600.0;
+  }
+  method_log->log.restart_clock();
+  method_log->log.begin_lap();
+  Index n_pass_next_sample = sample_period;
+  CountType n_step = 0;
+  while (!data.completion_check.is_complete(data.samplers, data.sample_weight, data.n_pass,
+                                            method_log->log)) {
+    OccEvent const &event = propose_event_f(random_number_generator);
+    double delta_potential_energy = potential_occ_delta_per_supercell_f(event);
+    if (metropolis_acceptance(delta_potential_energy, beta, random_number_generator)) {
+      data.n_accept++;
+      apply_event_f(event);
+    } else {
+      data.n_reject++;
+    }
+    n_step++;
+    if (n_step == data.n_steps_per_pass) {
+      n_step = 0;
+      data.n_pass += 1;
+    }
+    if (data.n_pass == n_pass_next_sample) {
+      n_pass_next_sample += sample_period;
+      for (auto const &pair : data.sampling_functions) {
+        auto const &f = pair.second;
+        data.samplers.at(f.name)->push_back(f());
+      }
+      if (write_status_f && method_log->log_frequency.has_value() &&
+          method_log->log.lap_time() >= method_log->log_frequency.value())
+        write_status_f(data, *method_log);
+    }
+  }
+  if (write_status_f) write_status_f(data, *method_log);
 }
 
 /// basic_semigrand_canonical.hh:486-590; tagged so that `run` can sample them
@@ -1422,7 +1581,12 @@ inline StateSamplingFunction make_parametric_composition_f(
   std::vector<Index> shape;
   shape.push_back(mc_calculator->system->param_composition_calculator.n_independent_compositions());
   auto *raw = mc_calculator.get();
-  auto f = [raw]() -> std::vector<double> {
+  std::weak_ptr<SemiGrandCanonicalCalculator> weak = mc_calculator;  // no ownership cycle
+  auto f = [weak]() -> std::vector<double> {
+    auto raw = weak.lock();
+    if (raw == nullptr)
+      throw std::runtime_error(
+          "Error in parametric_composition sampling function: mc_calculator == nullptr");
     if (raw->param_composition_calculator->state == nullptr)
       throw std::runtime_error(
           "Error in parametric_composition sampling function: "
@@ -1436,8 +1600,16 @@ inline StateSamplingFunction make_parametric_composition_f(
 }
 inline StateSamplingFunction make_formation_energy_f(
     std::shared_ptr<SemiGrandCanonicalCalculator> mc_calculator) {
+  if (mc_calculator == nullptr)
+    throw std::runtime_error(
+        "Error in formation_energy sampling function: mc_calculator == nullptr");
   auto *raw = mc_calculator.get();
-  auto f = [raw]() -> std::vector<double> {
+  std::weak_ptr<SemiGrandCanonicalCalculator> weak = mc_calculator;
+  auto f = [weak]() -> std::vector<double> {
+    auto raw = weak.lock();
+    if (raw == nullptr)
+      throw std::runtime_error(
+          "Error in formation_energy sampling function: mc_calculator == nullptr");
     if (raw->formation_energy_calculator->state == nullptr)
       throw std::runtime_error(
           "Error in formation_energy sampling function: "
@@ -1451,8 +1623,16 @@ inline StateSamplingFunction make_formation_energy_f(
 }
 inline StateSamplingFunction make_potential_energy_f(
     std::shared_ptr<SemiGrandCanonicalCalculator> mc_calculator) {
+  if (mc_calculator == nullptr)
+    throw std::runtime_error(
+        "Error in formation_energy sampling function: mc_calculator == nullptr");
   auto *raw = mc_calculator.get();
-  auto f = [raw]() -> std::vector<double> {
+  std::weak_ptr<SemiGrandCanonicalCalculator> weak = mc_calculator;
+  auto f = [weak]() -> std::vector<double> {
+    auto raw = weak.lock();
+    if (raw == nullptr)
+      throw std::runtime_error(
+          "Error in formation_energy sampling function: mc_calculator == nullptr");
     if (raw->potential.state == nullptr)
       throw std::runtime_error(
           "Error in formation_energy sampling function: mc_calculator->potential.state == nullptr");

@@ -177,3 +177,57 @@ def test_configuration_host_side():
     assert sgc.SemiGrandCanonicalConditions.from_values(v).exchange_potential[0] == 0.5
     with pytest.raises(RuntimeError):
         sgc.SemiGrandCanonicalConditions.from_values(monte.ValueMap.from_dict({"temperature": 1.0}))
+
+
+def test_generic_loop_with_python_callbacks_matches_oracle(oracle, tmp_path):
+    """methods.basic_occupation_metropolis with Python callbacks
+    (python/src/monte_methods.cpp:196-263): a tiny host-side Ising model drives it
+    and the trajectory equals the oracle's reference loop on the same engine."""
+    import casmcode_monte_b200.monte.events as events
+    import casmcode_monte_b200.monte.methods as methods
+
+    n0, n1, Jc, T, mu, seed, n_passes = 6, 4, 0.1, 1200.0, 0.1, 5, 25
+    N = n0 * n1
+    occ = np.ones(N, dtype=np.int32)
+    ev = events.OccEvent()
+    ev.linear_site_index.append(0)
+    ev.new_occ.append(1)
+
+    def propose(rng):
+        ev.linear_site_index[0] = rng.random_int(N - 1)
+        ev.new_occ[0] = -int(occ[ev.linear_site_index[0]])
+        return ev
+
+    def dpot(e):
+        l = e.linear_site_index[0]
+        i, j = l % n0, l // n0
+        nb = occ[(i + 1) % n0 + n0 * j] + occ[i + n0 * ((j + 1) % n1)] + occ[(i - 1) % n0 + n0 * j] + occ[i + n0 * ((j - 1) % n1)]
+        ds = e.new_occ[0] - int(occ[l])
+        return (-Jc * ds) * int(nb) - mu * (ds / 2.0)
+
+    def apply(e):
+        occ[e.linear_site_index[0]] = e.new_occ[0]
+
+    fns = sampling.StateSamplingFunctionMap()
+    fns["param_composition"] = sampling.StateSamplingFunction(
+        name="param_composition", description="x", shape=[1], function=lambda: [(N + int(occ.sum())) / 2.0 / N], component_names=["0"]
+    )
+    params = sampling.CompletionCheckParams()
+    params.cutoff_params.max_count = n_passes
+    data = methods.BasicOccupationMetropolisData(fns, sampling.jsonStateSamplingFunctionMap(), N, params)
+    e = monte.RandomNumberEngine()
+    e.seed(seed)
+    calls = []
+    methods.basic_occupation_metropolis(
+        data, T, dpot, propose, apply, sample_period=1, method_log=monte.MethodLog(str(tmp_path / "status.json"), 1e9), random_engine=e,
+        write_status_f=lambda d, log: calls.append(d.n_pass),
+    )
+    oe = oracle.RandomNumberEngine()
+    oe.seed(seed)
+    ref = oracle.sgc_run([n0, n1], np.ones(N, dtype=np.int32), Jc, T, mu, True, oe, {"max_count": n_passes}, 1)
+    assert np.array_equal(occ, ref["occupation"])
+    assert (data.n_pass, data.n_accept, data.n_reject) == (ref["n_pass"], ref["n_accept"], ref["n_reject"])
+    assert np.array_equal(data.samplers["param_composition"].component(0), ref["samplers"]["param_composition"])
+    assert e.dump() == oe.dump() and calls == [n_passes]
+    d = data.to_dict()
+    assert d["n_steps_per_pass"] == N and abs(d["acceptance_rate"] + d["rejection_rate"] - 1.0) < 1e-15
