@@ -18,6 +18,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 namespace cmg {
 
 constexpr int kMaxIdx = 14;  // 2*(2*3+1)
@@ -531,49 +533,70 @@ __global__ void __launch_bounds__(128) k_halfsweep_bulk2d(SweepArgs A) {
 
     const int p_below = (p0 == 0) ? h - 1 : p0 - 1;
     const int p_above = (p0 + 16 == h) ? 0 : p0 + 16;
-    // the byte across the vector edge for column j: p-1 if i = 2p (parity 0), else p+1
-    auto edge_byte = [&](int j) -> uint32_t {
-      const int par = (int)(((long long)j + L.col_offset + A.colour) & 1);
-      return __ldg(O + (long long)h * j + (par ? p_above : p_below));
-    };
-
     // software pipeline: the loads of column j+1 are in flight while column j is
-    // computed (the ~300 instructions per column hide an L2/HBM round trip)
+    // computed (the ~300 instructions per column hide an L2/HBM round trip).
+    // All addresses advance by pointer increments; the column loop is unrolled by
+    // four with the parity of each copy known at compile time, so the rolling
+    // window lives in renamed registers instead of being moved every column.
+    const int n = jend - jbeg;
+    const long long jg0 = (long long)jbeg + L.col_offset;
+    const uint8_t *Oend = ocol(jend) + p0;  // column jend of the opposite plane (wrap / halo)
     uint4 om = ld16_nc(ocol(jbeg - 1) + p0);
-    uint4 oc = ld16_nc(ocol(jbeg) + p0);
-    uint4 op = ld16_nc(ocol(jbeg + 1) + p0);
-    uint4 ce = ld16(C + (long long)h * jbeg + p0);
-    uint32_t eb = edge_byte(jbeg);
+    uint4 oc = ld16_nc(O + (long long)h * jbeg + p0);
+    uint4 op = ld16_nc((n > 1 ? O + (long long)h * (jbeg + 1) : ocol(jbeg + 1)) + p0);
+    uint8_t *Cp = C + (long long)h * jbeg + p0;                 // own plane, column j
+    const uint8_t *On = O + (long long)h * (jbeg + 2) + p0;     // opposite plane, column j + 2
+    const uint8_t *Ep = O + (long long)h * jbeg;                // opposite plane, column j, p = 0
+    unsigned long long g = (unsigned long long)(((long long)h * jg0 + p0) >> 3);
+    const unsigned int gstep = (unsigned int)h >> 3;
+    uint4 ce = ld16(Cp);
+    const int par0 = (int)((jg0 + A.colour) & 1);  // i = 2p + par
+    uint32_t eb = __ldg(Ep + (par0 ? p_above : p_below));
 
-    for (int j = jbeg; j < jend; ++j) {
-      uint4 op_n = op, ce_n = ce;
-      uint32_t eb_n = eb;
-      if (j + 1 < jend) {
-        op_n = ld16_nc(ocol(j + 2) + p0);
-        ce_n = ld16(C + (long long)h * (j + 1) + p0);
-        eb_n = edge_byte(j + 1);
-      }
-      const long long jg = (long long)j + L.col_offset;
-      const int par = (int)((jg + A.colour) & 1);  // i = 2p + par
+    auto column = [&](const int it, const int par) {
+      // prefetch column j + 1 (the last column of the strip re-reads itself)
+      const unsigned int step = (it + 1 < n) ? (unsigned int)h : 0u;
+      const uint4 op_n = ld16_nc((it + 2 >= n) ? Oend : On);
+      const uint4 ce_n = ld16(Cp + step);
+      const uint32_t eb_n = __ldg(Ep + step + (par ? p_below : p_above));
       const uint4 side = (par == 0) ? shift_up_1(oc, eb) : shift_down_1(oc, eb);
-      const unsigned long long group0 =
-          (unsigned long long)(((long long)h * jg + p0) >> 3);
-      const uint4 cn = update16<SAMPLE>(ce, om, oc, op, side, group0, A.pass,
-                                        A.colour, chain_word, A.rk, acc);
-      *reinterpret_cast<uint4 *>(C + (long long)h * j + p0) = cn;
-      if (push_lo && j == 0) {
-        *reinterpret_cast<uint4 *>(push_lo + p0) = cn;
-        pushed = true;
-      }
-      if (push_hi && j == n1 - 1) {
-        *reinterpret_cast<uint4 *>(push_hi + p0) = cn;
-        pushed = true;
-      }
+      const uint4 cn = update16<SAMPLE>(ce, om, oc, op, side, g, A.pass, A.colour, chain_word,
+                                        A.rk, acc);
+      *reinterpret_cast<uint4 *>(Cp) = cn;
+      Cp += step;
+      Ep += step;
+      On += (unsigned int)h;
+      g += gstep;
       om = oc;
       oc = op;
       op = op_n;
       ce = ce_n;
       eb = eb_n;
+    };
+    auto strip_loop = [&](auto par_tag) {
+      constexpr int P0 = decltype(par_tag)::value;
+      int it = 0;
+      for (; it + 4 <= n; it += 4) {
+        column(it, P0);
+        column(it + 1, P0 ^ 1);
+        column(it + 2, P0);
+        column(it + 3, P0 ^ 1);
+      }
+      for (; it < n; ++it) column(it, P0 ^ (it & 1));
+    };
+    if (par0) {
+      strip_loop(std::integral_constant<int, 1>{});
+    } else {
+      strip_loop(std::integral_constant<int, 0>{});
+    }
+    // slab decomposition: the boundary columns also go to the neighbours' halos
+    if (push_lo && jbeg == 0) {
+      *reinterpret_cast<uint4 *>(push_lo + p0) = ld16(C + p0);
+      pushed = true;
+    }
+    if (push_hi && jend == n1) {
+      *reinterpret_cast<uint4 *>(push_hi + p0) = ld16(C + (long long)h * (n1 - 1) + p0);
+      pushed = true;
     }
   }
   long long ones = 0, bsum = 0;
@@ -745,7 +768,11 @@ __global__ void __launch_bounds__(NT, 1) k_tile2d(TileArgs A) {
       // each thread keeps its vector offset and strides over columns
       const int p0 = (threadIdx.x % V) << 4;
       const int cstep = NT / V;
-      for (int dc = threadIdx.x / V; dc < hi - lo; dc += cstep) process(lo + dc, dc, p0);
+      int dc0 = threadIdx.x / V;
+      // short columns (V < 32): a warp spans 32/V columns; hand it columns of one
+      // parity (c, c+2, ...) so the parity branch in process() stays warp-uniform
+      if (V < 32 && (cstep & 7) == 0) dc0 = 2 * (dc0 % (cstep >> 1)) + dc0 / (cstep >> 1);
+      for (int dc = dc0; dc < hi - lo; dc += cstep) process(lo + dc, dc, p0);
     } else {
       const int items = (hi - lo) * V;
       for (int it = threadIdx.x; it < items; it += NT) {
