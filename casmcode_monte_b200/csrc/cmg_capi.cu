@@ -941,9 +941,9 @@ static int launch_half_sweep(cmg_context *c, int variant, int colour, unsigned l
     const long long strips = (c->shape[1] + A.js - 1) / A.js;
     dim3 grid(nblocks(V * strips, 128), c->n_chains);
     if (sample)
-      k_halfsweep_bulk2d<true><<<grid, block, kSmemSmall, c->stream>>>(A);
+      k_halfsweep_bulk2d<true><<<grid, block, kSmemBulk2d, c->stream>>>(A);
     else
-      k_halfsweep_bulk2d<false><<<grid, block, kSmemSmall, c->stream>>>(A);
+      k_halfsweep_bulk2d<false><<<grid, block, kSmemBulk2d, c->stream>>>(A);
   } else if (variant == V_BULK3D) {
     const long long V = c->shape[0] / 32;
     const long long strips = (c->shape[1] + A.js - 1) / A.js;

@@ -493,6 +493,45 @@ __device__ __forceinline__ void slab_signal_neighbours(const LatticeView &L, boo
   }
 }
 
+
+// ---- cp.async (LDGSTS) staging: global -> shared without passing through registers
+__device__ __forceinline__ void cp_async16_ca(uint32_t saddr, const void *g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async16_cg(uint32_t saddr, const void *g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async4_ca(uint32_t saddr, const void *g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+// shared-window (32-bit) addressed loads
+__device__ __forceinline__ uint4 lds16_abs(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "r"(saddr)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t lds8_abs(uint32_t saddr) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
+  return v;
+}
+// per-thread staging ring of the bulk kernels (128 threads per CTA): per stage
+// 128 x 16 B opposite-plane vectors, 128 x 16 B own-plane vectors, 128 x 4 B edge words
+constexpr int kBulkStages = 4;
+constexpr int kSmemRing = 128;
+constexpr uint32_t kBulkStageBytes = 128u * 36u;
+constexpr int kSmemBulk2d = kSmemRing + kBulkStages * (int)kBulkStageBytes;
+
 template <bool SAMPLE>
 __global__ void __launch_bounds__(128) k_halfsweep_bulk2d(SweepArgs A) {
   const LatticeView &L = A.L;
@@ -533,48 +572,67 @@ __global__ void __launch_bounds__(128) k_halfsweep_bulk2d(SweepArgs A) {
 
     const int p_below = (p0 == 0) ? h - 1 : p0 - 1;
     const int p_above = (p0 + 16 == h) ? 0 : p0 + 16;
-    // software pipeline: the loads of column j+1 are in flight while column j is
-    // computed (the ~300 instructions per column hide an L2/HBM round trip).
-    // All addresses advance by pointer increments; the column loop is unrolled by
-    // four with the parity of each copy known at compile time, so the rolling
-    // window lives in renamed registers instead of being moved every column.
+    // Software pipeline through shared memory: every thread owns a private ring of
+    // kBulkStages slots and keeps the loads of the next kBulkStages columns in
+    // flight with cp.async (LDGSTS), which costs no registers -- with ~270
+    // instructions per column and 4-5 warps per scheduler one column of lookahead
+    // does not cover an HBM round trip.  Slot k & 3 holds, for pipeline step k:
+    // the opposite-plane vector of column jbeg+k+1, the own-plane vector of column
+    // jbeg+k and the aligned word holding the byte across the vector edge of
+    // column jbeg+k.  The column loop is unrolled by the ring size, so slots and
+    // column parities are compile-time constants in the loop body.
     const int n = jend - jbeg;
     const long long jg0 = (long long)jbeg + L.col_offset;
+    const int par0 = (int)((jg0 + A.colour) & 1);  // i = 2p + par
     const uint8_t *Oend = ocol(jend) + p0;  // column jend of the opposite plane (wrap / halo)
+    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(cmg_smem) + kSmemRing;
+    const uint32_t s_o = ring + threadIdx.x * 16u;
+    const uint32_t s_c = ring + 128u * 16u + threadIdx.x * 16u;
+    const uint32_t s_e = ring + 128u * 32u + threadIdx.x * 4u;
+    const unsigned int hstep = (unsigned int)h;
+    const uint8_t *Of = O + (long long)h * (jbeg + 1) + p0;  // fetch front, opposite plane
+    const uint8_t *Cf = C + (long long)h * jbeg + p0;        // fetch front, own plane
+    const uint8_t *Ef = O + (long long)h * jbeg;             // fetch front, edge words
+    const int e_lo = p_below & ~3, e_hi = p_above;           // byte 3 / byte 0 of the word
+    auto fetch = [&](const int k, const int par) {
+      if (k < n) {
+        const uint32_t slot = (uint32_t)(k & (kBulkStages - 1)) * kBulkStageBytes;
+        cp_async16_ca(s_o + slot, (k + 1 >= n) ? Oend : Of);
+        cp_async16_cg(s_c + slot, Cf);
+        cp_async4_ca(s_e + slot, Ef + (par ? e_hi : e_lo));
+        Of += hstep;
+        Cf += hstep;
+        Ef += hstep;
+      }
+      cp_async_commit();
+    };
     uint4 om = ld16_nc(ocol(jbeg - 1) + p0);
     uint4 oc = ld16_nc(O + (long long)h * jbeg + p0);
-    uint4 op = ld16_nc((n > 1 ? O + (long long)h * (jbeg + 1) : ocol(jbeg + 1)) + p0);
-    uint8_t *Cp = C + (long long)h * jbeg + p0;                 // own plane, column j
-    const uint8_t *On = O + (long long)h * (jbeg + 2) + p0;     // opposite plane, column j + 2
-    const uint8_t *Ep = O + (long long)h * jbeg;                // opposite plane, column j, p = 0
+#pragma unroll
+    for (int k = 0; k < kBulkStages; ++k) fetch(k, par0 ^ (k & 1));
+    uint8_t *Cp = C + (long long)h * jbeg + p0;  // own plane, column j
     unsigned long long g = (unsigned long long)(((long long)h * jg0 + p0) >> 3);
     const unsigned int gstep = (unsigned int)h >> 3;
-    uint4 ce = ld16(Cp);
-    const int par0 = (int)((jg0 + A.colour) & 1);  // i = 2p + par
-    uint32_t eb = __ldg(Ep + (par0 ? p_above : p_below));
 
     auto column = [&](const int it, const int par) {
-      // prefetch column j + 1 (the last column of the strip re-reads itself)
-      const unsigned int step = (it + 1 < n) ? (unsigned int)h : 0u;
-      const uint4 op_n = ld16_nc((it + 2 >= n) ? Oend : On);
-      const uint4 ce_n = ld16(Cp + step);
-      const uint32_t eb_n = __ldg(Ep + step + (par ? p_below : p_above));
+      const uint32_t slot = (uint32_t)(it & (kBulkStages - 1)) * kBulkStageBytes;
+      cp_async_wait<kBulkStages - 1>();
+      const uint4 op = lds16_abs(s_o + slot);
+      const uint4 ce = lds16_abs(s_c + slot);
+      const uint32_t eb = lds8_abs(s_e + slot + (par ? 0u : 3u));
+      fetch(it + kBulkStages, par);
       const uint4 side = (par == 0) ? shift_up_1(oc, eb) : shift_down_1(oc, eb);
       const uint4 cn = update16<SAMPLE>(ce, om, oc, op, side, g, A.pass, A.colour, chain_word,
                                         A.rk, acc);
       *reinterpret_cast<uint4 *>(Cp) = cn;
-      Cp += step;
-      Ep += step;
-      On += (unsigned int)h;
+      Cp += hstep;
       g += gstep;
       om = oc;
       oc = op;
-      op = op_n;
-      ce = ce_n;
-      eb = eb_n;
     };
     auto strip_loop = [&](auto par_tag) {
       constexpr int P0 = decltype(par_tag)::value;
+      static_assert(kBulkStages == 4, "the column loop is unrolled by the ring size");
       int it = 0;
       for (; it + 4 <= n; it += 4) {
         column(it, P0);
