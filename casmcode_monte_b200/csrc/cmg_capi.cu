@@ -95,6 +95,7 @@ struct cmg_context {
   int tile_passes = 3;   // passes per launch of the tiled kernel (halo = 2*P columns)
   int tile_threads = 512;
   int sm_count = 148;
+  int js_auto[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // cached strip length per kernel variant
   size_t smem_optin = 0;
   long long launches = 0;
   std::string last_error;
@@ -898,16 +899,39 @@ static int pick_variant(cmg_context *c) {
   return V_GENERIC;
 }
 
-static int pick_js(const cmg_context *c, int variant) {
+static int pick_js(cmg_context *c, int variant) {
   if (c->js > 0) return c->js;
-  // strips long enough to amortise the two extra column loads, short enough to
-  // give every SM several CTAs (148 SMs x 16 CTAs of 128 threads)
+  if (c->js_auto[variant] > 0) return c->js_auto[variant];
+  // CTAs of 128 threads that fit on the device at once (register-limited)
+  int per_sm = 0;
+  cudaError_t e = variant == V_BULK3D
+                      ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_halfsweep_bulk3d<true>, 128, kSmemBulk3d)
+                      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_halfsweep_bulk2d<true>, 128, kSmemBulk2d);
+  if (e != cudaSuccess || per_sm < 1) per_sm = 4;
+  const double slots = (double)c->sm_count * per_sm;
   const long long V = c->shape[0] / 32;
   const long long layers = variant == V_BULK3D ? c->shape[2] : 1;
-  const long long target_threads = 148LL * 512;
-  int js = 16;
-  while (js > 2 && V * ((c->shape[1] + js - 1) / js) * layers * c->n_chains < target_threads) js >>= 1;
-  return js;
+  // Strip length: long strips amortise the two extra column loads and the
+  // pipeline fill at the strip start; the CTA count they imply should fill
+  // whole waves of `slots` CTAs (a 1.7-wave launch idles a quarter of the GPU
+  // during its tail).  Multiples of four match the unrolled column loop.
+  static const int cand[] = {2, 4, 6, 8, 12, 16, 20, 24, 28, 32, 36, 40, 44, 48};
+  int best = 16;
+  double best_score = -1.0;
+  for (int js : cand) {
+    if (js > c->shape[1] && js > 2) continue;
+    const long long strips = (c->shape[1] + js - 1) / js;
+    const double ctas = (double)nblocks(V * strips * layers, 128) * c->n_chains;
+    const double waves = ctas / slots;
+    const double fill = waves / std::ceil(waves);
+    const double score = fill * js / (js + 2.0);
+    if (score > best_score) {
+      best_score = score;
+      best = js;
+    }
+  }
+  c->js_auto[variant] = best;
+  return best;
 }
 
 static int launch_half_sweep(cmg_context *c, int variant, int colour, unsigned long long pass,
@@ -949,9 +973,9 @@ static int launch_half_sweep(cmg_context *c, int variant, int colour, unsigned l
     const long long strips = (c->shape[1] + A.js - 1) / A.js;
     dim3 grid(nblocks(V * strips * c->shape[2], 128), c->n_chains);
     if (sample)
-      k_halfsweep_bulk3d<true><<<grid, block, kSmemSmall, c->stream>>>(A);
+      k_halfsweep_bulk3d<true><<<grid, block, kSmemBulk3d, c->stream>>>(A);
     else
-      k_halfsweep_bulk3d<false><<<grid, block, kSmemSmall, c->stream>>>(A);
+      k_halfsweep_bulk3d<false><<<grid, block, kSmemBulk3d, c->stream>>>(A);
   } else {
     return fail(c, CMG_EUNSUPPORTED, "kernel variant not available");
   }

@@ -118,96 +118,101 @@ __device__ __forceinline__ uint4 site_group_random(unsigned long long group,
 // All sweep kernels use one dynamic shared-memory buffer, declared at
 // namespace scope so that every access is a plain LDS (no generic-address
 // conversion):
-//   [0, 64)                 the chain's acceptance table as ~thr_m1, 16 x u32
-//   [kSmemPair, +14*2048)   pair table: entry (A, B) = {~thr[A], ~thr[B]} at byte
-//                           offset 8*A + 2048*B, so the 16-bit value formed by two
-//                           neighbouring index bytes (each holding 8*index) IS the
-//                           byte offset of the pair: one LDS.64 per two sites
-//   [kSmemTile, ...)        tile data (k_tile2d)
+//   [0, 64)                 the chain's acceptance table thr_m1, 16 x u32 (exact path)
+//   [kSmemLaneLo, +64)      fast-compare lane G[idx] of every entry, in the low half
+//   [kSmemLaneHi, +64)      the same lane in the high half (G[idx] << 16)
+//   [kSmemPair, +14*1024)   pair table: entry (A, B) = G[A] | G[B] << 16 at byte
+//                           offset 4*A + 1024*B, so the 16-bit value formed by two
+//                           neighbouring index bytes (each holding 4*index) IS the
+//                           byte offset of the pair: one LDS per two sites
+//   [kSmemTile, ...)        tile data (k_tile2d) / staging ring (bulk kernels)
 extern __shared__ __align__(16) unsigned char cmg_smem[];
-constexpr int kSmemPair = 2048;
-constexpr int kSmemTile = kSmemPair + 14 * 2048;
+constexpr int kSmemLaneLo = 64;
+constexpr int kSmemLaneHi = 128;
+constexpr int kSmemSmall = 192;  // kernels that only use the 16-entry tables
+constexpr int kSmemPair = 1024;
+constexpr int kSmemTile = kSmemPair + 14 * 1024;
 
-constexpr int kSmemSmall = 128;  // kernels that only use the 16-entry table
+// Fast-compare lane of a table entry (see accept_mask4_fast): 0x7FFF + the
+// leading 15 bits of the threshold, 0xFFFF for an entry that always accepts.
+__device__ __forceinline__ uint32_t fast_lane(uint32_t thr_m1) {
+  return thr_m1 == 0xFFFFFFFFu ? 0xFFFFu : 0x7FFFu + (thr_m1 >> 17);
+}
 
 __device__ __forceinline__ void load_accept_table(const ChainTables *tab, bool with_pairs) {
-  if (threadIdx.x < 16)
-    reinterpret_cast<uint32_t *>(cmg_smem)[threadIdx.x] = ~tab->thr_m1[threadIdx.x];
+  if (threadIdx.x < 16) {
+    const uint32_t thr = tab->thr_m1[threadIdx.x];
+    reinterpret_cast<uint32_t *>(cmg_smem)[threadIdx.x] = thr;
+    reinterpret_cast<uint32_t *>(cmg_smem + kSmemLaneLo)[threadIdx.x] = fast_lane(thr);
+    reinterpret_cast<uint32_t *>(cmg_smem + kSmemLaneHi)[threadIdx.x] = fast_lane(thr) << 16;
+  }
   if (!with_pairs) return;
   for (int e = threadIdx.x; e < 14 * 14; e += blockDim.x) {
     const int A = e % 14, B = e / 14;
-    *reinterpret_cast<uint2 *>(cmg_smem + kSmemPair + 8 * A + 2048 * B) =
-        make_uint2(~tab->thr_m1[A], ~tab->thr_m1[B]);
+    *reinterpret_cast<uint32_t *>(cmg_smem + kSmemPair + 4 * A + 1024 * B) =
+        fast_lane(tab->thr_m1[A]) | (fast_lane(tab->thr_m1[B]) << 16);
   }
 }
 // byte_off = 4 * table index
-__device__ __forceinline__ uint32_t nthr_at(uint32_t byte_off) {
+__device__ __forceinline__ uint32_t thr_at(uint32_t byte_off) {
   return *reinterpret_cast<const uint32_t *>(cmg_smem + byte_off);
 }
-// pair_off = 8*indexA + 2048*indexB
-__device__ __forceinline__ uint2 nthr_pair_at(uint32_t pair_off) {
-  return *reinterpret_cast<const uint2 *>(cmg_smem + kSmemPair + pair_off);
+__device__ __forceinline__ uint32_t lane_lo_at(uint32_t byte_off) {
+  return *reinterpret_cast<const uint32_t *>(cmg_smem + kSmemLaneLo + byte_off);
+}
+__device__ __forceinline__ uint32_t lane_hi_at(uint32_t byte_off) {
+  return *reinterpret_cast<const uint32_t *>(cmg_smem + kSmemLaneHi + byte_off);
+}
+// pair_off = 4*indexA + 1024*indexB
+__device__ __forceinline__ uint32_t lane_pair_at(uint32_t pair_off) {
+  return *reinterpret_cast<const uint32_t *>(cmg_smem + kSmemPair + pair_off);
 }
 
 // Acceptance of 4 sites packed in a word.  Each site's uniform is the 32-bit
-// integer R = r16<<16 | r16' and the site is flipped iff R <= thr (thr =
-// thr_m1 of its table entry).  Only r16 is generated up front: with Y = r16<<16,
-//   Y >  thr              -> rejected whatever r16' is,
-//   Y <= thr - 65536      -> accepted whatever r16' is,
-//   otherwise (r16 equals the top half of thr, probability 2^-16) a tie that
-//   needs r16'.
-// idx4e: 8 * table index of each site in its byte; r01 / r23: the Philox words
+// integer R = rotl16(r16, 1) << 16 | r16' (r16, r16': the site's 16-bit Philox
+// lanes of the leading / refinement call) and the site is flipped iff
+// R <= thr (thr = thr_m1 of its table entry).  The leading 15 bits of R are
+// a = r16 & 0x7FFF, so with T = thr >> 17:
+//   a < T   -> accepted whatever the remaining 17 bits are,
+//   a > T   -> rejected,
+//   a == T  -> a tie (probability 2^-15 per site) that needs the exact compare.
+// Two sites are compared per 32-bit subtraction: their lanes G = 0x7FFF + T sit
+// in the two halves of a word and x = G - a never borrows across the halves;
+// x >= 0x8000 (sign bit of the half) iff accepted, x == 0x7FFF iff tie.  Entries
+// that always accept have G = 0xFFFF and can never tie.
+// idx4e: 4 * table index of each site in its byte; r01 / r23: the Philox words
 // holding the r16 of sites (0,1) / (2,3) in their (low, high) halves.
-// D = Y + ~thr carries out iff Y > thr (2 instructions per site through the
-// carry flag, no predicates), and D >= 0xFFFF0000 iff tie, tracked with one max
-// per site.  Returns 0x01 in the byte of every (provisionally) accepted site;
-// ties count as accepted here and are resolved by the caller when
-// dmax >= 0xFFFF0000.
-// PAIR: index bytes hold 8*index and thresholds come two at a time from the pair
-// table; otherwise they hold 4*index and come from the 16-entry table.
+// tmax: running per-half signed maximum (start at 0): a half equals 0x7FFF iff
+// some site tied.  Returns 0xFF in the byte of every accepted site (ties count
+// as rejected here; the caller redoes the vector exactly when one occurred).
+// PAIR: lanes come two at a time from the pair table; otherwise one LDS per
+// site from the two 16-entry lane tables (bank-conflict free) merged by the add.
 template <bool PAIR>
 __device__ __forceinline__ uint32_t accept_mask4_fast(uint32_t idx4e, uint32_t r01,
-                                                      uint32_t r23, uint32_t &dmax) {
-  uint32_t t0, t1, t2, t3;
+                                                      uint32_t r23, uint32_t &tmax) {
+  const uint32_t a01 = r01 & 0x7fff7fffu, a23 = r23 & 0x7fff7fffu;
+  uint32_t x01, x23;
   if (PAIR) {
-    const uint2 p01 = nthr_pair_at(idx4e & 0xffffu);
-    const uint2 p23 = nthr_pair_at(idx4e >> 16);
-    t0 = p01.x, t1 = p01.y, t2 = p23.x, t3 = p23.y;
+    x01 = lane_pair_at(idx4e & 0xffffu) - a01;
+    x23 = lane_pair_at(idx4e >> 16) - a23;
   } else {
-    t0 = nthr_at(idx4e & 0xffu);
-    t1 = nthr_at(__byte_perm(idx4e, 0u, 0x4441u));
-    t2 = nthr_at(__byte_perm(idx4e, 0u, 0x4442u));
-    t3 = nthr_at(idx4e >> 24);
+    x01 = lane_lo_at(idx4e & 0xffu) + lane_hi_at(__byte_perm(idx4e, 0u, 0x4441u)) - a01;
+    x23 = lane_lo_at(__byte_perm(idx4e, 0u, 0x4442u)) + lane_hi_at(idx4e >> 24) - a23;
   }
-  const uint32_t y0 = r01 << 16, y1 = r01 & 0xffff0000u;
-  const uint32_t y2 = r23 << 16, y3 = r23 & 0xffff0000u;
-  uint32_t rej, mx = dmax;
-  asm("{\n\t"
-      ".reg .u32 d;\n\t"
-      "add.cc.u32 d, %2, %6;\n\t"
-      "addc.u32 %0, 0, 0;\n\t"
-      "max.u32 %1, %1, d;\n\t"
-      "add.cc.u32 d, %3, %7;\n\t"
-      "addc.u32 %0, %0, %0;\n\t"
-      "max.u32 %1, %1, d;\n\t"
-      "add.cc.u32 d, %4, %8;\n\t"
-      "addc.u32 %0, %0, %0;\n\t"
-      "max.u32 %1, %1, d;\n\t"
-      "add.cc.u32 d, %5, %9;\n\t"
-      "addc.u32 %0, %0, %0;\n\t"
-      "max.u32 %1, %1, d;\n\t"
-      "}"
-      : "=r"(rej), "+r"(mx)
-      : "r"(t3), "r"(t2), "r"(t1), "r"(t0), "r"(y3), "r"(y2), "r"(y1), "r"(y0));
-  dmax = mx;
-  // bit k of rej = site k rejected; spread the 4 bits to the low bit of 4 bytes
-  const uint32_t rej_bytes = (rej * 0x00204081u) & 0x01010101u;
-  return rej_bytes ^ 0x01010101u;
+  tmax = __vimax3_s16x2(tmax, x01, x23);
+  uint32_t m;
+  // bytes 1 and 3 of x01, x23 with their sign bit replicated over the byte
+  asm("prmt.b32 %0, %1, %2, 0xFDB9;" : "=r"(m) : "r"(x01), "r"(x23));
+  return m;
+}
+__device__ __forceinline__ bool any_tie(uint32_t tmax) {
+  return ((tmax + 0x00010001u) & 0x80008000u) != 0u;
 }
 
 // Exact form with both halves (tie path and the generic kernel).
 __device__ __forceinline__ bool accept_exact(uint32_t r16, uint32_t r16b, uint32_t thr) {
-  return ((r16 << 16) | r16b) <= thr;
+  const uint32_t lead = ((r16 << 1) | (r16 >> 15)) & 0xffffu;  // rotl16(r16, 1)
+  return ((lead << 16) | r16b) <= thr;
 }
 __device__ __forceinline__ uint32_t lane16(uint4 v, int lane) {
   const uint32_t w = (lane >> 1) == 0 ? v.x : (lane >> 1) == 1 ? v.y : (lane >> 1) == 2 ? v.z : v.w;
@@ -314,7 +319,7 @@ __global__ void __launch_bounds__(128) k_halfsweep_generic(SweepArgs A) {
                 O[p + (long long)L.h * (j + (long long)L.n1 * kp)];
       }
       int b = C[q];
-      if (accept_exact(lane16(ra, w), lane16(rb, w), ~nthr_at(4u * (2 * n_up + b)))) {
+      if (accept_exact(lane16(ra, w), lane16(rb, w), thr_at(4u * (2 * n_up + b)))) {
         b ^= 1;
         C[q] = (uint8_t)b;
         ++acc;
@@ -368,10 +373,10 @@ __device__ __forceinline__ uint4 shift_down_1(uint4 v, uint32_t hi) {
   return o;
 }
 
-// Rare path: some site of a 16-site vector tied on its leading 16 bits.  Redo
+// Rare path: some site of a 16-site vector tied on its leading 15 bits.  Redo
 // all 16 decisions exactly with both halves (regenerating the leading words so
 // the hot path does not have to keep them alive).
-__device__ __noinline__ uint4 resolve_ties16(uint4 idx4e, int idx_shift, unsigned long long group0,
+__device__ __noinline__ uint4 resolve_ties16(uint4 idx4e, unsigned long long group0,
                                              unsigned long long pass, int colour,
                                              uint32_t chain_word, const uint32_t *rk) {
   const uint32_t iw[4] = {idx4e.x, idx4e.y, idx4e.z, idx4e.w};
@@ -386,8 +391,8 @@ __device__ __noinline__ uint4 resolve_ties16(uint4 idx4e, int idx_shift, unsigne
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int lane = 4 * ww + k;
-        const uint32_t thr = ~nthr_at(((iw[w] >> (8 * k)) & 0xffu) >> idx_shift);
-        mm |= accept_exact(lane16(r, lane), lane16(q, lane), thr) ? (1u << (8 * k)) : 0u;
+        const uint32_t thr = thr_at((iw[w] >> (8 * k)) & 0xffu);
+        mm |= accept_exact(lane16(r, lane), lane16(q, lane), thr) ? (0xffu << (8 * k)) : 0u;
       }
       m[w] = mm;
     }
@@ -426,15 +431,15 @@ __device__ __forceinline__ uint4 update16(uint4 ce, uint4 om, uint4 oc, uint4 op
   const uint4 ra = site_group_random(group0, chain_word, pass, colour, 0, rk);
   const uint4 rb = site_group_random(group0 + 1, chain_word, pass, colour, 0, rk);
   const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
-  uint32_t idx[4], m[4], dmax = 0;
+  uint32_t idx[4], m[4], tmax = 0;
 #pragma unroll
   for (int w = 0; w < 4; ++w) {
-    idx[w] = (nw[w] + nw[w] + cw[w]) << (PAIR ? 3 : 2);  // 8 (or 4) * (2*n_up + b) per byte
-    m[w] = accept_mask4_fast<PAIR>(idx[w], rw[2 * w], rw[2 * w + 1], dmax);
+    idx[w] = (nw[w] + nw[w] + cw[w]) << 2;  // 4 * (2*n_up + b) per byte
+    m[w] = accept_mask4_fast<PAIR>(idx[w], rw[2 * w], rw[2 * w + 1], tmax);
   }
-  if (dmax >= 0xffff0000u) {  // a tie somewhere in these 16 sites (probability 16 * 2^-16)
-    const uint4 mm = resolve_ties16(make_uint4(idx[0], idx[1], idx[2], idx[3]), PAIR ? 1 : 0,
-                                    group0, pass, colour, chain_word, rk);
+  if (any_tie(tmax)) {  // a tie somewhere in these 16 sites (probability 16 * 2^-15)
+    const uint4 mm = resolve_ties16(make_uint4(idx[0], idx[1], idx[2], idx[3]), group0, pass,
+                                    colour, chain_word, rk);
     m[0] = mm.x;
     m[1] = mm.y;
     m[2] = mm.z;
@@ -442,8 +447,8 @@ __device__ __forceinline__ uint4 update16(uint4 ce, uint4 om, uint4 oc, uint4 op
   }
 #pragma unroll
   for (int w = 0; w < 4; ++w) {
-    cw[w] ^= m[w];
-    a.acc = __dp4a(m[w], 0x01010101u, a.acc);
+    cw[w] ^= m[w] & 0x01010101u;
+    a.acc = (unsigned int)__dp4a((int)m[w], (int)0xffffffffu, (int)a.acc);  // (-1)*(-1) per accepted site
     if (SAMPLE) {
       const uint32_t flip7 = ~(cw[w] * 0xffu) & 0x07070707u;  // 7 where b = 0
       a.u7 = __dp4a(nw[w] ^ flip7, 0x01010101u, a.u7);
@@ -528,7 +533,8 @@ __device__ __forceinline__ uint32_t lds8_abs(uint32_t saddr) {
 // per-thread staging ring of the bulk kernels (128 threads per CTA): per stage
 // 128 x 16 B opposite-plane vectors, 128 x 16 B own-plane vectors, 128 x 4 B edge words
 constexpr int kBulkStages = 4;
-constexpr int kSmemRing = 128;
+constexpr bool kBulkPair = false;  // bulk kernels: pair table (1 LDS / 2 sites) or lane tables
+constexpr int kSmemRing = kBulkPair ? kSmemTile : 256;
 constexpr uint32_t kBulkStageBytes = 128u * 36u;
 constexpr int kSmemBulk2d = kSmemRing + kBulkStages * (int)kBulkStageBytes;
 
@@ -536,7 +542,7 @@ template <bool SAMPLE>
 __global__ void __launch_bounds__(128) k_halfsweep_bulk2d(SweepArgs A) {
   const LatticeView &L = A.L;
   const int chain = blockIdx.y;
-  load_accept_table(A.tabs + chain, false);
+  load_accept_table(A.tabs + chain, kBulkPair);
   __syncthreads();
   slab_wait_neighbours(L);
 
@@ -622,7 +628,7 @@ __global__ void __launch_bounds__(128) k_halfsweep_bulk2d(SweepArgs A) {
       const uint32_t eb = lds8_abs(s_e + slot + (par ? 0u : 3u));
       fetch(it + kBulkStages, par);
       const uint4 side = (par == 0) ? shift_up_1(oc, eb) : shift_down_1(oc, eb);
-      const uint4 cn = update16<SAMPLE>(ce, om, oc, op, side, g, A.pass, A.colour, chain_word,
+      const uint4 cn = update16<SAMPLE, kBulkPair>(ce, om, oc, op, side, g, A.pass, A.colour, chain_word,
                                         A.rk, acc);
       *reinterpret_cast<uint4 *>(Cp) = cn;
       Cp += hstep;
@@ -883,11 +889,16 @@ __global__ void __launch_bounds__(NT, 1) k_tile2d(TileArgs A) {
 // are two extra 16-byte loads per column (served by L2: a k-layer of 512^3 is
 // 128 KiB per colour).
 // ---------------------------------------------------------------------------
+// per stage: 128 x 16 B for each of j+1, k-1, k+1 (opposite plane) and the own
+// plane, 128 x 4 B edge words
+constexpr uint32_t kBulk3dStageBytes = 128u * 68u;
+constexpr int kSmemBulk3d = kSmemRing + kBulkStages * (int)kBulk3dStageBytes;
+
 template <bool SAMPLE>
 __global__ void __launch_bounds__(128) k_halfsweep_bulk3d(SweepArgs A) {
   const LatticeView &L = A.L;
   const int chain = blockIdx.y;
-  load_accept_table(A.tabs + chain, false);
+  load_accept_table(A.tabs + chain, kBulkPair);
   __syncthreads();
 
   const int h = L.h, n1 = L.n1, n2 = L.n2;
@@ -910,42 +921,93 @@ __global__ void __launch_bounds__(128) k_halfsweep_bulk3d(SweepArgs A) {
     const uint8_t *Oall = L.planes + (long long)chain * L.chain_stride +
                           (long long)(1 - A.colour) * L.plane_stride;
     const uint8_t *O = Oall + layer * k;
-    const uint8_t *Okm = Oall + layer * ((k == 0) ? n2 - 1 : k - 1);
-    const uint8_t *Okp = Oall + layer * ((k == n2 - 1) ? 0 : k + 1);
     const uint32_t chain_word = (uint32_t)(chain + A.chain_offset) << 8;
 
     auto wrapj = [&](int j) { return (j < 0) ? n1 - 1 : (j >= n1 ? 0 : j); };
-    uint4 om = ld16_nc(O + (long long)h * wrapj(jbeg - 1) + p0);
-    uint4 oc = ld16_nc(O + (long long)h * jbeg + p0);
     const int p_below = (p0 == 0) ? h - 1 : p0 - 1;
     const int p_above = (p0 + 16 == h) ? 0 : p0 + 16;
 
-    for (int j = jbeg; j < jend; ++j) {
-      const long long off = (long long)h * j + p0;
-      const uint4 op = ld16_nc(O + (long long)h * wrapj(j + 1) + p0);
-      const uint4 ka = ld16_nc(Okm + off);
-      const uint4 kb = ld16_nc(Okp + off);
-      const uint4 ce = ld16(C + off);
-      const int par = (j + k + A.colour) & 1;
-      const uint8_t *ocj = O + (long long)h * j;
-      uint4 side;
-      if (par == 0) {
-        side = shift_up_1(oc, __ldg(ocj + p_below));
-      } else {
-        side = shift_down_1(oc, __ldg(ocj + p_above));
+    // same staging ring as k_halfsweep_bulk2d, with the two k-neighbour vectors
+    // of the column added to every stage
+    const int n = jend - jbeg;
+    const int par0 = (jbeg + k + A.colour) & 1;  // i = 2p + par
+    const uint8_t *Oend = O + (long long)h * wrapj(jend) + p0;
+    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(cmg_smem) + kSmemRing;
+    const uint32_t s_o = ring + threadIdx.x * 16u;
+    const uint32_t s_a = s_o + 128u * 16u;
+    const uint32_t s_b = s_o + 128u * 32u;
+    const uint32_t s_c = s_o + 128u * 48u;
+    const uint32_t s_e = ring + 128u * 64u + threadIdx.x * 4u;
+    const unsigned int hstep = (unsigned int)h;
+    const long long col0 = (long long)h * jbeg + p0;
+    const uint8_t *Of = O + col0 + h;                                              // column j+1
+    const uint8_t *Af = Oall + layer * ((k == 0) ? n2 - 1 : k - 1) + col0;         // layer k-1
+    const uint8_t *Bf = Oall + layer * ((k == n2 - 1) ? 0 : k + 1) + col0;         // layer k+1
+    const uint8_t *Cf = C + col0;
+    const uint8_t *Ef = O + (long long)h * jbeg;
+    const int e_lo = p_below & ~3, e_hi = p_above;
+    auto fetch = [&](const int kk, const int par) {
+      if (kk < n) {
+        const uint32_t slot = (uint32_t)(kk & (kBulkStages - 1)) * kBulk3dStageBytes;
+        cp_async16_ca(s_o + slot, (kk + 1 >= n) ? Oend : Of);
+        cp_async16_cg(s_a + slot, Af);
+        cp_async16_cg(s_b + slot, Bf);
+        cp_async16_cg(s_c + slot, Cf);
+        cp_async4_ca(s_e + slot, Ef + (par ? e_hi : e_lo));
+        Of += hstep;
+        Af += hstep;
+        Bf += hstep;
+        Cf += hstep;
+        Ef += hstep;
       }
+      cp_async_commit();
+    };
+    uint4 om = ld16_nc(O + (long long)h * wrapj(jbeg - 1) + p0);
+    uint4 oc = ld16_nc(O + col0);
+#pragma unroll
+    for (int kk = 0; kk < kBulkStages; ++kk) fetch(kk, par0 ^ (kk & 1));
+    uint8_t *Cp = C + col0;
+    unsigned long long g = (unsigned long long)((layer * k + col0) >> 3);
+    const unsigned int gstep = (unsigned int)h >> 3;
+
+    auto column = [&](const int it, const int par) {
+      const uint32_t slot = (uint32_t)(it & (kBulkStages - 1)) * kBulk3dStageBytes;
+      cp_async_wait<kBulkStages - 1>();
+      const uint4 op = lds16_abs(s_o + slot);
+      const uint4 ka = lds16_abs(s_a + slot);
+      const uint4 kb = lds16_abs(s_b + slot);
+      const uint4 ce = lds16_abs(s_c + slot);
+      const uint32_t eb = lds8_abs(s_e + slot + (par ? 0u : 3u));
+      fetch(it + kBulkStages, par);
+      uint4 side = (par == 0) ? shift_up_1(oc, eb) : shift_down_1(oc, eb);
       // fold the two k-neighbours into the "side" word: sums stay <= 6
       side.x += ka.x + kb.x;
       side.y += ka.y + kb.y;
       side.z += ka.z + kb.z;
       side.w += ka.w + kb.w;
-      const unsigned long long group0 =
-          (unsigned long long)((layer * k + off) >> 3);
-      const uint4 cn = update16<SAMPLE>(ce, om, oc, op, side, group0, A.pass,
-                                        A.colour, chain_word, A.rk, acc);
-      *reinterpret_cast<uint4 *>(C + off) = cn;
+      const uint4 cn = update16<SAMPLE, kBulkPair>(ce, om, oc, op, side, g, A.pass, A.colour,
+                                                   chain_word, A.rk, acc);
+      *reinterpret_cast<uint4 *>(Cp) = cn;
+      Cp += hstep;
+      g += gstep;
       om = oc;
       oc = op;
+    };
+    auto strip_loop = [&](auto par_tag) {
+      constexpr int P0 = decltype(par_tag)::value;
+      int it = 0;
+      for (; it + 4 <= n; it += 4) {
+        column(it, P0);
+        column(it + 1, P0 ^ 1);
+        column(it + 2, P0);
+        column(it + 3, P0 ^ 1);
+      }
+      for (; it < n; ++it) column(it, P0 ^ (it & 1));
+    };
+    if (par0) {
+      strip_loop(std::integral_constant<int, 1>{});
+    } else {
+      strip_loop(std::integral_constant<int, 0>{});
     }
   }
   long long ones = 0, bsum = 0;

@@ -1722,13 +1722,15 @@ inline AcceptTable make_accept_table(int dim, double J, double T, double mu) {
 // Colour c = (i + j [+ k]) & 1.  Sites of one colour are numbered by the
 // "plane index" q = (i >> 1) + (n0/2) * (j + n1 * k).  The acceptance uniform
 // of site q in pass t, colour c, chain ch is the 32-bit integer
-//     R = (r16 << 16) | r16'
+//     R = (rotl16(r16, 1) << 16) | r16'
+// (the rotation puts the low 15 bits of the lane on top, which is what the
+// kernels' packed 15-bit first-stage compare looks at)
 // where r16 is 16-bit lane (q & 7) of
 //   Philox4x32-10(counter = {lo32(q>>3), (hi32(q>>3)&0xff) | ch<<8, lo32(t),
 //                            (hi32(t)<<2) | c},          key = {lo32(seed), hi32(seed)})
 // (lane l = bits [16*(l&1), 16*(l&1)+16) of output word l>>1) and r16' is the
 // same lane of the call with counter word 3 | 2 ("refinement" stream; the
-// kernels only evaluate it when r16 ties with the top half of the threshold).
+// kernels only evaluate it when r16 & 0x7FFF ties with the top 15 bits of the threshold).
 // The site is flipped iff R <= thr_m1[b][n_up].
 // Requires even extents.  One pass = colour 0 half-sweep then colour 1.
 struct CheckerboardResult {
@@ -1748,7 +1750,8 @@ inline uint32_t checkerboard_uniform(uint64_t q, uint32_t chain, uint64_t pass_i
   const uint32_t w1 = Philox4x32::generate(ctr, key)[lane >> 1];
   const uint32_t r16 = (w0 >> (16 * (lane & 1))) & 0xffffu;
   const uint32_t r16b = (w1 >> (16 * (lane & 1))) & 0xffffu;
-  return (r16 << 16) | r16b;
+  const uint32_t lead = ((r16 << 1) | (r16 >> 15)) & 0xffffu;  // rotl16(r16, 1)
+  return (lead << 16) | r16b;
 }
 inline void checkerboard_pass(std::vector<int> &occ, std::vector<int> const &shape,
                               AcceptTable const &tab, uint64_t seed,

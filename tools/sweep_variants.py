@@ -25,11 +25,11 @@ def main():
     stream = torch.cuda.Stream()
     out = []
     cases = [
-        ("2d", [4096, 4096], 1, ["bulk2d:js=8", "bulk2d:js=16", "tile2d:p=3:nt=512"], 120),
-        ("2d_sweep8", [4096, 4096], 8, ["bulk2d:js=8", "bulk2d:js=16", "bulk2d:js=32", "tile2d:p=3:nt=512"], 48),
+        ("2d", [4096, 4096], 1, ["bulk2d", "bulk2d:js=8", "tile2d:p=3:nt=512"], 120),
+        ("2d_sweep8", [4096, 4096], 8, ["bulk2d", "bulk2d:js=16", "bulk2d:js=32", "tile2d:p=3:nt=512"], 48),
         ("2d_grid", [256, 256], 128, ["tile2d:nt=512"], 128),
-        ("2d_big", [16384, 16384], 1, ["bulk2d:js=16", "bulk2d:js=32"], 20),
-        ("3d", [512, 512, 512], 1, ["bulk3d:js=8"], 10),
+        ("2d_big", [16384, 16384], 1, ["bulk2d", "bulk2d:js=32"], 20),
+        ("3d", [512, 512, 512], 1, ["bulk3d", "bulk3d:js=8", "bulk3d:js=16"], 10),
     ]
     for name, shape, chains, variants, n_passes in cases:
         lat = IsingLatticeGPU(shape, n_chains=chains, J=0.1)
