@@ -95,6 +95,7 @@ struct cmg_context {
   int tile_passes = 3;   // passes per launch of the tiled kernel (halo = 2*P columns)
   int tile_threads = 512;
   int sm_count = 148;
+  bool bulk_attr_set = false;
   int js_auto[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // cached strip length per kernel variant
   size_t smem_optin = 0;
   long long launches = 0;
@@ -951,6 +952,15 @@ static int launch_half_sweep(cmg_context *c, int variant, int colour, unsigned l
   A.colour = colour;
   A.chain_offset = c->chain_offset;
   A.L.epoch = 2ull * pass + (unsigned long long)colour - c->slab_epoch_base;
+  if (!c->bulk_attr_set) {
+    // the staging rings may exceed the 48 KiB default dynamic shared-memory limit
+    cudaError_t e = cudaFuncSetAttribute(k_halfsweep_bulk2d<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBulk2d);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_halfsweep_bulk2d<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBulk2d);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_halfsweep_bulk3d<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBulk3d);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_halfsweep_bulk3d<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBulk3d);
+    if (e != cudaSuccess) return fail(c, CMG_ECUDA, cudaGetErrorString(e));
+    c->bulk_attr_set = true;
+  }
   A.js = pick_js(c, variant);
   const long long plane_size = c->n_sites / 2;
   dim3 block(128);

@@ -20,6 +20,14 @@
 
 #include <type_traits>
 
+// build-time tuning knobs (tools/ab_build.py compiles variants side by side)
+#ifndef CMG_BULK_CTAS
+#define CMG_BULK_CTAS 4  // resident CTAs per SM the bulk kernels are compiled for
+#endif
+#ifndef CMG_BULK_PAIR
+#define CMG_BULK_PAIR 1  // bulk kernels: 1 = pair table, 0 = two lane tables
+#endif
+
 namespace cmg {
 
 constexpr int kMaxIdx = 14;  // 2*(2*3+1)
@@ -378,7 +386,15 @@ __device__ __forceinline__ uint4 shift_down_1(uint4 v, uint32_t hi) {
 // the hot path does not have to keep them alive).
 __device__ __noinline__ uint4 resolve_ties16(uint4 idx4e, unsigned long long group0,
                                              unsigned long long pass, int colour,
-                                             uint32_t chain_word, const uint32_t *rk) {
+                                             uint32_t chain_word, uint32_t key0, uint32_t key1) {
+  // the round keys are rebuilt here (by value) so that the kernel parameter block
+  // never has its address taken -- that would copy it to local memory at entry
+  uint32_t rk[20];
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    rk[2 * r] = key0 + (uint32_t)r * kPhiloxW0;
+    rk[2 * r + 1] = key1 + (uint32_t)r * kPhiloxW1;
+  }
   const uint32_t iw[4] = {idx4e.x, idx4e.y, idx4e.z, idx4e.w};
   uint32_t m[4];
   for (int half = 0; half < 2; ++half) {
@@ -439,7 +455,7 @@ __device__ __forceinline__ uint4 update16(uint4 ce, uint4 om, uint4 oc, uint4 op
   }
   if (any_tie(tmax)) {  // a tie somewhere in these 16 sites (probability 16 * 2^-15)
     const uint4 mm = resolve_ties16(make_uint4(idx[0], idx[1], idx[2], idx[3]), group0, pass,
-                                    colour, chain_word, rk);
+                                    colour, chain_word, rk[0], rk[1]);
     m[0] = mm.x;
     m[1] = mm.y;
     m[2] = mm.z;
@@ -471,7 +487,7 @@ __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned l
 }
 // before reading halos: both neighbours must have finished half-sweep epoch-1
 __device__ __forceinline__ void slab_wait_neighbours(const LatticeView &L) {
-  if (L.epoch == 0) return;
+  if (L.epoch == 0 || (!L.wait_flag[0] && !L.wait_flag[1])) return;
   if (threadIdx.x == 0) {
     for (int side = 0; side < 2; ++side)
       if (L.wait_flag[side])
@@ -533,18 +549,19 @@ __device__ __forceinline__ uint32_t lds8_abs(uint32_t saddr) {
 // per-thread staging ring of the bulk kernels (128 threads per CTA): per stage
 // 128 x 16 B opposite-plane vectors, 128 x 16 B own-plane vectors, 128 x 4 B edge words
 constexpr int kBulkStages = 4;
-constexpr bool kBulkPair = false;  // bulk kernels: pair table (1 LDS / 2 sites) or lane tables
+constexpr bool kBulkPair = CMG_BULK_PAIR != 0;  // bulk kernels: pair table (1 LDS / 2 sites) or lane tables
 constexpr int kSmemRing = kBulkPair ? kSmemTile : 256;
 constexpr uint32_t kBulkStageBytes = 128u * 36u;
 constexpr int kSmemBulk2d = kSmemRing + kBulkStages * (int)kBulkStageBytes;
 
 template <bool SAMPLE>
-__global__ void __launch_bounds__(128) k_halfsweep_bulk2d(SweepArgs A) {
+__global__ void __launch_bounds__(128, CMG_BULK_CTAS) k_halfsweep_bulk2d(SweepArgs A) {
   const LatticeView &L = A.L;
   const int chain = blockIdx.y;
-  load_accept_table(A.tabs + chain, kBulkPair);
-  __syncthreads();
   slab_wait_neighbours(L);
+  // the table loads are issued first and only waited for (CTA barrier below)
+  // after the thread's pipeline has been filled
+  load_accept_table(A.tabs + chain, kBulkPair);
 
   const int h = L.h, n1 = L.n1;
   const int V = h >> 4;  // 16-byte vectors per column
@@ -553,12 +570,14 @@ __global__ void __launch_bounds__(128) k_halfsweep_bulk2d(SweepArgs A) {
   Accum acc = {0u, 0u, 0u, 0u, 0u};
   bool pushed = false;
 
-  if (t < (long long)V * n_strips) {
-    const int v = (int)(t % V);
-    const int strip = (int)(t / V);
+  {
+    // threads past the end of the lattice run the same code with zero columns
+    const bool active = t < (long long)V * n_strips;
+    const int v = active ? (int)(t % V) : 0;
+    const int strip = active ? (int)(t / V) : 0;
     const int p0 = v << 4;
     const int jbeg = strip * A.js;
-    const int jend = min(jbeg + A.js, n1);
+    const int jend = active ? min(jbeg + A.js, n1) : jbeg;
     uint8_t *C = L.planes + (long long)chain * L.chain_stride +
                  (long long)A.colour * L.plane_stride;
     const uint8_t *O = L.planes + (long long)chain * L.chain_stride +
@@ -612,10 +631,14 @@ __global__ void __launch_bounds__(128) k_halfsweep_bulk2d(SweepArgs A) {
       }
       cp_async_commit();
     };
-    uint4 om = ld16_nc(ocol(jbeg - 1) + p0);
-    uint4 oc = ld16_nc(O + (long long)h * jbeg + p0);
+    uint4 om = make_uint4(0u, 0u, 0u, 0u), oc = om;
+    if (n > 0) {
+      om = ld16_nc(ocol(jbeg - 1) + p0);
+      oc = ld16_nc(O + (long long)h * jbeg + p0);
+    }
 #pragma unroll
     for (int k = 0; k < kBulkStages; ++k) fetch(k, par0 ^ (k & 1));
+    __syncthreads();  // acceptance tables are in shared memory
     uint8_t *Cp = C + (long long)h * jbeg + p0;  // own plane, column j
     unsigned long long g = (unsigned long long)(((long long)h * jg0 + p0) >> 3);
     const unsigned int gstep = (unsigned int)h >> 3;
@@ -654,11 +677,11 @@ __global__ void __launch_bounds__(128) k_halfsweep_bulk2d(SweepArgs A) {
       strip_loop(std::integral_constant<int, 0>{});
     }
     // slab decomposition: the boundary columns also go to the neighbours' halos
-    if (push_lo && jbeg == 0) {
+    if (active && push_lo && jbeg == 0) {
       *reinterpret_cast<uint4 *>(push_lo + p0) = ld16(C + p0);
       pushed = true;
     }
-    if (push_hi && jend == n1) {
+    if (active && push_hi && jend == n1) {
       *reinterpret_cast<uint4 *>(push_hi + p0) = ld16(C + (long long)h * (n1 - 1) + p0);
       pushed = true;
     }
@@ -895,11 +918,10 @@ constexpr uint32_t kBulk3dStageBytes = 128u * 68u;
 constexpr int kSmemBulk3d = kSmemRing + kBulkStages * (int)kBulk3dStageBytes;
 
 template <bool SAMPLE>
-__global__ void __launch_bounds__(128) k_halfsweep_bulk3d(SweepArgs A) {
+__global__ void __launch_bounds__(128, CMG_BULK_CTAS) k_halfsweep_bulk3d(SweepArgs A) {
   const LatticeView &L = A.L;
   const int chain = blockIdx.y;
-  load_accept_table(A.tabs + chain, kBulkPair);
-  __syncthreads();
+  load_accept_table(A.tabs + chain, kBulkPair);  // waited for after the pipeline fill
 
   const int h = L.h, n1 = L.n1, n2 = L.n2;
   const int V = h >> 4;
@@ -907,14 +929,15 @@ __global__ void __launch_bounds__(128) k_halfsweep_bulk3d(SweepArgs A) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   Accum acc = {0u, 0u, 0u, 0u, 0u};
 
-  if (t < (long long)V * n_strips * n2) {
-    const int v = (int)(t % V);
-    const long long t2 = t / V;
+  {
+    const bool active = t < (long long)V * n_strips * n2;
+    const int v = active ? (int)(t % V) : 0;
+    const long long t2 = active ? t / V : 0;
     const int strip = (int)(t2 % n_strips);
     const int k = (int)(t2 / n_strips);
     const int p0 = v << 4;
     const int jbeg = strip * A.js;
-    const int jend = min(jbeg + A.js, n1);
+    const int jend = active ? min(jbeg + A.js, n1) : jbeg;
     const long long layer = (long long)h * n1;
     uint8_t *C = L.planes + (long long)chain * L.chain_stride +
                  (long long)A.colour * L.plane_stride + layer * k;
@@ -962,10 +985,14 @@ __global__ void __launch_bounds__(128) k_halfsweep_bulk3d(SweepArgs A) {
       }
       cp_async_commit();
     };
-    uint4 om = ld16_nc(O + (long long)h * wrapj(jbeg - 1) + p0);
-    uint4 oc = ld16_nc(O + col0);
+    uint4 om = make_uint4(0u, 0u, 0u, 0u), oc = om;
+    if (n > 0) {
+      om = ld16_nc(O + (long long)h * wrapj(jbeg - 1) + p0);
+      oc = ld16_nc(O + col0);
+    }
 #pragma unroll
     for (int kk = 0; kk < kBulkStages; ++kk) fetch(kk, par0 ^ (kk & 1));
+    __syncthreads();  // acceptance tables are in shared memory
     uint8_t *Cp = C + col0;
     unsigned long long g = (unsigned long long)((layer * k + col0) >> 3);
     const unsigned int gstep = (unsigned int)h >> 3;

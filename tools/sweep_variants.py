@@ -31,7 +31,13 @@ def main():
         ("2d_big", [16384, 16384], 1, ["bulk2d", "bulk2d:js=32"], 20),
         ("3d", [512, 512, 512], 1, ["bulk3d", "bulk3d:js=8", "bulk3d:js=16"], 10),
     ]
+    only = sys.argv[1].split(",") if len(sys.argv) > 1 else None  # e.g. "2d_sweep8,3d"
+    auto_only = len(sys.argv) > 2 and sys.argv[2] == "auto"       # first listed variant only
     for name, shape, chains, variants, n_passes in cases:
+        if only and name not in only:
+            continue
+        if auto_only:
+            variants = variants[:1]
         lat = IsingLatticeGPU(shape, n_chains=chains, J=0.1)
         lat.set_stream(stream.cuda_stream)
         lat.set_conditions(2633.0 if len(shape) == 2 else 5235.0, 0.0)
