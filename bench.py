@@ -258,22 +258,48 @@ def ours(args):
     acc_tc = lat.counters(i_tc)
 
     # ---- end to end through the C ABI with HOST buffers (H2D + D2H in the timed region)
+    # The lattices of a temperature sweep are independent, so the end-to-end leg
+    # drives them as E2E_GROUPS contexts (chains i*k .. i*k+k-1 each, same global
+    # Philox streams through set_chain_offset) on their own CUDA streams: the
+    # upload of one group overlaps the sweeps of another, and the downloads of the
+    # first groups overlap the sweeps of the last.
     per_lat = N0 * N1
     host_occ = torch.empty((n_lat, per_lat), dtype=torch.int32).pin_memory()
     for ch in range(n_lat):
         lat.download(ch, out=host_occ.numpy()[ch])
     host_out = torch.empty((n_lat, per_lat), dtype=torch.int32).pin_memory()
     e2e_steps = max(1, min(args.steps, 3))
+    n_groups = max(1, min(args.e2e_groups, n_lat))
+    while n_lat % n_groups:
+        n_groups -= 1
+    per_group = n_lat // n_groups
+    main_variant = lat.kernel_variant
+    lat.close()
+    groups = []
+    for g in range(n_groups):
+        st = torch.cuda.Stream()
+        lg = IsingLatticeGPU([N0, N1], n_chains=per_group, device=local_rank, J=J)
+        lg.set_stream(st.cuda_stream)
+        for k in range(per_group):
+            lg.set_conditions(T_SWEEP[g * per_group + k], mu, chain=k)
+        lg.seed_philox(0xC0FFEE + rank)
+        lg.set_chain_offset(g * per_group)
+        if args.e2e_variant != "auto":
+            lg.set_kernel_variant(args.e2e_variant)
+        groups.append(lg)
 
     def e2e_step():
-        for ch in range(n_lat):
-            lat.upload(host_occ.numpy()[ch], ch)  # H2D of the int32 occupation + colour-plane split
-        lat.clear_samples()
-        lat.run_passes(PASSES_PER_STEP, MODE_CHECKERBOARD, 1)
+        for g, lg in enumerate(groups):
+            for k in range(per_group):
+                # H2D of the int32 occupation + colour-plane split (async on the group's stream)
+                lg.upload(host_occ.numpy()[g * per_group + k], k)
+            lg.clear_samples()
+            lg.run_passes(PASSES_PER_STEP, MODE_CHECKERBOARD, 1)
         out = []
-        for ch in range(n_lat):
-            lat.download(ch, out=host_out.numpy()[ch])  # D2H of the final occupation
-            out.append(lat.samples_sb(ch))  # D2H of the sampled (S, B) series
+        for g, lg in enumerate(groups):
+            for k in range(per_group):
+                lg.download(k, out=host_out.numpy()[g * per_group + k])  # D2H of the final occupation
+                out.append(lg.samples_sb(k))  # D2H of the sampled (S, B) series
         return out
 
     e2e_step()
@@ -288,6 +314,9 @@ def ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_value = float(n_sites) * PASSES_PER_STEP * e2e_steps * world / e2e_s
+    e2e_launches = sum(lg.launch_count for lg in groups)
+    for lg in groups:
+        lg.close()
 
     # ---- the single 4096x4096 lattice at T_c on its own (tiled shared-memory kernel)
     single = IsingLatticeGPU([N0, N1], device=local_rank, J=J)
@@ -333,6 +362,10 @@ def ours(args):
             "h2d_bytes_per_step": 4 * n_sites,
             "d2h_bytes_per_step": 4 * n_sites + 16 * PASSES_PER_STEP * n_lat,
             "steps": e2e_steps,
+            "contexts": n_groups,
+            "gpu_launches": e2e_launches,
+            "note": "pinned int32 host buffers in and out through cmg_upload/download_occupation_i32; "
+                    f"{n_groups} contexts of {per_group} lattices on separate streams so copies overlap sweeps",
         },
         "gpu_launches": launches,
         "roofline": {
@@ -343,15 +376,15 @@ def ours(args):
             "unit": "GB/s",
             "frac": achieved / peak,
             # dram__bytes_read.sum + dram__bytes_write.sum of one k_halfsweep_bulk2d launch of this
-            # workload from the ncu --set full capture in profiles/ncu_bulk2d_sweep8_r1c.txt
-            # (134.59 MB + 68.72 MB); the 128 MiB of planes do not fit the L2, so every
-            # half-sweep streams from HBM and traffic ~= algorithmic bytes (201.3 MB)
-            "traffic": 203.3e6 if lat.kernel_variant == "bulk2d" else None,
-            "kernel": ("k_halfsweep_" if lat.kernel_variant.startswith("bulk") else "k_") + lat.kernel_variant,
+            # workload from the ncu --set full capture in profiles/ncu_bulk2d_sweep8_r1f.txt
+            # (134.3 MB read + 27.9 MB written back within the launch window; the rest of the
+            # 67 MB written stays dirty in the 126 MB L2 and is evicted by the next launch)
+            "traffic": 162.2e6 if main_variant == "bulk2d" else None,
+            "kernel": ("k_halfsweep_" if main_variant.startswith("bulk") else "k_") + main_variant,
             "algorithmic_bytes_per_launch": bytes_per_launch,
             "avg_launch_us": avg_launch_s * 1e6,
             "launches_per_step": n_launches_step,
-            "note": "3 B per attempted flip (int8, two colour planes); kernel is ALU-issue-bound (Philox4x32-10 + table compare), not HBM-bound: see DESIGN.md / profiles/",
+            "note": "3 B per attempted flip (int8, two colour planes); the kernel is bound by integer issue (Philox4x32-10: the IMAD.WIDE pipe is 60-66 % busy, issue slots 62-64 %), not by HBM: see DESIGN.md / profiles/",
         },
         "single_lattice": {"value": single_value, "unit": UNIT, "kernel": "k_" + single_variant, "workload": f"one {N0}x{N1} lattice at T=2633 K, sampling every pass", "frac_of_roofline": single_value * ALGO_BYTES_PER_ATTEMPT / 1e9 / peak},
         "wall_s_timed_region": t_wall,
@@ -376,6 +409,8 @@ def ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--e2e-groups", type=int, default=4, help="contexts the end-to-end leg splits the lattices into")
+    ap.add_argument("--e2e-variant", default="bulk2d", help="kernel variant of the end-to-end contexts (concurrent streams: the strip kernel co-schedules, the one-CTA-per-SM tile kernel does not)")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
