@@ -852,14 +852,62 @@ __global__ void __launch_bounds__(NT, 1) k_tile2d(TileArgs A) {
       sts16(cbase + col_off + p0, cn);
     };
     if (NT % V == 0) {
-      // each thread keeps its vector offset and strides over columns
-      const int p0 = (threadIdx.x % V) << 4;
-      const int cstep = NT / V;
-      int dc0 = threadIdx.x / V;
-      // short columns (V < 32): a warp spans 32/V columns; hand it columns of one
-      // parity (c, c+2, ...) so the parity branch in process() stays warp-uniform
-      if (V < 32 && (cstep & 7) == 0) dc0 = 2 * (dc0 % (cstep >> 1)) + dc0 / (cstep >> 1);
-      for (int dc = dc0; dc < hi - lo; dc += cstep) process(lo + dc, dc, p0);
+      // Each thread keeps its vector offset and walks a contiguous run of columns
+      // with the three opposite-colour columns in a register rolling window (two
+      // LDS.128 per 16 sites instead of four), shared-memory offsets and the Philox
+      // group advanced incrementally, and the column parity static per copy of the
+      // body (columns are taken in pairs).
+      const int Q = NT / V, q = threadIdx.x / V;
+      const uint32_t p0 = (uint32_t)(threadIdx.x % V) << 4;
+      const int ncols = hi - lo, base = ncols / Q, rem = ncols - base * Q;
+      int cl = lo + q * base + min(q, rem);
+      const int cl1 = cl + base + (q < rem ? 1 : 0);
+      if (cl < cl1) {
+        int gc = gc_lo + (cl - lo);
+        gc -= (gc >= n1) ? n1 : 0;
+        const uint32_t gstep = (uint32_t)h >> 3;
+        unsigned long long g = (unsigned long long)gstep * (uint32_t)gc + (p0 >> 3);
+        const unsigned long long gwrap = (unsigned long long)gstep * (uint32_t)n1;
+        uint32_t coff = (uint32_t)(cl * h);  // byte offset of column cl inside a plane
+        const uint32_t e_lo = (p0 == 0) ? (uint32_t)h - 1u : p0 - 1u;
+        const uint32_t e_hi = (p0 + 16u == (uint32_t)h) ? 0u : p0 + 16u;
+        const uint32_t wrap_off = (uint32_t)((W - 1) * h);
+        uint4 om = lds16(obase + ((periodic && cl == 0) ? wrap_off : coff - (uint32_t)h) + p0);
+        uint4 oc = lds16(obase + coff + p0);
+        auto item = [&](const int par) {
+          const uint32_t noff = (periodic && cl == W - 1) ? 0u : coff + (uint32_t)h;
+          const uint4 op = lds16(obase + noff + p0);
+          const uint4 ce = lds16(cbase + coff + p0);
+          const uint32_t eb = cmg_smem[obase + coff + (par ? e_hi : e_lo)];
+          const uint4 side = par ? shift_down_1(oc, eb) : shift_up_1(oc, eb);
+          const bool owned = periodic || (cl >= H && cl < H + TW);
+          uint4 cn;
+          if (sample && owned) {
+            cn = update16<true, true>(ce, om, oc, op, side, g, pass, colour, chain_word, A.rk, acc);
+          } else {
+            Accum scratch = {0u, 0u, 0u, 0u, 0u};
+            cn = update16<false, true>(ce, om, oc, op, side, g, pass, colour, chain_word, A.rk,
+                                       scratch);
+            if (owned) acc.acc += scratch.acc;
+          }
+          sts16(cbase + coff + p0, cn);
+          om = oc;
+          oc = op;
+          coff += (uint32_t)h;
+          g += gstep;
+          ++cl;
+          if (++gc == n1) {  // halo columns past the lattice edge wrap around
+            gc = 0;
+            g -= gwrap;
+          }
+        };
+        if ((gc + colour) & 1) item(1);  // i = 2p + par; align the pair loop to par = 0
+        while (cl + 2 <= cl1) {
+          item(0);
+          item(1);
+        }
+        if (cl < cl1) item(0);
+      }
     } else {
       const int items = (hi - lo) * V;
       for (int it = threadIdx.x; it < items; it += NT) {
