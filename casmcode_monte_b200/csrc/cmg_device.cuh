@@ -917,15 +917,17 @@ __global__ void __launch_bounds__(NT, 1) k_tile2d(TileArgs A) {
     }
     n_acc += acc.acc;
     if (sample) {
-      // warp partial sums -> per-pass shared accumulators (flushed once at the end)
-      long long ones, bsum;
-      accum_finish(acc, 4, ones, bsum);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        ones += __shfl_xor_sync(0xffffffffu, ones, o);
-        bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
-      }
+      // warp partial sums (hardware integer reduction of the raw byte sums) ->
+      // per-pass shared accumulators (flushed once at the end)
+      Accum wa;
+      wa.acc = 0u;
+      wa.c1 = __reduce_add_sync(0xffffffffu, acc.c1);
+      wa.opp = __reduce_add_sync(0xffffffffu, acc.opp);
+      wa.u7 = __reduce_add_sync(0xffffffffu, acc.u7);
+      wa.sites = __reduce_add_sync(0xffffffffu, acc.sites);
       if ((threadIdx.x & 31) == 0) {
+        long long ones, bsum;
+        accum_finish(wa, 4, ones, bsum);
         atomicAdd(reinterpret_cast<unsigned long long *>(&s_acc[2 * slot]), (unsigned long long)ones);
         atomicAdd(reinterpret_cast<unsigned long long *>(&s_acc[2 * slot + 1]), (unsigned long long)bsum);
       }
