@@ -683,13 +683,16 @@ int cmg_randomize_occupation(cmg_context *c, int chain, uint64_t seed, double p_
     rc = sync_nat_from_planes(c);
     if (rc) return rc;
   }
+  // slabs key the draw on global site indices (n0 * col_begin is a multiple of 4:
+  // n0 and col_begin are even)
+  const long long g_offset = c->slab ? (long long)c->shape[0] * c->col_begin / 4 : 0;
   for (int ch = lo; ch < hi; ++ch) {
     if (scaled < 1.0) {
       CU(c, cudaMemsetAsync(c->d_nat + ch * c->n_sites, 0, (size_t)c->n_sites, c->stream));
     } else {
       k_randomize_natural<<<nblocks((c->n_sites + 3) / 4, 256), 256, 0, c->stream>>>(
           c->d_nat + ch * c->n_sites, c->n_sites, seed + 0x9E3779B97F4A7C15ull * (uint64_t)ch,
-          thr, always);
+          thr, always, g_offset);
       ++c->launches;
     }
   }

@@ -1162,16 +1162,20 @@ __global__ void k_fill_bytes(uint8_t *dst, long long n, uint8_t v) {
   if (i < n) dst[i] = v;
 }
 // synthetic input: i.i.d. b with P(b=1) = p_up, keyed on the natural index
+// g_offset: index of the context's first group of four sites in the GLOBAL
+// lattice (a slab starts at column col_begin), so a decomposed lattice draws the
+// same initial state as the undecomposed one
 __global__ void k_randomize_natural(uint8_t *nat, long long n, unsigned long long seed,
-                                    uint32_t thr_m1, int always) {
+                                    uint32_t thr_m1, int always, long long g_offset) {
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (4 * g >= n) return;
+  const long long gg = g + g_offset;
   uint32_t rk[20];
   for (int i = 0; i < 10; ++i) {
     rk[2 * i] = (uint32_t)seed + i * kPhiloxW0;
     rk[2 * i + 1] = (uint32_t)(seed >> 32) + i * kPhiloxW1;
   }
-  const uint4 r = philox4x32_10(make_uint4((uint32_t)g, (uint32_t)(g >> 32), 0x5EEDu, 0u), rk);
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)gg, (uint32_t)(gg >> 32), 0x5EEDu, 0u), rk);
   const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
   for (int w = 0; w < 4; ++w)
     if (4 * g + w < n) nat[4 * g + w] = (uint8_t)(always || rr[w] <= thr_m1);

@@ -101,3 +101,67 @@ def test_chain_grid_sharding_is_invisible():
         assert merged == whole
     # physics sanity: x increases with mu at fixed T, and is 1/2 at mu = 0 by symmetry within noise
     assert whole[3]["mean_param_composition"] < whole[5]["mean_param_composition"]
+
+
+def test_full_size_65536_decomposition_is_invisible():
+    """BASELINE config 5 at its full size (65536 x 65536 = 4.3e9 sites) on ONE GPU,
+    with no host copy of the lattice: the undecomposed run and a two-slab run with
+    fused peer halo pushes (same device) start from the same device-generated
+    state (the draw is keyed on global site indices) and must produce the same
+    integer sample series (S, B), acceptance counts and final observables."""
+    import torch
+
+    import casmcode_monte_b200 as cm
+    from casmcode_monte_b200.parallel import GpuSlabEngine, slab_columns
+
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40 << 30:
+        pytest.skip("needs ~30 GB of device memory")
+    shape = [65536, 65536]
+    n0, n1 = shape
+    n = n0 * n1
+    T, mu, seed, n_passes = 2633.0, 0.01, 0xC0FFEE, 2
+
+    lat = cm.IsingLatticeGPU(shape, J=J)
+    lat.set_conditions(T, mu)
+    lat.seed_philox(seed)
+    lat.randomize(777, 0.5)
+    S0, B0 = lat.sample_now()
+    assert abs(S0) < 1e-3 * n and abs(B0) < 1e-3 * n  # an i.i.d. +-1 state
+    lat.run_passes(n_passes, cm.MODE_CHECKERBOARD, 1)
+    assert lat.kernel_variant == "bulk2d"
+    S_ref, B_ref = lat.samples_sb()
+    acc_ref = lat.counters()
+    assert acc_ref[1] + acc_ref[2] == n_passes * n
+    assert lat.sample_now() == (int(S_ref[-1]), int(B_ref[-1]))  # fused sampling == reduction of the state
+    assert B_ref[-1] > B_ref[0] > B0  # relaxing towards order at T_c from a random state
+    lat.close()
+    del lat
+    torch.cuda.empty_cache()
+
+    engines = []
+    for r in range(2):
+        cb, nc = slab_columns(n1, 2, r)
+        e = GpuSlabEngine(shape, cb, nc, J, T, mu, seed)
+        e.lat.randomize(777, 0.5)
+        engines.append(e)
+    assert sum(e.observables()[0] + e.lat.n_sites for e in engines) - n == S0
+    for colour in (0, 1):
+        for r, e in enumerate(engines):
+            engines[(r - 1) % 2].halo(colour, 1).copy_(e.boundary(colour, 0))
+            engines[(r + 1) % 2].halo(colour, 0).copy_(e.boundary(colour, 1))
+    torch.cuda.synchronize()
+    for r, e in enumerate(engines):
+        e.lat.slab_ipc_attach(0, peer=engines[(r - 1) % 2].lat)
+        e.lat.slab_ipc_attach(1, peer=engines[(r + 1) % 2].lat)
+    for t in range(n_passes):
+        for colour in (0, 1):
+            for e in engines:
+                e.half_sweep(colour, t, sample=(colour == 1))
+    torch.cuda.synchronize()
+    S = sum(e.lat.samples_sb()[0] + e.lat.n_sites for e in engines) - n
+    B = sum(e.lat.samples_sb()[1] for e in engines)
+    assert np.array_equal(S, S_ref) and np.array_equal(B, B_ref)
+    assert sum(e.counters()[1] for e in engines) == acc_ref[1]
+    for e in engines:
+        e.lat.close()
