@@ -35,7 +35,7 @@ def main():
         if check:
             eng.upload(full[n0 * cb : n0 * (cb + nc)])
         else:
-            eng.lat.randomize(99 + rank, 0.5)
+            eng.lat.randomize(99, 0.5)  # keyed on global site indices: one i.i.d. state over all slabs
         ring = SlabRing(eng, rank, world, dist, transport=transport)
         ring.prime()
         torch.cuda.synchronize()
