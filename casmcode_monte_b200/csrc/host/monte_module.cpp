@@ -14,6 +14,7 @@
 #include <pybind11/stl_bind.h>
 
 #include "casm_monte_b200/monte.hh"
+#include "casm_monte_b200/run_management.hh"
 
 namespace py = pybind11;
 using namespace casm_monte_b200;
@@ -26,20 +27,20 @@ typedef std::map<std::string, bool> BooleanValueMap;
 
 // JSON-valued sampling (include/casm/monte/sampling/StateSamplingFunction.hh:79-95,
 // Sampler.hh:114-117): JSON values are Python objects here.
-struct jsonStateSamplingFunction {
+struct PyJsonStateSamplingFunction {
   std::string name, description;
   py::object function;
 };
-struct jsonSampler {
+struct PyJsonSampler {
   py::list values;
 };
-typedef std::map<std::string, jsonStateSamplingFunction> jsonStateSamplingFunctionMap;
-typedef std::map<std::string, jsonSampler> jsonSamplerMap;
+typedef std::map<std::string, PyJsonStateSamplingFunction> PyJsonStateSamplingFunctionMap;
+typedef std::map<std::string, PyJsonSampler> PyJsonSamplerMap;
 
 // per-run extras that live next to SemiGrandCanonicalData in the binding
 struct RunExtras {
-  jsonStateSamplingFunctionMap json_sampling_functions;
-  jsonSamplerMap json_samplers;
+  PyJsonStateSamplingFunctionMap json_sampling_functions;
+  PyJsonSamplerMap json_samplers;
 };
 // Keyed by the data object's address.  Deliberately leaked: it holds Python
 // objects, which must not be released after the interpreter has shut down.
@@ -56,9 +57,10 @@ static void register_extras(SemiGrandCanonicalData const *d, std::shared_ptr<Run
 
 PYBIND11_MAKE_OPAQUE(SamplerMap);
 PYBIND11_MAKE_OPAQUE(StateSamplingFunctionMap);
-PYBIND11_MAKE_OPAQUE(jsonStateSamplingFunctionMap);
-PYBIND11_MAKE_OPAQUE(jsonSamplerMap);
+PYBIND11_MAKE_OPAQUE(PyJsonStateSamplingFunctionMap);
+PYBIND11_MAKE_OPAQUE(PyJsonSamplerMap);
 PYBIND11_MAKE_OPAQUE(RequestedPrecisionMap);
+PYBIND11_MAKE_OPAQUE(ResultsAnalysisFunctionMap);
 PYBIND11_MAKE_OPAQUE(ScalarValueMap);
 PYBIND11_MAKE_OPAQUE(VectorValueMap);
 PYBIND11_MAKE_OPAQUE(BooleanValueMap);
@@ -564,21 +566,21 @@ PYBIND11_MODULE(_monte_b200, m) {
       .def("__call__", [](StateSamplingFunction const &f) { return as_array(f()); });
   py::bind_map<StateSamplingFunctionMap>(m, "StateSamplingFunctionMap");
 
-  py::class_<jsonStateSamplingFunction>(m, "jsonStateSamplingFunction")
+  py::class_<PyJsonStateSamplingFunction>(m, "jsonStateSamplingFunction")
       .def(py::init([](std::string name, std::string description, py::object function) {
-             return jsonStateSamplingFunction{name, description, function};
+             return PyJsonStateSamplingFunction{name, description, function};
            }),
            py::arg("name"), py::arg("description"), py::arg("function"))
-      .def_readwrite("name", &jsonStateSamplingFunction::name)
-      .def_readwrite("description", &jsonStateSamplingFunction::description)
-      .def_readwrite("function", &jsonStateSamplingFunction::function)
-      .def("__call__", [](jsonStateSamplingFunction const &f) { return f.function(); });
-  py::bind_map<jsonStateSamplingFunctionMap>(m, "jsonStateSamplingFunctionMap");
-  py::class_<jsonSampler>(m, "jsonSampler")
+      .def_readwrite("name", &PyJsonStateSamplingFunction::name)
+      .def_readwrite("description", &PyJsonStateSamplingFunction::description)
+      .def_readwrite("function", &PyJsonStateSamplingFunction::function)
+      .def("__call__", [](PyJsonStateSamplingFunction const &f) { return f.function(); });
+  py::bind_map<PyJsonStateSamplingFunctionMap>(m, "jsonStateSamplingFunctionMap");
+  py::class_<PyJsonSampler>(m, "jsonSampler")
       .def(py::init<>())
-      .def_readwrite("values", &jsonSampler::values)
-      .def("to_list", [](jsonSampler const &s) { return py::list(s.values); });
-  py::bind_map<jsonSamplerMap>(m, "jsonSamplerMap");
+      .def_readwrite("values", &PyJsonSampler::values)
+      .def("to_list", [](PyJsonSampler const &s) { return py::list(s.values); });
+  py::bind_map<PyJsonSamplerMap>(m, "jsonSamplerMap");
 
   py::class_<RequestedPrecision>(m, "RequestedPrecision")
       .def(py::init([](std::optional<double> abs, std::optional<double> rel) {
@@ -829,12 +831,12 @@ PYBIND11_MODULE(_monte_b200, m) {
       }, py::arg("occ_event"));
 
   py::class_<SemiGrandCanonicalData, std::shared_ptr<SemiGrandCanonicalData>>(m, "SemiGrandCanonicalData")
-      .def(py::init([](StateSamplingFunctionMap const &sf, jsonStateSamplingFunctionMap const &jsf,
+      .def(py::init([](StateSamplingFunctionMap const &sf, PyJsonStateSamplingFunctionMap const &jsf,
                        CountType n_steps_per_pass, CompletionCheckParams const &p) {
              auto d = std::make_shared<SemiGrandCanonicalData>(sf, n_steps_per_pass, p);
              auto ex = std::make_shared<RunExtras>();
              ex->json_sampling_functions = jsf;
-             for (auto const &kv : jsf) ex->json_samplers.emplace(kv.first, jsonSampler());
+             for (auto const &kv : jsf) ex->json_samplers.emplace(kv.first, PyJsonSampler());
              register_extras(d.get(), ex);
              return d;
            }),
@@ -845,7 +847,7 @@ PYBIND11_MODULE(_monte_b200, m) {
       .def_property_readonly("json_sampling_functions", [](SemiGrandCanonicalData const &d) {
         return extras_registry().at(&d)->json_sampling_functions;
       })
-      .def_property_readonly("json_samplers", [](SemiGrandCanonicalData const &d) -> jsonSamplerMap & {
+      .def_property_readonly("json_samplers", [](SemiGrandCanonicalData const &d) -> PyJsonSamplerMap & {
         return extras_registry().at(&d)->json_samplers;
       }, py::return_value_policy::reference)
       .def_readwrite("sample_weight", &SemiGrandCanonicalData::sample_weight)
@@ -901,7 +903,7 @@ PYBIND11_MODULE(_monte_b200, m) {
         return fns;
       })
       .def("default_json_sampling_functions", [](py::object self) {
-        jsonStateSamplingFunctionMap fns;
+        PyJsonStateSamplingFunctionMap fns;
         py::object weak = py::module_::import("weakref").attr("ref")(self);
         py::object f = py::cpp_function([weak]() -> py::object {
           py::object mc = weak();
@@ -911,12 +913,12 @@ PYBIND11_MODULE(_monte_b200, m) {
             throw std::runtime_error("Error in configuration sampling function: mc_calculator->state == nullptr");
           return config_to_dict(c.state->configuration);
         });
-        fns.emplace("configuration", jsonStateSamplingFunction{"configuration", "Configuration values", f});
+        fns.emplace("configuration", PyJsonStateSamplingFunction{"configuration", "Configuration values", f});
         return fns;
       })
       .def("run", [](std::shared_ptr<calculator_type> mc, IsingState &state,
                      StateSamplingFunctionMap const &sampling_functions,
-                     jsonStateSamplingFunctionMap const &json_sampling_functions,
+                     PyJsonStateSamplingFunctionMap const &json_sampling_functions,
                      CompletionCheckParams const &completion_check_params,
                      event_generator_type const &event_generator, int sample_period,
                      std::optional<MethodLog> method_log, std::optional<PyEngine> random_engine,
@@ -924,7 +926,7 @@ PYBIND11_MODULE(_monte_b200, m) {
         if (update_mode.has_value()) mc->update_mode = *update_mode;
         auto extras = std::make_shared<RunExtras>();
         extras->json_sampling_functions = json_sampling_functions;
-        for (auto const &kv : json_sampling_functions) extras->json_samplers.emplace(kv.first, jsonSampler());
+        for (auto const &kv : json_sampling_functions) extras->json_samplers.emplace(kv.first, PyJsonSampler());
         calculator_type::write_status_type wsf;
         if (write_status_f.is_none()) {
           wsf = default_write_status;
@@ -961,4 +963,309 @@ PYBIND11_MODULE(_monte_b200, m) {
            py::arg("write_status_f") = py::none(), py::arg("update_mode") = py::none());
 
   m.def("default_write_status", &default_write_status, py::arg("mc_calculator"), py::arg("method_log"));
+
+  // ------------------------------------------------- sampling schedules
+  // python/src/monte_sampling.cpp:414-742
+  py::enum_<SAMPLE_MODE>(m, "SAMPLE_MODE")
+      .value("BY_PASS", SAMPLE_MODE::BY_PASS)
+      .value("BY_STEP", SAMPLE_MODE::BY_STEP)
+      .value("BY_TIME", SAMPLE_MODE::BY_TIME)
+      .export_values();
+  py::enum_<SAMPLE_METHOD>(m, "SAMPLE_METHOD")
+      .value("LINEAR", SAMPLE_METHOD::LINEAR)
+      .value("LOG", SAMPLE_METHOD::LOG)
+      .value("CUSTOM", SAMPLE_METHOD::CUSTOM)
+      .export_values();
+  py::class_<SamplingParams>(m, "SamplingParams")
+      .def(py::init([](std::vector<std::string> sampler_names, std::vector<std::string> json_sampler_names,
+                       SAMPLE_MODE sample_mode, SAMPLE_METHOD sample_method, double period,
+                       std::optional<double> begin, double base, double shift, py::object custom_sample_at,
+                       bool stochastic_sample_period, bool do_sample_trajectory, bool do_sample_time) {
+             // make_sampling_params, python/src/monte_sampling.cpp:49-88
+             if (!begin.has_value()) begin = (sample_method == SAMPLE_METHOD::LINEAR) ? period : 0.0;
+             if (sample_method == SAMPLE_METHOD::CUSTOM && custom_sample_at.is_none())
+               throw std::runtime_error(
+                   "Error in make_sampling_params: sample_method==SAMPLE_METHOD::CUSTOM and "
+                   "!custom_sample_at.has_value()");
+             SamplingParams s;
+             s.sampler_names = sampler_names;
+             s.json_sampler_names = json_sampler_names;
+             s.sample_mode = sample_mode;
+             s.sample_method = sample_method;
+             s.period = period;
+             s.begin = begin.value();
+             s.base = base;
+             s.shift = shift;
+             if (!custom_sample_at.is_none())
+               s.custom_sample_at = [custom_sample_at](CountType n) {
+                 py::gil_scoped_acquire gil;
+                 return custom_sample_at(n).cast<double>();
+               };
+             s.stochastic_sample_period = stochastic_sample_period;
+             s.do_sample_trajectory = do_sample_trajectory;
+             s.do_sample_time = do_sample_time;
+             return s;
+           }),
+           py::arg("sampler_names") = std::vector<std::string>(),
+           py::arg("json_sampler_names") = std::vector<std::string>(),
+           py::arg("sample_mode") = SAMPLE_MODE::BY_PASS, py::arg("sample_method") = SAMPLE_METHOD::LINEAR,
+           py::arg("period") = 1.0, py::arg("begin") = py::none(), py::arg("base") = std::pow(10.0, 1.0 / 10.0),
+           py::arg("shift") = 0.0, py::arg("custom_sample_at") = py::none(),
+           py::arg("stochastic_sample_period") = false, py::arg("do_sample_trajectory") = false,
+           py::arg("do_sample_time") = false)
+      .def_readwrite("sample_mode", &SamplingParams::sample_mode)
+      .def_readwrite("sample_method", &SamplingParams::sample_method)
+      .def_readwrite("begin", &SamplingParams::begin)
+      .def_readwrite("period", &SamplingParams::period)
+      .def_readwrite("base", &SamplingParams::base)
+      .def_readwrite("shift", &SamplingParams::shift)
+      .def_readwrite("sampler_names", &SamplingParams::sampler_names)
+      .def_readwrite("json_sampler_names", &SamplingParams::json_sampler_names)
+      .def_readwrite("stochastic_sample_period", &SamplingParams::stochastic_sample_period)
+      .def_readwrite("do_sample_trajectory", &SamplingParams::do_sample_trajectory)
+      .def_readwrite("do_sample_time", &SamplingParams::do_sample_time)
+      .def("append_to_sampler_names", [](SamplingParams &s, std::string name) { s.sampler_names.push_back(name); },
+           py::arg("name"))
+      .def("remove_from_sampler_names",
+           [](SamplingParams &s, std::string name) {
+             auto it = std::find(s.sampler_names.begin(), s.sampler_names.end(), name);
+             if (it != s.sampler_names.end()) s.sampler_names.erase(it);
+           },
+           py::arg("name"))
+      .def("extend_sampler_names",
+           [](SamplingParams &s, std::vector<std::string> names) {
+             s.sampler_names.insert(s.sampler_names.end(), names.begin(), names.end());
+           },
+           py::arg("names"))
+      .def("append_to_json_sampler_names",
+           [](SamplingParams &s, std::string name) { s.json_sampler_names.push_back(name); }, py::arg("name"))
+      .def("remove_from_json_sampler_names",
+           [](SamplingParams &s, std::string name) {
+             auto it = std::find(s.json_sampler_names.begin(), s.json_sampler_names.end(), name);
+             if (it != s.json_sampler_names.end()) s.json_sampler_names.erase(it);
+           },
+           py::arg("name"))
+      .def("extend_json_sampler_names",
+           [](SamplingParams &s, std::vector<std::string> names) {
+             s.json_sampler_names.insert(s.json_sampler_names.end(), names.begin(), names.end());
+           },
+           py::arg("names"))
+      .def("sample_at", [](SamplingParams const &s, CountType i) { return sample_at(i, s); },
+           py::arg("sample_index"));
+  m.def("sample_at", [](CountType i, SamplingParams const &s) { return sample_at(i, s); },
+        py::arg("sample_index"), py::arg("sampling_params"));
+  m.def("stochastic_count_step",
+        [](double rate, RandomNumberGenerator<> &rng) { return stochastic_count_step(rate, rng); },
+        py::arg("sample_rate"), py::arg("random_number_generator"));
+  m.def("stochastic_time_step",
+        [](double rate, RandomNumberGenerator<> &rng) { return stochastic_time_step(rate, rng); },
+        py::arg("sample_rate"), py::arg("random_number_generator"));
+
+  // ------------------------------------------------- run management
+  typedef RunManager<default_engine_type> run_manager_type;
+  typedef SamplingFixture<default_engine_type> fixture_type;
+  py::class_<MonteCounter>(m, "MonteCounter")
+      .def(py::init<>())
+      .def_readonly("sample_mode", &MonteCounter::sample_mode)
+      .def_readonly("steps_per_pass", &MonteCounter::steps_per_pass)
+      .def_readonly("step", &MonteCounter::step)
+      .def_readonly("pass_", &MonteCounter::pass)
+      .def_readonly("count", &MonteCounter::count)
+      .def_readonly("time", &MonteCounter::time)
+      .def_readonly("n_accept", &MonteCounter::n_accept)
+      .def_readonly("n_reject", &MonteCounter::n_reject)
+      .def("reset", &MonteCounter::reset, py::arg("sample_mode"), py::arg("steps_per_pass"))
+      .def("increment_step", &MonteCounter::increment_step)
+      .def("increment_n_accept", &MonteCounter::increment_n_accept)
+      .def("increment_n_reject", &MonteCounter::increment_n_reject)
+      .def("advance_passes", &MonteCounter::advance_passes, py::arg("n_passes"), py::arg("d_accept"),
+           py::arg("d_reject"));
+
+  py::class_<Results>(m, "Results")
+      .def_readonly("sampler_names", &Results::sampler_names)
+      .def_readonly("json_sampler_names", &Results::json_sampler_names)
+      .def_readonly("sampling_functions", &Results::sampling_functions)
+      .def_readonly("analysis_functions", &Results::analysis_functions)
+      .def_readonly("samplers", &Results::samplers)
+      .def_property_readonly("json_samplers",
+                             [](Results const &r) {
+                               py::object loads = py::module_::import("json").attr("loads");
+                               py::dict d;
+                               for (auto const &kv : r.json_samplers) {
+                                 py::list l;
+                                 for (auto const &text : kv.second->values) l.append(loads(text));
+                                 d[py::str(kv.first)] = l;
+                               }
+                               return d;
+                             })
+      .def_property_readonly("analysis",
+                             [](Results const &r) {
+                               py::dict d;
+                               for (auto const &kv : r.analysis) d[py::str(kv.first)] = as_array(kv.second);
+                               return d;
+                             })
+      .def_readonly("sample_count", &Results::sample_count)
+      .def_readonly("sample_time", &Results::sample_time)
+      .def_readonly("sample_weight", &Results::sample_weight)
+      .def_readonly("sample_clocktime", &Results::sample_clocktime)
+      .def_property_readonly("sample_trajectory",
+                             [](Results const &r) {
+                               py::list l;
+                               for (auto const &occ : r.sample_trajectory) {
+                                 py::array_t<int> a(occ.size());
+                                 std::copy(occ.begin(), occ.end(), a.mutable_data());
+                                 l.append(a);
+                               }
+                               return l;
+                             })
+      .def_readonly("completion_check_results", &Results::completion_check_results)
+      .def_readonly("n_accept", &Results::n_accept)
+      .def_readonly("n_reject", &Results::n_reject)
+      .def_readonly("elapsed_clocktime", &Results::elapsed_clocktime)
+      .def_readonly("initial_memory_used_MiB", &Results::initial_memory_used_MiB)
+      .def_readonly("final_memory_used_MiB", &Results::final_memory_used_MiB)
+      .def("is_auto_converge_mode", [](Results const &r) { return is_auto_converge_mode(r); })
+      .def("N_samples", [](Results const &r) { return N_samples(r); })
+      .def("N_samples_for_statistics", [](Results const &r) { return N_samples_for_statistics(r); })
+      .def("N_samples_for_all_to_equilibrate", [](Results const &r) { return N_samples_for_all_to_equilibrate(r); })
+      .def("all_equilibrated", [](Results const &r) { return all_equilibrated(r); })
+      .def("all_converged", [](Results const &r) { return all_converged(r); })
+      .def("acceptance_rate", [](Results const &r) { return acceptance_rate(r); })
+      // Results.hh:217-330: per-component statistics as written to summary.json
+      .def("quantity_stats", [](Results const &r, std::string const &name) {
+        QuantityStats q(name, *r.samplers.at(name), r);
+        py::dict d;
+        d["shape"] = q.shape;
+        d["is_scalar"] = q.is_scalar;
+        d["component_names"] = q.component_names;
+        py::list conv, stats;
+        for (auto const &c : q.is_converged) conv.append(c.has_value() ? py::object(py::bool_(*c)) : py::object(py::none()));
+        for (auto const &st : q.component_stats) {
+          if (st.has_value()) {
+            py::dict sd;
+            sd["mean"] = st->mean;
+            sd["calculated_precision"] = st->calculated_precision;
+            stats.append(sd);
+          } else {
+            stats.append(py::none());
+          }
+        }
+        d["is_converged"] = conv;
+        d["component_stats"] = stats;
+        return d;
+      }, py::arg("quantity_name"));
+
+  py::class_<ResultsAnalysisFunction>(m, "ResultsAnalysisFunction")
+      .def(py::init([](std::string name, std::string description, std::vector<Index> shape, py::object function,
+                       std::optional<std::vector<std::string>> component_names) {
+             auto f = [function](Results const &results) -> std::vector<double> {
+               py::gil_scoped_acquire gil;
+               return to_dvec(function(py::cast(&results, py::return_value_policy::reference)));
+             };
+             return ResultsAnalysisFunction(name, description, shape, f, component_names);
+           }),
+           py::arg("name"), py::arg("description"), py::arg("shape"), py::arg("function"),
+           py::arg("component_names") = py::none())
+      .def_readwrite("name", &ResultsAnalysisFunction::name)
+      .def_readwrite("description", &ResultsAnalysisFunction::description)
+      .def_readwrite("shape", &ResultsAnalysisFunction::shape)
+      .def_readwrite("component_names", &ResultsAnalysisFunction::component_names)
+      .def("__call__", [](ResultsAnalysisFunction const &f, Results const &r) { return as_array(f(r)); });
+  py::bind_map<ResultsAnalysisFunctionMap>(m, "ResultsAnalysisFunctionMap");
+  m.def("make_heat_capacity_f", &make_heat_capacity_f, py::arg("mc_calculator"));
+  m.def("make_susceptibility_f", &make_susceptibility_f, py::arg("mc_calculator"));
+
+  py::class_<SamplingFixtureParams>(m, "SamplingFixtureParams")
+      .def(py::init([](std::string label, StateSamplingFunctionMap const &sampling_functions,
+                       PyJsonStateSamplingFunctionMap const &json_sampling_functions,
+                       ResultsAnalysisFunctionMap const &analysis_functions, SamplingParams const &sampling_params,
+                       CompletionCheckParams const &completion_check_params, std::vector<std::string> analysis_names,
+                       py::object results_io, std::optional<MethodLog> method_log) {
+             // JSON-valued functions return Python objects; the fixture stores JSON text
+             casm_monte_b200::jsonStateSamplingFunctionMap jfs;
+             for (auto const &kv : json_sampling_functions) {
+               py::object pyf = kv.second.function;
+               jfs.emplace(kv.first, casm_monte_b200::jsonStateSamplingFunction{
+                                         kv.second.name, kv.second.description, [pyf]() -> std::string {
+                                           py::gil_scoped_acquire gil;
+                                           return py::module_::import("json").attr("dumps")(pyf()).cast<std::string>();
+                                         }});
+             }
+             ResultsIOFunction io;
+             if (!results_io.is_none())
+               io = [results_io](Results const &results, ValueMap const &conditions, Index run_index) {
+                 py::gil_scoped_acquire gil;
+                 results_io.attr("write")(py::cast(&results, py::return_value_policy::reference),
+                                          py::cast(conditions), run_index);
+               };
+             return SamplingFixtureParams(label, sampling_functions, jfs, analysis_functions, sampling_params,
+                                          completion_check_params, analysis_names, io,
+                                          method_log.has_value() ? *method_log : MethodLog());
+           }),
+           py::arg("label"), py::arg("sampling_functions"), py::arg("json_sampling_functions"),
+           py::arg("analysis_functions"), py::arg("sampling_params"), py::arg("completion_check_params"),
+           py::arg("analysis_names") = std::vector<std::string>(), py::arg("results_io") = py::none(),
+           py::arg("method_log") = py::none())
+      .def_readonly("label", &SamplingFixtureParams::label)
+      .def_readonly("sampling_functions", &SamplingFixtureParams::sampling_functions)
+      .def_readonly("analysis_functions", &SamplingFixtureParams::analysis_functions)
+      .def_readonly("sampling_params", &SamplingFixtureParams::sampling_params)
+      .def_readonly("completion_check_params", &SamplingFixtureParams::completion_check_params)
+      .def_readonly("analysis_names", &SamplingFixtureParams::analysis_names)
+      .def_readonly("method_log", &SamplingFixtureParams::method_log);
+
+  py::class_<fixture_type, std::shared_ptr<fixture_type>>(m, "SamplingFixture")
+      .def(py::init([](SamplingFixtureParams const &params, PyEngine const &engine) {
+             return std::make_shared<fixture_type>(params, engine.e);
+           }),
+           py::arg("params"), py::arg("engine"))
+      .def("label", &fixture_type::label)
+      .def("params", &fixture_type::params, py::return_value_policy::reference_internal)
+      .def("counter", &fixture_type::counter, py::return_value_policy::reference_internal)
+      .def("results", &fixture_type::results, py::return_value_policy::reference_internal)
+      .def("completion_check_results", &fixture_type::completion_check_results,
+           py::return_value_policy::reference_internal)
+      .def("next_sample_count", &fixture_type::next_sample_count)
+      .def("initialize", &fixture_type::initialize, py::arg("steps_per_pass"))
+      .def("is_complete", &fixture_type::is_complete)
+      .def("increment_step", &fixture_type::increment_step)
+      .def("increment_n_accept", &fixture_type::increment_n_accept)
+      .def("increment_n_reject", &fixture_type::increment_n_reject)
+      .def("advance_passes", &fixture_type::advance_passes, py::arg("n_passes"), py::arg("d_accept"),
+           py::arg("d_reject"))
+      .def("sample_data", &fixture_type::sample_data, py::arg("state"))
+      .def("sample_data_by_count_if_due", &fixture_type::sample_data_by_count_if_due, py::arg("state"))
+      .def("steps_to_next_event", &fixture_type::steps_to_next_event)
+      .def("write_status", &fixture_type::write_status, py::arg("run_index"))
+      .def("finalize", &fixture_type::finalize, py::arg("state"), py::arg("run_index"));
+
+  py::class_<run_manager_type, std::shared_ptr<run_manager_type>>(m, "RunManager")
+      .def(py::init([](PyEngine const &engine, std::vector<SamplingFixtureParams> const &params, bool global_cutoff) {
+             return std::make_shared<run_manager_type>(engine.e, params, global_cutoff);
+           }),
+           py::arg("engine"), py::arg("sampling_fixture_params"), py::arg("global_cutoff") = true)
+      .def_readwrite("run_index", &run_manager_type::run_index)
+      .def_readwrite("global_cutoff", &run_manager_type::global_cutoff)
+      .def_property_readonly("engine", [](run_manager_type const &r) { return PyEngine{r.engine}; })
+      .def_readonly("sampling_fixtures", &run_manager_type::sampling_fixtures)
+      .def("initialize", &run_manager_type::initialize, py::arg("steps_per_pass"))
+      .def("is_complete", &run_manager_type::is_complete)
+      .def("write_status_if_due", &run_manager_type::write_status_if_due)
+      .def("increment_step", &run_manager_type::increment_step)
+      .def("increment_n_accept", &run_manager_type::increment_n_accept)
+      .def("increment_n_reject", &run_manager_type::increment_n_reject)
+      .def("advance_passes", &run_manager_type::advance_passes, py::arg("n_passes"), py::arg("d_accept"),
+           py::arg("d_reject"))
+      .def("sample_data_by_count_if_due", &run_manager_type::sample_data_by_count_if_due, py::arg("state"))
+      .def("steps_to_next_event", &run_manager_type::steps_to_next_event)
+      .def("finalize", &run_manager_type::finalize, py::arg("final_state"));
+
+  m.def("occupation_metropolis",
+        [](std::shared_ptr<calculator_type> mc_calculator, IsingState &state,
+           std::shared_ptr<run_manager_type> run_manager, std::string update_mode) {
+          if (!mc_calculator || !run_manager)
+            throw std::runtime_error("Error in occupation_metropolis: mc_calculator / run_manager is None");
+          occupation_metropolis(*mc_calculator, state, *run_manager, update_mode);
+        },
+        py::arg("mc_calculator"), py::arg("state"), py::arg("run_manager"), py::arg("update_mode") = "auto");
 }

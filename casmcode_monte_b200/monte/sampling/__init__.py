@@ -10,7 +10,7 @@ for _n in (
     "StateSamplingFunction StateSamplingFunctionMap jsonSampler jsonSamplerMap jsonStateSamplingFunction "
     "jsonStateSamplingFunctionMap all_minimums_met any_maximum_met colmajor_component_names "
     "default_component_names default_equilibration_check get_n_samples matrix_as_vector scalar_as_vector "
-    "vector_as_vector"
+    "vector_as_vector SAMPLE_MODE SAMPLE_METHOD SamplingParams"
 ).split():
     globals()[_n] = getattr(_ext, _n)
 del _n

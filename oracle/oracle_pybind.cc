@@ -9,6 +9,7 @@
 #include <sstream>
 
 #include "monte_oracle.hh"
+#include "run_management_oracle.hh"
 
 namespace py = pybind11;
 using namespace monte_oracle;
@@ -237,6 +238,103 @@ py::dict checkerboard_run(std::vector<int> shape, i32arr occ_in, double J,
   return out;
 }
 
+
+// ---- run management restatement (run_management_oracle.hh) ----
+SamplingParams sampling_params_from_dict(py::dict const &d) {
+  SamplingParams s;
+  if (d.contains("sampler_names")) s.sampler_names = d["sampler_names"].cast<std::vector<std::string>>();
+  if (d.contains("sample_mode")) {
+    std::string m = d["sample_mode"].cast<std::string>();
+    s.sample_mode = m == "step" ? SAMPLE_MODE::BY_STEP : m == "time" ? SAMPLE_MODE::BY_TIME : SAMPLE_MODE::BY_PASS;
+  }
+  if (d.contains("sample_method")) {
+    std::string m = d["sample_method"].cast<std::string>();
+    s.sample_method = m == "log" ? SAMPLE_METHOD::LOG : m == "custom" ? SAMPLE_METHOD::CUSTOM : SAMPLE_METHOD::LINEAR;
+  }
+  if (d.contains("period")) s.period = d["period"].cast<double>();
+  if (d.contains("begin")) s.begin = d["begin"].cast<double>();
+  if (d.contains("base")) s.base = d["base"].cast<double>();
+  if (d.contains("shift")) s.shift = d["shift"].cast<double>();
+  if (d.contains("stochastic_sample_period")) s.stochastic_sample_period = d["stochastic_sample_period"].cast<bool>();
+  if (d.contains("do_sample_trajectory")) s.do_sample_trajectory = d["do_sample_trajectory"].cast<bool>();
+  return s;
+}
+
+py::dict run_management_sgc_run(std::vector<int> shape, i32arr occ_in, double J, double T, double mu,
+                                bool use_nlist, Engine &engine, py::list fixtures, bool global_cutoff) {
+  IsingState state = make_state(shape, to_vec(occ_in), T, mu);
+  auto system = std::make_shared<IsingSystem>(IsingFormationEnergy(J, 1, use_nlist), IsingParamComposition());
+  auto mc = std::make_shared<SemiGrandCanonicalCalculator>(system);
+  mc->state = &state;
+  mc->conditions = std::make_shared<SemiGrandCanonicalConditions>(
+      SemiGrandCanonicalConditions::from_values(state.conditions));
+  mc->potential.set_state(&state, mc->conditions);
+  StateSamplingFunctionMap fns;
+  for (auto const &f : {make_parametric_composition_f(mc), make_formation_energy_f(mc), make_potential_energy_f(mc)})
+    fns.emplace(f.name, f);
+  const double N = static_cast<double>(state.configuration.n_unitcells);
+  ResultsAnalysisFunctionMap afs;
+  afs.emplace("heat_capacity", ResultsAnalysisFunction{"heat_capacity", "", {}, {"0"}, [=](RunResults const &r) {
+                                 return std::vector<double>{N * tail_variance(r, "potential_energy") / (KB * T * T)};
+                               }});
+  afs.emplace("susceptibility", ResultsAnalysisFunction{"susceptibility", "", {}, {"0"}, [=](RunResults const &r) {
+                                  return std::vector<double>{N * tail_variance(r, "param_composition") / (KB * T)};
+                                }});
+  std::vector<SamplingFixtureParams> params;
+  for (auto item : fixtures) {
+    py::dict d = item.cast<py::dict>();
+    SamplingFixtureParams p;
+    p.label = d["label"].cast<std::string>();
+    p.sampling_functions = fns;
+    p.analysis_functions = afs;
+    p.sampling_params = sampling_params_from_dict(d["sampling_params"].cast<py::dict>());
+    p.completion_check_params = params_from_dict(d["completion_check_params"].cast<py::dict>());
+    if (d.contains("analysis_names")) p.analysis_names = d["analysis_names"].cast<std::vector<std::string>>();
+    params.push_back(p);
+  }
+  RunManager<> run_manager(engine.e, params, global_cutoff);
+  SemiGrandCanonicalEventGenerator<> gen;
+  gen.set_state(&state);
+  RandomNumberGenerator<> rng(engine.e);
+  {
+    py::gil_scoped_release release;
+    ising_occupation_metropolis(state, mc->potential, gen, rng, run_manager);
+  }
+  py::dict out;
+  out["occupation"] = from_vec(state.configuration.occupation());
+  out["potential_energy_property"] = state.properties.scalar_values.at("potential_energy");
+  py::list fl;
+  for (auto const &fp : run_manager.sampling_fixtures) {
+    RunResults const &r = fp->results();
+    py::dict fd;
+    fd["label"] = fp->params().label;
+    fd["sample_count"] = r.sample_count;
+    py::dict sd;
+    for (auto const &kv : r.samplers) {
+      auto v = kv.second->component(0);
+      f64arr a(v.size());
+      std::copy(v.begin(), v.end(), a.mutable_data());
+      sd[py::str(kv.first)] = a;
+    }
+    fd["samplers"] = sd;
+    py::list traj;
+    for (auto const &occ : r.sample_trajectory) traj.append(from_vec(occ));
+    fd["sample_trajectory"] = traj;
+    py::dict ad;
+    for (auto const &kv : r.analysis) ad[py::str(kv.first)] = kv.second;
+    fd["analysis"] = ad;
+    fd["n_accept"] = r.n_accept;
+    fd["n_reject"] = r.n_reject;
+    fd["count"] = fp->counter().count;
+    fd["pass"] = fp->counter().pass;
+    fd["step"] = fp->counter().step;
+    fd["completion_check_results"] = cc_results_to_dict(r.completion_check_results);
+    fl.append(fd);
+  }
+  out["fixtures"] = fl;
+  return out;
+}
+
 }  // namespace
 
 PYBIND11_MODULE(_monte_oracle, m) {
@@ -413,6 +511,53 @@ PYBIND11_MODULE(_monte_oracle, m) {
   });
   m.def("susceptibility", [](f64arr x, long long N, double T) {
     return susceptibility(to_dvec(x), N, T);
+  });
+
+  m.def("run_management_sgc_run", &run_management_sgc_run, py::arg("shape"), py::arg("occupation"), py::arg("J"),
+        py::arg("temperature"), py::arg("mu"), py::arg("use_nlist"), py::arg("engine"), py::arg("fixtures"),
+        py::arg("global_cutoff") = true);
+  m.def("rm_sample_at", [](long i, py::dict d) { return sample_at(i, sampling_params_from_dict(d)); });
+  m.def("rm_stochastic_count_steps", [](Engine &engine, double rate, int n) {
+    RandomNumberGenerator<> rng(engine.e);
+    std::vector<long> out;
+    for (int i = 0; i < n; ++i) out.push_back(stochastic_count_step(rate, rng));
+    return out;
+  });
+  m.def("rm_monte_counter_trace", [](std::string mode, long steps_per_pass, long n_steps) {
+    MonteCounter c;
+    c.reset(mode == "step" ? SAMPLE_MODE::BY_STEP : SAMPLE_MODE::BY_PASS, steps_per_pass);
+    std::vector<std::array<long, 3>> out;
+    for (long i = 0; i < n_steps; ++i) {
+      c.increment_step();
+      out.push_back({c.step, c.pass, c.count});
+    }
+    return out;
+  });
+  m.def("rm_fixture_schedule", [](py::dict sampling_params, py::dict cc_params, long steps_per_pass, long max_steps,
+                                  Engine &engine) {
+    // drive one fixture step by step with constant sampling functions; returns the counts at which it sampled
+    SamplingFixtureParams p;
+    p.label = "schedule";
+    p.sampling_functions.emplace("x", StateSamplingFunction("x", "", {}, []() { return std::vector<double>{1.0}; }));
+    p.sampling_params = sampling_params_from_dict(sampling_params);
+    p.sampling_params.sampler_names = {"x"};
+    p.completion_check_params = params_from_dict(cc_params);
+    SamplingFixture<> f(p, engine.e);
+    IsingState state = make_state({2, 2}, std::vector<int>(4, 1), 1000.0, 0.0);
+    f.initialize(steps_per_pass);
+    f.sample_data_by_count_if_due(state);
+    long n = 0;
+    while (!f.is_complete() && n < max_steps) {
+      f.increment_step();
+      f.sample_data_by_count_if_due(state);
+      ++n;
+    }
+    py::dict out;
+    out["sample_count"] = f.results().sample_count;
+    out["steps"] = n;
+    out["count"] = f.counter().count;
+    out["is_complete"] = f.is_complete();
+    return out;
   });
 
   m.def("sgc_run", &sgc_run, py::arg("shape"), py::arg("occupation"),
