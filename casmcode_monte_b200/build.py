@@ -51,6 +51,9 @@ def build_host_module(force=False):
     ext = sysconfig.get_config_var("EXT_SUFFIX")
     out = os.path.join(HERE, "_monte_b200" + ext)
     hdrs = [os.path.join(CSRC, "host", f) for f in os.listdir(os.path.join(CSRC, "host"))]
+    inc = os.path.join(ROOT, "include")
+    hdrs += [os.path.join(inc, "casm_monte_gpu.h")]
+    hdrs += [os.path.join(inc, "casm_monte_b200", f) for f in os.listdir(os.path.join(inc, "casm_monte_b200"))]
     if not force and not _newer(out, hdrs + [LIB]):
         return out
     cmd = [
