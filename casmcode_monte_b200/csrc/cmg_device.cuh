@@ -108,8 +108,9 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, const uint32_t *rk) {
 // Random words of site group `group` (8 consecutive plane indices, one 16-bit
 // lane each) of `chain` in half-sweep (pass, colour): counter = {lo32(group),
 // (hi32(group)&0xff) | chain<<8, lo32(pass), hi32(pass)<<2 | refine<<1 | colour},
-// key = seed.  refine = 0: the leading 16 bits r16 of each site's uniform;
-// refine = 1: the trailing 16 bits r16' (only evaluated on a tie, see below).
+// key = seed.  refine = 0: the lane r16 that supplies the leading 16 bits of each
+// site's uniform (rotated, see accept_mask4_fast); refine = 1: the trailing 16
+// bits r16' (only evaluated on a tie).
 __device__ __forceinline__ uint4 site_group_random(unsigned long long group,
                                                    uint32_t chain_word,
                                                    unsigned long long pass,
@@ -350,10 +351,12 @@ __global__ void __launch_bounds__(128) k_halfsweep_generic(SweepArgs A) {
 // walks a strip of `js` columns.  The three opposite-colour columns j-1, j,
 // j+1 needed by column j are kept in registers as a rolling window, so moving
 // to the next column costs one 16-byte load of the opposite plane, one of the
-// own plane, one byte for the p+-1 neighbour across the vector edge, and one
-// 16-byte store: 3 B of traffic per attempted flip.  Neighbour counts are
-// formed four sites at a time with plain 32-bit adds (bytes are 0/1, sums <= 4
-// never carry).  Four Philox calls give the 16 uniforms.
+// own plane, the word holding the p+-1 neighbour across the vector edge (an L1
+// hit), and one 16-byte store: 3 B of traffic per attempted flip.  The loads
+// are staged four columns ahead through a per-thread cp.async ring in shared
+// memory (see below).  Neighbour counts are formed four sites at a time with
+// plain 32-bit adds (bytes are 0/1, sums <= 4 never carry).  Two Philox calls
+// give the 16 leading lanes.
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ uint4 ld16(const uint8_t *p) {
   return *reinterpret_cast<const uint4 *>(p);

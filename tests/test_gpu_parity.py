@@ -223,8 +223,8 @@ def test_tile2d_matches_oracle(cm, oracle, shape, variant):
 
 def test_threshold_ties_take_the_exact_path(cm, oracle):
     # mu chosen so that a threshold's top half is hit often is impossible to arrange
-    # (probability 2^-16 per site); instead run enough sites that ties occur:
-    # 1024x1024 x 8 passes = 8.4M attempts -> ~128 expected ties; every one must
+    # (probability 2^-15 per site); instead run enough sites that ties occur:
+    # 1024x1024 x 8 passes = 8.4M attempts -> ~256 expected ties; every one must
     # resolve exactly as the oracle's 32-bit compare does.
     shape = [1024, 1024]
     occ = rand_occ(nsites(shape), 25)
