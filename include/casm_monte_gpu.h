@@ -157,8 +157,8 @@ int cmg_randomize_occupation(cmg_context *ctx, int chain, uint64_t seed, double 
  * group, chain, pass index, colour [, refinement]).  The acceptance uniform of a
  * site is the 32-bit integer R = rotl16(r16, 1) << 16 | r16' built from the
  * site's 16-bit lane of the leading and of the refinement call; the site flips
- * iff R <= ceil(p * 2^32) - 1 (oracle/monte_oracle.hh: checkerboard_uniform,
- * checkerboard_pass state this definition in scalar form).  Serial mode: the reference's
+ * iff R <= ceil(p * 2^32) - 1, p = exp(-dE * beta) (DESIGN.md section 4 gives
+ * the definition in full).  Serial mode: the reference's
  * RandomNumberGenerator<std::mt19937_64> (include/casm/monte/
  * RandomNumberGenerator.hh:15-42, definitions.hh:17) restated on the device:
  * libstdc++-13 uniform_int_distribution (Lemire) and generate_canonical. */
