@@ -919,11 +919,13 @@ static int pick_js(cmg_context *c, int variant) {
   // pipeline fill at the strip start; the CTA count they imply should fill
   // whole waves of `slots` CTAs (a 1.7-wave launch idles a quarter of the GPU
   // during its tail).  Multiples of four match the unrolled column loop.
-  static const int cand[] = {2, 4, 6, 8, 12, 16, 20, 24, 28, 32, 36, 40, 44, 48};
+  static const int cand[] = {2,  4,  6,  8,  12, 16, 20, 24, 28, 32,  36,  40, 44,
+                             48, 52, 56, 60, 64, 72, 80, 88, 96, 104, 112, 120, 128};
   int best = 16;
   double best_score = -1.0;
   for (int js : cand) {
     if (js > c->shape[1] && js > 2) continue;
+    if (variant == V_BULK3D && js > 48) continue;  // measured: long strips lose L2 reuse across k-layers
     const long long strips = (c->shape[1] + js - 1) / js;
     const double ctas = (double)nblocks(V * strips * layers, 128) * c->n_chains;
     const double waves = ctas / slots;

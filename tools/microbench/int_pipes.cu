@@ -102,10 +102,10 @@ __global__ void kmix(uint32_t *out, uint32_t seed) {
   if (r == 0x12345678u) out[0] = r;
 }
 template <int OPA, int OPB>
-void runmix(const char *name, int sms, double ghz) {
+void runmix(const char *name, int sms, double ghz, int threads = 1024, int ctas_per_sm = 2) {
   uint32_t *out;
   cudaMalloc(&out, 4);
-  dim3 grid(sms * 2), block(1024);
+  dim3 grid(sms * ctas_per_sm), block(threads);
   kmix<OPA, OPB><<<grid, block>>>(out, 1);
   cudaDeviceSynchronize();
   cudaEvent_t e0, e1;
@@ -117,9 +117,10 @@ void runmix(const char *name, int sms, double ghz) {
   cudaEventSynchronize(e1);
   float ms;
   cudaEventElapsedTime(&ms, e0, e1);
-  double ops = (double)grid.x * 32 * ITERS * CHAINS;
+  double ops = (double)grid.x * (threads / 32) * ITERS * CHAINS;
   double clocks = ms * 1e-3 * ghz * 1e9;
-  printf("%-22s %8.3f ms  %6.2f warp-ops/clk/SM (50/50 mix)\n", name, ms, ops / clocks / sms);
+  printf("%-22s %8.3f ms  %6.2f warp-ops/clk/SM (50/50 mix, %d warps/SM)\n", name, ms, ops / clocks / sms,
+         threads / 32 * ctas_per_sm);
   cudaFree(out);
 }
 
@@ -151,5 +152,14 @@ int main() {
   runmix<1, 8>("LOP3 + IDP.4A", s, ghz);
   runmix<0, 2>("IMAD.WIDE + IMAD", s, ghz);
   runmix<1, 5>("LOP3 + SHF", s, ghz);
+  // occupancy sensitivity of the overlap (the sweep kernels run 16 warps per SM)
+  runmix<1, 2>("LOP3 + IMAD", s, ghz, 1024, 1);
+  runmix<1, 2>("LOP3 + IMAD", s, ghz, 512, 1);
+  runmix<1, 2>("LOP3 + IMAD", s, ghz, 256, 1);
+  runmix<1, 0>("LOP3 + IMAD.WIDE", s, ghz, 512, 1);
+  runmix<1, 0>("LOP3 + IMAD.WIDE", s, ghz, 256, 1);
+  runmix<1, 1>("LOP3 only", s, ghz, 512, 1);
+  runmix<1, 1>("LOP3 only", s, ghz, 256, 1);
+  runmix<1, 1>("LOP3 only", s, ghz, 128, 1);
   return 0;
 }

@@ -27,6 +27,8 @@ def main():
     cases = [
         ("2d", [4096, 4096], 1, ["bulk2d", "bulk2d:js=8", "tile2d:p=3:nt=512"], 120),
         ("2d_sweep8", [4096, 4096], 8, ["bulk2d", "bulk2d:js=16", "bulk2d:js=32", "tile2d:p=3:nt=512"], 48),
+        ("2d_sweep8_js", [4096, 4096], 8, ["bulk2d:js=28", "bulk2d:js=56", "bulk2d:js=52", "bulk2d:js=60", "bulk2d:js=19", "bulk2d:js=14"], 48),
+        ("2d_big_js", [16384, 16384], 1, ["bulk2d", "bulk2d:js=56", "bulk2d:js=112", "bulk2d:js=20"], 20),
         ("2d_grid", [256, 256], 128, ["tile2d:nt=512"], 128),
         ("2d_big", [16384, 16384], 1, ["bulk2d", "bulk2d:js=32"], 20),
         ("3d", [512, 512, 512], 1, ["bulk3d", "bulk3d:js=8", "bulk3d:js=16"], 10),
