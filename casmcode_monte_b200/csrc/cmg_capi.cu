@@ -33,7 +33,7 @@ struct RunState {
   long long n_samples;
 };
 
-enum Variant { V_AUTO = 0, V_GENERIC = 1, V_BULK2D = 2, V_BULK3D = 3, V_TILE2D = 4 };
+enum Variant { V_AUTO = 0, V_GENERIC = 1, V_BULK2D = 2, V_BULK3D = 3, V_TILE2D = 4, V_RING2D = 5 };
 
 struct cmg_context {
   int device = 0;
@@ -94,6 +94,11 @@ struct cmg_context {
   int js = 0;  // 0 = auto
   int tile_passes = 3;   // passes per launch of the tiled kernel (halo = 2*P columns)
   int tile_threads = 512;
+  int ring_passes = 128;  // passes per cooperative launch of the ring kernel
+  unsigned int *d_ring_flags = nullptr;  // [n_chains][n_tiles][2] + error word at the end
+  size_t ring_flag_words = 0;
+  unsigned int *h_ring_error = nullptr;  // pinned copy of the error word
+  int coop_launch = 0;
   int sm_count = 148;
   bool bulk_attr_set = false;
   int js_auto[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // cached strip length per kernel variant
@@ -300,6 +305,8 @@ static int create_common(int dim, const int64_t *shape, int n_chains, int device
       c->sm_count = v;
     if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) == cudaSuccess)
       c->smem_optin = (size_t)v;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, device) == cudaSuccess)
+      c->coop_launch = v;
   }
 #define CUC(call)                                                        \
   do {                                                                   \
@@ -394,6 +401,8 @@ int cmg_destroy(cmg_context *c) {
     for (int side = 0; side < 2; ++side) cudaFree(c->d_halo[col][side]);
   cudaFree(c->d_flags);
   cudaFree(c->d_done);
+  cudaFree(c->d_ring_flags);
+  if (c->h_ring_error) cudaFreeHost(c->h_ring_error);
   delete c;
   return CMG_OK;
 }
@@ -405,10 +414,17 @@ int cmg_set_stream(cmg_context *c, void *cuda_stream) {
   return CMG_OK;
 }
 
+// the ring kernel bounds its flag waits; a timeout is reported here, never hidden
+static int ring_error_check(cmg_context *c) {
+  if (c->h_ring_error && *c->h_ring_error)
+    return fail(c, CMG_ECUDA, "ring2d: a tile waited too long for its neighbour (results invalid)");
+  return CMG_OK;
+}
+
 int cmg_sync(cmg_context *c) {
   NEED(c);
   CU(c, cudaStreamSynchronize(c->stream));
-  return CMG_OK;
+  return ring_error_check(c);
 }
 
 int cmg_n_sites(const cmg_context *c, int64_t *n) {
@@ -570,7 +586,7 @@ int cmg_download_occupation_i32(cmg_context *c, int chain, int32_t *occ, int64_t
   CU(c, cudaMemcpyAsync(occ, c->d_stage, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost,
                         c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
-  return CMG_OK;
+  return ring_error_check(c);
 }
 
 int cmg_download_occupation_i32_dev(cmg_context *c, int chain, int32_t *occ_dev, int64_t n) {
@@ -892,12 +908,43 @@ static TilePlan plan_tiles(const cmg_context *c, long long passes_wanted) {
   return t;
 }
 
+// Geometry of the ring kernel: the whole lattice resident in shared memory,
+// one tile of whole columns per CTA, every CTA of the grid co-resident
+// (cooperative launch), at least two columns per column group.
+struct RingPlan {
+  bool ok = false;
+  int n_tiles = 0, w_max = 0;
+  size_t smem = 0;
+};
+static RingPlan plan_ring(const cmg_context *c) {
+  RingPlan r;
+  if (c->dim != 2 || c->slab || !c->coop_launch || c->shape[0] % 1024 != 0) return r;
+  const long long h = c->shape[0] / 2, n1 = c->shape[1], V = h / 16;
+  if (V > 512 || 512 % V != 0) return r;
+  const long long Q = 512 / V;
+  long long n_tiles = c->sm_count / c->n_chains;
+  n_tiles = std::min(n_tiles, n1 / (2 * Q));
+  if (n_tiles < 2) return r;
+  const long long w_max = (n1 + n_tiles - 1) / n_tiles;
+  const long long smem = 2 * w_max * h + kSmemTile;
+  if (smem + 6144 > (long long)c->smem_optin) return r;  // static: 4 KiB of per-pass sums
+  r.ok = true;
+  r.n_tiles = (int)n_tiles;
+  r.w_max = (int)w_max;
+  r.smem = (size_t)smem;
+  return r;
+}
+
 static int pick_variant(cmg_context *c) {
   if (c->forced_variant != V_AUTO) return c->forced_variant;
   // the tiled kernel wins while a half-sweep is short enough for launch ramp
   // and L2 latency to matter; very large batches stream better through bulk2d
-  if (plan_tiles(c, c->tile_passes).ok && c->n_sites * c->n_chains <= (1ll << 25))
+  if (plan_tiles(c, c->tile_passes).ok && c->n_sites * c->n_chains <= (1ll << 25)) {
+    // a lattice too large for one CTA but not for the GPU's shared memory stays
+    // resident across the launch (no halo recomputation): 4096^2 1.4e12 vs 0.98e12
+    if (plan_tiles(c, c->tile_passes).n_tiles > 1 && plan_ring(c).ok) return V_RING2D;
     return V_TILE2D;
+  }
   if (c->dim == 2 && c->shape[0] % 32 == 0) return V_BULK2D;
   if (c->dim == 3 && c->shape[0] % 32 == 0) return V_BULK3D;
   return V_GENERIC;
@@ -1045,8 +1092,62 @@ static int launch_tile_passes_sp(cmg_context *c, const TilePlan &tp, int n_passe
   return CMG_OK;
 }
 
+static int launch_ring_passes(cmg_context *c, const RingPlan &rp, int n_passes,
+                              long long sample_period) {
+  const size_t words = (size_t)2 * rp.n_tiles * c->n_chains + 1;
+  if (c->ring_flag_words < words) {
+    cudaFree(c->d_ring_flags);
+    c->d_ring_flags = nullptr;
+    CU(c, cudaMalloc(&c->d_ring_flags, sizeof(unsigned int) * words));
+    c->ring_flag_words = words;
+  }
+  if (!c->h_ring_error) {
+    CU(c, cudaMallocHost(&c->h_ring_error, sizeof(unsigned int)));
+    *c->h_ring_error = 0;
+  }
+  CU(c, cudaMemsetAsync(c->d_ring_flags, 0, sizeof(unsigned int) * words, c->stream));
+  RingArgs A;
+  memset(&A, 0, sizeof A);
+  A.L = view(c);
+  A.tabs = c->d_tabs;
+  A.n_accept = c->d_n_accept;
+  A.sb = c->d_series ? c->d_series + c->n_samples * 2 * c->n_chains : nullptr;
+  A.sb_chain_stride = 2;
+  A.sb_slot_stride = 2 * c->n_chains;
+  A.pass0 = c->h_pass;
+  A.pass_phase = c->n_pass;
+  A.sample_period = sample_period;
+  for (int r = 0; r < 10; ++r) {
+    A.rk[2 * r] = (uint32_t)c->philox_seed + (uint32_t)r * kPhiloxW0;
+    A.rk[2 * r + 1] = (uint32_t)(c->philox_seed >> 32) + (uint32_t)r * kPhiloxW1;
+  }
+  A.n_passes = n_passes;
+  A.chain_offset = c->chain_offset;
+  A.n_tiles = rp.n_tiles;
+  A.w_max = rp.w_max;
+  const unsigned long long V = (unsigned long long)(c->shape[0] / 32);
+  A.v_magic = (uint32_t)((0x100000000ull + V - 1) / V);
+  A.flags = c->d_ring_flags;
+  A.error = c->d_ring_flags + (words - 1);
+  cudaError_t e = cudaFuncSetAttribute(k_ring2d<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)rp.smem);
+  if (e != cudaSuccess) return fail(c, CMG_ECUDA, cudaGetErrorString(e));
+  dim3 grid(rp.n_tiles, c->n_chains);
+  void *args[] = {&A};
+  // cooperative: the grid starts only when every CTA can be resident, which
+  // the flag waits between neighbouring tiles rely on
+  e = cudaLaunchCooperativeKernel((const void *)k_ring2d<512>, grid, dim3(512), args, rp.smem,
+                                  c->stream);
+  if (e != cudaSuccess) return fail(c, CMG_ECUDA, cudaGetErrorString(e));
+  CU(c, cudaMemcpyAsync(c->h_ring_error, A.error, sizeof(unsigned int), cudaMemcpyDeviceToHost,
+                        c->stream));
+  ++c->launches;
+  return CMG_OK;
+}
+
 static const char *variant_str(int v) {
   switch (v) {
+    case V_RING2D: return "ring2d";
     case V_GENERIC: return "generic";
     case V_BULK2D: return "bulk2d";
     case V_BULK3D: return "bulk3d";
@@ -1167,6 +1268,10 @@ int cmg_run_passes(cmg_context *c, int64_t n_passes, int mode, int64_t sample_pe
     return fail(c, CMG_EINVAL, "bulk3d needs dim == 3 and n0 % 32 == 0");
   if (variant == V_TILE2D && !plan_tiles(c, 1).ok)
     return fail(c, CMG_EINVAL, "tile2d does not fit this lattice (need dim 2, n0 % 64 == 0, short columns)");
+  if (variant == V_RING2D && !plan_ring(c).ok)
+    return fail(c, CMG_EINVAL,
+                "ring2d does not fit this lattice (need dim 2, n0 in {1024..16384} a power of two, "
+                "the lattice within the GPU's shared memory, cooperative launch)");
   c->variant_name = variant_str(variant);
   long long n_new = 0;
   if (sample_period > 0)
@@ -1174,6 +1279,27 @@ int cmg_run_passes(cmg_context *c, int64_t n_passes, int mode, int64_t sample_pe
   rc = ensure_series(c, c->n_samples + n_new);
   if (rc) return rc;
   c->nat_is_current = false;
+  if (variant == V_RING2D) {
+    rc = ring_error_check(c);
+    if (rc) return rc;
+    const RingPlan rp = plan_ring(c);
+    long long left = n_passes;
+    while (left > 0) {
+      // at most kRingMaxPasses sampled passes per launch (shared per-pass accumulators)
+      long long P = std::min<long long>(left, c->ring_passes);
+      rc = launch_ring_passes(c, rp, (int)P, sample_period);
+      if (rc) return rc;
+      long long n_new_here = 0;
+      if (sample_period > 0)
+        n_new_here = (c->n_pass + P) / sample_period - c->n_pass / sample_period;
+      c->h_pass += P;
+      c->n_pass += P;
+      c->n_samples += n_new_here;
+      left -= P;
+    }
+    CU(c, cudaGetLastError());
+    return CMG_OK;
+  }
   if (variant == V_TILE2D) {
     long long left = n_passes;
     while (left > 0) {
@@ -1687,6 +1813,101 @@ int cmg_host_series_equilibration(int device, const double *x, int64_t n, double
   return rc;
 }
 
+// ---- weighted observations --------------------------------------------------------------
+static int run_weighted_job(const double *x, const double *w, int64_t n, double confidence,
+                            int method, double weight_sum, int64_t n_resamples, double *out5,
+                            int64_t *k_star, double *resampled_out) {
+  cmg_context *c = nullptr;
+  double *dx = nullptr, *dw = nullptr, *deq = nullptr, *dout = nullptr;
+  long long *dk = nullptr;
+  WeightedJob *dj = nullptr;
+  CU(c, cudaMalloc(&dx, sizeof(double) * (size_t)n));
+  CU(c, cudaMalloc(&dw, sizeof(double) * (size_t)n));
+  CU(c, cudaMalloc(&deq, sizeof(double) * (size_t)n_resamples));
+  CU(c, cudaMalloc(&dout, sizeof(double) * 5));
+  CU(c, cudaMalloc(&dk, sizeof(long long)));
+  CU(c, cudaMalloc(&dj, sizeof(WeightedJob)));
+  CU(c, cudaMemcpy(dx, x, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
+  CU(c, cudaMemcpy(dw, w, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
+  WeightedJob job{dx, dw, (long long)n, deq, (long long)n_resamples, method, weight_sum};
+  CU(c, cudaMemcpy(dj, &job, sizeof(job), cudaMemcpyHostToDevice));
+  k_series_stats_weighted<<<1, 256>>>(dj, z_confidence(confidence), dout, dk);
+  CU(c, cudaGetLastError());
+  long long hk = 0;
+  if (out5) CU(c, cudaMemcpy(out5, dout, sizeof(double) * 5, cudaMemcpyDeviceToHost));
+  CU(c, cudaMemcpy(&hk, dk, sizeof(long long), cudaMemcpyDeviceToHost));
+  if (resampled_out)
+    CU(c, cudaMemcpy(resampled_out, deq, sizeof(double) * (size_t)n_resamples,
+                     cudaMemcpyDeviceToHost));
+  if (k_star) *k_star = hk;
+  cudaFree(dx);
+  cudaFree(dw);
+  cudaFree(deq);
+  cudaFree(dout);
+  cudaFree(dk);
+  cudaFree(dj);
+  return CMG_OK;
+}
+
+int cmg_host_series_stats_weighted(int device, const double *x, const double *w, int64_t n,
+                                   double confidence, int method, int64_t n_resamples,
+                                   double *mean, double *calculated_precision, double *variance,
+                                   double *weight_sum, int64_t *k_star) {
+  int rc = device_ok(device);
+  if (rc) return rc;
+  if (!x || !w || n <= 0)
+    return fail(nullptr, CMG_EINVAL, "Error in BasicStatisticsCalculator: observations.size()==0");
+  if (method != 1 && method != 2)
+    return fail(nullptr, CMG_EINVAL, "Error in BasicStatisticsCalculator: invalid method");
+  if (n_resamples <= 0) return fail(nullptr, CMG_EINVAL, "n_resamples must be positive");
+  double out[5];
+  rc = run_weighted_job(x, w, n, confidence, method, 0.0, n_resamples, out, k_star, nullptr);
+  if (rc) return rc;
+  if (mean) *mean = out[0];
+  if (variance) *variance = out[1];
+  if (calculated_precision) *calculated_precision = out[3];
+  if (weight_sum) *weight_sum = out[4];
+  return CMG_OK;
+}
+
+int cmg_host_series_resample(int device, const double *x, const double *w, int64_t n,
+                             double weight_sum, int64_t n_equally_spaced, double *out) {
+  int rc = device_ok(device);
+  if (rc) return rc;
+  if (!x || !w || !out || n <= 0 || n_equally_spaced <= 0)
+    return fail(nullptr, CMG_EINVAL, "bad argument");
+  return run_weighted_job(x, w, n, 0.95, 0, weight_sum, n_equally_spaced, nullptr, nullptr, out);
+}
+
+int cmg_host_series_equilibration_weighted(int device, const double *x, const double *w,
+                                           int64_t n, double abs_precision,
+                                           int *is_equilibrated, int64_t *n_equil) {
+  int rc = device_ok(device);
+  if (rc) return rc;
+  if (!x || !w || n <= 0)
+    return fail(nullptr, CMG_EINVAL, "Error in equilibration_check: observations.size()==0");
+  cmg_context *c = nullptr;
+  double *dx = nullptr, *dw = nullptr, *dy = nullptr, *df = nullptr;
+  CU(c, cudaMalloc(&dx, sizeof(double) * (size_t)n));
+  CU(c, cudaMalloc(&dw, sizeof(double) * (size_t)n));
+  CU(c, cudaMalloc(&dy, sizeof(double) * (size_t)n));
+  CU(c, cudaMalloc(&df, sizeof(double)));
+  CU(c, cudaMemcpy(dx, x, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
+  CU(c, cudaMemcpy(dw, w, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
+  k_weight_factor<<<1, 32>>>(dw, n, df);
+  k_apply_weight_factor<<<nblocks(n, 256), 256>>>(dx, dw, n, df, dy);
+  CU(c, cudaGetLastError());
+  std::vector<SeriesJob> jobs(1);
+  jobs[0].x = dy;
+  jobs[0].n = n;
+  rc = run_equil_jobs(nullptr, 0, jobs, abs_precision, is_equilibrated, n_equil);
+  cudaFree(dx);
+  cudaFree(dw);
+  cudaFree(dy);
+  cudaFree(df);
+  return rc;
+}
+
 // ---- conversions ----------------------------------------------------------------------
 int cmg_conv_l_to_bijk(int device, const int64_t *n3, int64_t n_basis, const int64_t *l,
                        int64_t count, int64_t *bijk_out) {
@@ -1759,6 +1980,12 @@ int cmg_set_kernel_variant(cmg_context *c, const char *name) {
     c->tile_passes = atoi(s.c_str() + p + 3);
     if (c->tile_passes < 1 || c->tile_passes > 16) return fail(c, CMG_EINVAL, "bad p");
   }
+  p = s.find(":rp=");
+  if (p != std::string::npos) {
+    c->ring_passes = atoi(s.c_str() + p + 4);
+    if (c->ring_passes < 1 || c->ring_passes > kRingMaxPasses)
+      return fail(c, CMG_EINVAL, "rp must be in [1, 256]");
+  }
   p = s.find(":nt=");
   if (p != std::string::npos) {
     c->tile_threads = atoi(s.c_str() + p + 4);
@@ -1773,6 +2000,7 @@ int cmg_set_kernel_variant(cmg_context *c, const char *name) {
   else if (s == "bulk2d") c->forced_variant = V_BULK2D;
   else if (s == "bulk3d") c->forced_variant = V_BULK3D;
   else if (s == "tile2d") c->forced_variant = V_TILE2D;
+  else if (s == "ring2d") c->forced_variant = V_RING2D;
   else return fail(c, CMG_EINVAL, "unknown kernel variant");
   return CMG_OK;
 }

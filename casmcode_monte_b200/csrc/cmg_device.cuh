@@ -960,6 +960,259 @@ __global__ void __launch_bounds__(NT, 1) k_tile2d(TileArgs A) {
 }
 
 // ---------------------------------------------------------------------------
+// k_ring2d: one lattice resident in the shared memory of the whole GPU.
+//
+// Every CTA of a cooperative launch (grid <= #SMs, one CTA per SM) owns a
+// tile of whole columns for the entire launch and keeps both colour planes of
+// it in shared memory; nothing is recomputed.  The only data that crosses a
+// tile edge is one boundary column per side and half-sweep, and it travels
+// through the column's home location in global memory (L2-resident):
+//   * the column groups that own local column 0 / TW-1 update those columns
+//     first, store them to shared AND global memory, fence, and bump the
+//     tile's left / right flag (one increment per warp);
+//   * the neighbour's boundary warps wait on that flag (acquire) before
+//     loading the column with L1-bypassing loads straight into the register
+//     window -- there is no halo in shared memory and no extra CTA barrier.
+// A boundary column published at half-sweep s is consumed at the start of
+// half-sweep s+1, a whole half-sweep of interior work later, so the wait is
+// normally already satisfied.  The publisher can only overwrite a home
+// location at s+2, after it has itself waited for the consumer's s+1 flag,
+// which the consumer raises after reading: no read counters are needed.
+// Random numbers are counter-based, so the trajectory is the one of every
+// other kernel.  Any number of passes per launch (sample slots permitting).
+// ---------------------------------------------------------------------------
+struct RingArgs {
+  LatticeView L;
+  const ChainTables *tabs;
+  unsigned long long *n_accept;  // [chain]
+  long long *sb;                 // slot of the first sample taken by this launch (chain 0)
+  long long sb_chain_stride;     // long long units
+  long long sb_slot_stride;      // long long units
+  unsigned long long pass0;      // Philox pass index of the first pass
+  long long pass_phase;          // passes done before this launch (sample schedule)
+  long long sample_period;       // 0 = never
+  uint32_t rk[20];
+  int n_passes;
+  int n_tiles;
+  int w_max;                     // widest tile (smem plane = w_max*h bytes)
+  uint32_t v_magic;              // ceil(2^32 / V), V = h/16
+  int chain_offset;              // global index of chain 0
+  unsigned int *flags;           // [chain][tile][2], zero at launch: {left, right} columns published
+  unsigned int *error;           // raised if a flag wait timed out
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int *p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// lane 0 polls, the warp follows; bounded so that a scheduling accident cannot hang the GPU
+__device__ __forceinline__ void ring_wait(const unsigned int *flag, unsigned int target,
+                                          unsigned int *error) {
+  if ((threadIdx.x & 31) == 0) {
+    unsigned int spins = 0;
+    while (ld_acquire_gpu_u32(flag) < target) {
+      if (++spins > (1u << 22)) {
+        atomicExch(error, 1u);
+        break;
+      }
+    }
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void ring_publish(unsigned int *flag) {
+  __threadfence();
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) atomicAdd(flag, 1u);
+}
+
+constexpr int kRingMaxPasses = 256;
+
+template <int NT>
+__global__ void __launch_bounds__(NT, 1) k_ring2d(RingArgs A) {
+  __shared__ long long s_acc[2 * kRingMaxPasses];  // per-pass {ones, B} of this CTA
+  for (int i = threadIdx.x; i < 2 * kRingMaxPasses; i += NT) s_acc[i] = 0;
+  const LatticeView &L = A.L;
+  const int chain = blockIdx.y;
+  const int tile = blockIdx.x;
+  load_accept_table(A.tabs + chain, true);
+
+  const int h = L.h, n1 = L.n1;
+  const int V = h >> 4;
+  const int c0 = (int)(((long long)tile * n1) / A.n_tiles);
+  const int c1 = (int)(((long long)(tile + 1) * n1) / A.n_tiles);
+  const int TW = c1 - c0;
+  const uint32_t soff[2] = {(uint32_t)kSmemTile, (uint32_t)kSmemTile + (uint32_t)A.w_max * (uint32_t)h};
+  uint8_t *G[2] = {L.planes + (long long)chain * L.chain_stride,
+                   L.planes + (long long)chain * L.chain_stride + L.plane_stride};
+  const uint32_t chain_word = (uint32_t)(chain + A.chain_offset) << 8;
+
+  // ---- stage the owned columns
+  for (int it = threadIdx.x; it < 2 * TW * V; it += NT) {
+    const int plane = it >= TW * V;
+    const int r = it - plane * TW * V;
+    const int cl = (int)__umulhi((uint32_t)r, A.v_magic);
+    const int v = r - cl * V;
+    sts16(soff[plane] + (uint32_t)(cl * h + (v << 4)),
+          __ldg(reinterpret_cast<const uint4 *>(G[plane] + (long long)(c0 + cl) * h + (v << 4))));
+  }
+  __syncthreads();
+
+  // column groups: Q groups of V threads; group q walks columns [a, b)
+  const int Q = NT / V, q = threadIdx.x / V;
+  const uint32_t p0 = (uint32_t)(threadIdx.x % V) << 4;
+  const int base = TW / Q, rem = TW - base * Q;
+  const int a = q * base + min(q, rem);
+  const int b = a + base + (q < rem ? 1 : 0);
+  const bool has_left = (q == 0), has_right = (q == Q - 1);
+  const int tl = tile == 0 ? A.n_tiles - 1 : tile - 1;
+  const int tr = tile + 1 == A.n_tiles ? 0 : tile + 1;
+  unsigned int *fl_mine = A.flags + 2 * ((long long)chain * A.n_tiles + tile);
+  const unsigned int *fl_left = A.flags + 2 * ((long long)chain * A.n_tiles + tl) + 1;
+  const unsigned int *fl_right = A.flags + 2 * ((long long)chain * A.n_tiles + tr);
+  const int gcl = c0 == 0 ? n1 - 1 : c0 - 1;  // global columns of the two neighbours' edges
+  const int gcr = c1 == n1 ? 0 : c1;
+  const unsigned int warps_per_col = (unsigned int)(V >> 5);
+  const uint32_t gstep = (uint32_t)h >> 3;
+  const uint32_t e_lo = (p0 == 0) ? (uint32_t)h - 1u : p0 - 1u;
+  const uint32_t e_hi = (p0 + 16u == (uint32_t)h) ? 0u : p0 + 16u;
+
+  unsigned int n_acc = 0;
+  int slot = 0;
+  for (int s = 0; s < 2 * A.n_passes; ++s) {
+    const int colour = s & 1;
+    const int pl = s >> 1;
+    const unsigned long long pass = A.pass0 + (unsigned long long)pl;
+    const bool sample = colour == 1 && A.sample_period > 0 &&
+                        ((A.pass_phase + pl + 1) % A.sample_period) == 0;
+    const uint32_t cbase = colour ? soff[1] : soff[0];
+    const uint32_t obase = colour ? soff[0] : soff[1];
+    uint8_t *Gc = G[colour];
+    const uint8_t *Go = G[colour ^ 1];
+    Accum acc = {0u, 0u, 0u, 0u, 0u};
+
+    // one column: centre vector and edge byte from shared memory, the three
+    // opposite-colour vectors from the caller; returns the new centre vector
+    auto column = [&](int cl, uint4 om, uint4 oc, uint4 op) -> uint4 {
+      const uint32_t coff = (uint32_t)(cl * h);
+      const int gc = c0 + cl;
+      const int par = (gc + colour) & 1;  // i = 2p + par
+      const uint4 ce = lds16(cbase + coff + p0);
+      const uint32_t eb = cmg_smem[obase + coff + (par ? e_hi : e_lo)];
+      const uint4 side = par ? shift_down_1(oc, eb) : shift_up_1(oc, eb);
+      const unsigned long long g = (unsigned long long)gstep * (uint32_t)gc + (p0 >> 3);
+      uint4 cn;
+      if (sample) {
+        cn = update16<true, true>(ce, om, oc, op, side, g, pass, colour, chain_word, A.rk, acc);
+      } else {
+        Accum scratch = {0u, 0u, 0u, 0u, 0u};
+        cn = update16<false, true>(ce, om, oc, op, side, g, pass, colour, chain_word, A.rk,
+                                   scratch);
+        acc.acc += scratch.acc;
+      }
+      sts16(cbase + coff + p0, cn);
+      return cn;
+    };
+
+    // ---- boundary columns first: consume the neighbour's edge, publish ours
+    int ra = a, rb = b;
+    if (has_left) {
+      if (s > 0) ring_wait(fl_left, warps_per_col * (unsigned int)s, A.error);
+      const uint4 om = __ldcg(reinterpret_cast<const uint4 *>(Go + (long long)gcl * h + p0));
+      const uint4 oc = lds16(obase + p0);
+      const uint4 op = lds16(obase + (uint32_t)h + p0);
+      const uint4 cn = column(0, om, oc, op);
+      __stcg(reinterpret_cast<uint4 *>(Gc + (long long)c0 * h + p0), cn);
+      ring_publish(fl_mine);
+      ra = 1;
+    }
+    if (has_right) {  // tiles are at least two columns wide (host plan)
+      if (s > 0) ring_wait(fl_right, warps_per_col * (unsigned int)s, A.error);
+      const uint4 om = lds16(obase + (uint32_t)((TW - 2) * h) + p0);
+      const uint4 oc = lds16(obase + (uint32_t)((TW - 1) * h) + p0);
+      const uint4 op = __ldcg(reinterpret_cast<const uint4 *>(Go + (long long)gcr * h + p0));
+      const uint4 cn = column(TW - 1, om, oc, op);
+      __stcg(reinterpret_cast<uint4 *>(Gc + (long long)(c1 - 1) * h + p0), cn);
+      ring_publish(fl_mine + 1);
+      rb = b - 1;
+    }
+
+    // ---- interior run [ra, rb): register rolling window over shared memory
+    if (ra < rb) {
+      int cl = ra;
+      uint32_t coff = (uint32_t)(cl * h);
+      unsigned long long g = (unsigned long long)gstep * (uint32_t)(c0 + cl) + (p0 >> 3);
+      uint4 om = lds16(obase + coff - (uint32_t)h + p0);
+      uint4 oc = lds16(obase + coff + p0);
+      auto item = [&](const int par) {
+        const uint4 op = lds16(obase + coff + (uint32_t)h + p0);
+        const uint4 ce = lds16(cbase + coff + p0);
+        const uint32_t eb = cmg_smem[obase + coff + (par ? e_hi : e_lo)];
+        const uint4 side = par ? shift_down_1(oc, eb) : shift_up_1(oc, eb);
+        uint4 cn;
+        if (sample) {
+          cn = update16<true, true>(ce, om, oc, op, side, g, pass, colour, chain_word, A.rk, acc);
+        } else {
+          Accum scratch = {0u, 0u, 0u, 0u, 0u};
+          cn = update16<false, true>(ce, om, oc, op, side, g, pass, colour, chain_word, A.rk,
+                                     scratch);
+          acc.acc += scratch.acc;
+        }
+        sts16(cbase + coff + p0, cn);
+        om = oc;
+        oc = op;
+        coff += (uint32_t)h;
+        g += gstep;
+        ++cl;
+      };
+      if ((c0 + cl + colour) & 1) item(1);  // align the pair loop to par = 0
+      while (cl + 2 <= rb) {
+        item(0);
+        item(1);
+      }
+      if (cl < rb) item(0);
+    }
+
+    n_acc += acc.acc;
+    if (sample) {
+      Accum wa;
+      wa.acc = 0u;
+      wa.c1 = __reduce_add_sync(0xffffffffu, acc.c1);
+      wa.opp = __reduce_add_sync(0xffffffffu, acc.opp);
+      wa.u7 = __reduce_add_sync(0xffffffffu, acc.u7);
+      wa.sites = __reduce_add_sync(0xffffffffu, acc.sites);
+      if ((threadIdx.x & 31) == 0) {
+        long long ones, bsum;
+        accum_finish(wa, 4, ones, bsum);
+        atomicAdd(reinterpret_cast<unsigned long long *>(&s_acc[2 * slot]), (unsigned long long)ones);
+        atomicAdd(reinterpret_cast<unsigned long long *>(&s_acc[2 * slot + 1]), (unsigned long long)bsum);
+      }
+      ++slot;
+    }
+    __syncthreads();
+  }
+
+  // ---- flush the sampled sums of this launch
+  for (int i = threadIdx.x; i < 2 * slot; i += NT) {
+    long long *dst = A.sb + (long long)(i >> 1) * A.sb_slot_stride +
+                     (long long)chain * A.sb_chain_stride + (i & 1);
+    atomicAdd(reinterpret_cast<unsigned long long *>(dst), (unsigned long long)s_acc[i]);
+  }
+
+  // ---- write the interior columns back (the edge columns already are at home)
+  for (int it = threadIdx.x; it < 2 * (TW - 2) * V; it += NT) {
+    const int plane = it >= (TW - 2) * V;
+    const int r = it - plane * (TW - 2) * V;
+    const int dc = 1 + (int)__umulhi((uint32_t)r, A.v_magic);
+    const int v = r - (dc - 1) * V;
+    *reinterpret_cast<uint4 *>(G[plane] + (long long)(c0 + dc) * h + (v << 4)) =
+        lds16(soff[plane] + (uint32_t)(dc * h + (v << 4)));
+  }
+  n_acc = __reduce_add_sync(0xffffffffu, n_acc);
+  if ((threadIdx.x & 31) == 0 && n_acc) atomicAdd(A.n_accept + chain, (unsigned long long)n_acc);
+}
+
+// ---------------------------------------------------------------------------
 // k_halfsweep_bulk3d: 3-d simple cubic, n0 % 32 == 0, n1 and n2 even.
 // Same scheme; the strip runs along j inside one k-layer, the k+-1 neighbours
 // are two extra 16-byte loads per column (served by L2: a k-layer of 512^3 is
@@ -1677,6 +1930,145 @@ __global__ void __launch_bounds__(256) k_series_stats(const SeriesJob *jobs, dou
     out[3] = z_conf * sqrt(f * var / (double)N);
     k_star[blockIdx.x] = ks;
   }
+}
+
+// ---------------------------------------------------------------------------
+// Weighted observations (src/casm/monte/BasicStatistics.cc:50-73, :144-188;
+// include/casm/monte/misc/math.hh:46-55): the series is a time series of
+// unequal intervals.  One CTA per job.
+//  * W = sum(w) and the two-pointer walk of `resample` are sequential
+//    floating-point recurrences whose comparisons select samples, so thread 0
+//    evaluates them in the reference order (explicit _rn operations);
+//  * the weighted mean / variance and the lag search on the resampled series
+//    are block reductions like k_series_stats.
+// method 1: mean and variance from the weighted samples, only the
+// autocorrelation factor from the resampled series (rho = 2^(-1/(k*increment)));
+// method 2: everything from the resampled series.
+// out: {mean, variance, f_autocorr, precision, W}, k_star
+// ---------------------------------------------------------------------------
+struct WeightedJob {
+  const double *x;
+  const double *w;
+  long long n;
+  double *resampled;  // n_resamples doubles of scratch / output
+  long long n_resamples;
+  int method;         // 1 or 2; 0 = resample only (W taken from weight_sum)
+  double weight_sum;  // used when method == 0
+};
+
+__device__ __forceinline__ void block_lag_search(const double *x, long long N, double mean,
+                                                 double var, double increment, double *sh,
+                                                 double *f_out, long long *ks_out) {
+  double f = 1.0;
+  long long ks = 0;
+  if (!(fabs(var / mean) < 1e-8 || var == 0.0)) {
+    f = 1.7976931348623157e308;
+    ks = -1;
+    for (long long k = 1; k < N; ++k) {
+      const long long m = N - k;
+      double c = 0.0;
+      for (long long i = threadIdx.x; i < m; i += blockDim.x)
+        c += (x[i] - mean) * (x[i + k] - mean);
+      const double cov = block_sum_256(c, sh) / (double)m;
+      if (fabs(cov / var) <= 0.5) {
+        const double rho = pow(2.0, __ddiv_rn(-1.0, __dmul_rn((double)k, increment)));
+        f = (1.0 + rho) / (1.0 - rho);
+        ks = k;
+        break;
+      }
+    }
+  }
+  *f_out = f;
+  *ks_out = ks;
+}
+
+__global__ void __launch_bounds__(256) k_series_stats_weighted(const WeightedJob *jobs,
+                                                               double z_conf, double *out5,
+                                                               long long *k_star) {
+  __shared__ double sh[8];
+  __shared__ double sW;
+  const WeightedJob job = jobs[blockIdx.x];
+  const double *x = job.x, *w = job.w;
+  const long long n = job.n, R = job.n_resamples;
+  double *eq = job.resampled;
+  double *out = out5 + 5 * blockIdx.x;
+  if (threadIdx.x == 0) {
+    double W = job.weight_sum;
+    if (job.method != 0) {
+      W = 0.0;
+      for (long long i = 0; i < n; ++i) W = __dadd_rn(W, w[i]);
+    }
+    sW = W;
+    // resample (BasicStatistics.cc:57-72); j is kept inside the series
+    const double increment = __ddiv_rn(W, (double)R);
+    long long j = 0;
+    double W_j = 0.0;
+    for (long long i = 0; i < R; ++i) {
+      const double W_target = __dmul_rn((double)i, increment);
+      while (j < n - 1 && __dadd_rn(W_j, w[j]) < W_target) {
+        W_j = __dadd_rn(W_j, w[j]);
+        ++j;
+      }
+      eq[i] = x[j];
+    }
+  }
+  __syncthreads();
+  if (job.method == 0) return;
+  const double W = sW;
+  const double increment = __ddiv_rn(W, (double)R);
+
+  // statistics of the resampled series
+  double s = 0.0;
+  for (long long i = threadIdx.x; i < R; i += blockDim.x) s += eq[i];
+  const double mean_eq = block_sum_256(s, sh) / (double)R;
+  s = 0.0;
+  for (long long i = threadIdx.x; i < R; i += blockDim.x) {
+    const double d = eq[i] - mean_eq;
+    s += d * d;
+  }
+  const double var_eq = block_sum_256(s, sh) / (double)R;
+  double f;
+  long long ks;
+  block_lag_search(eq, R, mean_eq, var_eq, job.method == 1 ? increment : 1.0, sh, &f, &ks);
+
+  double mean = mean_eq, var = var_eq, denom = (double)R;
+  if (job.method == 1) {
+    s = 0.0;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) s += x[i] * w[i];
+    mean = block_sum_256(s, sh) / W;
+    s = 0.0;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+      const double d = x[i] - mean;
+      s += w[i] * d * d;
+    }
+    var = block_sum_256(s, sh) / W;
+    denom = W;
+  }
+  if (threadIdx.x == 0) {
+    out[0] = mean;
+    out[1] = var;
+    out[2] = f;
+    out[3] = z_conf * sqrt(f * var / denom);
+    out[4] = W;
+    k_star[blockIdx.x] = ks;
+  }
+}
+
+// weighted_observation(i) = x(i) * ((N / W) * w(i)), W summed in order
+// (src/casm/monte/checks/EquilibrationCheck.cc:145-158); two launches:
+// k_weight_factor (one thread) then k_apply_weight_factor.
+__global__ void k_weight_factor(const double *__restrict__ w, long long n, double *factor) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  double W = 0.0;
+  for (long long i = 0; i < n; ++i) W = __dadd_rn(W, w[i]);
+  *factor = __ddiv_rn((double)n, W);
+}
+__global__ void k_apply_weight_factor(const double *__restrict__ x, const double *__restrict__ w,
+                                      long long n, const double *__restrict__ factor,
+                                      double *__restrict__ y) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  y[i] = __dmul_rn(x[i], __dmul_rn(*factor, w[i]));
 }
 
 // Equilibration check, sequential semantics kept exactly

@@ -642,6 +642,12 @@ PYBIND11_MODULE(_monte_b200, m) {
         return d;
       });
 
+  // C++-only in the reference (BasicStatistics.hh:57-59); exposed for the parity tests
+  m.def("resample", [](py::object obs, py::object w, double weight_sum, Index n) {
+    return resample(to_dvec(obs), to_dvec(w), weight_sum, n);
+  }, py::arg("observations"), py::arg("sample_weight"), py::arg("sample_weight_sum"),
+     py::arg("n_equally_spaced"));
+
   py::class_<IndividualEquilibrationCheckResult>(m, "IndividualEquilibrationResult")
       .def(py::init<>())
       .def_readwrite("is_equilibrated", &IndividualEquilibrationCheckResult::is_equilibrated)

@@ -329,6 +329,40 @@ def host_series_equilibration(x, abs_precision, device=0):
     return bool(e.value), n.value
 
 
+def host_series_stats_weighted(x, w, confidence=0.95, method=1, n_resamples=10000, device=0):
+    """BasicStatisticsCalculator()(observations, sample_weight) on the device
+    (src/casm/monte/BasicStatistics.cc:144-188)."""
+    lib = _capi.load()
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    if x.size != w.size:
+        raise ValueError("Error in BasicStatisticsCalculator: observations.size() != sample_weight.size()")
+    m, p, v, W, k = C.c_double(), C.c_double(), C.c_double(), C.c_double(), C.c_int64()
+    check(lib.cmg_host_series_stats_weighted(device, _p(x, C.c_double), _p(w, C.c_double), x.size, confidence, method, n_resamples, C.byref(m), C.byref(p), C.byref(v), C.byref(W), C.byref(k)))
+    return {"mean": m.value, "calculated_precision": p.value, "variance": v.value, "weight_sum": W.value, "k_star": k.value}
+
+
+def host_series_resample(x, w, weight_sum, n_equally_spaced, device=0):
+    """resample (src/casm/monte/BasicStatistics.cc:50-73) on the device."""
+    lib = _capi.load()
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    out = np.zeros(int(n_equally_spaced), dtype=np.float64)
+    check(lib.cmg_host_series_resample(device, _p(x, C.c_double), _p(w, C.c_double), x.size, float(weight_sum), out.size, _p(out, C.c_double)))
+    return out
+
+
+def host_series_equilibration_weighted(x, w, abs_precision, device=0):
+    """Weighted branch of default_equilibration_check
+    (src/casm/monte/checks/EquilibrationCheck.cc:137-161)."""
+    lib = _capi.load()
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    e, n = C.c_int(), C.c_int64()
+    check(lib.cmg_host_series_equilibration_weighted(device, _p(x, C.c_double), _p(w, C.c_double), x.size, abs_precision, C.byref(e), C.byref(n)))
+    return bool(e.value), n.value
+
+
 def conv_l_to_bijk(n3, n_basis, l, device=0):
     lib = _capi.load()
     n3a = (C.c_int64 * 3)(*n3)

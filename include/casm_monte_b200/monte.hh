@@ -666,11 +666,33 @@ struct BasicStatisticsCalculator {
     if (observations.size() != sample_weight.size())
       throw std::runtime_error(
           "Error in BasicStatisticsCalculator: observations.size() != sample_weight.size()");
-    // weighted observations belong to the N-fold way driver
-    throw std::runtime_error(
-        "BasicStatisticsCalculator: weighted observations are outside the accelerated path");
+    // BasicStatistics.cc:163-187, evaluated on the device
+    if (method != 1 && method != 2)
+      throw std::runtime_error("Error in BasicStatisticsCalculator: invalid method");
+    BasicStatistics s;
+    double var = 0.0, W = 0.0;
+    int64_t k = 0;
+    cmg_check(cmg_host_series_stats_weighted(
+        device, observations.data(), sample_weight.data(),
+        static_cast<int64_t>(observations.size()), confidence, static_cast<int>(method),
+        static_cast<int64_t>(n_resamples), &s.mean, &s.calculated_precision, &var, &W, &k));
+    return s;
   }
 };
+/// BasicStatistics.cc:50-73: weighted observations -> n_equally_spaced observations
+inline std::vector<double> resample(std::vector<double> const &observations,
+                                    std::vector<double> const &sample_weight,
+                                    double sample_weight_sum, Index n_equally_spaced,
+                                    int device = 0) {
+  if (observations.empty() || observations.size() != sample_weight.size())
+    throw std::runtime_error("Error in resample: observations.size() != sample_weight.size()");
+  std::vector<double> out(static_cast<size_t>(n_equally_spaced));
+  cmg_check(cmg_host_series_resample(device, observations.data(), sample_weight.data(),
+                                     static_cast<int64_t>(observations.size()),
+                                     sample_weight_sum, static_cast<int64_t>(n_equally_spaced),
+                                     out.data()));
+  return out;
+}
 typedef std::function<BasicStatistics(std::vector<double> const &, std::vector<double> const &)>
     CalcStatisticsFunction;
 
@@ -705,14 +727,21 @@ inline IndividualEquilibrationCheckResult default_equilibration_check(
   }
   if (observations.empty())
     throw std::runtime_error("Error in equilibration_check: observations.size()==0");
-  if (!sample_weight.empty())
-    throw std::runtime_error(
-        "equilibration_check: weighted observations are outside the accelerated path");
   int is_eq = 0;
   int64_t n_eq = 0;
-  cmg_check(cmg_host_series_equilibration(0, observations.data(),
-                                          static_cast<int64_t>(observations.size()), prec, &is_eq,
-                                          &n_eq));
+  if (!sample_weight.empty()) {
+    // EquilibrationCheck.cc:137-161
+    if (sample_weight.size() != observations.size())
+      throw std::runtime_error(
+          "Error in equilibration_check: sample_weight.size() != observations.size()");
+    cmg_check(cmg_host_series_equilibration_weighted(
+        0, observations.data(), sample_weight.data(), static_cast<int64_t>(observations.size()),
+        prec, &is_eq, &n_eq));
+  } else {
+    cmg_check(cmg_host_series_equilibration(0, observations.data(),
+                                            static_cast<int64_t>(observations.size()), prec,
+                                            &is_eq, &n_eq));
+  }
   result.is_equilibrated = is_eq != 0;
   result.N_samples_for_equilibration = static_cast<CountType>(n_eq);
   return result;

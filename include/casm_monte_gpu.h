@@ -249,6 +249,27 @@ int cmg_host_series_stats(int device, const double *x, int64_t n, double confide
 int cmg_host_series_equilibration(int device, const double *x, int64_t n,
                                   double abs_precision, int *is_equilibrated,
                                   int64_t *n_equil);
+/* weighted observations (time series of unequal intervals):
+ * BasicStatisticsCalculator::operator()(observations, sample_weight)
+ * (src/casm/monte/BasicStatistics.cc:144-188; method 1 = weighted mean and
+ * weighted_variance (misc/math.hh:46-55) with the autocorrelation factor of the
+ * resampled series at rho = 2^(-1/(k*increment)); method 2 = all statistics
+ * from the resampled series), resample (BasicStatistics.cc:50-73) and the
+ * weighted branch of default_equilibration_check (src/casm/monte/checks/
+ * EquilibrationCheck.cc:137-161: x(i) * ((N/W) * w(i)) then the same scan).
+ * W and the resampling walk follow the reference's sequential order. */
+int cmg_host_series_stats_weighted(int device, const double *x, const double *w,
+                                   int64_t n, double confidence, int method,
+                                   int64_t n_resamples, double *mean,
+                                   double *calculated_precision, double *variance,
+                                   double *weight_sum, int64_t *k_star);
+int cmg_host_series_resample(int device, const double *x, const double *w,
+                             int64_t n, double weight_sum,
+                             int64_t n_equally_spaced, double *out);
+int cmg_host_series_equilibration_weighted(int device, const double *x,
+                                           const double *w, int64_t n,
+                                           double abs_precision,
+                                           int *is_equilibrated, int64_t *n_equil);
 
 /* ---- supercell index conversions --------------------------------------------
  * Replaces Conversions::l_to_b / l_to_ijk / bijk_to_l (include/casm/monte/

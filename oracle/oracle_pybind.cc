@@ -600,6 +600,10 @@ PYBIND11_MODULE(_monte_oracle, m) {
     double f = autocorrelation_factor(v.data(), v.size(), increment, &k);
     return py::make_tuple(f, k);
   }, py::arg("observations"), py::arg("increment") = 1.0);
+  m.def("resample", [](f64arr x, f64arr w, double weight_sum, long n) {
+    return resample(to_dvec(x), to_dvec(w), weight_sum, n);
+  }, py::arg("observations"), py::arg("sample_weight"), py::arg("sample_weight_sum"),
+     py::arg("n_equally_spaced"));
   m.def("basic_statistics",
         [](f64arr x, f64arr w, double confidence, long method, long n_resamples) {
           BasicStatisticsCalculator c(confidence, method, n_resamples);

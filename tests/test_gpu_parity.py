@@ -221,6 +221,44 @@ def test_tile2d_matches_oracle(cm, oracle, shape, variant):
     assert np.array_equal(S2, ref2["S"]) and np.array_equal(B2, ref2["B"])
 
 
+@pytest.mark.parametrize(
+    "shape,variant",
+    [
+        ([1024, 128], "ring2d"),  # 4 tiles of 32 columns, 16 column groups of 2
+        ([1024, 200], "ring2d:rp=2"),  # uneven tile widths, several launches
+        ([2048, 96], "ring2d"),  # 8 column groups
+        ([4096, 64], "ring2d:rp=1"),  # 4 column groups; one pass per launch
+        ([4096, 300], "ring2d"),  # 37 tiles of 8-9 columns
+    ],
+)
+def test_ring2d_matches_oracle(cm, oracle, shape, variant):
+    # the lattice stays in shared memory across the launch; tile edges travel
+    # through global memory under release/acquire flags
+    n = nsites(shape)
+    occ = rand_occ(n, 25)
+    T, mu = 2633.0, 0.02
+    lat = run_cb(cm, shape, occ, T, mu, 424242, 5, variant, sample_period=2)
+    assert lat.kernel_variant == "ring2d"
+    ref = oracle.checkerboard_run(shape, occ, J, T, mu, 424242, 0, 0, 5, 2)
+    assert np.array_equal(lat.download(), ref["occupation"])
+    S, B = lat.samples_sb()
+    assert np.array_equal(S, ref["S"]) and np.array_equal(B, ref["B"])
+    assert lat.counters()[1] == ref["n_accept"]
+    lat.run_passes(3, cm.MODE_CHECKERBOARD, 1)
+    ref2 = oracle.checkerboard_run(shape, ref["occupation"], J, T, mu, 424242, 0, 5, 3, 1)
+    assert np.array_equal(lat.download(), ref2["occupation"])
+    S2, B2 = lat.samples_sb(first=len(S))
+    assert np.array_equal(S2, ref2["S"]) and np.array_equal(B2, ref2["B"])
+
+
+def test_ring2d_rejects_lattices_it_cannot_hold(cm):
+    lat = cm.IsingLatticeGPU([96, 64], J=J)
+    lat.set_conditions(2633.0, 0.0)
+    lat.set_kernel_variant("ring2d")
+    with pytest.raises(cm.CmgError, match="ring2d does not fit"):
+        lat.run_passes(1, cm.MODE_CHECKERBOARD, 0)
+
+
 def test_threshold_ties_take_the_exact_path(cm, oracle):
     # mu chosen so that a threshold's top half is hit often is impossible to arrange
     # (probability 2^-15 per site); instead run enough sites that ties occur:
@@ -411,6 +449,76 @@ def test_host_series_statistics_edge_cases(cm, oracle):
             assert host_series_equilibration(x, p) == oracle.default_equilibration_check(x, abs=p)
 
 
+def test_weighted_statistics_match_oracle(cm, oracle):
+    # BasicStatistics.cc:50-73, :144-188; EquilibrationCheck.cc:137-161.  The
+    # resampling walk selects samples by floating-point comparisons, so it must
+    # be identical; the reductions are tree-ordered on the device (tolerances).
+    from casmcode_monte_b200.lattice import (
+        host_series_equilibration_weighted,
+        host_series_resample,
+        host_series_stats_weighted,
+    )
+
+    rng = np.random.default_rng(11)
+    cases = []
+    for n in (1, 2, 37, 1000, 5000):
+        x = np.cumsum(rng.normal(size=n)) * 0.1 + rng.normal(size=n) + 3.0
+        w = rng.exponential(size=n) + 1e-3  # residence times of a rejection-free walk
+        cases.append((x, w))
+    cases.append((np.full(200, 1.5), rng.exponential(size=200)))  # no variation
+    cases.append((rng.normal(size=300), np.ones(300)))  # equal weights
+    x = np.concatenate([np.linspace(4, 0, 100), np.zeros(900)]) + rng.normal(scale=0.02, size=1000)
+    cases.append((x, rng.uniform(0.5, 1.5, size=1000)))
+    for x, w in cases:
+        W = 0.0  # summed in order, as the oracle and the device do
+        for v in w:
+            W += float(v)
+        for R in (10, 1000, 10000):
+            assert np.array_equal(host_series_resample(x, w, W, R), oracle.resample(x, w, W, R))
+            for method in (1, 2):
+                st = host_series_stats_weighted(x, w, method=method, n_resamples=R)
+                mean, prec = oracle.basic_statistics(x, w, method=method, n_resamples=R)
+                assert st["weight_sum"] == W
+                assert math.isclose(st["mean"], mean, rel_tol=1e-12, abs_tol=1e-300)
+                if math.isfinite(prec) and prec < 1e300:
+                    # abs_tol: a constant series has a variance of rounding noise only
+                    assert math.isclose(st["calculated_precision"], prec, rel_tol=1e-10, abs_tol=1e-13 * max(1.0, abs(mean)))
+                else:
+                    assert not (st["calculated_precision"] < 1e300)
+        for p in (1e-3, 0.05, 0.5):
+            assert host_series_equilibration_weighted(x, w, p) == oracle.default_equilibration_check(x, w, abs=p)
+
+
+def test_weighted_statistics_through_the_mirrored_classes(cm, oracle):
+    from casmcode_monte_b200.monte import sampling
+
+    rng = np.random.default_rng(5)
+    x = np.cumsum(rng.normal(size=800)) * 0.05 + rng.normal(size=800)
+    w = rng.exponential(size=800) + 1e-3
+    for method in (1, 2):
+        calc = sampling.BasicStatisticsCalculator(confidence=0.9, weighted_observations_method=method, n_resamples=2000)
+        st = calc(x, w)
+        mean, prec = oracle.basic_statistics(x, w, confidence=0.9, method=method, n_resamples=2000)
+        assert math.isclose(st.mean, mean, rel_tol=1e-12)
+        assert math.isclose(st.calculated_precision, prec, rel_tol=1e-10)
+    calc = sampling.BasicStatisticsCalculator(weighted_observations_method=3)
+    with pytest.raises(RuntimeError, match="invalid method"):
+        calc(x, w)
+    with pytest.raises(RuntimeError, match="observations.size\\(\\) != sample_weight.size"):
+        sampling.BasicStatisticsCalculator()(x, w[:-1])
+    rp = sampling.RequestedPrecision(abs=0.05)
+    r = sampling.default_equilibration_check(x, w, rp)
+    assert (r.is_equilibrated, r.N_samples_for_equilibration) == oracle.default_equilibration_check(x, w, abs=0.05)
+
+    # a weighted completion check: Sampler columns + a sample_weight Sampler
+    s = sampling.Sampler(shape=[])
+    sw = sampling.Sampler(shape=[])
+    for xi, wi in zip(x, w):
+        s.append(np.array([xi]))
+        sw.append(np.array([wi]))
+    assert np.array_equal(sw.component(0), w)
+
+
 # ------------------------------------------------------------- conversions ----
 def test_conversions_batch(cm, oracle):
     from casmcode_monte_b200.lattice import conv_bijk_to_l, conv_l_to_bijk
@@ -460,8 +568,8 @@ def test_full_size_4096_properties(cm):
     assert int((g * (np.roll(g, -1, 0) + np.roll(g, -1, 1))).sum()) == B[-1]
     assert lat.counters(0)[1] + lat.counters(0)[2] == 3 * n
     # the tiled kernel (auto), bulk2d and the generic kernel agree at full size
-    assert lat.kernel_variant == "tile2d"
-    for variant in ("generic", "bulk2d"):
+    assert lat.kernel_variant in ("tile2d", "ring2d")
+    for variant in ("generic", "bulk2d", "tile2d", "ring2d"):
         lat3 = cm.IsingLatticeGPU(shape, J=J)
         lat3.set_conditions(2633.0, 0.0)
         lat3.seed_philox(0xC0FFEE)
