@@ -95,8 +95,8 @@ struct cmg_context {
   int tile_passes = 3;   // passes per launch of the tiled kernel (halo = 2*P columns)
   int tile_threads = 512;
   int ring_passes = 128;  // passes per cooperative launch of the ring kernel
-  unsigned int *d_ring_flags = nullptr;  // [n_chains][n_tiles][2] + error word at the end
-  size_t ring_flag_words = 0;
+  uint8_t *d_ring_mailbox = nullptr;  // [n_chains][n_tiles][side][plane][h] + error word at the end
+  size_t ring_mailbox_bytes = 0;
   unsigned int *h_ring_error = nullptr;  // pinned copy of the error word
   int coop_launch = 0;
   int sm_count = 148;
@@ -401,7 +401,7 @@ int cmg_destroy(cmg_context *c) {
     for (int side = 0; side < 2; ++side) cudaFree(c->d_halo[col][side]);
   cudaFree(c->d_flags);
   cudaFree(c->d_done);
-  cudaFree(c->d_ring_flags);
+  cudaFree(c->d_ring_mailbox);
   if (c->h_ring_error) cudaFreeHost(c->h_ring_error);
   delete c;
   return CMG_OK;
@@ -920,7 +920,7 @@ static RingPlan plan_ring(const cmg_context *c) {
   RingPlan r;
   if (c->dim != 2 || c->slab || !c->coop_launch || c->shape[0] % 1024 != 0) return r;
   const long long h = c->shape[0] / 2, n1 = c->shape[1], V = h / 16;
-  if (V > 512 || 512 % V != 0) return r;
+  if (V > 256 || 512 % V != 0) return r;  // at least two column groups per CTA
   const long long Q = 512 / V;
   long long n_tiles = c->sm_count / c->n_chains;
   n_tiles = std::min(n_tiles, n1 / (2 * Q));
@@ -1094,18 +1094,20 @@ static int launch_tile_passes_sp(cmg_context *c, const TilePlan &tp, int n_passe
 
 static int launch_ring_passes(cmg_context *c, const RingPlan &rp, int n_passes,
                               long long sample_period) {
-  const size_t words = (size_t)2 * rp.n_tiles * c->n_chains + 1;
-  if (c->ring_flag_words < words) {
-    cudaFree(c->d_ring_flags);
-    c->d_ring_flags = nullptr;
-    CU(c, cudaMalloc(&c->d_ring_flags, sizeof(unsigned int) * words));
-    c->ring_flag_words = words;
+  // edge mailbox: per tile and side one column of each plane; zeroed before every
+  // launch because its bytes carry the half-sweep stamp that validates them
+  const size_t mb_bytes = (size_t)c->n_chains * rp.n_tiles * 4 * (size_t)(c->shape[0] / 2);
+  if (c->ring_mailbox_bytes < mb_bytes + 16) {
+    cudaFree(c->d_ring_mailbox);
+    c->d_ring_mailbox = nullptr;
+    CU(c, cudaMalloc(&c->d_ring_mailbox, mb_bytes + 16));
+    c->ring_mailbox_bytes = mb_bytes + 16;
   }
   if (!c->h_ring_error) {
     CU(c, cudaMallocHost(&c->h_ring_error, sizeof(unsigned int)));
     *c->h_ring_error = 0;
   }
-  CU(c, cudaMemsetAsync(c->d_ring_flags, 0, sizeof(unsigned int) * words, c->stream));
+  CU(c, cudaMemsetAsync(c->d_ring_mailbox, 0, mb_bytes + 16, c->stream));
   RingArgs A;
   memset(&A, 0, sizeof A);
   A.L = view(c);
@@ -1127,8 +1129,8 @@ static int launch_ring_passes(cmg_context *c, const RingPlan &rp, int n_passes,
   A.w_max = rp.w_max;
   const unsigned long long V = (unsigned long long)(c->shape[0] / 32);
   A.v_magic = (uint32_t)((0x100000000ull + V - 1) / V);
-  A.flags = c->d_ring_flags;
-  A.error = c->d_ring_flags + (words - 1);
+  A.mailbox = c->d_ring_mailbox;
+  A.error = reinterpret_cast<unsigned int *>(c->d_ring_mailbox + mb_bytes);
   cudaError_t e = cudaFuncSetAttribute(k_ring2d<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)rp.smem);
   if (e != cudaSuccess) return fail(c, CMG_ECUDA, cudaGetErrorString(e));
@@ -1270,7 +1272,7 @@ int cmg_run_passes(cmg_context *c, int64_t n_passes, int mode, int64_t sample_pe
     return fail(c, CMG_EINVAL, "tile2d does not fit this lattice (need dim 2, n0 % 64 == 0, short columns)");
   if (variant == V_RING2D && !plan_ring(c).ok)
     return fail(c, CMG_EINVAL,
-                "ring2d does not fit this lattice (need dim 2, n0 in {1024..16384} a power of two, "
+                "ring2d does not fit this lattice (need dim 2, n0 in {1024..8192} a power of two, "
                 "the lattice within the GPU's shared memory, cooperative launch)");
   c->variant_name = variant_str(variant);
   long long n_new = 0;

@@ -140,6 +140,7 @@ constexpr int kSmemLaneLo = 64;
 constexpr int kSmemLaneHi = 128;
 constexpr int kSmemSmall = 192;  // kernels that only use the 16-entry tables
 constexpr int kSmemPair = 1024;
+constexpr int kPairCopy = 64;  // byte offset of the odd lanes' copy of every pair-table row
 constexpr int kSmemTile = kSmemPair + 14 * 1024;
 
 // Fast-compare lane of a table entry (see accept_mask4_fast): 0x7FFF + the
@@ -158,8 +159,11 @@ __device__ __forceinline__ void load_accept_table(const ChainTables *tab, bool w
   if (!with_pairs) return;
   for (int e = threadIdx.x; e < 14 * 14; e += blockDim.x) {
     const int A = e % 14, B = e / 14;
-    *reinterpret_cast<uint32_t *>(cmg_smem + kSmemPair + 4 * A + 1024 * B) =
-        fast_lane(tab->thr_m1[A]) | (fast_lane(tab->thr_m1[B]) << 16);
+    const uint32_t pair = fast_lane(tab->thr_m1[A]) | (fast_lane(tab->thr_m1[B]) << 16);
+    *reinterpret_cast<uint32_t *>(cmg_smem + kSmemPair + 4 * A + 1024 * B) = pair;
+    // second copy 16 banks further on (rows only use 56 of their 1024 bytes): odd
+    // lanes look up there, which halves the bank conflicts of the random lookups
+    *reinterpret_cast<uint32_t *>(cmg_smem + kSmemPair + kPairCopy + 4 * A + 1024 * B) = pair;
   }
 }
 // byte_off = 4 * table index
@@ -451,14 +455,17 @@ __device__ __forceinline__ uint4 update16(uint4 ce, uint4 om, uint4 oc, uint4 op
   const uint4 rb = site_group_random(group0 + 1, chain_word, pass, colour, 0, rk);
   const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
   uint32_t idx[4], m[4], tmax = 0;
+  // PAIR: bytes 0 and 2 also carry the lane's pair-table copy (0 or kPairCopy)
+  const uint32_t copy2 = PAIR ? (threadIdx.x & 1u) * (uint32_t)(kPairCopy | (kPairCopy << 16)) : 0u;
 #pragma unroll
   for (int w = 0; w < 4; ++w) {
-    idx[w] = (nw[w] + nw[w] + cw[w]) << 2;  // 4 * (2*n_up + b) per byte
+    idx[w] = ((nw[w] + nw[w] + cw[w]) << 2) + copy2;  // 4 * (2*n_up + b) per byte
     m[w] = accept_mask4_fast<PAIR>(idx[w], rw[2 * w], rw[2 * w + 1], tmax);
   }
   if (any_tie(tmax)) {  // a tie somewhere in these 16 sites (probability 16 * 2^-15)
-    const uint4 mm = resolve_ties16(make_uint4(idx[0], idx[1], idx[2], idx[3]), group0, pass,
-                                    colour, chain_word, rk[0], rk[1]);
+    const uint4 mm = resolve_ties16(make_uint4(idx[0] - copy2, idx[1] - copy2, idx[2] - copy2,
+                                               idx[3] - copy2),
+                                    group0, pass, colour, chain_word, rk[0], rk[1]);
     m[0] = mm.x;
     m[1] = mm.y;
     m[2] = mm.z;
@@ -965,19 +972,21 @@ __global__ void __launch_bounds__(NT, 1) k_tile2d(TileArgs A) {
 // Every CTA of a cooperative launch (grid <= #SMs, one CTA per SM) owns a
 // tile of whole columns for the entire launch and keeps both colour planes of
 // it in shared memory; nothing is recomputed.  The only data that crosses a
-// tile edge is one boundary column per side and half-sweep, and it travels
-// through the column's home location in global memory (L2-resident):
-//   * the column groups that own local column 0 / TW-1 update those columns
-//     first, store them to shared AND global memory, fence, and bump the
-//     tile's left / right flag (one increment per warp);
-//   * the neighbour's boundary warps wait on that flag (acquire) before
-//     loading the column with L1-bypassing loads straight into the register
-//     window -- there is no halo in shared memory and no extra CTA barrier.
-// A boundary column published at half-sweep s is consumed at the start of
-// half-sweep s+1, a whole half-sweep of interior work later, so the wait is
-// normally already satisfied.  The publisher can only overwrite a home
-// location at s+2, after it has itself waited for the consumer's s+1 flag,
-// which the consumer raises after reading: no read counters are needed.
+// tile edge is one boundary column per side and half-sweep.  It travels
+// through a mailbox in global memory (L2-resident) whose bytes validate
+// themselves: a published byte is  b | stamp << 1  with stamp = 1 + s mod 127
+// of the half-sweep s that produced it (occupation bytes only use bit 0), and
+// the mailbox is zeroed before the launch.  The consumer thread loads its own
+// 16-byte vector with a gpu-coherent load and accepts it when all 16 stamps
+// are the expected one -- no flags, no fences, and tearing of the 16-byte
+// access would be detected.  A slot is rewritten two half-sweeps later, by a
+// thread that has by then consumed the neighbour's next vector, which the
+// neighbour produced after reading this one: the dependency chain orders the
+// reuse.  The column groups that own an edge start their run at the edge
+// (the right-hand group walks its columns downwards), so an edge is published
+// one column-time into the half-sweep and consumed at the start of the next;
+// the consumer issues its load before the CTA barrier that ends the previous
+// half-sweep, so the L2 round trip overlaps the barrier wait.
 // Random numbers are counter-based, so the trajectory is the one of every
 // other kernel.  Any number of passes per launch (sample slots permitting).
 // ---------------------------------------------------------------------------
@@ -997,36 +1006,27 @@ struct RingArgs {
   int w_max;                     // widest tile (smem plane = w_max*h bytes)
   uint32_t v_magic;              // ceil(2^32 / V), V = h/16
   int chain_offset;              // global index of chain 0
-  unsigned int *flags;           // [chain][tile][2], zero at launch: {left, right} columns published
-  unsigned int *error;           // raised if a flag wait timed out
+  uint8_t *mailbox;              // [chain][tile][side][plane][h], zero at launch
+  unsigned int *error;           // raised if an edge wait timed out
 };
+constexpr int kRingMaxPasses = 256;
 
-__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int *p) {
-  unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ uint4 ld_relaxed_gpu_v4(const void *p) {
+  uint4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p)
+               : "memory");
   return v;
 }
-// lane 0 polls, the warp follows; bounded so that a scheduling accident cannot hang the GPU
-__device__ __forceinline__ void ring_wait(const unsigned int *flag, unsigned int target,
-                                          unsigned int *error) {
-  if ((threadIdx.x & 31) == 0) {
-    unsigned int spins = 0;
-    while (ld_acquire_gpu_u32(flag) < target) {
-      if (++spins > (1u << 22)) {
-        atomicExch(error, 1u);
-        break;
-      }
-    }
-  }
-  __syncwarp();
+__device__ __forceinline__ void st_relaxed_gpu_v4(void *p, uint4 v) {
+  asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y),
+               "r"(v.z), "r"(v.w)
+               : "memory");
 }
-__device__ __forceinline__ void ring_publish(unsigned int *flag) {
-  __threadfence();
-  __syncwarp();
-  if ((threadIdx.x & 31) == 0) atomicAdd(flag, 1u);
+__device__ __forceinline__ bool ring_stamp_ok(uint4 v, uint32_t expect) {
+  return ((((v.x ^ expect) | (v.y ^ expect)) | ((v.z ^ expect) | (v.w ^ expect))) & 0xfefefefeu) == 0u;
 }
-
-constexpr int kRingMaxPasses = 256;
 
 template <int NT>
 __global__ void __launch_bounds__(NT, 1) k_ring2d(RingArgs A) {
@@ -1056,26 +1056,34 @@ __global__ void __launch_bounds__(NT, 1) k_ring2d(RingArgs A) {
     sts16(soff[plane] + (uint32_t)(cl * h + (v << 4)),
           __ldg(reinterpret_cast<const uint4 *>(G[plane] + (long long)(c0 + cl) * h + (v << 4))));
   }
-  __syncthreads();
 
-  // column groups: Q groups of V threads; group q walks columns [a, b)
+  // column groups: Q >= 2 groups of V threads; group q owns columns [a, b).
+  // Group 0 starts at the left edge and walks up, group Q-1 starts at the
+  // right edge and walks down, the others walk up.
   const int Q = NT / V, q = threadIdx.x / V;
   const uint32_t p0 = (uint32_t)(threadIdx.x % V) << 4;
   const int base = TW / Q, rem = TW - base * Q;
   const int a = q * base + min(q, rem);
   const int b = a + base + (q < rem ? 1 : 0);
-  const bool has_left = (q == 0), has_right = (q == Q - 1);
-  const int tl = tile == 0 ? A.n_tiles - 1 : tile - 1;
-  const int tr = tile + 1 == A.n_tiles ? 0 : tile + 1;
-  unsigned int *fl_mine = A.flags + 2 * ((long long)chain * A.n_tiles + tile);
-  const unsigned int *fl_left = A.flags + 2 * ((long long)chain * A.n_tiles + tl) + 1;
-  const unsigned int *fl_right = A.flags + 2 * ((long long)chain * A.n_tiles + tr);
-  const int gcl = c0 == 0 ? n1 - 1 : c0 - 1;  // global columns of the two neighbours' edges
-  const int gcr = c1 == n1 ? 0 : c1;
-  const unsigned int warps_per_col = (unsigned int)(V >> 5);
+  const bool down = (q == Q - 1);
+  const bool edge = (q == 0) || down;
+  const int cl_first = down ? b - 1 : a;
+  const int n_cols = b - a;
+  const int dh = down ? -h : h;                   // byte step between consecutive columns of the run
   const uint32_t gstep = (uint32_t)h >> 3;
+  const long long dg = down ? -(long long)gstep : (long long)gstep;
   const uint32_t e_lo = (p0 == 0) ? (uint32_t)h - 1u : p0 - 1u;
   const uint32_t e_hi = (p0 + 16u == (uint32_t)h) ? 0u : p0 + 16u;
+  // mailbox slots: ours (publish) and the facing one of the neighbour (consume)
+  const int nb = down ? (tile + 1 == A.n_tiles ? 0 : tile + 1) : (tile == 0 ? A.n_tiles - 1 : tile - 1);
+  const long long slot_bytes = 2ll * h;  // two planes per (tile, side)
+  uint8_t *mb_out = A.mailbox + (((long long)chain * A.n_tiles + tile) * 2 + (down ? 1 : 0)) * slot_bytes + p0;
+  const uint8_t *mb_in = A.mailbox + (((long long)chain * A.n_tiles + nb) * 2 + (down ? 0 : 1)) * slot_bytes + p0;
+  // the neighbour's edge column at home (first half-sweep of the launch)
+  const int gc_nb = down ? (c1 == n1 ? 0 : c1) : (c0 == 0 ? n1 - 1 : c0 - 1);
+  uint4 hv = make_uint4(0u, 0u, 0u, 0u);
+  if (edge) hv = __ldcg(reinterpret_cast<const uint4 *>(G[1] + (long long)gc_nb * h + p0));
+  __syncthreads();
 
   unsigned int n_acc = 0;
   int slot = 0;
@@ -1087,20 +1095,37 @@ __global__ void __launch_bounds__(NT, 1) k_ring2d(RingArgs A) {
                         ((A.pass_phase + pl + 1) % A.sample_period) == 0;
     const uint32_t cbase = colour ? soff[1] : soff[0];
     const uint32_t obase = colour ? soff[0] : soff[1];
-    uint8_t *Gc = G[colour];
-    const uint8_t *Go = G[colour ^ 1];
+    const uint32_t stampw = ((uint32_t)(s % 127) + 1u) * 0x02020202u;  // this half-sweep's stamp << 1
     Accum acc = {0u, 0u, 0u, 0u, 0u};
 
-    // one column: centre vector and edge byte from shared memory, the three
-    // opposite-colour vectors from the caller; returns the new centre vector
-    auto column = [&](int cl, uint4 om, uint4 oc, uint4 op) -> uint4 {
-      const uint32_t coff = (uint32_t)(cl * h);
-      const int gc = c0 + cl;
-      const int par = (gc + colour) & 1;  // i = 2p + par
+    int cl = cl_first;
+    uint32_t coff = (uint32_t)(cl * h);
+    unsigned long long g = (unsigned long long)gstep * (uint32_t)(c0 + cl) + (p0 >> 3);
+    // the column behind the start of the run: the neighbour's edge, or shared memory
+    uint4 om;
+    if (edge) {
+      if (s > 0) {
+        const uint32_t expect = ((uint32_t)((s - 1) % 127) + 1u) * 0x02020202u;
+        unsigned int spins = 0;
+        while (!ring_stamp_ok(hv, expect)) {
+          hv = ld_relaxed_gpu_v4(mb_in + (colour ^ 1) * h);
+          if (++spins > (1u << 22)) {  // bounded: report instead of hanging the GPU
+            atomicExch(A.error, 1u);
+            break;
+          }
+        }
+      }
+      om = make_uint4(hv.x & 0x01010101u, hv.y & 0x01010101u, hv.z & 0x01010101u, hv.w & 0x01010101u);
+    } else {
+      om = lds16(obase + coff - (uint32_t)dh + p0);
+    }
+    uint4 oc = lds16(obase + coff + p0);
+    const int cl_pub = edge ? cl_first : -1;
+    auto item = [&](const int par) {
+      const uint4 op = lds16(obase + coff + (uint32_t)dh + p0);
       const uint4 ce = lds16(cbase + coff + p0);
       const uint32_t eb = cmg_smem[obase + coff + (par ? e_hi : e_lo)];
       const uint4 side = par ? shift_down_1(oc, eb) : shift_up_1(oc, eb);
-      const unsigned long long g = (unsigned long long)gstep * (uint32_t)gc + (p0 >> 3);
       uint4 cn;
       if (sample) {
         cn = update16<true, true>(ce, om, oc, op, side, g, pass, colour, chain_word, A.rk, acc);
@@ -1111,67 +1136,26 @@ __global__ void __launch_bounds__(NT, 1) k_ring2d(RingArgs A) {
         acc.acc += scratch.acc;
       }
       sts16(cbase + coff + p0, cn);
-      return cn;
+      if (cl == cl_pub)  // our edge column: publish it, stamped
+        st_relaxed_gpu_v4(mb_out + colour * h, make_uint4(cn.x | stampw, cn.y | stampw,
+                                                          cn.z | stampw, cn.w | stampw));
+      om = oc;
+      oc = op;
+      coff += (uint32_t)dh;
+      g += (unsigned long long)dg;
+      cl += down ? -1 : 1;
     };
-
-    // ---- boundary columns first: consume the neighbour's edge, publish ours
-    int ra = a, rb = b;
-    if (has_left) {
-      if (s > 0) ring_wait(fl_left, warps_per_col * (unsigned int)s, A.error);
-      const uint4 om = __ldcg(reinterpret_cast<const uint4 *>(Go + (long long)gcl * h + p0));
-      const uint4 oc = lds16(obase + p0);
-      const uint4 op = lds16(obase + (uint32_t)h + p0);
-      const uint4 cn = column(0, om, oc, op);
-      __stcg(reinterpret_cast<uint4 *>(Gc + (long long)c0 * h + p0), cn);
-      ring_publish(fl_mine);
-      ra = 1;
+    int left = n_cols;
+    if ((c0 + cl + colour) & 1) {  // align the pair loop to par = 0
+      item(1);
+      --left;
     }
-    if (has_right) {  // tiles are at least two columns wide (host plan)
-      if (s > 0) ring_wait(fl_right, warps_per_col * (unsigned int)s, A.error);
-      const uint4 om = lds16(obase + (uint32_t)((TW - 2) * h) + p0);
-      const uint4 oc = lds16(obase + (uint32_t)((TW - 1) * h) + p0);
-      const uint4 op = __ldcg(reinterpret_cast<const uint4 *>(Go + (long long)gcr * h + p0));
-      const uint4 cn = column(TW - 1, om, oc, op);
-      __stcg(reinterpret_cast<uint4 *>(Gc + (long long)(c1 - 1) * h + p0), cn);
-      ring_publish(fl_mine + 1);
-      rb = b - 1;
+    while (left >= 2) {
+      item(0);
+      item(1);
+      left -= 2;
     }
-
-    // ---- interior run [ra, rb): register rolling window over shared memory
-    if (ra < rb) {
-      int cl = ra;
-      uint32_t coff = (uint32_t)(cl * h);
-      unsigned long long g = (unsigned long long)gstep * (uint32_t)(c0 + cl) + (p0 >> 3);
-      uint4 om = lds16(obase + coff - (uint32_t)h + p0);
-      uint4 oc = lds16(obase + coff + p0);
-      auto item = [&](const int par) {
-        const uint4 op = lds16(obase + coff + (uint32_t)h + p0);
-        const uint4 ce = lds16(cbase + coff + p0);
-        const uint32_t eb = cmg_smem[obase + coff + (par ? e_hi : e_lo)];
-        const uint4 side = par ? shift_down_1(oc, eb) : shift_up_1(oc, eb);
-        uint4 cn;
-        if (sample) {
-          cn = update16<true, true>(ce, om, oc, op, side, g, pass, colour, chain_word, A.rk, acc);
-        } else {
-          Accum scratch = {0u, 0u, 0u, 0u, 0u};
-          cn = update16<false, true>(ce, om, oc, op, side, g, pass, colour, chain_word, A.rk,
-                                     scratch);
-          acc.acc += scratch.acc;
-        }
-        sts16(cbase + coff + p0, cn);
-        om = oc;
-        oc = op;
-        coff += (uint32_t)h;
-        g += gstep;
-        ++cl;
-      };
-      if ((c0 + cl + colour) & 1) item(1);  // align the pair loop to par = 0
-      while (cl + 2 <= rb) {
-        item(0);
-        item(1);
-      }
-      if (cl < rb) item(0);
-    }
+    if (left) item(0);
 
     n_acc += acc.acc;
     if (sample) {
@@ -1189,6 +1173,9 @@ __global__ void __launch_bounds__(NT, 1) k_ring2d(RingArgs A) {
       }
       ++slot;
     }
+    // the neighbour published its edge of this colour early in this half-sweep:
+    // fetch it now, so that the round trip overlaps the barrier
+    if (edge) hv = ld_relaxed_gpu_v4(mb_in + colour * h);
     __syncthreads();
   }
 
@@ -1199,12 +1186,12 @@ __global__ void __launch_bounds__(NT, 1) k_ring2d(RingArgs A) {
     atomicAdd(reinterpret_cast<unsigned long long *>(dst), (unsigned long long)s_acc[i]);
   }
 
-  // ---- write the interior columns back (the edge columns already are at home)
-  for (int it = threadIdx.x; it < 2 * (TW - 2) * V; it += NT) {
-    const int plane = it >= (TW - 2) * V;
-    const int r = it - plane * (TW - 2) * V;
-    const int dc = 1 + (int)__umulhi((uint32_t)r, A.v_magic);
-    const int v = r - (dc - 1) * V;
+  // ---- write the owned columns back
+  for (int it = threadIdx.x; it < 2 * TW * V; it += NT) {
+    const int plane = it >= TW * V;
+    const int r = it - plane * TW * V;
+    const int dc = (int)__umulhi((uint32_t)r, A.v_magic);
+    const int v = r - dc * V;
     *reinterpret_cast<uint4 *>(G[plane] + (long long)(c0 + dc) * h + (v << 4)) =
         lds16(soff[plane] + (uint32_t)(dc * h + (v << 4)));
   }
