@@ -935,14 +935,17 @@ static RingPlan plan_ring(const cmg_context *c) {
   return r;
 }
 
-static int pick_variant(cmg_context *c) {
+static int pick_variant(cmg_context *c, long long n_passes) {
   if (c->forced_variant != V_AUTO) return c->forced_variant;
   // the tiled kernel wins while a half-sweep is short enough for launch ramp
   // and L2 latency to matter; very large batches stream better through bulk2d
   if (plan_tiles(c, c->tile_passes).ok && c->n_sites * c->n_chains <= (1ll << 25)) {
     // a lattice too large for one CTA but not for the GPU's shared memory stays
     // resident across the launch (no halo recomputation): 4096^2 1.4e12 vs 0.98e12
-    if (plan_tiles(c, c->tile_passes).n_tiles > 1 && plan_ring(c).ok) return V_RING2D;
+    // (a ring launch costs ~18 us of staging and set-up: worth it from 4 passes per call,
+    // measured on one 4096^2 lattice; the trajectories are identical either way)
+    if (n_passes >= 4 && plan_tiles(c, c->tile_passes).n_tiles > 1 && plan_ring(c).ok)
+      return V_RING2D;
     return V_TILE2D;
   }
   if (c->dim == 2 && c->shape[0] % 32 == 0) return V_BULK2D;
@@ -962,24 +965,28 @@ static int pick_js(cmg_context *c, int variant) {
   const double slots = (double)c->sm_count * per_sm;
   const long long V = c->shape[0] / 32;
   const long long layers = variant == V_BULK3D ? c->shape[2] : 1;
-  // Strip length: long strips amortise the two extra column loads and the
-  // pipeline fill at the strip start; the CTA count they imply should fill
-  // whole waves of `slots` CTAs (a 1.7-wave launch idles a quarter of the GPU
-  // during its tail).  Multiples of four match the unrolled column loop.
+  // Strip length.  A launch takes ceil(CTAs / slots) waves and a wave lasts as
+  // long as its longest strip plus the strip start-up (two extra column loads,
+  // pipeline fill, table load: ~4 column-times), so minimise waves * (js + 4).
+  // A ragged last strip does not shorten a wave, which is why strip lengths that
+  // divide n1 win (512^3: js = 64 -> 512 CTAs in one wave, 1.17e12 against
+  // 1.12e12 for js = 20 in 2.8 waves).  Multiples of four match the unrolled
+  // column loop; 3-d strips must be even (two strips share a warp when n0 = 512
+  // and the column parity has to be warp-uniform).
   static const int cand[] = {2,  4,  6,  8,  12, 16, 20, 24, 28, 32,  36,  40, 44,
                              48, 52, 56, 60, 64, 72, 80, 88, 96, 104, 112, 120, 128};
   int best = 16;
-  double best_score = -1.0;
+  double best_cost = 1e300;
   for (int js : cand) {
     if (js > c->shape[1] && js > 2) continue;
-    if (variant == V_BULK3D && js > 48) continue;  // measured: long strips lose L2 reuse across k-layers
     const long long strips = (c->shape[1] + js - 1) / js;
     const double ctas = (double)nblocks(V * strips * layers, 128) * c->n_chains;
-    const double waves = ctas / slots;
-    const double fill = waves / std::ceil(waves);
-    const double score = fill * js / (js + 2.0);
-    if (score > best_score) {
-      best_score = score;
+    // measured on 512^3: strips that leave a ragged remainder run ~10 % slower
+    // than their CTA count predicts (js = 60: 1.06e12, js = 64: 1.19e12)
+    const double ragged = (c->shape[1] % js) ? 1.1 : 1.0;
+    const double cost = std::ceil(ctas / slots) * (js + 4.0) * ragged;
+    if (cost <= best_cost) {  // ties: the longer strip
+      best_cost = cost;
       best = js;
     }
   }
@@ -1263,7 +1270,7 @@ int cmg_run_passes(cmg_context *c, int64_t n_passes, int mode, int64_t sample_pe
                 "checkerboard mode needs even extents; use CMG_MODE_SERIAL_REFERENCE");
   if (c->slab)
     return fail(c, CMG_ESTATE, "slab contexts are stepped with cmg_slab_half_sweep");
-  const int variant = pick_variant(c);
+  const int variant = pick_variant(c, n_passes);
   if (variant == V_BULK2D && !(c->dim == 2 && c->shape[0] % 32 == 0))
     return fail(c, CMG_EINVAL, "bulk2d needs dim == 2 and n0 % 32 == 0");
   if (variant == V_BULK3D && !(c->dim == 3 && c->shape[0] % 32 == 0))
