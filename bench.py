@@ -268,7 +268,7 @@ def ours(args):
     for ch in range(n_lat):
         lat.download(ch, out=host_occ.numpy()[ch])
     host_out = torch.empty((n_lat, per_lat), dtype=torch.int32).pin_memory()
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = max(1, min(args.steps, 5))
     n_groups = max(1, min(args.e2e_groups, n_lat))
     while n_lat % n_groups:
         n_groups -= 1
@@ -288,25 +288,41 @@ def ours(args):
             lg.set_kernel_variant(args.e2e_variant)
         groups.append(lg)
 
-    def e2e_step():
-        for g, lg in enumerate(groups):
-            for k in range(per_group):
-                # H2D of the int32 occupation + colour-plane split (async on the group's stream)
-                lg.upload(host_occ.numpy()[g * per_group + k], k)
-            lg.clear_samples()
-            lg.run_passes(PASSES_PER_STEP, MODE_CHECKERBOARD, 1)
+    def enqueue(g):
+        # inputs of one step for group g: H2D of the int32 occupation + colour-plane
+        # split, then the sweeps -- all asynchronous on the group's stream
+        lg = groups[g]
+        for k in range(per_group):
+            lg.upload(host_occ.numpy()[g * per_group + k], k)
+        lg.clear_samples()
+        lg.run_passes(PASSES_PER_STEP, MODE_CHECKERBOARD, 1)
+
+    def collect(g):
+        # results of one step for group g (blocks on the group's stream only)
+        lg = groups[g]
         out = []
-        for g, lg in enumerate(groups):
-            for k in range(per_group):
-                lg.download(k, out=host_out.numpy()[g * per_group + k])  # D2H of the final occupation
-                out.append(lg.samples_sb(k))  # D2H of the sampled (S, B) series
+        for k in range(per_group):
+            lg.download(k, out=host_out.numpy()[g * per_group + k])  # D2H of the final occupation
+            out.append(lg.samples_sb(k))  # D2H of the sampled (S, B) series
         return out
 
-    e2e_step()
+    # Every step uploads all lattices, sweeps them and downloads all results.
+    # The calls are ordered per group -- collect step s, enqueue step s+1 -- so
+    # that while the host waits for one group's download the other groups'
+    # copies and sweeps are already queued (H2D, D2H and compute overlap).
+    for g in range(n_groups):
+        enqueue(g)
+    for g in range(n_groups):
+        collect(g)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
+    for g in range(n_groups):
+        enqueue(g)
+    for s in range(e2e_steps):
+        for g in range(n_groups):
+            collect(g)
+            if s + 1 < e2e_steps:
+                enqueue(g)
     barrier()
     e2e_s = time.perf_counter() - t0
     if dist is not None:
@@ -365,7 +381,8 @@ def ours(args):
             "contexts": n_groups,
             "gpu_launches": e2e_launches,
             "note": "pinned int32 host buffers in and out through cmg_upload/download_occupation_i32; "
-                    f"{n_groups} contexts of {per_group} lattices on separate streams so copies overlap sweeps",
+                    f"{n_groups} contexts of {per_group} lattice(s) on separate streams, calls ordered collect(step s) -> enqueue(step s+1) per context, "
+                    "so H2D, D2H and sweeps of different contexts overlap; every step uploads and downloads every lattice",
         },
         "gpu_launches": launches,
         "roofline": {
@@ -409,8 +426,8 @@ def ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--e2e-groups", type=int, default=4, help="contexts the end-to-end leg splits the lattices into")
-    ap.add_argument("--e2e-variant", default="bulk2d", help="kernel variant of the end-to-end contexts (concurrent streams: the strip kernel co-schedules, the one-CTA-per-SM tile kernel does not)")
+    ap.add_argument("--e2e-groups", type=int, default=8, help="contexts the end-to-end leg splits the lattices into")
+    ap.add_argument("--e2e-variant", default="auto", help="kernel variant of the end-to-end contexts (auto: one lattice per context runs resident in shared memory, k_ring2d, while the other contexts copy)")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
