@@ -97,6 +97,52 @@ def config2():
     }
 
 
+def config2seq():
+    """The sweep as the reference runs one: ONE 4096^2 supercell heated through
+    T_c, every temperature starting from the previous final state."""
+    temps = [1800.0, 2200.0, 2500.0, 2600.0, 2633.0, 2660.0, 2800.0, 3200.0]
+    n0 = n1 = 4096
+    n = n0 * n1
+    n_eq, n_meas = 1000, 4000
+    tc = 2 * J / (KB * math.log(1 + math.sqrt(2)))
+    lat = cm.IsingLatticeGPU([n0, n1], J=J)
+    lat.seed_philox(0xC0FFEE)
+    lat.fill(1)
+    rows, total_dt = [], 0.0
+    for T in temps:
+        lat.set_conditions(T, 0.0)
+        lat.run_passes(n_eq, cm.MODE_CHECKERBOARD, 0)
+        lat.clear_samples()
+        lat.reset_counters()
+        lat.sync()
+        dt = timed(lambda: (lat.run_passes(n_meas, cm.MODE_CHECKERBOARD, 1), lat.sync()))
+        total_dt += dt
+        st_e = lat.series_stats(cm.Q_FORMATION_ENERGY, 0)
+        st_x = lat.series_stats(cm.Q_PARAM_COMPOSITION, 0)
+        e = lat.samples(cm.Q_POTENTIAL_ENERGY, 0)
+        x = lat.samples(cm.Q_PARAM_COMPOSITION, 0)
+        row = {
+            "T": T, "attempts_per_s": n * n_meas / dt,
+            "e_formation": st_e["mean"], "e_precision": st_e["calculated_precision"], "e_onsager": onsager_energy_per_site(T),
+            "x": st_x["mean"], "x_precision": st_x["calculated_precision"], "x_onsager": onsager_x(T),
+            "heat_capacity_per_site_kB": n * float(np.var(e)) / (KB * T * T) / KB,
+            "susceptibility_per_site": n * float(np.var(x)) / (KB * T),
+            "acceptance": lat.counters(0)[1] / (lat.counters(0)[1] + lat.counters(0)[2]),
+        }
+        if abs(T - tc) > 150:
+            row["e_within_3sigma"] = bool(abs(row["e_formation"] - row["e_onsager"]) < 3 * row["e_precision"] / Z95 + 2e-7)
+            row["x_within_3sigma"] = bool(abs(row["x"] - row["x_onsager"]) < 3 * row["x_precision"] / Z95 + 2e-6)
+        rows.append(row)
+    return {
+        "config": "2 (sequential form): ONE 2D 4096x4096 SGC supercell heated through T_c, 8 temperatures one after the other, 1000 + 4000 passes each, sample every pass",
+        "kernel": lat.kernel_variant,
+        "attempts_per_s": len(temps) * n * n_meas / total_dt,
+        "seconds_measured": total_dt,
+        "T_c": tc,
+        "rows": rows,
+    }
+
+
 def config3():
     shape = [512, 512, 512]
     n = 512**3
@@ -162,4 +208,4 @@ def config4():
 
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "config2"
-    print(json.dumps({"config2": config2, "config3": config3, "config4": config4}[which]()), flush=True)
+    print(json.dumps({"config2": config2, "config2seq": config2seq, "config3": config3, "config4": config4}[which]()), flush=True)
