@@ -475,14 +475,23 @@ __device__ __forceinline__ uint4 update16(uint4 ce, uint4 om, uint4 oc, uint4 op
   for (int w = 0; w < 4; ++w) {
     cw[w] ^= m[w] & 0x01010101u;
     a.acc = (unsigned int)__dp4a((int)m[w], (int)0xffffffffu, (int)a.acc);  // (-1)*(-1) per accepted site
-    if (SAMPLE) {
-      const uint32_t flip7 = ~(cw[w] * 0xffu) & 0x07070707u;  // 7 where b = 0
-      a.u7 = __dp4a(nw[w] ^ flip7, 0x01010101u, a.u7);
-      a.c1 = __dp4a(cw[w], 0x01010101u, a.c1);
-      a.opp = __dp4a(ow[w], 0x01010101u, a.opp);
-    }
   }
-  if (SAMPLE) a.sites += 16;
+  if (SAMPLE) {
+    // Byte sums of the four words first (plain adds: a byte holds at most
+    // 4 * 7), one dot product per quantity afterwards.  Per byte
+    // t = 0x80 - b is 0x80 (b = 0) or 0x7f (b = 1), so ~t & 7 is 7 where b = 0:
+    // x = n ^ (~t & 7) = (b ? n : 7 - n) in one LOP3, with no multiply.
+    uint32_t x[4];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const uint32_t t = 0x80808080u - cw[w];
+      x[w] = nw[w] ^ (~t & 0x07070707u);
+    }
+    a.u7 = __dp4a((x[0] + x[1]) + (x[2] + x[3]), 0x01010101u, a.u7);
+    a.c1 = __dp4a((cw[0] + cw[1]) + (cw[2] + cw[3]), 0x01010101u, a.c1);
+    a.opp = __dp4a((ow[0] + ow[1]) + (ow[2] + ow[3]), 0x01010101u, a.opp);
+    a.sites += 16;
+  }
   return make_uint4(cw[0], cw[1], cw[2], cw[3]);
 }
 
@@ -1121,41 +1130,44 @@ __global__ void __launch_bounds__(NT, 1) k_ring2d(RingArgs A) {
     }
     uint4 oc = lds16(obase + coff + p0);
     const int cl_pub = edge ? cl_first : -1;
-    auto item = [&](const int par) {
-      const uint4 op = lds16(obase + coff + (uint32_t)dh + p0);
-      const uint4 ce = lds16(cbase + coff + p0);
-      const uint32_t eb = cmg_smem[obase + coff + (par ? e_hi : e_lo)];
-      const uint4 side = par ? shift_down_1(oc, eb) : shift_up_1(oc, eb);
-      uint4 cn;
-      if (sample) {
-        cn = update16<true, true>(ce, om, oc, op, side, g, pass, colour, chain_word, A.rk, acc);
-      } else {
-        Accum scratch = {0u, 0u, 0u, 0u, 0u};
-        cn = update16<false, true>(ce, om, oc, op, side, g, pass, colour, chain_word, A.rk,
-                                   scratch);
-        acc.acc += scratch.acc;
+    // the run of this half-sweep, compiled once per sampling mode so that a loop
+    // body holds one variant of the update only
+    auto run = [&](auto sample_tag) {
+      constexpr bool kSample = decltype(sample_tag)::value;
+      auto item = [&](const int par) {
+        const uint4 op = lds16(obase + coff + (uint32_t)dh + p0);
+        const uint4 ce = lds16(cbase + coff + p0);
+        const uint32_t eb = cmg_smem[obase + coff + (par ? e_hi : e_lo)];
+        const uint4 side = par ? shift_down_1(oc, eb) : shift_up_1(oc, eb);
+        const uint4 cn =
+            update16<kSample, true>(ce, om, oc, op, side, g, pass, colour, chain_word, A.rk, acc);
+        sts16(cbase + coff + p0, cn);
+        if (cl == cl_pub)  // our edge column: publish it, stamped
+          st_relaxed_gpu_v4(mb_out + colour * h, make_uint4(cn.x | stampw, cn.y | stampw,
+                                                            cn.z | stampw, cn.w | stampw));
+        om = oc;
+        oc = op;
+        coff += (uint32_t)dh;
+        g += (unsigned long long)dg;
+        cl += down ? -1 : 1;
+      };
+      int left = n_cols;
+      if ((c0 + cl + colour) & 1) {  // align the pair loop to par = 0
+        item(1);
+        --left;
       }
-      sts16(cbase + coff + p0, cn);
-      if (cl == cl_pub)  // our edge column: publish it, stamped
-        st_relaxed_gpu_v4(mb_out + colour * h, make_uint4(cn.x | stampw, cn.y | stampw,
-                                                          cn.z | stampw, cn.w | stampw));
-      om = oc;
-      oc = op;
-      coff += (uint32_t)dh;
-      g += (unsigned long long)dg;
-      cl += down ? -1 : 1;
+      while (left >= 2) {
+        item(0);
+        item(1);
+        left -= 2;
+      }
+      if (left) item(0);
     };
-    int left = n_cols;
-    if ((c0 + cl + colour) & 1) {  // align the pair loop to par = 0
-      item(1);
-      --left;
+    if (sample) {
+      run(std::true_type{});
+    } else {
+      run(std::false_type{});
     }
-    while (left >= 2) {
-      item(0);
-      item(1);
-      left -= 2;
-    }
-    if (left) item(0);
 
     n_acc += acc.acc;
     if (sample) {
