@@ -893,39 +893,48 @@ __global__ void __launch_bounds__(NT, 1) k_tile2d(TileArgs A) {
         const uint32_t wrap_off = (uint32_t)((W - 1) * h);
         uint4 om = lds16(obase + ((periodic && cl == 0) ? wrap_off : coff - (uint32_t)h) + p0);
         uint4 oc = lds16(obase + coff + p0);
-        auto item = [&](const int par) {
-          const uint32_t noff = (periodic && cl == W - 1) ? 0u : coff + (uint32_t)h;
-          const uint4 op = lds16(obase + noff + p0);
-          const uint4 ce = lds16(cbase + coff + p0);
-          const uint32_t eb = cmg_smem[obase + coff + (par ? e_hi : e_lo)];
-          const uint4 side = par ? shift_down_1(oc, eb) : shift_up_1(oc, eb);
-          const bool owned = periodic || (cl >= H && cl < H + TW);
-          uint4 cn;
-          if (sample && owned) {
-            cn = update16<true, true>(ce, om, oc, op, side, g, pass, colour, chain_word, A.rk, acc);
-          } else {
-            Accum scratch = {0u, 0u, 0u, 0u, 0u};
-            cn = update16<false, true>(ce, om, oc, op, side, g, pass, colour, chain_word, A.rk,
-                                       scratch);
-            if (owned) acc.acc += scratch.acc;
+        // compiled once per sampling mode, so a loop body holds one variant of the update
+        auto run = [&](auto sample_tag) {
+          constexpr bool kSample = decltype(sample_tag)::value;
+          auto item = [&](const int par) {
+            const uint32_t noff = (periodic && cl == W - 1) ? 0u : coff + (uint32_t)h;
+            const uint4 op = lds16(obase + noff + p0);
+            const uint4 ce = lds16(cbase + coff + p0);
+            const uint32_t eb = cmg_smem[obase + coff + (par ? e_hi : e_lo)];
+            const uint4 side = par ? shift_down_1(oc, eb) : shift_up_1(oc, eb);
+            const bool owned = periodic || (cl >= H && cl < H + TW);
+            uint4 cn;
+            if (kSample && owned) {
+              cn = update16<true, true>(ce, om, oc, op, side, g, pass, colour, chain_word, A.rk, acc);
+            } else {
+              Accum scratch = {0u, 0u, 0u, 0u, 0u};
+              cn = update16<false, true>(ce, om, oc, op, side, g, pass, colour, chain_word, A.rk,
+                                         scratch);
+              if (owned) acc.acc += scratch.acc;
+            }
+            sts16(cbase + coff + p0, cn);
+            om = oc;
+            oc = op;
+            coff += (uint32_t)h;
+            g += gstep;
+            ++cl;
+            if (++gc == n1) {  // halo columns past the lattice edge wrap around
+              gc = 0;
+              g -= gwrap;
+            }
+          };
+          if ((gc + colour) & 1) item(1);  // i = 2p + par; align the pair loop to par = 0
+          while (cl + 2 <= cl1) {
+            item(0);
+            item(1);
           }
-          sts16(cbase + coff + p0, cn);
-          om = oc;
-          oc = op;
-          coff += (uint32_t)h;
-          g += gstep;
-          ++cl;
-          if (++gc == n1) {  // halo columns past the lattice edge wrap around
-            gc = 0;
-            g -= gwrap;
-          }
+          if (cl < cl1) item(0);
         };
-        if ((gc + colour) & 1) item(1);  // i = 2p + par; align the pair loop to par = 0
-        while (cl + 2 <= cl1) {
-          item(0);
-          item(1);
+        if (sample) {
+          run(std::true_type{});
+        } else {
+          run(std::false_type{});
         }
-        if (cl < cl1) item(0);
       }
     } else {
       const int items = (hi - lo) * V;
