@@ -1,6 +1,6 @@
 """Per-call cost of short run_passes calls: ring2d vs tile2d on one 4096^2 lattice."""
 import os, sys, json
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from casmcode_monte_b200 import MODE_CHECKERBOARD, IsingLatticeGPU
 
