@@ -8,12 +8,15 @@ composition every pass) over one synthetic lattice.
 
 Workload (BASELINE.json configs[1]): the 2-d square 4096x4096 SGC Ising
 temperature sweep through T_c, J = 0.1 eV: the eight temperatures of the sweep
-(1800 ... 3200 K, T_c = 2633 K among them) run as eight independent lattices
-("chains") of one context on one GPU, mu = 0.  With N > 1 GPUs every rank runs
-the same eight-temperature sweep at its own exchange potential mu_r (a
-(T, mu) phase-diagram grid sharded over GPUs, no communication: weak scaling).
-The throughput of a single 4096x4096 lattice at T_c alone is reported next to
-it as `single_lattice`.
+(1800 ... 3200 K, T_c = 2633 K among them) are eight independent lattices on
+one GPU, mu = 0, swept one after the other; the lattice being swept lives in the
+shared memory of the whole GPU (k_ring2d, a cooperative launch of up to 128
+passes).  With N > 1 GPUs every rank runs the same eight-temperature sweep at
+its own exchange potential mu_r (a (T, mu) phase-diagram grid sharded over
+GPUs, no communication: weak scaling).  Reported next to it: the same eight
+lattices advanced concurrently by the HBM-streaming strip kernel
+(`streaming_8_lattices`, k_halfsweep_bulk2d, with its DRAM traffic) and a
+single lattice at T_c alone (`single_lattice`).
 
 `--impl reference` times the CPU restatement of the reference loop
 (oracle/oracle_bench, one independent chain per host core) on a bounded sample
@@ -163,7 +166,8 @@ def reference_arm(args):
 def workload_config(n_gpus):
     return {
         "workload": f"2D square Ising SGC temperature sweep through T_c, {N0}x{N1} supercell, checkerboard sweeps: "
-        f"{len(T_SWEEP)} temperatures {T_SWEEP} K as {len(T_SWEEP)} concurrent lattices per GPU, J=0.1 eV, "
+        f"{len(T_SWEEP)} temperatures {T_SWEEP} K as {len(T_SWEEP)} lattices per GPU swept one after the other "
+        f"(the lattice being swept is resident in shared memory), J=0.1 eV, "
         + ("mu=0" if n_gpus == 1 else f"rank r at mu_r={MU_GRID[:n_gpus]} eV ((T, mu) grid sharded over {n_gpus} GPUs, no communication)"),
         "lattice": [N0, N1],
         "lattices_per_gpu": len(T_SWEEP),
@@ -171,7 +175,8 @@ def workload_config(n_gpus):
         "sample_period": 1,
         "initial_state": "i.i.d. +1/-1 (Philox, seed 12345)",
         "philox_seed": "0xC0FFEE + rank",
-        "l2": "L2 flushed (256 MiB write) between timed steps; the 8 x 16 MiB int8 planes (128 MiB) slightly exceed the 126 MB L2",
+        "l2": "L2 flushed (256 MiB write) between timed steps; the 8 x 16 MiB int8 planes (128 MiB) slightly exceed the 126 MB L2, "
+              "every launch stages its lattice from global memory",
         "timing": "CUDA events on the launching stream per step, summed; max over ranks",
     }
 
@@ -214,30 +219,49 @@ def ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def one_step(timed):
+    # the eight lattices as eight one-lattice contexts on the timing stream (same
+    # global Philox streams as chains 0..7 of `lat` through set_chain_offset)
+    per_lat = N0 * N1
+    host_occ = torch.empty((n_lat, per_lat), dtype=torch.int32).pin_memory()
+    sweep = []
+    for k, T in enumerate(T_SWEEP):
+        lat.download(k, out=host_occ.numpy()[k])
+        lk = IsingLatticeGPU([N0, N1], device=local_rank, J=J)
+        lk.set_stream(stream.cuda_stream)
+        lk.set_conditions(T, mu)
+        lk.seed_philox(0xC0FFEE + rank)
+        lk.set_chain_offset(k)
+        if args.value_variant != "auto":
+            lk.set_kernel_variant(args.value_variant)
+        lk.upload(host_occ.numpy()[k])
+        sweep.append(lk)
+
+    def one_step(ctxs):
         with torch.cuda.stream(stream):
             flush.fill_(1)  # L2 flush, outside the events
             e0 = torch.cuda.Event(enable_timing=True)
             e1 = torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            lat.run_passes(PASSES_PER_STEP, MODE_CHECKERBOARD, 1)
+            for c in ctxs:
+                c.run_passes(PASSES_PER_STEP, MODE_CHECKERBOARD, 1)
             e1.record(stream)
         return (e0, e1)
 
     for _ in range(args.warmup):
-        one_step(False)
+        one_step(sweep)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    launches0 = lat.launch_count
-    lat.clear_samples()
+    launches0 = sum(c.launch_count for c in sweep)
+    for c in sweep:
+        c.clear_samples()
     barrier()
     t_wall0 = time.perf_counter()
-    evs = [one_step(True) for _ in range(args.steps)]
+    evs = [one_step(sweep) for _ in range(args.steps)]
     barrier()
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop()
-    launches = lat.launch_count - launches0
+    launches = sum(c.launch_count for c in sweep) - launches0
     launches_per_rank = launches
     ms_steps = [a.elapsed_time(b) for a, b in evs]
     total_ms = sum(ms_steps)
@@ -252,10 +276,28 @@ def ours(args):
     value = attempts / (total_ms * 1e-3)
     # sanity: the run really sampled and moved
     i_tc = T_SWEEP.index(T_HEADLINE)
-    S, B = lat.samples_sb(i_tc)
+    S, B = sweep[i_tc].samples_sb(0)
     assert len(S) == PASSES_PER_STEP * args.steps
     x_mean = float((N0 * N1 + S.astype(np.float64)).mean() / 2.0 / (N0 * N1))
-    acc_tc = lat.counters(i_tc)
+    acc_tc = sweep[i_tc].counters(0)
+    main_variant = sweep[0].kernel_variant
+    for c in sweep:
+        c.close()
+
+    # ---- the same eight lattices advanced concurrently by the HBM-streaming strip
+    # kernel (one context, eight chains): the workload whose DRAM traffic is real
+    lat.set_kernel_variant("bulk2d")
+    for _ in range(2):
+        one_step([lat])
+    torch.cuda.synchronize()
+    st_launch0 = lat.launch_count
+    st_evs = [one_step([lat]) for _ in range(max(1, min(args.steps, 3)))]
+    torch.cuda.synchronize()
+    st_ms = sum(a.elapsed_time(b) for a, b in st_evs)
+    st_launches = lat.launch_count - st_launch0
+    st_value = float(n_sites) * PASSES_PER_STEP * len(st_evs) / (st_ms * 1e-3)
+    st_bytes_per_launch = ALGO_BYTES_PER_ATTEMPT * float(n_sites) * PASSES_PER_STEP * len(st_evs) / max(1, st_launches)
+    st_launch_s = st_ms * 1e-3 / max(1, st_launches)
 
     # ---- end to end through the C ABI with HOST buffers (H2D + D2H in the timed region)
     # The lattices of a temperature sweep are independent, so the end-to-end leg
@@ -263,17 +305,12 @@ def ours(args):
     # Philox streams through set_chain_offset) on their own CUDA streams: the
     # upload of one group overlaps the sweeps of another, and the downloads of the
     # first groups overlap the sweeps of the last.
-    per_lat = N0 * N1
-    host_occ = torch.empty((n_lat, per_lat), dtype=torch.int32).pin_memory()
-    for ch in range(n_lat):
-        lat.download(ch, out=host_occ.numpy()[ch])
     host_out = torch.empty((n_lat, per_lat), dtype=torch.int32).pin_memory()
     e2e_steps = max(1, min(args.steps, 5))
     n_groups = max(1, min(args.e2e_groups, n_lat))
     while n_lat % n_groups:
         n_groups -= 1
     per_group = n_lat // n_groups
-    main_variant = lat.kernel_variant
     lat.close()
     groups = []
     for g in range(n_groups):
@@ -392,16 +429,30 @@ def ours(args):
             "peak_source": peak_src,
             "unit": "GB/s",
             "frac": achieved / peak,
-            # dram__bytes_read.sum + dram__bytes_write.sum of one k_halfsweep_bulk2d launch of this
-            # workload from the ncu --set full capture in profiles/ncu_bulk2d_sweep8_r1f.txt
-            # (134.3 MB read + 27.9 MB written back within the launch window; the rest of the
-            # 67 MB written stays dirty in the 126 MB L2 and is evicted by the next launch)
-            "traffic": 162.2e6 if main_variant == "bulk2d" else None,
+            # dram__bytes_read.sum + dram__bytes_write.sum of one k_ring2d launch from the ncu
+            # --set full capture in profiles/ncu_ring2d_r1h.txt: 16.8 MB read (the staging of the
+            # 16 MiB lattice) + 7 KB written inside the launch window (the write-back stays dirty
+            # in L2) -- the lattice lives in shared memory, so DRAM traffic is far BELOW the
+            # algorithmic bytes; for the HBM-streaming form see streaming_8_lattices
+            "traffic": 16.84e6 if main_variant == "ring2d" else (162.2e6 if main_variant == "bulk2d" else None),
             "kernel": ("k_halfsweep_" if main_variant.startswith("bulk") else "k_") + main_variant,
             "algorithmic_bytes_per_launch": bytes_per_launch,
             "avg_launch_us": avg_launch_s * 1e6,
             "launches_per_step": n_launches_step,
-            "note": "3 B per attempted flip (int8, two colour planes); the kernel is bound by integer issue (Philox4x32-10: the IMAD.WIDE pipe is 60-66 % busy, issue slots 62-64 %), not by HBM: see DESIGN.md / profiles/",
+            "note": "3 B per attempted flip (int8, two colour planes) is the algorithmic HBM traffic of a half-sweep; k_ring2d keeps the lattice on chip for up to 128 passes per launch, so the fraction compares its rate with what an HBM-streaming kernel could at best do. The update is bound by integer issue (Philox4x32-10: FMA-heavy pipe 67 % busy, issue slots 60 %): see DESIGN.md / profiles/",
+        },
+        "streaming_8_lattices": {
+            "value": st_value,
+            "unit": UNIT,
+            "kernel": "k_halfsweep_bulk2d",
+            "workload": "the same eight lattices as eight chains of one context, advanced concurrently, every half-sweep streaming 201 MB through HBM (128 MiB of planes > L2)",
+            "achieved": st_bytes_per_launch / st_launch_s / 1e9,
+            "frac": st_bytes_per_launch / st_launch_s / 1e9 / peak,
+            "avg_launch_us": st_launch_s * 1e6,
+            "algorithmic_bytes_per_launch": st_bytes_per_launch,
+            # profiles/ncu_bulk2d_sweep8_r1f.txt: 134.3 MB read + 27.9 MB written back within the
+            # launch window (the rest of the 67 MB written stays dirty in L2 until the next launch)
+            "traffic": 162.2e6,
         },
         "single_lattice": {"value": single_value, "unit": UNIT, "kernel": "k_" + single_variant, "workload": f"one {N0}x{N1} lattice at T=2633 K, sampling every pass", "frac_of_roofline": single_value * ALGO_BYTES_PER_ATTEMPT / 1e9 / peak},
         "wall_s_timed_region": t_wall,
@@ -426,6 +477,7 @@ def ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--value-variant", default="auto", help="kernel variant of the timed sweep (auto: k_ring2d)")
     ap.add_argument("--e2e-groups", type=int, default=8, help="contexts the end-to-end leg splits the lattices into")
     ap.add_argument("--e2e-variant", default="auto", help="kernel variant of the end-to-end contexts (auto: one lattice per context runs resident in shared memory, k_ring2d, while the other contexts copy)")
     ap.add_argument("--steps", type=int, default=10)
