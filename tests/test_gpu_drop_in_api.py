@@ -317,8 +317,8 @@ def test_run_serial_reference_mode_is_trajectory_exact(api, oracle, shape, T, mu
                 assert math.isclose(a["stats"]["calculated_precision"], b["calculated_precision"], rel_tol=1e-9)
 
 
-def test_run_checkerboard_mode_matches_oracle_checkerboard(api, oracle):
-    shape = (64, 48)
+@pytest.mark.parametrize("shape", [(64, 48), (1024, 512)])  # the second runs resident in shared memory (k_ring2d)
+def test_run_checkerboard_mode_matches_oracle_checkerboard(api, oracle, shape):
     n = shape[0] * shape[1]
     occ = np.random.default_rng(3).choice(np.array([-1, 1], dtype=np.int32), size=n)
     T, mu = 2633.0, 0.05
