@@ -286,7 +286,13 @@ int cmg_conv_bijk_to_l(int device, const int64_t *n3, int64_t n_basis,
 int cmg_launch_count(const cmg_context *ctx, int64_t *n_launches);
 /* name of the half-sweep kernel variant the context selected ("bulk2d", ...) */
 const char *cmg_kernel_variant(const cmg_context *ctx);
-/* force a variant ("auto", "generic", "bulk2d", "bulk3d", "smem"); for tests */
+/* force a variant, for tests and measurements: "auto", "generic", "bulk2d"
+ * (HBM-streaming strips), "bulk3d", "tile2d" (shared-memory tiles with
+ * temporal blocking), "ring2d" (the whole lattice resident in the shared memory
+ * of the GPU, one cooperative launch of many passes); options are appended as
+ * ":js=56" (strip length), ":p=3" / ":nt=512" (tile passes / threads) and
+ * ":rp=128" (passes per ring launch).  Every variant produces the same
+ * trajectory. */
 int cmg_set_kernel_variant(cmg_context *ctx, const char *name);
 
 #ifdef __cplusplus
