@@ -1642,6 +1642,29 @@ int cmg_accept_probe(cmg_context *c, int chain, const double *uniforms, uint8_t 
   return CMG_OK;
 }
 
+// ---- scratch memory of the statistics calls -----------------------------------------
+// Stream-ordered allocations from the device's default pool, which is told to
+// keep its memory: a completion check makes a dozen of these calls, and
+// cudaMalloc / cudaFree (a device synchronisation each) dominated its cost.
+#define scratch_alloc(pp, bytes, stream) scratch_alloc_raw(reinterpret_cast<void **>(pp), bytes, stream)
+static cudaError_t scratch_alloc_raw(void **p, size_t bytes, cudaStream_t stream) {
+  static thread_local bool pool_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !pool_set[dev]) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    pool_set[dev] = true;
+  }
+  return cudaMallocAsync(p, bytes, stream);
+}
+static void scratch_free(void *p, cudaStream_t stream) {
+  if (p) cudaFreeAsync(p, stream);
+}
+
 // ---- series statistics ---------------------------------------------------------------
 static int run_stats_jobs(cmg_context *c, cudaStream_t stream, const std::vector<SeriesJob> &jobs,
                           double confidence, double *mean, double *prec, double *var,
@@ -1651,9 +1674,9 @@ static int run_stats_jobs(cmg_context *c, cudaStream_t stream, const std::vector
   SeriesJob *dj = nullptr;
   double *dout = nullptr;
   long long *dk = nullptr;
-  CU(c, cudaMalloc(&dj, sizeof(SeriesJob) * n));
-  CU(c, cudaMalloc(&dout, sizeof(double) * 4 * n));
-  CU(c, cudaMalloc(&dk, sizeof(long long) * n));
+  CU(c, scratch_alloc(&dj, sizeof(SeriesJob) * n, stream));
+  CU(c, scratch_alloc(&dout, sizeof(double) * 4 * n, stream));
+  CU(c, scratch_alloc(&dk, sizeof(long long) * n, stream));
   CU(c, cudaMemcpyAsync(dj, jobs.data(), sizeof(SeriesJob) * n, cudaMemcpyHostToDevice, stream));
   k_series_stats<<<n, 256, 0, stream>>>(dj, z_confidence(confidence), dout, dk);
   if (c) ++c->launches;
@@ -1669,9 +1692,9 @@ static int run_stats_jobs(cmg_context *c, cudaStream_t stream, const std::vector
     if (prec) prec[i] = h[4 * i + 3];
     if (k_star) k_star[i] = hk[i];
   }
-  cudaFree(dj);
-  cudaFree(dout);
-  cudaFree(dk);
+  scratch_free(dj, stream);
+  scratch_free(dout, stream);
+  scratch_free(dk, stream);
   return CMG_OK;
 }
 
@@ -1682,11 +1705,19 @@ static int run_equil_jobs(cmg_context *c, cudaStream_t stream, const std::vector
   SeriesJob *dj = nullptr;
   int *de = nullptr;
   long long *dn = nullptr;
-  CU(c, cudaMalloc(&dj, sizeof(SeriesJob) * n));
-  CU(c, cudaMalloc(&de, sizeof(int) * n));
-  CU(c, cudaMalloc(&dn, sizeof(long long) * n));
+  CU(c, scratch_alloc(&dj, sizeof(SeriesJob) * n, stream));
+  CU(c, scratch_alloc(&de, sizeof(int) * n, stream));
+  CU(c, scratch_alloc(&dn, sizeof(long long) * n, stream));
   CU(c, cudaMemcpyAsync(dj, jobs.data(), sizeof(SeriesJob) * n, cudaMemcpyHostToDevice, stream));
-  k_series_equilibration<<<nblocks(n, 32), 32, 0, stream>>>(dj, n, prec, de, dn);
+  // the series is staged in shared memory when it fits (up to ~24 k samples)
+  static const long long kEquilSmemDoubles = 24 * 1024;
+  cudaFuncSetAttribute(k_series_equilibration, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)(kEquilSmemDoubles * sizeof(double)));  // per device: set every time
+  long long n_max = 0;
+  for (const SeriesJob &j : jobs) n_max = std::max<long long>(n_max, j.n);
+  const long long stage = n_max <= kEquilSmemDoubles ? n_max : 0;  // 0: read global memory
+  k_series_equilibration<<<n, kEquilThreads, (size_t)stage * sizeof(double), stream>>>(
+      dj, n, prec, de, dn, stage);
   if (c) ++c->launches;
   CU(c, cudaGetLastError());
   std::vector<int> he(n);
@@ -1698,9 +1729,9 @@ static int run_equil_jobs(cmg_context *c, cudaStream_t stream, const std::vector
     if (is_eq) is_eq[i] = he[i];
     if (n_eq) n_eq[i] = hn[i];
   }
-  cudaFree(dj);
-  cudaFree(de);
-  cudaFree(dn);
+  scratch_free(dj, stream);
+  scratch_free(de, stream);
+  scratch_free(dn, stream);
   return CMG_OK;
 }
 
@@ -1794,13 +1825,13 @@ int cmg_host_series_stats(int device, const double *x, int64_t n, double confide
     return fail(nullptr, CMG_EINVAL, "Error in BasicStatisticsCalculator: observations.size()==0");
   double *d = nullptr;
   cmg_context *c = nullptr;
-  CU(c, cudaMalloc(&d, sizeof(double) * (size_t)n));
+  CU(c, scratch_alloc(&d, sizeof(double) * (size_t)n, 0));
   CU(c, cudaMemcpy(d, x, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
   std::vector<SeriesJob> jobs(1);
   jobs[0].x = d;
   jobs[0].n = n;
   rc = run_stats_jobs(nullptr, 0, jobs, confidence, mean, calculated_precision, variance, k_star);
-  cudaFree(d);
+  scratch_free(d, 0);
   return rc;
 }
 
@@ -1812,13 +1843,13 @@ int cmg_host_series_equilibration(int device, const double *x, int64_t n, double
     return fail(nullptr, CMG_EINVAL, "Error in equilibration_check: observations.size()==0");
   double *d = nullptr;
   cmg_context *c = nullptr;
-  CU(c, cudaMalloc(&d, sizeof(double) * (size_t)n));
+  CU(c, scratch_alloc(&d, sizeof(double) * (size_t)n, 0));
   CU(c, cudaMemcpy(d, x, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
   std::vector<SeriesJob> jobs(1);
   jobs[0].x = d;
   jobs[0].n = n;
   rc = run_equil_jobs(nullptr, 0, jobs, abs_precision, is_equilibrated, n_equil);
-  cudaFree(d);
+  scratch_free(d, 0);
   return rc;
 }
 
@@ -1830,12 +1861,12 @@ static int run_weighted_job(const double *x, const double *w, int64_t n, double 
   double *dx = nullptr, *dw = nullptr, *deq = nullptr, *dout = nullptr;
   long long *dk = nullptr;
   WeightedJob *dj = nullptr;
-  CU(c, cudaMalloc(&dx, sizeof(double) * (size_t)n));
-  CU(c, cudaMalloc(&dw, sizeof(double) * (size_t)n));
-  CU(c, cudaMalloc(&deq, sizeof(double) * (size_t)n_resamples));
-  CU(c, cudaMalloc(&dout, sizeof(double) * 5));
-  CU(c, cudaMalloc(&dk, sizeof(long long)));
-  CU(c, cudaMalloc(&dj, sizeof(WeightedJob)));
+  CU(c, scratch_alloc(&dx, sizeof(double) * (size_t)n, 0));
+  CU(c, scratch_alloc(&dw, sizeof(double) * (size_t)n, 0));
+  CU(c, scratch_alloc(&deq, sizeof(double) * (size_t)n_resamples, 0));
+  CU(c, scratch_alloc(&dout, sizeof(double) * 5, 0));
+  CU(c, scratch_alloc(&dk, sizeof(long long), 0));
+  CU(c, scratch_alloc(&dj, sizeof(WeightedJob), 0));
   CU(c, cudaMemcpy(dx, x, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
   CU(c, cudaMemcpy(dw, w, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
   WeightedJob job{dx, dw, (long long)n, deq, (long long)n_resamples, method, weight_sum};
@@ -1849,12 +1880,12 @@ static int run_weighted_job(const double *x, const double *w, int64_t n, double 
     CU(c, cudaMemcpy(resampled_out, deq, sizeof(double) * (size_t)n_resamples,
                      cudaMemcpyDeviceToHost));
   if (k_star) *k_star = hk;
-  cudaFree(dx);
-  cudaFree(dw);
-  cudaFree(deq);
-  cudaFree(dout);
-  cudaFree(dk);
-  cudaFree(dj);
+  scratch_free(dx, 0);
+  scratch_free(dw, 0);
+  scratch_free(deq, 0);
+  scratch_free(dout, 0);
+  scratch_free(dk, 0);
+  scratch_free(dj, 0);
   return CMG_OK;
 }
 
@@ -1897,10 +1928,10 @@ int cmg_host_series_equilibration_weighted(int device, const double *x, const do
     return fail(nullptr, CMG_EINVAL, "Error in equilibration_check: observations.size()==0");
   cmg_context *c = nullptr;
   double *dx = nullptr, *dw = nullptr, *dy = nullptr, *df = nullptr;
-  CU(c, cudaMalloc(&dx, sizeof(double) * (size_t)n));
-  CU(c, cudaMalloc(&dw, sizeof(double) * (size_t)n));
-  CU(c, cudaMalloc(&dy, sizeof(double) * (size_t)n));
-  CU(c, cudaMalloc(&df, sizeof(double)));
+  CU(c, scratch_alloc(&dx, sizeof(double) * (size_t)n, 0));
+  CU(c, scratch_alloc(&dw, sizeof(double) * (size_t)n, 0));
+  CU(c, scratch_alloc(&dy, sizeof(double) * (size_t)n, 0));
+  CU(c, scratch_alloc(&df, sizeof(double), 0));
   CU(c, cudaMemcpy(dx, x, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
   CU(c, cudaMemcpy(dw, w, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
   k_weight_factor<<<1, 32>>>(dw, n, df);
@@ -1910,10 +1941,10 @@ int cmg_host_series_equilibration_weighted(int device, const double *x, const do
   jobs[0].x = dy;
   jobs[0].n = n;
   rc = run_equil_jobs(nullptr, 0, jobs, abs_precision, is_equilibrated, n_equil);
-  cudaFree(dx);
-  cudaFree(dw);
-  cudaFree(dy);
-  cudaFree(df);
+  scratch_free(dx, 0);
+  scratch_free(dw, 0);
+  scratch_free(dy, 0);
+  scratch_free(df, 0);
   return rc;
 }
 
