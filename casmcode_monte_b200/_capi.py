@@ -85,6 +85,7 @@ SIGNATURES = {
     "cmg_host_series_equilibration_weighted": (C.c_int, [C.c_int, _f64p, _f64p, C.c_int64, C.c_double, _intp, _i64p]),
     "cmg_conv_l_to_bijk": (C.c_int, [C.c_int, _i64p, C.c_int64, _i64p, C.c_int64, _i64p]),
     "cmg_conv_bijk_to_l": (C.c_int, [C.c_int, _i64p, C.c_int64, _i64p, C.c_int64, _i64p]),
+    "cmg_set_energy_form": (C.c_int, [_ctx, C.c_int]),
     "cmg_launch_count": (C.c_int, [_ctx, _i64p]),
     "cmg_kernel_variant": (C.c_char_p, [_ctx]),
     "cmg_set_kernel_variant": (C.c_int, [_ctx, C.c_char_p]),

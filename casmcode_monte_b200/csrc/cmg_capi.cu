@@ -90,6 +90,10 @@ struct cmg_context {
   long long dbl_capacity = 0;
   long long dbl_valid = 0;
 
+  // use_nlist = false energy form (2-d, checkerboard): per-sample line counts
+  bool nonlist = false;
+  int *d_lines = nullptr;  // [sample][chain][n0 + n1]
+  long long lines_capacity = 0;
   int forced_variant = V_AUTO;
   int js = 0;  // 0 = auto
   int tile_passes = 3;   // passes per launch of the tiled kernel (halo = 2*P columns)
@@ -402,6 +406,7 @@ int cmg_destroy(cmg_context *c) {
   cudaFree(c->d_flags);
   cudaFree(c->d_done);
   cudaFree(c->d_ring_mailbox);
+  cudaFree(c->d_lines);
   if (c->h_ring_error) cudaFreeHost(c->h_ring_error);
   delete c;
   return CMG_OK;
@@ -1165,6 +1170,37 @@ static const char *variant_str(int v) {
   }
 }
 
+// line counts of sample `slot` for every chain (use_nlist = false energy form)
+static int sample_lines(cmg_context *c, long long slot) {
+  const long long per = c->shape[0] + c->shape[1];
+  if (c->lines_capacity <= slot) {
+    long long cap = c->lines_capacity ? c->lines_capacity : 256;
+    while (cap <= slot) cap *= 2;
+    int *nb = nullptr;
+    CU(c, cudaMalloc(&nb, sizeof(int) * (size_t)cap * c->n_chains * per));
+    if (c->d_lines && slot > 0)
+      CU(c, cudaMemcpyAsync(nb, c->d_lines, sizeof(int) * (size_t)slot * c->n_chains * per,
+                            cudaMemcpyDeviceToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    cudaFree(c->d_lines);
+    c->d_lines = nb;
+    c->lines_capacity = cap;
+  }
+  int *dst = c->d_lines + (size_t)slot * c->n_chains * per;
+  CU(c, cudaMemsetAsync(dst, 0, sizeof(int) * (size_t)c->n_chains * per, c->stream));
+  const int js = 64;
+  const long long V = c->shape[0] / 32;
+  const long long strips = (c->shape[1] + js - 1) / js;
+  for (int ch = 0; ch < c->n_chains; ++ch) {
+    int *row = dst + (size_t)ch * per;
+    k_line_xor_planes<<<nblocks(V * strips, 128), 128, 0, c->stream>>>(view(c), ch, js, row,
+                                                                       row + c->shape[0]);
+    ++c->launches;
+  }
+  CU(c, cudaGetLastError());
+  return CMG_OK;
+}
+
 static int check_ready(cmg_context *c) {
   for (int ch = 0; ch < c->n_chains; ++ch)
     if (!c->h_tabs[ch].valid) return fail(c, CMG_ESTATE, "conditions not set for every chain");
@@ -1270,6 +1306,22 @@ int cmg_run_passes(cmg_context *c, int64_t n_passes, int mode, int64_t sample_pe
                 "checkerboard mode needs even extents; use CMG_MODE_SERIAL_REFERENCE");
   if (c->slab)
     return fail(c, CMG_ESTATE, "slab contexts are stepped with cmg_slab_half_sweep");
+  if (c->nonlist && sample_period > 0) {
+    // the row/column sums need the state at every sampled pass: advance to the next
+    // sample, count the unequal pairs of every line, repeat
+    if (c->dim != 2) return fail(c, CMG_EUNSUPPORTED, "the use_nlist=false energy form is 2-d only");
+    c->nonlist = false;  // the inner calls take the ordinary path
+    long long left = n_passes;
+    rc = CMG_OK;
+    while (left > 0 && rc == CMG_OK) {
+      const long long chunk = std::min<long long>(left, sample_period - (c->n_pass % sample_period));
+      rc = cmg_run_passes(c, chunk, mode, sample_period);
+      if (rc == CMG_OK && (c->n_pass % sample_period) == 0) rc = sample_lines(c, c->n_samples - 1);
+      left -= chunk;
+    }
+    c->nonlist = true;
+    return rc;
+  }
   const int variant = pick_variant(c, n_passes);
   if (variant == V_BULK2D && !(c->dim == 2 && c->shape[0] % 32 == 0))
     return fail(c, CMG_EINVAL, "bulk2d needs dim == 2 and n0 % 32 == 0");
@@ -1569,6 +1621,14 @@ static int ensure_doubles(cmg_context *c) {
         tmp, first, count, c->n_sites, c->d_tabs + ch, base, base + c->dbl_capacity,
         base + 2 * c->dbl_capacity);
     ++c->launches;
+    if (c->nonlist && c->d_lines) {
+      // formation and potential energy in the row/column form (model.hh:273-285)
+      const long long per = c->shape[0] + c->shape[1];
+      k_nonlist_to_doubles<<<nblocks(count, 64), 64, 0, c->stream>>>(
+          c->d_lines + (size_t)ch * per, per * c->n_chains, c->shape[0], c->shape[1], tmp, first,
+          count, c->n_sites, c->d_tabs + ch, base + c->dbl_capacity, base + 2 * c->dbl_capacity);
+      ++c->launches;
+    }
   }
   CU(c, cudaGetLastError());
   CU(c, cudaStreamSynchronize(c->stream));
@@ -2003,6 +2063,20 @@ int cmg_launch_count(const cmg_context *c, int64_t *n) {
 }
 
 const char *cmg_kernel_variant(const cmg_context *c) { return c ? c->variant_name.c_str() : ""; }
+
+int cmg_set_energy_form(cmg_context *c, int use_nlist) {
+  NEED(c);
+  if (!use_nlist) {
+    if (c->dim != 2 || !c->planar || c->slab || c->shape[0] % 32 != 0)
+      return fail(c, CMG_EUNSUPPORTED,
+                  "the use_nlist=false energy form is sampled on the device for 2-d lattices with "
+                  "even extents and n0 % 32 == 0");
+  }
+  if (c->nonlist != (use_nlist == 0) && c->n_samples > 0)
+    return fail(c, CMG_ESTATE, "change the energy form on an empty sample series (cmg_clear_samples)");
+  c->nonlist = (use_nlist == 0);
+  return CMG_OK;
+}
 
 int cmg_set_kernel_variant(cmg_context *c, const char *name) {
   NEED(c);

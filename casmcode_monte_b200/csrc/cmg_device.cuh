@@ -1864,6 +1864,101 @@ __global__ void k_series_to_doubles(const long long *__restrict__ sb, long long 
 }
 
 // ---------------------------------------------------------------------------
+// The use_nlist = false energy form on the device (model.hh:273-285):
+//   E = sum_i (-J * dot(row i, row i+1)) + sum_j (-J * dot(col j, col j+1)),
+// every term rounded and accumulated in double, rows first.  The dots are
+// integers: k_line_xor_planes counts, straight from the colour planes, the
+// unequal neighbour pairs of every "row" (fixed i) and "column" (fixed j) at a
+// sampled pass; dot = length - 2 * count.  k_nonlist_to_doubles then walks the
+// reference's accumulation order, one thread per sample.
+//   even row i = 2p   : planes 0 and 1 at (p, j)
+//   odd row i = 2p+1  : plane 1-(j&1) at (p, j) with plane (j&1) at (p+1, j)
+//   column j          : plane c at (p, j) with plane 1-c at (p, j+1), both c
+// A thread owns 16 bytes of p and walks a strip of at most 255 columns with
+// per-byte counters packed in registers.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_line_xor_planes(LatticeView L, int chain, int js,
+                                                         int *__restrict__ row_cnt,
+                                                         int *__restrict__ col_cnt) {
+  const int h = L.h, n1 = L.n1;
+  const int V = h >> 4;
+  const int n_strips = (n1 + js - 1) / js;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = t < (long long)V * n_strips;
+  const int v = active ? (int)(t % V) : 0;
+  const int strip = active ? (int)(t / V) : 0;
+  const int p0 = v << 4;
+  const int jbeg = strip * js;
+  const int jend = active ? min(jbeg + js, n1) : jbeg;
+  const uint8_t *P0 = L.planes + (long long)chain * L.chain_stride;
+  const uint8_t *P1 = P0 + L.plane_stride;
+  const bool warp_uniform = (V & 31) == 0;  // a warp then lies inside one strip
+  const int p_above = (p0 + 16 == h) ? 0 : p0 + 16;
+  uint4 ev = make_uint4(0u, 0u, 0u, 0u), od = ev;
+  uint4 a0 = ev, a1 = ev;
+  if (jbeg < jend) {
+    a0 = ld16(P0 + (long long)h * jbeg + p0);
+    a1 = ld16(P1 + (long long)h * jbeg + p0);
+  }
+  for (int j = jbeg; j < jend; ++j) {
+    const int jn = (j + 1 == n1) ? 0 : j + 1;
+    const uint4 b0 = ld16(P0 + (long long)h * jn + p0);
+    const uint4 b1 = ld16(P1 + (long long)h * jn + p0);
+    ev.x += a0.x ^ a1.x;
+    ev.y += a0.y ^ a1.y;
+    ev.z += a0.z ^ a1.z;
+    ev.w += a0.w ^ a1.w;
+    const uint4 A = (j & 1) ? a0 : a1;  // plane 1-(j&1) at p
+    const uint4 B = (j & 1) ? a1 : a0;  // plane (j&1), taken at p+1
+    const uint32_t eb = ((j & 1) ? P1 : P0)[(long long)h * j + p_above];
+    const uint4 Bs = shift_down_1(B, eb);
+    od.x += A.x ^ Bs.x;
+    od.y += A.y ^ Bs.y;
+    od.z += A.z ^ Bs.z;
+    od.w += A.w ^ Bs.w;
+    int cnt = bytesum(a0.x ^ b1.x) + bytesum(a0.y ^ b1.y) + bytesum(a0.z ^ b1.z) +
+              bytesum(a0.w ^ b1.w) + bytesum(a1.x ^ b0.x) + bytesum(a1.y ^ b0.y) +
+              bytesum(a1.z ^ b0.z) + bytesum(a1.w ^ b0.w);
+    if (warp_uniform) {
+      cnt = __reduce_add_sync(0xffffffffu, cnt);
+      if ((threadIdx.x & 31) == 0) atomicAdd(&col_cnt[j], cnt);
+    } else {
+      atomicAdd(&col_cnt[j], cnt);
+    }
+    a0 = b0;
+    a1 = b1;
+  }
+  if (jbeg < jend) {
+    const uint32_t e[4] = {ev.x, ev.y, ev.z, ev.w}, o[4] = {od.x, od.y, od.z, od.w};
+#pragma unroll
+    for (int b = 0; b < 16; ++b) {
+      atomicAdd(&row_cnt[2 * (p0 + b)], (int)((e[b >> 2] >> (8 * (b & 3))) & 0xffu));
+      atomicAdd(&row_cnt[2 * (p0 + b) + 1], (int)((o[b >> 2] >> (8 * (b & 3))) & 0xffu));
+    }
+  }
+}
+
+// lines: per sample n0 row counts then n1 column counts.  Overwrites the
+// formation / potential energy columns of samples [first, first + count).
+__global__ void k_nonlist_to_doubles(const int *__restrict__ lines, long long line_stride,
+                                     int n0, int n1, const long long *__restrict__ sb,
+                                     long long first, long long count, long long N,
+                                     const ChainTables *tab, double *ef, double *ep) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const int *ln = lines + (first + i) * line_stride;
+  const double mJ = -tab->J;
+  double e = 0.0;
+  for (int r = 0; r < n0; ++r) e = __dadd_rn(e, __dmul_rn(mJ, (double)(n1 - 2 * ln[r])));
+  for (int c = 0; c < n1; ++c) e = __dadd_rn(e, __dmul_rn(mJ, (double)(n0 - 2 * ln[n0 + c])));
+  const long long ones = sb[2 * (first + i)];
+  const long long S = 2 * ones - N;
+  const double Nx = __ddiv_rn((double)(N + S), 2.0);
+  ef[first + i] = __ddiv_rn(e, (double)N);
+  ep[first + i] = __ddiv_rn(__dsub_rn(e, __dmul_rn(tab->mu, Nx)), (double)N);
+}
+
+// ---------------------------------------------------------------------------
 // Series statistics (src/casm/monte/BasicStatistics.cc:24-48, :114-131;
 // include/casm/monte/misc/math.hh:21-39).  One CTA per series.  mean and
 // variance by block reduction; the lag search evaluates lag-k autocovariances

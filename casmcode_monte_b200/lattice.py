@@ -308,6 +308,10 @@ class IsingLatticeGPU:
     def kernel_variant(self):
         return self._lib.cmg_kernel_variant(self._ctx).decode()
 
+    def set_energy_form(self, use_nlist=True):
+        """Energy form of the sampled energies (model.hh:261-285); call on an empty sample series."""
+        self._ck(self._lib.cmg_set_energy_form(self._ctx, 1 if use_nlist else 0))
+
     def set_kernel_variant(self, name):
         self._ck(self._lib.cmg_set_kernel_variant(self._ctx, name.encode()))
 

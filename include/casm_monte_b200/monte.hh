@@ -1433,11 +1433,19 @@ class SemiGrandCanonicalCalculator {
     bool all_builtin = true;
     bool needs_potential_in_nonlist_form =
         !potential.formation_energy_calculator.use_nlist() && config.shape.size() == 2;
+    // the row/column energy form (model.hh:273-285) is sampled on the device in
+    // checkerboard mode where the library supports it; otherwise through the
+    // calculators on the downloaded state
+    dev.check(cmg_set_energy_form(ctx, 1));
+    bool nonlist_on_device = false;
+    if (needs_potential_in_nonlist_form && mode == CMG_MODE_CHECKERBOARD)
+      nonlist_on_device = cmg_set_energy_form(ctx, 0) == CMG_OK;
     for (auto const &pair : data->sampling_functions) {
       auto const &f = pair.second;
       if (f.builtin < 0 || f.builtin_owner != static_cast<void const *>(this)) all_builtin = false;
-      if (needs_potential_in_nonlist_form && f.builtin != CMG_Q_PARAM_COMPOSITION)
-        all_builtin = false;  // row/column energy form is evaluated through the calculators
+      if (needs_potential_in_nonlist_form && !nonlist_on_device &&
+          f.builtin != CMG_Q_PARAM_COMPOSITION)
+        all_builtin = false;
     }
     const bool host_state_each_sample = !all_builtin || static_cast<bool>(json_sample_hook);
     const bool device_samples = all_builtin;

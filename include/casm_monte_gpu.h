@@ -281,6 +281,16 @@ int cmg_conv_l_to_bijk(int device, const int64_t *n3, int64_t n_basis,
 int cmg_conv_bijk_to_l(int device, const int64_t *n3, int64_t n_basis,
                        const int64_t *bijk, int64_t count, int64_t *l_out);
 
+/* Energy form of the sampled formation / potential energies.  use_nlist != 0
+ * (default): -J * (integer bond sum), IsingFormationEnergy::per_supercell with
+ * the neighbour list (include/casm/monte/ising_cpp/model.hh:261-270).
+ * use_nlist == 0: the row/column form of model.hh:273-285, sum over rows then
+ * columns of (-J * dot), each term rounded and accumulated in double (it differs
+ * in the last bits when J is not dyadic): the integer dots of every sampled pass
+ * are taken on the device in checkerboard mode.  2-d, even extents, n0 % 32 == 0;
+ * otherwise CMG_EUNSUPPORTED (callers then evaluate on the downloaded state). */
+int cmg_set_energy_form(cmg_context *ctx, int use_nlist);
+
 /* ---- introspection for bench / tests ---------------------------------------- */
 /* number of kernels this context has launched since creation */
 int cmg_launch_count(const cmg_context *ctx, int64_t *n_launches);

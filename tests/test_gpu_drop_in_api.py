@@ -317,6 +317,35 @@ def test_run_serial_reference_mode_is_trajectory_exact(api, oracle, shape, T, mu
                 assert math.isclose(a["stats"]["calculated_precision"], b["calculated_precision"], rel_tol=1e-9)
 
 
+def test_run_checkerboard_with_the_row_column_energy_form(api, oracle):
+    # use_nlist=False: the calculators' row/column sums, sampled on the device
+    shape = (64, 48)
+    n = shape[0] * shape[1]
+    occ = np.random.default_rng(4).choice(np.array([-1, 1], dtype=np.int32), size=n)
+    T, mu = 2633.0, 0.05
+    mc = make_calculator(api, use_nlist=False)
+    fns = mc.default_sampling_functions()
+    p = api.sampling.CompletionCheckParams()
+    p.cutoff_params.max_count = 10
+    state = make_state(api, shape, T, mu, occ)
+    e = api.monte.RandomNumberEngine()
+    e.seed(78)
+    mc.run(state=state, sampling_functions=fns, json_sampling_functions=api.sampling.jsonStateSamplingFunctionMap(),
+           completion_check_params=p, event_generator=api.sgc.SemiGrandCanonicalEventGenerator(), sample_period=5, random_engine=e)
+    oe = oracle.RandomNumberEngine()
+    oe.seed(78)
+    philox_seed = oracle.random_int(oe, 2**64 - 1)
+    cur = occ
+    d = mc.data
+    for k in range(2):
+        cur = oracle.checkerboard_run(list(shape), cur, J, T, mu, philox_seed, 0, 5 * k, 5, 5)["occupation"]
+        assert d.samplers["formation_energy"].component(0)[k] == oracle.formation_energy(list(shape), cur, J, False)[1]
+        assert d.samplers["potential_energy"].component(0)[k] == oracle.potential(list(shape), cur, J, T, mu, False)[1]
+    assert np.array_equal(state.configuration.occupation(), cur)
+    # the calculators agree with what was sampled last
+    assert mc.formation_energy_calculator.per_unitcell() == d.samplers["formation_energy"].component(0)[-1]
+
+
 @pytest.mark.parametrize("shape", [(64, 48), (1024, 512)])  # the second runs resident in shared memory (k_ring2d)
 def test_run_checkerboard_mode_matches_oracle_checkerboard(api, oracle, shape):
     n = shape[0] * shape[1]

@@ -394,6 +394,55 @@ def test_serial_mode_multichain_and_continuation(cm, oracle):
         assert lat.counters(ch)[1] == ref["n_accept"]
 
 
+@pytest.mark.parametrize("shape,variant", [([64, 48], "auto"), ([96, 34], "bulk2d"), ([1024, 96], "ring2d"), ([32, 6], "generic")])
+def test_nonlist_energy_form_sampled_on_the_device(cm, oracle, shape, variant):
+    # use_nlist = false (model.hh:273-285): rows then columns, -J * dot each, every
+    # term rounded -- a J that is not dyadic makes the two forms differ in the last bits
+    n = nsites(shape)
+    occ = rand_occ(n, 31)
+    Jx, T, mu = 0.1, 2633.0, 0.03
+    lat = cm.IsingLatticeGPU(shape, J=Jx)
+    lat.set_conditions(T, mu)
+    lat.seed_philox(99)
+    lat.set_kernel_variant(variant)
+    lat.set_energy_form(use_nlist=False)
+    lat.upload(occ)
+    n_passes, period = 9, 2
+    lat.run_passes(n_passes, cm.MODE_CHECKERBOARD, period)
+    ef = lat.samples(cm.Q_FORMATION_ENERGY)
+    ep = lat.samples(cm.Q_POTENTIAL_ENERGY)
+    x = lat.samples(cm.Q_PARAM_COMPOSITION)
+    assert len(ef) == n_passes // period
+    cur, differs = occ, False
+    for k in range(n_passes // period):
+        ref = oracle.checkerboard_run(shape, cur, Jx, T, mu, 99, 0, k * period, period, period)
+        cur = ref["occupation"]
+        assert ef[k] == oracle.formation_energy(shape, cur, Jx, False)[1]
+        assert ep[k] == oracle.potential(shape, cur, Jx, T, mu, False)[1]
+        assert x[k] == ref["param_composition"][0]
+        differs |= ef[k] != ref["formation_energy"][0]
+    rest = n_passes % period  # passes after the last sample
+    if rest:
+        cur = oracle.checkerboard_run(shape, cur, Jx, T, mu, 99, 0, n_passes - rest, rest, 0)["occupation"]
+    assert np.array_equal(lat.download(), cur)
+    # statistics read the same columns
+    st = lat.series_stats(cm.Q_FORMATION_ENERGY, 0)
+    assert math.isclose(st["mean"], float(np.mean(ef)), rel_tol=1e-12)
+    # switching the form needs an empty series
+    with pytest.raises(cm.CmgError, match="empty sample series"):
+        lat.set_energy_form(use_nlist=True)
+    lat.clear_samples()
+    lat.set_energy_form(use_nlist=True)
+    lat.run_passes(1, cm.MODE_CHECKERBOARD, 2)  # pass 10 of the schedule: sampled
+    assert lat.samples(cm.Q_FORMATION_ENERGY)[0] == oracle.formation_energy(shape, lat.download(), Jx, True)[1]
+
+
+def test_nonlist_energy_form_is_refused_where_unsupported(cm):
+    lat = cm.IsingLatticeGPU([16, 16, 16], J=J)
+    with pytest.raises(cm.CmgError, match="use_nlist=false"):
+        lat.set_energy_form(use_nlist=False)
+
+
 # -------------------------------------------------------------- statistics ----
 def test_series_statistics_and_equilibration(cm, oracle):
     shape = [64, 64]
