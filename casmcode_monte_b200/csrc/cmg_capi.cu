@@ -865,6 +865,29 @@ static int ensure_series(cmg_context *c, long long need) {
   return CMG_OK;
 }
 
+// ---- scratch memory of the statistics calls -----------------------------------------
+// Stream-ordered allocations from the device's default pool, which is told to
+// keep its memory: a completion check makes a dozen of these calls, and
+// cudaMalloc / cudaFree (a device synchronisation each) dominated its cost.
+#define scratch_alloc(pp, bytes, stream) scratch_alloc_raw(reinterpret_cast<void **>(pp), bytes, stream)
+static cudaError_t scratch_alloc_raw(void **p, size_t bytes, cudaStream_t stream) {
+  static thread_local bool pool_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !pool_set[dev]) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    pool_set[dev] = true;
+  }
+  return cudaMallocAsync(p, bytes, stream);
+}
+static void scratch_free(void *p, cudaStream_t stream) {
+  if (p) cudaFreeAsync(p, stream);
+}
+
 // ---- the hot loop ------------------------------------------------------------------
 // Geometry of the tiled kernel for this lattice: number of column tiles,
 // passes per launch and dynamic shared memory.  ok = false if the lattice does
@@ -1259,7 +1282,7 @@ static int run_serial(cmg_context *c, long long n_passes, long long sample_perio
   // n_chains == 1; otherwise stage through a temporary
   long long *tmp = nullptr;
   if (c->n_chains > 1 && n_new > 0) {
-    CU(c, cudaMalloc(&tmp, sizeof(long long) * 2 * (size_t)n_new * c->n_chains));
+    CU(c, scratch_alloc(&tmp, sizeof(long long) * 2 * (size_t)n_new * c->n_chains, c->stream));
     A.series = tmp;
     A.series_chain_stride = 2 * n_new;
   }
@@ -1282,7 +1305,7 @@ static int run_serial(cmg_context *c, long long n_passes, long long sample_perio
                               sizeof(long long) * 2, sizeof(long long) * 2, (size_t)n_new,
                               cudaMemcpyDeviceToDevice, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
-    cudaFree(tmp);
+    scratch_free(tmp, c->stream);
   }
   c->n_samples += n_new;
   c->n_pass += n_passes;
@@ -1610,7 +1633,7 @@ static int ensure_doubles(cmg_context *c) {
   const long long first = c->dbl_valid, count = c->n_samples - first;
   // per chain: gather the strided (ones,B) pairs into a contiguous temp, convert
   long long *tmp = nullptr;
-  CU(c, cudaMalloc(&tmp, sizeof(long long) * 2 * (size_t)c->n_samples));
+  CU(c, scratch_alloc(&tmp, sizeof(long long) * 2 * (size_t)c->n_samples, c->stream));
   for (int ch = 0; ch < c->n_chains; ++ch) {
     CU(c, cudaMemcpy2DAsync(tmp + 2 * first, sizeof(long long) * 2,
                             c->d_series + first * 2 * c->n_chains + 2 * ch,
@@ -1632,7 +1655,7 @@ static int ensure_doubles(cmg_context *c) {
   }
   CU(c, cudaGetLastError());
   CU(c, cudaStreamSynchronize(c->stream));
-  cudaFree(tmp);
+  scratch_free(tmp, c->stream);
   c->dbl_valid = c->n_samples;
   return CMG_OK;
 }
@@ -1700,29 +1723,6 @@ int cmg_accept_probe(cmg_context *c, int chain, const double *uniforms, uint8_t 
   cudaFree(du);
   cudaFree(da);
   return CMG_OK;
-}
-
-// ---- scratch memory of the statistics calls -----------------------------------------
-// Stream-ordered allocations from the device's default pool, which is told to
-// keep its memory: a completion check makes a dozen of these calls, and
-// cudaMalloc / cudaFree (a device synchronisation each) dominated its cost.
-#define scratch_alloc(pp, bytes, stream) scratch_alloc_raw(reinterpret_cast<void **>(pp), bytes, stream)
-static cudaError_t scratch_alloc_raw(void **p, size_t bytes, cudaStream_t stream) {
-  static thread_local bool pool_set[64] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev >= 0 && dev < 64 && !pool_set[dev]) {
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-      unsigned long long keep = ~0ull;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
-    pool_set[dev] = true;
-  }
-  return cudaMallocAsync(p, bytes, stream);
-}
-static void scratch_free(void *p, cudaStream_t stream) {
-  if (p) cudaFreeAsync(p, stream);
 }
 
 // ---- series statistics ---------------------------------------------------------------

@@ -17,7 +17,7 @@ n1 = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
 max_count = int(sys.argv[3]) if len(sys.argv) > 3 else 2000
 check_period = int(sys.argv[4]) if len(sys.argv) > 4 else 100
 J = 0.1
-for T in (2800.0, 2200.0):
+for T in (2800.0, 2200.0, 2800.0):
     mc = sgc.SemiGrandCanonicalCalculator(
         system=ising.IsingSystem(
             formation_energy_calculator=ising.IsingFormationEnergy(J=J, lattice_type=1, use_nlist=(os.environ.get("USE_NLIST", "1") == "1")),
