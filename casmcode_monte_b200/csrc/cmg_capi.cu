@@ -1022,6 +1022,38 @@ static int pick_js(cmg_context *c, int variant) {
   return best;
 }
 
+// 3-d: balanced strips, their number chosen so that the CTAs fill the resident
+// places: the launch time is waves * (longest strip + ~4 column-times of start-up).
+// With n0 < 1024 a warp holds several strips; they are made the same strip of
+// layers k, k+2, ... (equal column parity), which needs n2 % (2 * strips per warp)
+// == 0 -- otherwise the uniform strips of pick_js are used.
+static int pick_strips3d(cmg_context *c, int *pair_layers) {
+  const long long V = c->shape[0] / 32, n1 = c->shape[1], n2 = c->shape[2];
+  const long long spw = V < 32 ? 32 / V : 1;
+  *pair_layers = 0;
+  if (c->js > 0 || n1 % 2 || V > 32 || (V < 32 && (32 % V || n2 % (2 * spw)))) return 0;
+  *pair_layers = V < 32 ? 1 : 0;
+  if (c->js_auto[7] > 0) return c->js_auto[7];
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_halfsweep_bulk3d<true>, 128, kSmemBulk3d) != cudaSuccess || per_sm < 1)
+    per_sm = 4;
+  const double slots = (double)c->sm_count * per_sm;
+  int best = 0;
+  double best_cost = 1e300;
+  for (long long S = 1; S <= n1 / 2; ++S) {
+    const double len = std::ceil((double)(n1 / 2) / S) * 2.0;
+    if (len > 128 && S < n1 / 2) continue;
+    const double ctas = (double)nblocks(V * S * n2, 128) * c->n_chains;
+    const double cost = std::ceil(ctas / slots) * (len + 4.0);
+    if (cost < best_cost) {
+      best_cost = cost;
+      best = (int)S;
+    }
+  }
+  c->js_auto[7] = best;
+  return best;
+}
+
 static int launch_half_sweep(cmg_context *c, int variant, int colour, unsigned long long pass,
                              bool sample, long long slot) {
   SweepArgs A;
@@ -1049,6 +1081,7 @@ static int launch_half_sweep(cmg_context *c, int variant, int colour, unsigned l
     c->bulk_attr_set = true;
   }
   A.js = pick_js(c, variant);
+  if (variant == V_BULK3D) A.n_strips = pick_strips3d(c, &A.pair_layers);
   const long long plane_size = c->n_sites / 2;
   dim3 block(128);
   if (variant == V_GENERIC) {
@@ -1067,7 +1100,7 @@ static int launch_half_sweep(cmg_context *c, int variant, int colour, unsigned l
       k_halfsweep_bulk2d<false><<<grid, block, kSmemBulk2d, c->stream>>>(A);
   } else if (variant == V_BULK3D) {
     const long long V = c->shape[0] / 32;
-    const long long strips = (c->shape[1] + A.js - 1) / A.js;
+    const long long strips = A.n_strips > 0 ? A.n_strips : (c->shape[1] + A.js - 1) / A.js;
     dim3 grid(nblocks(V * strips * c->shape[2], 128), c->n_chains);
     if (sample)
       k_halfsweep_bulk3d<true><<<grid, block, kSmemBulk3d, c->stream>>>(A);

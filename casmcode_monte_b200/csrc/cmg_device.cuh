@@ -78,6 +78,11 @@ struct SweepArgs {
   uint32_t rk[20];
   int colour;
   int js;  // columns per thread strip (bulk kernels)
+  // bulk3d, when > 0: n_strips balanced strips per layer (even starts, lengths
+  // within two columns of each other) instead of uniform js-column strips, and
+  // the lane groups of a warp take layers k, k+2, ... of ONE strip (pair_layers)
+  int n_strips;
+  int pair_layers;
   int chain_offset;  // global index of chain 0 (chains sharded over several contexts)
 };
 
@@ -1239,19 +1244,42 @@ __global__ void __launch_bounds__(128, CMG_BULK_CTAS) k_halfsweep_bulk3d(SweepAr
 
   const int h = L.h, n1 = L.n1, n2 = L.n2;
   const int V = h >> 4;
-  const int n_strips = (n1 + A.js - 1) / A.js;
+  const int n_strips = A.n_strips > 0 ? A.n_strips : (n1 + A.js - 1) / A.js;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   Accum acc = {0u, 0u, 0u, 0u, 0u};
 
   {
     const bool active = t < (long long)V * n_strips * n2;
-    const int v = active ? (int)(t % V) : 0;
-    const long long t2 = active ? t / V : 0;
-    const int strip = (int)(t2 % n_strips);
-    const int k = (int)(t2 / n_strips);
+    int v, strip, k;
+    if (A.pair_layers) {
+      // With V < 32 a warp holds 32/V strips.  The column parity of a strip is
+      // (jbeg + k + colour) & 1 and selects one of two statically specialised strip
+      // loops, so the strips of a warp must agree in it: they are the same strip in
+      // layers k, k+2, ... (strip starts are even).
+      const int spw = 32 / V;
+      const long long w = t >> 5;
+      const int g = (int)(threadIdx.x & 31) / V;
+      v = (int)(threadIdx.x % V);
+      strip = (int)(w % n_strips);
+      const long long rest = w / n_strips;
+      k = active ? (int)(2 * spw * (rest >> 1) + (rest & 1) + 2 * g) : 0;
+    } else {
+      v = active ? (int)(t % V) : 0;
+      const long long t2 = active ? t / V : 0;
+      strip = (int)(t2 % n_strips);
+      k = (int)(t2 / n_strips);
+    }
     const int p0 = v << 4;
-    const int jbeg = strip * A.js;
-    const int jend = active ? min(jbeg + A.js, n1) : jbeg;
+    int jbeg, jend;
+    if (A.n_strips > 0) {
+      const long long half = n1 >> 1;
+      jbeg = 2 * (int)(((long long)strip * half) / n_strips);
+      jend = 2 * (int)(((long long)(strip + 1) * half) / n_strips);
+    } else {
+      jbeg = strip * A.js;
+      jend = min(jbeg + A.js, n1);
+    }
+    if (!active) jend = jbeg;
     const long long layer = (long long)h * n1;
     uint8_t *C = L.planes + (long long)chain * L.chain_stride +
                  (long long)A.colour * L.plane_stride + layer * k;
