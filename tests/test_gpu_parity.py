@@ -251,6 +251,23 @@ def test_ring2d_matches_oracle(cm, oracle, shape, variant):
     assert np.array_equal(S2, ref2["S"]) and np.array_equal(B2, ref2["B"])
 
 
+def test_ring2d_two_chains_and_ties(cm, oracle):
+    # two lattices share the cooperative grid (grid.y = chain, separate mailboxes);
+    # 2 x 1024 x 512 x 8 passes = 8.4 M attempts -> a few hundred threshold ties
+    shape = [1024, 512]
+    n = nsites(shape)
+    occ = [rand_occ(n, 41), rand_occ(n, 42)]
+    conds = [(2633.0, 0.013), (2200.0, -0.02)]
+    lat = run_cb(cm, shape, occ, None, None, 31337, 8, "ring2d", n_chains=2, chain_conditions=conds, sample_period=4)
+    assert lat.kernel_variant == "ring2d"
+    for ch, (T, mu) in enumerate(conds):
+        ref = oracle.checkerboard_run(shape, occ[ch], J, T, mu, 31337, ch, 0, 8, 4)
+        assert np.array_equal(lat.download(ch), ref["occupation"])
+        S, B = lat.samples_sb(ch)
+        assert np.array_equal(S, ref["S"]) and np.array_equal(B, ref["B"])
+        assert lat.counters(ch)[1] == ref["n_accept"]
+
+
 def test_ring2d_rejects_lattices_it_cannot_hold(cm):
     lat = cm.IsingLatticeGPU([96, 64], J=J)
     lat.set_conditions(2633.0, 0.0)
@@ -273,7 +290,8 @@ def test_threshold_ties_take_the_exact_path(cm, oracle):
         assert lat.counters()[1] == ref["n_accept"]
 
 
-@pytest.mark.parametrize("shape", [[32, 4, 2], [64, 6, 4], [32, 10, 8]])
+# the last three take the layer-paired warp mapping (several strips per warp, n2 % (2 * strips per warp) == 0)
+@pytest.mark.parametrize("shape", [[32, 4, 2], [64, 6, 4], [32, 10, 8], [512, 8, 4], [256, 6, 8], [512, 22, 8]])
 def test_bulk3d_matches_oracle(cm, oracle, shape):
     n = nsites(shape)
     occ = rand_occ(n, 23)
