@@ -1139,11 +1139,17 @@ static int launch_tile_passes_sp(cmg_context *c, const TilePlan &tp, int n_passe
   A.v_magic = (uint32_t)((0x100000000ull + V - 1) / V);
   dim3 grid(tp.n_tiles, c->n_chains);
   cudaError_t e;
-#define LAUNCH_TILE(NT)                                                                       \
-  e = cudaFuncSetAttribute(k_tile2d<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+#define LAUNCH_TILE_S(NT, S)                                                                  \
+  e = cudaFuncSetAttribute(k_tile2d<NT, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
                            (int)tp.smem);                                                     \
   if (e != cudaSuccess) return fail(c, CMG_ECUDA, cudaGetErrorString(e));                     \
-  k_tile2d<NT><<<grid, NT, tp.smem, c->stream>>>(A);
+  k_tile2d<NT, S><<<grid, NT, tp.smem, c->stream>>>(A);
+#define LAUNCH_TILE(NT)                                                                       \
+  if (tp.n_tiles == 1) {                                                                      \
+    LAUNCH_TILE_S(NT, true)                                                                   \
+  } else {                                                                                    \
+    LAUNCH_TILE_S(NT, false)                                                                  \
+  }
   if (c->tile_threads == 1024) {
     LAUNCH_TILE(1024)
   } else if (c->tile_threads == 256) {
@@ -1155,6 +1161,7 @@ static int launch_tile_passes_sp(cmg_context *c, const TilePlan &tp, int n_passe
   } else {
     LAUNCH_TILE(512)
   }
+#undef LAUNCH_TILE_S
 #undef LAUNCH_TILE
   ++c->launches;
   return CMG_OK;

@@ -788,7 +788,10 @@ __device__ __forceinline__ void sts16(uint32_t off, uint4 v) {
 
 constexpr int kTileMaxPasses = 64;
 
-template <int NT>
+// SINGLE: the tile is the whole lattice (n_tiles == 1): periodic columns, no halo,
+// every column owned -- compiled separately so that the halo bookkeeping is not
+// in the loop of the many-small-lattices case.
+template <int NT, bool SINGLE>
 __global__ void __launch_bounds__(NT, 1) k_tile2d(TileArgs A) {
   __shared__ long long s_acc[2 * kTileMaxPasses];  // per-pass {ones, B} of this CTA
   for (int i = threadIdx.x; i < 2 * kTileMaxPasses; i += NT) s_acc[i] = 0;
@@ -799,7 +802,7 @@ __global__ void __launch_bounds__(NT, 1) k_tile2d(TileArgs A) {
 
   const int h = L.h, n1 = L.n1;
   const int V = h >> 4;
-  const bool periodic = (A.n_tiles == 1);
+  constexpr bool periodic = SINGLE;
   const int H = periodic ? 0 : A.halo;
   const int c0 = (int)(((long long)tile * n1) / A.n_tiles);
   const int c1 = (int)(((long long)(tile + 1) * n1) / A.n_tiles);
@@ -923,7 +926,7 @@ __global__ void __launch_bounds__(NT, 1) k_tile2d(TileArgs A) {
             coff += (uint32_t)h;
             g += gstep;
             ++cl;
-            if (++gc == n1) {  // halo columns past the lattice edge wrap around
+            if (!SINGLE && ++gc == n1) {  // halo columns past the lattice edge wrap around
               gc = 0;
               g -= gwrap;
             }
