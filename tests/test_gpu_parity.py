@@ -461,6 +461,54 @@ def test_nonlist_energy_form_is_refused_where_unsupported(cm):
         lat.set_energy_form(use_nlist=False)
 
 
+def test_device_reproduces_the_golden_vectors(cm):
+    # tests/golden/ising_sgc_golden.json (made by tests/golden/make_golden.py): the
+    # device against frozen vectors directly, without the oracle in the loop
+    import hashlib
+    import json
+    import os
+
+    from casmcode_monte_b200.lattice import host_series_equilibration, host_series_equilibration_weighted, host_series_stats, host_series_stats_weighted
+
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ising_sgc_golden.json")) as f:
+        g = json.load(f)
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    unhex = lambda v: np.array([float.fromhex(s) for s in v])
+    for c in g["checkerboard"]:
+        n = nsites(c["shape"])
+        occ = np.random.default_rng(c["occ_seed"]).choice(np.array([-1, 1], dtype=np.int32), size=n)
+        variants = ["auto", "generic"] + (["ring2d"] if c["shape"] == [1024, 128] else [])
+        for variant in variants:
+            lat = run_cb(cm, c["shape"], occ, c["T"], c["mu"], c["philox_seed"], c["n_passes"], variant, sample_period=c["sample_period"])
+            assert sha(lat.download().astype(np.int32)) == c["occupation_sha256"], (c["shape"], variant)
+            S, B = lat.samples_sb()
+            assert [int(v) for v in S] == c["S"] and [int(v) for v in B] == c["B"]
+            assert lat.counters()[1] == c["n_accept"]
+            assert np.array_equal(lat.samples(cm.Q_POTENTIAL_ENERGY), unhex(c["potential_energy"]))
+            assert np.array_equal(lat.samples(cm.Q_PARAM_COMPOSITION), unhex(c["param_composition"]))
+    for c in g["serial"]:
+        lat = cm.IsingLatticeGPU(c["shape"], J=g["J"])
+        lat.set_conditions(c["T"], c["mu"])
+        lat.seed_mt19937_64(c["mt19937_64_seed"])
+        lat.upload(np.ones(nsites(c["shape"]), dtype=np.int32))
+        lat.run_passes(c["max_count"], cm.MODE_SERIAL_REFERENCE, 1)
+        assert sha(lat.download().astype(np.int32)) == c["occupation_sha256"]
+        assert lat.counters()[1] == c["n_accept"]
+        assert np.array_equal(lat.samples(cm.Q_POTENTIAL_ENERGY), unhex(c["potential_energy"]))
+    for c in g["statistics"]:
+        x, w = unhex(c["x"]), unhex(c["w"])
+        st = host_series_stats(x)
+        assert st["k_star"] == c["k_star"]
+        assert math.isclose(st["mean"], float.fromhex(c["mean"]), rel_tol=1e-12)
+        assert math.isclose(st["calculated_precision"], float.fromhex(c["precision"]), rel_tol=1e-10)
+        assert list(host_series_equilibration(x, 0.05)) == c["equilibration_abs_0.05"]
+        assert list(host_series_equilibration_weighted(x, w, 0.05)) == c["weighted_equilibration_abs_0.05"]
+        for method, key in ((1, "weighted_method1"), (2, "weighted_method2")):
+            sw = host_series_stats_weighted(x, w, method=method, n_resamples=1000)
+            assert math.isclose(sw["mean"], float.fromhex(c[key][0]), rel_tol=1e-12)
+            assert math.isclose(sw["calculated_precision"], float.fromhex(c[key][1]), rel_tol=1e-10)
+
+
 # -------------------------------------------------------------- statistics ----
 def test_series_statistics_and_equilibration(cm, oracle):
     shape = [64, 64]

@@ -324,3 +324,52 @@ def test_sgc_run_reference_settings_and_onsager(oracle):
     m = (1.0 - math.sinh(2 * beta * J) ** -4) ** 0.125
     x = ind["param_composition"]["mean"]
     assert abs(x - (1 + m) / 2) < 5 * 0.001 + 2e-3  # finite-size slack at 25x25
+
+
+# --- frozen vectors: the oracle must keep producing tests/golden/ising_sgc_golden.json ---
+def _golden():
+    import json
+    import os
+
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ising_sgc_golden.json")) as f:
+        return json.load(f)
+
+
+def _sha(a):
+    import hashlib
+
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def _unhex(v):
+    return np.array([float.fromhex(s) for s in v])
+
+
+def test_oracle_reproduces_the_golden_vectors(oracle):
+    g = _golden()
+    for c in g["checkerboard"]:
+        n = int(np.prod(c["shape"]))
+        occ = np.random.default_rng(c["occ_seed"]).choice(np.array([-1, 1], dtype=np.int32), size=n)
+        r = oracle.checkerboard_run(c["shape"], occ, g["J"], c["T"], c["mu"], c["philox_seed"], 0, 0, c["n_passes"], c["sample_period"])
+        assert _sha(r["occupation"].astype(np.int32)) == c["occupation_sha256"]
+        assert [int(v) for v in r["S"]] == c["S"] and [int(v) for v in r["B"]] == c["B"]
+        assert int(r["n_accept"]) == c["n_accept"]
+        assert np.array_equal(r["potential_energy"], _unhex(c["potential_energy"]))
+    for c in g["serial"]:
+        occ = np.ones(int(np.prod(c["shape"])), dtype=np.int32)
+        e = oracle.RandomNumberEngine()
+        e.seed(c["mt19937_64_seed"])
+        r = oracle.sgc_run(c["shape"], occ, g["J"], c["T"], c["mu"], True, e, {"max_count": c["max_count"]}, 1)
+        assert _sha(r["occupation"].astype(np.int32)) == c["occupation_sha256"]
+        assert int(r["n_accept"]) == c["n_accept"]
+        assert np.array_equal(r["samplers"]["potential_energy"], _unhex(c["potential_energy"]))
+    for c in g["statistics"]:
+        x, w = _unhex(c["x"]), _unhex(c["w"])
+        mean, prec = oracle.basic_statistics(x)
+        assert mean == float.fromhex(c["mean"]) and prec == float.fromhex(c["precision"])
+        assert oracle.autocorrelation_factor(x)[1] == c["k_star"]
+        assert list(oracle.default_equilibration_check(x, abs=0.05)) == c["equilibration_abs_0.05"]
+        assert list(oracle.default_equilibration_check(x, w, abs=0.05)) == c["weighted_equilibration_abs_0.05"]
+        for method, key in ((1, "weighted_method1"), (2, "weighted_method2")):
+            m, p = oracle.basic_statistics(x, w, method=method, n_resamples=1000)
+            assert [float(m).hex(), float(p).hex()] == c[key]
