@@ -57,7 +57,9 @@ def measured_peak():
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """Samples SM clocks / throttle reasons while the timed region runs: NVML in
+    process every 10 ms (the timed region is well under a second), nvidia-smi as
+    the fallback."""
 
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
@@ -66,10 +68,36 @@ class ClockSampler(threading.Thread):
         self.index = index
         self.rows = []
         self._stop_evt = threading.Event()
+        self._nvml = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self._max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            self._nvml = pynvml
+        except Exception:
+            self._nvml = None
+
+    def _sample_nvml(self):
+        n = self._nvml
+        sm = float(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM))
+        mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+        bits = [
+            getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+        ]
+        self.rows.append([str(sm), str(self._max)] + ["Active" if mask & b else "Not Active" for b in bits])
 
     def run(self):
         while not self._stop_evt.is_set():
             try:
+                if self._nvml is not None:
+                    self._sample_nvml()
+                    self._stop_evt.wait(0.01)
+                    continue
                 out = subprocess.run(
                     ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
                     capture_output=True, text=True, timeout=5,
@@ -77,7 +105,7 @@ class ClockSampler(threading.Thread):
                 if out:
                     self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
-                pass
+                self._nvml = None
             self._stop_evt.wait(0.2)
 
     def stop(self):
