@@ -1050,6 +1050,52 @@ __device__ __forceinline__ void st_relaxed_gpu_v4(void *p, uint4 v) {
                "r"(v.z), "r"(v.w)
                : "memory");
 }
+// ---- bulk (TMA) copies of a tile: a contiguous run of whole columns of a plane --------
+// One thread issues one cp.async.bulk per plane (UBLKCP); completion is counted
+// in bytes on an mbarrier that every thread of the CTA then waits for.
+__device__ __forceinline__ void mbar_init(unsigned long long *mbar, unsigned int count) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(mbar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *mbar, unsigned int bytes) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(mbar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long *mbar, unsigned int parity) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(mbar);
+  unsigned int ok;
+  asm volatile(
+      "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+      : "=r"(ok)
+      : "r"(a), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// global -> shared, bytes % 16 == 0, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_load(uint32_t smem_dst, const void *gsrc, unsigned int bytes,
+                                          unsigned long long *mbar) {
+  const uint32_t m = (uint32_t)__cvta_generic_to_shared(mbar);
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst),
+      "l"(gsrc), "r"(bytes), "r"(m)
+      : "memory");
+}
+// shared -> global
+__device__ __forceinline__ void bulk_store(void *gdst, uint32_t smem_src, unsigned int bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+               "r"(smem_src), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_store_commit_and_wait() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_shared() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
 __device__ __forceinline__ bool ring_stamp_ok(uint4 v, uint32_t expect) {
   return ((((v.x ^ expect) | (v.y ^ expect)) | ((v.z ^ expect) | (v.w ^ expect))) & 0xfefefefeu) == 0u;
 }
@@ -1073,14 +1119,26 @@ __global__ void __launch_bounds__(NT, 1) k_ring2d(RingArgs A) {
                    L.planes + (long long)chain * L.chain_stride + L.plane_stride};
   const uint32_t chain_word = (uint32_t)(chain + A.chain_offset) << 8;
 
-  // ---- stage the owned columns
-  for (int it = threadIdx.x; it < 2 * TW * V; it += NT) {
-    const int plane = it >= TW * V;
-    const int r = it - plane * TW * V;
-    const int cl = (int)__umulhi((uint32_t)r, A.v_magic);
-    const int v = r - cl * V;
-    sts16(soff[plane] + (uint32_t)(cl * h + (v << 4)),
-          __ldg(reinterpret_cast<const uint4 *>(G[plane] + (long long)(c0 + cl) * h + (v << 4))));
+  // ---- stage the owned columns: the tile of a plane is TW*h contiguous bytes
+  // both in global and in shared memory, so it is one bulk (TMA) copy per plane
+  __shared__ __align__(8) unsigned long long s_mbar;
+  const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(cmg_smem);
+  const unsigned int tile_bytes = (unsigned int)(TW * h);
+  if (threadIdx.x == 0) mbar_init(&s_mbar, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&s_mbar, 2u * tile_bytes);
+    bulk_load(smem_base + soff[0], G[0] + (long long)c0 * h, tile_bytes, &s_mbar);
+    bulk_load(smem_base + soff[1], G[1] + (long long)c0 * h, tile_bytes, &s_mbar);
+  }
+  {
+    unsigned int spins = 0;
+    while (!mbar_try_wait(&s_mbar, 0)) {
+      if (++spins > (1u << 12)) {  // bounded (try_wait itself sleeps), like the edge waits
+        atomicExch(A.error, 2u);
+        break;
+      }
+    }
   }
 
   // column groups: Q >= 2 groups of V threads; group q owns columns [a, b).
@@ -1215,14 +1273,18 @@ __global__ void __launch_bounds__(NT, 1) k_ring2d(RingArgs A) {
     atomicAdd(reinterpret_cast<unsigned long long *>(dst), (unsigned long long)s_acc[i]);
   }
 
-  // ---- write the owned columns back
-  for (int it = threadIdx.x; it < 2 * TW * V; it += NT) {
-    const int plane = it >= TW * V;
-    const int r = it - plane * TW * V;
-    const int dc = (int)__umulhi((uint32_t)r, A.v_magic);
-    const int v = r - dc * V;
-    *reinterpret_cast<uint4 *>(G[plane] + (long long)(c0 + dc) * h + (v << 4)) =
-        lds16(soff[plane] + (uint32_t)(dc * h + (v << 4)));
+  // ---- write the owned columns back: one bulk store per plane.  The tile was
+  // written with ordinary shared-memory stores, which the async proxy only sees
+  // after a proxy fence by the writers and a barrier.
+  fence_proxy_async_shared();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t sb = (uint32_t)__cvta_generic_to_shared(cmg_smem);
+    const unsigned int nb = (unsigned int)((c1 - c0) * L.h);
+    uint8_t *g0 = L.planes + (long long)blockIdx.y * L.chain_stride + (long long)c0 * L.h;
+    bulk_store(g0, sb + (uint32_t)kSmemTile, nb);
+    bulk_store(g0 + L.plane_stride, sb + (uint32_t)kSmemTile + (uint32_t)A.w_max * (uint32_t)L.h, nb);
+    bulk_store_commit_and_wait();  // shared memory must outlive the reads
   }
   n_acc = __reduce_add_sync(0xffffffffu, n_acc);
   if ((threadIdx.x & 31) == 0 && n_acc) atomicAdd(A.n_accept + chain, (unsigned long long)n_acc);
