@@ -419,10 +419,10 @@ int cmg_set_stream(cmg_context *c, void *cuda_stream) {
   return CMG_OK;
 }
 
-// the ring kernel bounds its flag waits; a timeout is reported here, never hidden
+// the ring kernel bounds its waits (neighbour edges, bulk-copy completion); a timeout is reported here, never hidden
 static int ring_error_check(cmg_context *c) {
   if (c->h_ring_error && *c->h_ring_error)
-    return fail(c, CMG_ECUDA, "ring2d: a tile waited too long for its neighbour (results invalid)");
+    return fail(c, CMG_ECUDA, "ring2d: a tile waited too long for its neighbour or its bulk copy (results invalid)");
   return CMG_OK;
 }
 
@@ -1212,7 +1212,7 @@ static int launch_ring_passes(cmg_context *c, const RingPlan &rp, int n_passes,
   dim3 grid(rp.n_tiles, c->n_chains);
   void *args[] = {&A};
   // cooperative: the grid starts only when every CTA can be resident, which
-  // the flag waits between neighbouring tiles rely on
+  // the edge waits between neighbouring tiles rely on
   e = cudaLaunchCooperativeKernel((const void *)k_ring2d<512>, grid, dim3(512), args, rp.smem,
                                   c->stream);
   if (e != cudaSuccess) return fail(c, CMG_ECUDA, cudaGetErrorString(e));
