@@ -44,6 +44,8 @@ SIGNATURES = {
     "cmg_slab_ipc_export": (C.c_int, [_ctx, C.c_void_p, C.c_int64]),
     "cmg_slab_ipc_attach": (C.c_int, [_ctx, C.c_int, C.c_void_p, C.c_int64, C.c_int, _ctx]),
     "cmg_slab_half_sweep": (C.c_int, [_ctx, C.c_int, C.c_uint64, C.c_int]),
+    "cmg_slab_run_passes": (C.c_int, [_ctx, C.c_int64, C.c_int64]),
+    "cmg_slab_set_halo_exchange": (C.c_int, [_ctx, C.c_int]),
     "cmg_set_model": (C.c_int, [_ctx, C.c_double, C.c_int]),
     "cmg_set_conditions": (C.c_int, [_ctx, C.c_int, C.c_double, C.c_double]),
     "cmg_get_tables": (C.c_int, [_ctx, C.c_int, _f64p, _f64p, _u32p]),
@@ -51,6 +53,10 @@ SIGNATURES = {
     "cmg_download_occupation_i32": (C.c_int, [_ctx, C.c_int, _i32p, C.c_int64]),
     "cmg_upload_occupation_i32_dev": (C.c_int, [_ctx, C.c_int, C.c_void_p, C.c_int64]),
     "cmg_download_occupation_i32_dev": (C.c_int, [_ctx, C.c_int, C.c_void_p, C.c_int64]),
+    "cmg_upload_occupation_i8": (C.c_int, [_ctx, C.c_int, C.POINTER(C.c_int8), C.c_int64]),
+    "cmg_download_occupation_i8": (C.c_int, [_ctx, C.c_int, C.POINTER(C.c_int8), C.c_int64]),
+    "cmg_upload_occupation_bits": (C.c_int, [_ctx, C.c_int, _u8p, C.c_int64]),
+    "cmg_download_occupation_bits": (C.c_int, [_ctx, C.c_int, _u8p, C.c_int64]),
     "cmg_fill_occupation": (C.c_int, [_ctx, C.c_int, C.c_int]),
     "cmg_get_occ": (C.c_int, [_ctx, C.c_int, C.c_int64, _i32p]),
     "cmg_set_occ": (C.c_int, [_ctx, C.c_int, C.c_int64, C.c_int32]),

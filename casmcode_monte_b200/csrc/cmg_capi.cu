@@ -52,8 +52,8 @@ struct cmg_context {
   unsigned long long *d_flags = nullptr;       // [2] wait flags, raised by the neighbours
   unsigned long long *peer_flag[2] = {nullptr, nullptr};  // the neighbours' wait flags
   unsigned int *d_done = nullptr;
-  unsigned long long slab_epoch_base = 0;  // half-sweep index of the first fused half-sweep
-  bool slab_epoch_set = false;
+  unsigned long long slab_epoch = 0;  // fused half-sweeps stepped since the peers were attached
+  bool slab_exchange = true;          // false: halos neither pushed nor waited for (timing aid)
   std::vector<void *> ipc_opened;
 
   uint8_t *d_planes = nullptr;
@@ -99,9 +99,13 @@ struct cmg_context {
   int tile_passes = 3;   // passes per launch of the tiled kernel (halo = 2*P columns)
   int tile_threads = 512;
   int ring_passes = 128;  // passes per cooperative launch of the ring kernel
-  uint8_t *d_ring_mailbox = nullptr;  // [n_chains][n_tiles][side][plane][h] + error word at the end
+  uint8_t *d_ring_mailbox = nullptr;  // [n_chains][n_tiles][side][plane][h]
   size_t ring_mailbox_bytes = 0;
-  unsigned int *h_ring_error = nullptr;  // pinned copy of the error word
+  // sticky device error word (kErr* bits, raised with atomicOr by kernels whose
+  // waits are bounded) and its pinned host copy; zeroed at create and after a
+  // failure has been reported
+  unsigned int *d_error = nullptr;
+  unsigned int *h_error = nullptr;
   int coop_launch = 0;
   int sm_count = 148;
   bool bulk_attr_set = false;
@@ -180,6 +184,10 @@ static void build_tables(ChainTables &t, int dim, double J, double T, double mu)
       uint32_t thr;
       if (dE < 0.0 || p >= 1.0) {
         thr = 0xFFFFFFFFu;
+      } else if (!(p > 0.0)) {
+        // exp underflowed to 0: the reference's `rand < prob` is never true
+        thr = 0u;
+        t.never_mask |= 1u << idx;
       } else {
         double scaled = std::ceil(p * 4294967296.0);
         if (scaled < 1.0) scaled = 1.0;
@@ -224,19 +232,24 @@ static LatticeView view(const cmg_context *c) {
   L.n2 = (int)c->shape[2];
   L.dim = c->dim;
   L.col_offset = c->col_begin;
+  L.error = c->d_error;
   if (c->slab) {
     for (int col = 0; col < 2; ++col) {
       L.halo_lo[col] = c->d_halo[col][0];
       L.halo_hi[col] = c->d_halo[col][1];
-      L.push_lo[col] = c->push[col][0];
-      L.push_hi[col] = c->push[col][1];
+      if (c->slab_exchange) {
+        L.push_lo[col] = c->push[col][0];
+        L.push_hi[col] = c->push[col][1];
+      }
     }
-    for (int side = 0; side < 2; ++side) {
-      // only meaningful once a peer is attached on that side
-      L.wait_flag[side] = c->peer_flag[side] ? c->d_flags + side : nullptr;
-      L.signal_flag[side] = c->peer_flag[side];
+    if (c->slab_exchange) {
+      for (int side = 0; side < 2; ++side) {
+        // only meaningful once a peer is attached on that side
+        L.wait_flag[side] = c->peer_flag[side] ? c->d_flags + side : nullptr;
+        L.signal_flag[side] = c->peer_flag[side];
+      }
+      L.done_counter = (c->peer_flag[0] || c->peer_flag[1]) ? c->d_done : nullptr;
     }
-    L.done_counter = (c->peer_flag[0] || c->peer_flag[1]) ? c->d_done : nullptr;
   }
   return L;
 }
@@ -344,6 +357,10 @@ static int create_common(int dim, const int64_t *shape, int n_chains, int device
   CUC(cudaMemset(c->d_flag, 0, sizeof(int)));
   CUC(cudaMalloc(&c->d_cur_sb, sizeof(long long) * 2 * n_chains));
   CUC(cudaMalloc(&c->d_scratch_sb, sizeof(long long) * 2));
+  CUC(cudaMalloc(&c->d_error, sizeof(unsigned int)));
+  CUC(cudaMemset(c->d_error, 0, sizeof(unsigned int)));
+  CUC(cudaMallocHost(&c->h_error, sizeof(unsigned int)));
+  *c->h_error = 0;
   c->engine_seeded.assign(n_chains, 0);
   if (slab) {
     const long long hb = c->shape[0] / 2;
@@ -407,7 +424,8 @@ int cmg_destroy(cmg_context *c) {
   cudaFree(c->d_done);
   cudaFree(c->d_ring_mailbox);
   cudaFree(c->d_lines);
-  if (c->h_ring_error) cudaFreeHost(c->h_ring_error);
+  cudaFree(c->d_error);
+  if (c->h_error) cudaFreeHost(c->h_error);
   delete c;
   return CMG_OK;
 }
@@ -419,17 +437,35 @@ int cmg_set_stream(cmg_context *c, void *cuda_stream) {
   return CMG_OK;
 }
 
-// the ring kernel bounds its waits (neighbour edges, bulk-copy completion); a timeout is reported here, never hidden
-static int ring_error_check(cmg_context *c) {
-  if (c->h_ring_error && *c->h_ring_error)
-    return fail(c, CMG_ECUDA, "ring2d: a tile waited too long for its neighbour or its bulk copy (results invalid)");
-  return CMG_OK;
+// Kernels with waits (k_ring2d: neighbour edges and bulk-copy completion; slab
+// half-sweeps: the neighbours' flags) bound them and raise bits of the context's
+// STICKY device error word with atomicOr; no launch ever clears it.  Every entry
+// point that synchronises the stream fetches it here, so a timeout in any launch
+// of a multi-launch call surfaces at the next synchronising call -- and then the
+// word is cleared, the failure having been reported (results up to here are
+// invalid; re-upload the occupation to go on).
+static int device_error_check(cmg_context *c) {
+  if (!c->d_error) return CMG_OK;
+  CU(c, cudaMemcpyAsync(c->h_error, c->d_error, sizeof(unsigned int), cudaMemcpyDeviceToHost,
+                        c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  const unsigned int e = *c->h_error;
+  if (!e) return CMG_OK;
+  *c->h_error = 0;
+  cudaMemsetAsync(c->d_error, 0, sizeof(unsigned int), c->stream);
+  std::string msg;
+  if (e & (kErrRingEdge | kErrRingCopy))
+    msg += "ring2d: a tile waited too long for its neighbour or its bulk copy; ";
+  if (e & kErrSlabWait)
+    msg += "slab half-sweep: a neighbour's flag did not arrive within 20 s (dead rank or "
+           "half-sweep sequences that differ between ranks); ";
+  return fail(c, CMG_ECUDA, msg + "results since the last successful synchronisation are invalid");
 }
 
 int cmg_sync(cmg_context *c) {
   NEED(c);
   CU(c, cudaStreamSynchronize(c->stream));
-  return ring_error_check(c);
+  return device_error_check(c);
 }
 
 int cmg_n_sites(const cmg_context *c, int64_t *n) {
@@ -439,9 +475,19 @@ int cmg_n_sites(const cmg_context *c, int64_t *n) {
 }
 
 // ---- model / conditions ------------------------------------------------------
+// Samples are kept as integer sums and turned into doubles lazily with the
+// chain's (J, mu): before either changes, the samples taken so far are converted
+// with the values they were taken under (a temperature / mu sweep that re-uses a
+// context keeps a consistent series).
+static int ensure_doubles(cmg_context *c);
+
 int cmg_set_model(cmg_context *c, double J, int lattice_type) {
   NEED(c);
   if (lattice_type != 1) return fail(c, CMG_EINVAL, "Unsupported lattice_type");
+  {
+    const int rc = ensure_doubles(c);
+    if (rc) return rc;
+  }
   c->J = J;
   c->lattice_type = lattice_type;
   c->model_set = true;
@@ -459,6 +505,10 @@ int cmg_set_conditions(cmg_context *c, int chain, double temperature, double mu)
   NEED(c);
   if (chain < -1 || chain >= c->n_chains) return fail(c, CMG_EINVAL, "bad chain index");
   if (!(temperature > 0.0)) return fail(c, CMG_EINVAL, "temperature must be > 0");
+  {
+    const int rc = ensure_doubles(c);
+    if (rc) return rc;
+  }
   const int lo = chain < 0 ? 0 : chain, hi = chain < 0 ? c->n_chains : chain + 1;
   for (int ch = lo; ch < hi; ++ch) build_tables(c->h_tabs[ch], c->dim, c->J, temperature, mu);
   CU(c, cudaMemcpyAsync(c->d_tabs + lo, c->h_tabs.data() + lo, sizeof(ChainTables) * (hi - lo),
@@ -591,7 +641,7 @@ int cmg_download_occupation_i32(cmg_context *c, int chain, int32_t *occ, int64_t
   CU(c, cudaMemcpyAsync(occ, c->d_stage, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost,
                         c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
-  return ring_error_check(c);
+  return device_error_check(c);
 }
 
 int cmg_download_occupation_i32_dev(cmg_context *c, int chain, int32_t *occ_dev, int64_t n) {
@@ -599,6 +649,82 @@ int cmg_download_occupation_i32_dev(cmg_context *c, int chain, int32_t *occ_dev,
   if (chain < 0 || chain >= c->n_chains) return fail(c, CMG_EINVAL, "bad chain index");
   if (!occ_dev || n != c->n_sites) return fail(c, CMG_EINVAL, "size mismatch");
   return download_to(c, chain, occ_dev);
+}
+
+// ---- compact host formats (1 B or 1 bit per site instead of the reference's 4 B) ----
+static uint8_t *chain_base(cmg_context *c, int chain);
+
+int cmg_upload_occupation_i8(cmg_context *c, int chain, const int8_t *occ, int64_t n) {
+  NEED(c);
+  if (chain < 0 || chain >= c->n_chains) return fail(c, CMG_EINVAL, "bad chain index");
+  if (!occ || n != c->n_sites)
+    return fail(c, CMG_EINVAL, "Error in set_occupation: size mismatch");
+  int rc = ensure_stage(c);
+  if (rc) return rc;
+  CU(c, cudaMemcpyAsync(c->d_stage, occ, (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemsetAsync(c->d_flag, 0, sizeof(int), c->stream));
+  k_i8_to_sites<<<nblocks(n, 256), 256, 0, c->stream>>>(
+      reinterpret_cast<const int8_t *>(c->d_stage), chain_base(c, chain), c->plane_stride,
+      nat_shape(c), c->planar ? 1 : 0, c->d_flag);
+  ++c->launches;
+  if (c->planar) c->nat_is_current = false;
+  CU(c, cudaGetLastError());
+  int bad = 0;
+  CU(c, cudaMemcpyAsync(&bad, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  if (bad) return fail(c, CMG_EINVAL, "occupation values must be +1 or -1");
+  return CMG_OK;
+}
+
+int cmg_download_occupation_i8(cmg_context *c, int chain, int8_t *occ, int64_t n) {
+  NEED(c);
+  if (chain < 0 || chain >= c->n_chains) return fail(c, CMG_EINVAL, "bad chain index");
+  if (!occ || n != c->n_sites) return fail(c, CMG_EINVAL, "size mismatch");
+  int rc = ensure_stage(c);
+  if (rc) return rc;
+  k_sites_to_i8<<<nblocks(n, 256), 256, 0, c->stream>>>(
+      chain_base(c, chain), c->plane_stride, reinterpret_cast<int8_t *>(c->d_stage), nat_shape(c),
+      c->planar ? 1 : 0);
+  ++c->launches;
+  CU(c, cudaGetLastError());
+  CU(c, cudaMemcpyAsync(occ, c->d_stage, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return device_error_check(c);
+}
+
+int cmg_upload_occupation_bits(cmg_context *c, int chain, const uint8_t *bits, int64_t n_sites) {
+  NEED(c);
+  if (chain < 0 || chain >= c->n_chains) return fail(c, CMG_EINVAL, "bad chain index");
+  if (!bits || n_sites != c->n_sites)
+    return fail(c, CMG_EINVAL, "Error in set_occupation: size mismatch");
+  int rc = ensure_stage(c);
+  if (rc) return rc;
+  const size_t nbytes = (size_t)((n_sites + 7) / 8);
+  CU(c, cudaMemcpyAsync(c->d_stage, bits, nbytes, cudaMemcpyHostToDevice, c->stream));
+  k_bits_to_sites<<<nblocks(n_sites, 256), 256, 0, c->stream>>>(
+      reinterpret_cast<const uint8_t *>(c->d_stage), chain_base(c, chain), c->plane_stride,
+      nat_shape(c), c->planar ? 1 : 0);
+  ++c->launches;
+  if (c->planar) c->nat_is_current = false;
+  CU(c, cudaGetLastError());
+  return CMG_OK;
+}
+
+int cmg_download_occupation_bits(cmg_context *c, int chain, uint8_t *bits, int64_t n_sites) {
+  NEED(c);
+  if (chain < 0 || chain >= c->n_chains) return fail(c, CMG_EINVAL, "bad chain index");
+  if (!bits || n_sites != c->n_sites) return fail(c, CMG_EINVAL, "size mismatch");
+  int rc = ensure_stage(c);
+  if (rc) return rc;
+  const long long nbytes = (n_sites + 7) / 8;
+  k_sites_to_bits<<<nblocks(nbytes, 256), 256, 0, c->stream>>>(
+      chain_base(c, chain), c->plane_stride, reinterpret_cast<uint8_t *>(c->d_stage), nat_shape(c),
+      c->planar ? 1 : 0);
+  ++c->launches;
+  CU(c, cudaGetLastError());
+  CU(c, cudaMemcpyAsync(bits, c->d_stage, (size_t)nbytes, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return device_error_check(c);
 }
 
 int cmg_fill_occupation(cmg_context *c, int chain, int value) {
@@ -1070,7 +1196,7 @@ static int launch_half_sweep(cmg_context *c, int variant, int colour, unsigned l
   }
   A.colour = colour;
   A.chain_offset = c->chain_offset;
-  A.L.epoch = 2ull * pass + (unsigned long long)colour - c->slab_epoch_base;
+  A.L.epoch = c->slab_epoch;
   if (!c->bulk_attr_set) {
     // the staging rings may exceed the 48 KiB default dynamic shared-memory limit
     cudaError_t e = cudaFuncSetAttribute(k_halfsweep_bulk2d<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBulk2d);
@@ -1172,17 +1298,13 @@ static int launch_ring_passes(cmg_context *c, const RingPlan &rp, int n_passes,
   // edge mailbox: per tile and side one column of each plane; zeroed before every
   // launch because its bytes carry the half-sweep stamp that validates them
   const size_t mb_bytes = (size_t)c->n_chains * rp.n_tiles * 4 * (size_t)(c->shape[0] / 2);
-  if (c->ring_mailbox_bytes < mb_bytes + 16) {
+  if (c->ring_mailbox_bytes < mb_bytes) {
     cudaFree(c->d_ring_mailbox);
     c->d_ring_mailbox = nullptr;
-    CU(c, cudaMalloc(&c->d_ring_mailbox, mb_bytes + 16));
-    c->ring_mailbox_bytes = mb_bytes + 16;
+    CU(c, cudaMalloc(&c->d_ring_mailbox, mb_bytes));
+    c->ring_mailbox_bytes = mb_bytes;
   }
-  if (!c->h_ring_error) {
-    CU(c, cudaMallocHost(&c->h_ring_error, sizeof(unsigned int)));
-    *c->h_ring_error = 0;
-  }
-  CU(c, cudaMemsetAsync(c->d_ring_mailbox, 0, mb_bytes + 16, c->stream));
+  CU(c, cudaMemsetAsync(c->d_ring_mailbox, 0, mb_bytes, c->stream));
   RingArgs A;
   memset(&A, 0, sizeof A);
   A.L = view(c);
@@ -1205,7 +1327,7 @@ static int launch_ring_passes(cmg_context *c, const RingPlan &rp, int n_passes,
   const unsigned long long V = (unsigned long long)(c->shape[0] / 32);
   A.v_magic = (uint32_t)((0x100000000ull + V - 1) / V);
   A.mailbox = c->d_ring_mailbox;
-  A.error = reinterpret_cast<unsigned int *>(c->d_ring_mailbox + mb_bytes);
+  A.error = c->d_error;
   cudaError_t e = cudaFuncSetAttribute(k_ring2d<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)rp.smem);
   if (e != cudaSuccess) return fail(c, CMG_ECUDA, cudaGetErrorString(e));
@@ -1216,8 +1338,6 @@ static int launch_ring_passes(cmg_context *c, const RingPlan &rp, int n_passes,
   e = cudaLaunchCooperativeKernel((const void *)k_ring2d<512>, grid, dim3(512), args, rp.smem,
                                   c->stream);
   if (e != cudaSuccess) return fail(c, CMG_ECUDA, cudaGetErrorString(e));
-  CU(c, cudaMemcpyAsync(c->h_ring_error, A.error, sizeof(unsigned int), cudaMemcpyDeviceToHost,
-                        c->stream));
   ++c->launches;
   return CMG_OK;
 }
@@ -1404,8 +1524,6 @@ int cmg_run_passes(cmg_context *c, int64_t n_passes, int mode, int64_t sample_pe
   if (rc) return rc;
   c->nat_is_current = false;
   if (variant == V_RING2D) {
-    rc = ring_error_check(c);
-    if (rc) return rc;
     const RingPlan rp = plan_ring(c);
     long long left = n_passes;
     while (left > 0) {
@@ -1469,18 +1587,45 @@ int cmg_slab_half_sweep(cmg_context *c, int colour, uint64_t pass_index, int sam
   }
   c->nat_is_current = false;
   c->variant_name = "bulk2d";
-  if (!c->slab_epoch_set) {  // flags count half-sweeps from the first one stepped
-    c->slab_epoch_base = 2ull * pass_index + (unsigned long long)colour;
-    c->slab_epoch_set = true;
-  }
   rc = launch_half_sweep(c, V_BULK2D, colour, pass_index, do_sample, c->n_samples);
   if (rc) return rc;
+  // The neighbours' flags count fused half-sweeps since the peers were attached,
+  // whatever pass indices they carry: restarting or re-running a trajectory
+  // (cmg_set_pass_counter, a smaller pass_index) cannot wrap the epoch.  Every
+  // rank of the ring must step the same sequence of half-sweeps.
+  if (c->slab_exchange && (c->peer_flag[0] || c->peer_flag[1])) ++c->slab_epoch;
   if (colour == 1) {
     ++c->n_pass;
     c->h_pass = pass_index + 1;
     if (do_sample) ++c->n_samples;
   }
   CU(c, cudaGetLastError());
+  return CMG_OK;
+}
+
+int cmg_slab_run_passes(cmg_context *c, int64_t n_passes, int64_t sample_period) {
+  NEED(c);
+  if (!c->slab) return fail(c, CMG_ESTATE, "not a slab context");
+  if (n_passes < 0 || sample_period < 0) return fail(c, CMG_EINVAL, "negative count");
+  if (c->slab_exchange && !(c->peer_flag[0] && c->peer_flag[1]))
+    return fail(c, CMG_ESTATE,
+                "cmg_slab_run_passes needs both neighbours attached (cmg_slab_ipc_attach); drivers "
+                "with their own halo exchange step cmg_slab_half_sweep");
+  for (int64_t t = 0; t < n_passes; ++t) {
+    const int sample = sample_period > 0 && ((c->n_pass + 1) % sample_period) == 0;
+    const unsigned long long pass = c->h_pass;
+    int rc = cmg_slab_half_sweep(c, 0, pass, 0);
+    if (rc) return rc;
+    rc = cmg_slab_half_sweep(c, 1, pass, sample);
+    if (rc) return rc;
+  }
+  return CMG_OK;
+}
+
+int cmg_slab_set_halo_exchange(cmg_context *c, int enabled) {
+  NEED(c);
+  if (!c->slab) return fail(c, CMG_ESTATE, "not a slab context");
+  c->slab_exchange = enabled != 0;
   return CMG_OK;
 }
 
@@ -1571,6 +1716,10 @@ int cmg_counters(cmg_context *c, int chain, int64_t *n_pass, int64_t *n_accept, 
   unsigned long long acc = 0;
   CU(c, cudaMemcpyAsync(&acc, c->d_n_accept + chain, sizeof acc, cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
+  {
+    const int rc = device_error_check(c);
+    if (rc) return rc;
+  }
   if (n_pass) *n_pass = c->n_pass;
   if (n_accept) *n_accept = (int64_t)acc;
   if (n_reject) *n_reject = c->n_pass * c->n_sites - (int64_t)acc;
@@ -1593,6 +1742,8 @@ int cmg_sample_now(cmg_context *c, int chain, int64_t *S, int64_t *B) {
   long long sb[2];
   CU(c, cudaMemcpyAsync(sb, c->d_scratch_sb, sizeof sb, cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
+  rc = device_error_check(c);
+  if (rc) return rc;
   if (S) *S = 2 * sb[0] - c->n_sites;
   if (B) *B = sb[1];
   return CMG_OK;
@@ -1650,6 +1801,10 @@ int cmg_read_samples_sb(cmg_context *c, int chain, int64_t first, int64_t count,
                           sizeof(long long) * 2 * c->n_chains, sizeof(long long) * 2, (size_t)count,
                           cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
+  {
+    const int rc = device_error_check(c);
+    if (rc) return rc;
+  }
   for (long long i = 0; i < count; ++i) {
     if (S) S[i] = 2 * tmp[2 * i] - c->n_sites;
     if (B) B[i] = tmp[2 * i + 1];
@@ -1661,13 +1816,22 @@ int cmg_read_samples_sb(cmg_context *c, int chain, int64_t first, int64_t count,
 static int ensure_doubles(cmg_context *c) {
   if (c->n_samples == 0) return CMG_OK;
   if (c->dbl_capacity < c->n_samples) {
+    // grow, keeping what has been converted: those doubles were made with the
+    // (J, mu) in force when they were converted and must never change afterwards
     long long cap = c->dbl_capacity ? c->dbl_capacity : 1024;
     while (cap < c->n_samples) cap *= 2;
+    double *nb = nullptr;
+    CU(c, cudaMalloc(&nb, sizeof(double) * 3 * (size_t)cap * c->n_chains));
+    if (c->d_dbl && c->dbl_valid > 0)
+      CU(c, cudaMemcpy2DAsync(nb, sizeof(double) * (size_t)cap, c->d_dbl,
+                              sizeof(double) * (size_t)c->dbl_capacity,
+                              sizeof(double) * (size_t)c->dbl_valid, (size_t)3 * c->n_chains,
+                              cudaMemcpyDeviceToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
     cudaFree(c->d_dbl);
     c->d_dbl = nullptr;
-    CU(c, cudaMalloc(&c->d_dbl, sizeof(double) * 3 * (size_t)cap * c->n_chains));
+    c->d_dbl = nb;
     c->dbl_capacity = cap;
-    c->dbl_valid = 0;
   }
   if (c->dbl_valid >= c->n_samples) return CMG_OK;
   const long long first = c->dbl_valid, count = c->n_samples - first;
@@ -1715,7 +1879,7 @@ int cmg_read_samples(cmg_context *c, int chain, int quantity, int64_t first, int
                       (size_t)quantity * c->dbl_capacity + first;
   CU(c, cudaMemcpyAsync(out, src, sizeof(double) * (size_t)count, cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
-  return CMG_OK;
+  return device_error_check(c);
 }
 
 // ---- probes -----------------------------------------------------------------------

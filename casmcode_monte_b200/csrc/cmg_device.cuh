@@ -38,7 +38,11 @@ struct ChainTables {
   uint32_t thr_m1[16];  // checkerboard: accept iff philox_u32 <= thr_m1[idx]
   double J, mu, temperature, beta;
   int valid;
-  int pad[3];
+  // bit idx set: exp(-dE*beta) underflowed to 0, the reference's `rand < prob`
+  // (methods/metropolis.hh:33) can never accept; thr_m1[idx] is 0 for such an
+  // entry, so the fast compare can only tie and the exact compare rejects
+  uint32_t never_mask;
+  int pad[2];
 };
 
 struct LatticeView {
@@ -63,7 +67,8 @@ struct LatticeView {
   const unsigned long long *wait_flag[2];
   unsigned long long *signal_flag[2];
   unsigned int *done_counter;   // CTAs of this launch that have finished
-  unsigned long long epoch;     // index of this half-sweep (2*pass + colour)
+  unsigned long long epoch;     // number of fused half-sweeps stepped before this one
+  unsigned int *error;          // sticky error word of the context (bit 2: a neighbour wait timed out)
 };
 
 struct SweepArgs {
@@ -135,6 +140,7 @@ __device__ __forceinline__ uint4 site_group_random(unsigned long long group,
 //   [0, 64)                 the chain's acceptance table thr_m1, 16 x u32 (exact path)
 //   [kSmemLaneLo, +64)      fast-compare lane G[idx] of every entry, in the low half
 //   [kSmemLaneHi, +64)      the same lane in the high half (G[idx] << 16)
+//   [kSmemNever, +4)        never_mask of the chain (exact path only)
 //   [kSmemPair, +14*1024)   pair table: entry (A, B) = G[A] | G[B] << 16 at byte
 //                           offset 4*A + 1024*B, so the 16-bit value formed by two
 //                           neighbouring index bytes (each holding 4*index) IS the
@@ -143,7 +149,8 @@ __device__ __forceinline__ uint4 site_group_random(unsigned long long group,
 extern __shared__ __align__(16) unsigned char cmg_smem[];
 constexpr int kSmemLaneLo = 64;
 constexpr int kSmemLaneHi = 128;
-constexpr int kSmemSmall = 192;  // kernels that only use the 16-entry tables
+constexpr int kSmemNever = 192;  // u32: the chain's never_mask
+constexpr int kSmemSmall = 256;  // kernels that only use the 16-entry tables
 constexpr int kSmemPair = 1024;
 constexpr int kPairCopy = 64;  // byte offset of the odd lanes' copy of every pair-table row
 constexpr int kSmemTile = kSmemPair + 14 * 1024;
@@ -160,6 +167,7 @@ __device__ __forceinline__ void load_accept_table(const ChainTables *tab, bool w
     reinterpret_cast<uint32_t *>(cmg_smem)[threadIdx.x] = thr;
     reinterpret_cast<uint32_t *>(cmg_smem + kSmemLaneLo)[threadIdx.x] = fast_lane(thr);
     reinterpret_cast<uint32_t *>(cmg_smem + kSmemLaneHi)[threadIdx.x] = fast_lane(thr) << 16;
+    if (threadIdx.x == 0) *reinterpret_cast<uint32_t *>(cmg_smem + kSmemNever) = tab->never_mask;
   }
   if (!with_pairs) return;
   for (int e = threadIdx.x; e < 14 * 14; e += blockDim.x) {
@@ -174,6 +182,9 @@ __device__ __forceinline__ void load_accept_table(const ChainTables *tab, bool w
 // byte_off = 4 * table index
 __device__ __forceinline__ uint32_t thr_at(uint32_t byte_off) {
   return *reinterpret_cast<const uint32_t *>(cmg_smem + byte_off);
+}
+__device__ __forceinline__ bool never_at(uint32_t byte_off) {
+  return ((*reinterpret_cast<const uint32_t *>(cmg_smem + kSmemNever) >> (byte_off >> 2)) & 1u) != 0u;
 }
 __device__ __forceinline__ uint32_t lane_lo_at(uint32_t byte_off) {
   return *reinterpret_cast<const uint32_t *>(cmg_smem + kSmemLaneLo + byte_off);
@@ -231,6 +242,10 @@ __device__ __forceinline__ bool any_tie(uint32_t tmax) {
 __device__ __forceinline__ bool accept_exact(uint32_t r16, uint32_t r16b, uint32_t thr) {
   const uint32_t lead = ((r16 << 1) | (r16 >> 15)) & 0xffffu;  // rotl16(r16, 1)
   return ((lead << 16) | r16b) <= thr;
+}
+// exact decision for the table entry at byte_off = 4 * index
+__device__ __forceinline__ bool accept_exact_at(uint32_t r16, uint32_t r16b, uint32_t byte_off) {
+  return accept_exact(r16, r16b, thr_at(byte_off)) && !never_at(byte_off);
 }
 __device__ __forceinline__ uint32_t lane16(uint4 v, int lane) {
   const uint32_t w = (lane >> 1) == 0 ? v.x : (lane >> 1) == 1 ? v.y : (lane >> 1) == 2 ? v.z : v.w;
@@ -337,7 +352,7 @@ __global__ void __launch_bounds__(128) k_halfsweep_generic(SweepArgs A) {
                 O[p + (long long)L.h * (j + (long long)L.n1 * kp)];
       }
       int b = C[q];
-      if (accept_exact(lane16(ra, w), lane16(rb, w), thr_at(4u * (2 * n_up + b)))) {
+      if (accept_exact_at(lane16(ra, w), lane16(rb, w), 4u * (2 * n_up + b))) {
         b ^= 1;
         C[q] = (uint8_t)b;
         ++acc;
@@ -419,8 +434,9 @@ __device__ __noinline__ uint4 resolve_ties16(uint4 idx4e, unsigned long long gro
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int lane = 4 * ww + k;
-        const uint32_t thr = thr_at((iw[w] >> (8 * k)) & 0xffu);
-        mm |= accept_exact(lane16(r, lane), lane16(q, lane), thr) ? (0xffu << (8 * k)) : 0u;
+        mm |= accept_exact_at(lane16(r, lane), lane16(q, lane), (iw[w] >> (8 * k)) & 0xffu)
+                  ? (0xffu << (8 * k))
+                  : 0u;
       }
       m[w] = mm;
     }
@@ -509,13 +525,30 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-// before reading halos: both neighbours must have finished half-sweep epoch-1
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+constexpr unsigned int kErrRingEdge = 1u, kErrRingCopy = 2u, kErrSlabWait = 4u;
+constexpr unsigned long long kSlabWaitNs = 20ull * 1000ull * 1000ull * 1000ull;  // 20 s
+// before reading halos: both neighbours must have finished `epoch` half-sweeps.
+// The wait is bounded: a neighbour that never arrives (dead rank, sequence
+// mismatch) raises the context's sticky error word instead of hanging the GPU.
 __device__ __forceinline__ void slab_wait_neighbours(const LatticeView &L) {
   if (L.epoch == 0 || (!L.wait_flag[0] && !L.wait_flag[1])) return;
   if (threadIdx.x == 0) {
     for (int side = 0; side < 2; ++side)
-      if (L.wait_flag[side])
-        while (ld_acquire_sys(L.wait_flag[side]) < L.epoch) __nanosleep(64);
+      if (L.wait_flag[side] && ld_acquire_sys(L.wait_flag[side]) < L.epoch) {
+        const unsigned long long t0 = globaltimer_ns();
+        while (ld_acquire_sys(L.wait_flag[side]) < L.epoch) {
+          __nanosleep(64);
+          if (globaltimer_ns() - t0 > kSlabWaitNs) {
+            if (L.error) atomicOr(L.error, kErrSlabWait);
+            break;
+          }
+        }
+      }
   }
   __syncthreads();
 }
@@ -1033,7 +1066,7 @@ struct RingArgs {
   uint32_t v_magic;              // ceil(2^32 / V), V = h/16
   int chain_offset;              // global index of chain 0
   uint8_t *mailbox;              // [chain][tile][side][plane][h], zero at launch
-  unsigned int *error;           // raised if an edge wait timed out
+  unsigned int *error;           // the context's sticky error word (edge wait / bulk copy timed out)
 };
 constexpr int kRingMaxPasses = 256;
 
@@ -1135,7 +1168,7 @@ __global__ void __launch_bounds__(NT, 1) k_ring2d(RingArgs A) {
     unsigned int spins = 0;
     while (!mbar_try_wait(&s_mbar, 0)) {
       if (++spins > (1u << 12)) {  // bounded (try_wait itself sleeps), like the edge waits
-        atomicExch(A.error, 2u);
+        atomicOr(A.error, kErrRingCopy);
         break;
       }
     }
@@ -1194,7 +1227,7 @@ __global__ void __launch_bounds__(NT, 1) k_ring2d(RingArgs A) {
         while (!ring_stamp_ok(hv, expect)) {
           hv = ld_relaxed_gpu_v4(mb_in + (colour ^ 1) * h);
           if (++spins > (1u << 22)) {  // bounded: report instead of hanging the GPU
-            atomicExch(A.error, 1u);
+            atomicOr(A.error, kErrRingEdge);
             break;
           }
         }
@@ -1513,6 +1546,46 @@ __global__ void k_natural_to_planes(const uint8_t *__restrict__ nat, uint8_t *pl
   const long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (l >= s.n_sites) return;
   planes[plane_addr(s, l, plane_stride)] = nat[l];
+}
+// Compact host formats of the occupation (same site order l as the int32 form):
+// int8 +1/-1 per site, and one bit per site (bit l & 7 of byte l >> 3 set iff
+// s_l = +1).  `base` is the chain's planes (planar != 0) or its natural array.
+__device__ __forceinline__ long long site_addr_of(const NaturalShape &s, long long l, int planar,
+                                                  long long plane_stride) {
+  return planar ? plane_addr(s, l, plane_stride) : l;
+}
+__global__ void k_i8_to_sites(const int8_t *__restrict__ src, uint8_t *base, long long plane_stride,
+                              NaturalShape s, int planar, int *bad) {
+  const long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= s.n_sites) return;
+  const int v = src[l];
+  if (v != 1 && v != -1) atomicExch(bad, 1);
+  base[site_addr_of(s, l, planar, plane_stride)] = (uint8_t)(v > 0);
+}
+__global__ void k_sites_to_i8(const uint8_t *__restrict__ base, long long plane_stride, int8_t *dst,
+                              NaturalShape s, int planar) {
+  const long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= s.n_sites) return;
+  dst[l] = base[site_addr_of(s, l, planar, plane_stride)] ? 1 : -1;
+}
+__global__ void k_bits_to_sites(const uint8_t *__restrict__ bits, uint8_t *base,
+                                long long plane_stride, NaturalShape s, int planar) {
+  const long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= s.n_sites) return;
+  base[site_addr_of(s, l, planar, plane_stride)] = (uint8_t)((bits[l >> 3] >> (l & 7)) & 1u);
+}
+// one thread per output byte (8 sites)
+__global__ void k_sites_to_bits(const uint8_t *__restrict__ base, long long plane_stride,
+                                uint8_t *bits, NaturalShape s, int planar) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (8 * g >= s.n_sites) return;
+  unsigned int v = 0;
+#pragma unroll
+  for (int b = 0; b < 8; ++b) {
+    const long long l = 8 * g + b;
+    if (l < s.n_sites) v |= (unsigned int)(base[site_addr_of(s, l, planar, plane_stride)] & 1u) << b;
+  }
+  bits[g] = (uint8_t)v;
 }
 __global__ void k_fill_bytes(uint8_t *dst, long long n, uint8_t v) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -96,6 +96,30 @@ class IsingLatticeGPU:
         self._ck(self._lib.cmg_download_occupation_i32(self._ctx, chain, _p(out, C.c_int32), out.size))
         return out
 
+    def upload_i8(self, occ, chain=0):
+        """int8 +1/-1 per site (a quarter of the int32 form's PCIe traffic)."""
+        occ = np.ascontiguousarray(occ, dtype=np.int8).ravel()
+        self._ck(self._lib.cmg_upload_occupation_i8(self._ctx, chain, _p(occ, C.c_int8), occ.size))
+
+    def download_i8(self, chain=0, out=None):
+        if out is None:
+            out = np.empty(self.n_sites, dtype=np.int8)
+        self._ck(self._lib.cmg_download_occupation_i8(self._ctx, chain, _p(out, C.c_int8), out.size))
+        return out
+
+    def upload_bits(self, bits, chain=0):
+        """One bit per site, as numpy.packbits(occ > 0, bitorder='little')."""
+        bits = np.ascontiguousarray(bits, dtype=np.uint8).ravel()
+        if bits.size != (self.n_sites + 7) // 8:
+            raise ValueError("Error in set_occupation: size mismatch")
+        self._ck(self._lib.cmg_upload_occupation_bits(self._ctx, chain, _p(bits, C.c_uint8), self.n_sites))
+
+    def download_bits(self, chain=0, out=None):
+        if out is None:
+            out = np.empty((self.n_sites + 7) // 8, dtype=np.uint8)
+        self._ck(self._lib.cmg_download_occupation_bits(self._ctx, chain, _p(out, C.c_uint8), self.n_sites))
+        return out
+
     def upload_dev(self, dev_ptr, n, chain=0):
         self._ck(self._lib.cmg_upload_occupation_i32_dev(self._ctx, chain, C.c_void_p(int(dev_ptr)), int(n)))
 
@@ -274,6 +298,13 @@ class IsingLatticeGPU:
     # -- slab plumbing --
     def slab_half_sweep(self, colour, pass_index, sample=False):
         self._ck(self._lib.cmg_slab_half_sweep(self._ctx, int(colour), int(pass_index), int(bool(sample))))
+
+    def slab_run_passes(self, n_passes, sample_period=0):
+        """The pass loop of a slab whose neighbours are attached (fused halo push)."""
+        self._ck(self._lib.cmg_slab_run_passes(self._ctx, int(n_passes), int(sample_period)))
+
+    def slab_set_halo_exchange(self, enabled):
+        self._ck(self._lib.cmg_slab_set_halo_exchange(self._ctx, int(bool(enabled))))
 
     def slab_boundary_ptr(self, colour, side):
         p, n = C.c_void_p(), C.c_int64()

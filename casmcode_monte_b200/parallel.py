@@ -135,6 +135,10 @@ class GpuSlabEngine:
     def half_sweep(self, colour, pass_index, sample=False):
         self.lat.slab_half_sweep(colour, pass_index, sample)
 
+    def run_passes(self, n_passes, sample_period=0):
+        """Library-side pass loop (neighbours attached, halo exchange fused into the kernels)."""
+        self.lat.slab_run_passes(n_passes, sample_period)
+
     def observables(self):
         """(ones-based S, B) partial sums of this slab for the current state."""
         return self.lat.sample_now()
@@ -217,6 +221,11 @@ class SlabRing:
                 self.dist.barrier()
 
     def run_passes(self, n_passes, sample_period=0):
+        if self.transport == "peer" and hasattr(self.e, "run_passes"):
+            # the whole loop runs inside the C-ABI library: one call, no host work per half-sweep
+            self.e.run_passes(n_passes, sample_period)
+            self.pass_index += n_passes
+            return
         for _ in range(n_passes):
             sample = sample_period > 0 and ((self.pass_index + 1) % sample_period) == 0
             for colour in (0, 1):

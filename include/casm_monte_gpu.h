@@ -107,6 +107,21 @@ int cmg_slab_ipc_attach(cmg_context *ctx, int side, const void *handle,
  * own halo exchange.  pass_index is the global pass number (Philox counter). */
 int cmg_slab_half_sweep(cmg_context *ctx, int colour, uint64_t pass_index,
                         int sample);
+/* The pass loop of a slab with both neighbours attached (the body of
+ * methods::basic_occupation_metropolis, include/casm/monte/methods/
+ * basic_occupation_metropolis.hh:381-422, on this rank's columns): n_passes x
+ * (colour-0 half-sweep, colour-1 half-sweep) with the halo push and the
+ * neighbour flags fused into the kernels -- no host work, collective or second
+ * call between half-sweeps.  Continues from the context's pass counter;
+ * samples the slab's partial (S, B) whenever the pass count is a multiple of
+ * sample_period (> 0).  Every rank of the ring must make the same calls.
+ * Asynchronous; a neighbour that never arrives is reported by the next
+ * synchronising call (bounded waits), not by a hung GPU. */
+int cmg_slab_run_passes(cmg_context *ctx, int64_t n_passes, int64_t sample_period);
+/* measurement aid: enabled = 0 makes the half-sweeps neither push their
+ * boundary columns nor wait for the neighbours (halos go stale; the timing is
+ * that of the sweep alone, for the halo share of a decomposed run) */
+int cmg_slab_set_halo_exchange(cmg_context *ctx, int enabled);
 
 /* ---- model and conditions --------------------------------------------------
  * Replaces IsingFormationEnergy(J, lattice_type) (model.hh:168-181) and
@@ -136,6 +151,16 @@ int cmg_upload_occupation_i32_dev(cmg_context *ctx, int chain,
                                   const int32_t *occ_dev, int64_t n);
 int cmg_download_occupation_i32_dev(cmg_context *ctx, int chain, int32_t *occ_dev,
                                     int64_t n);
+/* The same occupation in compact host formats, for callers that move many
+ * lattices across PCIe: int8 +1/-1 per site, or one bit per site (bit l & 7 of
+ * byte l >> 3 set iff site l holds +1; (n_sites + 7) / 8 bytes).  Site order l
+ * as above.  The upload of bits is asynchronous (nothing to validate). */
+int cmg_upload_occupation_i8(cmg_context *ctx, int chain, const int8_t *occ, int64_t n);
+int cmg_download_occupation_i8(cmg_context *ctx, int chain, int8_t *occ, int64_t n);
+int cmg_upload_occupation_bits(cmg_context *ctx, int chain, const uint8_t *bits,
+                               int64_t n_sites);
+int cmg_download_occupation_bits(cmg_context *ctx, int chain, uint8_t *bits,
+                                 int64_t n_sites);
 int cmg_fill_occupation(cmg_context *ctx, int chain, int value);
 /* single-site access: IsingConfiguration::occ / set_occ (model.hh:62-70) */
 int cmg_get_occ(cmg_context *ctx, int chain, int64_t linear_site_index, int32_t *value);

@@ -1683,8 +1683,12 @@ struct AcceptTable {
   int dim = 2;
   double dE[2][7];
   double prob[2][7];       // exp(-dE*beta)  (unused when dE<0)
-  uint32_t thr_m1[2][7];   // checkerboard mode: accept iff r32 <= thr_m1
+  uint32_t thr_m1[2][7];   // checkerboard mode: accept iff r32 <= thr_m1 ...
+  bool never[2][7];        // ... unless exp(-dE*beta) == 0: `rand < prob` (metropolis.hh:33) never accepts
   double beta = 0.0;
+  bool accept_u32(int sp, int n_up, uint32_t r) const {
+    return !never[sp][n_up] && r <= thr_m1[sp][n_up];
+  }
 };
 inline AcceptTable make_accept_table(int dim, double J, double T, double mu) {
   AcceptTable t;
@@ -1704,8 +1708,12 @@ inline AcceptTable make_accept_table(int dim, double J, double T, double mu) {
       double p = std::exp(-dE * t.beta);
       t.prob[sp][nu] = p;
       uint32_t thr;
+      t.never[sp][nu] = false;
       if (dE < 0.0 || p >= 1.0) {
         thr = 0xFFFFFFFFu;
+      } else if (!(p > 0.0)) {
+        thr = 0u;
+        t.never[sp][nu] = true;
       } else {
         double scaled = std::ceil(p * 4294967296.0);  // in [0, 2^32]
         if (scaled < 1.0) scaled = 1.0;
@@ -1731,7 +1739,7 @@ inline AcceptTable make_accept_table(int dim, double J, double T, double mu) {
 // (lane l = bits [16*(l&1), 16*(l&1)+16) of output word l>>1) and r16' is the
 // same lane of the call with counter word 3 | 2 ("refinement" stream; the
 // kernels only evaluate it when r16 & 0x7FFF ties with the top 15 bits of the threshold).
-// The site is flipped iff R <= thr_m1[b][n_up].
+// The site is flipped iff R <= thr_m1[b][n_up] (and never when exp(-dE*beta) == 0).
 // Requires even extents.  One pass = colour 0 half-sweep then colour 1.
 struct CheckerboardResult {
   long long n_accept = 0;
@@ -1785,7 +1793,7 @@ inline void checkerboard_pass(std::vector<int> &occ, std::vector<int> const &sha
                     (occ[i + n0 * (j + n1 * km)] > 0);
           }
           int sp = occ[l] > 0 ? 1 : 0;
-          if (r <= tab.thr_m1[sp][n_up]) {
+          if (tab.accept_u32(sp, n_up, r)) {
             occ[l] = -occ[l];
             res.n_accept++;
           }
@@ -1818,7 +1826,7 @@ inline long long checkerboard_half_sweep_slab(std::vector<int> &occ, std::vector
       const int n_up = (occ[ip + n0 * jl] > 0) + (occ[im + n0 * jl] > 0) + (left > 0) + (right > 0);
       const long l = i + n0 * jl;
       const int sp = occ[l] > 0 ? 1 : 0;
-      if (r <= tab.thr_m1[sp][n_up]) {
+      if (tab.accept_u32(sp, n_up, r)) {
         occ[l] = -occ[l];
         ++n_accept;
       }

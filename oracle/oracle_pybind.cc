@@ -481,16 +481,19 @@ PYBIND11_MODULE(_monte_oracle, m) {
     const int z = 2 * dim;
     f64arr dE({2, z + 1}), prob({2, z + 1});
     py::array_t<uint32_t> thr({2, z + 1});
+    py::array_t<bool> never({2, z + 1});
     for (int s = 0; s < 2; ++s)
       for (int n = 0; n <= z; ++n) {
         dE.mutable_at(s, n) = t.dE[s][n];
         prob.mutable_at(s, n) = t.prob[s][n];
         thr.mutable_at(s, n) = t.thr_m1[s][n];
+        never.mutable_at(s, n) = t.never[s][n];
       }
     py::dict d;
     d["dE"] = dE;
     d["prob"] = prob;
     d["thr_m1"] = thr;
+    d["never"] = never;
     d["beta"] = t.beta;
     return d;
   });
