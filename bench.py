@@ -86,6 +86,16 @@ def ncu_traffic(kernel):
         return None, None
 
 
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clocks / throttle reasons while the timed region runs: NVML in
     process every 10 ms (the timed region is well under a second), nvidia-smi as

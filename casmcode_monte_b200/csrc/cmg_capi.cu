@@ -1446,7 +1446,8 @@ static int run_serial(cmg_context *c, long long n_passes, long long sample_perio
     A.series = tmp;
     A.series_chain_stride = 2 * n_new;
   }
-  size_t smem = 312 * sizeof(unsigned long long);
+  // engine state + its tempered words + dE / prob tables
+  size_t smem = 2 * 312 * sizeof(unsigned long long) + 32 * sizeof(double);
   A.use_smem = 0;
   if ((size_t)c->n_sites + smem <= 200 * 1024) {
     A.use_smem = 1;
@@ -1454,7 +1455,7 @@ static int run_serial(cmg_context *c, long long n_passes, long long sample_perio
   }
   CU(c, cudaFuncSetAttribute(k_serial_reference, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)(204 * 1024)));
-  k_serial_reference<<<c->n_chains, 128, smem, c->stream>>>(A);
+  k_serial_reference<<<c->n_chains, kSerialThreads, smem, c->stream>>>(A);
   ++c->launches;
   CU(c, cudaGetLastError());
   if (tmp) {

@@ -540,6 +540,8 @@ __device__ __forceinline__ void slab_wait_neighbours(const LatticeView &L) {
   if (threadIdx.x == 0) {
     for (int side = 0; side < 2; ++side)
       if (L.wait_flag[side] && ld_acquire_sys(L.wait_flag[side]) < L.epoch) {
+        // a wait that already timed out is not repeated by every later CTA and launch
+        if (L.error && (*(volatile unsigned int *)L.error & kErrSlabWait)) break;
         const unsigned long long t0 = globaltimer_ns();
         while (ld_acquire_sys(L.wait_flag[side]) < L.epoch) {
           __nanosleep(64);
@@ -1896,7 +1898,9 @@ __device__ __forceinline__ unsigned long long mt64_uniform_int(unsigned long lon
 __device__ __forceinline__ double mt64_uniform_real(unsigned long long *x, int &pos,
                                                     double maximum_value) {
   const unsigned long long u = mt64_next(x, pos);
-  double r = __ddiv_rn(__ull2double_rn(u), 18446744073709551616.0);
+  // u / 2^64: scaling by a power of two is exact, so the product with 2^-64 is
+  // the correctly rounded quotient (no software division in the loop)
+  double r = __dmul_rn(__ull2double_rn(u), 5.42101086242752217003726400434970855712890625e-20);
   if (r >= 1.0) r = 0.99999999999999988897769753748434595763683319091796875;
   return __dadd_rn(__dmul_rn(r, __dsub_rn(maximum_value, 0.0)), 0.0);
 }
@@ -1916,40 +1920,145 @@ struct SerialArgs {
   int use_smem;             // lattice staged in shared memory
 };
 
-__global__ void __launch_bounds__(128) k_serial_reference(SerialArgs A) {
+// neighbour count of site l with 32-bit index arithmetic (n_sites < 2^31; the 64-bit
+// divisions of natural_n_up are software routines)
+__device__ __forceinline__ int natural_n_up32(const uint8_t *nat, int n0, int n1, int n2, int dim,
+                                              unsigned int l) {
+  const unsigned int r = l / (unsigned int)n0;
+  const int i = (int)(l - r * (unsigned int)n0);
+  int j = (int)r, k = 0;
+  if (dim == 3) {
+    k = (int)(r / (unsigned int)n1);
+    j = (int)(r - (unsigned int)k * (unsigned int)n1);
+  }
+  const unsigned int base = (unsigned int)n0 * ((unsigned int)j + (unsigned int)n1 * (unsigned int)k);
+  const int ip = (i + 1 == n0) ? 0 : i + 1, im = (i == 0) ? n0 - 1 : i - 1;
+  const int jp = (j + 1 == n1) ? 0 : j + 1, jm = (j == 0) ? n1 - 1 : j - 1;
+  const unsigned int kk = (unsigned int)n1 * (unsigned int)k;
+  int n = nat[base + ip] + nat[base + im] + nat[i + (unsigned int)n0 * ((unsigned int)jp + kk)] +
+          nat[i + (unsigned int)n0 * ((unsigned int)jm + kk)];
+  if (dim == 3) {
+    const int kp = (k + 1 == n2) ? 0 : k + 1, km = (k == 0) ? n2 - 1 : k - 1;
+    n += nat[i + (unsigned int)n0 * ((unsigned int)j + (unsigned int)n1 * (unsigned int)kp)] +
+         nat[i + (unsigned int)n0 * ((unsigned int)j + (unsigned int)n1 * (unsigned int)km)];
+  }
+  return n;
+}
+
+// One block per chain.  The random stream is produced in blocks of 312 words by
+// the whole CTA (the Mersenne twist and the tempering are data-parallel within a
+// block of the recurrence), the Metropolis loop itself is walked by thread 0 in the
+// reference's order; it pauses whenever the block of words is used up, wherever in
+// a step that happens (a step draws one word for the site, redraws with the tiny
+// probability of Lemire's rejection, and one more word only when dE >= 0).
+constexpr int kSerialThreads = 128;
+__device__ __forceinline__ unsigned long long mt64_temper(unsigned long long z) {
+  z ^= (z >> 29) & 0x5555555555555555ull;
+  z ^= (z << 17) & 0x71D67FFFEDA60000ull;
+  z ^= (z << 37) & 0xFFF7EEE000000000ull;
+  z ^= (z >> 43);
+  return z;
+}
+// x[0..312) -> next block of the recurrence, in place, by all threads of the CTA
+__device__ __forceinline__ void mt64_twist_block(unsigned long long *x) {
+  constexpr unsigned long long UPPER = 0xFFFFFFFF80000000ull, LOWER = 0x7FFFFFFFull;
+  constexpr unsigned long long A = 0xB5026F5AA96619E9ull;
+  auto mix = [&](unsigned long long a, unsigned long long b) {
+    const unsigned long long y = (a & UPPER) | (b & LOWER);
+    return (y >> 1) ^ ((y & 1ull) ? A : 0ull);
+  };
+  unsigned long long v[2];
+  // k in [0, 156): x[k] = x[k + 156] ^ mix(x[k], x[k + 1]), all operands old
+  for (int r = 0, k = threadIdx.x; r < 2; ++r, k += kSerialThreads)
+    if (k < 156) v[r] = x[k + 156] ^ mix(x[k], x[k + 1]);
+  __syncthreads();
+  for (int r = 0, k = threadIdx.x; r < 2; ++r, k += kSerialThreads)
+    if (k < 156) x[k] = v[r];
+  __syncthreads();
+  // k in [156, 311): x[k] = x[k - 156] (new) ^ mix(x[k], x[k + 1]) (old)
+  for (int r = 0, k = 156 + threadIdx.x; r < 2; ++r, k += kSerialThreads)
+    if (k < 311) v[r] = x[k - 156] ^ mix(x[k], x[k + 1]);
+  __syncthreads();
+  for (int r = 0, k = 156 + threadIdx.x; r < 2; ++r, k += kSerialThreads)
+    if (k < 311) x[k] = v[r];
+  if (threadIdx.x == 0) x[311] = x[155] ^ mix(x[311], x[0]);  // x[311] still old, x[0] and x[155] new
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kSerialThreads) k_serial_reference(SerialArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int s_done;
   const int chain = blockIdx.x;
-  unsigned long long *mt = reinterpret_cast<unsigned long long *>(smem_raw);
-  uint8_t *lat_s = smem_raw + 312 * sizeof(unsigned long long);
+  unsigned long long *mt = reinterpret_cast<unsigned long long *>(smem_raw);      // recurrence state
+  unsigned long long *out = mt + 312;                                              // tempered words
+  double *tab_s = reinterpret_cast<double *>(out + 312);                           // dE[16], prob[16]
+  uint8_t *lat_s = reinterpret_cast<uint8_t *>(tab_s + 32);
   const NaturalShape s = A.shape;
   uint8_t *nat_g = A.nat + (long long)chain * s.n_sites;
   MT64State *eng = A.engines + chain;
 
-  for (int i = threadIdx.x; i < 312; i += blockDim.x) mt[i] = eng->x[i];
+  for (int i = threadIdx.x; i < 312; i += blockDim.x) {
+    mt[i] = eng->x[i];
+    out[i] = mt64_temper(mt[i]);
+  }
+  if (threadIdx.x < 16) {
+    tab_s[threadIdx.x] = A.tabs[chain].dE[threadIdx.x];
+    tab_s[16 + threadIdx.x] = A.tabs[chain].prob[threadIdx.x];
+  }
   if (A.use_smem)
     for (long long i = threadIdx.x; i < s.n_sites; i += blockDim.x) lat_s[i] = nat_g[i];
+  if (threadIdx.x == 0) s_done = (A.n_passes <= 0);
   __syncthreads();
 
+  // state of thread 0's walk (kept in registers across the pauses)
+  uint8_t *nat = A.use_smem ? lat_s : nat_g;
+  int pos = eng->pos;
+  long long ones = 0, B = 0, pass = 0, step = 0, slot = 0, l = 0;
+  unsigned long long n_acc = 0;
+  int n_up = 0, b = 0, idx = 0;
+  bool need_real = false;
+  const int z = 2 * s.dim;
+  const bool small = s.n_sites < (1ll << 31);
+  const unsigned long long range = (unsigned long long)s.n_sites;
+  const unsigned long long lemire_thr = (0ull - range) % range;
   if (threadIdx.x == 0) {
-    uint8_t *nat = A.use_smem ? lat_s : nat_g;
-    const ChainTables *tab = A.tabs + chain;
-    int pos = eng->pos;
-    long long ones = A.cur_sb[2 * chain], B = A.cur_sb[2 * chain + 1];
-    unsigned long long n_acc = 0;
-    const int z = 2 * s.dim;
-    long long slot = 0;
-    for (long long pass = 0; pass < A.n_passes; ++pass) {
-      for (long long step = 0; step < s.n_sites; ++step) {
-        const long long l =
-            (long long)mt64_uniform_int(mt, pos, (unsigned long long)s.n_sites);
-        const int n_up = natural_n_up(nat, s, l);
-        const int b = nat[l];
-        const int idx = 2 * n_up + b;
-        const double dE = tab->dE[idx];
-        bool accept = dE < 0.0;
-        if (!accept) {
-          const double u = mt64_uniform_real(mt, pos, 1.0);
-          accept = u < tab->prob[idx];
+    ones = A.cur_sb[2 * chain];
+    B = A.cur_sb[2 * chain + 1];
+  }
+
+  while (!s_done) {
+    if (pos >= 312) {  // block-uniform: pos is only advanced by thread 0 and published below
+      mt64_twist_block(mt);
+      for (int i = threadIdx.x; i < 312; i += blockDim.x) out[i] = mt64_temper(mt[i]);
+      pos = 0;
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      bool done = false;
+      while (pos < 312) {
+        const unsigned long long u = out[pos++];
+        bool accept;
+        if (!need_real) {
+          // libstdc++ 13 bits/uniform_int_dist.h:252-281 (Lemire, 128-bit product)
+          const unsigned long long low = u * range;
+          if (low < range && low < lemire_thr) continue;  // redraw
+          l = (long long)__umul64hi(u, range);
+          n_up = small ? natural_n_up32(nat, s.n0, s.n1, s.n2, s.dim, (unsigned int)l)
+                       : natural_n_up(nat, s, l);
+          b = nat[l];
+          idx = 2 * n_up + b;
+          accept = tab_s[idx] < 0.0;
+          if (!accept) {
+            need_real = true;  // metropolis.hh:28-34: the uniform is drawn only when dE >= 0
+            continue;
+          }
+        } else {
+          // bits/random.tcc:3349-3381 (one 64-bit word for 53 bits), then r*(b-a)+a
+          double r = __dmul_rn(__ull2double_rn(u), 5.42101086242752217003726400434970855712890625e-20);
+          if (r >= 1.0) r = 0.99999999999999988897769753748434595763683319091796875;
+          r = __dadd_rn(__dmul_rn(r, __dsub_rn(1.0, 0.0)), 0.0);
+          accept = r < tab_s[16 + idx];
+          need_real = false;
         }
         if (accept) {
           nat[l] = (uint8_t)(b ^ 1);
@@ -1958,15 +2067,27 @@ __global__ void __launch_bounds__(128) k_serial_reference(SerialArgs A) {
           ones += b ? -1 : 1;
           B += (long long)ds * (2 * n_up - z);
         }
+        if (++step == s.n_sites) {  // basic_occupation_metropolis.hh:399-411
+          step = 0;
+          if (A.sample_period > 0 && A.series && ((A.pass_base + pass + 1) % A.sample_period) == 0) {
+            long long *dst = A.series + (long long)chain * A.series_chain_stride + 2 * slot;
+            dst[0] = ones;
+            dst[1] = B;
+            ++slot;
+          }
+          if (++pass == A.n_passes) {
+            done = true;
+            break;
+          }
+        }
       }
-      if (A.sample_period > 0 && A.series &&
-          ((A.pass_base + pass + 1) % A.sample_period) == 0) {
-        long long *dst = A.series + (long long)chain * A.series_chain_stride + 2 * slot;
-        dst[0] = ones;
-        dst[1] = B;
-        ++slot;
-      }
+      if (done) s_done = 1;
     }
+    // every thread learns whether the block of words was used up (pos == 312) or the run ended
+    __syncthreads();
+    if (!s_done) pos = 312;
+  }
+  if (threadIdx.x == 0) {
     eng->pos = pos;
     A.cur_sb[2 * chain] = ones;
     A.cur_sb[2 * chain + 1] = B;

@@ -71,6 +71,89 @@ def test_slabs_on_one_gpu_match_single_context(n_slabs, transport):
     assert sum(e.observables()[1] for e in engines) == int(Br[-1])
 
 
+def test_library_side_pass_loop_and_restarted_pass_counter():
+    """cmg_slab_run_passes (the pass loop inside the library, halo exchange fused into the
+    kernels) on a ring of one slab attached to itself: bit-identical to the plain context.
+    Re-running the trajectory from pass 0 (cmg_set_pass_counter) must neither hang nor
+    change the result: the neighbour flags count fused half-sweeps, not pass indices."""
+    import torch
+
+    import casmcode_monte_b200 as cm
+    from casmcode_monte_b200.parallel import GpuSlabEngine
+
+    shape = [128, 48]
+    n0, n1 = shape
+    T, mu, seed, n_passes = 2633.0, -0.02, 4711, 7
+    occ = np.random.default_rng(3).choice(np.array([-1, 1], dtype=np.int32), size=n0 * n1)
+    ref = _single(cm, shape, occ, T, mu, seed, n_passes, sample_period=2)
+    e = GpuSlabEngine(shape, 0, n1, J, T, mu, seed)
+    with pytest.raises(cm.CmgError):
+        e.lat.slab_run_passes(1)  # neighbours not attached
+    for attempt in range(2):
+        e.upload(occ)
+        for colour in (0, 1):
+            e.halo(colour, 1).copy_(e.boundary(colour, 0))
+            e.halo(colour, 0).copy_(e.boundary(colour, 1))
+        torch.cuda.synchronize()
+        if attempt == 0:
+            e.lat.slab_ipc_attach(0, peer=e.lat)
+            e.lat.slab_ipc_attach(1, peer=e.lat)
+        e.lat.set_pass_counter(0)
+        e.lat.reset_counters()
+        e.lat.clear_samples()
+        e.lat.slab_run_passes(n_passes, 2)
+        e.sync()  # a timed-out neighbour wait would be reported here
+        assert np.array_equal(e.download(), ref.download())
+        S, B = e.lat.samples_sb()
+        assert np.array_equal(S, ref.samples_sb()[0]) and np.array_equal(B, ref.samples_sb()[1])
+        assert e.counters()[1] == ref.counters()[1]
+    # timing aid: with the exchange off the sweep still runs (stale halos), no waits
+    e.lat.slab_set_halo_exchange(False)
+    e.lat.slab_run_passes(2, 0)
+    e.sync()
+    e.lat.close()
+
+
+def test_two_slabs_on_two_streams_run_their_own_pass_loops():
+    """Two slab contexts of one GPU on two streams, each running cmg_slab_run_passes on its
+    own: the kernels order themselves through the neighbour flags alone."""
+    import torch
+
+    import casmcode_monte_b200 as cm
+    from casmcode_monte_b200.parallel import GpuSlabEngine, slab_columns
+
+    shape = [128, 48]
+    n0, n1 = shape
+    T, mu, seed, n_passes = 2500.0, 0.01, 99, 5
+    occ = np.random.default_rng(4).choice(np.array([-1, 1], dtype=np.int32), size=n0 * n1)
+    ref = _single(cm, shape, occ, T, mu, seed, n_passes)
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    engines = []
+    for r in range(2):
+        cb, nc = slab_columns(n1, 2, r)
+        e = GpuSlabEngine(shape, cb, nc, J, T, mu, seed, stream=streams[r].cuda_stream)
+        e.upload(occ[n0 * cb : n0 * (cb + nc)])
+        engines.append(e)
+    torch.cuda.synchronize()
+    for colour in (0, 1):
+        for r, e in enumerate(engines):
+            engines[(r - 1) % 2].halo(colour, 1).copy_(e.boundary(colour, 0))
+            engines[(r + 1) % 2].halo(colour, 0).copy_(e.boundary(colour, 1))
+    torch.cuda.synchronize()
+    for r, e in enumerate(engines):
+        e.lat.slab_ipc_attach(0, peer=engines[(r - 1) % 2].lat)
+        e.lat.slab_ipc_attach(1, peer=engines[(r + 1) % 2].lat)
+    for e in engines:
+        e.lat.slab_run_passes(n_passes, 1)  # asynchronous: both loops are in flight together
+    for e in engines:
+        e.sync()
+    assert np.array_equal(np.concatenate([e.download() for e in engines]), ref.download())
+    B = sum(e.lat.samples_sb()[1] for e in engines)
+    assert np.array_equal(B, ref.samples_sb()[1])
+    for e in engines:
+        e.lat.close()
+
+
 def test_slab_creation_errors():
     import casmcode_monte_b200 as cm
 
