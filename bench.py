@@ -674,7 +674,7 @@ def ours_slab(args):
         proxy = {
             "lattice": [PROXY_N, PROXY_N],
             "passes": proxy_passes,
-            "single_gpu_kernel": "k_" + ref.kernel_variant,
+            "single_gpu_kernel": ("k_halfsweep_" if ref.kernel_variant.startswith("bulk") else "k_") + ref.kernel_variant,
             "occupation_bit_identical_to_single_gpu": bool(same),
             "sampled_S_B_identical": bool(np.array_equal(S_sum, Sr) and np.array_equal(B_sum, Br)),
         }
