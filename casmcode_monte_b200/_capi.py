@@ -84,6 +84,7 @@ SIGNATURES = {
     "cmg_series_equilibration": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int64, C.c_double, _intp, _i64p]),
     "cmg_series_stats_all": (C.c_int, [_ctx, C.c_int, _i64p, C.c_int64, C.c_double, _f64p, _f64p, _f64p, _i64p]),
     "cmg_series_equilibration_all": (C.c_int, [_ctx, C.c_int, C.c_int64, C.c_double, _intp, _i64p]),
+    "cmg_series_check": (C.c_int, [_ctx, C.c_int, C.c_int, _intp, _f64p, C.c_int64, C.c_double, _intp, _i64p, _i64p, _f64p, _f64p]),
     "cmg_host_series_stats": (C.c_int, [C.c_int, _f64p, C.c_int64, C.c_double, _f64p, _f64p, _f64p, _i64p]),
     "cmg_host_series_equilibration": (C.c_int, [C.c_int, _f64p, C.c_int64, C.c_double, _intp, _i64p]),
     "cmg_host_series_stats_weighted": (C.c_int, [C.c_int, _f64p, _f64p, C.c_int64, C.c_double, C.c_int, C.c_int64, _f64p, _f64p, _f64p, _f64p, _i64p]),
@@ -91,6 +92,8 @@ SIGNATURES = {
     "cmg_host_series_equilibration_weighted": (C.c_int, [C.c_int, _f64p, _f64p, C.c_int64, C.c_double, _intp, _i64p]),
     "cmg_conv_l_to_bijk": (C.c_int, [C.c_int, _i64p, C.c_int64, _i64p, C.c_int64, _i64p]),
     "cmg_conv_bijk_to_l": (C.c_int, [C.c_int, _i64p, C.c_int64, _i64p, C.c_int64, _i64p]),
+    "cmg_conv_general_l_to_bijk": (C.c_int, [C.c_int, _i64p, C.c_int64, _i64p, C.c_int64, _i64p]),
+    "cmg_conv_general_bijk_to_l": (C.c_int, [C.c_int, _i64p, C.c_int64, _i64p, C.c_int64, _i64p]),
     "cmg_set_energy_form": (C.c_int, [_ctx, C.c_int]),
     "cmg_launch_count": (C.c_int, [_ctx, _i64p]),
     "cmg_kernel_variant": (C.c_char_p, [_ctx]),

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../include/casm_monte_gpu.h"
+#include "../../include/casm_monte_b200/snf.hh"
 #include "cmg_device.cuh"
 
 using namespace cmg;
@@ -2072,6 +2073,71 @@ int cmg_series_equilibration_all(cmg_context *c, int quantity, int64_t count, do
   return run_equil_jobs(c, c->stream, jobs, abs_precision, is_equilibrated, n_equil);
 }
 
+int cmg_series_check(cmg_context *c, int chain, int n_components, const int *quantity,
+                     const double *abs_precision, int64_t count, double confidence,
+                     int *is_equilibrated, int64_t *n_equil, int64_t *n_stats, double *mean,
+                     double *calculated_precision) {
+  NEED(c);
+  if (chain < 0 || chain >= c->n_chains) return fail(c, CMG_EINVAL, "bad chain index");
+  if (n_components < 1 || n_components > 3 || !quantity || !abs_precision)
+    return fail(c, CMG_EINVAL, "1 to 3 components");
+  for (int i = 0; i < n_components; ++i)
+    if (quantity[i] < 0 || quantity[i] > 2 || !(abs_precision[i] >= 0.0))
+      return fail(c, CMG_EINVAL, "bad quantity or precision");
+  if (count <= 0) return fail(c, CMG_EINVAL, "Error in equilibration_check: observations.size()==0");
+  if (count > c->n_samples) return fail(c, CMG_EINVAL, "sample range outside the series");
+  int rc = ensure_doubles(c);
+  if (rc) return rc;
+  const int n = n_components;
+  // one scratch block: eq jobs | stat jobs | is_eq | n_eq | n_stats | out4 | k_star
+  struct Host {
+    SeriesJob eq[3], st[3];
+    long long n_eq[3], n_stats, k_star[3];
+    double out4[12];
+    int is_eq[4];
+  } h;
+  memset(&h, 0, sizeof h);
+  for (int i = 0; i < n; ++i) {
+    h.eq[i].x = series_ptr(c, chain, quantity[i]);
+    h.eq[i].n = count;
+  }
+  Host *d = nullptr;
+  CU(c, scratch_alloc(&d, sizeof(Host), c->stream));
+  CU(c, cudaMemcpyAsync(d, &h, sizeof(Host), cudaMemcpyHostToDevice, c->stream));
+  static const long long kEquilSmemDoubles = 24 * 1024;
+  cudaFuncSetAttribute(k_series_equilibration, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)(kEquilSmemDoubles * sizeof(double)));
+  const long long stage = count <= kEquilSmemDoubles ? count : 0;
+  // one launch per distinct precision (the kernel takes one); usually they are equal
+  for (int i = 0; i < n; ++i) {
+    bool done = false;
+    for (int j = 0; j < i; ++j) done = done || abs_precision[j] == abs_precision[i];
+    if (done) continue;
+    // jobs i.. with this precision are contiguous in the common case; launch per job otherwise
+    for (int j = i; j < n; ++j)
+      if (abs_precision[j] == abs_precision[i]) {
+        k_series_equilibration<<<1, kEquilThreads, (size_t)stage * sizeof(double), c->stream>>>(
+            d->eq + j, 1, abs_precision[i], d->is_eq + j, d->n_eq + j, stage);
+        ++c->launches;
+      }
+  }
+  k_make_tail_jobs<<<1, 32, 0, c->stream>>>(d->eq, n, d->is_eq, d->n_eq, d->st, &d->n_stats);
+  k_series_stats<<<n, 256, 0, c->stream>>>(d->st, z_confidence(confidence), d->out4, d->k_star);
+  c->launches += 2;
+  CU(c, cudaGetLastError());
+  CU(c, cudaMemcpyAsync(&h, d, sizeof(Host), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  scratch_free(d, c->stream);
+  for (int i = 0; i < n; ++i) {
+    if (is_equilibrated) is_equilibrated[i] = h.is_eq[i];
+    if (n_equil) n_equil[i] = h.n_eq[i];
+    if (mean) mean[i] = h.out4[4 * i];
+    if (calculated_precision) calculated_precision[i] = h.out4[4 * i + 3];
+  }
+  if (n_stats) *n_stats = h.n_stats;
+  return device_error_check(c);
+}
+
 static int device_ok(int device) {
   int ndev = 0;
   int rc = cmg_device_count(&ndev);
@@ -2257,6 +2323,76 @@ int cmg_conv_bijk_to_l(int device, const int64_t *n3, int64_t n_basis, const int
   CU(c, cudaMemcpy(l_out, dl, 8 * (size_t)count, cudaMemcpyDeviceToHost));
   cudaFree(dl);
   cudaFree(db);
+  return CMG_OK;
+}
+
+static int make_conv_general(const int64_t *T9, int64_t n_basis, ConvGeneral *P) {
+  if (!T9 || n_basis < 1) return fail(nullptr, CMG_EINVAL, "bad argument");
+  try {
+    casm_monte_b200::SiteIndexConverter f(casm_monte_b200::Mat3l::from_row_major(T9), n_basis);
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) {
+        P->T[3 * r + c] = f.T.a[r][c];
+        P->adjT[3 * r + c] = f.adjT.a[r][c];
+        P->U[3 * r + c] = f.U.a[r][c];
+        P->Uinv[3 * r + c] = f.Uinv.a[r][c];
+      }
+    P->detT = f.detT;
+    for (int d = 0; d < 3; ++d) P->s[d] = f.s[d];
+    P->n_unitcells = f.n_unitcells;
+  } catch (std::exception const &e) {
+    return fail(nullptr, CMG_EINVAL, e.what());
+  }
+  return CMG_OK;
+}
+
+int cmg_conv_general_l_to_bijk(int device, const int64_t *T9, int64_t n_basis, const int64_t *l,
+                               int64_t count, int64_t *bijk_out) {
+  int rc = device_ok(device);
+  if (rc) return rc;
+  ConvGeneral P;
+  rc = make_conv_general(T9, n_basis, &P);
+  if (rc) return rc;
+  if (!l || !bijk_out || count < 0) return fail(nullptr, CMG_EINVAL, "bad argument");
+  if (count == 0) return CMG_OK;
+  const long long total = P.n_unitcells * n_basis;
+  for (int64_t i = 0; i < count; ++i)
+    if (l[i] < 0 || l[i] >= total) return fail(nullptr, CMG_EINVAL, "linear index out of range");
+  cmg_context *c = nullptr;
+  long long *dl = nullptr, *db = nullptr;
+  CU(c, scratch_alloc(&dl, 8 * (size_t)count, 0));
+  CU(c, scratch_alloc(&db, 32 * (size_t)count, 0));
+  CU(c, cudaMemcpy(dl, l, 8 * (size_t)count, cudaMemcpyHostToDevice));
+  k_conv_general_l_to_bijk<<<nblocks(count, 256), 256>>>(P, dl, count, db);
+  CU(c, cudaGetLastError());
+  CU(c, cudaMemcpy(bijk_out, db, 32 * (size_t)count, cudaMemcpyDeviceToHost));
+  scratch_free(dl, 0);
+  scratch_free(db, 0);
+  return CMG_OK;
+}
+
+int cmg_conv_general_bijk_to_l(int device, const int64_t *T9, int64_t n_basis, const int64_t *bijk,
+                               int64_t count, int64_t *l_out) {
+  int rc = device_ok(device);
+  if (rc) return rc;
+  ConvGeneral P;
+  rc = make_conv_general(T9, n_basis, &P);
+  if (rc) return rc;
+  if (!bijk || !l_out || count < 0) return fail(nullptr, CMG_EINVAL, "bad argument");
+  if (count == 0) return CMG_OK;
+  for (int64_t i = 0; i < count; ++i)
+    if (bijk[4 * i] < 0 || bijk[4 * i] >= n_basis)
+      return fail(nullptr, CMG_EINVAL, "sublattice index out of range");
+  cmg_context *c = nullptr;
+  long long *dl = nullptr, *db = nullptr;
+  CU(c, scratch_alloc(&dl, 8 * (size_t)count, 0));
+  CU(c, scratch_alloc(&db, 32 * (size_t)count, 0));
+  CU(c, cudaMemcpy(db, bijk, 32 * (size_t)count, cudaMemcpyHostToDevice));
+  k_conv_general_bijk_to_l<<<nblocks(count, 256), 256>>>(P, db, count, dl);
+  CU(c, cudaGetLastError());
+  CU(c, cudaMemcpy(l_out, dl, 8 * (size_t)count, cudaMemcpyDeviceToHost));
+  scratch_free(dl, 0);
+  scratch_free(db, 0);
   return CMG_OK;
 }
 

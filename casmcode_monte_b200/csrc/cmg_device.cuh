@@ -2461,20 +2461,26 @@ __global__ void k_apply_weight_factor(const double *__restrict__ x, const double
   y[i] = __dmul_rn(x[i], __dmul_rn(*factor, w[i]));
 }
 
-// Equilibration check, sequential semantics kept exactly
-// (src/casm/monte/checks/EquilibrationCheck.cc:50-117).  One CTA per series:
-// all threads stage the series into shared memory (when it fits) and decide
-// "all samples equal" in parallel; thread 0 then walks the reference's running
-// sums, which are a floating-point recurrence, from shared memory -- a lone
-// thread reading global memory paid a full memory latency per sample (1.7 ms
-// for 10^4 samples, now ~50 us).
+// Equilibration check (src/casm/monte/checks/EquilibrationCheck.cc:50-117).  One CTA
+// per series.  The series is staged into shared memory when it fits, "all samples
+// equal" is decided in parallel and the two initial partition sums are block
+// reductions (the reference takes them with Eigen's .sum(), whose order is not a
+// sequential one either).  The scan that follows is a floating-point recurrence
+// on the running sums (:93-103) and keeps the reference's order: thread 0 walks it
+// in chunks, recording (sum1, sum2) before every step, and the other threads
+// evaluate the loop condition of the recorded steps -- two double divisions each,
+// which dominated when one thread did everything (1.7 ms per check of 10^4 samples
+// that never equilibrate) -- and find the step at which the reference's loop stops.
 constexpr int kEquilThreads = 256;
+constexpr int kEquilChunk = 512;
 __global__ void __launch_bounds__(kEquilThreads) k_series_equilibration(const SeriesJob *jobs,
                                                                         int n_jobs, double prec,
                                                                         int *is_eq, long long *n_eq,
                                                                         long long smem_doubles) {
   extern __shared__ __align__(16) double eq_smem[];
   __shared__ int s_differs;
+  __shared__ int s_stop;  // first step of the chunk at which the loop condition is false
+  __shared__ double s_sum1[kEquilChunk], s_sum2[kEquilChunk], s_red[8];
   const int jb = blockIdx.x;
   if (jb >= n_jobs) return;
   const double *xg = jobs[jb].x;
@@ -2499,34 +2505,83 @@ __global__ void __launch_bounds__(kEquilThreads) k_series_equilibration(const Se
   }
   if (differs) s_differs = 1;
   __syncthreads();
-  if (threadIdx.x != 0) return;
   if (!s_differs) {  // all samples (approximately) equal
-    is_eq[jb] = 1;
-    n_eq[jb] = 0;
+    if (threadIdx.x == 0) {
+      is_eq[jb] = 1;
+      n_eq[jb] = 0;
+    }
     return;
   }
   const double *x = staged ? eq_smem : xg;
-  bool is_even = ((N % 2) == 0);
-  long long start1 = 0, start2 = is_even ? N / 2 : (N / 2) + 1;
-  double sum1 = 0.0, sum2 = 0.0;
-#pragma unroll 8
-  for (long long i = 0; i < start2; ++i) sum1 = __dadd_rn(sum1, x[i]);
-#pragma unroll 8
-  for (long long i = start2; i < N; ++i) sum2 = __dadd_rn(sum2, x[i]);
-  while (fabs(__dsub_rn(__ddiv_rn(sum1, (double)(start2 - start1)),
-                        __ddiv_rn(sum2, (double)(N - start2)))) > prec &&
-         start1 < N - 2) {
-    if (is_even) {
-      sum1 = __dsub_rn(sum1, x[start1]);
-      sum1 = __dadd_rn(sum1, x[start2]);
-      sum2 = __dsub_rn(sum2, x[start2]);
-      start2++;
-    } else {
-      sum1 = __dsub_rn(sum1, x[start1]);
+  const bool even0 = ((N % 2) == 0);
+  const long long start2_0 = even0 ? N / 2 : (N / 2) + 1;
+  double p = 0.0;
+  for (long long i = threadIdx.x; i < start2_0; i += kEquilThreads) p += x[i];
+  double sum1 = block_sum_256(p, s_red);
+  p = 0.0;
+  for (long long i = start2_0 + threadIdx.x; i < N; i += kEquilThreads) p += x[i];
+  double sum2 = block_sum_256(p, s_red);
+
+  // state before the first step of the chunk (kept by every thread; thread 0 advances the sums)
+  long long start1 = 0, start2 = start2_0;
+  const bool is_even = even0;  // parity of the chunk's first step (chunks hold an even number of steps)
+  __shared__ double s_end1, s_end2;
+  for (;;) {
+    if (threadIdx.x == 0) {
+      s_stop = kEquilChunk;
+      double a = sum1, b = sum2;
+      long long t1 = start1, t2 = start2;
+      bool ev = is_even;
+      for (int k = 0; k < kEquilChunk && t1 < N - 2; ++k) {  // EquilibrationCheck.cc:93-103
+        s_sum1[k] = a;
+        s_sum2[k] = b;
+        a = __dsub_rn(a, x[t1]);
+        if (ev) {
+          a = __dadd_rn(a, x[t2]);
+          b = __dsub_rn(b, x[t2]);
+          t2++;
+        }
+        t1++;
+        ev = !ev;
+      }
+      s_end1 = a;
+      s_end2 = b;
     }
-    start1++;
-    is_even = !is_even;
+    __syncthreads();
+    // the loop condition (:91-92) of the chunk's steps, in parallel
+    int first = kEquilChunk;
+    for (int k = threadIdx.x; k < kEquilChunk; k += kEquilThreads) {
+      const long long s1 = start1 + k;
+      // start2 has advanced once per even step taken so far
+      const long long s2 = start2 + (is_even ? (k + 1) / 2 : k / 2);
+      bool go = s1 < N - 2;
+      if (go)
+        go = fabs(__dsub_rn(__ddiv_rn(s_sum1[k], (double)(s2 - s1)), __ddiv_rn(s_sum2[k], (double)(N - s2)))) > prec;
+      if (!go) {
+        first = k;
+        break;
+      }
+    }
+    if (first < kEquilChunk) atomicMin(&s_stop, first);
+    __syncthreads();
+    const int stop = s_stop;
+    if (stop < kEquilChunk) {
+      // the reference's loop ends before step `stop`; its sums are the recorded ones
+      // (or, when the scan ran out of samples, the state after the last step taken)
+      const bool recorded = start1 + stop < N - 2;
+      sum1 = recorded ? s_sum1[stop] : s_end1;
+      sum2 = recorded ? s_sum2[stop] : s_end2;
+      start2 += is_even ? (stop + 1) / 2 : stop / 2;
+      start1 += stop;
+      break;
+    }
+    sum1 = s_end1;
+    sum2 = s_end2;
+    start2 += kEquilChunk / 2;
+    start1 += kEquilChunk;
+    __syncthreads();  // the buffers are rewritten by the next chunk
   }
+  if (threadIdx.x != 0) return;
   const double mean_tot = __ddiv_rn(__dadd_rn(sum1, sum2), (double)(N - start1));
   if (x[start1] < mean_tot) {
     while (x[start1] < mean_tot && start1 < N - 1) start1++;
@@ -2535,6 +2590,31 @@ __global__ void __launch_bounds__(kEquilThreads) k_series_equilibration(const Se
   }
   is_eq[jb] = (start1 < N - 1) ? 1 : 0;
   n_eq[jb] = start1;
+}
+
+// One completion check on the device-resident series without a host round trip in
+// the middle (CompletionCheck::_check_convergence, include/casm/monte/checks/
+// CompletionCheck.hh:353-376): after k_series_equilibration has filled is_eq / n_eq
+// for the requested components (in the caller's order), this builds the jobs of
+// the statistics pass: if every component up to the first failure equilibrated,
+// tail(count - max n_eq) of each series (ConvergenceCheck.hh:139-184); otherwise
+// empty jobs.
+__global__ void k_make_tail_jobs(const SeriesJob *eq_jobs, int n_jobs, const int *is_eq,
+                                 const long long *n_eq, SeriesJob *stat_jobs, long long *n_stats) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  bool all = true;
+  long long first = 0;
+  for (int i = 0; i < n_jobs; ++i) {
+    all = all && is_eq[i] != 0;
+    if (n_eq[i] > first) first = n_eq[i];
+  }
+  const long long count = n_jobs > 0 ? eq_jobs[0].n : 0;
+  const bool ok = all && first < count;
+  for (int i = 0; i < n_jobs; ++i) {
+    stat_jobs[i].x = eq_jobs[i].x + (ok ? first : 0);
+    stat_jobs[i].n = ok ? count - first : 0;
+  }
+  *n_stats = ok ? count - first : 0;
 }
 
 // ---------------------------------------------------------------------------
@@ -2567,6 +2647,44 @@ __global__ void k_conv_bijk_to_l(long long n0, long long n1, long long n2,
   const long long vol = n0 * n1 * n2;
   l[t] = bijk[4 * t] * vol + floor_mod(bijk[4 * t + 1], n0) +
          n0 * (floor_mod(bijk[4 * t + 2], n1) + n1 * floor_mod(bijk[4 * t + 3], n2));
+}
+
+// General integer transformation matrix (include/casm_monte_b200/snf.hh restates
+// xtal::UnitCellCoordIndexConverter): unit cell of index ix = U * (ix % s0,
+// (ix / s0) % s1, ix / (s0 s1)) brought within the supercell; inverse through
+// U^-1 and mod s.  Matrices row-major.
+struct ConvGeneral {
+  long long T[9], adjT[9], U[9], Uinv[9];
+  long long detT, s[3], n_unitcells;
+};
+__device__ __forceinline__ long long floor_div_ll(long long x, long long y) {
+  long long q = x / y, r = x % y;
+  return (r != 0 && ((r < 0) != (y < 0))) ? q - 1 : q;
+}
+__global__ void k_conv_general_l_to_bijk(ConvGeneral P, const long long *__restrict__ l, long long count,
+                                         long long *bijk) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  const long long v = l[t];
+  const long long ix = v % P.n_unitcells;
+  const long long mnp[3] = {ix % P.s[0], (ix / P.s[0]) % P.s[1], ix / (P.s[0] * P.s[1])};
+  long long ijk[3], f[3];
+  for (int r = 0; r < 3; ++r) ijk[r] = P.U[3 * r] * mnp[0] + P.U[3 * r + 1] * mnp[1] + P.U[3 * r + 2] * mnp[2];
+  for (int r = 0; r < 3; ++r)
+    f[r] = floor_div_ll(P.adjT[3 * r] * ijk[0] + P.adjT[3 * r + 1] * ijk[1] + P.adjT[3 * r + 2] * ijk[2], P.detT);
+  bijk[4 * t] = v / P.n_unitcells;
+  for (int r = 0; r < 3; ++r)
+    bijk[4 * t + 1 + r] = ijk[r] - (P.T[3 * r] * f[0] + P.T[3 * r + 1] * f[1] + P.T[3 * r + 2] * f[2]);
+}
+__global__ void k_conv_general_bijk_to_l(ConvGeneral P, const long long *__restrict__ bijk, long long count,
+                                         long long *l) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  const long long *in = bijk + 4 * t;
+  long long mnp[3];
+  for (int r = 0; r < 3; ++r)
+    mnp[r] = floor_mod(P.Uinv[3 * r] * in[1] + P.Uinv[3 * r + 1] * in[2] + P.Uinv[3 * r + 2] * in[3], P.s[r]);
+  l[t] = in[0] * P.n_unitcells + mnp[0] + P.s[0] * (mnp[1] + P.s[1] * mnp[2]);
 }
 
 }  // namespace cmg

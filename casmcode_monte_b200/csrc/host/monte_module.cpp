@@ -381,19 +381,122 @@ PYBIND11_MODULE(_monte_b200, m) {
       .def_readwrite("linear_site_index", &OccEvent::linear_site_index)
       .def_readwrite("new_occ", &OccEvent::new_occ);
 
+  // events.Conversions (python/src/monte_events.cpp:85-430).  libcasm.xtal is absent, so
+  // the prim is given as arrays: occ_dof (names per sublattice), the 3 x 3
+  // transformation matrix, and optionally the lattice column-vector matrix and the
+  // fractional basis coordinates as COLUMNS (shape 3 x n_basis, like xtal.Prim).
+  auto to_matrix = [](py::object o) {
+    auto a = py::array_t<int64_t, py::array::c_style | py::array::forcecast>::ensure(o);
+    if (!a || a.ndim() != 2 || a.shape(0) != 3 || a.shape(1) != 3)
+      throw std::runtime_error("Conversions: transformation matrix must be 3 x 3 integers");
+    Conversions::matrix_type t;
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) t[3 * r + c] = static_cast<long>(a.at(r, c));
+    return t;
+  };
+  auto to_prim = [](std::vector<std::vector<std::string>> occ_dof, py::object lattice, py::object frac) {
+    ConversionsPrim p;
+    p.occ_dof = std::move(occ_dof);
+    if (!lattice.is_none()) {
+      auto a = py::array_t<double, py::array::c_style | py::array::forcecast>::ensure(lattice);
+      if (!a || a.ndim() != 2 || a.shape(0) != 3 || a.shape(1) != 3)
+        throw std::runtime_error("Conversions: lattice column vector matrix must be 3 x 3");
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) p.lat_column_mat[3 * r + c] = a.at(r, c);
+    }
+    if (!frac.is_none()) {
+      auto a = py::array_t<double, py::array::c_style | py::array::forcecast>::ensure(frac);
+      if (!a || a.ndim() != 2 || a.shape(0) != 3 || static_cast<size_t>(a.shape(1)) != p.occ_dof.size())
+        throw std::runtime_error("Conversions: coordinate_frac must have shape (3, n_basis)");
+      for (py::ssize_t b = 0; b < a.shape(1); ++b) p.basis_frac.push_back({{a.at(0, b), a.at(1, b), a.at(2, b)}});
+    }
+    return p;
+  };
+  auto bijk_arg = [](std::vector<long> const &bijk) {
+    if (bijk.size() != 4) throw std::runtime_error("bijk must have 4 entries");
+    return bijk;
+  };
   py::class_<Conversions>(m, "Conversions")
       .def(py::init<std::vector<long>, long, int>(), py::arg("supercell_extents"),
            py::arg("n_basis") = 1, py::arg("device") = 0)
+      .def(py::init([to_matrix, to_prim](std::vector<std::vector<std::string>> occ_dof, py::object T,
+                                         py::object lattice, py::object frac, int device) {
+             return Conversions(to_prim(std::move(occ_dof), lattice, frac), to_matrix(T), device);
+           }),
+           py::arg("occ_dof"), py::arg("transformation_matrix_to_super"),
+           py::arg("lattice_column_vector_matrix") = py::none(), py::arg("coordinate_frac") = py::none(),
+           py::arg("device") = 0)
+      .def_static(
+          "make_with_custom_asym",
+          [to_matrix, to_prim](std::vector<std::vector<std::string>> occ_dof, py::object T, std::vector<Index> b_to_asym,
+                               py::object lattice, py::object frac, int device) {
+            return Conversions(to_prim(std::move(occ_dof), lattice, frac), to_matrix(T), b_to_asym, device);
+          },
+          py::arg("occ_dof"), py::arg("transformation_matrix_to_super"), py::arg("b_to_asym"),
+          py::arg("lattice_column_vector_matrix") = py::none(), py::arg("coordinate_frac") = py::none(),
+          py::arg("device") = 0)
+      .def_static(
+          "make_with_custom_unitcell",
+          [to_matrix, to_prim](std::vector<std::vector<std::string>> occ_dof, std::vector<std::string> species_list,
+                               py::object T, py::object unit_T, std::vector<Index> unitl_to_asym, py::object lattice,
+                               py::object frac, int device) {
+            return Conversions(to_prim(std::move(occ_dof), lattice, frac), species_list, to_matrix(T),
+                               to_matrix(unit_T), unitl_to_asym, device);
+          },
+          py::arg("occ_dof"), py::arg("species_list"), py::arg("transformation_matrix_to_super"),
+          py::arg("unit_transformation_matrix_to_super"), py::arg("unitl_to_asym"),
+          py::arg("lattice_column_vector_matrix") = py::none(), py::arg("coordinate_frac") = py::none(),
+          py::arg("device") = 0)
+      .def("lat_column_mat",
+           [](Conversions const &c) {
+             py::array_t<double> a({3, 3});
+             auto m = c.lat_column_mat();
+             std::copy(m.begin(), m.end(), a.mutable_data());
+             return a;
+           })
       .def("l_size", &Conversions::l_size)
       .def("l_to_b", &Conversions::l_to_b)
       .def("l_to_ijk", &Conversions::l_to_ijk)
       .def("l_to_bijk", [](Conversions const &c, long l) { return c.l_to_bijk(l); })
-      .def("bijk_to_l", [](Conversions const &c, std::vector<long> bijk) {
-        if (bijk.size() != 4) throw std::runtime_error("bijk must have 4 entries");
-        return c.bijk_to_l(bijk[0], bijk[1], bijk[2], bijk[3]);
-      })
+      .def("l_to_unitl", &Conversions::l_to_unitl)
+      .def("l_to_asym", &Conversions::l_to_asym)
+      .def("l_to_cart", &Conversions::l_to_cart)
+      .def("l_to_frac", &Conversions::l_to_frac)
+      .def("l_to_basis_cart", &Conversions::l_to_basis_cart)
+      .def("l_to_basis_frac", &Conversions::l_to_basis_frac)
+      .def("bijk_to_l", [bijk_arg](Conversions const &c, std::vector<long> bijk) { return c.bijk_to_l(bijk_arg(bijk)); })
+      .def("bijk_to_unitl", [bijk_arg](Conversions const &c, std::vector<long> bijk) { return c.bijk_to_unitl(bijk_arg(bijk)); })
+      .def("bijk_to_asym", [bijk_arg](Conversions const &c, std::vector<long> bijk) { return c.bijk_to_asym(bijk_arg(bijk)); })
+      .def("unitl_size", &Conversions::unitl_size)
+      .def("unitl_to_b", &Conversions::unitl_to_b)
+      .def("unitl_to_bijk", &Conversions::unitl_to_bijk)
+      .def("unitl_to_asym", &Conversions::unitl_to_asym)
+      .def("asym_size", &Conversions::asym_size)
+      .def("asym_to_b", [](Conversions const &c, Index asym) { return c.asym_to_b(asym); })
+      .def("asym_to_unitl", [](Conversions const &c, Index asym) { return c.asym_to_unitl(asym); })
+      .def("transformation_matrix_to_super",
+           [](Conversions const &c) {
+             py::array_t<int64_t> a({3, 3});
+             for (int i = 0; i < 9; ++i) a.mutable_data()[i] = c.transformation_matrix_to_super()[i];
+             return a;
+           })
+      .def("unit_transformation_matrix_to_super",
+           [](Conversions const &c) {
+             py::array_t<int64_t> a({3, 3});
+             for (int i = 0; i < 9; ++i) a.mutable_data()[i] = c.unit_transformation_matrix_to_super()[i];
+             return a;
+           })
+      .def("occ_size", &Conversions::occ_size)
+      .def("occ_to_species_index", [](Conversions const &c, Index asym, Index occ) { return c.species_index(asym, occ); })
+      .def("species_to_occ_index", [](Conversions const &c, Index asym, Index sp) { return c.occ_index(asym, sp); })
+      .def("species_allowed", &Conversions::species_allowed)
+      .def("species_size", &Conversions::species_size)
+      .def("species_name_to_index", [](Conversions const &c, std::string name) { return c.species_index(name); })
+      .def("species_index_to_name", [](Conversions const &c, Index sp) { return c.species_name(sp); })
+      .def("species_list", [](Conversions const &c) { return c.species_list(); })
+      .def("species_index_to_atoms_size", &Conversions::components_size)
       .def("l_to_bijk_batch", [](Conversions const &c, std::vector<int64_t> l) {
-        auto out = c.l_to_bijk(l);
+        auto out = c.l_to_bijk_batch(l);
         py::array_t<int64_t> a({static_cast<py::ssize_t>(l.size()), static_cast<py::ssize_t>(4)});
         std::copy(out.begin(), out.end(), a.mutable_data());
         return a;
@@ -401,7 +504,7 @@ PYBIND11_MODULE(_monte_b200, m) {
       .def("bijk_to_l_batch", [](Conversions const &c,
                                  py::array_t<int64_t, py::array::c_style | py::array::forcecast> bijk) {
         std::vector<int64_t> in(bijk.data(), bijk.data() + bijk.size());
-        return c.bijk_to_l(in);
+        return c.bijk_to_l_batch(in);
       });
 
   // --------------------------------------------------------------- ising_cpp

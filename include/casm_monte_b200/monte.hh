@@ -22,6 +22,7 @@
 #define CASM_MONTE_B200_MONTE_HH
 
 #include <algorithm>
+#include <array>
 #include <chrono>
 #include <cmath>
 #include <cstdint>
@@ -33,12 +34,14 @@
 #include <memory>
 #include <optional>
 #include <random>
+#include <set>
 #include <sstream>
 #include <stdexcept>
 #include <string>
 #include <vector>
 
 #include "../casm_monte_gpu.h"
+#include "snf.hh"
 
 namespace casm_monte_b200 {
 
@@ -936,6 +939,19 @@ struct CompletionCheckResults {
   }
 };
 
+/// This implementation only: the scheduled checks of a CompletionCheck can be
+/// evaluated on the device-resident sample series (one call per check, no copy of
+/// the series) instead of on the host samplers.  `check` fills, for the requested
+/// components in map order, the equilibration results and -- if all of them
+/// equilibrated -- the statistics of the last n_stats samples.
+struct DeviceSeriesCheck {
+  std::function<CountType()> n_samples;
+  std::function<void(RequestedPrecisionMap const &, CountType count,
+                     std::vector<IndividualEquilibrationCheckResult> &eq, CountType &n_stats,
+                     std::vector<BasicStatistics> &stats)>
+      check;
+};
+
 /// CompletionCheck.hh:175-376
 class CompletionCheck {
  public:
@@ -972,6 +988,7 @@ class CompletionCheck {
   }
   CompletionCheckResults const &results() const { return m_results; }
   Index n_checks() const { return m_n_checks; }
+  void set_device_series(std::shared_ptr<DeviceSeriesCheck> d) { m_device = std::move(d); }
 
   /// Pass-granular drivers: the pass count at which is_complete could next
   /// change anything (a cutoff on count, or the sample count reaching the next
@@ -1010,7 +1027,7 @@ class CompletionCheck {
  private:
   bool _is_complete(SamplerMap const &samplers, Sampler const &sample_weight,
                     std::optional<CountType> count, std::optional<TimeType> time, LogClock &log) {
-    CountType n_samples = get_n_samples(samplers);
+    CountType n_samples = m_device ? m_device->n_samples() : get_n_samples(samplers);
     TimeType clocktime = m_last_clocktime;
     if (n_samples != m_last_n_samples) {
       clocktime = log.time_s();
@@ -1043,6 +1060,10 @@ class CompletionCheck {
                           CountType n_samples) {
     if (!m_params.requested_precision.size()) return;
     m_results.n_samples_at_convergence_check = n_samples;
+    if (m_device) {
+      _check_convergence_on_device(n_samples);
+      return;
+    }
     m_results.equilibration_check_results =
         equilibration_check(m_params.equilibration_check_f, m_params.requested_precision, samplers,
                             sample_weight, false);
@@ -1055,8 +1076,44 @@ class CompletionCheck {
       m_results.convergence_check_results = ConvergenceCheckResults();
     }
   }
+  /// Same results as the host path (equilibration_check with check_all = false,
+  /// EquilibrationCheck.cc:203-224, then convergence_check, ConvergenceCheck.hh:139-184),
+  /// from one device call.
+  void _check_convergence_on_device(CountType n_samples) {
+    std::vector<IndividualEquilibrationCheckResult> eq;
+    std::vector<BasicStatistics> stats;
+    CountType n_stats = 0;
+    m_device->check(m_params.requested_precision, n_samples, eq, n_stats, stats);
+    EquilibrationCheckResults er;
+    er.all_equilibrated = true;
+    size_t i = 0;
+    for (auto const &p : m_params.requested_precision) {
+      IndividualEquilibrationCheckResult const &current = eq.at(i++);
+      er.N_samples_for_all_to_equilibrate =
+          std::max(er.N_samples_for_all_to_equilibrate, current.N_samples_for_equilibration);
+      er.all_equilibrated &= current.is_equilibrated;
+      er.individual_results.emplace(p.first, current);
+      if (!er.all_equilibrated) break;
+    }
+    m_results.equilibration_check_results = er;
+    ConvergenceCheckResults cr;
+    if (er.all_equilibrated && er.N_samples_for_all_to_equilibrate < n_samples) {
+      cr.N_samples_for_statistics = n_samples - er.N_samples_for_all_to_equilibrate;
+      if (cr.N_samples_for_statistics != n_stats)
+        throw std::runtime_error("Error in CompletionCheck: device statistics window mismatch");
+      cr.all_converged = true;
+      i = 0;
+      for (auto const &p : m_params.requested_precision) {
+        IndividualConvergenceCheckResult current = convergence_check(stats.at(i++), p.second);
+        cr.all_converged &= current.is_converged;
+        cr.individual_results.emplace(p.first, current);
+      }
+    }
+    m_results.convergence_check_results = cr;
+  }
   CompletionCheckParams m_params;
   CompletionCheckResults m_results;
+  std::shared_ptr<DeviceSeriesCheck> m_device;
   Index m_n_checks = 0;
   Index m_n_begin_linear = 0;
   Index m_last_n_samples = 0;
@@ -1450,6 +1507,66 @@ class SemiGrandCanonicalCalculator {
     const bool host_state_each_sample = !all_builtin || static_cast<bool>(json_sample_hook);
     const bool device_samples = all_builtin;
 
+    // Can the scheduled checks run on the device-resident series?  Yes if every
+    // requested component is one of the built-in observables with an absolute
+    // precision only, and the check functions are this library's defaults.
+    bool device_checks = device_samples && !host_state_each_sample;
+    std::vector<int> check_quantity;
+    std::vector<double> check_abs;
+    double check_confidence = 0.95;
+    if (device_checks) {
+      typedef IndividualEquilibrationCheckResult (*eq_fn)(std::vector<double> const &,
+                                                          std::vector<double> const &, RequestedPrecision);
+      eq_fn const *eq_target = completion_check_params.equilibration_check_f.target<eq_fn>();
+      BasicStatisticsCalculator const *calc =
+          completion_check_params.calc_statistics_f.target<BasicStatisticsCalculator>();
+      device_checks = eq_target && *eq_target == &default_equilibration_check && calc != nullptr &&
+                      completion_check_params.requested_precision.size() <= 3;
+      if (calc) check_confidence = calc->confidence;
+      for (auto const &p : completion_check_params.requested_precision) {
+        auto it = data->sampling_functions.find(p.first.sampler_name);
+        if (it == data->sampling_functions.end() || p.first.component_index != 0 ||
+            !p.second.abs_convergence_is_required || p.second.rel_convergence_is_required) {
+          device_checks = false;
+          break;
+        }
+        check_quantity.push_back(it->second.builtin);
+        check_abs.push_back(p.second.abs_precision);
+      }
+    }
+    if (device_checks) {
+      auto hook = std::make_shared<DeviceSeriesCheck>();
+      hook->n_samples = [ctx]() {
+        int64_t n = 0;
+        cmg_check(cmg_n_samples(ctx, &n), ctx);
+        return static_cast<CountType>(n);
+      };
+      hook->check = [ctx, check_quantity, check_abs, check_confidence](
+                        RequestedPrecisionMap const &req, CountType count,
+                        std::vector<IndividualEquilibrationCheckResult> &eq, CountType &n_stats,
+                        std::vector<BasicStatistics> &stats) {
+        const int n = static_cast<int>(req.size());
+        if (n == 0) return;
+        int is_eq[3] = {0, 0, 0};
+        int64_t n_eq[3] = {0, 0, 0}, ns = 0;
+        double mean[3] = {0, 0, 0}, prec[3] = {0, 0, 0};
+        cmg_check(cmg_series_check(ctx, 0, n, check_quantity.data(), check_abs.data(),
+                                   static_cast<int64_t>(count), check_confidence, is_eq, n_eq, &ns,
+                                   mean, prec),
+                  ctx);
+        eq.resize(n);
+        stats.resize(n);
+        for (int i = 0; i < n; ++i) {
+          eq[i].is_equilibrated = is_eq[i] != 0;
+          eq[i].N_samples_for_equilibration = static_cast<CountType>(n_eq[i]);
+          stats[i].mean = mean[i];
+          stats[i].calculated_precision = prec[i];
+        }
+        n_stats = static_cast<CountType>(ns);
+      };
+      data->completion_check.set_device_series(hook);
+    }
+
     CountType n_pass_dev = 0;       // passes done on the device
     CountType n_fetched = 0;        // device samples already appended to the host samplers
     auto fetch_device_samples = [&]() {
@@ -1473,6 +1590,13 @@ class SemiGrandCanonicalCalculator {
       data->n_reject = nr;
     };
 
+    auto current_n_samples = [&]() -> CountType {
+      if (!device_checks) return get_n_samples(data->samplers);
+      int64_t n = 0;
+      dev.check(cmg_n_samples(ctx, &n));
+      return static_cast<CountType>(n);
+    };
+
     // ### main loop at pass granularity: is_complete is consulted
     // at every pass boundary at which its answer could change, and re-consulted
     // while it is still catching up on scheduled checks.
@@ -1491,11 +1615,11 @@ class SemiGrandCanonicalCalculator {
         // stop at the next sample (or earlier at a count cutoff)
         target = (n_pass_dev / sample_period + 1) * sample_period;
         CountType nd = data->completion_check.next_decision_pass(
-            n_pass_dev, get_n_samples(data->samplers), sample_period);
+            n_pass_dev, current_n_samples(), sample_period);
         target = std::min(target, nd);
       } else {
         target = data->completion_check.next_decision_pass(
-            n_pass_dev, get_n_samples(data->samplers), sample_period);
+            n_pass_dev, current_n_samples(), sample_period);
       }
       CountType n_run = std::max<CountType>(1, target - n_pass_dev);
       dev.check(cmg_run_passes(ctx, n_run, mode, device_samples ? sample_period : 0));
@@ -1504,7 +1628,8 @@ class SemiGrandCanonicalCalculator {
       data->n_pass = n_pass_dev;
 
       const bool sample_due = (n_pass_dev % sample_period) == 0;
-      if (device_samples) fetch_device_samples();
+      // with the checks on the device series the samplers are filled once, at the end
+      if (device_samples && !device_checks) fetch_device_samples();
       if (sample_due && host_state_each_sample) {
         refresh_counters();
         config.pull();
@@ -1518,9 +1643,12 @@ class SemiGrandCanonicalCalculator {
       if (sample_due && write_status_f && method_log->log_frequency.has_value() &&
           method_log->log.lap_time() >= method_log->log_frequency.value()) {
         refresh_counters();
+        fetch_device_samples();
         write_status_f(*this, *method_log);
       }
     }
+    fetch_device_samples();
+    data->completion_check.set_device_series(nullptr);
 
     // ### finish: counters, final occupation visible in the caller's state,
     // engine advanced exactly as the reference would leave it (serial mode)
@@ -1682,48 +1810,272 @@ inline StateSamplingFunction make_potential_energy_f(
 }
 
 // ---------------------------------------------------------------------------
-// Conversions, index arithmetic for a diagonal transformation matrix
-// (include/casm/monte/Conversions.hh:43-135; src/casm/monte/Conversions.cc:181-229)
+// Conversions (include/casm/monte/Conversions.hh:43-135; src/casm/monte/Conversions.cc)
+//
+// The reference builds it from an xtal::BasicStructure; libcasm-xtal is absent
+// here, so the primitive cell is given as plain arrays (ConversionsPrim): the
+// lattice column matrix, the fractional basis coordinates and the occupant names
+// of every sublattice.  Everything the reference computes from those is mirrored:
+// l / b / ijk / bijk / unitl / asym conversions for ANY integer transformation
+// matrix (snf.hh), Cartesian / fractional site coordinates, and the occ_index <->
+// species_index tables (Conversions.cc:147-172, :296-321).  What needs the prim's
+// factor group (the default asymmetric unit, Conversions.cc:14-52) is replaced by
+// its occupant-order part: sublattices with identical occupant lists share an
+// orbit unless b_to_asym / unitl_to_asym is given (the reference's
+// make_with_custom_asym / make_with_custom_unitcell constructors).
+// Scalar calls are evaluated on the host; the batched forms run on the device.
 // ---------------------------------------------------------------------------
+struct ConversionsPrim {
+  /// lat_column_mat, row-major (a, b, c are the COLUMNS); identity by default
+  std::array<double, 9> lat_column_mat{{1, 0, 0, 0, 1, 0, 0, 0, 1}};
+  /// fractional coordinates of the basis sites
+  std::vector<std::array<double, 3>> basis_frac;
+  /// occupant names per sublattice, in occupation-index order (xtal::Prim occ_dof)
+  std::vector<std::vector<std::string>> occ_dof;
+};
+
 class Conversions {
  public:
+  typedef std::array<long, 9> matrix_type;  // row-major 3 x 3
+
+  /// Conversions.cc:63-68 (asymmetric unit from the occupant lists, see above)
+  Conversions(ConversionsPrim const &prim, matrix_type const &transformation_matrix_to_super, int device = 0)
+      : Conversions(prim, default_species_list(prim), transformation_matrix_to_super,
+                    matrix_type{{1, 0, 0, 0, 1, 0, 0, 0, 1}},
+                    default_b_to_asym(prim, default_species_list(prim)), device) {}
+  /// Conversions.cc:86-92: user specified asymmetric unit with reduced symmetry
+  Conversions(ConversionsPrim const &prim, matrix_type const &transformation_matrix_to_super,
+              std::vector<Index> const &b_to_asym, int device = 0)
+      : Conversions(prim, default_species_list(prim), transformation_matrix_to_super,
+                    matrix_type{{1, 0, 0, 0, 1, 0, 0, 0, 1}}, b_to_asym, device) {}
+  /// Conversions.cc:118-173: user specified asymmetric unit in a sub-supercell
+  Conversions(ConversionsPrim const &prim, std::vector<std::string> const &species_list,
+              matrix_type const &transformation_matrix_to_super,
+              matrix_type const &unit_transformation_matrix_to_super,
+              std::vector<Index> const &unitl_to_asym, int device = 0)
+      : m_prim(prim), m_T(transformation_matrix_to_super), m_unit_T(unit_transformation_matrix_to_super),
+        m_species(species_list), m_unitl_to_asym(unitl_to_asym), m_device(device) {
+    if (prim.occ_dof.empty()) throw std::runtime_error("Conversions: the prim has no basis sites");
+    if (m_prim.basis_frac.empty()) m_prim.basis_frac.assign(prim.occ_dof.size(), {{0.0, 0.0, 0.0}});
+    if (m_prim.basis_frac.size() != prim.occ_dof.size())
+      throw std::runtime_error("Conversions: basis_frac and occ_dof differ in size");
+    const int64_t nb = static_cast<int64_t>(prim.occ_dof.size());
+    int64_t t[9], u[9];
+    for (int i = 0; i < 9; ++i) {
+      t[i] = m_T[i];
+      u[i] = m_unit_T[i];
+    }
+    m_l_conv = SiteIndexConverter(Mat3l::from_row_major(t), nb);
+    m_unit_conv = SiteIndexConverter(Mat3l::from_row_major(u), nb);
+    {  // U must tile into S: S = U * T' with T' integer  <=>  adj(U) * T divisible by det(U)
+      Mat3l q = mul(adjugate(m_unit_conv.T), m_l_conv.T);
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c)
+          if (q.a[r][c] % m_unit_conv.detT != 0)
+            throw std::runtime_error("Conversions: the unit supercell does not tile the supercell");
+    }
+    if (static_cast<int64_t>(m_unitl_to_asym.size()) != m_unit_conv.total_sites())
+      throw std::runtime_error("Conversions: unitl_to_asym.size() != number of sites of the unit supercell");
+    for (int b = 0; b < nb; ++b) {
+      auto const &f = m_prim.basis_frac[b];
+      std::array<double, 3> c;
+      for (int r = 0; r < 3; ++r)
+        c[r] = m_prim.lat_column_mat[3 * r] * f[0] + m_prim.lat_column_mat[3 * r + 1] * f[1] +
+               m_prim.lat_column_mat[3 * r + 2] * f[2];
+      m_basis_cart.push_back(c);
+    }
+    // Conversions.cc:133-146
+    m_Nasym = *std::max_element(m_unitl_to_asym.begin(), m_unitl_to_asym.end()) + 1;
+    m_asym_to_unitl.resize(m_Nasym);
+    m_asym_to_b.resize(m_Nasym);
+    for (Index unitl = 0; unitl < m_unit_conv.total_sites(); ++unitl) {
+      Index asym = m_unitl_to_asym[unitl];
+      if (asym < 0) throw std::runtime_error("Conversions: negative asymmetric unit index");
+      m_asym_to_unitl[asym].insert(unitl);
+      m_asym_to_b[asym].insert(unitl_to_b(unitl));
+    }
+    // Conversions.cc:148-172: [b][occ] -> species and its inverse (size if not allowed)
+    std::vector<std::vector<Index>> conv = make_index_converter(prim, m_species);
+    std::vector<std::vector<Index>> conv_inv;
+    for (auto const &row : conv) {
+      std::vector<Index> occ_indices(m_species.size(), static_cast<Index>(row.size()));
+      Index occ_index = 0;
+      for (Index species_index : row) occ_indices[species_index] = occ_index++;
+      conv_inv.push_back(occ_indices);
+    }
+    m_occ_to_species.resize(m_Nasym);
+    m_species_to_occ.resize(m_Nasym);
+    for (Index asym = 0; asym < m_Nasym; ++asym) {
+      if (m_asym_to_b[asym].empty()) throw std::runtime_error("Conversions: empty asymmetric unit orbit");
+      Index b = *m_asym_to_b[asym].begin();
+      m_occ_to_species[asym] = conv[b];
+      m_species_to_occ[asym] = conv_inv[b];
+    }
+  }
+  /// round-1 form: n_basis sublattices (occupants "A", "B"), T = diag(n0, n1, n2)
   Conversions(std::vector<long> const &diagonal_T, long n_basis, int device = 0)
-      : m_nb(n_basis), m_device(device) {
-    if (diagonal_T.size() != 3 || n_basis < 1)
-      throw std::runtime_error("Conversions: need a 3-vector of supercell extents and n_basis >= 1");
-    for (int d = 0; d < 3; ++d) m_n[d] = diagonal_T[d];
-  }
-  Index l_size() const { return m_nb * m_n[0] * m_n[1] * m_n[2]; }
-  std::vector<long> l_to_bijk(Index l) const {
-    int64_t in = l, out[4];
-    cmg_check(cmg_conv_l_to_bijk(m_device, m_n, m_nb, &in, 1, out));
-    return {out[0], out[1], out[2], out[3]};
-  }
+      : Conversions(simple_prim(n_basis), diag(diagonal_T), device) {}
+
+  std::array<double, 9> lat_column_mat() const { return m_prim.lat_column_mat; }
+  Index l_size() const { return m_l_conv.total_sites(); }
   Index l_to_b(Index l) const { return l_to_bijk(l)[0]; }
   std::vector<long> l_to_ijk(Index l) const {
     auto v = l_to_bijk(l);
     return {v[1], v[2], v[3]};
   }
-  Index bijk_to_l(long b, long i, long j, long k) const {
-    int64_t in[4] = {b, i, j, k}, out = 0;
-    cmg_check(cmg_conv_bijk_to_l(m_device, m_n, m_nb, in, 1, &out));
-    return out;
+  std::vector<long> l_to_bijk(Index l) const {
+    int64_t o[4];
+    m_l_conv.bijk(l, o);
+    return {static_cast<long>(o[0]), static_cast<long>(o[1]), static_cast<long>(o[2]), static_cast<long>(o[3])};
   }
-  /// batched forms
-  std::vector<int64_t> l_to_bijk(std::vector<int64_t> const &l) const {
+  Index l_to_unitl(Index l) const { return bijk_to_unitl(l_to_bijk(l)); }
+  Index l_to_asym(Index l) const { return m_unitl_to_asym[l_to_unitl(l)]; }
+  std::array<double, 3> l_to_cart(Index l) const {
+    auto bijk = l_to_bijk(l);
+    std::array<double, 3> c = m_basis_cart[bijk[0]];
+    for (int r = 0; r < 3; ++r)
+      c[r] += m_prim.lat_column_mat[3 * r] * bijk[1] + m_prim.lat_column_mat[3 * r + 1] * bijk[2] +
+              m_prim.lat_column_mat[3 * r + 2] * bijk[3];
+    return c;
+  }
+  std::array<double, 3> l_to_frac(Index l) const {
+    auto bijk = l_to_bijk(l);
+    std::array<double, 3> f = m_prim.basis_frac[bijk[0]];
+    for (int r = 0; r < 3; ++r) f[r] += static_cast<double>(bijk[1 + r]);
+    return f;
+  }
+  std::array<double, 3> l_to_basis_cart(Index l) const { return m_basis_cart[l_to_b(l)]; }
+  std::array<double, 3> l_to_basis_frac(Index l) const { return m_prim.basis_frac[l_to_b(l)]; }
+
+  Index bijk_to_l(std::vector<long> const &bijk) const { return convert(m_l_conv, bijk); }
+  Index bijk_to_l(long b, long i, long j, long k) const { return bijk_to_l(std::vector<long>{b, i, j, k}); }
+  Index bijk_to_unitl(std::vector<long> const &bijk) const { return convert(m_unit_conv, bijk); }
+  Index bijk_to_asym(std::vector<long> const &bijk) const { return l_to_asym(bijk_to_l(bijk)); }
+
+  Index unitl_size() const { return m_unit_conv.total_sites(); }
+  Index unitl_to_b(Index unitl) const { return unitl_to_bijk(unitl)[0]; }
+  std::vector<long> unitl_to_bijk(Index unitl) const {
+    int64_t o[4];
+    m_unit_conv.bijk(unitl, o);
+    return {static_cast<long>(o[0]), static_cast<long>(o[1]), static_cast<long>(o[2]), static_cast<long>(o[3])};
+  }
+  Index unitl_to_asym(Index unitl) const { return m_unitl_to_asym.at(unitl); }
+
+  Index asym_size() const { return m_Nasym; }
+  std::set<Index> const &asym_to_b(Index asym) const { return m_asym_to_b.at(asym); }
+  std::set<Index> const &asym_to_unitl(Index asym) const { return m_asym_to_unitl.at(asym); }
+
+  matrix_type const &unit_transformation_matrix_to_super() const { return m_unit_T; }
+  matrix_type const &transformation_matrix_to_super() const { return m_T; }
+  SiteIndexConverter const &unit_index_converter() const { return m_unit_conv; }
+  SiteIndexConverter const &index_converter() const { return m_l_conv; }
+
+  Index occ_size(Index asym) const { return static_cast<Index>(m_occ_to_species.at(asym).size()); }
+  Index species_index(Index asym, Index occ_index) const { return m_occ_to_species.at(asym).at(occ_index); }
+  /// returns occ_size(asym) if the species is not allowed (Conversions.cc:300-303)
+  Index occ_index(Index asym, Index species_index) const { return m_species_to_occ.at(asym).at(species_index); }
+  bool species_allowed(Index asym, Index species_index) const {
+    return occ_index(asym, species_index) != occ_size(asym);
+  }
+  Index species_size() const { return static_cast<Index>(m_species.size()); }
+  /// index of the name, species_size() if absent (find_index semantics)
+  Index species_index(std::string const &species_name) const {
+    for (size_t i = 0; i < m_species.size(); ++i)
+      if (m_species[i] == species_name) return static_cast<Index>(i);
+    return species_size();
+  }
+  std::vector<std::string> const &species_list() const { return m_species; }
+  std::string const &species_name(Index species_index) const { return m_species.at(species_index); }
+  /// every species is a single atom in this mirror (no xtal::Molecule)
+  Index components_size(Index species_index) const {
+    m_species.at(species_index);
+    return 1;
+  }
+
+  /// batched forms, evaluated on the device
+  std::vector<int64_t> l_to_bijk_batch(std::vector<int64_t> const &l) const {
     std::vector<int64_t> out(4 * l.size());
-    cmg_check(cmg_conv_l_to_bijk(m_device, m_n, m_nb, l.data(), static_cast<int64_t>(l.size()), out.data()));
+    int64_t t[9];
+    for (int i = 0; i < 9; ++i) t[i] = m_T[i];
+    cmg_check(cmg_conv_general_l_to_bijk(m_device, t, m_l_conv.n_basis, l.data(),
+                                         static_cast<int64_t>(l.size()), out.data()));
     return out;
   }
-  std::vector<int64_t> bijk_to_l(std::vector<int64_t> const &bijk) const {
+  std::vector<int64_t> bijk_to_l_batch(std::vector<int64_t> const &bijk) const {
     std::vector<int64_t> out(bijk.size() / 4);
-    cmg_check(cmg_conv_bijk_to_l(m_device, m_n, m_nb, bijk.data(), static_cast<int64_t>(out.size()), out.data()));
+    int64_t t[9];
+    for (int i = 0; i < 9; ++i) t[i] = m_T[i];
+    cmg_check(cmg_conv_general_bijk_to_l(m_device, t, m_l_conv.n_basis, bijk.data(),
+                                         static_cast<int64_t>(out.size()), out.data()));
     return out;
   }
 
+  /// xtal::struc_molecule order: unique occupant names in order of first appearance
+  static std::vector<std::string> default_species_list(ConversionsPrim const &prim) {
+    std::vector<std::string> out;
+    for (auto const &site : prim.occ_dof)
+      for (auto const &name : site)
+        if (std::find(out.begin(), out.end(), name) == out.end()) out.push_back(name);
+    return out;
+  }
+  /// xtal::make_index_converter: [b][occ] -> species index
+  static std::vector<std::vector<Index>> make_index_converter(ConversionsPrim const &prim,
+                                                              std::vector<std::string> const &species) {
+    std::vector<std::vector<Index>> conv;
+    for (auto const &site : prim.occ_dof) {
+      std::vector<Index> row;
+      for (auto const &name : site) {
+        auto it = std::find(species.begin(), species.end(), name);
+        if (it == species.end())
+          throw std::runtime_error("Conversions: occupant '" + name + "' is not in the species list");
+        row.push_back(static_cast<Index>(it - species.begin()));
+      }
+      conv.push_back(row);
+    }
+    return conv;
+  }
+  /// Conversions.cc:14-46 with one symmetry orbit: sublattices are told apart by
+  /// their occ -> species lists, orbits numbered in the order of those keys
+  static std::vector<Index> default_b_to_asym(ConversionsPrim const &prim,
+                                              std::vector<std::string> const &species) {
+    std::vector<std::vector<Index>> conv = make_index_converter(prim, species);
+    std::map<std::vector<Index>, std::vector<Index>> by_occ;
+    for (size_t b = 0; b < conv.size(); ++b) by_occ[conv[b]].push_back(static_cast<Index>(b));
+    std::vector<Index> b_to_asym(conv.size());
+    Index asym = 0;
+    for (auto const &pair : by_occ) {
+      for (Index b : pair.second) b_to_asym[b] = asym;
+      ++asym;
+    }
+    return b_to_asym;
+  }
+
  private:
-  int64_t m_n[3];
-  int64_t m_nb;
+  static ConversionsPrim simple_prim(long n_basis) {
+    if (n_basis < 1) throw std::runtime_error("Conversions: need a 3-vector of supercell extents and n_basis >= 1");
+    ConversionsPrim p;
+    p.occ_dof.assign(static_cast<size_t>(n_basis), {"A", "B"});
+    p.basis_frac.assign(static_cast<size_t>(n_basis), {{0.0, 0.0, 0.0}});
+    return p;
+  }
+  static matrix_type diag(std::vector<long> const &d) {
+    if (d.size() != 3) throw std::runtime_error("Conversions: need a 3-vector of supercell extents and n_basis >= 1");
+    return matrix_type{{d[0], 0, 0, 0, d[1], 0, 0, 0, d[2]}};
+  }
+  static Index convert(SiteIndexConverter const &f, std::vector<long> const &bijk) {
+    if (bijk.size() != 4) throw std::runtime_error("Conversions: bijk needs 4 entries");
+    const int64_t in[4] = {bijk[0], bijk[1], bijk[2], bijk[3]};
+    return static_cast<Index>(f.linear_site_index(in));
+  }
+  ConversionsPrim m_prim;
+  matrix_type m_T, m_unit_T;
+  std::vector<std::string> m_species;
+  std::vector<std::array<double, 3>> m_basis_cart;
+  SiteIndexConverter m_l_conv, m_unit_conv;
+  Index m_Nasym = 0;
+  std::vector<Index> m_unitl_to_asym;
+  std::vector<std::set<Index>> m_asym_to_unitl, m_asym_to_b;
+  std::vector<std::vector<Index>> m_occ_to_species, m_species_to_occ;
   int m_device;
 };
 

@@ -266,6 +266,19 @@ int cmg_series_stats_all(cmg_context *ctx, int quantity, const int64_t *first,
 int cmg_series_equilibration_all(cmg_context *ctx, int quantity, int64_t count,
                                  double abs_precision, int *is_equilibrated,
                                  int64_t *n_equil);
+/* One completion check on the device-resident series of `chain` in a single
+ * round trip: CompletionCheck::_check_convergence (include/casm/monte/checks/
+ * CompletionCheck.hh:353-376) for n_components (<= 3) requested components with
+ * absolute precisions: default_equilibration_check of samples [0, count) for each
+ * (is_equilibrated / n_equil per component); if all equilibrated, n_stats =
+ * count - max(n_equil) and BasicStatisticsCalculator over the last n_stats
+ * samples of each (mean / calculated_precision); otherwise n_stats = 0 and the
+ * statistics are not evaluated.  The callers' early exit at the first component
+ * that has not equilibrated is applied by the caller to the returned arrays. */
+int cmg_series_check(cmg_context *ctx, int chain, int n_components, const int *quantity,
+                     const double *abs_precision, int64_t count, double confidence,
+                     int *is_equilibrated, int64_t *n_equil, int64_t *n_stats, double *mean,
+                     double *calculated_precision);
 /* statistics of an arbitrary host series (Sampler columns that did not come
  * from the device path): uploads, computes on the device, returns */
 int cmg_host_series_stats(int device, const double *x, int64_t n, double confidence,
@@ -305,6 +318,19 @@ int cmg_conv_l_to_bijk(int device, const int64_t *n3, int64_t n_basis,
                        const int64_t *l, int64_t count, int64_t *bijk_out);
 int cmg_conv_bijk_to_l(int device, const int64_t *n3, int64_t n_basis,
                        const int64_t *bijk, int64_t count, int64_t *l_out);
+
+/* The same two conversions for ANY integer transformation matrix T (row-major
+ * 3 x 3, S = P * T), batched on the device.  xtal::UnitCellCoordIndexConverter
+ * (CASMcode_crystallography, absent here) is restated in
+ * include/casm_monte_b200/snf.hh: unit cells are numbered through the Smith
+ * normal form of T; for diag(n0,n1,n2) with n0 | n1 | n2 this is the rule above,
+ * for other T the order of unit cells is this library's own (the reference pins
+ * no value).  The first-index-fastest forms above are the ones IsingConfiguration
+ * uses (include/casm/monte/ising_cpp/model.hh:82-99). */
+int cmg_conv_general_l_to_bijk(int device, const int64_t *T9, int64_t n_basis,
+                               const int64_t *l, int64_t count, int64_t *bijk_out);
+int cmg_conv_general_bijk_to_l(int device, const int64_t *T9, int64_t n_basis,
+                               const int64_t *bijk, int64_t count, int64_t *l_out);
 
 /* Energy form of the sampled formation / potential energies.  use_nlist != 0
  * (default): -J * (integer bond sum), IsingFormationEnergy::per_supercell with

@@ -653,6 +653,19 @@ def test_conversions_batch(cm, oracle):
         conv_l_to_bijk([3, 3, 3], 2, [54])
 
 
+def test_general_conversions_batched_on_the_device_match_the_host():
+    import casmcode_monte_b200.monte.events as ev
+
+    for T in ([[-1, 1, 1], [1, -1, 1], [1, 1, -1]], [[2, 0, 0], [0, 3, 0], [0, 0, 1]], [[2, 1, 0], [0, 3, 1], [1, 0, 2]], [[5, 0, 0], [0, 5, 0], [0, 0, 5]]):
+        c = ev.Conversions(occ_dof=[["A", "B"]] * 3, transformation_matrix_to_super=np.array(T))
+        ls = list(range(c.l_size()))
+        bijk = c.l_to_bijk_batch(ls)
+        assert [list(map(int, r)) for r in bijk] == [c.l_to_bijk(l) for l in ls]
+        shifted = bijk.copy()
+        shifted[:, 1:] += (np.array(T) @ np.array([2, -1, 3]))[None, :]  # a supercell translation
+        assert list(c.bijk_to_l_batch(shifted)) == ls
+
+
 # ------------------------------------- full-size, size-independent properties ----
 def test_full_size_4096_properties(cm):
     shape = [4096, 4096]

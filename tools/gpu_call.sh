@@ -4,7 +4,7 @@ tag=${1:-x}; what=${2:-all}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/smi_$tag.txt 2>&1
 if [ "$what" = "pytest" ] || [ "$what" = "all" ]; then
-  ( time timeout 1200 python -m pytest tests -m gpu -x -q --durations=15 ) > gpurun_out/pytest_$tag.log 2>&1
+  ( time timeout 600 python -m pytest tests -m gpu -x -q --durations=15 --timeout 150 ) > gpurun_out/pytest_$tag.log 2>&1
   tail -30 gpurun_out/pytest_$tag.log
 fi
 if [ "$what" = "bench" ] || [ "$what" = "all" ]; then
