@@ -222,6 +222,167 @@ py::array_t<long> to_long_array(std::vector<T> const &v) {
   for (size_t i = 0; i < v.size(); ++i) a.mutable_data()[i] = static_cast<long>(v[i]);
   return a;
 }
+// CutoffCheckParams <-> dict (src/casm/monte/checks/io/json/CutoffCheck_json_io.cc:11-92)
+py::dict cutoff_to_dict(CutoffCheckParams const &p) {
+  py::dict d;
+  auto put = [&](const char *key, auto const &mn, auto const &mx) {
+    if (!mn.has_value() && !mx.has_value()) return;
+    py::dict t;
+    if (mn.has_value()) t["min"] = *mn;
+    if (mx.has_value()) t["max"] = *mx;
+    d[key] = t;
+  };
+  put("count", p.min_count, p.max_count);
+  put("time", p.min_time, p.max_time);
+  put("sample", p.min_sample, p.max_sample);
+  put("clocktime", p.min_clocktime, p.max_clocktime);
+  return d;
+}
+CutoffCheckParams cutoff_from_dict(py::dict d) {
+  CutoffCheckParams p;
+  auto get = [&](const char *key, auto &mn, auto &mx) {
+    if (!d.contains(key) || d[key].is_none()) return;
+    py::dict t = d[key].cast<py::dict>();
+    typedef typename std::remove_reference<decltype(mn)>::type::value_type T;
+    if (t.contains("min") && !t["min"].is_none()) mn = t["min"].cast<T>();
+    if (t.contains("max") && !t["max"].is_none()) mx = t["max"].cast<T>();
+  };
+  get("count", p.min_count, p.max_count);
+  get("time", p.min_time, p.max_time);
+  get("sample", p.min_sample, p.max_sample);
+  get("clocktime", p.min_clocktime, p.max_clocktime);
+  return p;
+}
+RequestedPrecision req_prec_from_dict(py::dict d) {
+  // src/casm/monte/sampling/io/json/Sampler_json_io.cc:33-78 ("precision" is the deprecated key)
+  RequestedPrecision r;
+  for (const char *k : {"abs_precision", "precision"})
+    if (d.contains(k)) {
+      r.abs_convergence_is_required = true;
+      r.abs_precision = d[k].cast<double>();
+    }
+  if (d.contains("rel_precision")) {
+    r.rel_convergence_is_required = true;
+    r.rel_precision = d["rel_precision"].cast<double>();
+  }
+  return r;
+}
+// include/casm/monte/checks/io/json/CompletionCheck_json_io.hh:36-344 (parse): same keys,
+// defaults and error messages; all errors are collected and reported together
+CompletionCheckParams completion_check_params_from_dict(py::dict data,
+                                                        StateSamplingFunctionMap const &sampling_functions) {
+  std::vector<std::string> errors;
+  CompletionCheckParams p;
+  double confidence = 0.95;
+  Index method = 1, n_resamples = 10000;
+  if (data.contains("confidence")) confidence = data["confidence"].cast<double>();
+  if (data.contains("weighted_observations_method")) method = data["weighted_observations_method"].cast<Index>();
+  if (data.contains("n_resamples")) n_resamples = data["n_resamples"].cast<Index>();
+  p.equilibration_check_f = default_equilibration_check;
+  p.calc_statistics_f = BasicStatisticsCalculator(confidence, method, n_resamples);
+  if (data.contains("cutoff") && !data["cutoff"].is_none()) p.cutoff_params = cutoff_from_dict(data["cutoff"].cast<py::dict>());
+  if (data.contains("convergence")) {
+    if (!py::isinstance<py::list>(data["convergence"]) && !py::isinstance<py::tuple>(data["convergence"])) {
+      errors.push_back("Error: \"convergence\" must be an array");
+    } else {
+      for (py::handle h : data["convergence"]) {
+        py::dict c = h.cast<py::dict>();
+        if (!c.contains("quantity")) {
+          errors.push_back("Error: missing required option \"quantity\"");
+          continue;
+        }
+        std::string quantity = c["quantity"].cast<std::string>();
+        auto fit = sampling_functions.find(quantity);
+        if (fit == sampling_functions.end()) {
+          errors.push_back("Error: \"" + quantity + "\" is not a sampling option.");
+          continue;
+        }
+        StateSamplingFunction const &f = fit->second;
+        RequestedPrecision precision = req_prec_from_dict(c);
+        const bool has_index = c.contains("component_index"), has_name = c.contains("component_name");
+        if (has_index)
+          for (Index index : c["component_index"].cast<std::vector<Index>>()) {
+            const Index size = static_cast<Index>(f.component_names.size());
+            if (index < 0 || index >= size) {
+              errors.push_back("Error: For \"" + f.name + "\", component index " + std::to_string(index) +
+                               " is out of range. Valid range is [0," + std::to_string(size) + ").");
+              continue;
+            }
+            p.requested_precision.emplace(SamplerComponent(f.name, index, f.component_names[index]), precision);
+          }
+        if (has_name)
+          for (std::string const &name : c["component_name"].cast<std::vector<std::string>>()) {
+            auto it = std::find(f.component_names.begin(), f.component_names.end(), name);
+            if (it == f.component_names.end()) {
+              errors.push_back("Error: For \"" + f.name + "\", component name " + name + " is not valid.");
+              continue;
+            }
+            p.requested_precision.emplace(
+                SamplerComponent(f.name, static_cast<Index>(it - f.component_names.begin()), name), precision);
+          }
+        if (!has_index && !has_name)
+          for (Index index = 0; index < static_cast<Index>(f.component_names.size()); ++index)
+            p.requested_precision.emplace(SamplerComponent(f.name, index, f.component_names[index]), precision);
+      }
+    }
+  }
+  std::string spacing = "linear";
+  if (data.contains("spacing")) spacing = data["spacing"].cast<std::string>();
+  if (spacing == "linear") {
+    p.log_spacing = false;
+    p.check_begin = 100;
+    p.check_period = 100;
+  } else if (spacing == "log") {
+    p.log_spacing = true;
+    p.check_begin = 0;
+    p.check_base = 10.0;
+    p.check_shift = 2.0;
+    p.check_period_max = 10000;
+  } else {
+    errors.push_back("Error: \"spacing\" must be one of \"linear\", \"log\".");
+  }
+  if (data.contains("begin")) p.check_begin = data["begin"].cast<CountType>();
+  if (data.contains("period")) p.check_period = data["period"].cast<CountType>();
+  if (p.check_period <= 1) errors.push_back("Error: \"period\" must > 0.");
+  if (data.contains("base")) p.check_base = data["base"].cast<double>();
+  if (data.contains("shift")) p.check_shift = data["shift"].cast<double>();
+  if (data.contains("period_max")) p.check_period_max = data["period_max"].cast<CountType>();
+  if (p.check_base <= 1.0) errors.push_back("Error: \"base\" must > 1.0");
+  if (!errors.empty()) {
+    std::string msg = "Error in libcasm.monte.sampling.CompletionCheckParams.from_dict";
+    for (auto const &e : errors) msg += "\n  " + e;
+    throw std::runtime_error(msg);
+  }
+  return p;
+}
+// CompletionCheck_json_io.hh:347-395 (to_json)
+py::dict completion_check_params_to_dict(CompletionCheckParams const &p) {
+  py::dict d;
+  d["cutoff"] = cutoff_to_dict(p.cutoff_params);
+  py::list conv;
+  for (auto const &pair : p.requested_precision) {
+    py::dict t;
+    t["quantity"] = pair.first.sampler_name;
+    t["component_index"] = std::vector<Index>{pair.first.component_index};
+    t["component_name"] = std::vector<std::string>{pair.first.component_name};
+    for (auto item : req_prec_to_dict(pair.second)) t[item.first] = item.second;
+    conv.append(t);
+  }
+  d["convergence"] = conv;
+  if (!p.log_spacing) {
+    d["spacing"] = "linear";
+    d["begin"] = p.check_begin;
+    d["period"] = p.check_period;
+  } else {
+    d["spacing"] = "log";
+    d["begin"] = p.check_begin;
+    d["base"] = p.check_base;
+    d["shift"] = p.check_shift;
+    d["period_max"] = p.check_period_max;
+  }
+  return d;
+}
+
 py::dict config_to_dict(IsingConfiguration const &c) {
   py::dict d;
   d["shape"] = to_pylist(c.shape);
@@ -704,19 +865,7 @@ PYBIND11_MODULE(_monte_b200, m) {
       .def_readwrite("rel_convergence_is_required", &RequestedPrecision::rel_convergence_is_required)
       .def_readwrite("rel_precision", &RequestedPrecision::rel_precision)
       .def("to_dict", &req_prec_to_dict)
-      .def_static("from_dict", [](py::dict d) {
-        RequestedPrecision r;
-        for (const char *k : {"abs_precision", "precision"})
-          if (d.contains(k)) {
-            r.abs_convergence_is_required = true;
-            r.abs_precision = d[k].cast<double>();
-          }
-        if (d.contains("rel_precision")) {
-          r.rel_convergence_is_required = true;
-          r.rel_precision = d["rel_precision"].cast<double>();
-        }
-        return r;
-      });
+      .def_static("from_dict", &req_prec_from_dict, py::arg("data"));
   py::bind_map<RequestedPrecisionMap>(m, "RequestedPrecisionMap");
 
   py::class_<BasicStatistics>(m, "BasicStatistics")
@@ -743,7 +892,15 @@ PYBIND11_MODULE(_monte_b200, m) {
         d["weighted_observations_method"] = c.method;
         d["n_resamples"] = c.n_resamples;
         return d;
-      });
+      })
+      // python/src/monte_sampling.cpp:2363: keys as to_dict, defaults as the constructor
+      .def_static("from_dict", [](py::dict d) {
+        BasicStatisticsCalculator c;
+        if (d.contains("confidence")) c.confidence = d["confidence"].cast<double>();
+        if (d.contains("weighted_observations_method")) c.method = d["weighted_observations_method"].cast<Index>();
+        if (d.contains("n_resamples")) c.n_resamples = d["n_resamples"].cast<Index>();
+        return c;
+      }, py::arg("data"));
 
   // C++-only in the reference (BasicStatistics.hh:57-59); exposed for the parity tests
   m.def("resample", [](py::object obs, py::object w, double weight_sum, Index n) {
@@ -778,7 +935,28 @@ PYBIND11_MODULE(_monte_b200, m) {
       .def("to_dict", &conv_results_to_dict);
 
   py::class_<CutoffCheckParams>(m, "CutoffCheckParams")
-      .def(py::init<>())
+      // python/src/monte_sampling.cpp make_cutoff_check_params
+      .def(py::init([](std::optional<CountType> min_count, std::optional<CountType> max_count,
+                       std::optional<TimeType> min_time, std::optional<TimeType> max_time,
+                       std::optional<CountType> min_sample, std::optional<CountType> max_sample,
+                       std::optional<TimeType> min_clocktime, std::optional<TimeType> max_clocktime) {
+             CutoffCheckParams p;
+             p.min_count = min_count;
+             p.max_count = max_count;
+             p.min_time = min_time;
+             p.max_time = max_time;
+             p.min_sample = min_sample;
+             p.max_sample = max_sample;
+             p.min_clocktime = min_clocktime;
+             p.max_clocktime = max_clocktime;
+             return p;
+           }),
+           py::arg("min_count") = std::nullopt, py::arg("max_count") = std::nullopt,
+           py::arg("min_time") = std::nullopt, py::arg("max_time") = std::nullopt,
+           py::arg("min_sample") = std::nullopt, py::arg("max_sample") = std::nullopt,
+           py::arg("min_clocktime") = std::nullopt, py::arg("max_clocktime") = std::nullopt)
+      .def("to_dict", &cutoff_to_dict)
+      .def_static("from_dict", &cutoff_from_dict, py::arg("data"))
       .def_readwrite("min_count", &CutoffCheckParams::min_count)
       .def_readwrite("min_time", &CutoffCheckParams::min_time)
       .def_readwrite("min_sample", &CutoffCheckParams::min_sample)
@@ -791,7 +969,43 @@ PYBIND11_MODULE(_monte_b200, m) {
   m.def("any_maximum_met", &any_maximum_met);
 
   py::class_<CompletionCheckParams>(m, "CompletionCheckParams")
-      .def(py::init<>())
+      // python/src/monte_sampling.cpp:222-283 make_completion_check_params
+      .def(py::init([](std::optional<RequestedPrecisionMap> requested_precision,
+                       std::optional<CutoffCheckParams> cutoff_params, py::object calc_statistics_f,
+                       py::object equilibration_check_f, bool log_spacing, std::optional<CountType> check_begin,
+                       std::optional<CountType> check_period, std::optional<double> check_base,
+                       std::optional<double> check_shift, std::optional<CountType> check_period_max) {
+             CompletionCheckParams result;  // default check functions
+             if (!log_spacing) {
+               if (!check_period.has_value()) check_period = 100;
+               result.check_begin = *check_period;
+               result.check_period = *check_period;
+             } else {
+               result.check_begin = 0;
+               result.check_base = 10.0;
+               result.check_shift = 2.0;
+               result.check_period_max = 10000;
+             }
+             if (cutoff_params.has_value()) result.cutoff_params = *cutoff_params;
+             if (requested_precision.has_value()) result.requested_precision = *requested_precision;
+             result.log_spacing = log_spacing;
+             if (check_begin.has_value()) result.check_begin = *check_begin;
+             if (check_period.has_value()) result.check_period = *check_period;
+             if (check_base.has_value()) result.check_base = *check_base;
+             if (check_shift.has_value()) result.check_shift = *check_shift;
+             if (check_period_max.has_value()) result.check_period_max = *check_period_max;
+             py::object self = py::cast(result);
+             if (!calc_statistics_f.is_none()) self.attr("calc_statistics_f") = calc_statistics_f;
+             if (!equilibration_check_f.is_none()) self.attr("equilibration_check_f") = equilibration_check_f;
+             return self.cast<CompletionCheckParams>();
+           }),
+           py::arg("requested_precision") = std::nullopt, py::arg("cutoff_params") = std::nullopt,
+           py::arg("calc_statistics_f") = py::none(), py::arg("equilibration_check_f") = py::none(),
+           py::arg("log_spacing") = false, py::arg("check_begin") = std::nullopt,
+           py::arg("check_period") = std::nullopt, py::arg("check_base") = std::nullopt,
+           py::arg("check_shift") = std::nullopt, py::arg("check_period_max") = std::nullopt)
+      .def("to_dict", &completion_check_params_to_dict)
+      .def_static("from_dict", &completion_check_params_from_dict, py::arg("data"), py::arg("sampling_functions"))
       .def_readwrite("cutoff_params", &CompletionCheckParams::cutoff_params)
       .def_readwrite("requested_precision", &CompletionCheckParams::requested_precision)
       .def_readwrite("log_spacing", &CompletionCheckParams::log_spacing)

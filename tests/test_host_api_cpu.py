@@ -231,3 +231,113 @@ def test_generic_loop_with_python_callbacks_matches_oracle(oracle, tmp_path):
     assert e.dump() == oe.dump() and calls == [n_passes]
     d = data.to_dict()
     assert d["n_steps_per_pass"] == N and abs(d["acceptance_rate"] + d["rejection_rate"] - 1.0) < 1e-15
+
+
+# ---- constructors and parsers of the completion-check parameters ----
+# python/src/monte_sampling.cpp:222-283, :2704-2925; include/casm/monte/checks/io/json/
+# CompletionCheck_json_io.hh:36-395; src/casm/monte/checks/io/json/CutoffCheck_json_io.cc:11-92
+def _functions(sampling):
+    fns = sampling.StateSamplingFunctionMap()
+    for name, shape in (("potential_energy", []), ("param_composition", [2])):
+        f = sampling.StateSamplingFunction(name=name, description="", shape=shape, function=lambda: [0.0] * (2 if shape else 1))
+        fns[f.name] = f
+    return fns
+
+
+def test_completion_check_params_keyword_constructor():
+    import casmcode_monte_b200.monte.sampling as sampling
+
+    p = sampling.CompletionCheckParams()
+    assert (p.log_spacing, p.check_begin, p.check_period) == (False, 100, 100)
+    p = sampling.CompletionCheckParams(check_period=25)
+    assert (p.check_begin, p.check_period) == (25, 25)  # begin defaults to the period for linear spacing
+    p = sampling.CompletionCheckParams(log_spacing=True)
+    assert (p.log_spacing, p.check_begin, p.check_base, p.check_shift, p.check_period_max) == (True, 0, 10.0, 2.0, 10000)
+    rp = sampling.RequestedPrecisionMap()
+    key = sampling.SamplerComponent(sampler_name="e", component_index=0, component_name="0")
+    rp[key] = sampling.RequestedPrecision(abs=1e-3)
+    cut = sampling.CutoffCheckParams(min_sample=10, max_count=500)
+    p = sampling.CompletionCheckParams(requested_precision=rp, cutoff_params=cut, check_begin=7, check_period=3, check_shift=1.5)
+    assert p.cutoff_params.min_sample == 10 and p.cutoff_params.max_count == 500 and p.cutoff_params.min_count is None
+    assert (p.check_begin, p.check_period, p.check_shift) == (7, 3, 1.5)
+    assert p.requested_precision[key].abs_precision == 1e-3
+    calls = []
+
+    def stats(obs, w):
+        calls.append(len(obs))
+        s = sampling.BasicStatistics()
+        s.mean, s.calculated_precision = 1.0, 0.0
+        return s
+
+    p = sampling.CompletionCheckParams(requested_precision=rp, calc_statistics_f=stats, check_begin=2, check_period=2)
+    cc = sampling.CompletionCheck(p)
+    samplers = sampling.SamplerMap()
+    samplers["e"] = sampling.Sampler(shape=[], component_names=["0"])
+    for v in (1.0, 2.0, 1.0, 2.0):
+        samplers["e"].append([v])
+    import casmcode_monte_b200.monte as monte
+
+    # the default equilibration check runs on the device: only reached with a GPU
+    assert p.to_dict()["convergence"][0]["quantity"] == "e"
+    assert monte is not None and cc.params().check_begin == 2 and not calls
+
+
+def test_completion_check_params_from_dict_round_trip():
+    import casmcode_monte_b200.monte.sampling as sampling
+
+    fns = _functions(sampling)
+    data = {
+        "cutoff": {"count": {"min": 5, "max": 1000}, "sample": {"min": 20}, "clocktime": {"max": 3600.0}},
+        "convergence": [
+            {"quantity": "potential_energy", "abs_precision": 1e-4},
+            {"quantity": "param_composition", "precision": 1e-3, "rel_precision": 0.01, "component_index": [1]},
+        ],
+        "spacing": "log",
+        "begin": 10,
+        "base": 4.0,
+        "confidence": 0.9,
+    }
+    p = sampling.CompletionCheckParams.from_dict(data, fns)
+    assert p.log_spacing and p.check_begin == 10 and p.check_base == 4.0 and p.check_shift == 2.0 and p.check_period_max == 10000
+    c = p.cutoff_params
+    assert (c.min_count, c.max_count, c.min_sample, c.max_sample, c.max_clocktime, c.min_time) == (5, 1000, 20, None, 3600.0, None)
+    keys = {(k.sampler_name, k.component_index, k.component_name): v for k, v in p.requested_precision.items()}
+    assert set(keys) == {("potential_energy", 0, "0"), ("param_composition", 1, "1")}
+    r = keys[("param_composition", 1, "1")]
+    assert r.abs_convergence_is_required and r.abs_precision == 1e-3 and r.rel_convergence_is_required and r.rel_precision == 0.01
+    d = p.to_dict()
+    assert d["spacing"] == "log" and d["begin"] == 10 and d["base"] == 4.0 and d["cutoff"]["count"] == {"min": 5, "max": 1000}
+    again = sampling.CompletionCheckParams.from_dict(d, fns)
+    assert again.to_dict() == d
+    # defaults: linear spacing, all components of a quantity
+    p = sampling.CompletionCheckParams.from_dict({"convergence": [{"quantity": "param_composition", "precision": 0.1}]}, fns)
+    assert (p.log_spacing, p.check_begin, p.check_period) == (False, 100, 100) and len(p.requested_precision) == 2
+    p = sampling.CompletionCheckParams.from_dict({"convergence": [{"quantity": "param_composition", "precision": 0.1, "component_name": ["1"]}]}, fns)
+    assert [k.component_index for k in p.requested_precision] == [1]
+    # errors are collected and raised (RuntimeError, as the reference's report_and_throw_if_invalid)
+    for bad in (
+        {"convergence": [{"quantity": "nope", "precision": 0.1}]},
+        {"convergence": [{"quantity": "param_composition", "precision": 0.1, "component_index": [2]}]},
+        {"convergence": [{"quantity": "param_composition", "precision": 0.1, "component_name": ["x"]}]},
+        {"convergence": {"quantity": "potential_energy"}},
+        {"spacing": "cubic"},
+        {"period": 1},
+        {"spacing": "log", "base": 1.0},
+    ):
+        with pytest.raises(RuntimeError):
+            sampling.CompletionCheckParams.from_dict(bad, fns)
+
+
+def test_cutoff_and_statistics_calculator_dict_io():
+    import casmcode_monte_b200.monte.sampling as sampling
+
+    c = sampling.CutoffCheckParams(min_count=1, max_sample=9, min_clocktime=0.5)
+    assert c.to_dict() == {"count": {"min": 1}, "sample": {"max": 9}, "clocktime": {"min": 0.5}}
+    assert sampling.CutoffCheckParams.from_dict(c.to_dict()).to_dict() == c.to_dict()
+    assert sampling.CutoffCheckParams.from_dict({}).to_dict() == {}
+    calc = sampling.BasicStatisticsCalculator.from_dict({"confidence": 0.8, "n_resamples": 50})
+    assert calc.to_dict() == {"confidence": 0.8, "weighted_observations_method": 1, "n_resamples": 50}
+    assert sampling.BasicStatisticsCalculator.from_dict(sampling.BasicStatisticsCalculator(0.99, 2, 7).to_dict()).to_dict() == {
+        "confidence": 0.99, "weighted_observations_method": 2, "n_resamples": 7}
+    r = sampling.RequestedPrecision.from_dict({"precision": 0.5})
+    assert r.abs_convergence_is_required and r.abs_precision == 0.5 and not r.rel_convergence_is_required
