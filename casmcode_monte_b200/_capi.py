@@ -94,6 +94,15 @@ SIGNATURES = {
     "cmg_conv_bijk_to_l": (C.c_int, [C.c_int, _i64p, C.c_int64, _i64p, C.c_int64, _i64p]),
     "cmg_conv_general_l_to_bijk": (C.c_int, [C.c_int, _i64p, C.c_int64, _i64p, C.c_int64, _i64p]),
     "cmg_conv_general_bijk_to_l": (C.c_int, [C.c_int, _i64p, C.c_int64, _i64p, C.c_int64, _i64p]),
+    "cmg_kstate_set_model": (C.c_int, [_ctx, C.c_int, _f64p]),
+    "cmg_kstate_set_conditions": (C.c_int, [_ctx, C.c_int, C.c_double, _f64p]),
+    "cmg_kstate_get_tables": (C.c_int, [_ctx, C.c_int, _f64p, _f64p, _u32p, _u8p, C.c_int64]),
+    "cmg_kstate_upload_occupation_i32": (C.c_int, [_ctx, C.c_int, _i32p, C.c_int64]),
+    "cmg_kstate_download_occupation_i32": (C.c_int, [_ctx, C.c_int, _i32p, C.c_int64]),
+    "cmg_kstate_run_passes": (C.c_int, [_ctx, C.c_int64, C.c_int, C.c_int64]),
+    "cmg_kstate_n_samples": (C.c_int, [_ctx, _i64p]),
+    "cmg_kstate_clear_samples": (C.c_int, [_ctx]),
+    "cmg_kstate_read_samples": (C.c_int, [_ctx, C.c_int, C.c_int64, C.c_int64, _i64p, _i64p]),
     "cmg_set_energy_form": (C.c_int, [_ctx, C.c_int]),
     "cmg_launch_count": (C.c_int, [_ctx, _i64p]),
     "cmg_kernel_variant": (C.c_char_p, [_ctx]),

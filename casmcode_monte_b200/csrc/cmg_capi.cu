@@ -112,6 +112,15 @@ struct cmg_context {
   bool bulk_attr_set = false;
   int js_auto[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // cached strip length per kernel variant
   size_t smem_optin = 0;
+  // k-state model; K == 0: the context runs the Ising path
+  int ks_K = 0;
+  double ks_V[kMaxSpecies * kMaxSpecies] = {0};
+  KStateTables *d_ktabs = nullptr;  // [n_chains]
+  std::vector<char> ks_valid;
+  long long *d_kseries = nullptr;  // [sample][chain][K + K*K]
+  long long ks_capacity = 0, ks_n_samples = 0;
+  int *d_kloc = nullptr, *d_kloc_size = nullptr, *d_kmol_loc = nullptr;  // OccLocation of every chain
+  bool ks_loc_valid = false;
   long long launches = 0;
   std::string last_error;
   std::string variant_name = "auto";
@@ -426,6 +435,11 @@ int cmg_destroy(cmg_context *c) {
   cudaFree(c->d_ring_mailbox);
   cudaFree(c->d_lines);
   cudaFree(c->d_error);
+  cudaFree(c->d_ktabs);
+  cudaFree(c->d_kseries);
+  cudaFree(c->d_kloc);
+  cudaFree(c->d_kloc_size);
+  cudaFree(c->d_kmol_loc);
   if (c->h_error) cudaFreeHost(c->h_error);
   delete c;
   return CMG_OK;
@@ -2108,18 +2122,20 @@ int cmg_series_check(cmg_context *c, int chain, int n_components, const int *qua
   cudaFuncSetAttribute(k_series_equilibration, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)(kEquilSmemDoubles * sizeof(double)));
   const long long stage = count <= kEquilSmemDoubles ? count : 0;
-  // one launch per distinct precision (the kernel takes one); usually they are equal
-  for (int i = 0; i < n; ++i) {
-    bool done = false;
-    for (int j = 0; j < i; ++j) done = done || abs_precision[j] == abs_precision[i];
-    if (done) continue;
-    // jobs i.. with this precision are contiguous in the common case; launch per job otherwise
-    for (int j = i; j < n; ++j)
-      if (abs_precision[j] == abs_precision[i]) {
-        k_series_equilibration<<<1, kEquilThreads, (size_t)stage * sizeof(double), c->stream>>>(
-            d->eq + j, 1, abs_precision[i], d->is_eq + j, d->n_eq + j, stage);
-        ++c->launches;
-      }
+  // the kernel takes one precision: one launch (a CTA per series, side by side) when the
+  // requested precisions are equal, as they usually are; one launch per series otherwise
+  bool same = true;
+  for (int i = 1; i < n; ++i) same = same && abs_precision[i] == abs_precision[0];
+  if (same) {
+    k_series_equilibration<<<n, kEquilThreads, (size_t)stage * sizeof(double), c->stream>>>(
+        d->eq, n, abs_precision[0], d->is_eq, d->n_eq, stage);
+    ++c->launches;
+  } else {
+    for (int j = 0; j < n; ++j) {
+      k_series_equilibration<<<1, kEquilThreads, (size_t)stage * sizeof(double), c->stream>>>(
+          d->eq + j, 1, abs_precision[j], d->is_eq + j, d->n_eq + j, stage);
+      ++c->launches;
+    }
   }
   k_make_tail_jobs<<<1, 32, 0, c->stream>>>(d->eq, n, d->is_eq, d->n_eq, d->st, &d->n_stats);
   k_series_stats<<<n, 256, 0, c->stream>>>(d->st, z_confidence(confidence), d->out4, d->k_star);
@@ -2393,6 +2409,310 @@ int cmg_conv_general_bijk_to_l(int device, const int64_t *T9, int64_t n_basis, c
   CU(c, cudaMemcpy(l_out, dl, 8 * (size_t)count, cudaMemcpyDeviceToHost));
   scratch_free(dl, 0);
   scratch_free(db, 0);
+  return CMG_OK;
+}
+
+// ---- k-state model ------------------------------------------------------------------------
+// Tables with the expression order of the restated model: dE = sum_s n_s * (V[to][s] -
+// V[from][s]) accumulated in species order, dPhi = dE - (mu[to] - mu[from]),
+// prob = exp(-dPhi * beta), beta = 1 / (KB * T); thresholds as for the Ising tables.
+static void build_kstate_tables(KStateTables &t, int dim, int K, const double *V, double T, const double *mu) {
+  memset(&t, 0, sizeof t);
+  t.K = K;
+  t.z = 2 * dim;
+  t.n_cfg = 1;
+  for (int s = 1; s < K; ++s) t.n_cfg *= (t.z + 1);
+  volatile double kt = CMG_KB * T;
+  const double beta = 1.0 / kt;
+  int cnt[kMaxSpecies];
+  for (int cfg = 0; cfg < t.n_cfg; ++cfg) {
+    int rest = cfg, total = 0;
+    for (int s = 1; s < K; ++s) {
+      cnt[s] = rest % (t.z + 1);
+      rest /= (t.z + 1);
+      total += cnt[s];
+    }
+    if (total > t.z) continue;
+    cnt[0] = t.z - total;
+    for (int from = 0; from < K; ++from)
+      for (int to = 0; to < K; ++to) {
+        if (from == to) continue;
+        volatile double dE = 0.0;
+        for (int s = 0; s < K; ++s) {
+          volatile double dv = V[to * K + s] - V[from * K + s];
+          volatile double term = cnt[s] * dv;
+          dE = dE + term;
+        }
+        volatile double dmu = mu[to] - mu[from];
+        const double d = dE - dmu;
+        volatile double arg = -d * beta;
+        const double p = std::exp(arg);
+        const int i = (from * K + to) * t.n_cfg + cfg;
+        t.dPhi[i] = d;
+        t.prob[i] = p;
+        if (d < 0.0 || p >= 1.0) {
+          t.thr_m1[i] = 0xFFFFFFFFu;
+        } else if (!(p > 0.0)) {
+          t.thr_m1[i] = 0u;
+          t.never[i] = 1;
+        } else {
+          double scaled = std::ceil(p * 4294967296.0);
+          if (scaled < 1.0) scaled = 1.0;
+          if (scaled > 4294967296.0) scaled = 4294967296.0;
+          t.thr_m1[i] = (uint32_t)((unsigned long long)scaled - 1ull);
+        }
+      }
+  }
+  t.valid = 1;
+}
+
+int cmg_kstate_set_model(cmg_context *c, int n_species, const double *V) {
+  NEED(c);
+  if (n_species < 2 || n_species > kMaxSpecies || !V) return fail(c, CMG_EINVAL, "k-state model: 2 <= n_species <= 4");
+  if (c->slab) return fail(c, CMG_EUNSUPPORTED, "k-state model: single-GPU contexts only");
+  for (int a = 0; a < n_species; ++a)
+    for (int b = 0; b < n_species; ++b)
+      if (V[a * n_species + b] != V[b * n_species + a]) return fail(c, CMG_EINVAL, "k-state model: V must be symmetric");
+  c->ks_K = n_species;
+  for (int i = 0; i < n_species * n_species; ++i) c->ks_V[i] = V[i];
+  if (!c->d_ktabs) CU(c, cudaMalloc(&c->d_ktabs, sizeof(KStateTables) * (size_t)c->n_chains));
+  c->ks_valid.assign(c->n_chains, 0);
+  c->ks_n_samples = 0;
+  c->ks_loc_valid = false;
+  return CMG_OK;
+}
+
+int cmg_kstate_set_conditions(cmg_context *c, int chain, double temperature, const double *mu) {
+  NEED(c);
+  if (!c->ks_K) return fail(c, CMG_ESTATE, "k-state model not set");
+  if (chain < -1 || chain >= c->n_chains) return fail(c, CMG_EINVAL, "bad chain index");
+  if (!(temperature > 0.0) || !mu) return fail(c, CMG_EINVAL, "temperature must be > 0");
+  const int lo = chain < 0 ? 0 : chain, hi = chain < 0 ? c->n_chains : chain + 1;
+  std::vector<KStateTables> h(1);
+  build_kstate_tables(h[0], c->dim, c->ks_K, c->ks_V, temperature, mu);
+  for (int ch = lo; ch < hi; ++ch) {
+    CU(c, cudaMemcpyAsync(c->d_ktabs + ch, h.data(), sizeof(KStateTables), cudaMemcpyHostToDevice, c->stream));
+    c->ks_valid[ch] = 1;
+  }
+  CU(c, cudaStreamSynchronize(c->stream));
+  return CMG_OK;
+}
+
+int cmg_kstate_get_tables(cmg_context *c, int chain, double *dPhi, double *prob, uint32_t *thr_m1, uint8_t *never,
+                          int64_t n_entries) {
+  NEED(c);
+  if (!c->ks_K) return fail(c, CMG_ESTATE, "k-state model not set");
+  if (chain < 0 || chain >= c->n_chains) return fail(c, CMG_EINVAL, "bad chain index");
+  if (!c->ks_valid[chain]) return fail(c, CMG_ESTATE, "conditions not set");
+  std::vector<KStateTables> h(1);
+  CU(c, cudaMemcpyAsync(h.data(), c->d_ktabs + chain, sizeof(KStateTables), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  const int64_t n = (int64_t)h[0].K * h[0].K * h[0].n_cfg;
+  if (n_entries != n) return fail(c, CMG_EINVAL, "n_entries must be K * K * (z + 1)^(K - 1)");
+  for (int64_t i = 0; i < n; ++i) {
+    if (dPhi) dPhi[i] = h[0].dPhi[i];
+    if (prob) prob[i] = h[0].prob[i];
+    if (thr_m1) thr_m1[i] = h[0].thr_m1[i];
+    if (never) never[i] = h[0].never[i];
+  }
+  return CMG_OK;
+}
+
+int cmg_kstate_upload_occupation_i32(cmg_context *c, int chain, const int32_t *occ_index, int64_t n) {
+  NEED(c);
+  if (!c->ks_K) return fail(c, CMG_ESTATE, "k-state model not set");
+  if (chain < 0 || chain >= c->n_chains) return fail(c, CMG_EINVAL, "bad chain index");
+  if (!occ_index || n != c->n_sites) return fail(c, CMG_EINVAL, "Error in set_occupation: size mismatch");
+  int rc = ensure_stage(c);
+  if (rc) return rc;
+  CU(c, cudaMemcpyAsync(c->d_stage, occ_index, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemsetAsync(c->d_flag, 0, sizeof(int), c->stream));
+  k_kstate_i32_to_sites<<<nblocks(n, 256), 256, 0, c->stream>>>(c->d_stage, chain_base(c, chain), c->plane_stride,
+                                                                 nat_shape(c), c->planar ? 1 : 0, c->ks_K, c->d_flag);
+  ++c->launches;
+  if (c->planar) c->nat_is_current = false;
+  c->ks_loc_valid = false;
+  CU(c, cudaGetLastError());
+  int bad = 0;
+  CU(c, cudaMemcpyAsync(&bad, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  if (bad) return fail(c, CMG_EINVAL, "occupation indices must be in [0, n_species)");
+  return CMG_OK;
+}
+
+int cmg_kstate_download_occupation_i32(cmg_context *c, int chain, int32_t *occ_index, int64_t n) {
+  NEED(c);
+  if (!c->ks_K) return fail(c, CMG_ESTATE, "k-state model not set");
+  if (chain < 0 || chain >= c->n_chains) return fail(c, CMG_EINVAL, "bad chain index");
+  if (!occ_index || n != c->n_sites) return fail(c, CMG_EINVAL, "size mismatch");
+  int rc = ensure_stage(c);
+  if (rc) return rc;
+  k_kstate_sites_to_i32<<<nblocks(n, 256), 256, 0, c->stream>>>(chain_base(c, chain), c->plane_stride, c->d_stage,
+                                                                 nat_shape(c), c->planar ? 1 : 0);
+  ++c->launches;
+  CU(c, cudaGetLastError());
+  CU(c, cudaMemcpyAsync(occ_index, c->d_stage, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return CMG_OK;
+}
+
+static int kstate_sample(cmg_context *c) {
+  const int per = c->ks_K + c->ks_K * c->ks_K;
+  if (c->ks_n_samples >= c->ks_capacity) {
+    long long cap = c->ks_capacity ? 2 * c->ks_capacity : 1024;
+    long long *nb = nullptr;
+    CU(c, cudaMalloc(&nb, sizeof(long long) * (size_t)cap * c->n_chains * per));
+    CU(c, cudaMemsetAsync(nb, 0, sizeof(long long) * (size_t)cap * c->n_chains * per, c->stream));
+    if (c->d_kseries && c->ks_n_samples > 0)
+      CU(c, cudaMemcpyAsync(nb, c->d_kseries, sizeof(long long) * (size_t)c->ks_n_samples * c->n_chains * per,
+                            cudaMemcpyDeviceToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    cudaFree(c->d_kseries);
+    c->d_kseries = nb;
+    c->ks_capacity = cap;
+  }
+  int rc = sync_nat_from_planes(c);
+  if (rc) return rc;
+  for (int ch = 0; ch < c->n_chains; ++ch) {
+    long long *dst = c->d_kseries + ((size_t)c->ks_n_samples * c->n_chains + ch) * per;
+    CU(c, cudaMemsetAsync(dst, 0, sizeof(long long) * per, c->stream));
+    k_kstate_observables<<<(unsigned)std::min<long long>(nblocks(c->n_sites, 256), 148 * 4), 256, 0, c->stream>>>(
+        c->d_nat + (size_t)ch * c->n_sites, nat_shape(c), c->ks_K, dst);
+    ++c->launches;
+  }
+  CU(c, cudaGetLastError());
+  ++c->ks_n_samples;
+  return CMG_OK;
+}
+
+int cmg_kstate_run_passes(cmg_context *c, int64_t n_passes, int mode, int64_t sample_period) {
+  NEED(c);
+  if (!c->ks_K) return fail(c, CMG_ESTATE, "k-state model not set");
+  if (n_passes < 0 || sample_period < 0) return fail(c, CMG_EINVAL, "negative count");
+  for (int ch = 0; ch < c->n_chains; ++ch)
+    if (!c->ks_valid[ch]) return fail(c, CMG_ESTATE, "conditions not set for every chain");
+  if (mode == CMG_MODE_CHECKERBOARD) {
+    if (!c->planar) return fail(c, CMG_EINVAL, "checkerboard mode needs even extents; use CMG_MODE_SERIAL_REFERENCE");
+    KSweepArgs A;
+    memset(&A, 0, sizeof A);
+    A.L = view(c);
+    A.tabs = c->d_ktabs;
+    A.n_accept = c->d_n_accept;
+    for (int r = 0; r < 10; ++r) {
+      A.rk[2 * r] = (uint32_t)c->philox_seed + (uint32_t)r * kPhiloxW0;
+      A.rk[2 * r + 1] = (uint32_t)(c->philox_seed >> 32) + (uint32_t)r * kPhiloxW1;
+    }
+    A.chain_offset = c->chain_offset;
+    const dim3 grid(nblocks(c->n_sites / 2, 256), c->n_chains);
+    for (int64_t t = 0; t < n_passes; ++t) {
+      A.pass = c->h_pass;
+      for (int colour = 0; colour < 2; ++colour) {
+        A.colour = colour;
+        k_kstate_halfsweep<<<grid, 256, 0, c->stream>>>(A);
+        ++c->launches;
+      }
+      c->nat_is_current = false;
+      c->ks_loc_valid = false;
+      ++c->h_pass;
+      ++c->n_pass;
+      if (sample_period > 0 && (c->n_pass % sample_period) == 0) {
+        int rc = kstate_sample(c);
+        if (rc) return rc;
+      }
+    }
+    CU(c, cudaGetLastError());
+    c->variant_name = "kstate_generic";
+    return CMG_OK;
+  }
+  if (mode != CMG_MODE_SERIAL_REFERENCE) return fail(c, CMG_EINVAL, "unknown mode");
+  for (int ch = 0; ch < c->n_chains; ++ch)
+    if (!c->d_engines || !c->engine_seeded[ch]) return fail(c, CMG_ESTATE, "mt19937_64 engine not seeded for every chain");
+  if (c->n_sites >= (1ll << 31)) return fail(c, CMG_EUNSUPPORTED, "k-state serial mode: n_sites < 2^31");
+  int rc = sync_nat_from_planes(c);
+  if (rc) return rc;
+  if (!c->d_kloc) {
+    CU(c, cudaMalloc(&c->d_kloc, sizeof(int) * (size_t)c->n_chains * kMaxSpecies * c->n_sites));
+    CU(c, cudaMalloc(&c->d_kloc_size, sizeof(int) * (size_t)c->n_chains * kMaxSpecies));
+    CU(c, cudaMalloc(&c->d_kmol_loc, sizeof(int) * (size_t)c->n_chains * c->n_sites));
+    c->ks_loc_valid = false;
+  }
+  KLocation P;
+  if (!c->ks_loc_valid) {
+    // OccLocation::initialize from the current occupation
+    for (int ch = 0; ch < c->n_chains; ++ch) {
+      P.loc = c->d_kloc + (size_t)ch * c->ks_K * c->n_sites;
+      P.loc_size = c->d_kloc_size + (size_t)ch * kMaxSpecies;
+      P.mol_loc = c->d_kmol_loc + (size_t)ch * c->n_sites;
+      k_kstate_location_init<<<1, 1, 0, c->stream>>>(c->d_nat + (size_t)ch * c->n_sites, c->n_sites, c->ks_K, P);
+      ++c->launches;
+    }
+    c->ks_loc_valid = true;
+  }
+  KSerialArgs A;
+  memset(&A, 0, sizeof A);
+  A.nat = c->d_nat;
+  A.shape = nat_shape(c);
+  A.tabs = c->d_ktabs;
+  A.engines = c->d_engines;
+  A.n_accept = c->d_n_accept;
+  A.loc.loc = c->d_kloc;
+  A.loc.loc_size = c->d_kloc_size;
+  A.loc.mol_loc = c->d_kmol_loc;
+  int64_t left = n_passes;
+  while (left > 0) {
+    int64_t chunk = left;
+    if (sample_period > 0) chunk = std::min<int64_t>(left, sample_period - (c->n_pass % sample_period));
+    A.n_passes = chunk;
+    k_kstate_serial<<<c->n_chains, kSerialThreads, 0, c->stream>>>(A);
+    ++c->launches;
+    CU(c, cudaGetLastError());
+    c->n_pass += chunk;
+    left -= chunk;
+    // the planes follow the natural copy (which stays current: it is what the walk updates)
+    rc = sync_planes_from_nat(c);
+    if (rc) return rc;
+    c->nat_is_current = true;
+    if (sample_period > 0 && (c->n_pass % sample_period) == 0) {
+      rc = kstate_sample(c);
+      if (rc) return rc;
+    }
+  }
+  c->variant_name = "kstate_serial_reference";
+  return CMG_OK;
+}
+
+int cmg_kstate_n_samples(cmg_context *c, int64_t *n_samples) {
+  if (!c || !n_samples) return fail(c, CMG_EINVAL, "null argument");
+  *n_samples = c->ks_n_samples;
+  return CMG_OK;
+}
+
+int cmg_kstate_clear_samples(cmg_context *c) {
+  NEED(c);
+  c->ks_n_samples = 0;
+  return CMG_OK;
+}
+
+int cmg_kstate_read_samples(cmg_context *c, int chain, int64_t first, int64_t count, int64_t *counts,
+                            int64_t *bonds) {
+  NEED(c);
+  if (!c->ks_K) return fail(c, CMG_ESTATE, "k-state model not set");
+  if (chain < 0 || chain >= c->n_chains) return fail(c, CMG_EINVAL, "bad chain index");
+  if (first < 0 || count < 0 || first + count > c->ks_n_samples) return fail(c, CMG_EINVAL, "sample range outside the series");
+  if (count == 0) return CMG_OK;
+  const int K = c->ks_K, per = K + K * K;
+  std::vector<long long> tmp((size_t)count * per);
+  CU(c, cudaMemcpy2DAsync(tmp.data(), sizeof(long long) * per,
+                          c->d_kseries + ((size_t)first * c->n_chains + chain) * per,
+                          sizeof(long long) * per * c->n_chains, sizeof(long long) * per, (size_t)count,
+                          cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  for (int64_t i = 0; i < count; ++i) {
+    for (int a = 0; a < K; ++a)
+      if (counts) counts[i * K + a] = tmp[(size_t)i * per + a];
+    for (int e = 0; e < K * K; ++e)
+      if (bonds) bonds[i * K * K + e] = tmp[(size_t)i * per + K + e];
+  }
   return CMG_OK;
 }
 

@@ -2688,3 +2688,312 @@ __global__ void k_conv_general_bijk_to_l(ConvGeneral P, const long long *__restr
 }
 
 }  // namespace cmg
+
+// ===========================================================================
+// k-state lattice model served by the general multi-species proposal tables
+// (SURVEY 8f rank 3).  K <= 4 species per site, occupation byte = occupation
+// index; nearest-neighbour pair energy V[a][b] and exchange potential mu[s]:
+//     potential = sum_<ij> V[o_i][o_j] - sum_i mu[o_i].
+// The host builds, per chain, the table of dPhi / exp(-dPhi*beta) / 32-bit
+// threshold for every (from, to, neighbour configuration); configuration index
+// = sum_{s>=1} n_s * (z+1)^(s-1), n_s = number of neighbours holding species s.
+// Two update orders, as for the Ising path:
+//   checkerboard: every site of a colour proposes one of its K-1 other species
+//     (one Philox call per site: word 0 chooses the species, word 1 is the
+//     acceptance uniform);
+//   serial reference: the reference's general proposal machinery --
+//     OccCandidateList / OccLocation / propose_semigrand_canonical_event
+//     (include/casm/monte/events/OccEventProposal.hh:260-348,
+//     src/casm/monte/events/OccLocation.cc:39-116, :253-283) -- walked by one
+//     thread per chain on the reference's mt19937_64 stream, trajectory-exact.
+// ===========================================================================
+namespace cmg {
+
+constexpr int kMaxSpecies = 4;
+constexpr int kMaxKCfg = 343;  // (2*3+1)^(4-1)
+constexpr int kMaxKEntries = kMaxSpecies * kMaxSpecies * kMaxKCfg;
+
+struct KStateTables {
+  double dPhi[kMaxKEntries];
+  double prob[kMaxKEntries];
+  uint32_t thr_m1[kMaxKEntries];
+  uint8_t never[kMaxKEntries];
+  int K, z, n_cfg, valid;
+};
+__device__ __forceinline__ int kstate_entry(const KStateTables *t, int from, int to, int cfg) {
+  return (from * t->K + to) * t->n_cfg + cfg;
+}
+// (z+1)^(s-1) for s = 0..3 (weight of species 0 is 0: its count is implied)
+__device__ __forceinline__ int kstate_weight(int s, int z) {
+  return s == 0 ? 0 : s == 1 ? 1 : s == 2 ? (z + 1) : (z + 1) * (z + 1);
+}
+
+struct KSweepArgs {
+  LatticeView L;
+  const KStateTables *tabs;  // [chain]
+  unsigned long long *n_accept;
+  unsigned long long pass;
+  uint32_t rk[20];
+  int colour;
+  int chain_offset;
+};
+
+// one thread per site of the colour being updated
+__global__ void __launch_bounds__(256) k_kstate_halfsweep(KSweepArgs A) {
+  const LatticeView &L = A.L;
+  const int chain = blockIdx.y;
+  const KStateTables *tab = A.tabs + chain;
+  uint8_t *C = L.planes + (long long)chain * L.chain_stride + (long long)A.colour * L.plane_stride;
+  const uint8_t *O = L.planes + (long long)chain * L.chain_stride + (long long)(1 - A.colour) * L.plane_stride;
+  const long long plane_size = (long long)L.h * L.n1 * L.n2;
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int z = 2 * L.dim;
+  unsigned int acc = 0;
+  if (q < plane_size) {
+    const int p = (int)(q % L.h);
+    const long long jk = q / L.h;
+    const int j = (int)(jk % L.n1);
+    const int k = (int)(jk / L.n1);
+    const int par = (j + k + A.colour) & 1;  // i = 2p + par
+    const int jm = (j == 0) ? L.n1 - 1 : j - 1, jp = (j == L.n1 - 1) ? 0 : j + 1;
+    const long long rowk = (long long)L.n1 * k;
+    const int ps = par ? ((p == L.h - 1) ? 0 : p + 1) : ((p == 0) ? L.h - 1 : p - 1);
+    int cfg = kstate_weight(O[p + (long long)L.h * (jm + rowk)], z) + kstate_weight(O[p + (long long)L.h * (jp + rowk)], z) +
+              kstate_weight(O[p + (long long)L.h * (j + rowk)], z) + kstate_weight(O[ps + (long long)L.h * (j + rowk)], z);
+    if (L.dim == 3) {
+      const int km = (k == 0) ? L.n2 - 1 : k - 1, kp = (k == L.n2 - 1) ? 0 : k + 1;
+      cfg += kstate_weight(O[p + (long long)L.h * (j + (long long)L.n1 * km)], z) +
+             kstate_weight(O[p + (long long)L.h * (j + (long long)L.n1 * kp)], z);
+    }
+    const int from = C[q];
+    const uint4 w = site_group_random((unsigned long long)q, (uint32_t)(chain + A.chain_offset) << 8, A.pass, A.colour, 0, A.rk);
+    const int jj = (int)__umulhi(w.x, (uint32_t)(tab->K - 1));
+    const int to = jj + (jj >= from ? 1 : 0);
+    const int e = kstate_entry(tab, from, to, cfg);
+    if (!tab->never[e] && w.y <= tab->thr_m1[e]) {
+      C[q] = (uint8_t)to;
+      acc = 1;
+    }
+  }
+  acc = __reduce_add_sync(0xffffffffu, acc);
+  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(A.n_accept + chain, (unsigned long long)acc);
+}
+
+// integer observables of a k-state lattice in the natural layout: count[s] and the
+// bond-type histogram bonds[a][b], a <= b, over the (+i, +j [, +k]) bonds of every site.
+// out: K counts then K*K bond counts (row-major, only a <= b used)
+__global__ void __launch_bounds__(256) k_kstate_observables(const uint8_t *__restrict__ nat, NaturalShape s, int K,
+                                                            long long *out) {
+  __shared__ unsigned long long sh[kMaxSpecies + kMaxSpecies * kMaxSpecies];
+  for (int i = threadIdx.x; i < K + K * K; i += blockDim.x) sh[i] = 0ull;
+  __syncthreads();
+  for (long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x; l < s.n_sites; l += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(l % s.n0);
+    const long long r = l / s.n0;
+    const int j = (int)(r % s.n1);
+    const int k = (int)(r / s.n1);
+    const int a = nat[l];
+    atomicAdd(&sh[a], 1ull);
+    const int ip = (i + 1 == s.n0) ? 0 : i + 1;
+    const int jp = (j + 1 == s.n1) ? 0 : j + 1;
+    int b = nat[ip + (long long)s.n0 * (j + (long long)s.n1 * k)];
+    atomicAdd(&sh[K + min(a, b) * K + max(a, b)], 1ull);
+    b = nat[i + (long long)s.n0 * (jp + (long long)s.n1 * k)];
+    atomicAdd(&sh[K + min(a, b) * K + max(a, b)], 1ull);
+    if (s.dim == 3) {
+      const int kp = (k + 1 == s.n2) ? 0 : k + 1;
+      b = nat[i + (long long)s.n0 * (j + (long long)s.n1 * kp)];
+      atomicAdd(&sh[K + min(a, b) * K + max(a, b)], 1ull);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < K + K * K; i += blockDim.x)
+    if (sh[i]) atomicAdd(reinterpret_cast<unsigned long long *>(out + i), sh[i]);
+}
+
+// values must be occupation indices 0..K-1
+__global__ void k_kstate_i32_to_sites(const int32_t *__restrict__ src, uint8_t *base, long long plane_stride,
+                                      NaturalShape s, int planar, int K, int *bad) {
+  const long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= s.n_sites) return;
+  const int v = src[l];
+  if (v < 0 || v >= K) atomicExch(bad, 1);
+  base[site_addr_of(s, l, planar, plane_stride)] = (uint8_t)v;
+}
+__global__ void k_kstate_sites_to_i32(const uint8_t *__restrict__ base, long long plane_stride, int32_t *dst,
+                                      NaturalShape s, int planar) {
+  const long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= s.n_sites) return;
+  dst[l] = base[site_addr_of(s, l, planar, plane_stride)];
+}
+
+// ---- OccLocation on the device (one chain): loc[cand][i] -> mol id, loc_size[cand],
+// mol_loc[mol] -> position in its list.  Every site is a mutating site of one asymmetric
+// unit orbit here, so mol id == l and candidate index == species index.
+struct KLocation {
+  int *loc;       // [K][n_sites]
+  int *loc_size;  // [K]
+  int *mol_loc;   // [n_sites]
+};
+// OccLocation::initialize (src/casm/monte/events/OccLocation.cc:68-114): lists are filled in
+// site order, which fixes the order choose_mol draws from -- sequential by definition
+__global__ void k_kstate_location_init(const uint8_t *__restrict__ nat, long long n_sites, int K, KLocation P) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  for (int s = 0; s < K; ++s) P.loc_size[s] = 0;
+  for (long long l = 0; l < n_sites; ++l) {
+    const int s = nat[l];
+    P.mol_loc[l] = P.loc_size[s];
+    P.loc[(long long)s * n_sites + P.loc_size[s]++] = (int)l;
+  }
+}
+
+struct KSerialArgs {
+  uint8_t *nat;  // [chain][n_sites]
+  NaturalShape shape;
+  const KStateTables *tabs;
+  MT64State *engines;
+  unsigned long long *n_accept;
+  KLocation loc;  // chain 0; chains are n_sites*(K+1)+K ints apart (see host)
+  long long loc_chain_stride;  // ints between chains, for loc / mol_loc / loc_size separately scaled on the host
+  long long n_passes;
+};
+
+// The reference's loop with the general proposal machinery, one thread per chain
+// (thread 0 of the CTA; the CTA produces the Mersenne stream in blocks, see
+// k_serial_reference).  Per step: choose_semigrand_canonical_swap draws
+// random_real(total number of possible events), choose_mol draws
+// random_int(size - 1) in the list of the swap's first candidate, and
+// metropolis_acceptance draws random_real(1.0) only when dPhi >= 0.
+__global__ void __launch_bounds__(kSerialThreads) k_kstate_serial(KSerialArgs A) {
+  __shared__ unsigned long long mt[312], out[312];
+  __shared__ int s_done;
+  const int chain = blockIdx.x;
+  const NaturalShape s = A.shape;
+  uint8_t *nat = A.nat + (long long)chain * s.n_sites;
+  const KStateTables *tab = A.tabs + chain;
+  MT64State *eng = A.engines + chain;
+  const int K = tab->K, z = tab->z;
+  int *loc = A.loc.loc + (long long)chain * K * s.n_sites;
+  int *loc_size = A.loc.loc_size + (long long)chain * kMaxSpecies;
+  int *mol_loc = A.loc.mol_loc + (long long)chain * s.n_sites;
+
+  for (int i = threadIdx.x; i < 312; i += blockDim.x) {
+    mt[i] = eng->x[i];
+    out[i] = mt64_temper(mt[i]);
+  }
+  if (threadIdx.x == 0) s_done = (A.n_passes <= 0);
+  __syncthreads();
+  int pos = eng->pos;
+  long long pass = 0, step = 0, l = 0;
+  unsigned long long n_acc = 0;
+  int phase = 0, from = 0, to = 0, entry = 0;
+
+  while (!s_done) {
+    if (pos >= 312) {
+      mt64_twist_block(mt);
+      for (int i = threadIdx.x; i < 312; i += blockDim.x) out[i] = mt64_temper(mt[i]);
+      pos = 0;
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      bool done = false;
+      while (pos < 312) {
+        const unsigned long long u = out[pos++];
+        if (phase == 0) {
+          // choose_semigrand_canonical_swap (OccEventProposal.hh:262-306): swaps in the order of
+          // make_semigrand_canonical_swaps (a outer, b inner, a != b); tsum accumulates cand_size(a)
+          double total = 0.0;
+          for (int a = 0; a < K; ++a)
+            for (int b = 0; b < K; ++b)
+              if (a != b) total = __dadd_rn(total, (double)loc_size[a]);
+          double r = __dmul_rn(__ull2double_rn(u), 5.42101086242752217003726400434970855712890625e-20);
+          if (r >= 1.0) r = 0.99999999999999988897769753748434595763683319091796875;
+          const double rand = __dadd_rn(__dmul_rn(r, __dsub_rn(total, 0.0)), 0.0);
+          double tsum = 0.0;
+          from = -1;
+          for (int a = 0; a < K && from < 0; ++a)
+            for (int b = 0; b < K; ++b) {
+              if (a == b) continue;
+              tsum = __dadd_rn(tsum, (double)loc_size[a]);
+              if (rand < tsum) {
+                from = a;
+                to = b;
+                break;
+              }
+            }
+          if (from < 0) {  // cannot happen (rand < total); keep the walk well-defined
+            from = K - 1;
+            to = K - 2;
+          }
+          phase = 1;
+          continue;
+        }
+        if (phase == 1) {
+          // choose_mol (OccLocation.hh:255-262): random_int(size - 1), libstdc++ Lemire with range = size
+          const unsigned long long range = (unsigned long long)loc_size[from];
+          const unsigned long long low = u * range;
+          if (low < range && low < (0ull - range) % range) continue;  // redraw
+          const long long pick = (long long)__umul64hi(u, range);
+          l = loc[(long long)from * s.n_sites + pick];
+          // neighbour configuration of site l
+          const int i = (int)(l % s.n0);
+          const long long rr = l / s.n0;
+          const int j = (int)(rr % s.n1);
+          const int k = (int)(rr / s.n1);
+          const long long base = (long long)s.n0 * (j + (long long)s.n1 * k);
+          const int ip = (i + 1 == s.n0) ? 0 : i + 1, im = (i == 0) ? s.n0 - 1 : i - 1;
+          const int jp = (j + 1 == s.n1) ? 0 : j + 1, jm = (j == 0) ? s.n1 - 1 : j - 1;
+          const long long kk = (long long)s.n1 * k;
+          int cfg = kstate_weight(nat[base + ip], z) + kstate_weight(nat[base + im], z) +
+                    kstate_weight(nat[i + (long long)s.n0 * (jp + kk)], z) + kstate_weight(nat[i + (long long)s.n0 * (jm + kk)], z);
+          if (s.dim == 3) {
+            const int kp = (k + 1 == s.n2) ? 0 : k + 1, km = (k == 0) ? s.n2 - 1 : k - 1;
+            cfg += kstate_weight(nat[i + (long long)s.n0 * (j + (long long)s.n1 * kp)], z) +
+                   kstate_weight(nat[i + (long long)s.n0 * (j + (long long)s.n1 * km)], z);
+          }
+          entry = kstate_entry(tab, from, to, cfg);
+          if (!(tab->dPhi[entry] < 0.0)) {
+            phase = 2;  // metropolis.hh:28-34: the uniform is drawn only when dPhi >= 0
+            continue;
+          }
+        } else {
+          double r = __dmul_rn(__ull2double_rn(u), 5.42101086242752217003726400434970855712890625e-20);
+          if (r >= 1.0) r = 0.99999999999999988897769753748434595763683319091796875;
+          r = __dadd_rn(__dmul_rn(r, __dsub_rn(1.0, 0.0)), 0.0);
+          if (!(r < tab->prob[entry])) from = -1;  // rejected
+        }
+        if (from >= 0) {
+          // OccLocation::apply (OccLocation.cc:263-282): swap-remove from the old list, append to the new
+          nat[l] = (uint8_t)to;
+          const int at = mol_loc[l];
+          const int back = loc[(long long)from * s.n_sites + loc_size[from] - 1];
+          loc[(long long)from * s.n_sites + at] = back;
+          mol_loc[back] = at;
+          loc_size[from]--;
+          mol_loc[l] = loc_size[to];
+          loc[(long long)to * s.n_sites + loc_size[to]++] = (int)l;
+          ++n_acc;
+        }
+        phase = 0;
+        if (++step == s.n_sites) {
+          step = 0;
+          if (++pass == A.n_passes) {
+            done = true;
+            break;
+          }
+        }
+      }
+      if (done) s_done = 1;
+    }
+    __syncthreads();
+    if (!s_done) pos = 312;
+  }
+  if (threadIdx.x == 0) {
+    eng->pos = pos;
+    A.n_accept[chain] += n_acc;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 312; i += blockDim.x) eng->x[i] = mt[i];
+}
+
+}  // namespace cmg

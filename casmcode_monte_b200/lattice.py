@@ -295,6 +295,74 @@ class IsingLatticeGPU:
         self._ck(self._lib.cmg_series_equilibration_all(self._ctx, quantity, count, abs_precision, _p(e, C.c_int), _p(n, C.c_int64)))
         return e.astype(bool), n
 
+    def series_check(self, quantities, abs_precisions, count=None, confidence=0.95, chain=0):
+        """One completion check on the device series (cmg_series_check): equilibration of every
+        requested component and, if all equilibrated, the statistics of the common tail."""
+        if count is None:
+            count = self.n_samples
+        n = len(quantities)
+        q = (C.c_int * n)(*[int(v) for v in quantities])
+        a = (C.c_double * n)(*[float(v) for v in abs_precisions])
+        is_eq = (C.c_int * n)()
+        n_eq = (C.c_int64 * n)()
+        n_stats = C.c_int64()
+        mean = (C.c_double * n)()
+        prec = (C.c_double * n)()
+        self._ck(self._lib.cmg_series_check(self._ctx, chain, n, q, a, int(count), float(confidence), is_eq, n_eq, C.byref(n_stats), mean, prec))
+        return {
+            "is_equilibrated": [bool(v) for v in is_eq],
+            "n_equil": [int(v) for v in n_eq],
+            "n_stats": int(n_stats.value),
+            "mean": [float(v) for v in mean],
+            "calculated_precision": [float(v) for v in prec],
+        }
+
+    # -- k-state model behind the general multi-species proposal tables (SURVEY 8f rank 3) --
+    def kstate_set_model(self, V):
+        """Switch to the k-state path: V is the symmetric K x K nearest-neighbour pair energy."""
+        V = np.ascontiguousarray(V, dtype=np.float64)
+        assert V.ndim == 2 and V.shape[0] == V.shape[1]
+        self.n_species = int(V.shape[0])
+        self._ck(self._lib.cmg_kstate_set_model(self._ctx, self.n_species, _p(V, C.c_double)))
+
+    def kstate_set_conditions(self, temperature, mu, chain=-1):
+        mu = np.ascontiguousarray(mu, dtype=np.float64)
+        assert mu.size == self.n_species
+        self._ck(self._lib.cmg_kstate_set_conditions(self._ctx, int(chain), float(temperature), _p(mu, C.c_double)))
+
+    def kstate_tables(self, chain=0):
+        K, z = self.n_species, 2 * self.dim
+        n = K * K * (z + 1) ** (K - 1)
+        dPhi, prob = np.zeros(n), np.zeros(n)
+        thr, never = np.zeros(n, dtype=np.uint32), np.zeros(n, dtype=np.uint8)
+        self._ck(self._lib.cmg_kstate_get_tables(self._ctx, chain, _p(dPhi, C.c_double), _p(prob, C.c_double), _p(thr, C.c_uint32), _p(never, C.c_uint8), n))
+        return dPhi, prob, thr, never
+
+    def kstate_upload(self, occ_index, chain=0):
+        occ = np.ascontiguousarray(occ_index, dtype=np.int32).ravel()
+        self._ck(self._lib.cmg_kstate_upload_occupation_i32(self._ctx, chain, _p(occ, C.c_int32), occ.size))
+
+    def kstate_download(self, chain=0):
+        out = np.empty(self.n_sites, dtype=np.int32)
+        self._ck(self._lib.cmg_kstate_download_occupation_i32(self._ctx, chain, _p(out, C.c_int32), out.size))
+        return out
+
+    def kstate_run_passes(self, n_passes, mode=MODE_CHECKERBOARD, sample_period=0):
+        self._ck(self._lib.cmg_kstate_run_passes(self._ctx, int(n_passes), int(mode), int(sample_period)))
+
+    def kstate_samples(self, chain=0):
+        """(counts [n_samples, K], bonds [n_samples, K, K]) of the sampled passes."""
+        n = C.c_int64()
+        self._ck(self._lib.cmg_kstate_n_samples(self._ctx, C.byref(n)))
+        K = self.n_species
+        counts = np.zeros((n.value, K), dtype=np.int64)
+        bonds = np.zeros((n.value, K, K), dtype=np.int64)
+        self._ck(self._lib.cmg_kstate_read_samples(self._ctx, chain, 0, n.value, _p(counts, C.c_int64), _p(bonds, C.c_int64)))
+        return counts, bonds
+
+    def kstate_clear_samples(self):
+        self._ck(self._lib.cmg_kstate_clear_samples(self._ctx))
+
     # -- slab plumbing --
     def slab_half_sweep(self, colour, pass_index, sample=False):
         self._ck(self._lib.cmg_slab_half_sweep(self._ctx, int(colour), int(pass_index), int(bool(sample))))

@@ -342,6 +342,44 @@ int cmg_conv_general_bijk_to_l(int device, const int64_t *T9, int64_t n_basis,
  * otherwise CMG_EUNSUPPORTED (callers then evaluate on the downloaded state). */
 int cmg_set_energy_form(cmg_context *ctx, int use_nlist);
 
+/* ---- k-state lattice model behind the general multi-species proposal tables ----
+ * The step on the INPUT side of the path: sites hold one of
+ * n_species <= 4 occupants (occupation index 0..K-1, one asymmetric-unit orbit,
+ * occ_index == species_index); nearest-neighbour pair energy V[a][b] (symmetric,
+ * row-major K x K) and one exchange potential per species:
+ *     potential = sum_<ij> V[o_i][o_j] - sum_i mu[o_i]
+ * (the Ising SGC potential, include/casm/monte/ising_cpp/basic_semigrand_canonical.hh:
+ * 165-191, is K = 2, V = [[-J, J], [J, -J]], mu = (0, mu)).  Setting the model switches
+ * the context to this path; seeds, counters, pass counter and streams are shared with
+ * the Ising entry points.
+ *   CMG_MODE_SERIAL_REFERENCE: the reference's general proposal machinery --
+ *     OccCandidateList (src/casm/monte/events/OccCandidate.cc:32-60),
+ *     make_semigrand_canonical_swaps (:136-157), OccLocation::initialize / choose_mol /
+ *     apply (src/casm/monte/events/OccLocation.cc:39-116, :253-283),
+ *     choose_semigrand_canonical_swap + propose_semigrand_canonical_event
+ *     (include/casm/monte/events/OccEventProposal.hh:260-348) -- and
+ *     metropolis_acceptance, on the mt19937_64 stream, n_sites steps per pass;
+ *     the OccLocation lists persist between calls until the occupation is changed
+ *     otherwise.
+ *   CMG_MODE_CHECKERBOARD: coloured half-sweeps; every site proposes one of its
+ *     K - 1 other species (word 0 of the site's Philox call) and accepts with the
+ *     32-bit uniform of word 1 against the table threshold.
+ * Tables hold, for entry (from * K + to) * n_cfg + cfg with cfg = sum_{s>=1} n_s *
+ * (z + 1)^(s - 1) (n_s neighbours of species s, z = 2 * dim): dPhi, exp(-dPhi*beta),
+ * the threshold and the never-accept flag.  Samples are integer sums: the number of
+ * sites of every species and the histogram of bond types bonds[a * K + b], a <= b. */
+int cmg_kstate_set_model(cmg_context *ctx, int n_species, const double *V);
+int cmg_kstate_set_conditions(cmg_context *ctx, int chain, double temperature, const double *mu);
+int cmg_kstate_get_tables(cmg_context *ctx, int chain, double *dPhi, double *prob, uint32_t *thr_m1,
+                          uint8_t *never, int64_t n_entries);
+int cmg_kstate_upload_occupation_i32(cmg_context *ctx, int chain, const int32_t *occ_index, int64_t n);
+int cmg_kstate_download_occupation_i32(cmg_context *ctx, int chain, int32_t *occ_index, int64_t n);
+int cmg_kstate_run_passes(cmg_context *ctx, int64_t n_passes, int mode, int64_t sample_period);
+int cmg_kstate_n_samples(cmg_context *ctx, int64_t *n_samples);
+int cmg_kstate_clear_samples(cmg_context *ctx);
+int cmg_kstate_read_samples(cmg_context *ctx, int chain, int64_t first, int64_t count,
+                            int64_t *counts, int64_t *bonds);
+
 /* ---- introspection for bench / tests ---------------------------------------- */
 /* number of kernels this context has launched since creation */
 int cmg_launch_count(const cmg_context *ctx, int64_t *n_launches);

@@ -8,6 +8,7 @@
 
 #include <sstream>
 
+#include "kstate_oracle.hh"
 #include "monte_oracle.hh"
 #include "run_management_oracle.hh"
 
@@ -709,4 +710,96 @@ PYBIND11_MODULE(_monte_oracle, m) {
           DiagonalConversions c{{n[0], n[1], n[2]}, nb};
           return c.bijk_to_l(b, i, j, k);
         });
+
+  // ---- k-state model driven by the general proposal machinery (kstate_oracle.hh) ----
+  auto kmodel = [](int dim, int K, f64arr V) {
+    if (K < 2 || K > kstate::kMaxSpecies) throw std::runtime_error("K must be 2..4");
+    kstate::KStateModel m;
+    m.dim = dim;
+    m.K = K;
+    auto v = V.unchecked<2>();
+    for (int a = 0; a < K; ++a)
+      for (int b = 0; b < K; ++b) m.V[a][b] = v(a, b);
+    return m;
+  };
+  auto kresult = [](kstate::KStateRunResult const &r, int K) {
+    py::dict d;
+    d["occupation"] = from_vec(r.occupation);
+    d["n_accept"] = r.n_accept;
+    d["n_reject"] = r.n_reject;
+    const py::ssize_t n = static_cast<py::ssize_t>(r.samples.size());
+    py::array_t<int64_t> counts({n, static_cast<py::ssize_t>(K)});
+    py::array_t<int64_t> bonds({n, static_cast<py::ssize_t>(K), static_cast<py::ssize_t>(K)});
+    for (py::ssize_t i = 0; i < n; ++i)
+      for (int a = 0; a < K; ++a) {
+        counts.mutable_at(i, a) = r.samples[i].count[a];
+        for (int b = 0; b < K; ++b) bonds.mutable_at(i, a, b) = r.samples[i].bonds[a][b];
+      }
+    d["counts"] = counts;
+    d["bonds"] = bonds;
+    return d;
+  };
+  m.def("kstate_serial_run",
+        [kmodel, kresult](std::vector<int> shape, i32arr occ, int K, f64arr V, double T, f64arr mu,
+                          Engine &engine, long n_passes, long sample_period) {
+          kstate::KStateModel model = kmodel(static_cast<int>(shape.size()), K, V);
+          std::vector<double> muv = to_dvec(mu);
+          muv.resize(kstate::kMaxSpecies, 0.0);
+          return kresult(kstate::kstate_serial_run(shape, to_vec(occ), model, T, muv.data(), engine.e, n_passes, sample_period), K);
+        },
+        py::arg("shape"), py::arg("occupation"), py::arg("K"), py::arg("V"), py::arg("temperature"), py::arg("mu"),
+        py::arg("engine"), py::arg("n_passes"), py::arg("sample_period") = 1);
+  m.def("kstate_checkerboard_run",
+        [kmodel, kresult](std::vector<int> shape, i32arr occ, int K, f64arr V, double T, f64arr mu, uint64_t seed,
+                          uint32_t chain, uint64_t pass0, long n_passes, long sample_period) {
+          kstate::KStateModel model = kmodel(static_cast<int>(shape.size()), K, V);
+          std::vector<double> muv = to_dvec(mu);
+          muv.resize(kstate::kMaxSpecies, 0.0);
+          return kresult(kstate::kstate_checkerboard_run(shape, to_vec(occ), model, T, muv.data(), seed, chain, pass0, n_passes, sample_period), K);
+        },
+        py::arg("shape"), py::arg("occupation"), py::arg("K"), py::arg("V"), py::arg("temperature"), py::arg("mu"),
+        py::arg("seed"), py::arg("chain") = 0, py::arg("pass0") = 0, py::arg("n_passes") = 1, py::arg("sample_period") = 1);
+  m.def("kstate_table", [kmodel](int dim, int K, f64arr V, double T, f64arr mu) {
+    kstate::KStateModel model = kmodel(dim, K, V);
+    std::vector<double> muv = to_dvec(mu);
+    muv.resize(kstate::kMaxSpecies, 0.0);
+    kstate::KStateTable t = kstate::make_kstate_table(model, T, muv.data());
+    py::dict d;
+    const py::ssize_t n = static_cast<py::ssize_t>(t.dPhi.size());
+    f64arr dPhi(n), prob(n);
+    py::array_t<uint32_t> thr(n);
+    py::array_t<uint8_t> never(n);
+    for (py::ssize_t i = 0; i < n; ++i) {
+      dPhi.mutable_at(i) = t.dPhi[i];
+      prob.mutable_at(i) = t.prob[i];
+      thr.mutable_at(i) = t.thr_m1[i];
+      never.mutable_at(i) = t.never[i];
+    }
+    d["n_cfg"] = t.n_cfg;
+    d["dPhi"] = dPhi;
+    d["prob"] = prob;
+    d["thr_m1"] = thr;
+    d["never"] = never;
+    return d;
+  });
+  m.def("kstate_potential", [kmodel](int dim, int K, f64arr V, f64arr mu, py::array_t<int64_t> counts, py::array_t<int64_t> bonds) {
+    kstate::KStateModel model = kmodel(dim, K, V);
+    std::vector<double> muv = to_dvec(mu);
+    muv.resize(kstate::kMaxSpecies, 0.0);
+    kstate::KStateSample s;
+    for (int a = 0; a < K; ++a) {
+      s.count[a] = counts.at(a);
+      for (int b = 0; b < K; ++b) s.bonds[a][b] = bonds.at(a, b);
+    }
+    return kstate::kstate_potential(model, muv.data(), s);
+  });
+  // the restated proposal machinery on its own (for the host-mirror tests)
+  m.def("kstate_swaps", [](int K) {
+    kstate::SimpleConversions convert{1, K};
+    kstate::OccCandidateList list(convert);
+    std::vector<std::array<long, 4>> out;
+    for (auto const &sw : kstate::make_semigrand_canonical_swaps(convert, list))
+      out.push_back({sw.cand_a.asym, sw.cand_a.species_index, sw.cand_b.asym, sw.cand_b.species_index});
+    return out;
+  });
 }

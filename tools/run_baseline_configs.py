@@ -144,35 +144,46 @@ def config2seq():
 
 
 def config3():
+    """BASELINE configs[2]: all six (T, mu), each run to abs precision 1e-4 on potential_energy and
+    param_composition (cap 2e4 passes) with the whole completion-check loop on the device series:
+    a check every 100 samples = one cmg_series_check call (equilibration scan of both series, then
+    autocorrelation-aware statistics of the common tail)."""
     shape = [512, 512, 512]
     n = 512**3
     out = []
-    for T, mu in [(4000.0, 0.0), (6500.0, 0.05)]:
-        lat = cm.IsingLatticeGPU(shape, J=J)
-        lat.set_conditions(T, mu)
-        lat.seed_philox(0xC0FFEE)
-        lat.fill(1)
-        target = 1e-4
-        check_begin, check_period, max_count = 100, 100, 20000
-        t0 = time.perf_counter()
-        n_pass = 0
-        done = False
-        res = None
-        while not done and n_pass < max_count:
-            lat.run_passes(check_begin if n_pass == 0 else check_period, cm.MODE_CHECKERBOARD, 1)
-            n_pass = lat.counters()[0]
-            # on-device equilibration + convergence statistics (no series leaves the GPU)
-            eq = [lat.series_equilibration(q, target) for q in (cm.Q_POTENTIAL_ENERGY, cm.Q_PARAM_COMPOSITION)]
-            if all(e[0] for e in eq):
-                n_eq = max(e[1] for e in eq)
-                st = [lat.series_stats(q, first=n_eq) for q in (cm.Q_POTENTIAL_ENERGY, cm.Q_PARAM_COMPOSITION)]
-                res = {"n_equil": n_eq, "potential_energy": st[0], "param_composition": st[1]}
-                done = all(s["calculated_precision"] < target for s in st)
-        lat.sync()
-        dt = time.perf_counter() - t0
-        out.append({"T": T, "mu": mu, "n_pass": n_pass, "converged": bool(done), "seconds": dt, "attempts_per_s": n * n_pass / dt, "kernel": lat.kernel_variant, "results": res})
-        lat.close()
-    return {"config": "3: 3D simple-cubic 512^3 SGC run to abs precision 1e-4 on potential_energy and param_composition with on-device sampling, equilibration and convergence statistics", "runs": out}
+    quantities = (cm.Q_POTENTIAL_ENERGY, cm.Q_PARAM_COMPOSITION)
+    for T in (4000.0, 5235.0, 6500.0):
+        for mu in (0.0, 0.05):
+            lat = cm.IsingLatticeGPU(shape, J=J)
+            lat.set_conditions(T, mu)
+            lat.seed_philox(0xC0FFEE)
+            lat.fill(1)
+            target = 1e-4
+            check_begin, check_period, max_count = 100, 100, 20000
+            lat.sync()
+            t0 = time.perf_counter()
+            n_pass, n_checks, t_checks = 0, 0, 0.0
+            done = False
+            res = None
+            while not done and n_pass < max_count:
+                lat.run_passes(check_begin if n_pass == 0 else check_period, cm.MODE_CHECKERBOARD, 1)
+                n_pass = lat.counters()[0]
+                tc0 = time.perf_counter()
+                res = lat.series_check(quantities, [target, target])
+                t_checks += time.perf_counter() - tc0
+                n_checks += 1
+                done = all(res["is_equilibrated"]) and res["n_stats"] > 0 and all(p < target for p in res["calculated_precision"])
+            lat.sync()
+            dt = time.perf_counter() - t0
+            st = [lat.series_stats(q, first=max(res["n_equil"])) for q in quantities] if all(res["is_equilibrated"]) else None
+            out.append({
+                "T": T, "mu": mu, "n_pass": n_pass, "converged": bool(done), "hit_cap": bool(not done), "n_checks": n_checks,
+                "seconds": dt, "seconds_in_checks": t_checks, "attempts_per_s_including_checks": n * n_pass / dt,
+                "kernel": lat.kernel_variant, "last_check": res,
+                "k_star": [s["k_star"] for s in st] if st else None,
+            })
+            lat.close()
+    return {"config": "3: 3D simple-cubic 512^3 SGC, T in {4000, 5235 (T_c), 6500} K x mu in {0, 0.05} eV, run to abs precision 1e-4 on potential_energy and param_composition (cap 2e4 passes) with on-device sampling, equilibration and convergence statistics", "runs": out}
 
 
 def config4():
