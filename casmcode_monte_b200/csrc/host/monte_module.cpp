@@ -13,6 +13,7 @@
 #include <pybind11/stl.h>
 #include <pybind11/stl_bind.h>
 
+#include "casm_monte_b200/events.hh"
 #include "casm_monte_b200/monte.hh"
 #include "casm_monte_b200/run_management.hh"
 
@@ -537,10 +538,105 @@ PYBIND11_MODULE(_monte_b200, m) {
   py::implicitly_convertible<py::list, std::vector<int>>();
   py::implicitly_convertible<py::tuple, std::vector<int>>();
   py::implicitly_convertible<py::array, std::vector<int>>();
+  py::class_<OccTransform>(m, "OccTransform")
+      .def(py::init<>())
+      .def_readwrite("linear_site_index", &OccTransform::l)
+      .def_readwrite("mol_id", &OccTransform::mol_id)
+      .def_readwrite("asym", &OccTransform::asym)
+      .def_readwrite("from_species", &OccTransform::from_species)
+      .def_readwrite("to_species", &OccTransform::to_species);
   py::class_<OccEvent>(m, "OccEvent")
       .def(py::init<>())
       .def_readwrite("linear_site_index", &OccEvent::linear_site_index)
-      .def_readwrite("new_occ", &OccEvent::new_occ);
+      .def_readwrite("new_occ", &OccEvent::new_occ)
+      .def_readwrite("occ_transform", &OccEvent::occ_transform);
+
+  // ---- general multi-species proposal machinery (include/casm_monte_b200/events.hh;
+  // python/src/monte_events.cpp:432-1100 of the reference) ----
+  py::class_<OccCandidate>(m, "OccCandidate")
+      .def(py::init<Index, Index>(), py::arg("asymmetric_unit_index"), py::arg("species_index"))
+      .def_readwrite("asymmetric_unit_index", &OccCandidate::asym)
+      .def_readwrite("species_index", &OccCandidate::species_index)
+      .def("is_valid", [](OccCandidate const &c, Conversions const &convert) { return is_valid(convert, c); })
+      .def("__lt__", [](OccCandidate const &a, OccCandidate const &b) { return a < b; })
+      .def("__eq__", [](OccCandidate const &a, OccCandidate const &b) { return a == b; })
+      .def("to_tuple", [](OccCandidate const &c) { return py::make_tuple(c.asym, c.species_index); });
+  py::class_<OccSwap>(m, "OccSwap")
+      .def(py::init<OccCandidate const &, OccCandidate const &>(), py::arg("first"), py::arg("second"))
+      .def_readwrite("first", &OccSwap::cand_a)
+      .def_readwrite("second", &OccSwap::cand_b)
+      .def("reverse", &OccSwap::reverse)
+      .def("sort", [](OccSwap &s) { s.sort(); })
+      .def("sorted", &OccSwap::sorted)
+      .def("is_valid", [](OccSwap const &s, Conversions const &convert) { return is_valid(convert, s); })
+      .def("__lt__", [](OccSwap const &a, OccSwap const &b) { return a < b; })
+      .def("__eq__", [](OccSwap const &a, OccSwap const &b) { return a == b; })
+      .def("to_tuple", [](OccSwap const &s) {
+        return py::make_tuple(s.cand_a.asym, s.cand_a.species_index, s.cand_b.asym, s.cand_b.species_index);
+      });
+  py::class_<OccCandidateList>(m, "OccCandidateList")
+      .def(py::init<Conversions const &>(), py::arg("convert"))
+      .def(py::init<std::vector<OccCandidate>, Conversions const &>(), py::arg("candidates"), py::arg("convert"))
+      .def("index", [](OccCandidateList const &l, OccCandidate const &c) { return l.index(c); })
+      .def("matching_index", [](OccCandidateList const &l, Index asym, Index species_index) { return l.index(asym, species_index); })
+      .def("__getitem__", [](OccCandidateList const &l, Index i) { return l[i]; })
+      .def("__len__", &OccCandidateList::size)
+      .def("__iter__", [](OccCandidateList const &l) { return py::make_iterator(l.begin(), l.end()); },
+           py::keep_alive<0, 1>());
+  m.def("is_allowed_canonical_swap", [](Conversions const &c, OccCandidate a, OccCandidate b) { return allowed_canonical_swap(c, a, b); });
+  m.def("make_canonical_swaps", &make_canonical_swaps, py::arg("convert"), py::arg("occ_candidate_list"));
+  m.def("is_allowed_semigrand_canonical_swap", [](Conversions const &c, OccCandidate a, OccCandidate b) { return allowed_semigrand_canonical_swap(c, a, b); });
+  m.def("make_semigrand_canonical_swaps", &make_semigrand_canonical_swaps, py::arg("convert"), py::arg("occ_candidate_list"));
+  m.def("get_n_allowed_per_unitcell", &get_n_allowed_per_unitcell, py::arg("convert"), py::arg("semigrand_canonical_swaps"));
+  py::class_<Mol>(m, "Mol")
+      .def(py::init<>())
+      .def_readwrite("id", &Mol::id)
+      .def_readwrite("linear_site_index", &Mol::l)
+      .def_readwrite("asymmetric_unit_index", &Mol::asym)
+      .def_readwrite("species_index", &Mol::species_index)
+      .def_readwrite("mol_location_index", &Mol::loc);
+  py::class_<OccLocation>(m, "OccLocation")
+      .def(py::init<Conversions const &, OccCandidateList const &, bool, bool, bool>(), py::arg("convert"),
+           py::arg("candidate_list"), py::arg("update_atoms") = false, py::arg("track_unique_atoms") = false,
+           py::arg("save_atom_info") = false, py::keep_alive<1, 2>(), py::keep_alive<1, 3>())
+      .def("initialize", [](OccLocation &o, py::object occupation) { o.initialize(to_ivec(occupation)); }, py::arg("occupation"))
+      .def("apply",
+           [](OccLocation &o, OccEvent const &e, py::array_t<int32_t, py::array::c_style> occupation) {
+             // the caller's array is updated in place, as the reference's Eigen::Ref argument is
+             std::vector<int> occ(occupation.data(), occupation.data() + occupation.size());
+             o.apply(e, occ);
+             std::copy(occ.begin(), occ.end(), occupation.mutable_data());
+           },
+           py::arg("e"), py::arg("occupation"))
+      .def("choose_mol", [](OccLocation const &o, OccCandidate const &c, RandomNumberGenerator<> &rng) { return o.choose_mol(c, rng); },
+           py::arg("cand"), py::arg("random_number_generator"))
+      .def("choose_mol_by_candidate_index", [](OccLocation const &o, Index i, RandomNumberGenerator<> &rng) { return o.choose_mol(i, rng); },
+           py::arg("cand_index"), py::arg("random_number_generator"))
+      .def("mol_size", &OccLocation::mol_size)
+      .def("mol", [](OccLocation const &o, Index id) { return o.mol(id); })
+      .def("cand_size", [](OccLocation const &o, OccCandidate const &c) { return o.cand_size(c); })
+      .def("cand_size_by_candidate_index", [](OccLocation const &o, Index i) { return o.cand_size(i); })
+      .def("mol_id", [](OccLocation const &o, OccCandidate const &c, Index loc) { return o.mol_id(c, loc); })
+      .def("mol_id_by_candidate_index", [](OccLocation const &o, Index i, Index loc) { return o.mol_id(i, loc); })
+      .def("linear_site_index_to_mol_id", &OccLocation::l_to_mol_id);
+  m.def("choose_canonical_swap",
+        [](OccLocation const &o, std::vector<OccSwap> const &swaps, RandomNumberGenerator<> &rng) { return choose_canonical_swap(o, swaps, rng); },
+        py::arg("occ_location"), py::arg("canonical_swaps"), py::arg("random_number_generator"));
+  m.def("propose_canonical_event_from_swap",
+        [](OccEvent &e, OccLocation const &o, OccSwap const &swap, RandomNumberGenerator<> &rng) { propose_canonical_event_from_swap(e, o, swap, rng); },
+        py::arg("occ_event"), py::arg("occ_location"), py::arg("swap"), py::arg("random_number_generator"));
+  m.def("propose_canonical_event",
+        [](OccEvent &e, OccLocation const &o, std::vector<OccSwap> const &swaps, RandomNumberGenerator<> &rng) { propose_canonical_event(e, o, swaps, rng); },
+        py::arg("occ_event"), py::arg("occ_location"), py::arg("canonical_swaps"), py::arg("random_number_generator"));
+  m.def("choose_semigrand_canonical_swap",
+        [](OccLocation const &o, std::vector<OccSwap> const &swaps, RandomNumberGenerator<> &rng) { return choose_semigrand_canonical_swap(o, swaps, rng); },
+        py::arg("occ_location"), py::arg("semigrand_canonical_swaps"), py::arg("random_number_generator"));
+  m.def("propose_semigrand_canonical_event_from_swap",
+        [](OccEvent &e, OccLocation const &o, OccSwap const &swap, RandomNumberGenerator<> &rng) { propose_semigrand_canonical_event_from_swap(e, o, swap, rng); },
+        py::arg("occ_event"), py::arg("occ_location"), py::arg("swap"), py::arg("random_number_generator"));
+  m.def("propose_semigrand_canonical_event",
+        [](OccEvent &e, OccLocation const &o, std::vector<OccSwap> const &swaps, RandomNumberGenerator<> &rng) { propose_semigrand_canonical_event(e, o, swaps, rng); },
+        py::arg("occ_event"), py::arg("occ_location"), py::arg("semigrand_canonical_swaps"), py::arg("random_number_generator"));
 
   // events.Conversions (python/src/monte_events.cpp:85-430).  libcasm.xtal is absent, so
   // the prim is given as arrays: occ_dof (names per sublattice), the 3 x 3

@@ -193,11 +193,21 @@ inline void words_to_engine(uint64_t const *words312, int pos, default_engine_ty
 }
 
 // ---------------------------------------------------------------------------
-// OccEvent (include/casm/monte/events/OccEvent.hh:57-73), Ising subset
+// OccEvent (include/casm/monte/events/OccEvent.hh:33-73).  atom_traj (species
+// trajectories for kinetic Monte Carlo) is out of scope.
 // ---------------------------------------------------------------------------
+struct OccTransform {
+  Index l = 0;             ///< Config occupant that is being transformed
+  Index mol_id = 0;        ///< Location in OccLocation.m_mol
+  Index asym = 0;          ///< Asym index
+  Index from_species = 0;  ///< Species index before transformation
+  Index to_species = 0;    ///< Species index after transformation
+};
 struct OccEvent {
   std::vector<Index> linear_site_index;
   std::vector<int> new_occ;
+  /// used to update the occupant tracking of OccLocation (events.hh)
+  std::vector<OccTransform> occ_transform;
 };
 
 // ---------------------------------------------------------------------------
@@ -215,6 +225,7 @@ class IsingConfiguration {
     for (int s : shape) n *= static_cast<Index>(s);
     m_occupation.assign(static_cast<size_t>(n), fill_value);
     n_sites = n_variable_sites = n_unitcells = n;
+    if (fill_value == 1 || fill_value == -1) m_uniform = fill_value;  // filled on the device, not uploaded
   }
   // deep copy of the host mirror; the copy gets its own device lattice on demand
   IsingConfiguration(IsingConfiguration const &o)
@@ -222,6 +233,7 @@ class IsingConfiguration {
         n_unitcells(o.n_unitcells), device_index(o.device_index) {
     o.pull();
     m_occupation = o.m_occupation;
+    m_uniform = o.m_uniform;
   }
   IsingConfiguration &operator=(IsingConfiguration const &o) {
     if (this == &o) return *this;
@@ -232,6 +244,7 @@ class IsingConfiguration {
     n_unitcells = o.n_unitcells;
     device_index = o.device_index;
     m_occupation = o.m_occupation;
+    m_uniform = o.m_uniform;
     m_dev.reset();
     m_host_valid = true;
     m_dev_valid = false;
@@ -250,6 +263,7 @@ class IsingConfiguration {
     if (m_occupation.size() != occupation.size())
       throw std::runtime_error("Error in set_occupation: size mismatch");
     m_occupation = occupation;
+    m_uniform = 0;
     m_host_valid = true;
     m_dev_valid = false;
   }
@@ -260,6 +274,7 @@ class IsingConfiguration {
   void set_occ(Index l, int new_occ) {
     pull();
     m_occupation[l] = new_occ;
+    m_uniform = 0;
     if (m_dev && m_dev_valid) m_dev->check(cmg_set_occ(m_dev->ctx(), 0, l, new_occ));
   }
   Index within(Index index, int dim) const {
@@ -296,22 +311,28 @@ class IsingConfiguration {
     }
     if (!m_dev_valid) {
       if (m_occupation.empty()) throw std::runtime_error("empty configuration");
-      std::vector<int32_t> tmp(m_occupation.begin(), m_occupation.end());
-      m_dev->check(cmg_upload_occupation_i32(m_dev->ctx(), 0, tmp.data(),
-                                             static_cast<int64_t>(tmp.size())));
+      static_assert(sizeof(int) == sizeof(int32_t), "the host mirror is the reference's VectorXi");
+      if (m_uniform != 0) {
+        // a freshly constructed configuration: fill on the device instead of copying 4 B per site
+        m_dev->check(cmg_fill_occupation(m_dev->ctx(), 0, m_uniform));
+      } else {
+        m_dev->check(cmg_upload_occupation_i32(m_dev->ctx(), 0, reinterpret_cast<int32_t const *>(m_occupation.data()),
+                                               static_cast<int64_t>(m_occupation.size())));
+      }
       m_dev_valid = true;
     }
     return *m_dev;
   }
   /// the device copy was modified by a kernel: the host mirror is stale
-  void mark_device_modified() const { m_host_valid = false; }
-  /// refresh the host mirror from the device if needed
+  void mark_device_modified() const {
+    m_host_valid = false;
+    m_uniform = 0;
+  }
+  /// refresh the host mirror from the device if needed (every accessor does)
   void pull() const {
     if (m_host_valid) return;
-    std::vector<int32_t> tmp(m_occupation.size());
-    m_dev->check(cmg_download_occupation_i32(m_dev->ctx(), 0, tmp.data(),
-                                             static_cast<int64_t>(tmp.size())));
-    std::copy(tmp.begin(), tmp.end(), m_occupation.begin());
+    m_dev->check(cmg_download_occupation_i32(m_dev->ctx(), 0, reinterpret_cast<int32_t *>(m_occupation.data()),
+                                             static_cast<int64_t>(m_occupation.size())));
     m_host_valid = true;
   }
 
@@ -320,6 +341,7 @@ class IsingConfiguration {
   mutable std::shared_ptr<DeviceLattice> m_dev;
   mutable bool m_host_valid = true;
   mutable bool m_dev_valid = false;
+  mutable int m_uniform = 0;  // +1 / -1: every site holds this value (as constructed); 0: unknown
 };
 
 // model.hh:141-157
@@ -1650,10 +1672,11 @@ class SemiGrandCanonicalCalculator {
     fetch_device_samples();
     data->completion_check.set_device_series(nullptr);
 
-    // ### finish: counters, final occupation visible in the caller's state,
-    // engine advanced exactly as the reference would leave it (serial mode)
+    // ### finish: counters; the final occupation is visible in the caller's state through
+    // every accessor of its configuration (the host mirror is refreshed on first use, 4 B
+    // per site are not moved unless somebody looks); engine advanced exactly as the
+    // reference would leave it (serial mode)
     refresh_counters();
-    config.pull();
     if (mode == CMG_MODE_SERIAL_REFERENCE) {
       uint64_t words[312];
       int pos = 0;

@@ -793,6 +793,25 @@ PYBIND11_MODULE(_monte_oracle, m) {
     }
     return kstate::kstate_potential(model, muv.data(), s);
   });
+  // propose + apply n semi-grand canonical events (every event accepted) with the restated
+  // OccLocation: [(linear_site_index, new_occ)] and the final occupation
+  m.def("kstate_propose_sequence", [](int K, i32arr occ_in, Engine &engine, long n) {
+    std::vector<int> occ = to_vec(occ_in);
+    kstate::SimpleConversions convert{static_cast<Index>(occ.size()), K};
+    kstate::OccCandidateList list(convert);
+    std::vector<kstate::OccSwap> swaps = kstate::make_semigrand_canonical_swaps(convert, list);
+    kstate::OccLocation loc(convert, list);
+    loc.initialize(occ);
+    RandomNumberGenerator<std::mt19937_64> rng(engine.e);
+    kstate::KOccEvent e;
+    std::vector<std::pair<long, int>> out;
+    for (long i = 0; i < n; ++i) {
+      kstate::propose_semigrand_canonical_event(e, loc, swaps, rng);
+      out.emplace_back(e.linear_site_index[0], e.new_occ[0]);
+      loc.apply(e, occ);
+    }
+    return py::make_tuple(out, from_vec(occ));
+  });
   // the restated proposal machinery on its own (for the host-mirror tests)
   m.def("kstate_swaps", [](int K) {
     kstate::SimpleConversions convert{1, K};
