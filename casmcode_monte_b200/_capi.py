@@ -84,6 +84,8 @@ SIGNATURES = {
     "cmg_series_equilibration": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int64, C.c_double, _intp, _i64p]),
     "cmg_series_stats_all": (C.c_int, [_ctx, C.c_int, _i64p, C.c_int64, C.c_double, _f64p, _f64p, _f64p, _i64p]),
     "cmg_series_equilibration_all": (C.c_int, [_ctx, C.c_int, C.c_int64, C.c_double, _intp, _i64p]),
+    "cmg_mark": (C.c_int, [_ctx]),
+    "cmg_rollback": (C.c_int, [_ctx]),
     "cmg_series_check": (C.c_int, [_ctx, C.c_int, C.c_int, _intp, _f64p, C.c_int64, C.c_double, _intp, _i64p, _i64p, _f64p, _f64p]),
     "cmg_host_series_stats": (C.c_int, [C.c_int, _f64p, C.c_int64, C.c_double, _f64p, _f64p, _f64p, _i64p]),
     "cmg_host_series_equilibration": (C.c_int, [C.c_int, _f64p, C.c_int64, C.c_double, _intp, _i64p]),

@@ -112,6 +112,16 @@ struct cmg_context {
   bool bulk_attr_set = false;
   int js_auto[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // cached strip length per kernel variant
   size_t smem_optin = 0;
+  // cmg_mark / cmg_rollback: a restore point (planes, acceptance counters, host counters) and
+  // a second, higher-priority stream on which the statistics of the samples taken up to
+  // the mark are evaluated while the main stream already sweeps on
+  cudaStream_t aux = nullptr;
+  cudaEvent_t ev_mark = nullptr;
+  uint8_t *d_shadow = nullptr;
+  unsigned long long *d_shadow_accept = nullptr;
+  bool mark_valid = false;
+  unsigned long long mark_h_pass = 0;
+  long long mark_n_pass = 0, mark_n_samples = 0;
   // k-state model; K == 0: the context runs the Ising path
   int ks_K = 0;
   double ks_V[kMaxSpecies * kMaxSpecies] = {0};
@@ -435,6 +445,10 @@ int cmg_destroy(cmg_context *c) {
   cudaFree(c->d_ring_mailbox);
   cudaFree(c->d_lines);
   cudaFree(c->d_error);
+  cudaFree(c->d_shadow);
+  cudaFree(c->d_shadow_accept);
+  if (c->aux) cudaStreamDestroy(c->aux);
+  if (c->ev_mark) cudaEventDestroy(c->ev_mark);
   cudaFree(c->d_ktabs);
   cudaFree(c->d_kseries);
   cudaFree(c->d_kloc);
@@ -994,6 +1008,7 @@ static int ensure_series(cmg_context *c, long long need) {
   while (cap < need) cap *= 2;
   long long *nb = nullptr;
   const size_t slot_bytes = sizeof(long long) * 2 * (size_t)c->n_chains;
+  if (c->aux) CU(c, cudaStreamSynchronize(c->aux));  // nobody reads the old series any more
   CU(c, cudaMalloc(&nb, slot_bytes * (size_t)cap));
   CU(c, cudaMemsetAsync(nb, 0, slot_bytes * (size_t)cap, c->stream));
   if (c->d_series && c->n_samples > 0)
@@ -1091,7 +1106,11 @@ static RingPlan plan_ring(const cmg_context *c) {
   const long long h = c->shape[0] / 2, n1 = c->shape[1], V = h / 16;
   if (V > 256 || 512 % V != 0) return r;  // at least two column groups per CTA
   const long long Q = 512 / V;
+  // one SM is left free when that costs nothing (4096 / 147 and 4096 / 148 both round up to 28
+  // columns per tile): the statistics kernels of cmg_mark / cmg_series_check run there while
+  // the cooperative kernel, whose CTAs fill the register file of their SMs, sweeps on
   long long n_tiles = c->sm_count / c->n_chains;
+  if (c->n_chains == 1 && n_tiles > 2 && (n1 + n_tiles - 2) / (n_tiles - 1) == (n1 + n_tiles - 1) / n_tiles) n_tiles -= 1;
   n_tiles = std::min(n_tiles, n1 / (2 * Q));
   if (n_tiles < 2) return r;
   const long long w_max = (n1 + n_tiles - 1) / n_tiles;
@@ -1989,15 +2008,7 @@ static int run_equil_jobs(cmg_context *c, cudaStream_t stream, const std::vector
   CU(c, scratch_alloc(&de, sizeof(int) * n, stream));
   CU(c, scratch_alloc(&dn, sizeof(long long) * n, stream));
   CU(c, cudaMemcpyAsync(dj, jobs.data(), sizeof(SeriesJob) * n, cudaMemcpyHostToDevice, stream));
-  // the series is staged in shared memory when it fits (up to ~24 k samples)
-  static const long long kEquilSmemDoubles = 24 * 1024;
-  cudaFuncSetAttribute(k_series_equilibration, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       (int)(kEquilSmemDoubles * sizeof(double)));  // per device: set every time
-  long long n_max = 0;
-  for (const SeriesJob &j : jobs) n_max = std::max<long long>(n_max, j.n);
-  const long long stage = n_max <= kEquilSmemDoubles ? n_max : 0;  // 0: read global memory
-  k_series_equilibration<<<n, kEquilThreads, (size_t)stage * sizeof(double), stream>>>(
-      dj, n, prec, de, dn, stage);
+  k_series_equilibration<<<n, kEquilThreads, 0, stream>>>(dj, n, prec, de, dn);
   if (c) ++c->launches;
   CU(c, cudaGetLastError());
   std::vector<int> he(n);
@@ -2087,6 +2098,55 @@ int cmg_series_equilibration_all(cmg_context *c, int quantity, int64_t count, do
   return run_equil_jobs(c, c->stream, jobs, abs_precision, is_equilibrated, n_equil);
 }
 
+int cmg_mark(cmg_context *c) {
+  NEED(c);
+  if (!c->planar || c->slab || c->ks_K) return fail(c, CMG_EUNSUPPORTED, "cmg_mark: checkerboard contexts only");
+  if (!c->aux) {
+    int lo = 0, hi = 0;
+    CU(c, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CU(c, cudaStreamCreateWithPriority(&c->aux, cudaStreamNonBlocking, hi));
+    CU(c, cudaEventCreateWithFlags(&c->ev_mark, cudaEventDisableTiming));
+  }
+  if (!c->d_shadow) {
+    CU(c, cudaMalloc(&c->d_shadow, (size_t)c->chain_stride * c->n_chains));
+    CU(c, cudaMalloc(&c->d_shadow_accept, sizeof(unsigned long long) * c->n_chains));
+  }
+  // everything enqueued so far is "before the mark": the aux stream waits for it, the copy
+  // of the state follows it, whatever is enqueued next can be undone
+  CU(c, cudaEventRecord(c->ev_mark, c->stream));
+  CU(c, cudaStreamWaitEvent(c->aux, c->ev_mark, 0));
+  CU(c, cudaMemcpyAsync(c->d_shadow, c->d_planes, (size_t)c->chain_stride * c->n_chains,
+                        cudaMemcpyDeviceToDevice, c->stream));
+  CU(c, cudaMemcpyAsync(c->d_shadow_accept, c->d_n_accept, sizeof(unsigned long long) * c->n_chains,
+                        cudaMemcpyDeviceToDevice, c->stream));
+  c->mark_h_pass = c->h_pass;
+  c->mark_n_pass = c->n_pass;
+  c->mark_n_samples = c->n_samples;
+  c->mark_valid = true;
+  return CMG_OK;
+}
+
+int cmg_rollback(cmg_context *c) {
+  NEED(c);
+  if (!c->mark_valid) return fail(c, CMG_ESTATE, "cmg_rollback: no mark");
+  CU(c, cudaMemcpyAsync(c->d_planes, c->d_shadow, (size_t)c->chain_stride * c->n_chains,
+                        cudaMemcpyDeviceToDevice, c->stream));
+  CU(c, cudaMemcpyAsync(c->d_n_accept, c->d_shadow_accept, sizeof(unsigned long long) * c->n_chains,
+                        cudaMemcpyDeviceToDevice, c->stream));
+  // sample slots are accumulated into: the ones taken after the mark go back to zero
+  if (c->n_samples > c->mark_n_samples && c->d_series)
+    CU(c, cudaMemsetAsync(c->d_series + c->mark_n_samples * 2 * c->n_chains, 0,
+                          sizeof(long long) * 2 * (size_t)c->n_chains * (size_t)(c->n_samples - c->mark_n_samples),
+                          c->stream));
+  c->h_pass = c->mark_h_pass;
+  c->n_pass = c->mark_n_pass;
+  c->n_samples = c->mark_n_samples;
+  if (c->dbl_valid > c->n_samples) c->dbl_valid = c->n_samples;
+  c->nat_is_current = false;
+  c->mark_valid = false;
+  return CMG_OK;
+}
+
 int cmg_series_check(cmg_context *c, int chain, int n_components, const int *quantity,
                      const double *abs_precision, int64_t count, double confidence,
                      int *is_equilibrated, int64_t *n_equil, int64_t *n_stats, double *mean,
@@ -2100,6 +2160,26 @@ int cmg_series_check(cmg_context *c, int chain, int n_components, const int *qua
       return fail(c, CMG_EINVAL, "bad quantity or precision");
   if (count <= 0) return fail(c, CMG_EINVAL, "Error in equilibration_check: observations.size()==0");
   if (count > c->n_samples) return fail(c, CMG_EINVAL, "sample range outside the series");
+  // Samples up to a mark (cmg_mark) are complete once the work before the mark is: their
+  // check runs on the second stream, next to whatever the main stream has been given since.
+  struct StreamView {
+    cmg_context *c;
+    cudaStream_t stream;
+    long long n_samples;
+    bool on;
+    StreamView(cmg_context *ctx, bool use_aux) : c(ctx), stream(ctx->stream), n_samples(ctx->n_samples), on(use_aux) {
+      if (on) {
+        c->stream = c->aux;
+        c->n_samples = c->mark_n_samples;
+      }
+    }
+    ~StreamView() {
+      if (on) {
+        c->stream = stream;
+        c->n_samples = n_samples;
+      }
+    }
+  } view_guard(c, c->mark_valid && c->aux && count <= c->mark_n_samples && c->n_samples > c->mark_n_samples);
   int rc = ensure_doubles(c);
   if (rc) return rc;
   const int n = n_components;
@@ -2118,27 +2198,31 @@ int cmg_series_check(cmg_context *c, int chain, int n_components, const int *qua
   Host *d = nullptr;
   CU(c, scratch_alloc(&d, sizeof(Host), c->stream));
   CU(c, cudaMemcpyAsync(d, &h, sizeof(Host), cudaMemcpyHostToDevice, c->stream));
-  static const long long kEquilSmemDoubles = 24 * 1024;
-  cudaFuncSetAttribute(k_series_equilibration, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       (int)(kEquilSmemDoubles * sizeof(double)));
-  const long long stage = count <= kEquilSmemDoubles ? count : 0;
-  // the kernel takes one precision: one launch (a CTA per series, side by side) when the
-  // requested precisions are equal, as they usually are; one launch per series otherwise
+  // The kernel takes one precision: one launch (a CTA per series, side by side) when the
+  // requested precisions are equal, as they usually are; one launch per series otherwise.
+  // Next to a sweep (the view above is on) the series are taken one CTA after the other, so
+  // that the check never holds more than one SM: a cooperative sweep kernel needs all the
+  // others at once.
   bool same = true;
   for (int i = 1; i < n; ++i) same = same && abs_precision[i] == abs_precision[0];
-  if (same) {
-    k_series_equilibration<<<n, kEquilThreads, (size_t)stage * sizeof(double), c->stream>>>(
-        d->eq, n, abs_precision[0], d->is_eq, d->n_eq, stage);
+  const bool one_at_a_time = view_guard.on;
+  if (same && !one_at_a_time) {
+    k_series_equilibration<<<n, kEquilThreads, 0, c->stream>>>(d->eq, n, abs_precision[0], d->is_eq, d->n_eq);
     ++c->launches;
   } else {
     for (int j = 0; j < n; ++j) {
-      k_series_equilibration<<<1, kEquilThreads, (size_t)stage * sizeof(double), c->stream>>>(
-          d->eq + j, 1, abs_precision[j], d->is_eq + j, d->n_eq + j, stage);
+      k_series_equilibration<<<1, kEquilThreads, 0, c->stream>>>(d->eq + j, 1, abs_precision[j], d->is_eq + j,
+                                                                 d->n_eq + j);
       ++c->launches;
     }
   }
   k_make_tail_jobs<<<1, 32, 0, c->stream>>>(d->eq, n, d->is_eq, d->n_eq, d->st, &d->n_stats);
-  k_series_stats<<<n, 256, 0, c->stream>>>(d->st, z_confidence(confidence), d->out4, d->k_star);
+  if (!one_at_a_time) {
+    k_series_stats<<<n, 256, 0, c->stream>>>(d->st, z_confidence(confidence), d->out4, d->k_star);
+  } else {
+    for (int j = 0; j < n; ++j)
+      k_series_stats<<<1, 256, 0, c->stream>>>(d->st + j, z_confidence(confidence), d->out4 + 4 * j, d->k_star + j);
+  }
   c->launches += 2;
   CU(c, cudaGetLastError());
   CU(c, cudaMemcpyAsync(&h, d, sizeof(Host), cudaMemcpyDeviceToHost, c->stream));

@@ -2462,28 +2462,31 @@ __global__ void k_apply_weight_factor(const double *__restrict__ x, const double
 }
 
 // Equilibration check (src/casm/monte/checks/EquilibrationCheck.cc:50-117).  One CTA
-// per series.  The series is staged into shared memory when it fits, "all samples
-// equal" is decided in parallel and the two initial partition sums are block
-// reductions (the reference takes them with Eigen's .sum(), whose order is not a
-// sequential one either).  The scan that follows is a floating-point recurrence
-// on the running sums (:93-103) and keeps the reference's order: thread 0 walks it
-// in chunks, recording (sum1, sum2) before every step, and the other threads
-// evaluate the loop condition of the recorded steps -- two double divisions each,
-// which dominated when one thread did everything (1.7 ms per check of 10^4 samples
-// that never equilibrate) -- and find the step at which the reference's loop stops.
+// per series.  "All samples equal" is decided in parallel and the two initial
+// partition sums are block reductions (the reference takes them with Eigen's
+// .sum(), whose order is not a sequential one either).  The scan that follows is a
+// floating-point recurrence on the running sums (:93-103) and keeps the reference's
+// order: it is walked in chunks; all threads first bring the two runs of samples the
+// chunk consumes into shared memory, thread 0 walks the recurrence recording
+// (sum1, sum2) before every step, and all threads then evaluate the loop condition
+// of the recorded steps -- two double divisions each, which dominated when one
+// thread did everything (1.7 ms per check of 10^4 samples that never equilibrate,
+// 0.44 ms now) -- and find the step at which the reference's loop stops.  Shared
+// memory is a few KiB whatever the series length, so the kernel runs next to a
+// sweep kernel (see cmg_mark).
 constexpr int kEquilThreads = 256;
 constexpr int kEquilChunk = 512;
 __global__ void __launch_bounds__(kEquilThreads) k_series_equilibration(const SeriesJob *jobs,
                                                                         int n_jobs, double prec,
-                                                                        int *is_eq, long long *n_eq,
-                                                                        long long smem_doubles) {
-  extern __shared__ __align__(16) double eq_smem[];
+                                                                        int *is_eq, long long *n_eq) {
   __shared__ int s_differs;
   __shared__ int s_stop;  // first step of the chunk at which the loop condition is false
   __shared__ double s_sum1[kEquilChunk], s_sum2[kEquilChunk], s_red[8];
+  __shared__ double s_x1[kEquilChunk], s_x2[kEquilChunk / 2 + 1];  // x[start1 + k], x[start2 + m]
+  __shared__ double s_end1, s_end2;
   const int jb = blockIdx.x;
   if (jb >= n_jobs) return;
-  const double *xg = jobs[jb].x;
+  const double *x = jobs[jb].x;
   const long long N = jobs[jb].n;
   if (N <= 0) {
     if (threadIdx.x == 0) {
@@ -2494,17 +2497,23 @@ __global__ void __launch_bounds__(kEquilThreads) k_series_equilibration(const Se
   }
   if (threadIdx.x == 0) s_differs = 0;
   __syncthreads();
-  const bool staged = N <= smem_doubles;
-  const double x0 = xg[0];
+  const double x0 = x[0];
   const double eps = (x0 == 0.0) ? 1e-8 : fabs(x0) * 1e-8;
+  const bool even0 = ((N % 2) == 0);
+  const long long start2_0 = even0 ? N / 2 : (N / 2) + 1;
   bool differs = false;
+  double p1 = 0.0, p2 = 0.0;
   for (long long i = threadIdx.x; i < N; i += kEquilThreads) {
-    const double v = xg[i];
-    if (staged) eq_smem[i] = v;
+    const double v = x[i];
     differs |= fabs(v - x0) > eps;
+    if (i < start2_0)
+      p1 += v;
+    else
+      p2 += v;
   }
   if (differs) s_differs = 1;
-  __syncthreads();
+  double sum1 = block_sum_256(p1, s_red);
+  double sum2 = block_sum_256(p2, s_red);
   if (!s_differs) {  // all samples (approximately) equal
     if (threadIdx.x == 0) {
       is_eq[jb] = 1;
@@ -2512,34 +2521,29 @@ __global__ void __launch_bounds__(kEquilThreads) k_series_equilibration(const Se
     }
     return;
   }
-  const double *x = staged ? eq_smem : xg;
-  const bool even0 = ((N % 2) == 0);
-  const long long start2_0 = even0 ? N / 2 : (N / 2) + 1;
-  double p = 0.0;
-  for (long long i = threadIdx.x; i < start2_0; i += kEquilThreads) p += x[i];
-  double sum1 = block_sum_256(p, s_red);
-  p = 0.0;
-  for (long long i = start2_0 + threadIdx.x; i < N; i += kEquilThreads) p += x[i];
-  double sum2 = block_sum_256(p, s_red);
 
   // state before the first step of the chunk (kept by every thread; thread 0 advances the sums)
   long long start1 = 0, start2 = start2_0;
   const bool is_even = even0;  // parity of the chunk's first step (chunks hold an even number of steps)
-  __shared__ double s_end1, s_end2;
   for (;;) {
+    // the samples this chunk can consume: x[start1 .. start1 + chunk) and x[start2 .. start2 + chunk/2]
+    for (int k = threadIdx.x; k < kEquilChunk; k += kEquilThreads) s_x1[k] = (start1 + k < N) ? x[start1 + k] : 0.0;
+    for (int k = threadIdx.x; k < kEquilChunk / 2 + 1; k += kEquilThreads) s_x2[k] = (start2 + k < N) ? x[start2 + k] : 0.0;
+    __syncthreads();
     if (threadIdx.x == 0) {
       s_stop = kEquilChunk;
       double a = sum1, b = sum2;
-      long long t1 = start1, t2 = start2;
+      long long t1 = start1;
+      int m = 0;
       bool ev = is_even;
       for (int k = 0; k < kEquilChunk && t1 < N - 2; ++k) {  // EquilibrationCheck.cc:93-103
         s_sum1[k] = a;
         s_sum2[k] = b;
-        a = __dsub_rn(a, x[t1]);
+        a = __dsub_rn(a, s_x1[k]);
         if (ev) {
-          a = __dadd_rn(a, x[t2]);
-          b = __dsub_rn(b, x[t2]);
-          t2++;
+          a = __dadd_rn(a, s_x2[m]);
+          b = __dsub_rn(b, s_x2[m]);
+          m++;
         }
         t1++;
         ev = !ev;

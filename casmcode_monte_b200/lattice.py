@@ -295,6 +295,13 @@ class IsingLatticeGPU:
         self._ck(self._lib.cmg_series_equilibration_all(self._ctx, quantity, count, abs_precision, _p(e, C.c_int), _p(n, C.c_int64)))
         return e.astype(bool), n
 
+    def mark(self):
+        """Restore point (cmg_mark): what is enqueued next can be undone by rollback()."""
+        self._ck(self._lib.cmg_mark(self._ctx))
+
+    def rollback(self):
+        self._ck(self._lib.cmg_rollback(self._ctx))
+
     def series_check(self, quantities, abs_precisions, count=None, confidence=0.95, chain=0):
         """One completion check on the device series (cmg_series_check): equilibration of every
         requested component and, if all equilibrated, the statistics of the common tail."""

@@ -1010,6 +1010,11 @@ class CompletionCheck {
   }
   CompletionCheckResults const &results() const { return m_results; }
   Index n_checks() const { return m_n_checks; }
+  /// sample count of the next scheduled check
+  CountType next_check_at() const {
+    return m_params.log_spacing ? m_params.sample_check_log(m_n_checks, m_n_begin_linear)
+                                : m_params.sample_check_linear(m_n_checks);
+  }
   void set_device_series(std::shared_ptr<DeviceSeriesCheck> d) { m_device = std::move(d); }
 
   /// Pass-granular drivers: the pass count at which is_complete could next
@@ -1017,7 +1022,10 @@ class CompletionCheck {
   /// scheduled check / a sample cutoff).  Calling is_complete earlier is
   /// harmless; this only lets a device loop run several passes between calls.
   /// Returns `n_pass + 1` when a clock-based cutoff is set.
-  CountType next_decision_pass(CountType n_pass, CountType n_samples, CountType sample_period) const {
+  /// `extra_checks`: number of scheduled checks assumed to have been made by then (for a
+  /// driver that plans one block ahead of the decision).
+  CountType next_decision_pass(CountType n_pass, CountType n_samples, CountType sample_period,
+                               Index extra_checks = 0) const {
     CutoffCheckParams const &c = m_params.cutoff_params;
     if (c.min_clocktime || c.max_clocktime || c.min_time || c.max_time) return n_pass + 1;
     CountType best = std::numeric_limits<CountType>::max();
@@ -1029,8 +1037,8 @@ class CompletionCheck {
     CountType s_target = std::numeric_limits<CountType>::max();
     if (m_params.requested_precision.size()) {
       CountType check_at = m_params.log_spacing
-                               ? m_params.sample_check_log(m_n_checks, m_n_begin_linear)
-                               : m_params.sample_check_linear(m_n_checks);
+                               ? m_params.sample_check_log(m_n_checks + extra_checks, m_n_begin_linear)
+                               : m_params.sample_check_linear(m_n_checks + extra_checks);
       s_target = std::max<CountType>(check_at, c.min_sample ? *c.min_sample : 0);
     }
     if (c.max_sample) s_target = std::min(s_target, std::max<CountType>(*c.max_sample, c.min_sample ? *c.min_sample : 0));
@@ -1556,9 +1564,13 @@ class SemiGrandCanonicalCalculator {
         check_abs.push_back(p.second.abs_precision);
       }
     }
+    // samples of the passes that are decided (a speculative block may be in flight beyond them);
+    // negative: whatever the device has
+    auto committed_samples = std::make_shared<CountType>(-1);
     if (device_checks) {
       auto hook = std::make_shared<DeviceSeriesCheck>();
-      hook->n_samples = [ctx]() {
+      hook->n_samples = [ctx, committed_samples]() {
+        if (*committed_samples >= 0) return *committed_samples;
         int64_t n = 0;
         cmg_check(cmg_n_samples(ctx, &n), ctx);
         return static_cast<CountType>(n);
@@ -1614,9 +1626,24 @@ class SemiGrandCanonicalCalculator {
 
     auto current_n_samples = [&]() -> CountType {
       if (!device_checks) return get_n_samples(data->samplers);
+      if (*committed_samples >= 0) return *committed_samples;
       int64_t n = 0;
       dev.check(cmg_n_samples(ctx, &n));
       return static_cast<CountType>(n);
+    };
+    // Sweeping on while a check is evaluated: with the checks on the device series, the block
+    // after the next decision is enqueued BEFORE that decision is taken (cmg_mark keeps a
+    // restore point), the check runs on a second stream next to it, and a "complete" verdict --
+    // or a decision that asks for a different block -- rolls the speculative block back.  The
+    // results are those of the loop that waits for every decision.
+    const bool can_speculate = device_checks && mode == CMG_MODE_CHECKERBOARD && even && !nonlist_on_device;
+    bool have_spec = false;
+    CountType spec_n_run = 0;
+    auto drop_speculation = [&]() {
+      if (!have_spec) return;
+      dev.check(cmg_rollback(ctx));
+      have_spec = false;
+      *committed_samples = -1;
     };
 
     // ### main loop at pass granularity: is_complete is consulted
@@ -1630,7 +1657,10 @@ class SemiGrandCanonicalCalculator {
                                                   data->n_pass, method_log->log);
         if (done || data->completion_check.n_checks() == checks_before) break;
       }
-      if (done) break;
+      if (done) {
+        drop_speculation();
+        break;
+      }
 
       CountType target;
       if (host_state_each_sample) {
@@ -1644,7 +1674,13 @@ class SemiGrandCanonicalCalculator {
             n_pass_dev, current_n_samples(), sample_period);
       }
       CountType n_run = std::max<CountType>(1, target - n_pass_dev);
-      dev.check(cmg_run_passes(ctx, n_run, mode, device_samples ? sample_period : 0));
+      if (have_spec && spec_n_run == n_run) {
+        have_spec = false;  // the block in flight is the block asked for
+        *committed_samples = -1;
+      } else {
+        drop_speculation();
+        dev.check(cmg_run_passes(ctx, n_run, mode, device_samples ? sample_period : 0));
+      }
       config.mark_device_modified();
       n_pass_dev += n_run;
       data->n_pass = n_pass_dev;
@@ -1662,11 +1698,23 @@ class SemiGrandCanonicalCalculator {
           }
         if (json_sample_hook) json_sample_hook();
       }
-      if (sample_due && write_status_f && method_log->log_frequency.has_value() &&
-          method_log->log.lap_time() >= method_log->log_frequency.value()) {
+      const bool status_due = sample_due && write_status_f && method_log->log_frequency.has_value() &&
+                              method_log->log.lap_time() >= method_log->log_frequency.value();
+      if (status_due) {
         refresh_counters();
         fetch_device_samples();
         write_status_f(*this, *method_log);
+      } else if (can_speculate) {
+        // the block the loop will ask for if the decision at n_pass_dev is "go on"
+        const CountType s_now = current_n_samples();
+        CompletionCheck const &cc = data->completion_check;
+        const Index extra = (completion_check_params.requested_precision.size() && s_now >= cc.next_check_at()) ? 1 : 0;
+        const CountType t2 = cc.next_decision_pass(n_pass_dev, s_now, sample_period, extra);
+        spec_n_run = std::max<CountType>(1, t2 - n_pass_dev);
+        dev.check(cmg_mark(ctx));
+        dev.check(cmg_run_passes(ctx, spec_n_run, mode, sample_period));
+        *committed_samples = s_now;
+        have_spec = true;
       }
     }
     fetch_device_samples();

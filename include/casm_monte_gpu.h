@@ -279,6 +279,18 @@ int cmg_series_check(cmg_context *ctx, int chain, int n_components, const int *q
                      const double *abs_precision, int64_t count, double confidence,
                      int *is_equilibrated, int64_t *n_equil, int64_t *n_stats, double *mean,
                      double *calculated_precision);
+/* Restore point for drivers that sweep on while a completion check is evaluated
+ * (methods::basic_occupation_metropolis decides after every sample, include/casm/monte/
+ * methods/basic_occupation_metropolis.hh:381-422; a device loop that waited for every
+ * decision would idle during the checks).  cmg_mark records "now" on the stream: a copy of
+ * the state (planes, acceptance counters, pass and sample counters) follows the work
+ * enqueued so far; a cmg_series_check of samples taken up to the mark then runs on a second
+ * stream, concurrently with the passes enqueued after the mark.  cmg_rollback returns the
+ * context to the mark (the samples taken since are dropped), so a "complete" verdict leaves
+ * exactly the state the reference's loop would have stopped in.  Checkerboard contexts. */
+int cmg_mark(cmg_context *ctx);
+int cmg_rollback(cmg_context *ctx);
+
 /* statistics of an arbitrary host series (Sampler columns that did not come
  * from the device path): uploads, computes on the device, returns */
 int cmg_host_series_stats(int device, const double *x, int64_t n, double confidence,

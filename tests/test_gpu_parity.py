@@ -666,6 +666,42 @@ def test_general_conversions_batched_on_the_device_match_the_host():
         assert list(c.bijk_to_l_batch(shifted)) == ls
 
 
+@pytest.mark.parametrize("shape,variant", [([64, 48], "auto"), ([1024, 128], "ring2d"), ([256, 64], "bulk2d"), ([32, 10, 8], "auto")])
+def test_mark_and_rollback_undo_a_speculative_block(cm, oracle, shape, variant):
+    """cmg_mark / cmg_rollback: passes enqueued after the mark leave no trace after a rollback
+    (occupation, acceptance count, pass and sample counters, sample series), the samples up to
+    the mark can be checked meanwhile, and the trajectory continues as if nothing happened."""
+    n = nsites(shape)
+    occ = rand_occ(n, 77)
+    T, mu, seed = 2633.0 if len(shape) == 2 else 5235.0, 0.02, 4711
+    lat = cm.IsingLatticeGPU(shape, J=J)
+    lat.set_conditions(T, mu)
+    lat.seed_philox(seed)
+    lat.set_kernel_variant(variant)
+    lat.upload(occ)
+    lat.run_passes(5, cm.MODE_CHECKERBOARD, 1)
+    lat.mark()
+    lat.run_passes(7, cm.MODE_CHECKERBOARD, 1)  # speculative
+    chk = lat.series_check((cm.Q_POTENTIAL_ENERGY, cm.Q_PARAM_COMPOSITION), [1e-3, 1e-3], count=5)  # next to it
+    lat.rollback()
+    ref5 = oracle.checkerboard_run(shape, occ, J, T, mu, seed, 0, 0, 5, 1)
+    assert np.array_equal(lat.download(), ref5["occupation"])
+    assert lat.counters()[:2] == (5, ref5["n_accept"]) and lat.n_samples == 5
+    S, B = lat.samples_sb()
+    assert np.array_equal(S, ref5["S"]) and np.array_equal(B, ref5["B"])
+    assert np.array_equal(lat.samples(cm.Q_POTENTIAL_ENERGY), ref5["potential_energy"])
+    same = lat.series_check((cm.Q_POTENTIAL_ENERGY, cm.Q_PARAM_COMPOSITION), [1e-3, 1e-3], count=5)
+    assert chk == same
+    lat.run_passes(7, cm.MODE_CHECKERBOARD, 1)
+    ref12 = oracle.checkerboard_run(shape, occ, J, T, mu, seed, 0, 0, 12, 1)
+    assert np.array_equal(lat.download(), ref12["occupation"])
+    S, B = lat.samples_sb()
+    assert np.array_equal(S, ref12["S"]) and np.array_equal(B, ref12["B"]) and lat.counters()[1] == ref12["n_accept"]
+    with pytest.raises(cm.CmgError):
+        lat.rollback()  # no mark any more
+    lat.close()
+
+
 # ------------------------------------- full-size, size-independent properties ----
 def test_full_size_4096_properties(cm):
     shape = [4096, 4096]
