@@ -105,6 +105,9 @@ SIGNATURES = {
     "cmg_kstate_n_samples": (C.c_int, [_ctx, _i64p]),
     "cmg_kstate_clear_samples": (C.c_int, [_ctx]),
     "cmg_kstate_read_samples": (C.c_int, [_ctx, C.c_int, C.c_int64, C.c_int64, _i64p, _i64p]),
+    "cmg_nfold_run": (C.c_int, [_ctx, C.c_int64, C.c_int64]),
+    "cmg_nfold_read_weights": (C.c_int, [_ctx, C.c_int, C.c_int64, C.c_int64, _f64p, _f64p]),
+    "cmg_nfold_time": (C.c_int, [_ctx, C.c_int, _f64p, _i64p]),
     "cmg_set_energy_form": (C.c_int, [_ctx, C.c_int]),
     "cmg_launch_count": (C.c_int, [_ctx, _i64p]),
     "cmg_kernel_variant": (C.c_char_p, [_ctx]),

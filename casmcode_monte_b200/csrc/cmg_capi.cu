@@ -131,6 +131,12 @@ struct cmg_context {
   long long ks_capacity = 0, ks_n_samples = 0;
   int *d_kloc = nullptr, *d_kloc_size = nullptr, *d_kmol_loc = nullptr;  // OccLocation of every chain
   bool ks_loc_valid = false;
+  // N-fold way driver: class lists of every chain, weights of its samples, clock
+  int *d_nf_members = nullptr, *d_nf_n = nullptr, *d_nf_pos = nullptr;
+  uint8_t *d_nf_class = nullptr;
+  double *d_nf_weight = nullptr, *d_nf_ratio = nullptr, *d_nf_time = nullptr;  // [sample][chain] x2, [chain]
+  long long nf_capacity = 0, nf_first_sample = -1, nf_steps = 0;
+  bool nf_lists_valid = false;
   long long launches = 0;
   std::string last_error;
   std::string variant_name = "auto";
@@ -449,6 +455,13 @@ int cmg_destroy(cmg_context *c) {
   cudaFree(c->d_shadow_accept);
   if (c->aux) cudaStreamDestroy(c->aux);
   if (c->ev_mark) cudaEventDestroy(c->ev_mark);
+  cudaFree(c->d_nf_members);
+  cudaFree(c->d_nf_n);
+  cudaFree(c->d_nf_pos);
+  cudaFree(c->d_nf_class);
+  cudaFree(c->d_nf_weight);
+  cudaFree(c->d_nf_ratio);
+  cudaFree(c->d_nf_time);
   cudaFree(c->d_ktabs);
   cudaFree(c->d_kseries);
   cudaFree(c->d_kloc);
@@ -1820,6 +1833,7 @@ int cmg_clear_samples(cmg_context *c) {
                           c->stream));
   c->n_samples = 0;
   c->dbl_valid = 0;
+  c->nf_first_sample = -1;
   return CMG_OK;
 }
 
@@ -2797,6 +2811,136 @@ int cmg_kstate_read_samples(cmg_context *c, int chain, int64_t first, int64_t co
     for (int e = 0; e < K * K; ++e)
       if (bonds) bonds[i * K * K + e] = tmp[(size_t)i * per + K + e];
   }
+  return CMG_OK;
+}
+
+// ---- N-fold way driver ------------------------------------------------------------------
+int cmg_nfold_run(cmg_context *c, int64_t n_steps, int64_t sample_period_steps) {
+  NEED(c);
+  if (n_steps < 0 || sample_period_steps < 0) return fail(c, CMG_EINVAL, "negative count");
+  if (c->slab || c->ks_K) return fail(c, CMG_EUNSUPPORTED, "nfold: Ising contexts on one GPU");
+  if (c->n_sites >= (1ll << 31)) return fail(c, CMG_EUNSUPPORTED, "nfold: n_sites < 2^31");
+  int rc = check_ready(c);
+  if (rc) return rc;
+  for (int ch = 0; ch < c->n_chains; ++ch)
+    if (!c->d_engines || !c->engine_seeded[ch]) return fail(c, CMG_ESTATE, "mt19937_64 engine not seeded for every chain");
+  if (n_steps == 0) return CMG_OK;
+  rc = sync_nat_from_planes(c);
+  if (rc) return rc;
+  if (!c->d_nf_members) {
+    CU(c, cudaMalloc(&c->d_nf_members, sizeof(int) * (size_t)c->n_chains * 16 * c->n_sites));
+    CU(c, cudaMalloc(&c->d_nf_n, sizeof(int) * (size_t)c->n_chains * 16));
+    CU(c, cudaMalloc(&c->d_nf_pos, sizeof(int) * (size_t)c->n_chains * c->n_sites));
+    CU(c, cudaMalloc(&c->d_nf_class, (size_t)c->n_chains * c->n_sites));
+    CU(c, cudaMalloc(&c->d_nf_time, sizeof(double) * c->n_chains));
+    CU(c, cudaMemsetAsync(c->d_nf_time, 0, sizeof(double) * c->n_chains, c->stream));
+    c->nf_lists_valid = false;
+  }
+  NfoldArgs A;
+  memset(&A, 0, sizeof A);
+  A.lists.members = c->d_nf_members;
+  A.lists.n_members = c->d_nf_n;
+  A.lists.site_pos = c->d_nf_pos;
+  A.lists.site_class = c->d_nf_class;
+  // the lists follow the occupation as long as only this driver changes it
+  if (!c->nf_lists_valid || !c->nat_is_current) c->nf_lists_valid = false;
+  for (int ch = 0; ch < c->n_chains; ++ch) {
+    CU(c, cudaMemsetAsync(c->d_cur_sb + 2 * ch, 0, 2 * sizeof(long long), c->stream));
+    k_observables_natural<<<(unsigned)std::min<long long>(nblocks(c->n_sites, 256), 148 * 8), 256, 0, c->stream>>>(
+        c->d_nat + (size_t)ch * c->n_sites, nat_shape(c), c->d_cur_sb + 2 * ch);
+    ++c->launches;
+    if (!c->nf_lists_valid) {
+      NfoldLists P;
+      P.members = c->d_nf_members + (size_t)ch * 16 * c->n_sites;
+      P.n_members = c->d_nf_n + ch * 16;
+      P.site_pos = c->d_nf_pos + (size_t)ch * c->n_sites;
+      P.site_class = c->d_nf_class + (size_t)ch * c->n_sites;
+      k_nfold_init<<<1, 1, 0, c->stream>>>(c->d_nat + (size_t)ch * c->n_sites, nat_shape(c), P);
+      ++c->launches;
+    }
+  }
+  c->nf_lists_valid = true;
+  long long n_new = 0;
+  if (sample_period_steps > 0) n_new = (c->nf_steps + n_steps) / sample_period_steps - c->nf_steps / sample_period_steps;
+  rc = ensure_series(c, c->n_samples + n_new);
+  if (rc) return rc;
+  if (c->nf_first_sample < 0) c->nf_first_sample = c->n_samples;
+  const long long w_need = c->n_samples - c->nf_first_sample + n_new;
+  if (w_need > c->nf_capacity) {
+    long long cap = c->nf_capacity ? c->nf_capacity : 1024;
+    while (cap < w_need) cap *= 2;
+    double *nw = nullptr, *nr = nullptr;
+    CU(c, cudaMalloc(&nw, sizeof(double) * (size_t)cap * c->n_chains));
+    CU(c, cudaMalloc(&nr, sizeof(double) * (size_t)cap * c->n_chains));
+    const size_t used = sizeof(double) * (size_t)(c->n_samples - c->nf_first_sample) * c->n_chains;
+    if (used) {
+      CU(c, cudaMemcpyAsync(nw, c->d_nf_weight, used, cudaMemcpyDeviceToDevice, c->stream));
+      CU(c, cudaMemcpyAsync(nr, c->d_nf_ratio, used, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    CU(c, cudaStreamSynchronize(c->stream));
+    cudaFree(c->d_nf_weight);
+    cudaFree(c->d_nf_ratio);
+    c->d_nf_weight = nw;
+    c->d_nf_ratio = nr;
+    c->nf_capacity = cap;
+  }
+  A.nat = c->d_nat;
+  A.shape = nat_shape(c);
+  A.tabs = c->d_tabs;
+  A.engines = c->d_engines;
+  A.cur_sb = c->d_cur_sb;
+  A.series = c->d_series + c->n_samples * 2 * c->n_chains;
+  A.series_slot_stride = 2 * c->n_chains;
+  A.weight = c->d_nf_weight + (size_t)(c->n_samples - c->nf_first_sample) * c->n_chains;
+  A.rate_ratio = c->d_nf_ratio + (size_t)(c->n_samples - c->nf_first_sample) * c->n_chains;
+  A.wstride = c->n_chains;
+  A.time = c->d_nf_time;
+  A.n_steps = n_steps;
+  A.sample_period = sample_period_steps;
+  A.step_base = c->nf_steps;
+  k_nfold<<<c->n_chains, kSerialThreads, 0, c->stream>>>(A);
+  ++c->launches;
+  CU(c, cudaGetLastError());
+  c->nf_steps += n_steps;
+  c->n_samples += n_new;
+  rc = sync_planes_from_nat(c);
+  if (rc) return rc;
+  c->nat_is_current = true;
+  c->variant_name = "nfold";
+  return CMG_OK;
+}
+
+int cmg_nfold_read_weights(cmg_context *c, int chain, int64_t first, int64_t count, double *weight,
+                           double *expected_acceptance_rate) {
+  NEED(c);
+  if (chain < 0 || chain >= c->n_chains) return fail(c, CMG_EINVAL, "bad chain index");
+  if (c->nf_first_sample < 0) return fail(c, CMG_ESTATE, "no nfold samples");
+  if (first < c->nf_first_sample || count < 0 || first + count > c->n_samples)
+    return fail(c, CMG_EINVAL, "sample range outside the nfold samples");
+  if (count == 0) return CMG_OK;
+  const size_t off = (size_t)(first - c->nf_first_sample) * c->n_chains + chain;
+  if (weight)
+    CU(c, cudaMemcpy2DAsync(weight, sizeof(double), c->d_nf_weight + off, sizeof(double) * c->n_chains, sizeof(double),
+                            (size_t)count, cudaMemcpyDeviceToHost, c->stream));
+  if (expected_acceptance_rate)
+    CU(c, cudaMemcpy2DAsync(expected_acceptance_rate, sizeof(double), c->d_nf_ratio + off,
+                            sizeof(double) * c->n_chains, sizeof(double), (size_t)count, cudaMemcpyDeviceToHost,
+                            c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return CMG_OK;
+}
+
+int cmg_nfold_time(cmg_context *c, int chain, double *time, int64_t *n_steps) {
+  NEED(c);
+  if (chain < 0 || chain >= c->n_chains) return fail(c, CMG_EINVAL, "bad chain index");
+  if (time) {
+    *time = 0.0;
+    if (c->d_nf_time) {
+      CU(c, cudaMemcpyAsync(time, c->d_nf_time + chain, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      CU(c, cudaStreamSynchronize(c->stream));
+    }
+  }
+  if (n_steps) *n_steps = c->nf_steps;
   return CMG_OK;
 }
 

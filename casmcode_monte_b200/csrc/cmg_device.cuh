@@ -3001,3 +3001,211 @@ __global__ void __launch_bounds__(kSerialThreads) k_kstate_serial(KSerialArgs A)
 }
 
 }  // namespace cmg
+
+// ===========================================================================
+// N-fold way (rejection-free) driver for the Ising SGC model
+// (include/casm/monte/methods/nfold.hh:80-147): per step the total rate, the
+// selection of (event, time_increment), a sample if one is due -- taken BEFORE the
+// event is applied, with the time increment as its weight -- and the event.  The
+// event selector is outside the reference tree; this one is the Bortz-Kalos-
+// Lebowitz selector over the 2*(2*dim+1) rate classes of the acceptance table
+// (rate = 1 if dE < 0 else exp(-dE*beta)), with class lists kept like OccLocation
+// keeps its candidate lists.  Sequential by nature: one thread per chain walks it on
+// the reference's mt19937_64 stream (three draws per step), independent chains side
+// by side.  It produces the weighted observations the statistics kernels accept.
+// ===========================================================================
+namespace cmg {
+
+struct NfoldLists {
+  int *members;     // [n_class][n_sites]
+  int *n_members;   // [16]
+  int *site_pos;    // [n_sites]
+  uint8_t *site_class;  // [n_sites]
+};
+__device__ __forceinline__ void nfold_insert(const NfoldLists &P, long long n_sites, int l, int c) {
+  P.site_class[l] = (uint8_t)c;
+  P.site_pos[l] = P.n_members[c];
+  P.members[(long long)c * n_sites + P.n_members[c]++] = l;
+}
+__device__ __forceinline__ void nfold_move(const NfoldLists &P, long long n_sites, int l, int c_new) {
+  const int c = P.site_class[l];
+  if (c == c_new) return;
+  const int back = P.members[(long long)c * n_sites + P.n_members[c] - 1];
+  P.members[(long long)c * n_sites + P.site_pos[l]] = back;
+  P.site_pos[back] = P.site_pos[l];
+  P.n_members[c]--;
+  nfold_insert(P, n_sites, l, c_new);
+}
+// lists filled in site order (which fixes the order the member draw indexes)
+__global__ void k_nfold_init(const uint8_t *__restrict__ nat, NaturalShape s, NfoldLists P) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  for (int c = 0; c < 16; ++c) P.n_members[c] = 0;
+  for (long long l = 0; l < s.n_sites; ++l)
+    nfold_insert(P, s.n_sites, (int)l, 2 * natural_n_up32(nat, s.n0, s.n1, s.n2, s.dim, (unsigned int)l) + nat[l]);
+}
+
+struct NfoldArgs {
+  uint8_t *nat;  // [chain][n_sites]
+  NaturalShape shape;
+  const ChainTables *tabs;
+  MT64State *engines;
+  NfoldLists lists;            // chain 0
+  long long *cur_sb;           // [chain][2] current {ones, B}
+  long long *series;           // slot of the first sample of this launch, chain 0: {ones, B}
+  long long series_slot_stride;  // long long units between consecutive samples
+  double *weight;              // [sample][chain] time increments, first sample of this launch
+  double *rate_ratio;          // [sample][chain] total_rate / n_sites
+  long long wstride;           // doubles between consecutive samples (= n_chains)
+  double *time;                // [chain]
+  long long n_steps;
+  long long sample_period;     // steps; 0 = never
+  long long step_base;         // steps done before this launch
+};
+
+__global__ void __launch_bounds__(kSerialThreads) k_nfold(NfoldArgs A) {
+  __shared__ unsigned long long mt[312], out[312];
+  __shared__ int s_done;
+  const int chain = blockIdx.x;
+  const NaturalShape s = A.shape;
+  uint8_t *nat = A.nat + (long long)chain * s.n_sites;
+  const ChainTables *tab = A.tabs + chain;
+  MT64State *eng = A.engines + chain;
+  const int z = 2 * s.dim, n_class = 2 * (z + 1);
+  NfoldLists P;
+  P.members = A.lists.members + (long long)chain * 16 * s.n_sites;
+  P.n_members = A.lists.n_members + chain * 16;
+  P.site_pos = A.lists.site_pos + (long long)chain * s.n_sites;
+  P.site_class = A.lists.site_class + (long long)chain * s.n_sites;
+
+  for (int i = threadIdx.x; i < 312; i += blockDim.x) {
+    mt[i] = eng->x[i];
+    out[i] = mt64_temper(mt[i]);
+  }
+  if (threadIdx.x == 0) s_done = (A.n_steps <= 0);
+  __syncthreads();
+  int pos = eng->pos;
+  long long step = 0, slot = 0;
+  long long ones = 0, B = 0;
+  double time = 0.0, total_rate = 0.0;
+  int phase = 0, chosen = 0, l = 0;
+  double rate[16];
+  if (threadIdx.x == 0) {
+    ones = A.cur_sb[2 * chain];
+    B = A.cur_sb[2 * chain + 1];
+    time = A.time[chain];
+    for (int c = 0; c < n_class; ++c) rate[c] = tab->dE[c] < 0.0 ? 1.0 : tab->prob[c];
+  }
+
+  while (!s_done) {
+    if (pos >= 312) {
+      mt64_twist_block(mt);
+      for (int i = threadIdx.x; i < 312; i += blockDim.x) out[i] = mt64_temper(mt[i]);
+      pos = 0;
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      bool done = false;
+      while (pos < 312) {
+        const unsigned long long u = out[pos++];
+        if (phase == 0) {
+          // total rate (before selection) and the class of the event
+          total_rate = 0.0;
+          for (int c = 0; c < n_class; ++c) total_rate = __dadd_rn(total_rate, __dmul_rn((double)P.n_members[c], rate[c]));
+          double r = __dmul_rn(__ull2double_rn(u), 5.42101086242752217003726400434970855712890625e-20);
+          if (r >= 1.0) r = 0.99999999999999988897769753748434595763683319091796875;
+          const double u1 = __dadd_rn(__dmul_rn(r, __dsub_rn(total_rate, 0.0)), 0.0);
+          chosen = -1;
+          double cum = 0.0;
+          for (int c = 0; c < n_class; ++c) {
+            cum = __dadd_rn(cum, __dmul_rn((double)P.n_members[c], rate[c]));
+            if (u1 < cum) {
+              chosen = c;
+              break;
+            }
+          }
+          if (chosen < 0)
+            for (int c = n_class - 1; c >= 0; --c)
+              if (P.n_members[c] > 0) {
+                chosen = c;
+                break;
+              }
+          phase = 1;
+          continue;
+        }
+        if (phase == 1) {
+          const unsigned long long range = (unsigned long long)P.n_members[chosen];
+          const unsigned long long low = u * range;
+          if (low < range && low < (0ull - range) % range) continue;  // Lemire redraw
+          l = P.members[(long long)chosen * s.n_sites + (long long)__umul64hi(u, range)];
+          phase = 2;
+          continue;
+        }
+        // phase 2: the time increment, the sample if one is due, the event
+        double r = __dmul_rn(__ull2double_rn(u), 5.42101086242752217003726400434970855712890625e-20);
+        if (r >= 1.0) r = 0.99999999999999988897769753748434595763683319091796875;
+        r = __dadd_rn(__dmul_rn(r, __dsub_rn(1.0, 0.0)), 0.0);
+        const double time_increment = __ddiv_rn(-log(__dsub_rn(1.0, r)), total_rate);
+        if (A.sample_period > 0 && ((A.step_base + step + 1) % A.sample_period) == 0) {
+          long long *dst = A.series + slot * A.series_slot_stride + 2 * chain;
+          dst[0] = ones;
+          dst[1] = B;
+          A.weight[slot * A.wstride + chain] = time_increment;
+          A.rate_ratio[slot * A.wstride + chain] = __ddiv_rn(total_rate, (double)s.n_sites);
+          ++slot;
+        }
+        {
+          const int n_up = natural_n_up32(nat, s.n0, s.n1, s.n2, s.dim, (unsigned int)l);
+          const int b = nat[l];
+          const int sgn = 2 * b - 1;
+          B += (long long)(-2 * sgn) * (2 * n_up - z);
+          ones += b ? -1 : 1;
+          nat[l] = (uint8_t)(b ^ 1);
+          nfold_move(P, s.n_sites, l, 2 * n_up + (b ^ 1));
+          // the neighbours change class: +i, +j, -i, -j [, +k, -k]
+          const unsigned int ul = (unsigned int)l;
+          const unsigned int rr = ul / (unsigned int)s.n0;
+          const int i = (int)(ul - rr * (unsigned int)s.n0);
+          int j = (int)rr, k = 0;
+          if (s.dim == 3) {
+            k = (int)(rr / (unsigned int)s.n1);
+            j = (int)(rr - (unsigned int)k * (unsigned int)s.n1);
+          }
+          const int ip = (i + 1 == s.n0) ? 0 : i + 1, im = (i == 0) ? s.n0 - 1 : i - 1;
+          const int jp = (j + 1 == s.n1) ? 0 : j + 1, jm = (j == 0) ? s.n1 - 1 : j - 1;
+          int nb[6];
+          nb[0] = ip + s.n0 * (j + s.n1 * k);
+          nb[1] = i + s.n0 * (jp + s.n1 * k);
+          nb[2] = im + s.n0 * (j + s.n1 * k);
+          nb[3] = i + s.n0 * (jm + s.n1 * k);
+          if (s.dim == 3) {
+            const int kp = (k + 1 == s.n2) ? 0 : k + 1, km = (k == 0) ? s.n2 - 1 : k - 1;
+            nb[4] = i + s.n0 * (j + s.n1 * kp);
+            nb[5] = i + s.n0 * (j + s.n1 * km);
+          }
+          for (int d = 0; d < z; ++d)
+            nfold_move(P, s.n_sites, nb[d],
+                       2 * natural_n_up32(nat, s.n0, s.n1, s.n2, s.dim, (unsigned int)nb[d]) + nat[nb[d]]);
+        }
+        time = __dadd_rn(time, time_increment);
+        phase = 0;
+        if (++step == A.n_steps) {
+          done = true;
+          break;
+        }
+      }
+      if (done) s_done = 1;
+    }
+    __syncthreads();
+    if (!s_done) pos = 312;
+  }
+  if (threadIdx.x == 0) {
+    eng->pos = pos;
+    A.cur_sb[2 * chain] = ones;
+    A.cur_sb[2 * chain + 1] = B;
+    A.time[chain] = time;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 312; i += blockDim.x) eng->x[i] = mt[i];
+}
+
+}  // namespace cmg

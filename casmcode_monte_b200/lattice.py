@@ -370,6 +370,24 @@ class IsingLatticeGPU:
     def kstate_clear_samples(self):
         self._ck(self._lib.cmg_kstate_clear_samples(self._ctx))
 
+    # -- N-fold way driver (include/casm/monte/methods/nfold.hh) --
+    def nfold_run(self, n_steps, sample_period_steps=0):
+        self._ck(self._lib.cmg_nfold_run(self._ctx, int(n_steps), int(sample_period_steps)))
+
+    def nfold_weights(self, chain=0, first=0, count=None):
+        """(time increments, expected acceptance rates) of the nfold samples [first, first + count)."""
+        if count is None:
+            count = self.n_samples - first
+        w = np.zeros(count)
+        r = np.zeros(count)
+        self._ck(self._lib.cmg_nfold_read_weights(self._ctx, chain, first, count, _p(w, C.c_double), _p(r, C.c_double)))
+        return w, r
+
+    def nfold_time(self, chain=0):
+        t, n = C.c_double(), C.c_int64()
+        self._ck(self._lib.cmg_nfold_time(self._ctx, chain, C.byref(t), C.byref(n)))
+        return t.value, n.value
+
     # -- slab plumbing --
     def slab_half_sweep(self, colour, pass_index, sample=False):
         self._ck(self._lib.cmg_slab_half_sweep(self._ctx, int(colour), int(pass_index), int(bool(sample))))

@@ -392,6 +392,25 @@ int cmg_kstate_clear_samples(cmg_context *ctx);
 int cmg_kstate_read_samples(cmg_context *ctx, int chain, int64_t first, int64_t count,
                             int64_t *counts, int64_t *bonds);
 
+/* ---- N-fold way (rejection-free) driver ------------------------------------------
+ * Replaces the loop of methods::nfold (include/casm/monte/methods/nfold.hh:80-147) for
+ * the Ising SGC model: per step the total rate, the selection of (event,
+ * time_increment), a sample if one is due by count -- taken before the event is applied
+ * and weighted with the time increment (:104-123) -- and the event (:129-137).  The event
+ * selector is a template parameter supplied from outside the reference tree; this
+ * library's is the Bortz-Kalos-Lebowitz selector over the rate classes of the acceptance
+ * table (rate = 1 if dE < 0 else exp(-dE*beta)): class by random_real(total_rate), member
+ * by random_int(n - 1) in the class list, time_increment = -log(1 - random_real(1)) /
+ * total_rate, all on the chain's mt19937_64 stream.  Every step is an accepted event.
+ * Samples (S, B) are appended to the regular series (cmg_read_samples*); their weights
+ * and the expected Metropolis acceptance rate total_rate / n_sites (NfoldData::
+ * expected_acceptance_rate, :38-41) are read with cmg_nfold_read_weights and feed the
+ * weighted statistics (cmg_host_series_stats_weighted). */
+int cmg_nfold_run(cmg_context *ctx, int64_t n_steps, int64_t sample_period_steps);
+int cmg_nfold_read_weights(cmg_context *ctx, int chain, int64_t first, int64_t count,
+                           double *weight, double *expected_acceptance_rate);
+int cmg_nfold_time(cmg_context *ctx, int chain, double *time, int64_t *n_steps);
+
 /* ---- introspection for bench / tests ---------------------------------------- */
 /* number of kernels this context has launched since creation */
 int cmg_launch_count(const cmg_context *ctx, int64_t *n_launches);

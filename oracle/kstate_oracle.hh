@@ -437,3 +437,137 @@ inline KStateRunResult kstate_checkerboard_run(std::vector<int> const &shape, st
 }  // namespace monte_oracle
 
 #endif
+
+// ===========================================================================
+// N-fold way (rejection-free) driver, include/casm/monte/methods/nfold.hh:80-147,
+// for the Ising SGC model.  The reference's loop is: total_rate (before selection);
+// (event, time_increment) = event_selector.select_event(); sample if due, with
+// sample weight = time_increment; apply the event; time += time_increment; count++.
+// The event selector is a template parameter that lives outside the reference tree
+// (libcasm-clexmonte supplies one), so the selector is this repo's, the textbook
+// Bortz-Kalos-Lebowitz one over rate classes:
+//   event l = flip of site l, rate r_l = 1 if dE_l < 0 else exp(-dE_l * beta): the
+//   Metropolis acceptance probability, one of 2 * (2 dim + 1) values (class c =
+//   2 * n_up + b, the index of the acceptance table);
+//   total_rate = sum over classes in index order of n_c * rate_c;
+//   class chosen by u1 = random_real(total_rate) against the running sum, member by
+//   random_int(n_c - 1) in the class list (lists are kept like OccLocation's: filled
+//   in site order, swap-remove, append);
+//   time_increment = -log(1 - random_real(1.0)) / total_rate.
+// PARITY: unpinned (the reference holds no test of nfold); restatement of the loop.
+// ===========================================================================
+namespace monte_oracle {
+namespace nfold {
+
+struct ClassLists {
+  int n_class;
+  std::vector<std::vector<long>> members;  // [class] -> sites
+  std::vector<int> site_class;
+  std::vector<long> site_pos;
+  void init(int n_class_, long n_sites) {
+    n_class = n_class_;
+    members.assign(n_class, {});
+    site_class.assign(n_sites, 0);
+    site_pos.assign(n_sites, 0);
+  }
+  void insert(long l, int c) {
+    site_class[l] = c;
+    site_pos[l] = static_cast<long>(members[c].size());
+    members[c].push_back(l);
+  }
+  void move(long l, int c_new) {
+    const int c = site_class[l];
+    if (c == c_new) return;
+    const long back = members[c].back();
+    members[c][site_pos[l]] = back;
+    site_pos[back] = site_pos[l];
+    members[c].pop_back();
+    insert(l, c_new);
+  }
+};
+
+struct NfoldResult {
+  std::vector<int> occupation;
+  std::vector<long long> S, B;     // integer observables at the sampled steps (before the event)
+  std::vector<double> weight;      // time_increment of the event selected at the sample
+  std::vector<double> expected_acceptance_rate;  // total_rate / n_events_possible at the sample
+  std::vector<long> event_site;    // every selected site, in order (for trajectory parity)
+  double time = 0.0;
+  long long n_steps = 0;
+};
+
+template <typename EngineType>
+NfoldResult nfold_run(std::vector<int> const &shape, std::vector<int> occ, double J, double T, double mu,
+                      std::shared_ptr<EngineType> engine, long long n_steps, long long sample_period,
+                      bool keep_events) {
+  kstate::Lattice L(shape);
+  const int dim = L.dim, z = 2 * dim, n_class = 2 * (z + 1);
+  AcceptTable tab = make_accept_table(dim, J, T, mu);
+  std::vector<double> rate(n_class);
+  for (int nu = 0; nu <= z; ++nu)
+    for (int b = 0; b < 2; ++b) rate[2 * nu + b] = tab.dE[b][nu] < 0.0 ? 1.0 : tab.prob[b][nu];
+  auto n_up_of = [&](long l) {
+    long nb[6];
+    L.neighbours(l, nb);
+    int n = 0;
+    for (int d = 0; d < z; ++d) n += occ[nb[d]] > 0;
+    return n;
+  };
+  ClassLists lists;
+  lists.init(n_class, L.n_sites());
+  for (long l = 0; l < L.n_sites(); ++l) lists.insert(l, 2 * n_up_of(l) + (occ[l] > 0));
+  long long S = 0, B = 0;
+  integer_observables(occ, shape, S, B);
+  RandomNumberGenerator<EngineType> rng(engine);
+  NfoldResult r;
+  double time = 0.0;
+  for (long long step = 0; step < n_steps; ++step) {
+    double total_rate = 0.0;
+    for (int c = 0; c < n_class; ++c) total_rate += static_cast<double>(lists.members[c].size()) * rate[c];
+    // select_event
+    const double u1 = rng.random_real(total_rate);
+    int chosen = -1;
+    double cum = 0.0;
+    for (int c = 0; c < n_class; ++c) {
+      cum += static_cast<double>(lists.members[c].size()) * rate[c];
+      if (u1 < cum) {
+        chosen = c;
+        break;
+      }
+    }
+    if (chosen < 0)  // rounding at the upper end: the last non-empty class
+      for (int c = n_class - 1; c >= 0; --c)
+        if (!lists.members[c].empty()) {
+          chosen = c;
+          break;
+        }
+    const long l = lists.members[chosen][rng.random_int(static_cast<long>(lists.members[chosen].size()) - 1)];
+    const double time_increment = -std::log(1.0 - rng.random_real(1.0)) / total_rate;
+    // sample, if due by count (nfold.hh:119-123: before the event is applied, weight = time_increment)
+    if (sample_period > 0 && ((step + 1) % sample_period) == 0) {
+      r.S.push_back(S);
+      r.B.push_back(B);
+      r.weight.push_back(time_increment);
+      r.expected_acceptance_rate.push_back(total_rate / static_cast<double>(L.n_sites()));
+    }
+    // apply (nfold.hh:129-131)
+    if (keep_events) r.event_site.push_back(l);
+    const int n_up = n_up_of(l);
+    const int s = occ[l];
+    B += static_cast<long long>(-2 * s) * (2 * n_up - z);
+    S += -2 * s;
+    occ[l] = -s;
+    lists.move(l, 2 * n_up + (occ[l] > 0));
+    long nb[6];
+    L.neighbours(l, nb);
+    for (int d = 0; d < z; ++d) lists.move(nb[d], 2 * n_up_of(nb[d]) + (occ[nb[d]] > 0));
+    time += time_increment;
+  }
+  r.occupation = occ;
+  r.time = time;
+  r.n_steps = n_steps;
+  return r;
+}
+
+}  // namespace nfold
+}  // namespace monte_oracle

@@ -812,6 +812,21 @@ PYBIND11_MODULE(_monte_oracle, m) {
     }
     return py::make_tuple(out, from_vec(occ));
   });
+  // N-fold way driver (nfold.hh:80-147) with the BKL class selector
+  m.def("nfold_run", [](std::vector<int> shape, i32arr occ, double J, double T, double mu, Engine &engine,
+                        long long n_steps, long long sample_period, bool keep_events) {
+    nfold::NfoldResult r = nfold::nfold_run(shape, to_vec(occ), J, T, mu, engine.e, n_steps, sample_period, keep_events);
+    py::dict d;
+    d["occupation"] = from_vec(r.occupation);
+    d["S"] = py::array_t<long long>(r.S.size(), r.S.data());
+    d["B"] = py::array_t<long long>(r.B.size(), r.B.data());
+    d["weight"] = from_dvec(r.weight);
+    d["expected_acceptance_rate"] = from_dvec(r.expected_acceptance_rate);
+    d["event_site"] = py::array_t<long>(r.event_site.size(), r.event_site.data());
+    d["time"] = r.time;
+    return d;
+  }, py::arg("shape"), py::arg("occupation"), py::arg("J"), py::arg("temperature"), py::arg("mu"), py::arg("engine"),
+     py::arg("n_steps"), py::arg("sample_period") = 1, py::arg("keep_events") = false);
   // the restated proposal machinery on its own (for the host-mirror tests)
   m.def("kstate_swaps", [](int K) {
     kstate::SimpleConversions convert{1, K};
