@@ -1313,6 +1313,7 @@ PYBIND11_MODULE(_monte_b200, m) {
                              py::return_value_policy::reference_internal)
       .def_readonly("data", &calculator_type::data)
       .def_readwrite("update_mode", &calculator_type::update_mode)
+      .def_readwrite("overlap_checks", &calculator_type::overlap_checks)
       .def_readonly("last_kernel", &calculator_type::last_kernel)
       .def("default_sampling_functions", [](std::shared_ptr<calculator_type> mc) {
         StateSamplingFunctionMap fns;

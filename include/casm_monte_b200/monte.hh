@@ -1452,6 +1452,13 @@ class SemiGrandCanonicalCalculator {
   std::string update_mode = "auto";
   /// name of the kernel that ran the last `run` (introspection)
   std::string last_kernel;
+  /// (not in the reference) enqueue the next block of passes before the pending completion
+  /// check is evaluated and evaluate the check on a second stream (cmg_mark / cmg_rollback).
+  /// Results are identical either way.  Off by default: measured on B200 it pays with the
+  /// streaming kernels (many small CTAs: the check's CTA costs one slot of ~600), not with the
+  /// kernels that fill every SM with one CTA (k_tile2d, k_ring2d), whose launches then wait for
+  /// the SM the check holds.
+  bool overlap_checks = false;
 
   /// `json_sample_hook`, if set, is called after every sample with the host
   /// mirror of the configuration current (JSON samplers live in the binding).
@@ -1636,7 +1643,7 @@ class SemiGrandCanonicalCalculator {
     // restore point), the check runs on a second stream next to it, and a "complete" verdict --
     // or a decision that asks for a different block -- rolls the speculative block back.  The
     // results are those of the loop that waits for every decision.
-    const bool can_speculate = device_checks && mode == CMG_MODE_CHECKERBOARD && even && !nonlist_on_device;
+    const bool can_speculate = overlap_checks && device_checks && mode == CMG_MODE_CHECKERBOARD && even && !nonlist_on_device;
     bool have_spec = false;
     CountType spec_n_run = 0;
     auto drop_speculation = [&]() {

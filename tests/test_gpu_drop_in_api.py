@@ -479,3 +479,37 @@ def test_conversions_class(api):
     assert f.bijk_to_l([0, 3, 0, 0]) == 0 and f.bijk_to_l([0, -1, 0, 0]) == f.bijk_to_l([0, 2, 0, 0])
     b = f.l_to_bijk_batch(list(range(54)))
     assert list(f.bijk_to_l_batch(b)) == list(range(54))
+
+
+def test_run_with_overlapped_checks_gives_the_same_results(api):
+    """overlap_checks = True (next block enqueued before the pending check, check on a second
+    stream, rollback on completion) must change nothing: samplers, counters, completion results
+    and the final occupation are those of the waiting loop."""
+    out = {}
+    for overlap in (False, True):
+        mc = make_calculator(api)
+        mc.overlap_checks = overlap
+        fns = mc.default_sampling_functions()
+        p = api.sampling.CompletionCheckParams()
+        p.cutoff_params.min_sample = 50
+        p.cutoff_params.max_sample = 900
+        p.check_begin = 50
+        p.check_period = 25
+        api.sampling.converge(fns, p).set_precision("potential_energy", abs=2e-4).set_precision("param_composition", abs=2e-4)
+        state = make_state(api, (64, 64), 3200.0, 0.03)
+        e = api.monte.RandomNumberEngine()
+        e.seed(77)
+        mc.run(state=state, sampling_functions=fns, json_sampling_functions=api.sampling.jsonStateSamplingFunctionMap(),
+               completion_check_params=p, event_generator=api.sgc.SemiGrandCanonicalEventGenerator(), random_engine=e,
+               update_mode="checkerboard")
+        d = mc.data
+        res = d.completion_check.results()
+        out[overlap] = (
+            d.n_pass, d.n_accept, d.n_reject, np.array(state.configuration.occupation()).copy(),
+            np.array(d.samplers["potential_energy"].component(0)).copy(), res.is_complete, res.n_samples,
+            json.dumps(res.to_dict(), sort_keys=True, default=str).replace(str(res.clocktime), ""),
+        )
+    a, b = out[False], out[True]
+    assert a[0] == b[0] and a[1] == b[1] and a[2] == b[2] and a[5] and b[5] and a[6] == b[6]
+    assert np.array_equal(a[3], b[3]) and np.array_equal(a[4], b[4])
+    assert 50 <= a[6] < 900  # converged before the cutoff: the speculative block was rolled back
