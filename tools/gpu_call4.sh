@@ -5,6 +5,9 @@ mkdir -p gpurun_out
 cap() {  # name kernel-regex skip count case passes variant
   timeout 300 ncu --set full --clock-control none --import-source on -k regex:$2 -s $3 -c $4 -f -o gpurun_out/$1_$tag python tools/profile_target.py $5 $6 $7 > gpurun_out/ncu_$1_$tag.log 2>&1
   tail -2 gpurun_out/ncu_$1_$tag.log
+  # the reports together exceed what a call may bring back: summarise on the box, keep the headline kernel's report only
+  python tools/ncu_brief.py gpurun_out/$1_$tag.ncu-rep > gpurun_out/ncu_$1_$tag.txt 2>&1
+  [ "$1" = ring2d ] || rm -f gpurun_out/$1_$tag.ncu-rep
 }
 cap ring2d k_ring2d 1 1 2d 300 auto
 cap bulk2d_sweep8 k_halfsweep_bulk2d 8 2 sweep8 6 bulk2d
