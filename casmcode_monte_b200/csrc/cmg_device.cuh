@@ -1411,9 +1411,9 @@ __global__ void __launch_bounds__(128, CMG_BULK_CTAS) k_halfsweep_bulk3d(SweepAr
     const uint8_t *Cf = C + col0;
     const uint8_t *Ef = O + (long long)h * jbeg;
     const int e_lo = p_below & ~3, e_hi = p_above;
-    auto fetch = [&](const int kk, const int par) {
+    auto fetch = [&](const int kk, const int par, const uint32_t slot_idx) {
       if (kk < n) {
-        const uint32_t slot = (uint32_t)(kk & (kBulkStages - 1)) * kBulk3dStageBytes;
+        const uint32_t slot = slot_idx * kBulk3dStageBytes;
         cp_async16_ca(s_o + slot, (kk + 1 >= n) ? Oend : Of);
         cp_async16_cg(s_a + slot, Af);
         cp_async16_cg(s_b + slot, Bf);
@@ -1432,22 +1432,29 @@ __global__ void __launch_bounds__(128, CMG_BULK_CTAS) k_halfsweep_bulk3d(SweepAr
       om = ld16_nc(O + (long long)h * wrapj(jbeg - 1) + p0);
       oc = ld16_nc(O + col0);
     }
+    // The ring slot and the column parity of a column are functions of its VIRTUAL
+    // index iv = it - par0 (it = 0 .. n-1 the column of the strip): slot = iv & 3,
+    // par = iv & 1.  A strip that starts on an odd-parity column therefore begins
+    // with one peeled column (iv = -1: slot 3, par 1) and then runs the SAME
+    // four-column body as every other strip.  Warps of layers k and k+1 (opposite
+    // start parities) share one hot loop in the instruction cache instead of two.
+    auto fetch_v = [&](const int iv) { fetch(iv + par0, iv & 1, (uint32_t)(iv & (kBulkStages - 1))); };
 #pragma unroll
-    for (int kk = 0; kk < kBulkStages; ++kk) fetch(kk, par0 ^ (kk & 1));
+    for (int s = 0; s < kBulkStages; ++s) fetch_v(s - par0);
     __syncthreads();  // acceptance tables are in shared memory
     uint8_t *Cp = C + col0;
     unsigned long long g = (unsigned long long)((layer * k + col0) >> 3);
     const unsigned int gstep = (unsigned int)h >> 3;
 
-    auto column = [&](const int it, const int par) {
-      const uint32_t slot = (uint32_t)(it & (kBulkStages - 1)) * kBulk3dStageBytes;
+    auto column = [&](const int iv, const int par, const uint32_t slot_idx) {
+      const uint32_t slot = slot_idx * kBulk3dStageBytes;
       cp_async_wait<kBulkStages - 1>();
       const uint4 op = lds16_abs(s_o + slot);
       const uint4 ka = lds16_abs(s_a + slot);
       const uint4 kb = lds16_abs(s_b + slot);
       const uint4 ce = lds16_abs(s_c + slot);
       const uint32_t eb = lds8_abs(s_e + slot + (par ? 0u : 3u));
-      fetch(it + kBulkStages, par);
+      fetch(iv + par0 + kBulkStages, par, slot_idx);
       uint4 side = (par == 0) ? shift_up_1(oc, eb) : shift_down_1(oc, eb);
       // fold the two k-neighbours into the "side" word: sums stay <= 6
       side.x += ka.x + kb.x;
@@ -1462,22 +1469,17 @@ __global__ void __launch_bounds__(128, CMG_BULK_CTAS) k_halfsweep_bulk3d(SweepAr
       om = oc;
       oc = op;
     };
-    auto strip_loop = [&](auto par_tag) {
-      constexpr int P0 = decltype(par_tag)::value;
-      int it = 0;
-      for (; it + 4 <= n; it += 4) {
-        column(it, P0);
-        column(it + 1, P0 ^ 1);
-        column(it + 2, P0);
-        column(it + 3, P0 ^ 1);
-      }
-      for (; it < n; ++it) column(it, P0 ^ (it & 1));
-    };
-    if (par0) {
-      strip_loop(std::integral_constant<int, 1>{});
-    } else {
-      strip_loop(std::integral_constant<int, 0>{});
+    static_assert(kBulkStages == 4, "the column loop is unrolled by the ring size");
+    if (par0 && n > 0) column(-1, 1, 3u);
+    const int nv = n - par0;  // columns with virtual index >= 0
+    int iv = 0;
+    for (; iv + 4 <= nv; iv += 4) {
+      column(iv, 0, 0u);
+      column(iv + 1, 1, 1u);
+      column(iv + 2, 0, 2u);
+      column(iv + 3, 1, 3u);
     }
+    for (; iv < nv; ++iv) column(iv, iv & 1, (uint32_t)(iv & 3));
   }
   long long ones = 0, bsum = 0;
   if (SAMPLE) accum_finish(acc, 6, ones, bsum);
