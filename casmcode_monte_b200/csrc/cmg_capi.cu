@@ -34,7 +34,7 @@ struct RunState {
   long long n_samples;
 };
 
-enum Variant { V_AUTO = 0, V_GENERIC = 1, V_BULK2D = 2, V_BULK3D = 3, V_TILE2D = 4, V_RING2D = 5 };
+enum Variant { V_AUTO = 0, V_GENERIC = 1, V_BULK2D = 2, V_BULK3D = 3, V_TILE2D = 4, V_RING2D = 5, V_TMA3D = 6 };
 
 struct cmg_context {
   int device = 0;
@@ -110,6 +110,7 @@ struct cmg_context {
   int coop_launch = 0;
   int sm_count = 148;
   bool bulk_attr_set = false;
+  bool tma3d_attr_set = false;
   int js_auto[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // cached strip length per kernel variant
   size_t smem_optin = 0;
   // cmg_mark / cmg_rollback: a restore point (planes, acceptance counters, host counters) and
@@ -1227,6 +1228,63 @@ static int pick_strips3d(cmg_context *c, int *pair_layers) {
   return best;
 }
 
+// k_halfsweep_tma3d: K = 128 / V layers per CTA (V = n0 / 32 vectors per column), whole
+// columns moved by bulk copies.  Strip count chosen like pick_strips3d's.
+struct Tma3dPlan {
+  bool ok;
+  int n_strips, K;
+  size_t smem;
+};
+static Tma3dPlan plan_tma3d(cmg_context *c) {
+  Tma3dPlan r = {false, 0, 0, 0};
+  if (c->dim != 3 || c->slab) return r;
+  const long long n0 = c->shape[0], n1 = c->shape[1], n2 = c->shape[2];
+  if ((n0 != 512 && n0 != 1024) || n1 % 2 || n1 < 2) return r;
+  const long long V = n0 / 32, K = 128 / V;
+  if (n2 % K) return r;
+  r.K = (int)K;
+  r.smem = (size_t)kSmemTile + (size_t)kTmaStages * (size_t)tma3d_stage_bytes((int)(n0 / 2));
+  if (r.smem + 1024 > (size_t)c->smem_optin) return r;
+  if (!c->tma3d_attr_set) {
+    if (cudaFuncSetAttribute(k_halfsweep_tma3d<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r.smem) != cudaSuccess ||
+        cudaFuncSetAttribute(k_halfsweep_tma3d<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r.smem) != cudaSuccess) {
+      cudaGetLastError();
+      return r;
+    }
+    c->tma3d_attr_set = true;
+  }
+  if (c->js_auto[6] > 0) {
+    r.n_strips = c->js_auto[6];
+    r.ok = true;
+    return r;
+  }
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_halfsweep_tma3d<true>, 128, r.smem) != cudaSuccess || per_sm < 1) {
+    cudaGetLastError();
+    return r;
+  }
+  const double slots = (double)c->sm_count * per_sm;
+  int best = 0;
+  double best_cost = 1e300;
+  const long long max_strips = c->js > 0 ? std::max<long long>(1, n1 / c->js) : n1 / 2;
+  for (long long S = 1; S <= std::min(max_strips, n1 / 2); ++S) {
+    const double len = std::ceil((double)(n1 / 2) / S) * 2.0;
+    if (c->js > 0 && S != max_strips) continue;
+    if (c->js <= 0 && len > 128 && S < n1 / 2) continue;
+    const double ctas = (double)(S * (n2 / K)) * c->n_chains;
+    const double cost = std::ceil(ctas / slots) * (len + 4.0);
+    if (cost < best_cost) {
+      best_cost = cost;
+      best = (int)S;
+    }
+  }
+  if (best < 1) return r;
+  if (c->js <= 0) c->js_auto[6] = best;
+  r.n_strips = best;
+  r.ok = true;
+  return r;
+}
+
 static int launch_half_sweep(cmg_context *c, int variant, int colour, unsigned long long pass,
                              bool sample, long long slot) {
   SweepArgs A;
@@ -1252,6 +1310,18 @@ static int launch_half_sweep(cmg_context *c, int variant, int colour, unsigned l
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_halfsweep_bulk3d<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBulk3d);
     if (e != cudaSuccess) return fail(c, CMG_ECUDA, cudaGetErrorString(e));
     c->bulk_attr_set = true;
+  }
+  if (variant == V_TMA3D) {
+    const Tma3dPlan tp = plan_tma3d(c);
+    if (!tp.ok) return fail(c, CMG_EUNSUPPORTED, "tma3d does not fit this lattice");
+    A.n_strips = tp.n_strips;
+    dim3 grid((unsigned)(tp.n_strips * (c->shape[2] / tp.K)), c->n_chains);
+    if (sample)
+      k_halfsweep_tma3d<true><<<grid, dim3(128), tp.smem, c->stream>>>(A);
+    else
+      k_halfsweep_tma3d<false><<<grid, dim3(128), tp.smem, c->stream>>>(A);
+    ++c->launches;
+    return CMG_OK;
   }
   A.js = pick_js(c, variant);
   if (variant == V_BULK3D) A.n_strips = pick_strips3d(c, &A.pair_layers);
@@ -1395,6 +1465,7 @@ static const char *variant_str(int v) {
     case V_GENERIC: return "generic";
     case V_BULK2D: return "bulk2d";
     case V_BULK3D: return "bulk3d";
+    case V_TMA3D: return "tma3d";
     case V_TILE2D: return "tile2d";
     default: return "auto";
   }
@@ -1558,6 +1629,8 @@ int cmg_run_passes(cmg_context *c, int64_t n_passes, int mode, int64_t sample_pe
     return fail(c, CMG_EINVAL, "bulk2d needs dim == 2 and n0 % 32 == 0");
   if (variant == V_BULK3D && !(c->dim == 3 && c->shape[0] % 32 == 0))
     return fail(c, CMG_EINVAL, "bulk3d needs dim == 3 and n0 % 32 == 0");
+  if (variant == V_TMA3D && !plan_tma3d(c).ok)
+    return fail(c, CMG_EINVAL, "tma3d needs dim == 3, n0 in {512, 1024}, n1 even and n2 a multiple of 4096 / n0");
   if (variant == V_TILE2D && !plan_tiles(c, 1).ok)
     return fail(c, CMG_EINVAL, "tile2d does not fit this lattice (need dim 2, n0 % 64 == 0, short columns)");
   if (variant == V_RING2D && !plan_ring(c).ok)
@@ -3002,6 +3075,7 @@ int cmg_set_kernel_variant(cmg_context *c, const char *name) {
   else if (s == "generic") c->forced_variant = V_GENERIC;
   else if (s == "bulk2d") c->forced_variant = V_BULK2D;
   else if (s == "bulk3d") c->forced_variant = V_BULK3D;
+  else if (s == "tma3d") c->forced_variant = V_TMA3D;
   else if (s == "tile2d") c->forced_variant = V_TILE2D;
   else if (s == "ring2d") c->forced_variant = V_RING2D;
   else return fail(c, CMG_EINVAL, "unknown kernel variant");

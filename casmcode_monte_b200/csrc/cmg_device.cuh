@@ -1488,6 +1488,187 @@ __global__ void __launch_bounds__(128, CMG_BULK_CTAS) k_halfsweep_bulk3d(SweepAr
 }
 
 // ---------------------------------------------------------------------------
+// k_halfsweep_tma3d: the 3-d half-sweep with the columns moved by the bulk-copy
+// (TMA) engine and shared by the CTA.
+//
+// A CTA of 128 threads owns K = 128 / V consecutive k-layers (V = 16-byte vectors
+// per column) of one strip of columns and walks the strip one column at a time, all
+// K layers abreast.  Stage t of its shared-memory ring holds, for column jbeg + t,
+// the opposite plane of the K + 2 layers k0-1 .. k0+K and (t >= 1) the own plane of
+// the K layers at column jbeg + t - 1: 2K + 2 bulk copies of one whole column each
+// (cp.async.bulk, completion counted in bytes on the stage's `full` mbarrier),
+// issued by the lanes of one warp in one instruction.  Item i (column jbeg + i)
+// reads j+1 and its own vector from stage i + 1 and the two k-neighbours and the
+// p-edge byte from stage i, where column j of the layers above and below was put
+// for THEIR j+1: an opposite-plane vector crosses L2 -> SM (1 + 2/K) times per
+// half-sweep instead of three times (plus the 32-byte sector of the edge word), the
+// threads issue no load instructions for the stream, and the L1 data pipe only
+// carries the LDS.  A stage is released on its `empty` mbarrier (one arrival per
+// warp) when the k-neighbours have been read; warp w refills the stages = w mod 4,
+// four stages ahead.  Same update, same random numbers, same trajectory as every
+// other kernel.  Host side: V in {16, 32} (n0 = 512 or 1024), n2 % K == 0.
+// ---------------------------------------------------------------------------
+constexpr int kTmaStages = 8;
+__device__ __forceinline__ void mbar_arrive(unsigned long long *mbar) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(mbar);
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_bounded(unsigned long long *mbar, unsigned int parity,
+                                                  unsigned int *error) {
+  unsigned int spins = 0;
+  while (!mbar_try_wait(mbar, parity)) {
+    if (++spins > (1u << 22)) {  // bounded (try_wait itself sleeps): report instead of hanging
+      if (error) atomicOr(error, kErrRingCopy);
+      break;
+    }
+  }
+}
+__host__ __device__ inline int tma3d_stage_bytes(int h) {
+  const int V = h >> 4, K = 128 / V;
+  return (2 * K + 2) * h;
+}
+
+template <bool SAMPLE>
+__global__ void __launch_bounds__(128, CMG_BULK_CTAS) k_halfsweep_tma3d(SweepArgs A) {
+  __shared__ __align__(8) unsigned long long s_full[kTmaStages], s_empty[kTmaStages];
+  const LatticeView &L = A.L;
+  const int chain = blockIdx.y;
+  load_accept_table(A.tabs + chain, true);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kTmaStages; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], 4);
+    }
+  }
+  const int h = L.h, n1 = L.n1, n2 = L.n2;
+  const int V = h >> 4, K = 128 / V;
+  const int n_strips = A.n_strips;
+  const int strip = (int)(blockIdx.x % (unsigned)n_strips);
+  const int k0 = (int)(blockIdx.x / (unsigned)n_strips) * K;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // layers of a warp share their parity: with V = 16 a warp holds layers w and w + 4
+  int kk, v;
+  if (V <= 32) {
+    v = lane % V;
+    kk = warp + 4 * (lane / V);
+  } else {
+    const int wpl = V >> 5;
+    kk = warp / wpl;
+    v = (warp % wpl) * 32 + lane;
+  }
+  const int k = k0 + kk;
+  const uint32_t p0 = (uint32_t)v << 4;
+  const long long half = n1 >> 1;
+  const int jbeg = 2 * (int)(((long long)strip * half) / n_strips);
+  const int jend = 2 * (int)(((long long)(strip + 1) * half) / n_strips);
+  const int n = jend - jbeg;
+  const long long layer = (long long)h * n1;
+  uint8_t *Cplane = L.planes + (long long)chain * L.chain_stride + (long long)A.colour * L.plane_stride;
+  const uint8_t *Oall = L.planes + (long long)chain * L.chain_stride + (long long)(1 - A.colour) * L.plane_stride;
+  const uint32_t chain_word = (uint32_t)(chain + A.chain_offset) << 8;
+  const uint32_t SB = (uint32_t)((2 * K + 2) * h);
+  const uint32_t opp_bytes = (uint32_t)((K + 2) * h);
+  const uint32_t ring = (uint32_t)__cvta_generic_to_shared(cmg_smem) + kSmemTile;
+
+  // ---- the loader role (a whole warp; lane l < K+2 copies opposite layer k0-1+l,
+  // lane K+2+m copies own layer k0+m)
+  const uint8_t *src = nullptr;
+  uint32_t dst = 0;
+  if (lane < K + 2) {
+    int kl = k0 - 1 + lane;
+    kl = kl < 0 ? n2 - 1 : (kl >= n2 ? kl - n2 : kl);
+    src = Oall + layer * kl + (long long)h * jbeg;
+    dst = ring + (uint32_t)lane * (uint32_t)h;
+  } else if (lane < 2 * K + 2) {
+    src = Cplane + layer * (k0 + lane - (K + 2)) + (long long)h * (jbeg - 1);
+    dst = ring + opp_bytes + (uint32_t)(lane - (K + 2)) * (uint32_t)h;
+  }
+  auto load_stage = [&](const int t) {
+    if (t > n) return;
+    const int s = t & (kTmaStages - 1), u = t / kTmaStages;
+    if (u >= 1) mbar_wait_bounded(&s_empty[s], (unsigned)(u - 1) & 1u, L.error);
+    if (lane == 0) mbar_expect_tx(&s_full[s], t >= 1 ? SB : opp_bytes);
+    __syncwarp();
+    if (lane < K + 2) {
+      // the column after the last one of the lattice is column 0
+      const long long off = (jbeg + t == n1) ? -(long long)h * jbeg : (long long)h * t;
+      bulk_load(dst + (uint32_t)s * SB, src + off, (unsigned)h, &s_full[s]);
+    } else if (lane < 2 * K + 2 && t >= 1) {
+      bulk_load(dst + (uint32_t)s * SB, src + (long long)h * t, (unsigned)h, &s_full[s]);
+    }
+  };
+  __syncthreads();  // mbarriers initialised, tables in shared memory
+  if (warp < 3) load_stage(warp);
+
+  Accum acc = {0u, 0u, 0u, 0u, 0u};
+  {
+    const uint8_t *O = Oall + layer * k;
+    const int par0 = (jbeg + k + A.colour) & 1;  // i = 2p + par
+    // thread-constant shared-memory offsets inside a stage
+    const uint32_t a_ka = ring + (uint32_t)kk * (uint32_t)h + p0;            // opposite layer k-1
+    const uint32_t a_oc = a_ka + (uint32_t)h;                                // opposite layer k
+    const uint32_t a_kb = a_oc + (uint32_t)h;                                // opposite layer k+1
+    const uint32_t a_ce = ring + opp_bytes + (uint32_t)kk * (uint32_t)h + p0;  // own layer k
+    const uint32_t row = ring + (uint32_t)(kk + 1) * (uint32_t)h;
+    const uint32_t a_e0 = row + ((p0 == 0) ? (uint32_t)h - 1u : p0 - 1u);
+    const uint32_t a_e1 = row + ((p0 + 16u == (uint32_t)h) ? 0u : p0 + 16u);
+    uint4 om = make_uint4(0u, 0u, 0u, 0u), oc = om;
+    if (n > 0) {
+      om = ld16_nc(O + (long long)h * (jbeg == 0 ? n1 - 1 : jbeg - 1) + p0);
+      mbar_wait_bounded(&s_full[0], 0u, L.error);
+      oc = lds16_abs(a_oc);
+    }
+    uint8_t *Cp = Cplane + layer * k + (long long)h * jbeg + p0;
+    unsigned long long g = (unsigned long long)((layer * k + (long long)h * jbeg + p0) >> 3);
+    const unsigned int gstep = (unsigned int)h >> 3;
+    const unsigned int hstep = (unsigned int)h;
+
+    auto item = [&](const int i, const int par) {
+      const uint32_t s1 = (uint32_t)((i + 1) & (kTmaStages - 1)), s0 = (uint32_t)(i & (kTmaStages - 1));
+      const uint32_t o1 = s1 * SB, o0 = s0 * SB;
+      mbar_wait_bounded(&s_full[s1], ((unsigned)(i + 1) / kTmaStages) & 1u, L.error);
+      const uint4 op = lds16_abs(a_oc + o1);
+      const uint4 ce = lds16_abs(a_ce + o1);
+      const uint4 ka = lds16_abs(a_ka + o0);
+      const uint4 kb = lds16_abs(a_kb + o0);
+      const uint32_t eb = lds8_abs((par ? a_e1 : a_e0) + o0);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[s0]);  // stage i: every read of this warp is done
+      if (warp == (i & 3)) load_stage(i + 3);
+      uint4 side = (par == 0) ? shift_up_1(oc, eb) : shift_down_1(oc, eb);
+      side.x += ka.x + kb.x;
+      side.y += ka.y + kb.y;
+      side.z += ka.z + kb.z;
+      side.w += ka.w + kb.w;
+      const uint4 cn = update16<SAMPLE, true>(ce, om, oc, op, side, g, A.pass, A.colour, chain_word,
+                                              A.rk, acc);
+      *reinterpret_cast<uint4 *>(Cp) = cn;
+      Cp += hstep;
+      g += gstep;
+      om = oc;
+      oc = op;
+    };
+    // one hot four-column body for both start parities (see k_halfsweep_bulk3d)
+    int i = 0;
+    if (par0 && n > 0) {
+      item(0, 1);
+      i = 1;
+    }
+    for (; i + 4 <= n; i += 4) {
+      item(i, 0);
+      item(i + 1, 1);
+      item(i + 2, 0);
+      item(i + 3, 1);
+    }
+    for (; i < n; ++i) item(i, (i + par0) & 1);
+  }
+  long long ones = 0, bsum = 0;
+  if (SAMPLE) accum_finish(acc, 6, ones, bsum);
+  block_accumulate<128>(acc.acc, ones, bsum, SAMPLE, A.n_accept + chain,
+                        SAMPLE ? A.sb + (long long)chain * A.sb_chain_stride : nullptr);
+}
+
+// ---------------------------------------------------------------------------
 // Natural-order helpers.  "Natural" = one int8 b per site in the reference's
 // linear order l = i + n0*(j + n1*k) (model.hh:82-99); used at the API edge,
 // by the probes and by the serial reference mode, and as the only layout for

@@ -178,14 +178,14 @@ def test_full_plane_3d_kernel_matches_the_oracle_directly(cm, oracle):
     T, mu, seed, n_passes = 5235.0, 0.05, 77, 3
     occ = np.random.default_rng(5).choice(np.array([-1, 1], dtype=np.int32), size=int(np.prod(shape)))
     ref = oracle.checkerboard_run(shape, occ, E.J, T, mu, seed, 0, 0, n_passes, 1)
-    for variant in ("bulk3d", "auto"):
+    for variant in ("bulk3d", "tma3d", "auto"):
         lat = cm.IsingLatticeGPU(shape, J=E.J)
         lat.set_conditions(T, mu)
         lat.seed_philox(seed)
         lat.set_kernel_variant(variant)
         lat.upload(occ)
         lat.run_passes(n_passes, cm.MODE_CHECKERBOARD, 1)
-        assert lat.kernel_variant == "bulk3d"
+        assert lat.kernel_variant in ("bulk3d", "tma3d") and (variant == "auto" or lat.kernel_variant == variant)
         assert np.array_equal(lat.download(), ref["occupation"])
         S, B = lat.samples_sb()
         assert np.array_equal(S, ref["S"]) and np.array_equal(B, ref["B"])

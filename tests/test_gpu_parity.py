@@ -305,6 +305,38 @@ def test_bulk3d_matches_oracle(cm, oracle, shape):
     assert lat.counters()[1] == ref["n_accept"]
 
 
+# k_halfsweep_tma3d: K = 8 (n0 = 512) or 4 (n0 = 1024) layers per CTA, columns by bulk copies.
+# Shapes: one layer group that is its own k-neighbour (n2 = K), two groups, short strips
+# (n1 = 2: one strip of two columns, the column after the last is column 0), n1 = 22 (ragged
+# strips, start parities differ between the warps of a CTA), two chains.
+@pytest.mark.parametrize("shape,chains", [([512, 2, 8], 1), ([512, 8, 8], 1), ([512, 22, 16], 1), ([1024, 6, 8], 1),
+                                          ([512, 12, 8], 2), ([512, 130, 8], 1)])
+def test_tma3d_matches_oracle(cm, oracle, shape, chains):
+    n = nsites(shape)
+    occs = [rand_occ(n, 23 + ch) for ch in range(chains)]
+    conds = [(5235.0, 0.05), (4000.0, -0.03)][:chains]
+    lat = run_cb(cm, shape, occs if chains > 1 else occs[0], None if chains > 1 else conds[0][0],
+                 None if chains > 1 else conds[0][1], 99, 3,
+                 "tma3d:js=44" if shape[1] == 130 else "tma3d",  # 130 columns: two strips of 64 and 66
+                 n_chains=chains,
+                 chain_conditions=conds if chains > 1 else None)
+    assert lat.kernel_variant == "tma3d"
+    for ch, (T, mu) in enumerate(conds):
+        ref = oracle.checkerboard_run(shape, occs[ch], J, T, mu, 99, ch, 0, 3, 1)
+        assert np.array_equal(lat.download(ch), ref["occupation"])
+        S, B = lat.samples_sb(ch)
+        assert np.array_equal(S, ref["S"]) and np.array_equal(B, ref["B"])
+        assert lat.counters(ch)[1] == ref["n_accept"]
+
+
+def test_tma3d_rejects_lattices_it_cannot_hold(cm):
+    lat = cm.IsingLatticeGPU([256, 8, 8], J=J)
+    lat.set_conditions(5235.0, 0.0)
+    lat.set_kernel_variant("tma3d")
+    with pytest.raises(cm.CmgError, match="tma3d needs"):
+        lat.run_passes(1, cm.MODE_CHECKERBOARD, 0)
+
+
 def test_multichain_grid_matches_oracle(cm, oracle):
     # a 2x3 (T, mu) grid of independent chains, one context (BASELINE config 4 in small)
     shape = [64, 32]

@@ -32,6 +32,7 @@ def main():
         ("2d_grid", [256, 256], 128, ["tile2d:nt=512"], 128),
         ("2d_big", [16384, 16384], 1, ["bulk2d", "bulk2d:js=32"], 20),
         ("3d", [512, 512, 512], 1, ["bulk3d", "bulk3d:js=8", "bulk3d:js=16"], 10),
+        ("3d_tma", [512, 512, 512], 1, ["tma3d", "bulk3d", "tma3d:js=32", "tma3d:js=64", "tma3d:js=128"], 10),
         ("2d_tile", [4096, 4096], 1, ["tile2d:p=2:nt=512", "tile2d:p=3:nt=512", "tile2d:p=4:nt=512", "tile2d:p=3:nt=640", "tile2d:p=4:nt=640", "tile2d:p=3:nt=768", "tile2d:p=3:nt=1024", "tile2d:p=3:nt=256"], 120),
         ("3d_js", [512, 512, 512], 1, ["bulk3d:js=%d" % j for j in (24, 36, 40, 44, 48, 52, 56, 60, 64, 68, 72, 76, 80, 88, 96, 104, 128)], 10),
         ("2d_ring", [4096, 4096], 1, ["ring2d:rp=128", "ring2d:rp=32", "ring2d:rp=256", "tile2d:p=3:nt=512", "bulk2d"], 256),
