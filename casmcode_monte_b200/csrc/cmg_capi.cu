@@ -111,6 +111,7 @@ struct cmg_context {
   int sm_count = 148;
   bool bulk_attr_set = false;
   bool tma3d_attr_set = false;
+  int n_strips2d = 0;  // bulk2d: 0 = automatic, 1 = balanced strips whenever two to four waves of them exist, > 1 = that many
   int js_auto[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // cached strip length per kernel variant
   size_t smem_optin = 0;
   // cmg_mark / cmg_rollback: a restore point (planes, acceptance counters, host counters) and
@@ -261,6 +262,8 @@ static LatticeView view(const cmg_context *c) {
   L.col_offset = c->col_begin;
   L.error = c->d_error;
   if (c->slab) {
+    // every CTA of k_halfsweep_bulk2d inside one strip: the boundary columns go first
+    L.edge_mode = (c->shape[0] / 32) % 128 == 0 ? 1 : 0;
     for (int col = 0; col < 2; ++col) {
       L.halo_lo[col] = c->d_halo[col][0];
       L.halo_hi[col] = c->d_halo[col][1];
@@ -398,8 +401,8 @@ static int create_common(int dim, const int64_t *shape, int n_chains, int device
       }
     CUC(cudaMalloc(&c->d_flags, 2 * sizeof(unsigned long long)));
     CUC(cudaMemset(c->d_flags, 0, 2 * sizeof(unsigned long long)));
-    CUC(cudaMalloc(&c->d_done, sizeof(unsigned int)));
-    CUC(cudaMemset(c->d_done, 0, sizeof(unsigned int)));
+    CUC(cudaMalloc(&c->d_done, 3 * sizeof(unsigned int)));
+    CUC(cudaMemset(c->d_done, 0, 3 * sizeof(unsigned int)));
   }
 #undef CUC
   *out = c;
@@ -1196,6 +1199,51 @@ static int pick_js(cmg_context *c, int variant) {
   return best;
 }
 
+// 2-d: balanced strips (even starts, lengths within two columns of each other), their
+// number chosen to minimise waves * (longest strip + ~4 column-times of start-up) with
+// no upper limit on the strip length: a large lattice runs as ONE wave of long strips
+// (65536 x 8192: 37 strips of 220-222 columns on 592 resident CTAs instead of 256
+// strips of 32 in seven waves, whose start-up cost 14 %).
+static int pick_strips2d(cmg_context *c) {
+  const long long V = c->shape[0] / 32, n1 = c->shape[1];
+  if (c->js > 0 || n1 % 2) return 0;
+  if (c->n_strips2d > 1) return (int)std::min<long long>(c->n_strips2d, n1 / 2);
+  if (c->js_auto[5] != 0) return std::max(c->js_auto[5], 0);
+  // Measured on 65536 x {8192, 16384, 32768, 65536}, 16384^2 and 8 x 4096^2
+  // (profiles/sweep2d_r2s.json): ONE wave of long strips is up to 2.5 % slower than
+  // several waves (every CTA starts at once, so the start-up is exposed and nothing
+  // rebalances a slow SM), and from two waves on the strip count matters by < 2 % --
+  // except when wave quantisation pushes the uniform strips of pick_js below ~64
+  // columns (65536 x 8192: js = 32 in 6.9 waves is 4 % slower than 74 balanced strips
+  // of 110-112 columns in exactly two waves).  Only that case takes balanced strips.
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_halfsweep_bulk2d<true>, 128, kSmemBulk2d) != cudaSuccess || per_sm < 1)
+    per_sm = 4;
+  const double slots = (double)c->sm_count * per_sm;
+  const int js = pick_js(c, V_BULK2D);
+  int best = 0;
+  if (js < 64 || c->n_strips2d == 1) {
+    const double uniform_cost =
+        std::ceil((double)nblocks(V * ((n1 + js - 1) / js), 128) * c->n_chains / slots) * (js + 2.0);
+    double best_cost = c->n_strips2d == 1 ? 1e300 : 0.99 * uniform_cost;
+    for (int waves = 2; waves <= 4; ++waves) {
+      // the largest strip count that still fits `waves` waves
+      long long S = (long long)(waves * slots / c->n_chains) * 128 / V;
+      while (S > 1 && (double)nblocks(V * S, 128) * c->n_chains > waves * slots) --S;
+      if (S < 2 || S > n1 / 2) continue;
+      const double len = std::ceil((double)(n1 / 2) / S) * 2.0;
+      if (len < 64) continue;
+      const double cost = waves * (len + 2.0);
+      if (cost < best_cost) {
+        best_cost = cost;
+        best = (int)S;
+      }
+    }
+  }
+  c->js_auto[5] = best > 0 ? best : -1;
+  return best;
+}
+
 // 3-d: balanced strips, their number chosen so that the CTAs fill the resident
 // places: the launch time is waves * (longest strip + ~4 column-times of start-up).
 // With n0 < 1024 a warp holds several strips; they are made the same strip of
@@ -1325,6 +1373,7 @@ static int launch_half_sweep(cmg_context *c, int variant, int colour, unsigned l
   }
   A.js = pick_js(c, variant);
   if (variant == V_BULK3D) A.n_strips = pick_strips3d(c, &A.pair_layers);
+  if (variant == V_BULK2D) A.n_strips = pick_strips2d(c);
   const long long plane_size = c->n_sites / 2;
   dim3 block(128);
   if (variant == V_GENERIC) {
@@ -1335,7 +1384,7 @@ static int launch_half_sweep(cmg_context *c, int variant, int colour, unsigned l
       k_halfsweep_generic<false><<<grid, block, kSmemSmall, c->stream>>>(A);
   } else if (variant == V_BULK2D) {
     const long long V = c->shape[0] / 32;
-    const long long strips = (c->shape[1] + A.js - 1) / A.js;
+    const long long strips = A.n_strips > 0 ? A.n_strips : (c->shape[1] + A.js - 1) / A.js;
     dim3 grid(nblocks(V * strips, 128), c->n_chains);
     if (sample)
       k_halfsweep_bulk2d<true><<<grid, block, kSmemBulk2d, c->stream>>>(A);
@@ -3056,6 +3105,10 @@ int cmg_set_kernel_variant(cmg_context *c, const char *name) {
     c->tile_passes = atoi(s.c_str() + p + 3);
     if (c->tile_passes < 1 || c->tile_passes > 16) return fail(c, CMG_EINVAL, "bad p");
   }
+  c->n_strips2d = 0;
+  c->js_auto[5] = 0;
+  p = s.find(":ns=");
+  if (p != std::string::npos) c->n_strips2d = std::max(0, atoi(s.c_str() + p + 4));
   p = s.find(":rp=");
   if (p != std::string::npos) {
     c->ring_passes = atoi(s.c_str() + p + 4);

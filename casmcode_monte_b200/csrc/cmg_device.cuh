@@ -66,7 +66,8 @@ struct LatticeView {
   // neighbour's wait flag (peer memory).  Values count finished half-sweeps.
   const unsigned long long *wait_flag[2];
   unsigned long long *signal_flag[2];
-  unsigned int *done_counter;   // CTAs of this launch that have finished
+  unsigned int *done_counter;   // [3]: CTAs of this launch that have finished; edge CTAs done on side 0 / 1
+  int edge_mode;                // slab: the boundary columns are swept, pushed and signalled first (below)
   unsigned long long epoch;     // number of fused half-sweeps stepped before this one
   unsigned int *error;          // sticky error word of the context (bit 2: a neighbour wait timed out)
 };
@@ -573,6 +574,42 @@ __device__ __forceinline__ void slab_signal_neighbours(const LatticeView &L, boo
   }
 }
 
+// Edge mode (every CTA lies inside one strip, at least two strips): only the CTAs of
+// the first and of the last strip touch a halo.  They come first in the grid, sweep
+// the two boundary columns of their strip before the rest of it, push them and raise
+// the neighbour's flag at once -- one column-time into the half-sweep instead of at
+// the end of the launch -- so a neighbour that runs a whole half-sweep behind or
+// ahead never waits.  flag[side] counts the half-sweeps whose edge CTAs on that side
+// are done; a CTA waits for flag >= epoch before it reads that halo, which also
+// orders its push (into the buffer the neighbour read one half-sweep earlier).
+__device__ __forceinline__ void slab_wait_side(const LatticeView &L, int side) {
+  if (L.epoch == 0 || !L.wait_flag[side]) return;
+  if (threadIdx.x == 0 && ld_acquire_sys(L.wait_flag[side]) < L.epoch &&
+      !(L.error && (*(volatile unsigned int *)L.error & kErrSlabWait))) {
+    const unsigned long long t0 = globaltimer_ns();
+    while (ld_acquire_sys(L.wait_flag[side]) < L.epoch) {
+      __nanosleep(64);
+      if (globaltimer_ns() - t0 > kSlabWaitNs) {
+        if (L.error) atomicOr(L.error, kErrSlabWait);
+        break;
+      }
+    }
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ void slab_signal_side(const LatticeView &L, int side, unsigned int n_edge_ctas) {
+  if (!L.done_counter || !L.signal_flag[side]) return;
+  __threadfence_system();  // this thread's peer stores are visible system-wide
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(L.done_counter + 1 + side, 1u);
+    if (prev == n_edge_ctas - 1) {
+      L.done_counter[1 + side] = 0;
+      __threadfence_system();
+      st_release_sys(L.signal_flag[side], L.epoch + 1);
+    }
+  }
+}
 
 // ---- cp.async (LDGSTS) staging: global -> shared without passing through registers
 __device__ __forceinline__ void cp_async16_ca(uint32_t saddr, const void *g) {
@@ -617,14 +654,17 @@ template <bool SAMPLE>
 __global__ void __launch_bounds__(128, CMG_BULK_CTAS) k_halfsweep_bulk2d(SweepArgs A) {
   const LatticeView &L = A.L;
   const int chain = blockIdx.y;
-  slab_wait_neighbours(L);
+  const int h = L.h, n1 = L.n1;
+  const int V = h >> 4;  // 16-byte vectors per column
+  // strips: A.n_strips balanced ones (even starts, lengths within two columns of each
+  // other) or uniform strips of A.js columns
+  const int n_strips = A.n_strips > 0 ? A.n_strips : (n1 + A.js - 1) / A.js;
+  const bool edge_mode = L.edge_mode != 0 && n_strips >= 2;
+  if (!edge_mode) slab_wait_neighbours(L);
   // the table loads are issued first and only waited for (CTA barrier below)
   // after the thread's pipeline has been filled
   load_accept_table(A.tabs + chain, kBulkPair);
 
-  const int h = L.h, n1 = L.n1;
-  const int V = h >> 4;  // 16-byte vectors per column
-  const int n_strips = (n1 + A.js - 1) / A.js;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   Accum acc = {0u, 0u, 0u, 0u, 0u};
   bool pushed = false;
@@ -633,10 +673,20 @@ __global__ void __launch_bounds__(128, CMG_BULK_CTAS) k_halfsweep_bulk2d(SweepAr
     // threads past the end of the lattice run the same code with zero columns
     const bool active = t < (long long)V * n_strips;
     const int v = active ? (int)(t % V) : 0;
-    const int strip = active ? (int)(t / V) : 0;
+    int strip = active ? (int)(t / V) : 0;
+    // edge mode: the last strip is second in the grid (its CTAs start in the first wave)
+    if (edge_mode) strip = strip == 0 ? 0 : (strip == 1 ? n_strips - 1 : strip - 1);
     const int p0 = v << 4;
-    const int jbeg = strip * A.js;
-    const int jend = active ? min(jbeg + A.js, n1) : jbeg;
+    int sbeg, send;
+    if (A.n_strips > 0) {
+      const long long half = n1 >> 1;
+      sbeg = 2 * (int)(((long long)strip * half) / n_strips);
+      send = 2 * (int)(((long long)(strip + 1) * half) / n_strips);
+    } else {
+      sbeg = strip * A.js;
+      send = min(sbeg + A.js, n1);
+    }
+    if (!active) send = sbeg;
     uint8_t *C = L.planes + (long long)chain * L.chain_stride +
                  (long long)A.colour * L.plane_stride;
     const uint8_t *O = L.planes + (long long)chain * L.chain_stride +
@@ -656,100 +706,123 @@ __global__ void __launch_bounds__(128, CMG_BULK_CTAS) k_halfsweep_bulk2d(SweepAr
 
     const int p_below = (p0 == 0) ? h - 1 : p0 - 1;
     const int p_above = (p0 + 16 == h) ? 0 : p0 + 16;
-    // Software pipeline through shared memory: every thread owns a private ring of
-    // kBulkStages slots and keeps the loads of the next kBulkStages columns in
-    // flight with cp.async (LDGSTS), which costs no registers -- with ~270
-    // instructions per column and 4-5 warps per scheduler one column of lookahead
-    // does not cover an HBM round trip.  Slot k & 3 holds, for pipeline step k:
-    // the opposite-plane vector of column jbeg+k+1, the own-plane vector of column
-    // jbeg+k and the aligned word holding the byte across the vector edge of
-    // column jbeg+k.  The column loop is unrolled by the ring size, so slots and
-    // column parities are compile-time constants in the loop body.
-    const int n = jend - jbeg;
-    const long long jg0 = (long long)jbeg + L.col_offset;
-    const int par0 = (int)((jg0 + A.colour) & 1);  // i = 2p + par
-    const uint8_t *Oend = ocol(jend) + p0;  // column jend of the opposite plane (wrap / halo)
     const uint32_t ring = (uint32_t)__cvta_generic_to_shared(cmg_smem) + kSmemRing;
     const uint32_t s_o = ring + threadIdx.x * 16u;
     const uint32_t s_c = ring + 128u * 16u + threadIdx.x * 16u;
     const uint32_t s_e = ring + 128u * 32u + threadIdx.x * 4u;
     const unsigned int hstep = (unsigned int)h;
-    const uint8_t *Of = O + (long long)h * (jbeg + 1) + p0;  // fetch front, opposite plane
-    const uint8_t *Cf = C + (long long)h * jbeg + p0;        // fetch front, own plane
-    const uint8_t *Ef = O + (long long)h * jbeg;             // fetch front, edge words
     const int e_lo = p_below & ~3, e_hi = p_above;           // byte 3 / byte 0 of the word
-    auto fetch = [&](const int k, const int par) {
-      if (k < n) {
-        const uint32_t slot = (uint32_t)(k & (kBulkStages - 1)) * kBulkStageBytes;
-        cp_async16_ca(s_o + slot, (k + 1 >= n) ? Oend : Of);
-        cp_async16_cg(s_c + slot, Cf);
-        cp_async4_ca(s_e + slot, Ef + (par ? e_hi : e_lo));
-        Of += hstep;
-        Cf += hstep;
-        Ef += hstep;
-      }
-      cp_async_commit();
-    };
-    uint4 om = make_uint4(0u, 0u, 0u, 0u), oc = om;
-    if (n > 0) {
-      om = ld16_nc(ocol(jbeg - 1) + p0);
-      oc = ld16_nc(O + (long long)h * jbeg + p0);
-    }
-#pragma unroll
-    for (int k = 0; k < kBulkStages; ++k) fetch(k, par0 ^ (k & 1));
-    __syncthreads();  // acceptance tables are in shared memory
-    uint8_t *Cp = C + (long long)h * jbeg + p0;  // own plane, column j
-    unsigned long long g = (unsigned long long)(((long long)h * jg0 + p0) >> 3);
     const unsigned int gstep = (unsigned int)h >> 3;
 
-    auto column = [&](const int it, const int par) {
-      const uint32_t slot = (uint32_t)(it & (kBulkStages - 1)) * kBulkStageBytes;
-      cp_async_wait<kBulkStages - 1>();
-      const uint4 op = lds16_abs(s_o + slot);
-      const uint4 ce = lds16_abs(s_c + slot);
-      const uint32_t eb = lds8_abs(s_e + slot + (par ? 0u : 3u));
-      fetch(it + kBulkStages, par);
-      const uint4 side = (par == 0) ? shift_up_1(oc, eb) : shift_down_1(oc, eb);
-      const uint4 cn = update16<SAMPLE, kBulkPair>(ce, om, oc, op, side, g, A.pass, A.colour, chain_word,
-                                        A.rk, acc);
-      *reinterpret_cast<uint4 *>(Cp) = cn;
-      Cp += hstep;
-      g += gstep;
-      om = oc;
-      oc = op;
-    };
-    auto strip_loop = [&](auto par_tag) {
-      constexpr int P0 = decltype(par_tag)::value;
-      static_assert(kBulkStages == 4, "the column loop is unrolled by the ring size");
-      int it = 0;
-      for (; it + 4 <= n; it += 4) {
-        column(it, P0);
-        column(it + 1, P0 ^ 1);
-        column(it + 2, P0);
-        column(it + 3, P0 ^ 1);
+    // Edge mode: a CTA of the first (last) strip sweeps the two columns at the slab
+    // boundary as a segment of their own, ahead of the rest of its strip.  (In edge
+    // mode every CTA lies inside one strip, so the segments are CTA-uniform.)
+    const int edge_side = !edge_mode ? -1 : (sbeg == 0 ? 0 : (send == n1 ? 1 : -1));
+    const int n_seg = (edge_side >= 0 && send - sbeg > 2) ? 2 : 1;
+    for (int sg = 0; sg < n_seg; ++sg) {
+      int jbeg = sbeg, jend = send;
+      if (n_seg == 2) {
+        if (edge_side == 0) {
+          jbeg = sg == 0 ? 0 : 2;
+          jend = sg == 0 ? 2 : send;
+        } else {
+          jbeg = sg == 0 ? n1 - 2 : sbeg;
+          jend = sg == 0 ? n1 : n1 - 2;
+        }
       }
-      for (; it < n; ++it) column(it, P0 ^ (it & 1));
-    };
-    if (par0) {
-      strip_loop(std::integral_constant<int, 1>{});
-    } else {
-      strip_loop(std::integral_constant<int, 0>{});
-    }
-    // slab decomposition: the boundary columns also go to the neighbours' halos
-    if (active && push_lo && jbeg == 0) {
-      *reinterpret_cast<uint4 *>(push_lo + p0) = ld16(C + p0);
-      pushed = true;
-    }
-    if (active && push_hi && jend == n1) {
-      *reinterpret_cast<uint4 *>(push_hi + p0) = ld16(C + (long long)h * (n1 - 1) + p0);
-      pushed = true;
+      const bool edge_seg = edge_side >= 0 && sg == 0;
+      if (edge_seg) slab_wait_side(L, edge_side);
+      // Software pipeline through shared memory: every thread owns a private ring of
+      // kBulkStages slots and keeps the loads of the next kBulkStages columns in
+      // flight with cp.async (LDGSTS), which costs no registers -- with ~270
+      // instructions per column and 4-5 warps per scheduler one column of lookahead
+      // does not cover an HBM round trip.  Slot k & 3 holds, for pipeline step k:
+      // the opposite-plane vector of column jbeg+k+1, the own-plane vector of column
+      // jbeg+k and the aligned word holding the byte across the vector edge of
+      // column jbeg+k.  The column loop is unrolled by the ring size, so slots and
+      // column parities are compile-time constants in the loop body.
+      const int n = jend - jbeg;
+      const long long jg0 = (long long)jbeg + L.col_offset;
+      const int par0 = (int)((jg0 + A.colour) & 1);  // i = 2p + par
+      const uint8_t *Oend = ocol(jend) + p0;  // column jend of the opposite plane (wrap / halo)
+      const uint8_t *Of = O + (long long)h * (jbeg + 1) + p0;  // fetch front, opposite plane
+      const uint8_t *Cf = C + (long long)h * jbeg + p0;        // fetch front, own plane
+      const uint8_t *Ef = O + (long long)h * jbeg;             // fetch front, edge words
+      auto fetch = [&](const int k, const int par) {
+        if (k < n) {
+          const uint32_t slot = (uint32_t)(k & (kBulkStages - 1)) * kBulkStageBytes;
+          cp_async16_ca(s_o + slot, (k + 1 >= n) ? Oend : Of);
+          cp_async16_cg(s_c + slot, Cf);
+          cp_async4_ca(s_e + slot, Ef + (par ? e_hi : e_lo));
+          Of += hstep;
+          Cf += hstep;
+          Ef += hstep;
+        }
+        cp_async_commit();
+      };
+      uint4 om = make_uint4(0u, 0u, 0u, 0u), oc = om;
+      if (n > 0) {
+        om = ld16_nc(ocol(jbeg - 1) + p0);
+        oc = ld16_nc(O + (long long)h * jbeg + p0);
+      }
+#pragma unroll
+      for (int k = 0; k < kBulkStages; ++k) fetch(k, par0 ^ (k & 1));
+      __syncthreads();  // acceptance tables are in shared memory
+      uint8_t *Cp = C + (long long)h * jbeg + p0;  // own plane, column j
+      unsigned long long g = (unsigned long long)(((long long)h * jg0 + p0) >> 3);
+
+      auto column = [&](const int it, const int par) {
+        const uint32_t slot = (uint32_t)(it & (kBulkStages - 1)) * kBulkStageBytes;
+        cp_async_wait<kBulkStages - 1>();
+        const uint4 op = lds16_abs(s_o + slot);
+        const uint4 ce = lds16_abs(s_c + slot);
+        const uint32_t eb = lds8_abs(s_e + slot + (par ? 0u : 3u));
+        fetch(it + kBulkStages, par);
+        const uint4 side = (par == 0) ? shift_up_1(oc, eb) : shift_down_1(oc, eb);
+        const uint4 cn = update16<SAMPLE, kBulkPair>(ce, om, oc, op, side, g, A.pass, A.colour, chain_word,
+                                          A.rk, acc);
+        *reinterpret_cast<uint4 *>(Cp) = cn;
+        Cp += hstep;
+        g += gstep;
+        om = oc;
+        oc = op;
+      };
+      auto strip_loop = [&](auto par_tag) {
+        constexpr int P0 = decltype(par_tag)::value;
+        static_assert(kBulkStages == 4, "the column loop is unrolled by the ring size");
+        int it = 0;
+        for (; it + 4 <= n; it += 4) {
+          column(it, P0);
+          column(it + 1, P0 ^ 1);
+          column(it + 2, P0);
+          column(it + 3, P0 ^ 1);
+        }
+        for (; it < n; ++it) column(it, P0 ^ (it & 1));
+      };
+      if (par0) {
+        strip_loop(std::integral_constant<int, 1>{});
+      } else {
+        strip_loop(std::integral_constant<int, 0>{});
+      }
+      // slab decomposition: the boundary columns also go to the neighbours' halos
+      if (!edge_mode || edge_seg) {
+        if (active && push_lo && jbeg == 0) {
+          *reinterpret_cast<uint4 *>(push_lo + p0) = ld16(C + p0);
+          pushed = true;
+        }
+        if (active && push_hi && jend == n1) {
+          *reinterpret_cast<uint4 *>(push_hi + p0) = ld16(C + (long long)h * (n1 - 1) + p0);
+          pushed = true;
+        }
+      }
+      if (edge_seg) slab_signal_side(L, edge_side, (unsigned int)(V >> 7) * gridDim.y);
     }
   }
   long long ones = 0, bsum = 0;
   if (SAMPLE) accum_finish(acc, 4, ones, bsum);
   block_accumulate<128>(acc.acc, ones, bsum, SAMPLE, A.n_accept + chain,
                         SAMPLE ? A.sb + (long long)chain * A.sb_chain_stride : nullptr);
-  slab_signal_neighbours(L, pushed);
+  if (!edge_mode) slab_signal_neighbours(L, pushed);
 }
 
 // ---------------------------------------------------------------------------

@@ -493,9 +493,11 @@ def test_run_with_overlapped_checks_gives_the_same_results(api):
         p = api.sampling.CompletionCheckParams()
         p.cutoff_params.min_sample = 50
         p.cutoff_params.max_sample = 900
+        p.log_spacing = False  # a check every 25 samples from 50 on
         p.check_begin = 50
         p.check_period = 25
-        api.sampling.converge(fns, p).set_precision("potential_energy", abs=2e-4).set_precision("param_composition", abs=2e-4)
+        # (oracle, same conditions: the composition reaches 6e-3 after ~250 samples, 2.7e-3 after 900)
+        api.sampling.converge(fns, p).set_precision("potential_energy", abs=2e-3).set_precision("param_composition", abs=6e-3)
         state = make_state(api, (64, 64), 3200.0, 0.03)
         e = api.monte.RandomNumberEngine()
         e.seed(77)

@@ -26,12 +26,16 @@ def main():
     out = []
     cases = [
         ("2d", [4096, 4096], 1, ["bulk2d", "bulk2d:js=8", "tile2d:p=3:nt=512"], 120),
-        ("2d_sweep8", [4096, 4096], 8, ["bulk2d", "bulk2d:js=16", "bulk2d:js=32", "tile2d:p=3:nt=512"], 48),
+        ("2d_sweep8", [4096, 4096], 8, ["bulk2d", "bulk2d:ns=1", "bulk2d:js=32", "tile2d:p=3:nt=512"], 48),
         ("2d_sweep8_js", [4096, 4096], 8, ["bulk2d:js=28", "bulk2d:js=56", "bulk2d:js=52", "bulk2d:js=60", "bulk2d:js=19", "bulk2d:js=14"], 48),
         ("2d_big_js", [16384, 16384], 1, ["bulk2d", "bulk2d:js=56", "bulk2d:js=112", "bulk2d:js=20"], 20),
         ("2d_grid", [256, 256], 128, ["tile2d:nt=512"], 128),
-        ("2d_big", [16384, 16384], 1, ["bulk2d", "bulk2d:js=32"], 20),
+        ("2d_big", [16384, 16384], 1, ["bulk2d", "bulk2d:ns=296", "bulk2d:ns=444", "bulk2d:ns=592"], 20),
         ("3d", [512, 512, 512], 1, ["bulk3d", "bulk3d:js=8", "bulk3d:js=16"], 10),
+        ("2d_slab8", [65536, 8192], 1, ["bulk2d", "bulk2d:ns=1", "bulk2d:ns=74", "bulk2d:ns=111"], 6),
+        ("2d_slab2", [65536, 32768], 1, ["bulk2d", "bulk2d:ns=74", "bulk2d:ns=111", "bulk2d:ns=148", "bulk2d:ns=296"], 4),
+        ("2d_slab4", [65536, 16384], 1, ["bulk2d", "bulk2d:ns=74", "bulk2d:ns=111", "bulk2d:ns=148", "bulk2d:ns=222"], 4),
+        ("2d_one", [65536, 65536], 1, ["bulk2d", "bulk2d:ns=74", "bulk2d:ns=148", "bulk2d:ns=296"], 2),
         ("3d_tma", [512, 512, 512], 1, ["tma3d", "bulk3d", "tma3d:js=32", "tma3d:js=64", "tma3d:js=128"], 10),
         ("2d_tile", [4096, 4096], 1, ["tile2d:p=2:nt=512", "tile2d:p=3:nt=512", "tile2d:p=4:nt=512", "tile2d:p=3:nt=640", "tile2d:p=4:nt=640", "tile2d:p=3:nt=768", "tile2d:p=3:nt=1024", "tile2d:p=3:nt=256"], 120),
         ("3d_js", [512, 512, 512], 1, ["bulk3d:js=%d" % j for j in (24, 36, 40, 44, 48, 52, 56, 60, 64, 68, 72, 76, 80, 88, 96, 104, 128)], 10),
