@@ -102,6 +102,11 @@ struct cmg_context {
   int ring_passes = 128;  // passes per cooperative launch of the ring kernel
   uint8_t *d_ring_mailbox = nullptr;  // [n_chains][n_tiles][side][plane][h]
   size_t ring_mailbox_bytes = 0;
+  // slab ring (k_ring2d continuing on the neighbour GPUs): the neighbours' mailboxes
+  uint8_t *ring_peer_mb[2] = {nullptr, nullptr};
+  int ring_peer_tiles[2] = {0, 0};
+  int ring_tiles_cap = 0;              // "ring2d:rt=<n>": at most n tiles (several rings on one GPU)
+  unsigned long long ring_s0 = 0;      // half-sweeps the ring has stepped since the peers were attached
   // sticky device error word (kErr* bits, raised with atomicOr by kernels whose
   // waits are bounded) and its pinned host copy; zeroed at create and after a
   // failure has been reported
@@ -1119,7 +1124,8 @@ struct RingPlan {
 };
 static RingPlan plan_ring(const cmg_context *c) {
   RingPlan r;
-  if (c->dim != 2 || c->slab || !c->coop_launch || c->shape[0] % 1024 != 0) return r;
+  // (a slab runs resident only as part of a ring of slabs: cmg_slab_run_passes checks the peers)
+  if (c->dim != 2 || !c->coop_launch || c->shape[0] % 1024 != 0) return r;
   const long long h = c->shape[0] / 2, n1 = c->shape[1], V = h / 16;
   if (V > 256 || 512 % V != 0) return r;  // at least two column groups per CTA
   const long long Q = 512 / V;
@@ -1131,6 +1137,7 @@ static RingPlan plan_ring(const cmg_context *c) {
   // 27-column tiles to absorb the jitter of the edge exchange).
   long long n_tiles = c->sm_count / c->n_chains;
   if (c->aux && c->n_chains == 1 && n_tiles > 2 && (n1 + n_tiles - 2) / (n_tiles - 1) == (n1 + n_tiles - 1) / n_tiles) n_tiles -= 1;
+  if (c->ring_tiles_cap > 0) n_tiles = std::min<long long>(n_tiles, c->ring_tiles_cap);
   n_tiles = std::min(n_tiles, n1 / (2 * Q));
   if (n_tiles < 2) return r;
   const long long w_max = (n1 + n_tiles - 1) / n_tiles;
@@ -1463,19 +1470,30 @@ static int launch_tile_passes_sp(cmg_context *c, const TilePlan &tp, int n_passe
 }
 
 static int launch_ring_passes(cmg_context *c, const RingPlan &rp, int n_passes,
-                              long long sample_period) {
+                              long long sample_period, bool publish_first = false) {
   // edge mailbox: per tile and side one column of each plane; zeroed before every
   // launch because its bytes carry the half-sweep stamp that validates them
   const size_t mb_bytes = (size_t)c->n_chains * rp.n_tiles * 4 * (size_t)(c->shape[0] / 2);
+  const bool peers = c->ring_peer_mb[0] && c->ring_peer_mb[1];
   if (c->ring_mailbox_bytes < mb_bytes) {
+    if (peers) return fail(c, CMG_ESTATE, "ring2d: the mailbox the neighbours write into cannot grow");
     cudaFree(c->d_ring_mailbox);
     c->d_ring_mailbox = nullptr;
     CU(c, cudaMalloc(&c->d_ring_mailbox, mb_bytes));
     c->ring_mailbox_bytes = mb_bytes;
   }
-  CU(c, cudaMemsetAsync(c->d_ring_mailbox, 0, mb_bytes, c->stream));
+  // (a mailbox the neighbour GPUs write into is never zeroed: their edges may arrive before
+  // this launch starts; its stamps count the half-sweeps of the whole trajectory instead)
+  if (!peers) CU(c, cudaMemsetAsync(c->d_ring_mailbox, 0, mb_bytes, c->stream));
   RingArgs A;
   memset(&A, 0, sizeof A);
+  if (peers) {
+    for (int side = 0; side < 2; ++side) {
+      A.peer_mb[side] = c->ring_peer_mb[side];
+      A.peer_tiles[side] = c->ring_peer_tiles[side];
+    }
+    A.stamp0 = (uint32_t)(c->ring_s0 % 127ull);
+  }
   A.L = view(c);
   A.tabs = c->d_tabs;
   A.n_accept = c->d_n_accept;
@@ -1504,10 +1522,34 @@ static int launch_ring_passes(cmg_context *c, const RingPlan &rp, int n_passes,
   void *args[] = {&A};
   // cooperative: the grid starts only when every CTA can be resident, which
   // the edge waits between neighbouring tiles rely on
+  if (peers && publish_first) {
+    const int V = (int)(c->shape[0] / 32);
+    k_ring_publish<<<dim3((unsigned)nblocks(V, 128), 2), 128, 0, c->stream>>>(A);
+    ++c->launches;
+  }
   e = cudaLaunchCooperativeKernel((const void *)k_ring2d<512>, grid, dim3(512), args, rp.smem,
                                   c->stream);
   if (e != cudaSuccess) return fail(c, CMG_ECUDA, cudaGetErrorString(e));
   ++c->launches;
+  if (peers) c->ring_s0 += 2ull * (unsigned long long)n_passes;
+  return CMG_OK;
+}
+
+// the mailbox of a slab that may become part of a ring of slabs: allocated (and zeroed) once,
+// before its address is handed to the neighbours
+static int ensure_ring_mailbox(cmg_context *c, int *n_tiles) {
+  *n_tiles = 0;
+  const RingPlan rp = plan_ring(c);
+  if (!rp.ok) return CMG_OK;
+  const size_t mb_bytes = (size_t)c->n_chains * rp.n_tiles * 4 * (size_t)(c->shape[0] / 2);
+  if (c->ring_mailbox_bytes < mb_bytes) {
+    cudaFree(c->d_ring_mailbox);
+    c->d_ring_mailbox = nullptr;
+    CU(c, cudaMalloc(&c->d_ring_mailbox, mb_bytes));
+    c->ring_mailbox_bytes = mb_bytes;
+    CU(c, cudaMemset(c->d_ring_mailbox, 0, mb_bytes));
+  }
+  *n_tiles = rp.n_tiles;
   return CMG_OK;
 }
 
@@ -1784,6 +1826,52 @@ int cmg_slab_run_passes(cmg_context *c, int64_t n_passes, int64_t sample_period)
     return fail(c, CMG_ESTATE,
                 "cmg_slab_run_passes needs both neighbours attached (cmg_slab_ipc_attach); drivers "
                 "with their own halo exchange step cmg_slab_half_sweep");
+  if (c->forced_variant == V_RING2D) {
+    // The slab stays resident in shared memory and its outer tiles exchange their edge
+    // columns with the neighbour GPUs' outer tiles through the mailboxes (peer stores over
+    // NVLink inside the cooperative kernel): one launch per GPU per block of passes.
+    if (!c->slab_exchange || !(c->ring_peer_mb[0] && c->ring_peer_mb[1]))
+      return fail(c, CMG_ESTATE, "ring2d on a slab needs both neighbours attached with a slab that can run resident too");
+    int rc = check_ready(c);
+    if (rc) return rc;
+    const RingPlan rp = plan_ring(c);
+    if (!rp.ok) return fail(c, CMG_EINVAL, "ring2d does not fit this slab");
+    long long n_new = 0;
+    if (sample_period > 0) n_new = (c->n_pass + n_passes) / sample_period - c->n_pass / sample_period;
+    rc = ensure_series(c, c->n_samples + n_new);
+    if (rc) return rc;
+    c->nat_is_current = false;
+    c->variant_name = "ring2d";
+    // every call starts two stamps further on: what its first half-sweep consumes can only
+    // come from the publish kernels of THIS call, whatever happened to the state in between
+    // (upload, rollback); every rank of the ring makes the same calls
+    c->ring_s0 += 2;
+    long long left = n_passes;
+    bool first = true;
+    while (left > 0) {
+      const long long P = std::min<long long>(left, c->ring_passes);
+      rc = launch_ring_passes(c, rp, (int)P, sample_period, first);
+      if (rc) return rc;
+      first = false;
+      long long n_new_here = 0;
+      if (sample_period > 0) n_new_here = (c->n_pass + P) / sample_period - c->n_pass / sample_period;
+      c->h_pass += P;
+      c->n_pass += P;
+      c->n_samples += n_new_here;
+      left -= P;
+    }
+    if (n_passes > 0) {
+      // leave the halos as the streaming kernel would: the neighbours' copies of our boundary
+      // columns current, their flags one epoch further on
+      LatticeView L = view(c);
+      L.epoch = c->slab_epoch;
+      k_slab_push_edges<<<dim3((unsigned)nblocks(c->shape[0] / 32, 128), 4), 128, 0, c->stream>>>(L);
+      ++c->launches;
+      ++c->slab_epoch;
+    }
+    CU(c, cudaGetLastError());
+    return CMG_OK;
+  }
   for (int64_t t = 0; t < n_passes; ++t) {
     const int sample = sample_period > 0 && ((c->n_pass + 1) % sample_period) == 0;
     const unsigned long long pass = c->h_pass;
@@ -1826,18 +1914,27 @@ int cmg_slab_halo_ptr(cmg_context *c, int colour, int side, void **dev_ptr, int6
 struct SlabIpcBlob {
   cudaIpcMemHandle_t h[2][2];
   cudaIpcMemHandle_t flags;
+  cudaIpcMemHandle_t mailbox;  // k_ring2d's edge mailbox (valid when ring_tiles > 0)
+  int ring_tiles;              // tiles of the resident kernel on this slab, 0: it cannot run resident
+  int pad;
 };
 
 int cmg_slab_ipc_export(cmg_context *c, void *handle_out, int64_t handle_bytes) {
   NEED(c);
   if (!c->slab) return fail(c, CMG_ESTATE, "not a slab context");
   if (!handle_out || handle_bytes < (int64_t)sizeof(SlabIpcBlob))
-    return fail(c, CMG_EINVAL, "handle buffer too small (need 320 bytes)");
+    return fail(c, CMG_EINVAL, "handle buffer too small (need 392 bytes)");
   SlabIpcBlob blob;
+  memset(&blob, 0, sizeof blob);
   for (int col = 0; col < 2; ++col)
     for (int side = 0; side < 2; ++side)
       CU(c, cudaIpcGetMemHandle(&blob.h[col][side], c->d_halo[col][side]));
   CU(c, cudaIpcGetMemHandle(&blob.flags, c->d_flags));
+  {
+    const int rc = ensure_ring_mailbox(c, &blob.ring_tiles);
+    if (rc) return rc;
+    if (blob.ring_tiles > 0) CU(c, cudaIpcGetMemHandle(&blob.mailbox, c->d_ring_mailbox));
+  }
   memcpy(handle_out, &blob, sizeof blob);
   return CMG_OK;
 }
@@ -1862,6 +1959,14 @@ int cmg_slab_ipc_attach(cmg_context *c, int side, const void *handle, int64_t ha
     }
     for (int col = 0; col < 2; ++col) c->push[col][side] = peer->d_halo[col][1 - side];
     c->peer_flag[side] = peer->d_flags + (1 - side);
+    {
+      int mine = 0, theirs = 0;
+      int rc = ensure_ring_mailbox(c, &mine);
+      if (rc == CMG_OK) rc = ensure_ring_mailbox(peer, &theirs);
+      if (rc) return rc;
+      c->ring_peer_mb[side] = (mine > 0 && theirs > 0) ? peer->d_ring_mailbox : nullptr;
+      c->ring_peer_tiles[side] = theirs;
+    }
     return CMG_OK;
   }
   if (!handle || handle_bytes < (int64_t)sizeof(SlabIpcBlob))
@@ -1879,6 +1984,19 @@ int cmg_slab_ipc_attach(cmg_context *c, int side, const void *handle, int64_t ha
     CU(c, cudaIpcOpenMemHandle(&p, blob.flags, cudaIpcMemLazyEnablePeerAccess));
     c->ipc_opened.push_back(p);
     c->peer_flag[side] = (unsigned long long *)p + (1 - side);
+  }
+  {
+    int mine = 0;
+    const int rc = ensure_ring_mailbox(c, &mine);
+    if (rc) return rc;
+    c->ring_peer_mb[side] = nullptr;
+    c->ring_peer_tiles[side] = blob.ring_tiles;
+    if (mine > 0 && blob.ring_tiles > 0) {
+      void *p = nullptr;
+      CU(c, cudaIpcOpenMemHandle(&p, blob.mailbox, cudaIpcMemLazyEnablePeerAccess));
+      c->ipc_opened.push_back(p);
+      c->ring_peer_mb[side] = (uint8_t *)p;
+    }
   }
   return CMG_OK;
 }
@@ -3110,6 +3228,11 @@ int cmg_set_kernel_variant(cmg_context *c, const char *name) {
   }
   c->n_strips2d = 0;
   c->js_auto[5] = 0;
+  p = s.find(":rt=");
+  if (p != std::string::npos) {
+    if (c->ring_peer_mb[0] || c->ring_peer_mb[1]) return fail(c, CMG_ESTATE, "rt cannot change once ring peers are attached");
+    c->ring_tiles_cap = std::max(0, atoi(s.c_str() + p + 4));
+  }
   p = s.find(":ns=");
   if (p != std::string::npos) c->n_strips2d = std::max(0, atoi(s.c_str() + p + 4));
   p = s.find(":rp=");

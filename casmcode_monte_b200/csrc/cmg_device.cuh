@@ -1140,8 +1140,19 @@ struct RingArgs {
   int w_max;                     // widest tile (smem plane = w_max*h bytes)
   uint32_t v_magic;              // ceil(2^32 / V), V = h/16
   int chain_offset;              // global index of chain 0
-  uint8_t *mailbox;              // [chain][tile][side][plane][h], zero at launch
+  uint8_t *mailbox;              // [chain][tile][side][plane][h]: what ARRIVES at `side` of `tile`
   unsigned int *error;           // the context's sticky error word (edge wait / bulk copy timed out)
+  // A ring that continues on other GPUs (column slabs of one lattice, one cooperative
+  // launch per GPU): the outer edge of the first / last tile is published into the
+  // mailbox of the low / high neighbour GPU (peer memory over NVLink; null: the ring
+  // closes on this GPU) and consumed from our own, with system scope.  The stamps then
+  // count the half-sweeps of the whole trajectory (stamp0 = half-sweeps before this
+  // launch, mod 127), the mailbox is never zeroed, and the outer edges of the first
+  // half-sweep of a launch come from the mailbox too (the last half-sweep of the
+  // previous launch, or k_ring_publish, put them there).
+  uint8_t *peer_mb[2];
+  int peer_tiles[2];             // tiles per chain on that neighbour
+  uint32_t stamp0;
 };
 constexpr int kRingMaxPasses = 256;
 
@@ -1155,6 +1166,19 @@ __device__ __forceinline__ uint4 ld_relaxed_gpu_v4(const void *p) {
 }
 __device__ __forceinline__ void st_relaxed_gpu_v4(void *p, uint4 v) {
   asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y),
+               "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ uint4 ld_relaxed_sys_v4(const void *p) {
+  uint4 v;
+  asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_sys_v4(void *p, uint4 v) {
+  asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y),
                "r"(v.z), "r"(v.w)
                : "memory");
 }
@@ -1266,15 +1290,31 @@ __global__ void __launch_bounds__(NT, 1) k_ring2d(RingArgs A) {
   const long long dg = down ? -(long long)gstep : (long long)gstep;
   const uint32_t e_lo = (p0 == 0) ? (uint32_t)h - 1u : p0 - 1u;
   const uint32_t e_hi = (p0 + 16u == (uint32_t)h) ? 0u : p0 + 16u;
-  // mailbox slots: ours (publish) and the facing one of the neighbour (consume)
-  const int nb = down ? (tile + 1 == A.n_tiles ? 0 : tile + 1) : (tile == 0 ? A.n_tiles - 1 : tile - 1);
+  // mailbox slots, indexed by the CONSUMER: we publish into the slot of the neighbouring
+  // tile's side that faces us (on the neighbour GPU for the outer edges of a slab) and
+  // consume what arrives at our own side
+  int nb = down ? (tile + 1 == A.n_tiles ? 0 : tile + 1) : (tile == 0 ? A.n_tiles - 1 : tile - 1);
+  uint8_t *out_base = A.mailbox;
+  int out_tiles = A.n_tiles;
+  bool remote = false;
+  if (down && tile + 1 == A.n_tiles && A.peer_mb[1]) {
+    remote = true;
+    out_base = A.peer_mb[1];
+    out_tiles = A.peer_tiles[1];
+    nb = 0;
+  } else if (!down && tile == 0 && A.peer_mb[0]) {
+    remote = true;
+    out_base = A.peer_mb[0];
+    out_tiles = A.peer_tiles[0];
+    nb = out_tiles - 1;
+  }
   const long long slot_bytes = 2ll * h;  // two planes per (tile, side)
-  uint8_t *mb_out = A.mailbox + (((long long)chain * A.n_tiles + tile) * 2 + (down ? 1 : 0)) * slot_bytes + p0;
-  const uint8_t *mb_in = A.mailbox + (((long long)chain * A.n_tiles + nb) * 2 + (down ? 0 : 1)) * slot_bytes + p0;
+  uint8_t *mb_out = out_base + (((long long)chain * out_tiles + nb) * 2 + (down ? 0 : 1)) * slot_bytes + p0;
+  const uint8_t *mb_in = A.mailbox + (((long long)chain * A.n_tiles + tile) * 2 + (down ? 1 : 0)) * slot_bytes + p0;
   // the neighbour's edge column at home (first half-sweep of the launch)
   const int gc_nb = down ? (c1 == n1 ? 0 : c1) : (c0 == 0 ? n1 - 1 : c0 - 1);
-  uint4 hv = make_uint4(0u, 0u, 0u, 0u);
-  if (edge) hv = __ldcg(reinterpret_cast<const uint4 *>(G[1] + (long long)gc_nb * h + p0));
+  uint4 hv = make_uint4(0u, 0u, 0u, 0u);  // (no stamp: an outer edge polls its mailbox at once)
+  if (edge && !remote) hv = __ldcg(reinterpret_cast<const uint4 *>(G[1] + (long long)gc_nb * h + p0));
   __syncthreads();
 
   unsigned int n_acc = 0;
@@ -1287,20 +1327,20 @@ __global__ void __launch_bounds__(NT, 1) k_ring2d(RingArgs A) {
                         ((A.pass_phase + pl + 1) % A.sample_period) == 0;
     const uint32_t cbase = colour ? soff[1] : soff[0];
     const uint32_t obase = colour ? soff[0] : soff[1];
-    const uint32_t stampw = ((uint32_t)(s % 127) + 1u) * 0x02020202u;  // this half-sweep's stamp << 1
+    const uint32_t stampw = ((A.stamp0 + (uint32_t)s) % 127u + 1u) * 0x02020202u;  // this half-sweep's stamp << 1
     Accum acc = {0u, 0u, 0u, 0u, 0u};
 
     int cl = cl_first;
     uint32_t coff = (uint32_t)(cl * h);
-    unsigned long long g = (unsigned long long)gstep * (uint32_t)(c0 + cl) + (p0 >> 3);
+    unsigned long long g = (unsigned long long)gstep * (unsigned long long)(L.col_offset + c0 + cl) + (p0 >> 3);
     // the column behind the start of the run: the neighbour's edge, or shared memory
     uint4 om;
     if (edge) {
-      if (s > 0) {
-        const uint32_t expect = ((uint32_t)((s - 1) % 127) + 1u) * 0x02020202u;
+      if (s > 0 || remote) {
+        const uint32_t expect = ((A.stamp0 + (uint32_t)s + 126u) % 127u + 1u) * 0x02020202u;
         unsigned int spins = 0;
         while (!ring_stamp_ok(hv, expect)) {
-          hv = ld_relaxed_gpu_v4(mb_in + (colour ^ 1) * h);
+          hv = remote ? ld_relaxed_sys_v4(mb_in + (colour ^ 1) * h) : ld_relaxed_gpu_v4(mb_in + (colour ^ 1) * h);
           if (++spins > (1u << 22)) {  // bounded: report instead of hanging the GPU
             atomicOr(A.error, kErrRingEdge);
             break;
@@ -1325,9 +1365,13 @@ __global__ void __launch_bounds__(NT, 1) k_ring2d(RingArgs A) {
         const uint4 cn =
             update16<kSample, true>(ce, om, oc, op, side, g, pass, colour, chain_word, A.rk, acc);
         sts16(cbase + coff + p0, cn);
-        if (cl == cl_pub)  // our edge column: publish it, stamped
-          st_relaxed_gpu_v4(mb_out + colour * h, make_uint4(cn.x | stampw, cn.y | stampw,
-                                                            cn.z | stampw, cn.w | stampw));
+        if (cl == cl_pub) {  // our edge column: publish it, stamped
+          const uint4 pv = make_uint4(cn.x | stampw, cn.y | stampw, cn.z | stampw, cn.w | stampw);
+          if (remote)
+            st_relaxed_sys_v4(mb_out + colour * h, pv);
+          else
+            st_relaxed_gpu_v4(mb_out + colour * h, pv);
+        }
         om = oc;
         oc = op;
         coff += (uint32_t)dh;
@@ -1370,7 +1414,7 @@ __global__ void __launch_bounds__(NT, 1) k_ring2d(RingArgs A) {
     }
     // the neighbour published its edge of this colour early in this half-sweep:
     // fetch it now, so that the round trip overlaps the barrier
-    if (edge) hv = ld_relaxed_gpu_v4(mb_in + colour * h);
+    if (edge) hv = remote ? ld_relaxed_sys_v4(mb_in + colour * h) : ld_relaxed_gpu_v4(mb_in + colour * h);
     __syncthreads();
   }
 
@@ -1396,6 +1440,39 @@ __global__ void __launch_bounds__(NT, 1) k_ring2d(RingArgs A) {
   }
   n_acc = __reduce_add_sync(0xffffffffu, n_acc);
   if ((threadIdx.x & 31) == 0 && n_acc) atomicAdd(A.n_accept + chain, (unsigned long long)n_acc);
+}
+
+// Slab ring: before the first launch of a run the outer edge columns of plane 1 (what
+// the first half-sweep, colour 0, of the neighbour's outer tile reads) go into the
+// neighbours' mailboxes, stamped as the half-sweep before the run.  grid (V / 128 or 1, 2 sides).
+__global__ void k_ring_publish(RingArgs A) {
+  const LatticeView &L = A.L;
+  const int h = L.h, side = blockIdx.y;
+  const int p0 = (int)(blockIdx.x * blockDim.x + threadIdx.x) << 4;
+  if (p0 >= h || !A.peer_mb[side]) return;
+  const uint8_t *src = L.planes + L.plane_stride + (side ? (long long)h * (L.n1 - 1) : 0) + p0;
+  const int nb = side ? 0 : A.peer_tiles[0] - 1;
+  uint8_t *dst = A.peer_mb[side] + ((long long)nb * 2 + (side ? 0 : 1)) * (2ll * h) + h + p0;  // plane 1 of the slot
+  const uint32_t stampw = ((A.stamp0 + 126u) % 127u + 1u) * 0x02020202u;
+  const uint4 v = *reinterpret_cast<const uint4 *>(src);
+  st_relaxed_sys_v4(dst, make_uint4(v.x | stampw, v.y | stampw, v.z | stampw, v.w | stampw));
+}
+
+// Slab ring: after the last launch of a run the four boundary columns (two sides, two
+// planes) go into the neighbours' halo buffers, as the streaming kernel leaves them after
+// every half-sweep, and the neighbours' flags are raised to epoch + 1: sample_now and the
+// streaming kernel find the halos they expect.  grid (ceil(V / 128), 4).
+__global__ void k_slab_push_edges(LatticeView L) {
+  const int h = L.h, side = blockIdx.y & 1, plane = blockIdx.y >> 1;
+  const int p0 = (int)(blockIdx.x * blockDim.x + threadIdx.x) << 4;
+  bool pushed = false;
+  uint8_t *dst = side ? L.push_hi[plane] : L.push_lo[plane];
+  if (p0 < h && dst) {
+    const uint8_t *src = L.planes + (long long)plane * L.plane_stride + (side ? (long long)h * (L.n1 - 1) : 0) + p0;
+    *reinterpret_cast<uint4 *>(dst + p0) = *reinterpret_cast<const uint4 *>(src);
+    pushed = true;
+  }
+  slab_signal_neighbours(L, pushed);
 }
 
 // ---------------------------------------------------------------------------

@@ -410,16 +410,16 @@ class IsingLatticeGPU:
         return p.value, n.value
 
     def slab_ipc_export(self):
-        buf = C.create_string_buffer(320)
-        self._ck(self._lib.cmg_slab_ipc_export(self._ctx, buf, 320))
+        buf = C.create_string_buffer(512)
+        self._ck(self._lib.cmg_slab_ipc_export(self._ctx, buf, 512))
         return buf.raw
 
     def slab_ipc_attach(self, side, handle=None, peer=None):
         if peer is not None:
             self._ck(self._lib.cmg_slab_ipc_attach(self._ctx, side, None, 0, 1, peer._ctx))
         else:
-            buf = C.create_string_buffer(handle, 320)
-            self._ck(self._lib.cmg_slab_ipc_attach(self._ctx, side, buf, 320, 0, None))
+            buf = C.create_string_buffer(handle, 512)
+            self._ck(self._lib.cmg_slab_ipc_attach(self._ctx, side, buf, 512, 0, None))
 
     # -- introspection --
     @property

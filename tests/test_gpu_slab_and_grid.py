@@ -154,6 +154,85 @@ def test_two_slabs_on_two_streams_run_their_own_pass_loops():
         e.lat.close()
 
 
+def test_resident_ring_over_slabs_matches_single_context():
+    """k_ring2d on slab contexts (variant "ring2d"): the slab stays in shared memory and the
+    outer tiles trade their edge columns with the neighbour slab's outer tiles through the
+    mailboxes (stores into the neighbour's memory inside the cooperative kernel, stamps that
+    count the half-sweeps of the whole trajectory, no zeroing, no flags).  (a) one slab whose
+    ring closes on itself through the "remote" path; (b) two slabs of one GPU, 64 tiles each,
+    on two streams -- both cooperative kernels are resident together -- over several calls
+    and launches (passes per launch 3), with an upload in between."""
+    import torch
+
+    import casmcode_monte_b200 as cm
+    from casmcode_monte_b200.parallel import GpuSlabEngine, slab_columns
+
+    shape = [1024, 512]
+    n0, n1 = shape
+    T, mu, seed = 2633.0, 0.013, 4242
+    rng = np.random.default_rng(8)
+    occ = rng.choice(np.array([-1, 1], dtype=np.int32), size=n0 * n1)
+    occ2 = rng.choice(np.array([-1, 1], dtype=np.int32), size=n0 * n1)
+
+    def single(o, passes):
+        lat = cm.IsingLatticeGPU(shape, J=J)
+        lat.set_conditions(T, mu)
+        lat.seed_philox(seed)
+        lat.upload(o)
+        lat.run_passes(passes, cm.MODE_CHECKERBOARD, 2)
+        return lat
+
+    for n_slabs in (1, 2):
+        streams = [torch.cuda.Stream() for _ in range(n_slabs)]
+        engines = []
+        for r in range(n_slabs):
+            cb, nc = slab_columns(n1, n_slabs, r)
+            e = GpuSlabEngine(shape, cb, nc, J, T, mu, seed, stream=streams[r].cuda_stream)
+            e.lat.set_kernel_variant("ring2d:rp=3:rt=64")
+            e.upload(occ[n0 * cb : n0 * (cb + nc)])
+            engines.append(e)
+        torch.cuda.synchronize()
+        for r, e in enumerate(engines):
+            e.lat.slab_ipc_attach(0, peer=engines[(r - 1) % n_slabs].lat)
+            e.lat.slab_ipc_attach(1, peer=engines[(r + 1) % n_slabs].lat)
+        for n_passes in (7, 4):
+            for e in engines:
+                e.lat.slab_run_passes(n_passes, 2)  # asynchronous: all rings are in flight together
+        for e in engines:
+            e.sync()
+            assert e.lat.kernel_variant == "ring2d"
+        ref = single(occ, 11)
+        assert np.array_equal(np.concatenate([e.download() for e in engines]), ref.download())
+        assert np.array_equal(sum(e.lat.samples_sb()[1] for e in engines), ref.samples_sb()[1])
+        assert sum(e.lat.counters()[1] for e in engines) == ref.counters()[1]
+        # a new state: nothing of the old run may be taken for an edge of the new one
+        for r, e in enumerate(engines):
+            cb, nc = slab_columns(n1, n_slabs, r)
+            e.upload(occ2[n0 * cb : n0 * (cb + nc)])
+            e.lat.set_pass_counter(0)
+        torch.cuda.synchronize()
+        for e in engines:
+            e.lat.slab_run_passes(5, 0)
+        for e in engines:
+            e.sync()
+        ref2 = single(occ2, 5)
+        assert np.array_equal(np.concatenate([e.download() for e in engines]), ref2.download())
+        # the run left the neighbours' halos current: the bond sums of the slabs add up, and the
+        # streaming kernel (fused halo exchange, flags) carries on from there
+        assert sum(e.observables()[1] for e in engines) == ref2.sample_now()[1]
+        for e in engines:
+            e.lat.set_kernel_variant("auto")
+        for e in engines:
+            e.lat.slab_run_passes(2, 0)
+        for e in engines:
+            e.sync()
+            assert e.lat.kernel_variant == "bulk2d"
+        ref2.run_passes(2, cm.MODE_CHECKERBOARD, 0)
+        assert np.array_equal(np.concatenate([e.download() for e in engines]), ref2.download())
+        for e in engines:
+            e.lat.close()
+
+
 def test_slab_creation_errors():
     import casmcode_monte_b200 as cm
 

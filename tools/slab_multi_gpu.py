@@ -29,9 +29,15 @@ def main():
     rng = np.random.default_rng(1234)
     full = rng.choice(np.array([-1, 1], dtype=np.int32), size=n0 * n1) if check else None
     results = {}
-    for transport in ("nccl", "peer"):
+    modes = [("nccl", "nccl", "auto"), ("peer", "peer", "auto"), ("ring", "peer", "ring2d")]
+    if len(sys.argv) > 4:
+        modes = [m for m in modes if m[0] in sys.argv[4].split(",")]
+    for name, transport, variant in modes:
         stream = torch.cuda.current_stream()
         eng = GpuSlabEngine([n0, n1], cb, nc, J, T, mu, seed, device=local, stream=stream.cuda_stream)
+        # "ring": the slab resident in shared memory (k_ring2d), its outer tiles trading edges
+        # with the neighbour GPUs' outer tiles through peer memory -- one launch per block of passes
+        eng.lat.set_kernel_variant(variant)
         if check:
             eng.upload(full[n0 * cb : n0 * (cb + nc)])
         else:
@@ -61,11 +67,13 @@ def main():
                 ref.seed_philox(seed)
                 ref.set_kernel_variant("bulk2d")
                 ref.upload(full)
-                ref.run_passes(3 + n_passes, cm.MODE_CHECKERBOARD, 0)
+                ref.run_passes(3, cm.MODE_CHECKERBOARD, 0)
+                ref.run_passes(n_passes, cm.MODE_CHECKERBOARD, 0)
                 res["bit_identical_to_single_gpu"] = bool(np.array_equal(lattice, ref.download()))
                 res["B_single_gpu"] = int(ref.sample_now()[1])
                 ref.close()
-        results[transport] = res
+        res["kernel"] = eng.lat.kernel_variant
+        results[name] = res
         eng.lat.close()
         dist.barrier()
     if rank == 0:
