@@ -627,9 +627,12 @@ def ours_slab(args):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return int(t.item())
 
-    def make_ring(n, T, mu, randomize_seed=None, occ=None):
-        cb, nc = slab_columns(n, world, rank)
-        eng = GpuSlabEngine([n, n], cb, nc, J, T, mu, seed, device=local_rank, stream=stream.cuda_stream)
+    def make_ring(n, T, mu, randomize_seed=None, occ=None, n1=None, variant=None):
+        n1 = n if n1 is None else n1
+        cb, nc = slab_columns(n1, world, rank)
+        eng = GpuSlabEngine([n, n1], cb, nc, J, T, mu, seed, device=local_rank, stream=stream.cuda_stream)
+        if variant:
+            eng.lat.set_kernel_variant(variant)
         if occ is not None:
             eng.upload(occ[n * cb : n * (cb + nc)])
         else:
@@ -680,6 +683,71 @@ def ours_slab(args):
         }
         ref.close()
         assert proxy["occupation_bit_identical_to_single_gpu"] and proxy["sampled_S_B_identical"], proxy
+    # ---- the same proxy RESIDENT in shared memory over the GPUs (k_ring2d on slabs: the outer
+    # tiles of neighbouring GPUs trade their edge columns through peer memory inside the
+    # cooperative kernel, one launch per GPU per 128 passes): bit-identity against the
+    # streaming run above, then its rate.  8192 x 8192 needs four GPUs' shared memory; two
+    # GPUs take 8192 x 4096.
+    ring_n1 = PROXY_N if world >= 4 else PROXY_N // 2
+    ring_occ = proxy_full[: PROXY_N * ring_n1]
+    ring_err = []
+
+    def guarded(f):
+        # every rank walks the same sequence of collectives whatever happens to its own calls
+        if not ring_err:
+            try:
+                return f()
+            except Exception as exc:
+                ring_err.append(str(exc)[:300])
+        return None
+
+    def timed_passes(ring, n_passes, reps):
+        evs = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(stream):
+                e0.record(stream)
+                guarded(lambda: ring.run_passes(n_passes, sample_period=10))
+                e1.record(stream)
+            evs.append((e0, e1))
+        barrier()
+        return max_over_ranks(sum(a.elapsed_time(b) for a, b in evs))
+
+    def digest_after(ring, eng):
+        with torch.cuda.stream(stream):
+            guarded(lambda: ring.run_passes(proxy_passes, sample_period=2))
+        guarded(eng.sync)
+        d = guarded(lambda: hashlib.sha256(np.ascontiguousarray(eng.lat.download_i8()).tobytes()).hexdigest())
+        barrier()
+        return d
+
+    ring_passes, ring_reps = 384, 3
+    eng, ring, _ = make_ring(PROXY_N, T_HEADLINE, 0.01, occ=ring_occ, n1=ring_n1, variant="ring2d")
+    r_digest = digest_after(ring, eng)
+    r_kernel = eng.lat.kernel_variant
+    timed_passes(ring, ring_passes, 1)  # warm-up
+    r_ms = timed_passes(ring, ring_passes, ring_reps)
+    guarded(eng.sync)
+    eng.lat.close()
+    # the streaming run of the same lattice on the same ranks
+    eng, ring, _ = make_ring(PROXY_N, T_HEADLINE, 0.01, occ=ring_occ, n1=ring_n1)
+    s_digest = digest_after(ring, eng)
+    s_ms = timed_passes(ring, 40, 2)
+    eng.lat.close()
+    same = sum_over_ranks(0 if (r_digest is not None and r_digest == s_digest) else 1) == 0
+    n_failed = sum_over_ranks(1 if ring_err else 0)
+    resident = {
+        "lattice": [PROXY_N, ring_n1],
+        "value": float(PROXY_N) * ring_n1 * ring_passes * ring_reps / (r_ms * 1e-3) if n_failed == 0 else None,
+        "unit": "attempts/s",
+        "kernel": "k_" + r_kernel,
+        "passes_per_launch": 128,
+        "streaming_same_lattice": float(PROXY_N) * ring_n1 * 40 * 2 / (s_ms * 1e-3),
+        "bit_identical_to_the_streaming_run": bool(same),
+        "ranks_with_errors": n_failed,
+        "error": ring_err[0] if ring_err else None,
+        "workload": "the lattice resident in the GPUs' shared memory (one cooperative k_ring2d launch per GPU per 128 passes); outer tiles of neighbouring GPUs exchange edge columns by stores into each other's mailboxes over NVLink inside the kernel; sampling every 10 passes",
+    }
     del proxy_full
     barrier()
 
@@ -855,6 +923,7 @@ def ours_slab(args):
             "how": "halo_fraction = 1 - (step time with cmg_slab_set_halo_exchange(0)) / (step time with the exchange), same lattice, max over ranks",
         },
         "proxy_bit_identity": proxy,
+        "resident_ring_8192": resident,
         "e2e": {
             "value": e2e_value,
             "unit": UNIT,
