@@ -87,6 +87,7 @@ SIGNATURES = {
     "cmg_mark": (C.c_int, [_ctx]),
     "cmg_rollback": (C.c_int, [_ctx]),
     "cmg_series_check": (C.c_int, [_ctx, C.c_int, C.c_int, _intp, _f64p, C.c_int64, C.c_double, _intp, _i64p, _i64p, _f64p, _f64p]),
+    "cmg_series_check_prefetch": (C.c_int, [_ctx, C.c_int, C.c_int, _intp, _f64p, C.c_int64, C.c_double]),
     "cmg_host_series_stats": (C.c_int, [C.c_int, _f64p, C.c_int64, C.c_double, _f64p, _f64p, _f64p, _i64p]),
     "cmg_host_series_equilibration": (C.c_int, [C.c_int, _f64p, C.c_int64, C.c_double, _intp, _i64p]),
     "cmg_host_series_stats_weighted": (C.c_int, [C.c_int, _f64p, _f64p, C.c_int64, C.c_double, C.c_int, C.c_int64, _f64p, _f64p, _f64p, _f64p, _i64p]),

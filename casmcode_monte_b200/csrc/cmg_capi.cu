@@ -36,6 +36,8 @@ struct RunState {
 
 enum Variant { V_AUTO = 0, V_GENERIC = 1, V_BULK2D = 2, V_BULK3D = 3, V_TILE2D = 4, V_RING2D = 5, V_TMA3D = 6 };
 
+struct SeriesCheckBlock;
+
 struct cmg_context {
   int device = 0;
   cudaStream_t stream = 0;
@@ -127,6 +129,14 @@ struct cmg_context {
   uint8_t *d_shadow = nullptr;
   unsigned long long *d_shadow_accept = nullptr;
   bool mark_valid = false;
+  bool reserve_sm = false;  // checks have run on the aux stream next to the sweep: k_ring2d leaves them an SM
+  // a completion check enqueued ahead of its decision (cmg_series_check_prefetch)
+  struct SeriesCheckBlock *d_check = nullptr, *h_check_in = nullptr, *h_check_out = nullptr;
+  cudaEvent_t ev_check = nullptr;
+  bool check_pending = false;
+  int check_key_n = 0, check_key_chain = 0, check_key_q[3] = {0, 0, 0};
+  double check_key_abs[3] = {0, 0, 0}, check_key_conf = 0;
+  long long check_key_count = 0;
   unsigned long long mark_h_pass = 0;
   long long mark_n_pass = 0, mark_n_samples = 0;
   // k-state model; K == 0: the context runs the Ising path
@@ -458,6 +468,10 @@ int cmg_destroy(cmg_context *c) {
   cudaFree(c->d_flags);
   cudaFree(c->d_done);
   cudaFree(c->d_ring_mailbox);
+  cudaFree(c->d_check);
+  if (c->h_check_in) cudaFreeHost(c->h_check_in);
+  if (c->h_check_out) cudaFreeHost(c->h_check_out);
+  if (c->ev_check) cudaEventDestroy(c->ev_check);
   cudaFree(c->d_lines);
   cudaFree(c->d_error);
   cudaFree(c->d_shadow);
@@ -1129,14 +1143,14 @@ static RingPlan plan_ring(const cmg_context *c) {
   const long long h = c->shape[0] / 2, n1 = c->shape[1], V = h / 16;
   if (V > 256 || 512 % V != 0) return r;  // at least two column groups per CTA
   const long long Q = 512 / V;
-  // A context that overlaps its completion checks with the sweep (cmg_mark has been called: the
-  // aux stream exists) leaves one SM free when the widest tile stays the same (4096 / 147 and
+  // A context whose completion checks run on the second stream NEXT TO the sweep (a check of
+  // marked samples that was not prefetched) leaves one SM free when the widest tile stays the same (4096 / 147 and
   // 4096 / 148 both round up to 28 columns): the statistics kernels of cmg_series_check run there
   // while the cooperative kernel, whose CTAs fill the register file of their SMs, sweeps on.
   // Everybody else keeps all SMs (147 tiles measured 2.3 % slower than 148 on 4096^2: fewer
   // 27-column tiles to absorb the jitter of the edge exchange).
   long long n_tiles = c->sm_count / c->n_chains;
-  if (c->aux && c->n_chains == 1 && n_tiles > 2 && (n1 + n_tiles - 2) / (n_tiles - 1) == (n1 + n_tiles - 1) / n_tiles) n_tiles -= 1;
+  if (c->reserve_sm && c->n_chains == 1 && n_tiles > 2 && (n1 + n_tiles - 2) / (n_tiles - 1) == (n1 + n_tiles - 1) / n_tiles) n_tiles -= 1;
   if (c->ring_tiles_cap > 0) n_tiles = std::min<long long>(n_tiles, c->ring_tiles_cap);
   n_tiles = std::min(n_tiles, n1 / (2 * Q));
   if (n_tiles < 2) return r;
@@ -2404,11 +2418,108 @@ int cmg_rollback(cmg_context *c) {
   return CMG_OK;
 }
 
+// one scratch block of a completion check: eq jobs | stat jobs | results | the error word
+struct SeriesCheckBlock {
+  SeriesJob eq[3], st[3];
+  long long n_eq[3], n_stats, k_star[3];
+  double out4[12];
+  int is_eq[4];
+  unsigned int error;
+};
+
+// The check of the first `count` samples, ENQUEUED on the context's stream and not waited
+// for: a caller that knows a check is due enqueues it, then its next (speculative) block of
+// passes, and collects the verdict with cmg_series_check (same arguments) while that block
+// runs -- the device never idles between a block and the host's decision.  The series up to
+// `count` is complete in stream order; later blocks only append.
+int cmg_series_check_prefetch(cmg_context *c, int chain, int n_components, const int *quantity,
+                              const double *abs_precision, int64_t count, double confidence) {
+  NEED(c);
+  if (chain < 0 || chain >= c->n_chains) return fail(c, CMG_EINVAL, "bad chain index");
+  if (n_components < 1 || n_components > 3 || !quantity || !abs_precision)
+    return fail(c, CMG_EINVAL, "1 to 3 components");
+  for (int i = 0; i < n_components; ++i)
+    if (quantity[i] < 0 || quantity[i] > 2 || !(abs_precision[i] >= 0.0))
+      return fail(c, CMG_EINVAL, "bad quantity or precision");
+  if (count <= 0) return fail(c, CMG_EINVAL, "Error in equilibration_check: observations.size()==0");
+  if (count > c->n_samples) return fail(c, CMG_EINVAL, "sample range outside the series");
+  if (!c->d_check) {
+    CU(c, cudaMalloc(&c->d_check, sizeof(SeriesCheckBlock)));
+    CU(c, cudaMallocHost(&c->h_check_in, sizeof(SeriesCheckBlock)));
+    CU(c, cudaMallocHost(&c->h_check_out, sizeof(SeriesCheckBlock)));
+    CU(c, cudaEventCreateWithFlags(&c->ev_check, cudaEventDisableTiming));
+  }
+  if (c->check_pending) CU(c, cudaEventSynchronize(c->ev_check));  // the staging block is free again
+  c->check_pending = false;
+  int rc = ensure_doubles(c);
+  if (rc) return rc;
+  const int n = n_components;
+  SeriesCheckBlock &h = *c->h_check_in;
+  memset(&h, 0, sizeof h);
+  for (int i = 0; i < n; ++i) {
+    h.eq[i].x = series_ptr(c, chain, quantity[i]);
+    h.eq[i].n = count;
+  }
+  SeriesCheckBlock *d = c->d_check;
+  CU(c, cudaMemcpyAsync(d, &h, sizeof h, cudaMemcpyHostToDevice, c->stream));
+  bool same = true;
+  for (int i = 1; i < n; ++i) same = same && abs_precision[i] == abs_precision[0];
+  if (same) {
+    k_series_equilibration<<<n, kEquilThreads, 0, c->stream>>>(d->eq, n, abs_precision[0], d->is_eq, d->n_eq);
+    ++c->launches;
+  } else {
+    for (int j = 0; j < n; ++j) {
+      k_series_equilibration<<<1, kEquilThreads, 0, c->stream>>>(d->eq + j, 1, abs_precision[j], d->is_eq + j, d->n_eq + j);
+      ++c->launches;
+    }
+  }
+  k_make_tail_jobs<<<1, 32, 0, c->stream>>>(d->eq, n, d->is_eq, d->n_eq, d->st, &d->n_stats);
+  k_series_stats<<<n, 256, 0, c->stream>>>(d->st, z_confidence(confidence), d->out4, d->k_star);
+  c->launches += 2;
+  CU(c, cudaGetLastError());
+  if (c->d_error)
+    CU(c, cudaMemcpyAsync(&d->error, c->d_error, sizeof(unsigned int), cudaMemcpyDeviceToDevice, c->stream));
+  CU(c, cudaMemcpyAsync(c->h_check_out, d, sizeof(SeriesCheckBlock), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaEventRecord(c->ev_check, c->stream));
+  c->check_pending = true;
+  c->check_key_n = n;
+  c->check_key_chain = chain;
+  c->check_key_count = count;
+  c->check_key_conf = confidence;
+  for (int i = 0; i < n; ++i) {
+    c->check_key_q[i] = quantity[i];
+    c->check_key_abs[i] = abs_precision[i];
+  }
+  return CMG_OK;
+}
+
 int cmg_series_check(cmg_context *c, int chain, int n_components, const int *quantity,
                      const double *abs_precision, int64_t count, double confidence,
                      int *is_equilibrated, int64_t *n_equil, int64_t *n_stats, double *mean,
                      double *calculated_precision) {
   NEED(c);
+  if (c->check_pending) {
+    // the verdict of a prefetched check with these very arguments: wait for it alone
+    bool match = n_components == c->check_key_n && chain == c->check_key_chain && count == c->check_key_count &&
+                 confidence == c->check_key_conf && quantity && abs_precision;
+    for (int i = 0; match && i < n_components; ++i)
+      match = quantity[i] == c->check_key_q[i] && abs_precision[i] == c->check_key_abs[i];
+    CU(c, cudaEventSynchronize(c->ev_check));
+    c->check_pending = false;
+    if (match) {
+      const SeriesCheckBlock &h = *c->h_check_out;
+      for (int i = 0; i < n_components; ++i) {
+        if (is_equilibrated) is_equilibrated[i] = h.is_eq[i];
+        if (n_equil) n_equil[i] = h.n_eq[i];
+        if (mean) mean[i] = h.out4[4 * i];
+        if (calculated_precision) calculated_precision[i] = h.out4[4 * i + 3];
+      }
+      if (n_stats) *n_stats = h.n_stats;
+      if (h.error) return device_error_check(c);  // reports and clears the sticky word
+      return CMG_OK;
+    }
+  }
+
   if (chain < 0 || chain >= c->n_chains) return fail(c, CMG_EINVAL, "bad chain index");
   if (n_components < 1 || n_components > 3 || !quantity || !abs_precision)
     return fail(c, CMG_EINVAL, "1 to 3 components");
@@ -2437,6 +2548,7 @@ int cmg_series_check(cmg_context *c, int chain, int n_components, const int *qua
       }
     }
   } view_guard(c, c->mark_valid && c->aux && count <= c->mark_n_samples && c->n_samples > c->mark_n_samples);
+  if (view_guard.on) c->reserve_sm = true;
   int rc = ensure_doubles(c);
   if (rc) return rc;
   const int n = n_components;

@@ -2866,20 +2866,47 @@ __global__ void __launch_bounds__(kEquilThreads) k_series_equilibration(const Se
     if (threadIdx.x == 0) {
       s_stop = kEquilChunk;
       double a = sum1, b = sum2;
-      long long t1 = start1;
-      int m = 0;
-      bool ev = is_even;
-      for (int k = 0; k < kEquilChunk && t1 < N - 2; ++k) {  // EquilibrationCheck.cc:93-103
-        s_sum1[k] = a;
-        s_sum2[k] = b;
-        a = __dsub_rn(a, s_x1[k]);
-        if (ev) {
-          a = __dadd_rn(a, s_x2[m]);
-          b = __dsub_rn(b, s_x2[m]);
-          m++;
+      // EquilibrationCheck.cc:93-103, two steps (one of each parity) per trip: the parity
+      // pattern of a chunk is fixed, so the trip has no branch and its loads do not depend on
+      // the sums -- what is left on the critical path is three dependent additions per trip
+      const long long left = N - 2 - start1;
+      const int steps = (int)(left < (long long)kEquilChunk ? (left > 0 ? left : 0) : kEquilChunk);
+      int k = 0, m = 0;
+      if (is_even) {
+#pragma unroll 4
+        for (; k + 2 <= steps; k += 2, ++m) {
+          const double xa = s_x1[k], xb = s_x1[k + 1], x2 = s_x2[m];
+          s_sum1[k] = a;
+          s_sum2[k] = b;
+          a = __dadd_rn(__dsub_rn(a, xa), x2);
+          b = __dsub_rn(b, x2);
+          s_sum1[k + 1] = a;
+          s_sum2[k + 1] = b;
+          a = __dsub_rn(a, xb);
         }
-        t1++;
-        ev = !ev;
+        if (k < steps) {
+          s_sum1[k] = a;
+          s_sum2[k] = b;
+          a = __dadd_rn(__dsub_rn(a, s_x1[k]), s_x2[m]);
+          b = __dsub_rn(b, s_x2[m]);
+        }
+      } else {
+#pragma unroll 4
+        for (; k + 2 <= steps; k += 2, ++m) {
+          const double xa = s_x1[k], xb = s_x1[k + 1], x2 = s_x2[m];
+          s_sum1[k] = a;
+          s_sum2[k] = b;
+          a = __dsub_rn(a, xa);
+          s_sum1[k + 1] = a;
+          s_sum2[k + 1] = b;
+          a = __dadd_rn(__dsub_rn(a, xb), x2);
+          b = __dsub_rn(b, x2);
+        }
+        if (k < steps) {
+          s_sum1[k] = a;
+          s_sum2[k] = b;
+          a = __dsub_rn(a, s_x1[k]);
+        }
       }
       s_end1 = a;
       s_end2 = b;

@@ -279,6 +279,14 @@ int cmg_series_check(cmg_context *ctx, int chain, int n_components, const int *q
                      const double *abs_precision, int64_t count, double confidence,
                      int *is_equilibrated, int64_t *n_equil, int64_t *n_stats, double *mean,
                      double *calculated_precision);
+/* The same check ENQUEUED on the context's stream and not waited for.  A driver that knows
+ * a check is due at the current sample count enqueues it, then its next (speculative) block
+ * of passes behind a cmg_mark, and collects the verdict with cmg_series_check (identical
+ * arguments) while that block runs: the device never idles between a block and the host's
+ * decision (checks/CompletionCheck.hh:273-376 is evaluated exactly when and on what the
+ * reference evaluates it; a "complete" verdict is followed by cmg_rollback). */
+int cmg_series_check_prefetch(cmg_context *ctx, int chain, int n_components, const int *quantity,
+                              const double *abs_precision, int64_t count, double confidence);
 /* Restore point for drivers that sweep on while a completion check is evaluated
  * (methods::basic_occupation_metropolis decides after every sample, include/casm/monte/
  * methods/basic_occupation_metropolis.hh:381-422; a device loop that waited for every

@@ -24,6 +24,7 @@ for T in (2800.0, 2200.0, 2800.0):
             param_composition_calculator=ising.IsingParamComposition(),
         )
     )
+    mc.overlap_checks = os.environ.get("OVERLAP", "0") == "1"
     state = ising.IsingState(
         configuration=ising.IsingConfiguration(shape=(n0, n1)),
         conditions=monte.ValueMap.from_dict({"temperature": T, "exchange_potential": [0.0]}),
