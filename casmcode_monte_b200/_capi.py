@@ -63,6 +63,7 @@ SIGNATURES = {
     "cmg_event_delta": (C.c_int, [_ctx, C.c_int, C.c_int, _i64p, _i32p, _f64p, _f64p]),
     "cmg_randomize_occupation": (C.c_int, [_ctx, C.c_int, C.c_uint64, C.c_double]),
     "cmg_seed_philox": (C.c_int, [_ctx, C.c_uint64]),
+    "cmg_set_philox_rounds": (C.c_int, [_ctx, C.c_int]),
     "cmg_set_pass_counter": (C.c_int, [_ctx, C.c_uint64]),
     "cmg_set_chain_offset": (C.c_int, [_ctx, C.c_int64]),
     "cmg_seed_mt19937_64": (C.c_int, [_ctx, C.c_int, C.c_uint64]),

@@ -129,6 +129,7 @@ struct cmg_context {
   uint8_t *d_shadow = nullptr;
   unsigned long long *d_shadow_accept = nullptr;
   bool mark_valid = false;
+  int philox_rounds = 10;  // 10 (published default) or 7 (cmg_set_philox_rounds)
   bool reserve_sm = false;  // checks have run on the aux stream next to the sweep: k_ring2d leaves them an SM
   // a completion check enqueued ahead of its decision (cmg_series_check_prefetch)
   struct SeriesCheckBlock *d_check = nullptr, *h_check_in = nullptr, *h_check_out = nullptr;
@@ -924,6 +925,15 @@ int cmg_seed_philox(cmg_context *c, uint64_t seed) {
   return CMG_OK;
 }
 
+int cmg_set_philox_rounds(cmg_context *c, int rounds) {
+  NEED(c);
+  if (rounds != 10 && rounds != 7)
+    return fail(c, CMG_EINVAL, "philox rounds: 10 (default) or 7 (the fewest that pass BigCrush)");
+  if (rounds != 10 && c->ks_K) return fail(c, CMG_EUNSUPPORTED, "the k-state model runs Philox4x32-10 only");
+  c->philox_rounds = rounds;
+  return CMG_OK;
+}
+
 static int push_run_state(cmg_context *c) {
   RunState rs;
   rs.pass = c->h_pass;
@@ -1166,6 +1176,12 @@ static RingPlan plan_ring(const cmg_context *c) {
 
 static int pick_variant(cmg_context *c, long long n_passes) {
   if (c->forced_variant != V_AUTO) return c->forced_variant;
+  if (c->philox_rounds != 10) {
+    // the seven-round stream is compiled into the resident, the streaming 2-d and the generic kernel
+    if (c->dim == 2 && n_passes >= 4 && plan_ring(c).ok && c->n_sites * c->n_chains <= (1ll << 25)) return V_RING2D;
+    if (c->dim == 2 && c->shape[0] % 32 == 0) return V_BULK2D;
+    return V_GENERIC;
+  }
   // the tiled kernel wins while a half-sweep is short enough for launch ramp
   // and L2 latency to matter; very large batches stream better through bulk2d
   if (plan_tiles(c, c->tile_passes).ok && c->n_sites * c->n_chains <= (1ll << 25)) {
@@ -1378,6 +1394,8 @@ static int launch_half_sweep(cmg_context *c, int variant, int colour, unsigned l
     // the staging rings may exceed the 48 KiB default dynamic shared-memory limit
     cudaError_t e = cudaFuncSetAttribute(k_halfsweep_bulk2d<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBulk2d);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_halfsweep_bulk2d<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBulk2d);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_halfsweep_bulk2d<true, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBulk2d);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_halfsweep_bulk2d<false, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBulk2d);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_halfsweep_bulk3d<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBulk3d);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_halfsweep_bulk3d<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBulk3d);
     if (e != cudaSuccess) return fail(c, CMG_ECUDA, cudaGetErrorString(e));
@@ -1403,17 +1421,17 @@ static int launch_half_sweep(cmg_context *c, int variant, int colour, unsigned l
   if (variant == V_GENERIC) {
     dim3 grid(nblocks((plane_size + 7) / 8, 128), c->n_chains);
     if (sample)
-      k_halfsweep_generic<true><<<grid, block, kSmemSmall, c->stream>>>(A);
+      (c->philox_rounds == 7 ? k_halfsweep_generic<true, 7> : k_halfsweep_generic<true, 10>)<<<grid, block, kSmemSmall, c->stream>>>(A);
     else
-      k_halfsweep_generic<false><<<grid, block, kSmemSmall, c->stream>>>(A);
+      (c->philox_rounds == 7 ? k_halfsweep_generic<false, 7> : k_halfsweep_generic<false, 10>)<<<grid, block, kSmemSmall, c->stream>>>(A);
   } else if (variant == V_BULK2D) {
     const long long V = c->shape[0] / 32;
     const long long strips = A.n_strips > 0 ? A.n_strips : (c->shape[1] + A.js - 1) / A.js;
     dim3 grid(nblocks(V * strips, 128), c->n_chains);
     if (sample)
-      k_halfsweep_bulk2d<true><<<grid, block, kSmemBulk2d, c->stream>>>(A);
+      (c->philox_rounds == 7 ? k_halfsweep_bulk2d<true, 7> : k_halfsweep_bulk2d<true, 10>)<<<grid, block, kSmemBulk2d, c->stream>>>(A);
     else
-      k_halfsweep_bulk2d<false><<<grid, block, kSmemBulk2d, c->stream>>>(A);
+      (c->philox_rounds == 7 ? k_halfsweep_bulk2d<false, 7> : k_halfsweep_bulk2d<false, 10>)<<<grid, block, kSmemBulk2d, c->stream>>>(A);
   } else if (variant == V_BULK3D) {
     const long long V = c->shape[0] / 32;
     const long long strips = A.n_strips > 0 ? A.n_strips : (c->shape[1] + A.js - 1) / A.js;
@@ -1529,8 +1547,8 @@ static int launch_ring_passes(cmg_context *c, const RingPlan &rp, int n_passes,
   A.v_magic = (uint32_t)((0x100000000ull + V - 1) / V);
   A.mailbox = c->d_ring_mailbox;
   A.error = c->d_error;
-  cudaError_t e = cudaFuncSetAttribute(k_ring2d<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)rp.smem);
+  const void *ring_kernel = c->philox_rounds == 7 ? (const void *)k_ring2d<512, 7> : (const void *)k_ring2d<512, 10>;
+  cudaError_t e = cudaFuncSetAttribute(ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rp.smem);
   if (e != cudaSuccess) return fail(c, CMG_ECUDA, cudaGetErrorString(e));
   dim3 grid(rp.n_tiles, c->n_chains);
   void *args[] = {&A};
@@ -1541,8 +1559,7 @@ static int launch_ring_passes(cmg_context *c, const RingPlan &rp, int n_passes,
     k_ring_publish<<<dim3((unsigned)nblocks(V, 128), 2), 128, 0, c->stream>>>(A);
     ++c->launches;
   }
-  e = cudaLaunchCooperativeKernel((const void *)k_ring2d<512>, grid, dim3(512), args, rp.smem,
-                                  c->stream);
+  e = cudaLaunchCooperativeKernel(ring_kernel, grid, dim3(512), args, rp.smem, c->stream);
   if (e != cudaSuccess) return fail(c, CMG_ECUDA, cudaGetErrorString(e));
   ++c->launches;
   if (peers) c->ring_s0 += 2ull * (unsigned long long)n_passes;
@@ -1739,6 +1756,8 @@ int cmg_run_passes(cmg_context *c, int64_t n_passes, int mode, int64_t sample_pe
     return fail(c, CMG_EINVAL, "bulk3d needs dim == 3 and n0 % 32 == 0");
   if (variant == V_TMA3D && !plan_tma3d(c).ok)
     return fail(c, CMG_EINVAL, "tma3d needs dim == 3, n0 in {512, 1024}, n1 even and n2 a multiple of 4096 / n0");
+  if (c->philox_rounds != 10 && (variant == V_TILE2D || variant == V_BULK3D || variant == V_TMA3D))
+    return fail(c, CMG_EUNSUPPORTED, "seven Philox rounds: kernels ring2d, bulk2d and generic only");
   if (variant == V_TILE2D && !plan_tiles(c, 1).ok)
     return fail(c, CMG_EINVAL, "tile2d does not fit this lattice (need dim 2, n0 % 64 == 0, short columns)");
   if (variant == V_RING2D && !plan_ring(c).ok)

@@ -100,10 +100,13 @@ struct SweepArgs {
 constexpr uint32_t kPhiloxM0 = 0xD2511F53u, kPhiloxM1 = 0xCD9E8D57u;
 constexpr uint32_t kPhiloxW0 = 0x9E3779B9u, kPhiloxW1 = 0xBB67AE85u;
 
-// rk = the ten round-key pairs (key + r*(W0,W1))
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, const uint32_t *rk) {
+// rk = the ten round-key pairs (key + r*(W0,W1)).  R = 10 is the published default;
+// R = 7 (cmg_set_philox_rounds) is the fewest rounds of Philox4x32 that pass BigCrush
+// (Salmon et al., table 2) -- an opt-in, never chosen by the library itself.
+template <int R = 10>
+__device__ __forceinline__ uint4 philox4x32(uint4 c, const uint32_t *rk) {
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < R; ++r) {
     unsigned long long p0 = (unsigned long long)kPhiloxM0 * c.x;
     unsigned long long p1 = (unsigned long long)kPhiloxM1 * c.z;
     uint4 n;
@@ -122,6 +125,7 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, const uint32_t *rk) {
 // key = seed.  refine = 0: the lane r16 that supplies the leading 16 bits of each
 // site's uniform (rotated, see accept_mask4_fast); refine = 1: the trailing 16
 // bits r16' (only evaluated on a tie).
+template <int R = 10>
 __device__ __forceinline__ uint4 site_group_random(unsigned long long group,
                                                    uint32_t chain_word,
                                                    unsigned long long pass,
@@ -132,7 +136,7 @@ __device__ __forceinline__ uint4 site_group_random(unsigned long long group,
   c.y = ((uint32_t)(group >> 32) & 0xffu) | chain_word;
   c.z = (uint32_t)pass;
   c.w = ((uint32_t)(pass >> 32) << 2) | ((uint32_t)refine << 1) | (uint32_t)colour;
-  return philox4x32_10(c, rk);
+  return philox4x32<R>(c, rk);
 }
 
 // All sweep kernels use one dynamic shared-memory buffer, declared at
@@ -309,7 +313,7 @@ __device__ __forceinline__ void block_accumulate(unsigned int acc, long long s_o
 // s*(sum of neighbour s) (every bond joins the two colours exactly once).
 // The host turns ones into S = 2*ones - N.
 // ---------------------------------------------------------------------------
-template <bool SAMPLE>
+template <bool SAMPLE, int R = 10>
 __global__ void __launch_bounds__(128) k_halfsweep_generic(SweepArgs A) {
   const LatticeView &L = A.L;
   const int chain = blockIdx.y;
@@ -327,10 +331,10 @@ __global__ void __launch_bounds__(128) k_halfsweep_generic(SweepArgs A) {
   unsigned int acc = 0;
   long long ones = 0, bsum = 0;
   if (8 * g < plane_size) {
-    const uint4 ra = site_group_random((unsigned long long)g, (uint32_t)(chain + A.chain_offset) << 8, A.pass,
-                                       A.colour, 0, A.rk);
-    const uint4 rb = site_group_random((unsigned long long)g, (uint32_t)(chain + A.chain_offset) << 8, A.pass,
-                                       A.colour, 1, A.rk);
+    const uint4 ra = site_group_random<R>((unsigned long long)g, (uint32_t)(chain + A.chain_offset) << 8, A.pass,
+                                          A.colour, 0, A.rk);
+    const uint4 rb = site_group_random<R>((unsigned long long)g, (uint32_t)(chain + A.chain_offset) << 8, A.pass,
+                                          A.colour, 1, A.rk);
 #pragma unroll
     for (int w = 0; w < 8; ++w) {
       const long long q = 8 * g + w;
@@ -426,6 +430,7 @@ __device__ __noinline__ uint4 clear_never16(uint4 m, uint4 idx4e) {
 // Rare path: some site of a 16-site vector tied on its leading 15 bits.  Redo
 // all 16 decisions exactly with both halves (regenerating the leading words so
 // the hot path does not have to keep them alive).
+template <int R = 10>
 __device__ __noinline__ uint4 resolve_ties16(uint4 idx4e, unsigned long long group0,
                                              unsigned long long pass, int colour,
                                              uint32_t chain_word, uint32_t key0, uint32_t key1) {
@@ -440,8 +445,8 @@ __device__ __noinline__ uint4 resolve_ties16(uint4 idx4e, unsigned long long gro
   const uint32_t iw[4] = {idx4e.x, idx4e.y, idx4e.z, idx4e.w};
   uint32_t m[4];
   for (int half = 0; half < 2; ++half) {
-    const uint4 r = site_group_random(group0 + half, chain_word, pass, colour, 0, rk);
-    const uint4 q = site_group_random(group0 + half, chain_word, pass, colour, 1, rk);
+    const uint4 r = site_group_random<R>(group0 + half, chain_word, pass, colour, 0, rk);
+    const uint4 q = site_group_random<R>(group0 + half, chain_word, pass, colour, 1, rk);
 #pragma unroll
     for (int ww = 0; ww < 2; ++ww) {
       const int w = 2 * half + ww;
@@ -480,7 +485,7 @@ __device__ __forceinline__ void accum_finish(const Accum &a, int z, long long &o
 
 // Update 16 sites (one 16-byte vector of a colour plane); returns the new
 // centre vector.  group0 = plane index of the first site >> 3.
-template <bool SAMPLE, bool PAIR = false>
+template <bool SAMPLE, bool PAIR = false, int R = 10>
 __device__ __forceinline__ uint4 update16(uint4 ce, uint4 om, uint4 oc, uint4 op,
                                           uint4 side, unsigned long long group0,
                                           unsigned long long pass, int colour,
@@ -490,8 +495,8 @@ __device__ __forceinline__ uint4 update16(uint4 ce, uint4 om, uint4 oc, uint4 op
   const uint32_t nw[4] = {om.x + oc.x + op.x + side.x, om.y + oc.y + op.y + side.y,
                           om.z + oc.z + op.z + side.z, om.w + oc.w + op.w + side.w};
   const uint32_t ow[4] = {oc.x, oc.y, oc.z, oc.w};
-  const uint4 ra = site_group_random(group0, chain_word, pass, colour, 0, rk);
-  const uint4 rb = site_group_random(group0 + 1, chain_word, pass, colour, 0, rk);
+  const uint4 ra = site_group_random<R>(group0, chain_word, pass, colour, 0, rk);
+  const uint4 rb = site_group_random<R>(group0 + 1, chain_word, pass, colour, 0, rk);
   const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
   uint32_t idx[4], m[4], tmax = 0;
   // PAIR: bytes 0 and 2 also carry the lane's pair-table copy (0 or kPairCopy)
@@ -502,7 +507,7 @@ __device__ __forceinline__ uint4 update16(uint4 ce, uint4 om, uint4 oc, uint4 op
     m[w] = accept_mask4_fast<PAIR>(idx[w], rw[2 * w], rw[2 * w + 1], tmax);
   }
   if (any_tie(tmax)) {  // a tie somewhere in these 16 sites (probability 16 * 2^-15)
-    const uint4 mm = resolve_ties16(make_uint4(idx[0] - copy2, idx[1] - copy2, idx[2] - copy2,
+    const uint4 mm = resolve_ties16<R>(make_uint4(idx[0] - copy2, idx[1] - copy2, idx[2] - copy2,
                                                idx[3] - copy2),
                                     group0, pass, colour, chain_word, rk[0], rk[1]);
     m[0] = mm.x;
@@ -667,7 +672,7 @@ constexpr int kSmemRing = kBulkPair ? kSmemTile : 256;
 constexpr uint32_t kBulkStageBytes = 128u * 36u;
 constexpr int kSmemBulk2d = kSmemRing + kBulkStages * (int)kBulkStageBytes;
 
-template <bool SAMPLE>
+template <bool SAMPLE, int R = 10>
 __global__ void __launch_bounds__(128, CMG_BULK_CTAS) k_halfsweep_bulk2d(SweepArgs A) {
   const LatticeView &L = A.L;
   const int chain = blockIdx.y;
@@ -796,8 +801,8 @@ __global__ void __launch_bounds__(128, CMG_BULK_CTAS) k_halfsweep_bulk2d(SweepAr
         const uint32_t eb = lds8_abs(s_e + slot + (par ? 0u : 3u));
         fetch(it + kBulkStages, par);
         const uint4 side = (par == 0) ? shift_up_1(oc, eb) : shift_down_1(oc, eb);
-        const uint4 cn = update16<SAMPLE, kBulkPair>(ce, om, oc, op, side, g, A.pass, A.colour, chain_word,
-                                          A.rk, acc);
+        const uint4 cn = update16<SAMPLE, kBulkPair, R>(ce, om, oc, op, side, g, A.pass, A.colour, chain_word,
+                                             A.rk, acc);
         *reinterpret_cast<uint4 *>(Cp) = cn;
         Cp += hstep;
         g += gstep;
@@ -1249,7 +1254,7 @@ __device__ __forceinline__ bool ring_stamp_ok(uint4 v, uint32_t expect) {
   return ((((v.x ^ expect) | (v.y ^ expect)) | ((v.z ^ expect) | (v.w ^ expect))) & 0xfefefefeu) == 0u;
 }
 
-template <int NT>
+template <int NT, int R = 10>
 __global__ void __launch_bounds__(NT, 1) k_ring2d(RingArgs A) {
   __shared__ long long s_acc[2 * kRingMaxPasses];  // per-pass {ones, B} of this CTA
   for (int i = threadIdx.x; i < 2 * kRingMaxPasses; i += NT) s_acc[i] = 0;
@@ -1380,7 +1385,7 @@ __global__ void __launch_bounds__(NT, 1) k_ring2d(RingArgs A) {
         const uint32_t eb = cmg_smem[obase + coff + (par ? e_hi : e_lo)];
         const uint4 side = par ? shift_down_1(oc, eb) : shift_up_1(oc, eb);
         const uint4 cn =
-            update16<kSample, true>(ce, om, oc, op, side, g, pass, colour, chain_word, A.rk, acc);
+            update16<kSample, true, R>(ce, om, oc, op, side, g, pass, colour, chain_word, A.rk, acc);
         sts16(cbase + coff + p0, cn);
         if (cl == cl_pub) {  // our edge column: publish it, stamped
           const uint4 pv = make_uint4(cn.x | stampw, cn.y | stampw, cn.z | stampw, cn.w | stampw);
@@ -1957,7 +1962,7 @@ __global__ void k_randomize_natural(uint8_t *nat, long long n, unsigned long lon
     rk[2 * i] = (uint32_t)seed + i * kPhiloxW0;
     rk[2 * i + 1] = (uint32_t)(seed >> 32) + i * kPhiloxW1;
   }
-  const uint4 r = philox4x32_10(make_uint4((uint32_t)gg, (uint32_t)(gg >> 32), 0x5EEDu, 0u), rk);
+  const uint4 r = philox4x32<10>(make_uint4((uint32_t)gg, (uint32_t)(gg >> 32), 0x5EEDu, 0u), rk);
   const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
   for (int w = 0; w < 4; ++w)
     if (4 * g + w < n) nat[4 * g + w] = (uint8_t)(always || rr[w] <= thr_m1);

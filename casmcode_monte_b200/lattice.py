@@ -152,6 +152,10 @@ class IsingLatticeGPU:
     def seed_philox(self, seed):
         self._ck(self._lib.cmg_seed_philox(self._ctx, int(seed)))
 
+    def set_philox_rounds(self, rounds):
+        """10 (default) or 7 (the fewest rounds of Philox4x32 that pass BigCrush; opt-in)."""
+        self._ck(self._lib.cmg_set_philox_rounds(self._ctx, int(rounds)))
+
     def set_pass_counter(self, t):
         self._ck(self._lib.cmg_set_pass_counter(self._ctx, int(t)))
 

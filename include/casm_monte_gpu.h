@@ -188,6 +188,12 @@ int cmg_randomize_occupation(cmg_context *ctx, int chain, uint64_t seed, double 
  * RandomNumberGenerator.hh:15-42, definitions.hh:17) restated on the device:
  * libstdc++-13 uniform_int_distribution (Lemire) and generate_canonical. */
 int cmg_seed_philox(cmg_context *ctx, uint64_t seed);
+/* Rounds of the checkerboard mode's Philox4x32 stream: 10 (the published default, what
+ * every number in BASELINE / bench.py is measured with) or 7, the fewest rounds that pass
+ * BigCrush (Salmon et al., SC'11, table 2) -- an opt-in worth ~+17 % on the resident
+ * kernel.  The trajectory is a different one; kernels ring2d,
+ * bulk2d and generic.  No counterpart in the reference (its stream is mt19937_64). */
+int cmg_set_philox_rounds(cmg_context *ctx, int rounds);
 int cmg_set_pass_counter(cmg_context *ctx, uint64_t pass_index);
 /* chains sharded over several contexts / GPUs keep the Philox stream of their
  * GLOBAL chain index: global index = this offset + local chain */

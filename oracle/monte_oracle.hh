@@ -1745,7 +1745,7 @@ struct CheckerboardResult {
   long long n_accept = 0;
 };
 inline uint32_t checkerboard_uniform(uint64_t q, uint32_t chain, uint64_t pass_index,
-                                     int colour, std::array<uint32_t, 2> key) {
+                                     int colour, std::array<uint32_t, 2> key, int rounds = 10) {
   const uint64_t g = q >> 3;
   const int lane = static_cast<int>(q & 7);
   std::array<uint32_t, 4> ctr = {
@@ -1753,9 +1753,9 @@ inline uint32_t checkerboard_uniform(uint64_t q, uint32_t chain, uint64_t pass_i
       (static_cast<uint32_t>(g >> 32) & 0xffu) | (chain << 8),
       static_cast<uint32_t>(pass_index),
       (static_cast<uint32_t>(pass_index >> 32) << 2) | static_cast<uint32_t>(colour)};
-  const uint32_t w0 = Philox4x32::generate(ctr, key)[lane >> 1];
+  const uint32_t w0 = Philox4x32::generate(ctr, key, rounds)[lane >> 1];
   ctr[3] |= 2u;
-  const uint32_t w1 = Philox4x32::generate(ctr, key)[lane >> 1];
+  const uint32_t w1 = Philox4x32::generate(ctr, key, rounds)[lane >> 1];
   const uint32_t r16 = (w0 >> (16 * (lane & 1))) & 0xffffu;
   const uint32_t r16b = (w1 >> (16 * (lane & 1))) & 0xffffu;
   const uint32_t lead = ((r16 << 1) | (r16 >> 15)) & 0xffffu;  // rotl16(r16, 1)
@@ -1764,7 +1764,7 @@ inline uint32_t checkerboard_uniform(uint64_t q, uint32_t chain, uint64_t pass_i
 inline void checkerboard_pass(std::vector<int> &occ, std::vector<int> const &shape,
                               AcceptTable const &tab, uint64_t seed,
                               uint32_t chain, uint64_t pass_index,
-                              CheckerboardResult &res) {
+                              CheckerboardResult &res, int rounds = 10) {
   const int dim = static_cast<int>(shape.size());
   const long n0 = shape[0], n1 = shape[1], n2 = (dim == 3) ? shape[2] : 1;
   const long h = n0 / 2;
@@ -1780,7 +1780,7 @@ inline void checkerboard_pass(std::vector<int> &occ, std::vector<int> const &sha
                        static_cast<uint64_t>(h) *
                            (static_cast<uint64_t>(j) +
                             static_cast<uint64_t>(n1) * static_cast<uint64_t>(k));
-          uint32_t r = checkerboard_uniform(q, chain, pass_index, colour, key);
+          uint32_t r = checkerboard_uniform(q, chain, pass_index, colour, key, rounds);
           long ip = (i + 1) % n0, im = (i + n0 - 1) % n0;
           long jp = (j + 1) % n1, jm = (j + n1 - 1) % n1;
           int n_up = (occ[ip + n0 * (j + n1 * k)] > 0) +

@@ -195,7 +195,7 @@ py::dict sgc_run(std::vector<int> shape, i32arr occ_in, double J, double T,
 
 py::dict checkerboard_run(std::vector<int> shape, i32arr occ_in, double J,
                           double T, double mu, uint64_t seed, uint32_t chain,
-                          uint64_t pass0, long n_passes, long sample_period) {
+                          uint64_t pass0, long n_passes, long sample_period, int philox_rounds) {
   std::vector<int> occ = to_vec(occ_in);
   const int dim = static_cast<int>(shape.size());
   for (int s : shape)
@@ -208,7 +208,7 @@ py::dict checkerboard_run(std::vector<int> shape, i32arr occ_in, double J,
   {
     py::gil_scoped_release release;
     for (long t = 0; t < n_passes; ++t) {
-      checkerboard_pass(occ, shape, tab, seed, chain, pass0 + t, res);
+      checkerboard_pass(occ, shape, tab, seed, chain, pass0 + t, res, philox_rounds);
       if (sample_period > 0 && ((t + 1) % sample_period) == 0) {
         long long S, B;
         integer_observables(occ, shape, S, B);
@@ -572,7 +572,7 @@ PYBIND11_MODULE(_monte_oracle, m) {
         py::arg("occupation"), py::arg("J"), py::arg("temperature"),
         py::arg("mu"), py::arg("seed"), py::arg("chain") = 0,
         py::arg("pass0") = 0, py::arg("n_passes") = 1,
-        py::arg("sample_period") = 1);
+        py::arg("sample_period") = 1, py::arg("philox_rounds") = 10);
 
   m.def("checkerboard_half_sweep_slab",
         [](i32arr occ, i32arr halo_lo, i32arr halo_hi, long n0, long col_begin, long n_cols, double J,

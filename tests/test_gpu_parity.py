@@ -337,6 +337,41 @@ def test_tma3d_rejects_lattices_it_cannot_hold(cm):
         lat.run_passes(1, cm.MODE_CHECKERBOARD, 0)
 
 
+def test_seven_philox_rounds_opt_in_matches_the_oracle(cm, oracle):
+    """cmg_set_philox_rounds(7): the seven-round stream (the fewest rounds of Philox4x32 that pass
+    BigCrush) in the resident, the streaming 2-d and the generic kernel == the oracle's restatement
+    with seven rounds; a different trajectory from the default; kernels without it refuse."""
+    T, mu, seed = 2633.0, 0.013, 31337
+    for shape, variants, n_passes in (([1024, 512], ("ring2d", "bulk2d", "generic", "auto"), 6), ([64, 48], ("bulk2d", "generic", "auto"), 5),
+                                      ([32, 4, 6], ("generic", "auto"), 4)):
+        occ = rand_occ(nsites(shape), 77)
+        ref7 = oracle.checkerboard_run(shape, occ, J, T, mu, seed, 0, 0, n_passes, 2, philox_rounds=7)
+        ref10 = oracle.checkerboard_run(shape, occ, J, T, mu, seed, 0, 0, n_passes, 2)
+        assert not np.array_equal(ref7["occupation"], ref10["occupation"])
+        for variant in variants:
+            lat = cm.IsingLatticeGPU(shape, J=J)
+            lat.set_conditions(T, mu)
+            lat.seed_philox(seed)
+            lat.set_philox_rounds(7)
+            lat.set_kernel_variant(variant)
+            lat.upload(occ)
+            lat.run_passes(n_passes, cm.MODE_CHECKERBOARD, 2)
+            assert np.array_equal(lat.download(), ref7["occupation"]), (shape, variant, lat.kernel_variant)
+            S, B = lat.samples_sb()
+            assert np.array_equal(S, ref7["S"]) and np.array_equal(B, ref7["B"])
+            assert lat.counters()[1] == ref7["n_accept"]
+            lat.close()
+    lat = cm.IsingLatticeGPU([64, 48], J=J)
+    lat.set_conditions(T, mu)
+    with pytest.raises(cm.CmgError):
+        lat.set_philox_rounds(8)
+    lat.set_philox_rounds(7)
+    lat.set_kernel_variant("tile2d")
+    with pytest.raises(cm.CmgError, match="seven Philox rounds"):
+        lat.run_passes(1, cm.MODE_CHECKERBOARD, 0)
+    lat.close()
+
+
 def test_multichain_grid_matches_oracle(cm, oracle):
     # a 2x3 (T, mu) grid of independent chains, one context (BASELINE config 4 in small)
     shape = [64, 32]
