@@ -108,6 +108,7 @@ struct cmg_context {
   uint8_t *ring_peer_mb[2] = {nullptr, nullptr};
   int ring_peer_tiles[2] = {0, 0};
   int ring_tiles_cap = 0;              // "ring2d:rt=<n>": at most n tiles (several rings on one GPU)
+  bool pdl = true;                     // half-sweep kernels launched as programmatic dependents (":pdl=0" turns it off)
   unsigned long long ring_s0 = 0;      // half-sweeps the ring has stepped since the peers were attached
   // sticky device error word (kErr* bits, raised with atomicOr by kernels whose
   // waits are bounded) and its pinned host copy; zeroed at create and after a
@@ -1373,6 +1374,26 @@ static Tma3dPlan plan_tma3d(cmg_context *c) {
   return r;
 }
 
+// A half-sweep kernel as a programmatic dependent of the kernel before it on the stream
+// (pdl_launch_dependents / pdl_wait in the kernels): the ramp of one half-sweep overlaps
+// the tail of the previous one.  Slab contexts (peer flags, pushes) keep plain launches.
+static cudaError_t launch_dependent(const void *kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl,
+                                    SweepArgs &A) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  void *args[] = {&A};
+  return cudaLaunchKernelExC(&cfg, kernel, args);
+}
+
 static int launch_half_sweep(cmg_context *c, int variant, int colour, unsigned long long pass,
                              bool sample, long long slot) {
   SweepArgs A;
@@ -1428,18 +1449,21 @@ static int launch_half_sweep(cmg_context *c, int variant, int colour, unsigned l
     const long long V = c->shape[0] / 32;
     const long long strips = A.n_strips > 0 ? A.n_strips : (c->shape[1] + A.js - 1) / A.js;
     dim3 grid(nblocks(V * strips, 128), c->n_chains);
+    const bool pdl = c->pdl && !c->slab;
+    cudaError_t e;
     if (sample)
-      (c->philox_rounds == 7 ? k_halfsweep_bulk2d<true, 7> : k_halfsweep_bulk2d<true, 10>)<<<grid, block, kSmemBulk2d, c->stream>>>(A);
+      e = launch_dependent(c->philox_rounds == 7 ? (const void *)k_halfsweep_bulk2d<true, 7> : (const void *)k_halfsweep_bulk2d<true, 10>, grid, block, kSmemBulk2d, c->stream, pdl, A);
     else
-      (c->philox_rounds == 7 ? k_halfsweep_bulk2d<false, 7> : k_halfsweep_bulk2d<false, 10>)<<<grid, block, kSmemBulk2d, c->stream>>>(A);
+      e = launch_dependent(c->philox_rounds == 7 ? (const void *)k_halfsweep_bulk2d<false, 7> : (const void *)k_halfsweep_bulk2d<false, 10>, grid, block, kSmemBulk2d, c->stream, pdl, A);
+    if (e != cudaSuccess) return fail(c, CMG_ECUDA, cudaGetErrorString(e));
   } else if (variant == V_BULK3D) {
     const long long V = c->shape[0] / 32;
     const long long strips = A.n_strips > 0 ? A.n_strips : (c->shape[1] + A.js - 1) / A.js;
     dim3 grid(nblocks(V * strips * c->shape[2], 128), c->n_chains);
-    if (sample)
-      k_halfsweep_bulk3d<true><<<grid, block, kSmemBulk3d, c->stream>>>(A);
-    else
-      k_halfsweep_bulk3d<false><<<grid, block, kSmemBulk3d, c->stream>>>(A);
+    const bool pdl = c->pdl && !c->slab;
+    const cudaError_t e = sample ? launch_dependent((const void *)k_halfsweep_bulk3d<true>, grid, block, kSmemBulk3d, c->stream, pdl, A)
+                                 : launch_dependent((const void *)k_halfsweep_bulk3d<false>, grid, block, kSmemBulk3d, c->stream, pdl, A);
+    if (e != cudaSuccess) return fail(c, CMG_ECUDA, cudaGetErrorString(e));
   } else {
     return fail(c, CMG_EUNSUPPORTED, "kernel variant not available");
   }
@@ -3075,12 +3099,12 @@ int cmg_kstate_run_passes(cmg_context *c, int64_t n_passes, int mode, int64_t sa
       A.rk[2 * r + 1] = (uint32_t)(c->philox_seed >> 32) + (uint32_t)r * kPhiloxW1;
     }
     A.chain_offset = c->chain_offset;
-    const dim3 grid(nblocks(c->n_sites / 2, 256), c->n_chains);
+    const dim3 grid((unsigned)nblocks(c->shape[0] / 2, 32), (unsigned)nblocks(c->shape[1], 8 * kKStateTrips), (unsigned)(c->shape[2] * c->n_chains));
     for (int64_t t = 0; t < n_passes; ++t) {
       A.pass = c->h_pass;
       for (int colour = 0; colour < 2; ++colour) {
         A.colour = colour;
-        k_kstate_halfsweep<<<grid, 256, 0, c->stream>>>(A);
+        k_kstate_halfsweep<<<grid, dim3(32, 8), 0, c->stream>>>(A);
         ++c->launches;
       }
       c->nat_is_current = false;
@@ -3364,6 +3388,7 @@ int cmg_set_kernel_variant(cmg_context *c, const char *name) {
     if (c->ring_peer_mb[0] || c->ring_peer_mb[1]) return fail(c, CMG_ESTATE, "rt cannot change once ring peers are attached");
     c->ring_tiles_cap = std::max(0, atoi(s.c_str() + p + 4));
   }
+  c->pdl = s.find(":pdl=0") == std::string::npos;
   p = s.find(":ns=");
   if (p != std::string::npos) c->n_strips2d = std::max(0, atoi(s.c_str() + p + 4));
   p = s.find(":rp=");

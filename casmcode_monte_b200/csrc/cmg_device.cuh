@@ -672,8 +672,19 @@ constexpr int kSmemRing = kBulkPair ? kSmemTile : 256;
 constexpr uint32_t kBulkStageBytes = 128u * 36u;
 constexpr int kSmemBulk2d = kSmemRing + kBulkStages * (int)kBulkStageBytes;
 
+// Programmatic dependent launch (the half-sweeps of a run are a chain of kernels on one
+// stream): a kernel lets the next one start as soon as its own CTAs have all started, so the
+// next half-sweep's CTAs become resident while this one's tail drains, load their tables and
+// then wait here for the whole of this grid (and its memory) before they touch the planes.
+// Both are no-ops in a launch without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 template <bool SAMPLE, int R = 10>
 __global__ void __launch_bounds__(128, CMG_BULK_CTAS) k_halfsweep_bulk2d(SweepArgs A) {
+  pdl_launch_dependents();
   const LatticeView &L = A.L;
   const int chain = blockIdx.y;
   const int h = L.h, n1 = L.n1;
@@ -682,10 +693,11 @@ __global__ void __launch_bounds__(128, CMG_BULK_CTAS) k_halfsweep_bulk2d(SweepAr
   // other) or uniform strips of A.js columns
   const int n_strips = A.n_strips > 0 ? A.n_strips : (n1 + A.js - 1) / A.js;
   const bool edge_mode = L.edge_mode != 0 && n_strips >= 2;
-  if (!edge_mode) slab_wait_neighbours(L);
   // the table loads are issued first and only waited for (CTA barrier below)
   // after the thread's pipeline has been filled
   load_accept_table(A.tabs + chain, kBulkPair);
+  pdl_wait();
+  if (!edge_mode) slab_wait_neighbours(L);
 
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   Accum acc = {0u, 0u, 0u, 0u, 0u};
@@ -1217,6 +1229,10 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long *mbar, unsigne
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes)
                : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(unsigned long long *mbar) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(mbar);
+  asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(unsigned long long *mbar, unsigned int parity) {
   const uint32_t a = (uint32_t)__cvta_generic_to_shared(mbar);
   unsigned int ok;
@@ -1254,6 +1270,9 @@ __device__ __forceinline__ bool ring_stamp_ok(uint4 v, uint32_t expect) {
   return ((((v.x ^ expect) | (v.y ^ expect)) | ((v.z ^ expect) | (v.w ^ expect))) & 0xfefefefeu) == 0u;
 }
 
+#ifndef CMG_RING_CTA_SYNC
+#define CMG_RING_CTA_SYNC 0
+#endif
 template <int NT, int R = 10>
 __global__ void __launch_bounds__(NT, 1) k_ring2d(RingArgs A) {
   __shared__ long long s_acc[2 * kRingMaxPasses];  // per-pass {ones, B} of this CTA
@@ -1337,6 +1356,32 @@ __global__ void __launch_bounds__(NT, 1) k_ring2d(RingArgs A) {
   const int gc_nb = down ? (c1 == n1 ? 0 : c1) : (c0 == 0 ? n1 - 1 : c0 - 1);
   uint4 hv = make_uint4(0u, 0u, 0u, 0u);  // (no stamp: an outer edge polls its mailbox at once)
   if (edge && !remote) hv = __ldcg(reinterpret_cast<const uint4 *>(G[1] + (long long)gc_nb * h + p0));
+  // Between half-sweeps a warp waits for the warps whose bytes it reads and whose reads it
+  // overwrites, not for the CTA: the warps above and below it in its column group (the byte
+  // across the vector edge) and the warps of the same rows in the two adjacent groups (the
+  // column next to the run).  One mbarrier per warp and half-sweep parity counts the
+  // arrivals of those neighbours; a warp is never more than one half-sweep ahead of a
+  // neighbour, so two barriers per warp suffice, and the waits are bounded like the others.
+  __shared__ __align__(8) unsigned long long s_nbar[2][NT / 32];
+  const int wpg = V >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wu = warp % wpg;
+  int nbr[4], n_nbr = 0;
+  {
+    const int cand[4] = {q > 0 ? warp - wpg : -1, q < Q - 1 ? warp + wpg : -1,
+                         q * wpg + (wu + 1) % wpg, q * wpg + (wu + wpg - 1) % wpg};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      bool take = cand[i] >= 0 && cand[i] != warp;
+#pragma unroll
+      for (int k = 0; k < i; ++k) take = take && cand[k] != cand[i];
+      nbr[i] = take ? cand[i] : -1;
+      n_nbr += take ? 1 : 0;
+    }
+  }
+  if (lane == 0) {
+    mbar_init(&s_nbar[0][warp], (unsigned int)n_nbr);
+    mbar_init(&s_nbar[1][warp], (unsigned int)n_nbr);
+  }
+  const int my_nbr = lane == 0 ? nbr[0] : lane == 1 ? nbr[1] : lane == 2 ? nbr[2] : lane == 3 ? nbr[3] : -1;
   __syncthreads();
 
   unsigned int n_acc = 0;
@@ -1437,8 +1482,21 @@ __global__ void __launch_bounds__(NT, 1) k_ring2d(RingArgs A) {
     // the neighbour published its edge of this colour early in this half-sweep:
     // fetch it now, so that the round trip overlaps the barrier
     if (edge) hv = remote ? ld_relaxed_sys_v4(mb_in + colour * h) : ld_relaxed_gpu_v4(mb_in + colour * h);
-    __syncthreads();
+    if (CMG_RING_CTA_SYNC) {  // the first form: one CTA barrier per half-sweep (kept for A/B builds)
+      __syncthreads();
+    } else {
+      __syncwarp();
+      if (my_nbr >= 0) mbar_arrive(&s_nbar[colour][my_nbr]);
+      unsigned int spins = 0;
+      while (!mbar_try_wait(&s_nbar[colour][warp], (unsigned int)pl & 1u)) {
+        if (++spins > (1u << 25)) {  // (try_wait itself sleeps)
+          atomicOr(A.error, kErrRingEdge);
+          break;
+        }
+      }
+    }
   }
+  __syncthreads();
 
   // ---- flush the sampled sums of this launch
   for (int i = threadIdx.x; i < 2 * slot; i += NT) {
@@ -1510,9 +1568,11 @@ constexpr int kSmemBulk3d = kSmemRing + kBulkStages * (int)kBulk3dStageBytes;
 
 template <bool SAMPLE>
 __global__ void __launch_bounds__(128, CMG_BULK_CTAS) k_halfsweep_bulk3d(SweepArgs A) {
+  pdl_launch_dependents();
   const LatticeView &L = A.L;
   const int chain = blockIdx.y;
   load_accept_table(A.tabs + chain, kBulkPair);  // waited for after the pipeline fill
+  pdl_wait();
 
   const int h = L.h, n1 = L.n1, n2 = L.n2;
   const int V = h >> 4;
@@ -1681,10 +1741,6 @@ __global__ void __launch_bounds__(128, CMG_BULK_CTAS) k_halfsweep_bulk3d(SweepAr
 // other kernel.  Host side: V in {16, 32} (n0 = 512 or 1024), n2 % K == 0.
 // ---------------------------------------------------------------------------
 constexpr int kTmaStages = 8;
-__device__ __forceinline__ void mbar_arrive(unsigned long long *mbar) {
-  const uint32_t a = (uint32_t)__cvta_generic_to_shared(mbar);
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
-}
 __device__ __forceinline__ void mbar_wait_bounded(unsigned long long *mbar, unsigned int parity,
                                                   unsigned int *error) {
   unsigned int spins = 0;
@@ -3124,45 +3180,71 @@ struct KSweepArgs {
   int chain_offset;
 };
 
-// one thread per site of the colour being updated
+// Coloured half-sweep.  Block (32, 8): a warp takes 32 consecutive plane indices p of one
+// column, the block eight columns per trip and kKStateTrips trips (no division or modulo per
+// site); grid.z = k + n2 * chain.  The chain's threshold table is staged in shared memory when
+// it fits (every model but K = 4 in 3-d), accepted counts are reduced per block: one atomic
+// per block (the one-atomic-per-warp form was bound by same-address atomics in L2).
+constexpr int kKStateTrips = 8;
+constexpr int kKStateShared = 2048;
 __global__ void __launch_bounds__(256) k_kstate_halfsweep(KSweepArgs A) {
+  __shared__ uint32_t s_thr[kKStateShared];
+  __shared__ uint8_t s_never[kKStateShared];
+  __shared__ unsigned int s_acc;
   const LatticeView &L = A.L;
-  const int chain = blockIdx.y;
+  const int chain = (int)(blockIdx.z / (unsigned)L.n2);
+  const int k = (int)(blockIdx.z - (unsigned)chain * (unsigned)L.n2);
+  const int p = (int)(blockIdx.x * 32u + threadIdx.x);
   const KStateTables *tab = A.tabs + chain;
+  const int K = tab->K, n_cfg = tab->n_cfg;
+  const int n_entries = K * K * n_cfg;
+  const bool staged = n_entries <= kKStateShared;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  if (staged)
+    for (int e = tid; e < n_entries; e += 256) {
+      s_thr[e] = tab->thr_m1[e];
+      s_never[e] = tab->never[e];
+    }
+  if (tid == 0) s_acc = 0;
+  __syncthreads();
   uint8_t *C = L.planes + (long long)chain * L.chain_stride + (long long)A.colour * L.plane_stride;
   const uint8_t *O = L.planes + (long long)chain * L.chain_stride + (long long)(1 - A.colour) * L.plane_stride;
-  const long long plane_size = (long long)L.h * L.n1 * L.n2;
-  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int z = 2 * L.dim;
+  const uint32_t chain_word = (uint32_t)(chain + A.chain_offset) << 8;
+  const long long rowk = (long long)L.n1 * k;
+  const int km = (k == 0) ? L.n2 - 1 : k - 1, kp = (k == L.n2 - 1) ? 0 : k + 1;
   unsigned int acc = 0;
-  if (q < plane_size) {
-    const int p = (int)(q % L.h);
-    const long long jk = q / L.h;
-    const int j = (int)(jk % L.n1);
-    const int k = (int)(jk / L.n1);
-    const int par = (j + k + A.colour) & 1;  // i = 2p + par
-    const int jm = (j == 0) ? L.n1 - 1 : j - 1, jp = (j == L.n1 - 1) ? 0 : j + 1;
-    const long long rowk = (long long)L.n1 * k;
-    const int ps = par ? ((p == L.h - 1) ? 0 : p + 1) : ((p == 0) ? L.h - 1 : p - 1);
-    int cfg = kstate_weight(O[p + (long long)L.h * (jm + rowk)], z) + kstate_weight(O[p + (long long)L.h * (jp + rowk)], z) +
-              kstate_weight(O[p + (long long)L.h * (j + rowk)], z) + kstate_weight(O[ps + (long long)L.h * (j + rowk)], z);
-    if (L.dim == 3) {
-      const int km = (k == 0) ? L.n2 - 1 : k - 1, kp = (k == L.n2 - 1) ? 0 : k + 1;
-      cfg += kstate_weight(O[p + (long long)L.h * (j + (long long)L.n1 * km)], z) +
-             kstate_weight(O[p + (long long)L.h * (j + (long long)L.n1 * kp)], z);
-    }
-    const int from = C[q];
-    const uint4 w = site_group_random((unsigned long long)q, (uint32_t)(chain + A.chain_offset) << 8, A.pass, A.colour, 0, A.rk);
-    const int jj = (int)__umulhi(w.x, (uint32_t)(tab->K - 1));
-    const int to = jj + (jj >= from ? 1 : 0);
-    const int e = kstate_entry(tab, from, to, cfg);
-    if (!tab->never[e] && w.y <= tab->thr_m1[e]) {
-      C[q] = (uint8_t)to;
-      acc = 1;
+  if (p < L.h) {
+#pragma unroll 2
+    for (int t = 0; t < kKStateTrips; ++t) {
+      const int j = (int)((blockIdx.y * kKStateTrips + t) * 8u + threadIdx.y);
+      if (j >= L.n1) break;
+      const int par = (j + k + A.colour) & 1;  // i = 2p + par
+      const int jm = (j == 0) ? L.n1 - 1 : j - 1, jp = (j == L.n1 - 1) ? 0 : j + 1;
+      const long long q = p + (long long)L.h * (j + rowk);
+      const int ps = par ? ((p == L.h - 1) ? 0 : p + 1) : ((p == 0) ? L.h - 1 : p - 1);
+      int cfg = kstate_weight(O[p + (long long)L.h * (jm + rowk)], z) + kstate_weight(O[p + (long long)L.h * (jp + rowk)], z) +
+                kstate_weight(O[q], z) + kstate_weight(O[ps + (long long)L.h * (j + rowk)], z);
+      if (L.dim == 3)
+        cfg += kstate_weight(O[p + (long long)L.h * (j + (long long)L.n1 * km)], z) +
+               kstate_weight(O[p + (long long)L.h * (j + (long long)L.n1 * kp)], z);
+      const int from = C[q];
+      const uint4 w = site_group_random((unsigned long long)q, chain_word, A.pass, A.colour, 0, A.rk);
+      const int jj = (int)__umulhi(w.x, (uint32_t)(K - 1));
+      const int to = jj + (jj >= from ? 1 : 0);
+      const int e = (from * K + to) * n_cfg + cfg;
+      const bool never = staged ? s_never[e] : tab->never[e];
+      const uint32_t thr = staged ? s_thr[e] : tab->thr_m1[e];
+      if (!never && w.y <= thr) {
+        C[q] = (uint8_t)to;
+        ++acc;
+      }
     }
   }
   acc = __reduce_add_sync(0xffffffffu, acc);
-  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(A.n_accept + chain, (unsigned long long)acc);
+  if (threadIdx.x == 0 && acc) atomicAdd(&s_acc, acc);
+  __syncthreads();
+  if (tid == 0 && s_acc) atomicAdd(A.n_accept + chain, (unsigned long long)s_acc);
 }
 
 // integer observables of a k-state lattice in the natural layout: count[s] and the

@@ -40,6 +40,13 @@ def main():
         ("2d_tile", [4096, 4096], 1, ["tile2d:p=2:nt=512", "tile2d:p=3:nt=512", "tile2d:p=4:nt=512", "tile2d:p=3:nt=640", "tile2d:p=4:nt=640", "tile2d:p=3:nt=768", "tile2d:p=3:nt=1024", "tile2d:p=3:nt=256"], 120),
         ("3d_js", [512, 512, 512], 1, ["bulk3d:js=%d" % j for j in (24, 36, 40, 44, 48, 52, 56, 60, 64, 68, 72, 76, 80, 88, 96, 104, 128)], 10),
         ("2d_ring", [4096, 4096], 1, ["ring2d:rp=128", "ring2d:rp=32", "ring2d:rp=256", "tile2d:p=3:nt=512", "bulk2d"], 256),
+        ("2d_ringsync", [4096, 4096], 1, ["ring2d", "ring2d"], 512),
+        ("2d_ringsync_small", [1024, 4096], 1, ["ring2d"], 512),
+        ("2d_ringsync_8192", [8192, 2048], 1, ["ring2d"], 256),
+        ("pdl_3d", [512, 512, 512], 1, ["bulk3d", "bulk3d:pdl=0", "bulk3d", "bulk3d:pdl=0"], 20),
+        ("pdl_2d_sweep8", [4096, 4096], 8, ["bulk2d", "bulk2d:pdl=0", "bulk2d", "bulk2d:pdl=0"], 48),
+        ("pdl_2d_one", [4096, 4096], 1, ["bulk2d", "bulk2d:pdl=0"], 120),
+        ("pdl_3d_256", [256, 256, 256], 1, ["bulk3d", "bulk3d:pdl=0"], 40),
         ("2d_gridtile", [256, 256], 128, ["tile2d:nt=256", "tile2d:nt=512", "tile2d:nt=640", "tile2d:nt=768", "tile2d:nt=1024"], 128),
     ]
     only = sys.argv[1].split(",") if len(sys.argv) > 1 else None  # e.g. "2d_sweep8,3d"
