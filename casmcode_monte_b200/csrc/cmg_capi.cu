@@ -109,6 +109,12 @@ struct cmg_context {
   int ring_peer_tiles[2] = {0, 0};
   int ring_tiles_cap = 0;              // "ring2d:rt=<n>": at most n tiles (several rings on one GPU)
   bool pdl = true;                     // half-sweep kernels launched as programmatic dependents (":pdl=0" turns it off)
+  // chained half-sweeps (bulk2d / bulk3d): per-CTA completion flags, see hs_wait_for
+  bool hs_chain = true;                // ":chain=0": every half-sweep waits for the whole previous grid
+  unsigned int *d_hs_flags = nullptr;
+  size_t hs_flags_count = 0;
+  uint32_t hs_epoch = 1;
+  bool hs_prev_chained = false;        // the kernel before this one on the stream is a flagged half-sweep of the same geometry
   unsigned long long ring_s0 = 0;      // half-sweeps the ring has stepped since the peers were attached
   // sticky device error word (kErr* bits, raised with atomicOr by kernels whose
   // waits are bounded) and its pinned host copy; zeroed at create and after a
@@ -470,6 +476,7 @@ int cmg_destroy(cmg_context *c) {
   cudaFree(c->d_flags);
   cudaFree(c->d_done);
   cudaFree(c->d_ring_mailbox);
+  cudaFree(c->d_hs_flags);
   cudaFree(c->d_check);
   if (c->h_check_in) cudaFreeHost(c->h_check_in);
   if (c->h_check_out) cudaFreeHost(c->h_check_out);
@@ -523,6 +530,8 @@ static int device_error_check(cmg_context *c) {
   std::string msg;
   if (e & (kErrRingEdge | kErrRingCopy))
     msg += "ring2d: a tile waited too long for its neighbour or its bulk copy; ";
+  if (e & kErrChain)
+    msg += "chained half-sweeps: a CTA waited too long for its neighbours of the previous half-sweep; ";
   if (e & kErrSlabWait)
     msg += "slab half-sweep: a neighbour's flag did not arrive within 20 s (dead rank or "
            "half-sweep sequences that differ between ranks); ";
@@ -1296,6 +1305,7 @@ static int pick_strips3d(cmg_context *c, int *pair_layers) {
   *pair_layers = 0;
   if (c->js > 0 || n1 % 2 || V > 32 || (V < 32 && (32 % V || n2 % (2 * spw)))) return 0;
   *pair_layers = V < 32 ? 1 : 0;
+  if (c->n_strips2d > 1) return (int)std::min<long long>(c->n_strips2d, n1 / 2);  // ":ns=<n>"
   if (c->js_auto[7] > 0) return c->js_auto[7];
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_halfsweep_bulk3d<true>, 128, kSmemBulk3d) != cudaSuccess || per_sm < 1)
@@ -1394,8 +1404,50 @@ static cudaError_t launch_dependent(const void *kernel, dim3 grid, dim3 block, s
   return cudaLaunchKernelExC(&cfg, kernel, args);
 }
 
+// Per-CTA completion flags of the chained half-sweeps.  The first half-sweep of a run (the
+// caller cleared hs_prev_chained) waits for the whole grid before it; the ones behind it
+// wait for their neighbour CTAs only.
+static int chain_half_sweep(cmg_context *c, SweepArgs &A, dim3 grid, bool pdl, long long cols_per_strip) {
+  A.error = c->d_error;
+  // Worth it when a CTA's strip is long against the wait (five to seven flags per thread and
+  // a fence) and the grid fills the GPU: with a small grid the CTAs of the next half-sweep
+  // would poll next to the ones that work (one 4096^2 lattice, 74 CTAs: 0.76e12 chained
+  // against 0.88e12 waiting for the whole grid; 256^3 in 8-column strips: 0.70 against 0.76).
+  const bool worth = cols_per_strip >= 24 && 2ll * grid.x * grid.y >= (long long)c->sm_count * CMG_BULK_CTAS;
+  if (!pdl || !c->hs_chain || !worth) {
+    c->hs_prev_chained = false;
+    return CMG_OK;
+  }
+  const size_t need = (size_t)grid.x * grid.y;
+  if (c->hs_flags_count < need) {
+    CU(c, cudaStreamSynchronize(c->stream));
+    cudaFree(c->d_hs_flags);
+    c->d_hs_flags = nullptr;
+    CU(c, cudaMalloc(&c->d_hs_flags, need * sizeof(unsigned int)));
+    CU(c, cudaMemset(c->d_hs_flags, 0, need * sizeof(unsigned int)));
+    c->hs_flags_count = need;
+    c->hs_prev_chained = false;
+  }
+  if (c->hs_epoch >= 0x7ffffff0u) {  // (2^31 half-sweeps: start the epochs over behind a full wait)
+    CU(c, cudaMemsetAsync(c->d_hs_flags, 0, c->hs_flags_count * sizeof(unsigned int), c->stream));
+    c->hs_epoch = 1;
+    c->hs_prev_chained = false;
+  }
+  A.hs_flags = c->d_hs_flags;
+  A.hs_epoch = ++c->hs_epoch;
+  A.hs_wait = c->hs_prev_chained ? 1 : 0;
+  c->hs_prev_chained = true;
+  return CMG_OK;
+}
+
+// sample_kernel: run the sampling instantiation although this half-sweep is not sampled
+// (sums computed and dropped).  Chained half-sweeps overlap in time, and two different
+// kernels sharing an SM thrash its instruction cache (512^3 sampled every pass: 1.15e12
+// with the two instantiations alternating, 1.33e12 unchained, 1.48e12 with one), so a 3-d
+// run that samples often uses one instantiation throughout.  (The 2-d loops are half the
+// size and share the cache: 8 x 4096^2 1.55e12 alternating, 1.50e12 with one.)
 static int launch_half_sweep(cmg_context *c, int variant, int colour, unsigned long long pass,
-                             bool sample, long long slot) {
+                             bool sample, long long slot, bool sample_kernel = false) {
   SweepArgs A;
   memset(&A, 0, sizeof A);
   A.L = view(c);
@@ -1450,6 +1502,8 @@ static int launch_half_sweep(cmg_context *c, int variant, int colour, unsigned l
     const long long strips = A.n_strips > 0 ? A.n_strips : (c->shape[1] + A.js - 1) / A.js;
     dim3 grid(nblocks(V * strips, 128), c->n_chains);
     const bool pdl = c->pdl && !c->slab;
+    int rc = chain_half_sweep(c, A, grid, pdl, c->shape[1] / strips);
+    if (rc) return rc;
     cudaError_t e;
     if (sample)
       e = launch_dependent(c->philox_rounds == 7 ? (const void *)k_halfsweep_bulk2d<true, 7> : (const void *)k_halfsweep_bulk2d<true, 10>, grid, block, kSmemBulk2d, c->stream, pdl, A);
@@ -1461,7 +1515,9 @@ static int launch_half_sweep(cmg_context *c, int variant, int colour, unsigned l
     const long long strips = A.n_strips > 0 ? A.n_strips : (c->shape[1] + A.js - 1) / A.js;
     dim3 grid(nblocks(V * strips * c->shape[2], 128), c->n_chains);
     const bool pdl = c->pdl && !c->slab;
-    const cudaError_t e = sample ? launch_dependent((const void *)k_halfsweep_bulk3d<true>, grid, block, kSmemBulk3d, c->stream, pdl, A)
+    int rc = chain_half_sweep(c, A, grid, pdl, c->shape[1] / strips);
+    if (rc) return rc;
+    const cudaError_t e = (sample || (sample_kernel && A.hs_flags)) ? launch_dependent((const void *)k_halfsweep_bulk3d<true>, grid, block, kSmemBulk3d, c->stream, pdl, A)
                                  : launch_dependent((const void *)k_halfsweep_bulk3d<false>, grid, block, kSmemBulk3d, c->stream, pdl, A);
     if (e != cudaSuccess) return fail(c, CMG_ECUDA, cudaGetErrorString(e));
   } else {
@@ -1832,11 +1888,13 @@ int cmg_run_passes(cmg_context *c, int64_t n_passes, int mode, int64_t sample_pe
     CU(c, cudaGetLastError());
     return CMG_OK;
   }
+  c->hs_prev_chained = false;  // whatever is on the stream before this run is waited for as a whole
   for (long long t = 0; t < n_passes; ++t) {
     const bool sample = sample_period > 0 && ((c->n_pass + 1) % sample_period) == 0;
-    rc = launch_half_sweep(c, variant, 0, c->h_pass, false, 0);
+    const bool often = sample_period > 0 && sample_period <= 4;
+    rc = launch_half_sweep(c, variant, 0, c->h_pass, false, 0, often);
     if (rc) return rc;
-    rc = launch_half_sweep(c, variant, 1, c->h_pass, sample, c->n_samples);
+    rc = launch_half_sweep(c, variant, 1, c->h_pass, sample, c->n_samples, often);
     if (rc) return rc;
     ++c->h_pass;
     ++c->n_pass;
@@ -1859,6 +1917,7 @@ int cmg_slab_half_sweep(cmg_context *c, int colour, uint64_t pass_index, int sam
   }
   c->nat_is_current = false;
   c->variant_name = "bulk2d";
+  c->hs_prev_chained = false;
   rc = launch_half_sweep(c, V_BULK2D, colour, pass_index, do_sample, c->n_samples);
   if (rc) return rc;
   // The neighbours' flags count fused half-sweeps since the peers were attached,
@@ -3389,6 +3448,7 @@ int cmg_set_kernel_variant(cmg_context *c, const char *name) {
     c->ring_tiles_cap = std::max(0, atoi(s.c_str() + p + 4));
   }
   c->pdl = s.find(":pdl=0") == std::string::npos;
+  c->hs_chain = s.find(":chain=0") == std::string::npos;
   p = s.find(":ns=");
   if (p != std::string::npos) c->n_strips2d = std::max(0, atoi(s.c_str() + p + 4));
   p = s.find(":rp=");

@@ -90,6 +90,14 @@ struct SweepArgs {
   int n_strips;
   int pair_layers;
   int chain_offset;  // global index of chain 0 (chains sharded over several contexts)
+  // Chained half-sweeps (bulk2d / bulk3d, one context, consecutive launches of one run):
+  // every CTA publishes hs_epoch in hs_flags[chain][cta] when its columns are written;
+  // with hs_wait a thread waits for the CTAs of the previous half-sweep that wrote what
+  // it reads (and read what it writes) instead of for the whole previous grid.
+  unsigned int *hs_flags;
+  uint32_t hs_epoch;
+  int hs_wait;
+  unsigned int *error;  // sticky error word (bounded waits)
 };
 
 // ---------------------------------------------------------------------------
@@ -393,6 +401,9 @@ __device__ __forceinline__ uint4 ld16(const uint8_t *p) {
 __device__ __forceinline__ uint4 ld16_nc(const uint8_t *p) {
   return __ldg(reinterpret_cast<const uint4 *>(p));
 }
+__device__ __forceinline__ uint4 ld16_cg(const uint8_t *p) {
+  return __ldcg(reinterpret_cast<const uint4 *>(p));
+}
 
 // out byte k = in byte k-1, byte 0 <- lo (a single byte value)
 __device__ __forceinline__ uint4 shift_up_1(uint4 v, uint32_t lo) {
@@ -553,7 +564,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-constexpr unsigned int kErrRingEdge = 1u, kErrRingCopy = 2u, kErrSlabWait = 4u;
+constexpr unsigned int kErrRingEdge = 1u, kErrRingCopy = 2u, kErrSlabWait = 4u, kErrChain = 8u;
 constexpr unsigned long long kSlabWaitNs = 20ull * 1000ull * 1000ull * 1000ull;  // 20 s
 // before reading halos: both neighbours must have finished `epoch` half-sweeps.
 // The wait is bounded: a neighbour that never arrives (dead rank, sequence
@@ -673,18 +684,53 @@ constexpr uint32_t kBulkStageBytes = 128u * 36u;
 constexpr int kSmemBulk2d = kSmemRing + kBulkStages * (int)kBulkStageBytes;
 
 // Programmatic dependent launch (the half-sweeps of a run are a chain of kernels on one
-// stream): a kernel lets the next one start as soon as its own CTAs have all started, so the
-// next half-sweep's CTAs become resident while this one's tail drains, load their tables and
-// then wait here for the whole of this grid (and its memory) before they touch the planes.
+// stream): a kernel lets the next one start as soon as its own CTAs are all past their wait,
+// so the next half-sweep's CTAs become resident while this one's tail drains, load their
+// tables and then wait for this grid (pdl_wait: the whole of it and its memory; chained
+// launches: the neighbour CTAs only, hs_wait_for) before they touch the planes.
 // Both are no-ops in a launch without the attribute.
 __device__ __forceinline__ void pdl_launch_dependents() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// Chained half-sweeps: instead of pdl_wait (the WHOLE previous grid) a thread waits for the
+// CTAs of the previous half-sweep that hold its neighbours -- N of them, ids[] within the
+// chain's row of flags -- to have published epoch `want` or later.  The kernels are launched
+// as programmatic dependents with the trigger at their start, so every CTA waited for is
+// resident or finished (no deadlock), and a CTA only ever waits for CTAs of the half-sweep
+// before it.  Relaxed polls, then one acquire fence (which also drops stale L1 lines of the
+// plane the previous half-sweep rewrote).  Bounded like every other wait of the library.
+__device__ __forceinline__ unsigned int ld_relaxed_gpu_u32(const unsigned int *p) {
+  unsigned int v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+template <int N>
+__device__ __forceinline__ void hs_wait_for(const unsigned int *flags, const int (&ids)[N], uint32_t want,
+                                            unsigned int *error) {
+  unsigned int spins = 0;
+  for (;;) {
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < N; ++i) ok = ok && (int)(ld_relaxed_gpu_u32(flags + ids[i]) - want) >= 0;
+    if (ok) break;
+    if (++spins > (1u << 22)) {
+      if (error) atomicOr(error, kErrChain);
+      break;
+    }
+    __nanosleep(100);
+  }
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+}
+// after the CTA's last plane store: barrier, then one release store
+__device__ __forceinline__ void hs_publish(unsigned int *flag, uint32_t epoch) {
+  __syncthreads();
+  if (threadIdx.x == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+}
+
 template <bool SAMPLE, int R = 10>
 __global__ void __launch_bounds__(128, CMG_BULK_CTAS) k_halfsweep_bulk2d(SweepArgs A) {
-  pdl_launch_dependents();
   const LatticeView &L = A.L;
   const int chain = blockIdx.y;
   const int h = L.h, n1 = L.n1;
@@ -696,10 +742,24 @@ __global__ void __launch_bounds__(128, CMG_BULK_CTAS) k_halfsweep_bulk2d(SweepAr
   // the table loads are issued first and only waited for (CTA barrier below)
   // after the thread's pipeline has been filled
   load_accept_table(A.tabs + chain, kBulkPair);
-  pdl_wait();
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (A.hs_wait) {
+    if (t < (long long)V * n_strips) {
+      const int v = (int)(t % V), strip = (int)(t / V);
+      const int sm = strip == 0 ? n_strips - 1 : strip - 1, sp = strip == n_strips - 1 ? 0 : strip + 1;
+      const int vm = v == 0 ? V - 1 : v - 1, vp = v == V - 1 ? 0 : v + 1;
+      const int ids[5] = {(int)blockIdx.x, (v + V * sm) >> 7, (v + V * sp) >> 7, (vm + V * strip) >> 7,
+                          (vp + V * strip) >> 7};
+      hs_wait_for(A.hs_flags + (long long)chain * gridDim.x, ids, A.hs_epoch - 1u, A.error);
+    }
+  } else {
+    pdl_wait();
+  }
+  // the next half-sweep may become resident once every CTA of this one is past its wait: at
+  // most two half-sweeps share the GPU, and everything a CTA waits for has been resident
+  pdl_launch_dependents();
   if (!edge_mode) slab_wait_neighbours(L);
 
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   Accum acc = {0u, 0u, 0u, 0u, 0u};
   bool pushed = false;
 
@@ -796,8 +856,8 @@ __global__ void __launch_bounds__(128, CMG_BULK_CTAS) k_halfsweep_bulk2d(SweepAr
       };
       uint4 om = make_uint4(0u, 0u, 0u, 0u), oc = om;
       if (n > 0) {
-        om = ld16_nc(ocol(jbeg - 1) + p0);
-        oc = ld16_nc(O + (long long)h * jbeg + p0);
+        om = ld16_cg(ocol(jbeg - 1) + p0);  // (not .nc: a chained half-sweep overlaps the one that wrote them)
+        oc = ld16_cg(O + (long long)h * jbeg + p0);
       }
 #pragma unroll
       for (int k = 0; k < kBulkStages; ++k) fetch(k, par0 ^ (k & 1));
@@ -854,9 +914,10 @@ __global__ void __launch_bounds__(128, CMG_BULK_CTAS) k_halfsweep_bulk2d(SweepAr
   }
   long long ones = 0, bsum = 0;
   if (SAMPLE) accum_finish(acc, 4, ones, bsum);
-  block_accumulate<128>(acc.acc, ones, bsum, SAMPLE, A.n_accept + chain,
-                        SAMPLE ? A.sb + (long long)chain * A.sb_chain_stride : nullptr);
+  block_accumulate<128>(acc.acc, ones, bsum, SAMPLE && A.sb, A.n_accept + chain,
+                        SAMPLE && A.sb ? A.sb + (long long)chain * A.sb_chain_stride : nullptr);
   if (!edge_mode) slab_signal_neighbours(L, pushed);
+  if (A.hs_flags) hs_publish(A.hs_flags + (long long)chain * gridDim.x + blockIdx.x, A.hs_epoch);
 }
 
 // ---------------------------------------------------------------------------
@@ -1568,11 +1629,10 @@ constexpr int kSmemBulk3d = kSmemRing + kBulkStages * (int)kBulk3dStageBytes;
 
 template <bool SAMPLE>
 __global__ void __launch_bounds__(128, CMG_BULK_CTAS) k_halfsweep_bulk3d(SweepArgs A) {
-  pdl_launch_dependents();
   const LatticeView &L = A.L;
   const int chain = blockIdx.y;
   load_accept_table(A.tabs + chain, kBulkPair);  // waited for after the pipeline fill
-  pdl_wait();
+  if (!A.hs_wait) pdl_wait();
 
   const int h = L.h, n1 = L.n1, n2 = L.n2;
   const int V = h >> 4;
@@ -1601,6 +1661,24 @@ __global__ void __launch_bounds__(128, CMG_BULK_CTAS) k_halfsweep_bulk3d(SweepAr
       strip = (int)(t2 % n_strips);
       k = (int)(t2 / n_strips);
     }
+    if (A.hs_wait && active) {
+      // CTA (within the chain) of the thread that holds vector v2 of unit (strip s2, layer k2)
+      auto cta_of = [&](int v2, int s2, int k2) -> int {
+        if (A.pair_layers) {
+          const int spw = 32 / V;
+          const long long rest = 2ll * ((k2 >> 1) / spw) + (k2 & 1);
+          return (int)((rest * n_strips + s2) >> 2);
+        }
+        return (int)(((long long)v2 + (long long)V * (s2 + (long long)n_strips * k2)) >> 7);
+      };
+      const int sm = strip == 0 ? n_strips - 1 : strip - 1, sp = strip == n_strips - 1 ? 0 : strip + 1;
+      const int km = k == 0 ? n2 - 1 : k - 1, kp = k == n2 - 1 ? 0 : k + 1;
+      const int vm = v == 0 ? V - 1 : v - 1, vp = v == V - 1 ? 0 : v + 1;
+      const int ids[7] = {(int)blockIdx.x,       cta_of(v, sm, k),      cta_of(v, sp, k),     cta_of(v, strip, km),
+                          cta_of(v, strip, kp), cta_of(vm, strip, k), cta_of(vp, strip, k)};
+      hs_wait_for(A.hs_flags + (long long)chain * gridDim.x, ids, A.hs_epoch - 1u, A.error);
+    }
+    pdl_launch_dependents();  // (see k_halfsweep_bulk2d)
     const int p0 = v << 4;
     int jbeg, jend;
     if (A.n_strips > 0) {
@@ -1661,8 +1739,8 @@ __global__ void __launch_bounds__(128, CMG_BULK_CTAS) k_halfsweep_bulk3d(SweepAr
     };
     uint4 om = make_uint4(0u, 0u, 0u, 0u), oc = om;
     if (n > 0) {
-      om = ld16_nc(O + (long long)h * wrapj(jbeg - 1) + p0);
-      oc = ld16_nc(O + col0);
+      om = ld16_cg(O + (long long)h * wrapj(jbeg - 1) + p0);
+      oc = ld16_cg(O + col0);
     }
     // The ring slot and the column parity of a column are functions of its VIRTUAL
     // index iv = it - par0 (it = 0 .. n-1 the column of the strip): slot = iv & 3,
@@ -1715,8 +1793,9 @@ __global__ void __launch_bounds__(128, CMG_BULK_CTAS) k_halfsweep_bulk3d(SweepAr
   }
   long long ones = 0, bsum = 0;
   if (SAMPLE) accum_finish(acc, 6, ones, bsum);
-  block_accumulate<128>(acc.acc, ones, bsum, SAMPLE, A.n_accept + chain,
-                        SAMPLE ? A.sb + (long long)chain * A.sb_chain_stride : nullptr);
+  block_accumulate<128>(acc.acc, ones, bsum, SAMPLE && A.sb, A.n_accept + chain,
+                        SAMPLE && A.sb ? A.sb + (long long)chain * A.sb_chain_stride : nullptr);
+  if (A.hs_flags) hs_publish(A.hs_flags + (long long)chain * gridDim.x + blockIdx.x, A.hs_epoch);
 }
 
 // ---------------------------------------------------------------------------

@@ -838,3 +838,37 @@ def test_3d_full_plane_properties(cm):
     assert int(g.sum()) == S[-1]
     assert int((g * (np.roll(g, -1, 0) + np.roll(g, -1, 1) + np.roll(g, -1, 2))).sum()) == B[-1]
     assert lat.sample_now() == (int(S[-1]), int(B[-1]))
+
+
+# ------------------------------------------------- chained half-sweeps ----
+# Consecutive half-sweeps of a run are launched as programmatic dependents and wait for the
+# neighbour CTAs of the previous half-sweep only (per-CTA flags) -- half-sweeps overlap in
+# time.  The trajectory, the sampled sums and the counters must equal those of the plain
+# one-grid-after-the-other launches bit for bit, on lattices large enough for the CTAs of a
+# half-sweep to drift apart (several waves, several chains, 2-d and 3-d, V below / at / above
+# one CTA per strip).
+@pytest.mark.parametrize(
+    "shape,chains,variant,n_passes",
+    [([4096, 4096], 2, "bulk2d", 24), ([1024, 2048], 3, "bulk2d", 40), ([8192, 1024], 1, "bulk2d", 30),
+     ([256, 4096], 2, "bulk2d:js=16", 30), ([512, 128, 128], 1, "bulk3d", 20), ([256, 64, 96], 2, "bulk3d", 30),
+     ([1024, 64, 32], 1, "bulk3d", 20), ([4096, 16, 8], 1, "bulk3d", 20), ([64, 40, 24], 1, "bulk3d", 30)])
+def test_chained_half_sweeps_equal_whole_grid_launches(cm, shape, chains, variant, n_passes):
+    states = []
+    for opts in ("", ":pdl=0"):
+        lat = cm.IsingLatticeGPU(shape, n_chains=chains, J=J)
+        for ch in range(chains):
+            lat.set_conditions(2633.0 if len(shape) == 2 else 5235.0, 0.01 * ch, chain=ch)
+            lat.randomize(77 + ch, 0.5, chain=ch)
+        lat.seed_philox(0xABCDEF)
+        lat.set_kernel_variant(variant + opts)
+        lat.run_passes(n_passes, cm.MODE_CHECKERBOARD, 3)
+        lat.run_passes(5, cm.MODE_CHECKERBOARD, 1)  # a second call: its first half-sweep waits for the whole grid
+        lat.sync()
+        states.append(([lat.download(ch) for ch in range(chains)], [lat.samples_sb(ch) for ch in range(chains)],
+                       [lat.counters(ch) for ch in range(chains)]))
+        lat.close()
+    (occ_a, sb_a, cnt_a), (occ_b, sb_b, cnt_b) = states
+    for ch in range(chains):
+        assert np.array_equal(occ_a[ch], occ_b[ch])
+        assert np.array_equal(sb_a[ch][0], sb_b[ch][0]) and np.array_equal(sb_a[ch][1], sb_b[ch][1])
+        assert cnt_a[ch] == cnt_b[ch]

@@ -43,10 +43,13 @@ def main():
         ("2d_ringsync", [4096, 4096], 1, ["ring2d", "ring2d"], 512),
         ("2d_ringsync_small", [1024, 4096], 1, ["ring2d"], 512),
         ("2d_ringsync_8192", [8192, 2048], 1, ["ring2d"], 256),
-        ("pdl_3d", [512, 512, 512], 1, ["bulk3d", "bulk3d:pdl=0", "bulk3d", "bulk3d:pdl=0"], 20),
-        ("pdl_2d_sweep8", [4096, 4096], 8, ["bulk2d", "bulk2d:pdl=0", "bulk2d", "bulk2d:pdl=0"], 48),
-        ("pdl_2d_one", [4096, 4096], 1, ["bulk2d", "bulk2d:pdl=0"], 120),
-        ("pdl_3d_256", [256, 256, 256], 1, ["bulk3d", "bulk3d:pdl=0"], 40),
+        ("pdl_3d", [512, 512, 512], 1, ["bulk3d", "bulk3d:chain=0", "bulk3d:pdl=0", "bulk3d", "bulk3d:chain=0"], 20),
+        ("pdl_2d_sweep8", [4096, 4096], 8, ["bulk2d", "bulk2d:chain=0", "bulk2d:pdl=0", "bulk2d", "bulk2d:chain=0"], 48),
+        ("pdl_2d_one", [4096, 4096], 1, ["bulk2d", "bulk2d:chain=0", "bulk2d:pdl=0"], 120),
+        ("pdl_3d_256", [256, 256, 256], 1, ["bulk3d", "bulk3d:chain=0", "bulk3d:pdl=0"], 40),
+        ("chain_ns_2d", [4096, 4096], 8, ["bulk2d", "bulk2d:ns=92", "bulk2d:ns=111", "bulk2d:ns=148", "bulk2d:ns=56", "bulk2d:ns=222"], 48),
+        ("chain_ns_3d", [512, 512, 512], 1, ["bulk3d", "bulk3d:ns=12", "bulk3d:ns=14", "bulk3d:ns=18", "bulk3d:ns=7", "bulk3d:ns=27"], 20),
+        ("pdl_2d_16k", [16384, 16384], 1, ["bulk2d", "bulk2d:chain=0", "bulk2d:pdl=0"], 20),
         ("2d_gridtile", [256, 256], 128, ["tile2d:nt=256", "tile2d:nt=512", "tile2d:nt=640", "tile2d:nt=768", "tile2d:nt=1024"], 128),
     ]
     only = sys.argv[1].split(",") if len(sys.argv) > 1 else None  # e.g. "2d_sweep8,3d"
