@@ -529,7 +529,7 @@ static int device_error_check(cmg_context *c) {
   cudaMemsetAsync(c->d_error, 0, sizeof(unsigned int), c->stream);
   std::string msg;
   if (e & (kErrRingEdge | kErrRingCopy))
-    msg += "ring2d: a tile waited too long for its neighbour or its bulk copy; ";
+    msg += "ring2d / tile2d: a tile or warp waited too long for its neighbour or its bulk copy; ";
   if (e & kErrChain)
     msg += "chained half-sweeps: a CTA waited too long for its neighbours of the previous half-sweep; ";
   if (e & kErrSlabWait)
@@ -1547,6 +1547,7 @@ static int launch_tile_passes_sp(cmg_context *c, const TilePlan &tp, int n_passe
   A.n_passes = n_passes;
   A.chain_offset = c->chain_offset;
   A.n_tiles = tp.n_tiles;
+  A.error = c->d_error;
   A.halo = tp.n_tiles == 1 ? 0 : 2 * n_passes;
   A.w_max = tp.w_max;
   const unsigned long long V = (unsigned long long)(c->shape[0] / 32);

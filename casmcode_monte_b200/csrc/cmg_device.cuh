@@ -936,6 +936,32 @@ __global__ void __launch_bounds__(128, CMG_BULK_CTAS) k_halfsweep_bulk2d(SweepAr
 // any number of passes per launch (the 256x256 chains of the (T, mu) grid).
 // Launches per pass drop from 2 to 1/P and the per-site loads become LDS.
 // ---------------------------------------------------------------------------
+// mbarrier helpers (shared by k_tile2d, k_ring2d, k_halfsweep_tma3d)
+__device__ __forceinline__ void mbar_init(unsigned long long *mbar, unsigned int count) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(mbar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *mbar, unsigned int bytes) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(mbar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *mbar) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(mbar);
+  asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long *mbar, unsigned int parity) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(mbar);
+  unsigned int ok;
+  asm volatile(
+      "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+      : "=r"(ok)
+      : "r"(a), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
 struct TileArgs {
   LatticeView L;
   const ChainTables *tabs;
@@ -953,7 +979,11 @@ struct TileArgs {
   int w_max;                     // widest tile incl. halos (smem plane = w_max*h bytes)
   uint32_t v_magic;              // ceil(2^32 / V), V = h/16
   int chain_offset;              // global index of chain 0
+  unsigned int *error;           // sticky error word (bounded waits)
 };
+#ifndef CMG_TILE_CTA_SYNC
+#define CMG_TILE_CTA_SYNC 0  // 1: the CTA barrier per half-sweep of the first form (A/B builds)
+#endif
 
 template <int NT>
 __device__ __forceinline__ void block_add2(long long a, long long b, long long *dst,
@@ -1029,6 +1059,19 @@ __global__ void __launch_bounds__(NT, 1) k_tile2d(TileArgs A) {
     sts16(soff[plane] + (uint32_t)(cl * h + (v << 4)),
           __ldg(reinterpret_cast<const uint4 *>(G[plane] + (long long)gc * h + (v << 4))));
   }
+  // One lattice per CTA with a fixed assignment of columns to threads and every column
+  // group inside one warp (V <= 32): between half-sweeps a warp waits for the two warps
+  // that hold the columns next to its own, not for the CTA (per-warp mbarriers as in
+  // k_ring2d; with 256^2 chains a thread has four columns per half-sweep, so a CTA barrier
+  // per half-sweep tied sixteen independent warps together every ~1400 cycles).
+  __shared__ __align__(8) unsigned long long s_tbar[2][NT / 32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool fine = !CMG_TILE_CTA_SYNC && SINGLE && NT % V == 0 && V <= 32 && 32 % V == 0 && W >= NT / V;
+  if (fine && lane == 0) {
+    mbar_init(&s_tbar[0][warp], 2);
+    mbar_init(&s_tbar[1][warp], 2);
+  }
+  const int nbr_warp = lane == 0 ? (warp == 0 ? NT / 32 - 1 : warp - 1) : (warp == NT / 32 - 1 ? 0 : warp + 1);
   __syncthreads();
 
   unsigned int n_acc = 0;
@@ -1172,8 +1215,21 @@ __global__ void __launch_bounds__(NT, 1) k_tile2d(TileArgs A) {
       }
       ++slot;
     }
-    __syncthreads();
+    if (fine) {
+      __syncwarp();
+      if (lane < 2) mbar_arrive(&s_tbar[colour][nbr_warp]);
+      unsigned int spins = 0;
+      while (!mbar_try_wait(&s_tbar[colour][warp], (unsigned int)pl & 1u)) {
+        if (++spins > (1u << 25)) {  // bounded like every wait of the library (try_wait itself sleeps)
+          if (A.error) atomicOr(A.error, kErrRingEdge);
+          break;
+        }
+      }
+    } else {
+      __syncthreads();
+    }
   }
+  __syncthreads();
 
   // ---- flush the sampled sums of this launch (one global atomic per slot and quantity)
   for (int i = threadIdx.x; i < 2 * slot; i += NT) {
@@ -1280,30 +1336,6 @@ __device__ __forceinline__ void st_relaxed_sys_v4(void *p, uint4 v) {
 // ---- bulk (TMA) copies of a tile: a contiguous run of whole columns of a plane --------
 // One thread issues one cp.async.bulk per plane (UBLKCP); completion is counted
 // in bytes on an mbarrier that every thread of the CTA then waits for.
-__device__ __forceinline__ void mbar_init(unsigned long long *mbar, unsigned int count) {
-  const uint32_t a = (uint32_t)__cvta_generic_to_shared(mbar);
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *mbar, unsigned int bytes) {
-  const uint32_t a = (uint32_t)__cvta_generic_to_shared(mbar);
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long *mbar) {
-  const uint32_t a = (uint32_t)__cvta_generic_to_shared(mbar);
-  asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(unsigned long long *mbar, unsigned int parity) {
-  const uint32_t a = (uint32_t)__cvta_generic_to_shared(mbar);
-  unsigned int ok;
-  asm volatile(
-      "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-      : "=r"(ok)
-      : "r"(a), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
 // global -> shared, bytes % 16 == 0, both addresses 16-byte aligned
 __device__ __forceinline__ void bulk_load(uint32_t smem_dst, const void *gsrc, unsigned int bytes,
                                           unsigned long long *mbar) {
