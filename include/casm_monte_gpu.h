@@ -435,8 +435,11 @@ const char *cmg_kernel_variant(const cmg_context *ctx);
  * temporal blocking), "ring2d" (the whole lattice resident in the shared memory
  * of the GPU, one cooperative launch of many passes); options are appended as
  * ":js=56" (strip length), ":p=3" / ":nt=512" (tile passes / threads) and
- * ":rp=128" (passes per ring launch).  Every variant produces the same
- * trajectory. */
+ * ":rp=128" (passes per ring launch), ":ns=74" (balanced strips per lattice /
+ * layer), ":pdl=0" (bulk2d / bulk3d: plain launches instead of programmatic
+ * dependent ones) and ":chain=0" (dependent launches that wait for the whole
+ * previous half-sweep instead of for their neighbour CTAs).  Every variant and
+ * every option produces the same trajectory. */
 int cmg_set_kernel_variant(cmg_context *ctx, const char *name);
 
 #ifdef __cplusplus

@@ -49,6 +49,8 @@ def main():
         ("pdl_3d_256", [256, 256, 256], 1, ["bulk3d", "bulk3d:chain=0", "bulk3d:pdl=0"], 40),
         ("chain_ns_2d", [4096, 4096], 8, ["bulk2d", "bulk2d:ns=92", "bulk2d:ns=111", "bulk2d:ns=148", "bulk2d:ns=56", "bulk2d:ns=222"], 48),
         ("chain_ns_3d", [512, 512, 512], 1, ["bulk3d", "bulk3d:ns=12", "bulk3d:ns=14", "bulk3d:ns=18", "bulk3d:ns=7", "bulk3d:ns=27"], 20),
+        ("chain_slab8", [65536, 8192], 1, ["bulk2d", "bulk2d:chain=0", "bulk2d:pdl=0"], 12),
+        ("chain_slab4", [65536, 16384], 1, ["bulk2d", "bulk2d:chain=0", "bulk2d:pdl=0"], 8),
         ("pdl_2d_16k", [16384, 16384], 1, ["bulk2d", "bulk2d:chain=0", "bulk2d:pdl=0"], 20),
         ("2d_gridtile", [256, 256], 128, ["tile2d:nt=256", "tile2d:nt=512", "tile2d:nt=640", "tile2d:nt=768", "tile2d:nt=1024"], 128),
     ]
