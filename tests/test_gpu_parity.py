@@ -872,3 +872,42 @@ def test_chained_half_sweeps_equal_whole_grid_launches(cm, shape, chains, varian
         assert np.array_equal(occ_a[ch], occ_b[ch])
         assert np.array_equal(sb_a[ch][0], sb_b[ch][0]) and np.array_equal(sb_a[ch][1], sb_b[ch][1])
         assert cnt_a[ch] == cnt_b[ch]
+
+
+# One lattice per CTA with warps that wait for their two neighbour warps instead of for the
+# CTA (k_tile2d, single tile): many passes per launch, several chains, column groups of 4 /
+# 8 / 16 / 32 threads and CTAs of 256 / 512 / 1024 threads, against the oracle.
+@pytest.mark.parametrize(
+    "shape,variant",
+    [([256, 256], "tile2d"), ([256, 256], "tile2d:nt=1024"), ([256, 256], "tile2d:nt=256"), ([128, 256], "tile2d"),
+     ([512, 128], "tile2d"), ([1024, 64], "tile2d"), ([256, 70], "tile2d")])
+def test_tile2d_neighbour_warp_waits_match_oracle(cm, oracle, shape, variant):
+    n = nsites(shape)
+    conds = [(2633.0, 0.0), (2200.0, 0.03), (3500.0, -0.05)]
+    occs = [rand_occ(n, 300 + i) for i in range(len(conds))]
+    lat = run_cb(cm, shape, occs, None, None, 99, 60, variant, n_chains=len(conds), chain_conditions=conds, sample_period=7)
+    assert lat.kernel_variant == "tile2d"
+    for ch, (t, m) in enumerate(conds):
+        ref = oracle.checkerboard_run(shape, occs[ch], J, t, m, 99, ch, 0, 60, 7)
+        assert np.array_equal(lat.download(ch), ref["occupation"])
+        S, B = lat.samples_sb(ch)
+        assert np.array_equal(S, ref["S"]) and np.array_equal(B, ref["B"])
+        assert lat.counters(ch)[1] == ref["n_accept"]
+
+
+# The resident kernel over many half-sweeps per launch: warps wait for their neighbour warps
+# on per-warp mbarriers (two per warp, alternating with the colour), one / two / four / eight
+# warps per column group, against the oracle.
+@pytest.mark.parametrize("shape,variant", [([1024, 256], "ring2d"), ([2048, 160], "ring2d"), ([4096, 300], "ring2d:rp=17"),
+                                           ([8192, 64], "ring2d")])
+def test_ring2d_neighbour_warp_waits_over_many_passes(cm, oracle, shape, variant):
+    n = nsites(shape)
+    occ = rand_occ(n, 77)
+    T, mu = 2633.0, 0.01
+    lat = run_cb(cm, shape, occ, T, mu, 31337, 40, variant, sample_period=3)
+    assert lat.kernel_variant == "ring2d"
+    ref = oracle.checkerboard_run(shape, occ, J, T, mu, 31337, 0, 0, 40, 3)
+    assert np.array_equal(lat.download(), ref["occupation"])
+    S, B = lat.samples_sb()
+    assert np.array_equal(S, ref["S"]) and np.array_equal(B, ref["B"])
+    assert lat.counters()[1] == ref["n_accept"]
