@@ -3159,12 +3159,23 @@ int cmg_kstate_run_passes(cmg_context *c, int64_t n_passes, int mode, int64_t sa
       A.rk[2 * r + 1] = (uint32_t)(c->philox_seed >> 32) + (uint32_t)r * kPhiloxW1;
     }
     A.chain_offset = c->chain_offset;
-    const dim3 grid((unsigned)nblocks(c->shape[0] / 2, 32), (unsigned)nblocks(c->shape[1], 8 * kKStateTrips), (unsigned)(c->shape[2] * c->n_chains));
+    const dim3 grid((unsigned)nblocks((c->shape[0] / 2 + 1) / 2, 32), (unsigned)nblocks(c->shape[1], 8 * kKStateTrips), (unsigned)(c->shape[2] * c->n_chains));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(32, 8);
+    cfg.stream = c->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = c->pdl ? 1 : 0;
     for (int64_t t = 0; t < n_passes; ++t) {
       A.pass = c->h_pass;
       for (int colour = 0; colour < 2; ++colour) {
         A.colour = colour;
-        k_kstate_halfsweep<<<grid, dim3(32, 8), 0, c->stream>>>(A);
+        void *args[] = {&A};
+        CU(c, cudaLaunchKernelExC(&cfg, (const void *)k_kstate_halfsweep, args));
         ++c->launches;
       }
       c->nat_is_current = false;

@@ -3291,21 +3291,25 @@ struct KSweepArgs {
   int chain_offset;
 };
 
-// Coloured half-sweep.  Block (32, 8): a warp takes 32 consecutive plane indices p of one
-// column, the block eight columns per trip and kKStateTrips trips (no division or modulo per
-// site); grid.z = k + n2 * chain.  The chain's threshold table is staged in shared memory when
-// it fits (every model but K = 4 in 3-d), accepted counts are reduced per block: one atomic
-// per block (the one-atomic-per-warp form was bound by same-address atomics in L2).
+// Coloured half-sweep.  One Philox call serves the two sites p = 2g, 2g + 1 of a column
+// (group G = g + ceil(h/2) * (j + n1 * k); words 0, 1 for the even site, 2, 3 for the odd one:
+// species choice and acceptance uniform).  Block (32, 8): a warp takes 32 consecutive groups
+// of one column, the block eight columns per trip and kKStateTrips trips (no division or
+// modulo per site); grid.z = k + n2 * chain.  The chain's threshold table is staged in shared
+// memory when it fits (every model but K = 4 in 3-d), accepted counts are reduced per block:
+// one atomic per block (the one-atomic-per-warp form was bound by same-address atomics in
+// L2).  Launched as a programmatic dependent of the half-sweep before it (pdl_wait).
 constexpr int kKStateTrips = 8;
 constexpr int kKStateShared = 2048;
-__global__ void __launch_bounds__(256) k_kstate_halfsweep(KSweepArgs A) {
+__global__ void __launch_bounds__(256, 4) k_kstate_halfsweep(KSweepArgs A) {
   __shared__ uint32_t s_thr[kKStateShared];
   __shared__ uint8_t s_never[kKStateShared];
   __shared__ unsigned int s_acc;
   const LatticeView &L = A.L;
   const int chain = (int)(blockIdx.z / (unsigned)L.n2);
   const int k = (int)(blockIdx.z - (unsigned)chain * (unsigned)L.n2);
-  const int p = (int)(blockIdx.x * 32u + threadIdx.x);
+  const int g = (int)(blockIdx.x * 32u + threadIdx.x);
+  const int hh = (L.h + 1) >> 1;
   const KStateTables *tab = A.tabs + chain;
   const int K = tab->K, n_cfg = tab->n_cfg;
   const int n_entries = K * K * n_cfg;
@@ -3318,6 +3322,8 @@ __global__ void __launch_bounds__(256) k_kstate_halfsweep(KSweepArgs A) {
     }
   if (tid == 0) s_acc = 0;
   __syncthreads();
+  pdl_wait();
+  pdl_launch_dependents();
   uint8_t *C = L.planes + (long long)chain * L.chain_stride + (long long)A.colour * L.plane_stride;
   const uint8_t *O = L.planes + (long long)chain * L.chain_stride + (long long)(1 - A.colour) * L.plane_stride;
   const int z = 2 * L.dim;
@@ -3325,29 +3331,67 @@ __global__ void __launch_bounds__(256) k_kstate_halfsweep(KSweepArgs A) {
   const long long rowk = (long long)L.n1 * k;
   const int km = (k == 0) ? L.n2 - 1 : k - 1, kp = (k == L.n2 - 1) ? 0 : k + 1;
   unsigned int acc = 0;
-  if (p < L.h) {
+  // weights of the four species, one per byte: branch-free table in a register (the ternary
+  // chain compiled to two divergent branches per neighbour byte, which serialised the loads)
+  const uint32_t wpack = (1u << 8) | ((uint32_t)(z + 1) << 16) | ((uint32_t)((z + 1) * (z + 1)) << 24);
+  auto weight = [&](uint32_t sp) { return (wpack >> (8u * sp)) & 0xffu; };
+  if (g < hh) {
+    const int p0 = 2 * g;
+    const bool two = p0 + 1 < L.h;
+    const int p1 = two ? p0 + 1 : p0;
+    const int pb = (p0 == 0) ? L.h - 1 : p0 - 1;        // below the even site
+    const int pa = (p1 == L.h - 1) ? 0 : p1 + 1;        // above the odd site
 #pragma unroll 2
     for (int t = 0; t < kKStateTrips; ++t) {
       const int j = (int)((blockIdx.y * kKStateTrips + t) * 8u + threadIdx.y);
       if (j >= L.n1) break;
       const int par = (j + k + A.colour) & 1;  // i = 2p + par
       const int jm = (j == 0) ? L.n1 - 1 : j - 1, jp = (j == L.n1 - 1) ? 0 : j + 1;
-      const long long q = p + (long long)L.h * (j + rowk);
-      const int ps = par ? ((p == L.h - 1) ? 0 : p + 1) : ((p == 0) ? L.h - 1 : p - 1);
-      int cfg = kstate_weight(O[p + (long long)L.h * (jm + rowk)], z) + kstate_weight(O[p + (long long)L.h * (jp + rowk)], z) +
-                kstate_weight(O[q], z) + kstate_weight(O[ps + (long long)L.h * (j + rowk)], z);
-      if (L.dim == 3)
-        cfg += kstate_weight(O[p + (long long)L.h * (j + (long long)L.n1 * km)], z) +
-               kstate_weight(O[p + (long long)L.h * (j + (long long)L.n1 * kp)], z);
-      const int from = C[q];
-      const uint4 w = site_group_random((unsigned long long)q, chain_word, A.pass, A.colour, 0, A.rk);
-      const int jj = (int)__umulhi(w.x, (uint32_t)(K - 1));
-      const int to = jj + (jj >= from ? 1 : 0);
-      const int e = (from * K + to) * n_cfg + cfg;
-      const bool never = staged ? s_never[e] : tab->never[e];
-      const uint32_t thr = staged ? s_thr[e] : tab->thr_m1[e];
-      if (!never && w.y <= thr) {
-        C[q] = (uint8_t)to;
+      const long long col = (long long)L.h * (j + rowk);
+      const uint8_t *__restrict__ Oc = O + col;
+      const uint8_t *__restrict__ Om = O + (long long)L.h * (jm + rowk);
+      const uint8_t *__restrict__ Op = O + (long long)L.h * (jp + rowk);
+      uint8_t *__restrict__ Cc = C + col;
+      // every load of the two sites first
+      const uint32_t m0 = Om[p0], m1 = Om[p1], q0 = Op[p0], q1 = Op[p1], c0 = Oc[p0], c1 = Oc[p1];
+      const uint32_t e0 = Oc[par ? p1 : pb];  // the other i-neighbour of the even site (p1 == p0 + 1 when two)
+      const uint32_t e1 = Oc[par ? pa : p0];  // ... of the odd site
+      uint32_t a0 = 0, a1 = 0, b0 = 0, b1 = 0;
+      if (L.dim == 3) {
+        const uint8_t *__restrict__ Oa = O + (long long)L.h * (j + (long long)L.n1 * km);
+        const uint8_t *__restrict__ Ob = O + (long long)L.h * (j + (long long)L.n1 * kp);
+        a0 = Oa[p0], a1 = Oa[p1], b0 = Ob[p0], b1 = Ob[p1];
+      }
+      const int from0 = Cc[p0], from1 = Cc[p1];
+      const uint4 w = site_group_random((unsigned long long)g + (unsigned long long)hh * (unsigned long long)(j + rowk),
+                                        chain_word, A.pass, A.colour, 0, A.rk);
+      // even site; when the column has an odd number of plane indices its last group holds
+      // one site only, whose "other i-neighbour" for par = 1 is p0 + 1 wrapped to 0
+      const uint32_t e0x = (!two && par) ? (uint32_t)Oc[(p0 == L.h - 1) ? 0 : p0 + 1] : e0;
+      int cfg0 = (int)(weight(m0) + weight(q0) + weight(c0) + weight(e0x));
+      int cfg1 = (int)(weight(m1) + weight(q1) + weight(c1) + weight(e1));
+      if (L.dim == 3) {
+        cfg0 += (int)(weight(a0) + weight(b0));
+        cfg1 += (int)(weight(a1) + weight(b1));
+      }
+      const int jj0 = (int)__umulhi(w.x, (uint32_t)(K - 1)), jj1 = (int)__umulhi(w.z, (uint32_t)(K - 1));
+      const int to0 = jj0 + (jj0 >= from0 ? 1 : 0), to1 = jj1 + (jj1 >= from1 ? 1 : 0);
+      const int i0 = (from0 * K + to0) * n_cfg + cfg0, i1 = (from1 * K + to1) * n_cfg + cfg1;
+      uint32_t thr0, thr1;
+      bool nv0, nv1;
+      if (staged) {
+        thr0 = s_thr[i0], thr1 = s_thr[i1];
+        nv0 = s_never[i0], nv1 = s_never[i1];
+      } else {
+        thr0 = tab->thr_m1[i0], thr1 = tab->thr_m1[i1];
+        nv0 = tab->never[i0], nv1 = tab->never[i1];
+      }
+      if (!nv0 && w.y <= thr0) {
+        Cc[p0] = (uint8_t)to0;
+        ++acc;
+      }
+      if (two && !nv1 && w.w <= thr1) {
+        Cc[p1] = (uint8_t)to1;
         ++acc;
       }
     }

@@ -386,11 +386,14 @@ KStateRunResult kstate_serial_run(std::vector<int> const &shape, std::vector<int
 }
 
 /// Checkerboard order for the k-state model, scalar statement of the device kernel.
-/// Site q of colour c (plane index as in checkerboard_pass), pass t, chain ch: one call
-///   w = Philox4x32-10(counter = {lo32(q), (hi32(q)&0xff) | ch<<8, lo32(t), (hi32(t)<<2) | c}, key = seed)
-/// w[0] chooses the proposed species: j = (w[0] * (K-1)) >> 32, to = j + (j >= from);
-/// w[1] is the acceptance uniform: the site changes iff w[1] <= thr_m1[from][to][cfg]
-/// (and never when exp(-dPhi*beta) == 0).
+/// The two sites p = 2g, 2g + 1 of column (j, k) of colour c (plane index p as in
+/// checkerboard_pass; h = n0 / 2 plane indices per column) share one call: group
+/// G = g + ceil(h / 2) * (j + n1 * k), pass t, chain ch,
+///   w = Philox4x32-10(counter = {lo32(G), (hi32(G)&0xff) | ch<<8, lo32(t), (hi32(t)<<2) | c}, key = seed)
+/// The even site uses (w[0], w[1]), the odd one (w[2], w[3]): the first word chooses the
+/// proposed species, j = (w * (K-1)) >> 32, to = j + (j >= from); the second is the
+/// acceptance uniform: the site changes iff u <= thr_m1[from][to][cfg] (and never when
+/// exp(-dPhi*beta) == 0).
 inline KStateRunResult kstate_checkerboard_run(std::vector<int> const &shape, std::vector<int> occ,
                                                KStateModel const &m, double T, double const *mu, uint64_t seed,
                                                uint32_t chain, uint64_t pass0, long n_passes, long sample_period) {
@@ -409,10 +412,12 @@ inline KStateRunResult kstate_checkerboard_run(std::vector<int> const &shape, st
           for (long p = 0; p < h; ++p) {
             const long i = 2 * p + ((j + k + colour) & 1);
             const long l = i + L.n0 * (j + L.n1 * k);
-            const uint64_t q = static_cast<uint64_t>(p) + static_cast<uint64_t>(h) * (static_cast<uint64_t>(j) + static_cast<uint64_t>(L.n1) * static_cast<uint64_t>(k));
+            const uint64_t hh = static_cast<uint64_t>((h + 1) / 2);
+            const uint64_t q = static_cast<uint64_t>(p / 2) + hh * (static_cast<uint64_t>(j) + static_cast<uint64_t>(L.n1) * static_cast<uint64_t>(k));
             std::array<uint32_t, 4> ctr = {static_cast<uint32_t>(q), (static_cast<uint32_t>(q >> 32) & 0xffu) | (chain << 8),
                                            static_cast<uint32_t>(t), (static_cast<uint32_t>(t >> 32) << 2) | static_cast<uint32_t>(colour)};
-            const std::array<uint32_t, 4> w = Philox4x32::generate(ctr, key);
+            const std::array<uint32_t, 4> w4 = Philox4x32::generate(ctr, key);
+            const uint32_t w[2] = {w4[2 * (p & 1)], w4[2 * (p & 1) + 1]};
             const int from = occ[l];
             const int jj = static_cast<int>((static_cast<uint64_t>(w[0]) * static_cast<uint64_t>(m.K - 1)) >> 32);
             const int to = jj + (jj >= from ? 1 : 0);
