@@ -68,7 +68,12 @@ def test_serial_mode_reproduces_the_restated_proposal_machinery(cm, oracle, shap
     assert e.dump().split()[:312] == [str(int(v)) for v in st] and int(e.dump().split()[312]) == pos
 
 
-@pytest.mark.parametrize("shape,V,mu,T", [([16, 12], V3, MU3, 2500.0), ([64, 48], V4, MU4, 3000.0), ([8, 6, 4], V3, MU3, 4000.0)])
+# (odd numbers of plane indices per column: the last group of a column holds one site;
+# K = 4 in 3-d: the threshold table is read from global memory; 300 x 70: several blocks along
+# the column with a ragged last one, more columns than one block walks)
+@pytest.mark.parametrize("shape,V,mu,T", [([16, 12], V3, MU3, 2500.0), ([64, 48], V4, MU4, 3000.0), ([8, 6, 4], V3, MU3, 4000.0),
+                                          ([6, 4], V3, MU3, 2500.0), ([10, 6, 4], V3, MU3, 4000.0), ([8, 6, 4], V4, MU4, 4000.0),
+                                          ([300, 70], V3, MU3, 2500.0), ([2, 2], V3, MU3, 2500.0)])
 def test_checkerboard_kernel_matches_its_scalar_statement(cm, oracle, shape, V, mu, T):
     K = V.shape[0]
     n = int(np.prod(shape))
