@@ -1,7 +1,7 @@
 #!/bin/bash
-tag=${1:-x}
+tag=${1:-x}; cases=${2:-stagger}
 mkdir -p gpurun_out
-timeout 400 python tools/sweep_variants.py chain_slab8,chain_slab4 2>&1 | tee gpurun_out/chainslab_$tag.json | python -c "
+timeout 400 python tools/sweep_variants.py $cases 2>&1 | tee gpurun_out/sweep_$tag.json | python -c "
 import sys, json
 for l in sys.stdin:
     try:
