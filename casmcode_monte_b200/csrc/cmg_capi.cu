@@ -1194,7 +1194,11 @@ static int pick_variant(cmg_context *c, long long n_passes) {
   }
   // the tiled kernel wins while a half-sweep is short enough for launch ramp
   // and L2 latency to matter; very large batches stream better through bulk2d
-  if (plan_tiles(c, c->tile_passes).ok && c->n_sites * c->n_chains <= (1ll << 25)) {
+  // (one lattice per CTA -- no halo work, many passes per launch -- wins at any number of
+  // chains: the 1024 chains of 256^2 of BASELINE config 4 on one GPU 1.42e12 against 1.18e12
+  // streamed)
+  const TilePlan tp0 = plan_tiles(c, c->tile_passes);
+  if (tp0.ok && (tp0.n_tiles == 1 || c->n_sites * c->n_chains <= (1ll << 25))) {
     // a lattice too large for one CTA but not for the GPU's shared memory stays
     // resident across the launch (no halo recomputation): 4096^2 1.4e12 vs 0.98e12
     // (a ring launch costs ~18 us of staging and set-up: worth it from 4 passes per call,

@@ -186,15 +186,16 @@ def config3():
     return {"config": "3: 3D simple-cubic 512^3 SGC, T in {4000, 5235 (T_c), 6500} K x mu in {0, 0.05} eV, run to abs precision 1e-4 on potential_energy and param_composition (cap 2e4 passes) with on-device sampling, equilibration and convergence statistics", "runs": out}
 
 
-def config4():
+def config4(n_shards=8, variant="auto"):
     from casmcode_monte_b200.parallel import shard_chains
 
     temps = np.linspace(1500.0, 4000.0, 32)
     mus = np.linspace(-0.2, 0.2, 32)
     conds = [(float(T), float(mu)) for T in temps for mu in mus]
-    mine = shard_chains(len(conds), 8, 0)  # rank 0 of 8: 128 chains
+    mine = shard_chains(len(conds), n_shards, 0)  # rank 0 of 8: 128 chains; n_shards = 1: the whole grid on this GPU
     shape = [256, 256]
     lat = cm.IsingLatticeGPU(shape, n_chains=len(mine), J=J)
+    lat.set_kernel_variant(variant)
     for local, g in enumerate(mine):
         lat.set_conditions(*conds[g], chain=local)
     lat.seed_philox(0xC0FFEE)
@@ -207,7 +208,7 @@ def config4():
     m, p, v, k = lat.series_stats_all(cm.Q_POTENTIAL_ENERGY)
     mx, px, vx, kx = lat.series_stats_all(cm.Q_PARAM_COMPOSITION)
     return {
-        "config": "4: 1024-point (T, mu) grid of independent 256x256 SGC chains; this is one GPU's share (128 chains), 2000 + 8000 passes, sample every pass, per-chain statistics on the device",
+        "config": "4: 1024-point (T, mu) grid of independent 256x256 SGC chains; %d chains on this GPU (%s), 2000 + 8000 passes, sample every pass, per-chain statistics on the device" % (len(mine), "one GPU's share of eight" if n_shards == 8 else "the whole grid"),
         "kernel": lat.kernel_variant,
         "n_chains": len(mine),
         "attempts_per_s": len(mine) * 256 * 256 * n_meas / dt,
@@ -219,4 +220,5 @@ def config4():
 
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "config2"
-    print(json.dumps({"config2": config2, "config2seq": config2seq, "config3": config3, "config4": config4}[which]()), flush=True)
+    print(json.dumps({"config2": config2, "config2seq": config2seq, "config3": config3, "config4": config4,
+                      "config4full": lambda: config4(1), "config4full_tile": lambda: config4(1, "tile2d")}[which]()), flush=True)
