@@ -1558,11 +1558,26 @@ static int launch_tile_passes_sp(cmg_context *c, const TilePlan &tp, int n_passe
   A.v_magic = (uint32_t)((0x100000000ull + V - 1) / V);
   dim3 grid(tp.n_tiles, c->n_chains);
   cudaError_t e;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = grid;
+  cfg.dynamicSmemBytes = tp.smem;
+  cfg.stream = c->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  // (tiles with halos: launches of a few passes, 10-20 us each -- 512^2 +20 %, 768 x 2048 +15 %;
+  // one lattice per CTA runs up to 64 passes per launch and gains nothing)
+  cfg.numAttrs = (c->pdl && tp.n_tiles > 1) ? 1 : 0;
+  void *args[] = {&A};
 #define LAUNCH_TILE_S(NT, S)                                                                  \
   e = cudaFuncSetAttribute(k_tile2d<NT, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
                            (int)tp.smem);                                                     \
   if (e != cudaSuccess) return fail(c, CMG_ECUDA, cudaGetErrorString(e));                     \
-  k_tile2d<NT, S><<<grid, NT, tp.smem, c->stream>>>(A);
+  cfg.blockDim = dim3(NT);                                                                    \
+  e = cudaLaunchKernelExC(&cfg, (const void *)k_tile2d<NT, S>, args);                         \
+  if (e != cudaSuccess) return fail(c, CMG_ECUDA, cudaGetErrorString(e));
 #define LAUNCH_TILE(NT)                                                                       \
   if (tp.n_tiles == 1) {                                                                      \
     LAUNCH_TILE_S(NT, true)                                                                   \

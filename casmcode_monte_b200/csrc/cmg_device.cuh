@@ -1032,6 +1032,10 @@ __global__ void __launch_bounds__(NT, 1) k_tile2d(TileArgs A) {
   const int chain = blockIdx.y;
   const int tile = blockIdx.x;
   load_accept_table(A.tabs + chain, true);
+  // consecutive launches of a run are programmatic dependents: this grid becomes resident
+  // and loads its tables under the tail of the one before it
+  pdl_wait();
+  pdl_launch_dependents();
 
   const int h = L.h, n1 = L.n1;
   const int V = h >> 4;
@@ -1057,7 +1061,7 @@ __global__ void __launch_bounds__(NT, 1) k_tile2d(TileArgs A) {
     gc += (gc < 0) ? n1 : 0;
     gc -= (gc >= n1) ? n1 : 0;
     sts16(soff[plane] + (uint32_t)(cl * h + (v << 4)),
-          __ldg(reinterpret_cast<const uint4 *>(G[plane] + (long long)gc * h + (v << 4))));
+          __ldcg(reinterpret_cast<const uint4 *>(G[plane] + (long long)gc * h + (v << 4))));  // (not .nc: the grid may start under its predecessor)
   }
   // One lattice per CTA with a fixed assignment of columns to threads and every column
   // group inside one warp (V <= 32): between half-sweeps a warp waits for the two warps

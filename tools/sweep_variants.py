@@ -51,6 +51,9 @@ def main():
         ("chain_ns_3d", [512, 512, 512], 1, ["bulk3d", "bulk3d:ns=12", "bulk3d:ns=14", "bulk3d:ns=18", "bulk3d:ns=7", "bulk3d:ns=27"], 20),
         ("chain_slab8", [65536, 8192], 1, ["bulk2d", "bulk2d:chain=0", "bulk2d:pdl=0"], 12),
         ("chain_slab4", [65536, 16384], 1, ["bulk2d", "bulk2d:chain=0", "bulk2d:pdl=0"], 8),
+        ("pdl_tile_512", [512, 512], 1, ["auto", "auto:pdl=0", "tile2d:p=3", "tile2d:p=3:pdl=0", "tile2d:p=2", "tile2d:p=2:pdl=0"], 600),
+        ("pdl_tile_768", [768, 2048], 1, ["auto", "auto:pdl=0"], 300),
+        ("pdl_tile_grid", [256, 256], 128, ["auto", "auto:pdl=0"], 128),
         ("pdl_2d_16k", [16384, 16384], 1, ["bulk2d", "bulk2d:chain=0", "bulk2d:pdl=0"], 20),
         ("2d_gridtile", [256, 256], 128, ["tile2d:nt=256", "tile2d:nt=512", "tile2d:nt=640", "tile2d:nt=768", "tile2d:nt=1024"], 128),
     ]
