@@ -3305,7 +3305,7 @@ struct KSweepArgs {
 // L2).  Launched as a programmatic dependent of the half-sweep before it (pdl_wait).
 constexpr int kKStateTrips = 8;
 constexpr int kKStateShared = 2048;
-__global__ void __launch_bounds__(256, 4) k_kstate_halfsweep(KSweepArgs A) {
+__global__ void __launch_bounds__(256, 3) k_kstate_halfsweep(KSweepArgs A) {
   __shared__ uint32_t s_thr[kKStateShared];
   __shared__ uint8_t s_never[kKStateShared];
   __shared__ unsigned int s_acc;
