@@ -60,6 +60,7 @@ struct cmg_context {
   std::vector<void *> ipc_opened;
 
   uint8_t *d_planes = nullptr;
+  uint8_t *d_planes_alt = nullptr;  // second copy, written by k_tile2d launches with halos (then swapped with d_planes)
   long long plane_stride = 0, chain_stride = 0;
   uint8_t *d_nat = nullptr;  // [n_chains][n_sites]
   bool nat_is_current = false;     // natural copy mirrors the planes
@@ -459,6 +460,7 @@ int cmg_destroy(cmg_context *c) {
   cudaStreamSynchronize(c->stream);
   for (void *p : c->ipc_opened) cudaIpcCloseMemHandle(p);
   cudaFree(c->d_planes);
+  cudaFree(c->d_planes_alt);
   cudaFree(c->d_nat);
   cudaFree(c->d_stage);
   cudaFree(c->d_flag);
@@ -1552,6 +1554,11 @@ static int launch_tile_passes_sp(cmg_context *c, const TilePlan &tp, int n_passe
   A.chain_offset = c->chain_offset;
   A.n_tiles = tp.n_tiles;
   A.error = c->d_error;
+  A.out_planes = c->d_planes;
+  if (tp.n_tiles > 1) {  // tiles with halos never write back in place (TileArgs::out_planes)
+    if (!c->d_planes_alt) CU(c, cudaMalloc(&c->d_planes_alt, (size_t)c->chain_stride * c->n_chains));
+    A.out_planes = c->d_planes_alt;
+  }
   A.halo = tp.n_tiles == 1 ? 0 : 2 * n_passes;
   A.w_max = tp.w_max;
   const unsigned long long V = (unsigned long long)(c->shape[0] / 32);
@@ -1598,6 +1605,7 @@ static int launch_tile_passes_sp(cmg_context *c, const TilePlan &tp, int n_passe
 #undef LAUNCH_TILE_S
 #undef LAUNCH_TILE
   ++c->launches;
+  if (tp.n_tiles > 1) std::swap(c->d_planes, c->d_planes_alt);  // (stream order: everything enqueued from here on sees the new planes)
   return CMG_OK;
 }
 

@@ -980,6 +980,13 @@ struct TileArgs {
   uint32_t v_magic;              // ceil(2^32 / V), V = h/16
   int chain_offset;              // global index of chain 0
   unsigned int *error;           // sticky error word (bounded waits)
+  // where the owned columns are written back: the planes themselves for one lattice per
+  // CTA; the context's second copy of the planes for tiles with halos (the host swaps the two
+  // after the launch).  A tile stages its halo columns from global memory, so writing back in
+  // place is only right while every tile of a lattice has staged before any finishes -- true
+  // for one wave of CTAs on an otherwise idle GPU, false for several waves (16 chains of
+  // 1024^2 in 16 waves differed from run to run; found by tools/auto_vs_generic.py).
+  uint8_t *out_planes;
 };
 #ifndef CMG_TILE_CTA_SYNC
 #define CMG_TILE_CTA_SYNC 0  // 1: the CTA barrier per half-sweep of the first form (A/B builds)
@@ -1248,7 +1255,8 @@ __global__ void __launch_bounds__(NT, 1) k_tile2d(TileArgs A) {
     const int r = it - plane * TW * V;
     const int dc = (int)__umulhi((uint32_t)r, A.v_magic);
     const int v = r - dc * V;
-    *reinterpret_cast<uint4 *>(G[plane] + (long long)(c0 + dc) * h + (v << 4)) =
+    *reinterpret_cast<uint4 *>(A.out_planes + (long long)chain * L.chain_stride + (plane ? L.plane_stride : 0) +
+                               (long long)(c0 + dc) * h + (v << 4)) =
         lds16(soff[plane] + (uint32_t)((H + dc) * h + (v << 4)));
   }
   n_acc = __reduce_add_sync(0xffffffffu, n_acc);
