@@ -13,6 +13,11 @@ import casmcode_monte_b200 as cm
 cases = [([2048, 2048], 1, 24), ([8192, 8192], 1, 6), ([1024, 1024], 16, 12), ([512, 512, 64], 1, 10), ([128, 128, 128], 2, 12),
          ([64, 64], 512, 30), ([100, 100], 3, 10), ([4096, 64], 1, 20), ([512, 512], 1, 20), ([768, 2048], 2, 12),
          ([256, 256], 300, 20), ([96, 34], 5, 10), ([2048, 64, 16], 1, 10), ([16384, 2048], 1, 6), ([32, 6], 1, 9)]
+if len(sys.argv) > 1 and sys.argv[1] == "more":  # a second assortment: many chains on the resident kernel, ragged sizes, long thin lattices
+    cases = [([1024, 256], 40, 12), ([2048, 512], 7, 10), ([4096, 512], 3, 9), ([8192, 64], 64, 8), ([1024, 4096], 2, 9),
+             ([64, 4096], 6, 12), ([192, 300], 9, 10), ([320, 64], 100, 16), ([1024, 130], 1, 14), ([8192, 2050], 1, 6),
+             ([256, 32, 64], 5, 10), ([512, 64, 64], 3, 8), ([1024, 32, 32], 2, 8), ([64, 64, 64], 9, 10), ([4096, 4096], 2, 6),
+             ([128, 100], 148, 14), ([448, 448], 4, 10), ([2, 2], 3, 5), ([6, 4, 2], 2, 6)]
 bad = 0
 for shape, chains, n_passes in cases:
     out = {}
