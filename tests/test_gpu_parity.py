@@ -911,3 +911,16 @@ def test_ring2d_neighbour_warp_waits_over_many_passes(cm, oracle, shape, variant
     S, B = lat.samples_sb()
     assert np.array_equal(S, ref["S"]) and np.array_equal(B, ref["B"])
     assert lat.counters()[1] == ref["n_accept"]
+
+
+def test_statistics_fuzz_against_the_oracle():
+    """tools/stats_fuzz.py: 250 random series (constant, drifting, stepping, heavy-tailed, discrete,
+    one to 6000 samples, lengths around the chunk sizes of the equilibration scan) through the device
+    statistics and the oracle."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "stats_fuzz.py"), "250", "3"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
