@@ -733,7 +733,10 @@ def test_general_conversions_batched_on_the_device_match_the_host():
         assert list(c.bijk_to_l_batch(shifted)) == ls
 
 
-@pytest.mark.parametrize("shape,variant", [([64, 48], "auto"), ([1024, 128], "ring2d"), ([256, 64], "bulk2d"), ([32, 10, 8], "auto")])
+# (512 x 96 / 768 x 64 through tile2d: tiles with halos write back to the second copy of the planes and
+# the two are swapped after every launch -- 7 passes are three launches, an odd number of swaps)
+@pytest.mark.parametrize("shape,variant", [([64, 48], "auto"), ([1024, 128], "ring2d"), ([256, 64], "bulk2d"), ([32, 10, 8], "auto"),
+                                           ([512, 96], "tile2d"), ([768, 64], "tile2d:p=2"), ([4096, 64], "bulk2d")])
 def test_mark_and_rollback_undo_a_speculative_block(cm, oracle, shape, variant):
     """cmg_mark / cmg_rollback: passes enqueued after the mark leave no trace after a rollback
     (occupation, acceptance count, pass and sample counters, sample series), the samples up to
@@ -924,3 +927,36 @@ def test_statistics_fuzz_against_the_oracle():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "stats_fuzz.py"), "250", "3"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_host_formats_after_tiled_launches(cm, oracle):
+    """int32 / int8 / bit-packed downloads, an upload in between and the natural-layout observables
+    see the planes the last tiled launch wrote (tiles with halos alternate between two copies)."""
+    shape = [512, 96]
+    n = nsites(shape)
+    occ = rand_occ(n, 5)
+    T, mu, seed = 2633.0, 0.01, 99
+    lat = cm.IsingLatticeGPU(shape, J=J)
+    lat.set_conditions(T, mu)
+    lat.seed_philox(seed)
+    lat.set_kernel_variant("tile2d")
+    lat.upload(occ)
+    ref = occ
+    done = 0
+    for n_passes in (1, 3, 2, 5):  # 1, 1, 1 and 2 launches: the current copy alternates
+        lat.run_passes(n_passes, cm.MODE_CHECKERBOARD, 1)
+        r = oracle.checkerboard_run(shape, ref, J, T, mu, seed, 0, done, n_passes, 1)
+        ref, done = r["occupation"], done + n_passes
+        a32 = lat.download()
+        assert np.array_equal(a32, ref)
+        assert np.array_equal(lat.download_i8().astype(np.int32), ref)
+        bits = lat.download_bits()
+        assert np.array_equal(np.unpackbits(bits, bitorder="little")[:n].astype(np.int32) * 2 - 1, ref)
+        assert lat.sample_now() == (int(r["S"][-1]), int(r["B"][-1]))
+    other = rand_occ(n, 6)
+    lat.upload_i8(other.astype(np.int8))
+    assert np.array_equal(lat.download(), other)
+    lat.run_passes(3, cm.MODE_CHECKERBOARD, 1)
+    r = oracle.checkerboard_run(shape, other, J, T, mu, seed, 0, done, 3, 1)
+    assert np.array_equal(lat.download(), r["occupation"])
+    lat.close()
