@@ -346,7 +346,8 @@ def test_run_checkerboard_with_the_row_column_energy_form(api, oracle):
     assert mc.formation_energy_calculator.per_unitcell() == d.samplers["formation_energy"].component(0)[-1]
 
 
-@pytest.mark.parametrize("shape", [(64, 48), (1024, 512)])  # the second runs resident in shared memory (k_ring2d)
+# (the second runs resident in shared memory, k_ring2d; the third in tiles with halos, k_tile2d; the fourth streams)
+@pytest.mark.parametrize("shape", [(64, 48), (1024, 512), (512, 96), (96, 34)])
 def test_run_checkerboard_mode_matches_oracle_checkerboard(api, oracle, shape):
     n = shape[0] * shape[1]
     occ = np.random.default_rng(3).choice(np.array([-1, 1], dtype=np.int32), size=n)
@@ -481,7 +482,8 @@ def test_conversions_class(api):
     assert list(f.bijk_to_l_batch(b)) == list(range(54))
 
 
-def test_run_with_overlapped_checks_gives_the_same_results(api):
+@pytest.mark.parametrize("shape", [(64, 64), (512, 96), (1024, 128)])  # one CTA; tiles with halos (two copies of the planes); resident
+def test_run_with_overlapped_checks_gives_the_same_results(api, shape):
     """overlap_checks = True (next block enqueued before the pending check, check on a second
     stream, rollback on completion) must change nothing: samplers, counters, completion results
     and the final occupation are those of the waiting loop."""
@@ -498,7 +500,7 @@ def test_run_with_overlapped_checks_gives_the_same_results(api):
         p.check_period = 25
         # (oracle, same conditions: the composition reaches 6e-3 after ~250 samples, 2.7e-3 after 900)
         api.sampling.converge(fns, p).set_precision("potential_energy", abs=2e-3).set_precision("param_composition", abs=6e-3)
-        state = make_state(api, (64, 64), 3200.0, 0.03)
+        state = make_state(api, shape, 3200.0, 0.03)
         e = api.monte.RandomNumberEngine()
         e.seed(77)
         mc.run(state=state, sampling_functions=fns, json_sampling_functions=api.sampling.jsonStateSamplingFunctionMap(),
@@ -515,3 +517,4 @@ def test_run_with_overlapped_checks_gives_the_same_results(api):
     assert a[0] == b[0] and a[1] == b[1] and a[2] == b[2] and a[5] and b[5] and a[6] == b[6]
     assert np.array_equal(a[3], b[3]) and np.array_equal(a[4], b[4])
     assert 50 <= a[6] < 900  # converged before the cutoff: the speculative block was rolled back
+    # (larger lattices converge sooner; every shape stops at a check, with a block in flight)
