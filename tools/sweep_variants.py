@@ -54,6 +54,10 @@ def main():
         ("pdl_tile_512", [512, 512], 1, ["auto", "auto:pdl=0", "tile2d:p=3", "tile2d:p=3:pdl=0", "tile2d:p=2", "tile2d:p=2:pdl=0"], 600),
         ("pdl_tile_768", [768, 2048], 1, ["auto", "auto:pdl=0"], 300),
         ("pdl_tile_grid", [256, 256], 128, ["auto", "auto:pdl=0"], 128),
+        ("tile_p_512", [512, 512], 1, ["tile2d:p=3", "tile2d:p=4", "tile2d:p=5", "tile2d:p=6", "tile2d:p=7", "tile2d:p=8", "tile2d:p=10", "tile2d:p=12"], 840),
+        ("tile_p_768", [768, 2048], 1, ["tile2d:p=3", "tile2d:p=4", "tile2d:p=5", "tile2d:p=6", "tile2d:p=8"], 240),
+        ("tile_p_256", [256, 1024], 1, ["tile2d:p=3", "tile2d:p=5", "tile2d:p=7", "tile2d:p=10"], 840),
+        ("tile_p_2048", [2048, 2048], 1, ["tile2d:p=3", "tile2d:p=4", "tile2d:p=5", "ring2d"], 240),
         ("pdl_2d_16k", [16384, 16384], 1, ["bulk2d", "bulk2d:chain=0", "bulk2d:pdl=0"], 20),
         ("2d_gridtile", [256, 256], 128, ["tile2d:nt=256", "tile2d:nt=512", "tile2d:nt=640", "tile2d:nt=768", "tile2d:nt=1024"], 128),
     ]
