@@ -58,6 +58,9 @@ def main():
         ("tile_p_768", [768, 2048], 1, ["tile2d:p=3", "tile2d:p=4", "tile2d:p=5", "tile2d:p=6", "tile2d:p=8"], 240),
         ("tile_p_256", [256, 1024], 1, ["tile2d:p=3", "tile2d:p=5", "tile2d:p=7", "tile2d:p=10"], 840),
         ("tile_p_2048", [2048, 2048], 1, ["tile2d:p=3", "tile2d:p=4", "tile2d:p=5", "ring2d"], 240),
+        ("tile_nt_512", [512, 512], 1, ["tile2d:nt=512", "tile2d:nt=256", "tile2d:nt=256:p=5"], 840),
+        ("tile_nt_768", [768, 2048], 1, ["tile2d:nt=512", "tile2d:nt=256"], 240),
+        ("tile_nt_256", [256, 1024], 1, ["tile2d:nt=512", "tile2d:nt=256"], 840),
         ("pdl_2d_16k", [16384, 16384], 1, ["bulk2d", "bulk2d:chain=0", "bulk2d:pdl=0"], 20),
         ("2d_gridtile", [256, 256], 128, ["tile2d:nt=256", "tile2d:nt=512", "tile2d:nt=640", "tile2d:nt=768", "tile2d:nt=1024"], 128),
     ]
