@@ -141,12 +141,13 @@ def test_serial_reference_mode_reproduces_the_restated_loop(api, oracle, shape, 
     assert thermo.completion_check_results.is_complete  # global cutoff: the first complete fixture ends the run
 
 
-def test_checkerboard_mode_samples_at_the_scheduled_counts(api, tmp_path):
+@pytest.mark.parametrize("shape", [(64, 48), (512, 96)])  # one CTA per lattice; tiles with halos (two copies of the planes)
+def test_checkerboard_mode_samples_at_the_scheduled_counts(api, tmp_path, shape):
     """Checkerboard update order: the fixtures' samples equal what the C-ABI lattice
     gives when driven to the same pass counts with the same Philox key."""
     import casmcode_monte_b200 as cm
 
-    shape, T, mu = (64, 48), 2500.0, 0.01
+    T, mu = 2500.0, 0.01
     n = shape[0] * shape[1]
     occ = np.random.default_rng(8).choice(np.array([-1, 1], dtype=np.int32), size=n)
     mc = make_calculator(api)
