@@ -1157,15 +1157,23 @@ static TilePlan plan_tiles(const cmg_context *c, long long passes_wanted) {
 struct RingPlan {
   bool ok = false;
   int n_tiles = 0, w_max = 0;
+  int nt = 512;  // threads per CTA: 512, or 128 for the short columns of n0 = 256 / 512
   size_t smem = 0;
 };
 static RingPlan plan_ring(const cmg_context *c) {
   RingPlan r;
   // (a slab runs resident only as part of a ring of slabs: cmg_slab_run_passes checks the peers)
-  if (c->dim != 2 || !c->coop_launch || c->shape[0] % 1024 != 0) return r;
+  // n0 a multiple of 1024 (column groups of one to eight warps, 512 threads per CTA), or
+  // n0 = 256 / 512 outside slabs (column groups of 8 / 16 threads, 128 threads per CTA: with
+  // columns this short a 512-thread CTA would hold more groups than a mid-size lattice has
+  // columns to give them)
+  if (c->dim != 2 || !c->coop_launch) return r;
+  const bool small = !c->slab && (c->shape[0] == 256 || c->shape[0] == 512);
+  if (c->shape[0] % 1024 != 0 && !small) return r;
   const long long h = c->shape[0] / 2, n1 = c->shape[1], V = h / 16;
-  if (V > 256 || 512 % V != 0) return r;  // at least two column groups per CTA
-  const long long Q = 512 / V;
+  r.nt = small ? 128 : 512;
+  if (V > 256 || r.nt % V != 0) return r;  // at least two column groups per CTA
+  const long long Q = r.nt / V;
   // A context whose completion checks run on the second stream NEXT TO the sweep (a check of
   // marked samples that was not prefetched) leaves one SM free when the widest tile stays the same (4096 / 147 and
   // 4096 / 148 both round up to 28 columns): the statistics kernels of cmg_series_check run there
@@ -1208,6 +1216,10 @@ static int pick_variant(cmg_context *c, long long n_passes) {
     // measured on one 4096^2 lattice; the trajectories are identical either way)
     if (n_passes >= 4 && plan_tiles(c, c->tile_passes).n_tiles > 1 && plan_ring(c).ok)
       return V_RING2D;
+    // ONE lattice that fits a CTA but keeps it busy for more than the ~1.4 us an edge takes
+    // from tile to tile through L2 (three or more vectors per thread and half-sweep) is spread
+    // over several SMs too: 256^2 2.1e10 against 9.8e9 attempts/s in one CTA
+    if (n_passes >= 4 && c->n_chains == 1 && c->n_sites >= 49152 && plan_ring(c).ok) return V_RING2D;
     return V_TILE2D;
   }
   if (c->dim == 2 && c->shape[0] % 32 == 0) return V_BULK2D;
@@ -1661,7 +1673,8 @@ static int launch_ring_passes(cmg_context *c, const RingPlan &rp, int n_passes,
   A.v_magic = (uint32_t)((0x100000000ull + V - 1) / V);
   A.mailbox = c->d_ring_mailbox;
   A.error = c->d_error;
-  const void *ring_kernel = c->philox_rounds == 7 ? (const void *)k_ring2d<512, 7> : (const void *)k_ring2d<512, 10>;
+  const void *ring_kernel = rp.nt == 128 ? (c->philox_rounds == 7 ? (const void *)k_ring2d<128, 7> : (const void *)k_ring2d<128, 10>)
+                                         : (c->philox_rounds == 7 ? (const void *)k_ring2d<512, 7> : (const void *)k_ring2d<512, 10>);
   cudaError_t e = cudaFuncSetAttribute(ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rp.smem);
   if (e != cudaSuccess) return fail(c, CMG_ECUDA, cudaGetErrorString(e));
   dim3 grid(rp.n_tiles, c->n_chains);
@@ -1673,7 +1686,7 @@ static int launch_ring_passes(cmg_context *c, const RingPlan &rp, int n_passes,
     k_ring_publish<<<dim3((unsigned)nblocks(V, 128), 2), 128, 0, c->stream>>>(A);
     ++c->launches;
   }
-  e = cudaLaunchCooperativeKernel(ring_kernel, grid, dim3(512), args, rp.smem, c->stream);
+  e = cudaLaunchCooperativeKernel(ring_kernel, grid, dim3(rp.nt), args, rp.smem, c->stream);
   if (e != cudaSuccess) return fail(c, CMG_ECUDA, cudaGetErrorString(e));
   ++c->launches;
   if (peers) c->ring_s0 += 2ull * (unsigned long long)n_passes;
@@ -1876,7 +1889,7 @@ int cmg_run_passes(cmg_context *c, int64_t n_passes, int mode, int64_t sample_pe
     return fail(c, CMG_EINVAL, "tile2d does not fit this lattice (need dim 2, n0 % 64 == 0, short columns)");
   if (variant == V_RING2D && !plan_ring(c).ok)
     return fail(c, CMG_EINVAL,
-                "ring2d does not fit this lattice (need dim 2, n0 in {1024..8192} a power of two, "
+                "ring2d does not fit this lattice (need dim 2, n0 = 256, 512 or a power of two in {1024..8192}, "
                 "the lattice within the GPU's shared memory, cooperative launch)");
   c->variant_name = variant_str(variant);
   long long n_new = 0;

@@ -1468,11 +1468,14 @@ __global__ void __launch_bounds__(NT, 1) k_ring2d(RingArgs A) {
   // arrivals of those neighbours; a warp is never more than one half-sweep ahead of a
   // neighbour, so two barriers per warp suffice, and the waits are bounded like the others.
   __shared__ __align__(8) unsigned long long s_nbar[2][NT / 32];
-  const int wpg = V >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wu = warp % wpg;
+  // (column groups narrower than a warp, V < 32 -- the 128-thread form for n0 = 256 / 512: a
+  // warp holds several whole groups and borders the warps before and after it only)
+  const int wpg = V >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wu = wpg ? warp % wpg : 0;
   int nbr[4], n_nbr = 0;
   {
-    const int cand[4] = {q > 0 ? warp - wpg : -1, q < Q - 1 ? warp + wpg : -1,
-                         q * wpg + (wu + 1) % wpg, q * wpg + (wu + wpg - 1) % wpg};
+    const int cand[4] = {wpg ? (q > 0 ? warp - wpg : -1) : (warp > 0 ? warp - 1 : -1),
+                         wpg ? (q < Q - 1 ? warp + wpg : -1) : (warp < NT / 32 - 1 ? warp + 1 : -1),
+                         wpg ? q * wpg + (wu + 1) % wpg : -1, wpg ? q * wpg + (wu + wpg - 1) % wpg : -1};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       bool take = cand[i] >= 0 && cand[i] != warp;

@@ -433,7 +433,8 @@ const char *cmg_kernel_variant(const cmg_context *ctx);
 /* force a variant, for tests and measurements: "auto", "generic", "bulk2d"
  * (HBM-streaming strips), "bulk3d", "tile2d" (shared-memory tiles with
  * temporal blocking), "ring2d" (the whole lattice resident in the shared memory
- * of the GPU, one cooperative launch of many passes); options are appended as
+ * of the GPU, one cooperative launch of many passes; n0 = 256, 512 or a multiple
+ * of 1024 up to 8192); options are appended as
  * ":js=56" (strip length), ":p=3" / ":nt=512" (tile passes / threads) and
  * ":rp=128" (passes per ring launch), ":ns=74" (balanced strips per lattice /
  * layer), ":pdl=0" (bulk2d / bulk3d: plain launches instead of programmatic

@@ -901,8 +901,10 @@ def test_tile2d_neighbour_warp_waits_match_oracle(cm, oracle, shape, variant):
 # The resident kernel over many half-sweeps per launch: warps wait for their neighbour warps
 # on per-warp mbarriers (two per warp, alternating with the colour), one / two / four / eight
 # warps per column group, against the oracle.
+# (n0 = 256 / 512: the 128-thread form, column groups of 8 / 16 threads, several groups per warp)
 @pytest.mark.parametrize("shape,variant", [([1024, 256], "ring2d"), ([2048, 160], "ring2d"), ([4096, 300], "ring2d:rp=17"),
-                                           ([8192, 64], "ring2d")])
+                                           ([8192, 64], "ring2d"), ([512, 512], "ring2d"), ([256, 1024], "ring2d"), ([512, 70], "ring2d:rp=9"),
+                                           ([256, 100], "ring2d"), ([512, 2048], "ring2d")])
 def test_ring2d_neighbour_warp_waits_over_many_passes(cm, oracle, shape, variant):
     n = nsites(shape)
     occ = rand_occ(n, 77)

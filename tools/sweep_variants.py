@@ -61,6 +61,10 @@ def main():
         ("tile_nt_512", [512, 512], 1, ["tile2d:nt=512", "tile2d:nt=256", "tile2d:nt=256:p=5"], 840),
         ("tile_nt_768", [768, 2048], 1, ["tile2d:nt=512", "tile2d:nt=256"], 240),
         ("tile_nt_256", [256, 1024], 1, ["tile2d:nt=512", "tile2d:nt=256"], 840),
+        ("mid_ring", [512, 512], 1, ["auto", "ring2d", "tile2d"], 840),
+        ("mid_ring_256", [256, 1024], 1, ["auto", "tile2d"], 840),
+        ("mid_ring_512x2048", [512, 2048], 1, ["auto", "tile2d"], 400),
+        ("mid_ring_256sq", [256, 256], 1, ["auto", "ring2d"], 840),
         ("pdl_2d_16k", [16384, 16384], 1, ["bulk2d", "bulk2d:chain=0", "bulk2d:pdl=0"], 20),
         ("2d_gridtile", [256, 256], 128, ["tile2d:nt=256", "tile2d:nt=512", "tile2d:nt=640", "tile2d:nt=768", "tile2d:nt=1024"], 128),
     ]
